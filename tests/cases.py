@@ -1,0 +1,94 @@
+"""Small model / parameter cases shared by the golden generator and the tests.
+
+Models are plain data (see oracle/functionals.py): ``{'d', 'kernels'}`` with
+``kernels[k][i]`` a list of bases ``{'type', 'fixed'}``.  Parameter values
+follow the configurations of BASELINE.md / SURVEY.md section 8d, at reduced T_f so
+that the literal O(N^2) reference finishes in well under a second.
+"""
+import numpy as np
+
+
+def exp_kernel():
+    return [{'type': 'exp'}]
+
+
+def gauss_kernel():
+    return [{'type': 'gauss'}]
+
+
+def sbf_gauss_kernel(n_basis, beta=0.5, spacing=1.0):
+    """SBF kernel of fit_sbgauss1d10r.py:60-63: beta and delta fixed, omega free."""
+    return [{'type': 'gauss', 'fixed': {1: beta, 2: spacing * r}}
+            for r in range(n_basis)]
+
+
+def square(d, make):
+    return {'d': d, 'kernels': [[make() for _ in range(d)] for _ in range(d)]}
+
+
+# name -> (model, mu, kernel_param[k][i], T_f)
+CASES = {
+    # C1: examples/fit_exp1d.ipynb cell 4
+    'exp1d': (square(1, exp_kernel), [1.5], [[[0.3, 0.8]]], 150.),
+    # C2: papers/grad_based_estim/experiments/fit_exp2d.py:34-51
+    'exp2d': (square(2, exp_kernel), [1.5, 1.],
+              [[[.2, 1.], [.6, 1.5]], [[.7, 2.], [.1, 1.3]]], 60.),
+    # C3: papers/grad_based_estim/experiments/fit_gauss1d.py:31-34
+    'gauss1d': (square(1, gauss_kernel), [1.5], [[[.5, .5, 3.]]], 100.),
+    # all three Gaussian variables free in 2-D: exercises the cross beta/delta
+    # branches (known-wrong in the reference)
+    'gauss2d': (square(2, gauss_kernel), [.8, .6],
+                [[[.2, .5, 1.], [.3, .7, 2.]], [[.25, .4, 1.5], [.1, .6, .5]]], 80.),
+    # C4-like: sum of Gaussians with (beta, delta) fixed
+    'sbf1d3': (square(1, lambda: sbf_gauss_kernel(3)), [.5],
+               [[[.2, .3, .2]]], 150.),
+    'sbf1d10': (square(1, lambda: sbf_gauss_kernel(10)), [.2],
+                [[[.05, .1, .05, .1, .05, .1, .05, .1, .05, .1]]], 300.),
+    # C5-like: multi-dimensional SBF
+    'sbf2d3': (square(2, lambda: sbf_gauss_kernel(3)), [.5, .4],
+               [[[.2, .1, .1], [.1, .2, .05]], [[.05, .1, .2], [.2, .1, .1]]], 100.),
+    # two free exponentials per kernel (multi-basis with free beta)
+    'exp1d2b': (square(1, lambda: [{'type': 'exp'}, {'type': 'exp'}]), [1.],
+                [[[.2, .8, .15, 3.]]], 120.),
+    # mixed fixed pattern: gaussian with only delta fixed, two bases
+    'gauss1d2b': (square(1, lambda: [{'type': 'gauss', 'fixed': {2: 1.0}},
+                                     {'type': 'gauss', 'fixed': {1: 0.4}}]), [.7],
+                  [[[.2, .5, .25, 2.5]]], 120.),
+}
+
+
+def case_x(name):
+    """Evaluation points: truth * (1 + 0.1 U(-1, 1)), default_rng(12)
+    (SURVEY section 8d)."""
+    model, mu, kp, T_f = CASES[name]
+    rng = np.random.default_rng(12)
+    xs = []
+    for k in range(model['d']):
+        x = np.concatenate([[mu[k]]] + [np.asarray(kp[k][i], float)
+                                        for i in range(model['d'])])
+        xs.append(x * (1 + 0.1 * rng.uniform(-1, 1, size=len(x))))
+    return xs
+
+
+def flatten_sums(sum_f, sum_diff_f, prefix):
+    """{'phi_0': ...} -> flat dict of arrays for npz storage."""
+    out = {}
+    for name, val in sum_f.items():
+        out['%s/f/%s' % (prefix, name)] = np.float64(val)
+        dv = sum_diff_f[name]
+        if isinstance(dv, list):
+            out['%s/df1/%s' % (prefix, name)] = np.asarray(dv[1], dtype=float)
+            out['%s/df2/%s' % (prefix, name)] = np.asarray(dv[2], dtype=float)
+        else:
+            out['%s/df/%s' % (prefix, name)] = np.asarray(dv, dtype=float)
+    return out
+
+
+def term_names(d):
+    names = []
+    for i in range(d):
+        names += ['phi_%d' % i, 'upsilonzero_%d' % i, 'psi_%d' % i]
+    for i in range(d):
+        for j in range(d):
+            names.append('upsilon_%d_%d' % (i, j))
+    return names
