@@ -1,0 +1,13 @@
+"""aslsd_b200: B200-native engine for the LSE hot path of saadlabyad/aslsd.
+
+Host-side mirrors of the reference's interfaces for this path (same names,
+argument meaning and error behaviour) over a C-ABI CUDA library
+(include/aslsd_b200.h).  There is no CPU fallback.
+"""
+from aslsd_b200.engine import Engine, EngineError  # noqa: F401
+from aslsd_b200.events import ProcessPath, get_kappa_varpi, get_lag_sizes  # noqa: F401
+from aslsd_b200.model import (MHP, KernelModel, ExponentialKernel,  # noqa: F401
+                              GaussianKernel, describe_model)
+
+__all__ = ['Engine', 'EngineError', 'ProcessPath', 'get_kappa_varpi', 'get_lag_sizes',
+           'MHP', 'KernelModel', 'ExponentialKernel', 'GaussianKernel', 'describe_model']

@@ -1,0 +1,163 @@
+// Shared host-side state of the aslsd_b200 engine (one context per GPU).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/aslsd_b200.h"
+
+#define ASLSD_MAX_COMP 8       // raw accumulators per work item
+#define ASLSD_BUCKET_SHIFT 2   // one time bucket per 2^2 events (lookup table)
+
+struct BasisHost {
+  int type;
+  int free_mask;
+  double fixed[3];
+  int n_vars() const { return type == ASLSD_BASIS_EXPONENTIAL ? 2 : 3; }
+  int n_param() const {
+    int n = 0;
+    for (int v = 0; v < n_vars(); ++v) n += (free_mask >> v) & 1;
+    return n;
+  }
+};
+
+struct KernelHost {
+  std::vector<BasisHost> bases;
+  int n_param() const {
+    int n = 0;
+    for (auto& b : bases) n += b.n_param();
+    return n;
+  }
+};
+
+// Device-side description of one work item of the pair / single kernels.
+// An item is one basis pair (upsilon), one basis (phi, psi) of one named term.
+struct ItemDev {
+  int32_t family;    // ITEM_* below
+  int32_t mask;      // which raw components to accumulate
+  int32_t tgt_dim, src_dim;
+  int32_t same;      // target and source are the same event type (n < m by index)
+  int32_t n_chunks;  // work units of this item
+  int64_t m_lo, m_hi;    // target block
+  int64_t tpw;           // targets per work unit
+  int64_t wu_first;      // first work unit (prefix over items)
+  double s_lo, s_hi;     // lag window
+  double t_int;          // targets with T - t_m >= t_int are interior
+  double b1, d1, b2, d2; // beta / delta of the two bases (cross components)
+  double bo, dlo;        // beta / delta of the own basis (sim-own components)
+};
+
+enum {
+  ITEM_UPS_EXP = 0,
+  ITEM_UPS_GAUSS = 1,
+  ITEM_PHI_EXP = 2,
+  ITEM_PHI_GAUSS = 3,
+  ITEM_PSI_EXP = 4,
+  ITEM_PSI_GAUSS = 5,
+  ITEM_UPS0_EXP = 6,   // upsilon at lag zero: one evaluation per target
+  ITEM_UPS0_GAUSS = 7
+};
+
+// Raw component slots.
+//   upsilon exp  : 0 G, 1 B1, 2 B2, 5 SW, 6 SB
+//   upsilon gauss: 0 G, 1 B1, 2 D1, 3 B2, 4 D2, 5 SW, 6 SB, 7 SD
+//   phi exp      : 0 E0, 1 EB            phi gauss: 0 P, 1 PB, 2 PD
+//   psi exp      : 0 I, 1 IB             psi gauss: 0 I, 1 IB, 2 ID
+enum { C_G = 0, C_B1 = 1, C_D1 = 2, C_B2 = 3, C_D2 = 4, C_SW = 5, C_SB = 6, C_SD = 7 };
+// exponential upsilon reuses slots: B1 -> 1, B2 -> 3
+#define MASK(c) (1 << (c))
+
+struct TermPlan {
+  int kind;          // 0 psi, 1 upsilonzero, 2 phi, 3 upsilon
+  int i, j;          // dimensions (j == i for single-index terms and upsilon_i_i)
+  int n1, n2;        // derivative counts (packed output)
+  int64_t out_off;   // offset in the packed output
+  int item_first, item_count;   // items computing this term's cross components
+};
+
+struct aslsd_ctx {
+  int device = 0;
+  cudaStream_t own_stream = nullptr;
+  cudaStream_t stream = nullptr;
+  std::string err;
+
+  // events
+  int d = 0;
+  double T_f = 0.;
+  std::vector<int64_t> n_events;
+  std::vector<int64_t> off;        // offsets (in doubles) into d_times, 16 B aligned
+  double* d_times = nullptr;       // all event types, padded
+  int64_t times_len = 0;
+  // per-dimension time-bucket lookup tables (lower_bound accelerators)
+  std::vector<int64_t> tab_off;    // offsets into d_tab
+  std::vector<int64_t> tab_len;    // number of buckets per dim
+  std::vector<double> tab_t0, tab_w;
+  int32_t* d_tab = nullptr;
+  // device copies of the per-dimension metadata
+  void* d_dims = nullptr;          // DimDev[d]
+
+  // model
+  bool has_model = false;
+  std::vector<KernelHost> kernels;   // [k*d + i]
+
+  // scratch
+  void* d_items = nullptr;  size_t items_cap = 0;
+  double* d_partials = nullptr; size_t partials_cap = 0;
+  double* d_raw = nullptr; size_t raw_cap = 0;
+  unsigned long long* d_counts = nullptr; size_t counts_cap = 0;
+  void* h_pinned = nullptr; size_t pinned_cap = 0;
+  void* d_sample = nullptr; size_t sample_cap = 0;
+
+  // timing
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  double last_ms = 0.;
+  bool timing_pending = false;
+  int64_t last_launches = 0;
+};
+
+struct DimDev {
+  const double* t;     // event times of this type
+  const int32_t* tab;  // bucket table: tab[g] = lower_bound(t, t0 + g * w), g = 0..n_buckets
+  int64_t n;
+  int64_t n_buckets;
+  double t0, w, inv_w;
+};
+
+int aslsd_fail(aslsd_ctx* ctx, int code, const std::string& msg);
+#define CUDA_TRY(ctx, expr)                                                        \
+  do {                                                                             \
+    cudaError_t _e = (expr);                                                       \
+    if (_e != cudaSuccess)                                                         \
+      return aslsd_fail(ctx, ASLSD_ERR_CUDA,                                       \
+                        std::string(#expr) + ": " + cudaGetErrorString(_e));       \
+  } while (0)
+
+int ensure_device_buffer(aslsd_ctx* ctx, void** ptr, size_t* cap, size_t bytes);
+int ensure_pinned_buffer(aslsd_ctx* ctx, size_t bytes);
+
+// lower_bound through the bucket table: first index with t[idx] >= x
+__device__ __forceinline__ int64_t dim_lower_bound(const DimDev& D, double x) {
+  if (D.n == 0) return 0;
+  double gf = (x - D.t0) * D.inv_w;
+  int64_t g = gf <= 0. ? 0 : (gf >= (double)(D.n_buckets - 1) ? D.n_buckets - 1 : (int64_t)gf);
+  // make the bucket choice consistent with the boundaries used at build time
+  while (g > 0 && x < D.t0 + (double)g * D.w) --g;
+  while (g < D.n_buckets - 1 && x >= D.t0 + (double)(g + 1) * D.w) ++g;
+  int64_t lo = D.tab[g], hi = D.tab[g + 1];
+  if (g == 0 && x < D.t0) { lo = 0; }
+  while (lo < hi) {
+    int64_t mid = (lo + hi) >> 1;
+    if (D.t[mid] < x) lo = mid + 1; else hi = mid;
+  }
+  return lo;
+}
+
+// first index with t[idx] > x
+__device__ __forceinline__ int64_t dim_upper_bound(const DimDev& D, double x) {
+  int64_t p = dim_lower_bound(D, x);
+  while (p < D.n && D.t[p] == x) ++p;
+  return p;
+}

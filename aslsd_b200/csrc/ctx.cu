@@ -1,0 +1,243 @@
+// Context lifetime, event upload and model description.
+//   aslsd_set_events  <- stats/events/process_path.py:63-106 (data members)
+//   aslsd_set_model   <- models/hawkes/linear/mhp.py:1525-1538 (init_estimator)
+#include "common.cuh"
+
+#include <algorithm>
+#include <cstring>
+
+int aslsd_fail(aslsd_ctx* ctx, int code, const std::string& msg) {
+  if (ctx) ctx->err = msg;
+  return code;
+}
+
+int ensure_device_buffer(aslsd_ctx* ctx, void** ptr, size_t* cap, size_t bytes) {
+  if (bytes <= *cap && *ptr) return ASLSD_OK;
+  if (*ptr) CUDA_TRY(ctx, cudaFree(*ptr));
+  *ptr = nullptr;
+  *cap = 0;
+  size_t want = std::max<size_t>(bytes + bytes / 4, 256);
+  CUDA_TRY(ctx, cudaMalloc(ptr, want));
+  *cap = want;
+  return ASLSD_OK;
+}
+
+int ensure_pinned_buffer(aslsd_ctx* ctx, size_t bytes) {
+  if (bytes <= ctx->pinned_cap && ctx->h_pinned) return ASLSD_OK;
+  if (ctx->h_pinned) CUDA_TRY(ctx, cudaFreeHost(ctx->h_pinned));
+  ctx->h_pinned = nullptr;
+  ctx->pinned_cap = 0;
+  size_t want = std::max<size_t>(bytes + bytes / 4, 4096);
+  CUDA_TRY(ctx, cudaMallocHost(&ctx->h_pinned, want));
+  ctx->pinned_cap = want;
+  return ASLSD_OK;
+}
+
+extern "C" int aslsd_create(aslsd_ctx** out, int device) {
+  if (!out) return ASLSD_ERR_ARG;
+  *out = nullptr;
+  int n_dev = 0;
+  cudaError_t e = cudaGetDeviceCount(&n_dev);
+  if (e != cudaSuccess || n_dev == 0 || device < 0 || device >= n_dev) return ASLSD_ERR_CUDA;
+  aslsd_ctx* ctx = new aslsd_ctx();
+  ctx->device = device;
+  if (cudaSetDevice(device) != cudaSuccess ||
+      cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaEventCreate(&ctx->ev0) != cudaSuccess || cudaEventCreate(&ctx->ev1) != cudaSuccess) {
+    delete ctx;
+    return ASLSD_ERR_CUDA;
+  }
+  ctx->stream = ctx->own_stream;
+  *out = ctx;
+  return ASLSD_OK;
+}
+
+extern "C" int aslsd_destroy(aslsd_ctx* ctx) {
+  if (!ctx) return ASLSD_OK;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  cudaFree(ctx->d_times);
+  cudaFree(ctx->d_tab);
+  cudaFree(ctx->d_dims);
+  cudaFree(ctx->d_items);
+  cudaFree(ctx->d_partials);
+  cudaFree(ctx->d_raw);
+  cudaFree(ctx->d_counts);
+  cudaFree(ctx->d_sample);
+  if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
+  cudaEventDestroy(ctx->ev0);
+  cudaEventDestroy(ctx->ev1);
+  cudaStreamDestroy(ctx->own_stream);
+  delete ctx;
+  return ASLSD_OK;
+}
+
+extern "C" const char* aslsd_last_error(const aslsd_ctx* ctx) {
+  return ctx ? ctx->err.c_str() : "no context (no CUDA device?)";
+}
+
+extern "C" int aslsd_set_stream(aslsd_ctx* ctx, void* cuda_stream) {
+  if (!ctx) return ASLSD_ERR_ARG;
+  ctx->stream = cuda_stream ? (cudaStream_t)cuda_stream : ctx->own_stream;
+  return ASLSD_OK;
+}
+
+extern "C" int aslsd_last_timing(const aslsd_ctx* ctx_, double* kernel_ms, int64_t* n_launches) {
+  aslsd_ctx* ctx = const_cast<aslsd_ctx*>(ctx_);
+  if (!ctx) return ASLSD_ERR_ARG;
+  if (ctx->timing_pending) {
+    float ms = 0.f;
+    if (cudaEventSynchronize(ctx->ev1) == cudaSuccess &&
+        cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1) == cudaSuccess)
+      ctx->last_ms = ms;
+    ctx->timing_pending = false;
+  }
+  if (kernel_ms) *kernel_ms = ctx->last_ms;
+  if (n_launches) *n_launches = ctx->last_launches;
+  return ASLSD_OK;
+}
+
+// tab[g] = lower_bound(t, t0 + g*w) for g = 0..n_buckets (tab[n_buckets] = n)
+__global__ void build_bucket_table_kernel(const double* __restrict__ t, int64_t n, int32_t* tab,
+                                          int64_t n_buckets, double t0, double w) {
+  int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (g > n_buckets) return;
+  if (g == n_buckets) { tab[g] = (int32_t)n; return; }
+  double x = t0 + (double)g * w;
+  int64_t lo = 0, hi = n;
+  while (lo < hi) {
+    int64_t mid = (lo + hi) >> 1;
+    if (t[mid] < x) lo = mid + 1; else hi = mid;
+  }
+  tab[g] = (int32_t)lo;
+}
+
+extern "C" int aslsd_set_events(aslsd_ctx* ctx, int d, const int64_t* n_events,
+                                const double* const* times, double T_f) {
+  if (!ctx || d <= 0 || !n_events || !times) return aslsd_fail(ctx, ASLSD_ERR_ARG, "set_events: bad arguments");
+  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  for (int i = 0; i < d; ++i) {
+    if (n_events[i] < 0 || n_events[i] >= (int64_t)2147483000)
+      return aslsd_fail(ctx, ASLSD_ERR_ARG, "set_events: event count out of range");
+    for (int64_t m = 1; m < n_events[i]; ++m)
+      if (!(times[i][m] >= times[i][m - 1]))
+        return aslsd_fail(ctx, ASLSD_ERR_ARG, "set_events: times must be sorted");
+  }
+  ctx->d = d;
+  ctx->T_f = T_f;
+  ctx->n_events.assign(n_events, n_events + d);
+  ctx->off.assign(d + 1, 0);
+  ctx->tab_off.assign(d + 1, 0);
+  ctx->tab_len.assign(d, 1);
+  ctx->tab_t0.assign(d, 0.);
+  ctx->tab_w.assign(d, 1.);
+  for (int i = 0; i < d; ++i) {
+    // every type starts on a 16 B boundary and is followed by >= 2 pad doubles so
+    // that aligned bulk copies may over-read
+    int64_t padded = ((n_events[i] + 1) / 2) * 2 + 2;
+    ctx->off[i + 1] = ctx->off[i] + padded;
+    int64_t nb = std::max<int64_t>(1, n_events[i] >> ASLSD_BUCKET_SHIFT);
+    ctx->tab_len[i] = nb;
+    ctx->tab_off[i + 1] = ctx->tab_off[i] + nb + 1;
+    if (n_events[i] > 0) {
+      double t0 = times[i][0], t1 = times[i][n_events[i] - 1];
+      double w = (t1 - t0) / (double)nb;
+      w = w * (1. + 1e-9) + 1e-300;
+      if (!(w > 0.)) w = 1.;
+      ctx->tab_t0[i] = t0;
+      ctx->tab_w[i] = w;
+    }
+  }
+  cudaFree(ctx->d_times); ctx->d_times = nullptr;
+  cudaFree(ctx->d_tab); ctx->d_tab = nullptr;
+  cudaFree(ctx->d_dims); ctx->d_dims = nullptr;
+  ctx->times_len = ctx->off[d];
+  CUDA_TRY(ctx, cudaMalloc(&ctx->d_times, sizeof(double) * ctx->times_len));
+  CUDA_TRY(ctx, cudaMemsetAsync(ctx->d_times, 0x7f, sizeof(double) * ctx->times_len, ctx->stream));
+  CUDA_TRY(ctx, cudaMalloc(&ctx->d_tab, sizeof(int32_t) * ctx->tab_off[d]));
+  CUDA_TRY(ctx, cudaMalloc(&ctx->d_dims, sizeof(DimDev) * d));
+  std::vector<DimDev> dims(d);
+  for (int i = 0; i < d; ++i) {
+    if (n_events[i] > 0)
+      CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_times + ctx->off[i], times[i], sizeof(double) * n_events[i],
+                                    cudaMemcpyHostToDevice, ctx->stream));
+    dims[i].t = ctx->d_times + ctx->off[i];
+    dims[i].tab = ctx->d_tab + ctx->tab_off[i];
+    dims[i].n = n_events[i];
+    dims[i].n_buckets = ctx->tab_len[i];
+    dims[i].t0 = ctx->tab_t0[i];
+    dims[i].w = ctx->tab_w[i];
+    dims[i].inv_w = 1. / ctx->tab_w[i];
+  }
+  CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_dims, dims.data(), sizeof(DimDev) * d, cudaMemcpyHostToDevice,
+                                ctx->stream));
+  for (int i = 0; i < d; ++i) {
+    int64_t nb = ctx->tab_len[i];
+    int threads = 256;
+    int blocks = (int)((nb + 1 + threads - 1) / threads);
+    build_bucket_table_kernel<<<blocks, threads, 0, ctx->stream>>>(
+        dims[i].t, dims[i].n, ctx->d_tab + ctx->tab_off[i], nb, dims[i].t0, dims[i].w);
+  }
+  CUDA_TRY(ctx, cudaGetLastError());
+  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  return ASLSD_OK;
+}
+
+extern "C" int aslsd_set_model(aslsd_ctx* ctx, int d, const int32_t* n_basis, const aslsd_basis* bases) {
+  if (!ctx || d <= 0 || !n_basis || !bases) return aslsd_fail(ctx, ASLSD_ERR_ARG, "set_model: bad arguments");
+  if (ctx->d != 0 && ctx->d != d)
+    return aslsd_fail(ctx, ASLSD_ERR_ARG, "set_model: dimension differs from the events'");
+  std::vector<KernelHost> ks(d * d);
+  const aslsd_basis* b = bases;
+  for (int k = 0; k < d; ++k)
+    for (int i = 0; i < d; ++i) {
+      KernelHost& K = ks[k * d + i];
+      int nb = n_basis[k * d + i];
+      if (nb <= 0) return aslsd_fail(ctx, ASLSD_ERR_ARG, "set_model: kernel without bases");
+      for (int r = 0; r < nb; ++r, ++b) {
+        if (b->type != ASLSD_BASIS_EXPONENTIAL && b->type != ASLSD_BASIS_GAUSSIAN)
+          return aslsd_fail(ctx, ASLSD_ERR_UNSUPPORTED,
+                            "set_model: only ExponentialKernel and GaussianKernel bases are supported");
+        BasisHost h;
+        h.type = b->type;
+        int nv = (b->type == ASLSD_BASIS_EXPONENTIAL) ? 2 : 3;
+        h.free_mask = b->free_mask & ((1 << nv) - 1);
+        for (int v = 0; v < 3; ++v) h.fixed[v] = b->fixed[v];
+        K.bases.push_back(h);
+      }
+    }
+  // Upsilon closures of the reference are all bound to the kernel objects of
+  // the last loop iteration (mhp.py:527-536): K[d-1][d-1] provides the basis
+  // structure of every upsilon term, so all kernels must share it.
+  const KernelHost& KU = ks[d * d - 1];
+  for (auto& K : ks) {
+    if (K.bases.size() != KU.bases.size())
+      return aslsd_fail(ctx, ASLSD_ERR_UNSUPPORTED,
+                        "set_model: all kernels must have the same basis structure");
+    for (size_t r = 0; r < K.bases.size(); ++r) {
+      if (K.bases[r].type != KU.bases[r].type || K.bases[r].free_mask != KU.bases[r].free_mask)
+        return aslsd_fail(ctx, ASLSD_ERR_UNSUPPORTED,
+                          "set_model: all kernels must have the same basis structure");
+      for (size_t q = 0; q < KU.bases.size(); ++q)
+        if (K.bases[r].type != KU.bases[q].type)
+          return aslsd_fail(ctx, ASLSD_ERR_UNSUPPORTED,
+                            "set_model: mixed exponential x gaussian interactions are not supported");
+    }
+  }
+  ctx->kernels.swap(ks);
+  ctx->has_model = true;
+  if (ctx->d == 0) ctx->d = d;
+  return ASLSD_OK;
+}
+
+extern "C" int aslsd_model_n_param(const aslsd_ctx* ctx, int k, int32_t* n_param_k, int32_t* n_param) {
+  if (!ctx || !ctx->has_model || k < 0 || k >= ctx->d) return ASLSD_ERR_ARG;
+  int tot = 1;
+  for (int i = 0; i < ctx->d; ++i) {
+    int n = ctx->kernels[k * ctx->d + i].n_param();
+    if (n_param) n_param[i] = n;
+    tot += n;
+  }
+  if (n_param_k) *n_param_k = tot;
+  return ASLSD_OK;
+}

@@ -1,0 +1,200 @@
+"""Engine: one device context of the B200 library, behind plain numpy arguments.
+
+This is the thin layer between the reference-facing host classes
+(``aslsd_b200.events``, ``aslsd_b200.estimators``) and the C ABI.  One Engine
+may be shared by the d estimators of a fit (same ProcessPath).
+"""
+import ctypes
+
+import numpy as np
+
+from aslsd_b200 import capi
+from aslsd_b200.model import describe_model
+
+
+class EngineError(RuntimeError):
+    pass
+
+
+def term_layout(desc, k):
+    """Packed output layout of aslsd_exact_sums: list of
+    (log_name, offset, n1, n2, n_func) in the order the reference evaluates the
+    terms (mhp_exact_estimator.py:722-756); n_func as in make_param_indexing
+    (:141-170)."""
+    d = desc.d
+    npar = desc.matrix_n_param[k]
+    out, pos = [], 0
+    for i in range(d):
+        for name, n1, n2, n_func in (('psi_%d' % i, npar[i], 1, 2),
+                                     ('upsilonzero_%d' % i, npar[i], 0, 1),
+                                     ('phi_%d' % i, npar[i], 0, 1),
+                                     ('upsilon_%d_%d' % (i, i), npar[i], 0, 1)):
+            out.append((name, pos, n1, n2, n_func))
+            pos += 1 + n1 + n2
+    for i in range(d):
+        for j in range(d):
+            if i != j:
+                out.append(('upsilon_%d_%d' % (i, j), pos, npar[i], npar[j], 2))
+                pos += 1 + npar[i] + npar[j]
+    return out, pos
+
+
+def unpack_terms(desc, k, packed):
+    """Packed vector -> (sum_f, sum_diff_f) dictionaries with the shapes of
+    make_null_sumarray (mhp_exact_estimator.py:242-255)."""
+    layout, _ = term_layout(desc, k)
+    sum_f, sum_diff_f = {}, {}
+    for name, off, n1, n2, n_func in layout:
+        sum_f[name] = float(packed[off])
+        if n_func == 2:
+            sum_diff_f[name] = [None, packed[off + 1:off + 1 + n1].copy(),
+                                packed[off + 1 + n1:off + 1 + n1 + n2].copy()]
+        else:
+            sum_diff_f[name] = packed[off + 1:off + 1 + n1].copy()
+    return sum_f, sum_diff_f
+
+
+class Engine:
+    def __init__(self, device=0):
+        self._lib = capi.load_library()
+        self._ctx = ctypes.c_void_p()
+        rc = self._lib.aslsd_create(ctypes.byref(self._ctx), int(device))
+        if rc != 0 or not self._ctx:
+            raise EngineError('aslsd_create failed (rc=%d): no usable CUDA device %d; '
+                              'the B200 engine has no CPU fallback' % (rc, device))
+        self.device = int(device)
+        self.desc = None
+        self.d = None
+        self.n_events = None
+        self.T_f = None
+
+    def close(self):
+        if getattr(self, '_ctx', None):
+            self._lib.aslsd_destroy(self._ctx)
+            self._ctx = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc != 0:
+            msg = self._lib.aslsd_last_error(self._ctx)
+            msg = msg.decode() if msg else ''
+            if rc == capi.ERR_UNSUPPORTED:
+                raise NotImplementedError(msg)
+            raise EngineError('aslsd_b200 error %d: %s' % (rc, msg))
+
+    def set_stream(self, cuda_stream):
+        self._check(self._lib.aslsd_set_stream(self._ctx, ctypes.c_void_p(cuda_stream or 0)))
+
+    def last_timing(self):
+        ms = ctypes.c_double()
+        n = ctypes.c_int64()
+        self._check(self._lib.aslsd_last_timing(self._ctx, ctypes.byref(ms), ctypes.byref(n)))
+        return ms.value, n.value
+
+    # ---- events ----------------------------------------------------------------------
+    def set_events(self, list_times, T_f):
+        times = [capi.as_f64(t) for t in list_times]
+        d = len(times)
+        n_events = np.array([len(t) for t in times], dtype=np.int64)
+        ptrs = (capi.c_f64_p * d)(*[capi.ptr_f64(t) for t in times])
+        self._check(self._lib.aslsd_set_events(self._ctx, d, capi.ptr_i64(n_events), ptrs,
+                                               float(T_f)))
+        self.d, self.n_events, self.T_f = d, n_events, float(T_f)
+
+    def index_maps(self, want_kappa=True, want_varpi=True, want_lag_sizes=True):
+        """kappa, varpi, lag_sizes as d x d lists of int64 arrays
+        (time_ordering.py:9-119)."""
+        d = self.d
+        klen = np.zeros(d * d, dtype=np.int64)
+        vlen = np.zeros(d * d, dtype=np.int64)
+        self._check(self._lib.aslsd_index_map_sizes(self._ctx, capi.ptr_i64(klen),
+                                                    capi.ptr_i64(vlen)))
+
+        def alloc(lens, want):
+            if not want:
+                return None, None
+            arrs = [np.empty(int(n), dtype=np.int64) for n in lens]
+            ptrs = (capi.c_i64_p * (d * d))(*[capi.ptr_i64(a) for a in arrs])
+            return arrs, ptrs
+        kap, kap_p = alloc(klen, want_kappa)
+        var, var_p = alloc(vlen, want_varpi)
+        lag, lag_p = alloc(vlen, want_lag_sizes)
+        self._check(self._lib.aslsd_index_maps(self._ctx, kap_p, var_p, lag_p))
+
+        def nest(arrs):
+            return None if arrs is None else [[arrs[i * d + j] for j in range(d)]
+                                              for i in range(d)]
+        return nest(kap), nest(var), nest(lag)
+
+    # ---- model -----------------------------------------------------------------------
+    def set_model(self, model):
+        desc = describe_model(model)
+        n_basis, bases = desc.c_arrays()
+        self._check(self._lib.aslsd_set_model(self._ctx, desc.d, n_basis, bases))
+        self.desc = desc
+        return desc
+
+    # ---- exact sums ------------------------------------------------------------------
+    def _ranges(self, ranges):
+        if ranges is None:
+            return None, None, None, None
+        lo = np.array([r[0] for r in ranges], dtype=np.int64)
+        hi = np.array([r[1] for r in ranges], dtype=np.int64)
+        return lo, hi, capi.ptr_i64(lo), capi.ptr_i64(hi)
+
+    def exact_sums_packed(self, k, x_k, compute_f_sum=True, compute_diff_f_sum=True,
+                          ranges=None, count_pairs=False):
+        x = capi.as_f64(np.asarray(x_k, dtype=np.float64))
+        if len(x) != self.desc.n_param_k(k):
+            raise ValueError('x_k has %d entries, expected %d' % (len(x), self.desc.n_param_k(k)))
+        layout, out_len = term_layout(self.desc, k)
+        out = np.zeros(out_len, dtype=np.float64)
+        flags = (capi.ASLSD_F if compute_f_sum else 0) | (capi.ASLSD_DIFF if compute_diff_f_sum else 0)
+        lo, hi, lo_p, hi_p = self._ranges(ranges)
+        counts = np.zeros(len(layout), dtype=np.int64) if count_pairs else None
+        self._check(self._lib.aslsd_exact_sums(
+            self._ctx, int(k), capi.ptr_f64(x), flags, lo_p, hi_p, capi.ptr_f64(out),
+            capi.ptr_i64(counts) if count_pairs else None))
+        if count_pairs:
+            return out, {entry[0]: int(c) for entry, c in zip(layout, counts)}
+        return out
+
+    def exact_sums(self, k, x_k, compute_f_sum=True, compute_diff_f_sum=True, ranges=None,
+                   count_pairs=False):
+        res = self.exact_sums_packed(k, x_k, compute_f_sum, compute_diff_f_sum, ranges,
+                                     count_pairs)
+        packed, counts = res if count_pairs else (res, None)
+        sum_f, sum_diff_f = unpack_terms(self.desc, k, packed)
+        if count_pairs:
+            return sum_f, sum_diff_f, counts
+        return sum_f, sum_diff_f
+
+    # split form (multi-GPU): raw accumulators stay on the device
+    def exact_raw_len(self, k):
+        n = ctypes.c_int64()
+        self._check(self._lib.aslsd_exact_raw_len(self._ctx, int(k), ctypes.byref(n)))
+        return n.value
+
+    def exact_raw_device(self, k, x_k, raw_device_ptr, compute_f_sum=True,
+                         compute_diff_f_sum=True, ranges=None):
+        x = capi.as_f64(np.asarray(x_k, dtype=np.float64))
+        flags = (capi.ASLSD_F if compute_f_sum else 0) | (capi.ASLSD_DIFF if compute_diff_f_sum else 0)
+        lo, hi, lo_p, hi_p = self._ranges(ranges)
+        self._check(self._lib.aslsd_exact_raw_device(
+            self._ctx, int(k), capi.ptr_f64(x), flags, lo_p, hi_p,
+            ctypes.c_void_p(raw_device_ptr), None))
+
+    def exact_assemble(self, k, x_k, raw_host, compute_f_sum=True, compute_diff_f_sum=True):
+        x = capi.as_f64(np.asarray(x_k, dtype=np.float64))
+        raw = capi.as_f64(raw_host)
+        _, out_len = term_layout(self.desc, k)
+        out = np.zeros(out_len, dtype=np.float64)
+        flags = (capi.ASLSD_F if compute_f_sum else 0) | (capi.ASLSD_DIFF if compute_diff_f_sum else 0)
+        self._check(self._lib.aslsd_exact_assemble(self._ctx, int(k), capi.ptr_f64(x), flags,
+                                                   capi.ptr_f64(raw), capi.ptr_f64(out)))
+        return out

@@ -1,0 +1,190 @@
+"""Host-side model description for the B200 engine.
+
+Lightweight mirrors of the reference's model objects - only what the LSE path
+reads from them - plus ``describe_model`` which extracts the device descriptor
+from *either* these mirrors, the reference's own ``MHP`` object (duck typing on
+``_kernel_matrix[k][i]._basis_kernels[r]``: class name, ``fixed_indices``,
+``fixed_vars``) or a plain dict ``{'d', 'kernels'}``.
+
+Reference interfaces mirrored:
+  * BasisKernel fixed variables   functionals/kernels/basis_kernel.py:113-130, :364-401
+  * KernelModel parameter maps    functionals/kernels/kernel.py:97-117
+  * MHP parameter maps            models/hawkes/linear/mhp.py:276-299
+  * MHP.init_estimator            models/hawkes/linear/mhp.py:1525-1538
+"""
+import numpy as np
+
+from aslsd_b200 import capi
+
+_N_VARS = {'ExponentialKernel': 2, 'GaussianKernel': 3}
+_TYPE_ID = {'ExponentialKernel': capi.BASIS_EXPONENTIAL,
+            'GaussianKernel': capi.BASIS_GAUSSIAN}
+_SHORT = {'exp': 'ExponentialKernel', 'gauss': 'GaussianKernel'}
+
+
+class BasisKernel:
+    """A basis kernel with optionally fixed variables
+    (basis_kernel.py:113-130)."""
+    n_vars = None
+
+    def __init__(self, fixed_indices=None, fixed_vars=None):
+        if fixed_indices is None:
+            fixed_indices, fixed_vars = [], []
+        fixed_indices = np.atleast_1d(np.asarray(fixed_indices, dtype=int))
+        fixed_vars = np.atleast_1d(np.asarray(fixed_vars, dtype=float))
+        if len(fixed_indices) != len(fixed_vars):
+            raise ValueError('fixed_indices and fixed_vars must have the same length')
+        order = np.argsort(fixed_indices, kind='stable')
+        self.fixed_indices = fixed_indices[order]
+        self.fixed_vars = fixed_vars[order]
+        self.n_fixed_vars = len(self.fixed_vars)
+
+    def get_n_vars(self):
+        return self.n_vars
+
+    def get_n_param(self):
+        return self.n_vars - self.n_fixed_vars
+
+
+class ExponentialKernel(BasisKernel):
+    """phi(t) = omega beta exp(-beta t) (basis_kernel_exponential.py:387-388)."""
+    n_vars = 2
+
+
+class GaussianKernel(BasisKernel):
+    """phi(t) = omega N(t; delta, beta) (basis_kernel_gaussian.py:448-452)."""
+    n_vars = 3
+
+
+class KernelModel:
+    """Sum of basis kernels (kernel.py:14-92)."""
+
+    def __init__(self, _basis_kernels):
+        if isinstance(_basis_kernels, BasisKernel):
+            _basis_kernels = [_basis_kernels]
+        self._basis_kernels = list(_basis_kernels)
+        self.n_basis_ker = len(self._basis_kernels)
+        self.vec_n_param = [b.get_n_param() for b in self._basis_kernels]
+        self.n_param = sum(self.vec_n_param)
+
+
+class MHP:
+    """Multivariate Hawkes model: only the parameter book-keeping of
+    models/hawkes/linear/mhp.py:216-299."""
+
+    def __init__(self, _kernel_matrix):
+        self._kernel_matrix = [list(row) for row in _kernel_matrix]
+        self.d = len(self._kernel_matrix)
+        self.desc = describe_model(self)
+        self.matrix_n_param = self.desc.matrix_n_param
+        self.ix_map = self.desc.ix_map
+        self.interval_map = self.desc.interval_map
+
+    def init_estimator(self, estimator, k):
+        estimator.n_param_k = 1 + sum(self.matrix_n_param[k])
+        estimator.matrix_n_param = self.matrix_n_param
+        estimator.ix_map = self.ix_map
+        estimator.interval_map = self.interval_map
+
+
+class ModelDesc:
+    """Device descriptor of a model + the reference's parameter maps."""
+
+    def __init__(self, d, bases):
+        # bases[k][i] = list of (type_name, free_mask, fixed[3])
+        self.d = d
+        self.bases = bases
+        self.matrix_n_param = [[sum(bin(b[1]).count('1') for b in bases[k][i])
+                                for i in range(d)] for k in range(d)]
+        # mhp.py:276-299
+        self.ix_map = []
+        self.interval_map = []
+        for k in range(d):
+            row = [-1]
+            imap = []
+            pos = 1
+            for i in range(d):
+                n = self.matrix_n_param[k][i]
+                imap.append([pos, pos + n])
+                row.extend({'ker': i, 'par': r} for r in range(n))
+                pos += n
+            self.ix_map.append(row)
+            self.interval_map.append(imap)
+
+    def n_param_k(self, k):
+        return 1 + sum(self.matrix_n_param[k])
+
+    def c_arrays(self):
+        d = self.d
+        n_basis = (capi.ctypes.c_int32 * (d * d))()
+        flat = [b for k in range(d) for i in range(d) for b in self.bases[k][i]]
+        arr = (capi.Basis * len(flat))()
+        for k in range(d):
+            for i in range(d):
+                n_basis[k * d + i] = len(self.bases[k][i])
+        for ix, (type_name, free_mask, fixed) in enumerate(flat):
+            arr[ix].type = _TYPE_ID[type_name]
+            arr[ix].free_mask = free_mask
+            for v in range(3):
+                arr[ix].fixed[v] = fixed[v]
+        return n_basis, arr
+
+    def to_plain(self):
+        """Plain-data form used by the tests' oracle."""
+        short = {v: k for k, v in _SHORT.items()}
+        out = []
+        for k in range(self.d):
+            row = []
+            for i in range(self.d):
+                ker = []
+                for type_name, free_mask, fixed in self.bases[k][i]:
+                    nv = _N_VARS[type_name]
+                    ker.append({'type': short[type_name],
+                                'fixed': {v: fixed[v] for v in range(nv)
+                                          if not (free_mask >> v) & 1}})
+                row.append(ker)
+            out.append(row)
+        return {'d': self.d, 'kernels': out}
+
+
+def _describe_basis(b):
+    if isinstance(b, dict):
+        type_name = _SHORT[b['type']]
+        fixed_map = dict(b.get('fixed', {}))
+    else:
+        type_name = type(b).__name__
+        fixed_map = {int(ix): float(val)
+                     for ix, val in zip(np.atleast_1d(b.fixed_indices),
+                                        np.atleast_1d(b.fixed_vars))}
+    if type_name not in _N_VARS:
+        # mirrors the NotImplementedError of mhp.py:538-540 for unsupported kernels
+        raise NotImplementedError(
+            'basis kernel %s is outside the B200 engine scope '
+            '(ExponentialKernel, GaussianKernel)' % type_name)
+    nv = _N_VARS[type_name]
+    free_mask = 0
+    fixed = [0., 0., 0.]
+    for v in range(nv):
+        if v in fixed_map:
+            fixed[v] = float(fixed_map[v])
+        else:
+            free_mask |= 1 << v
+    return (type_name, free_mask, fixed)
+
+
+def describe_model(model):
+    """Build the ModelDesc of a reference MHP, a mirror MHP, or a plain dict."""
+    if isinstance(model, ModelDesc):
+        return model
+    if isinstance(model, dict):
+        d = model['d']
+        bases = [[[_describe_basis(b) for b in model['kernels'][k][i]]
+                  for i in range(d)] for k in range(d)]
+        return ModelDesc(d, bases)
+    mat = getattr(model, '_kernel_matrix', None)
+    if mat is None:
+        raise TypeError('cannot describe model of type %s' % type(model).__name__)
+    d = len(mat)
+    bases = [[[_describe_basis(b) for b in mat[k][i]._basis_kernels]
+              for i in range(d)] for k in range(d)]
+    return ModelDesc(d, bases)

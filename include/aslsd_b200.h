@@ -1,0 +1,150 @@
+/*
+ * aslsd_b200 - C ABI of the B200 engine for the LSE hot path of saadlabyad/aslsd.
+ *
+ * Plain C: pointers and sizes only, no torch types.  Every entry point names
+ * the reference interface (file:line under the reference tree) it replaces.
+ * The caller owns every host buffer; the library owns device memory between
+ * aslsd_create and aslsd_destroy.  All functions return 0 on success or a
+ * negative code; the message is available from aslsd_last_error.  A context is
+ * bound to one GPU (one process per GPU) and is not re-entrant.
+ *
+ * There is no CPU fallback: without a CUDA device aslsd_create fails.
+ */
+#ifndef ASLSD_B200_H
+#define ASLSD_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct aslsd_ctx aslsd_ctx;
+
+enum {
+  ASLSD_OK = 0,
+  ASLSD_ERR_CUDA = -1,      /* CUDA runtime error (no device, OOM, launch failure) */
+  ASLSD_ERR_ARG = -2,       /* invalid argument / call order */
+  ASLSD_ERR_UNSUPPORTED = -3 /* model outside the engine's scope (NotImplementedError upstream) */
+};
+
+/* Basis-kernel families.  The reference dispatches on str(type(.))
+ * (functionals/kernels/basis_kernels/basis_kernel_exponential.py:418-420). */
+enum {
+  ASLSD_BASIS_EXPONENTIAL = 0, /* vars (omega, beta)        basis_kernel_exponential.py:387-439 */
+  ASLSD_BASIS_GAUSSIAN = 1     /* vars (omega, beta, delta) basis_kernel_gaussian.py:448-529    */
+};
+
+/* One basis kernel of a KernelModel (functionals/kernels/kernel.py:14-92) with
+ * its fixed variables (functionals/kernels/basis_kernel.py:113-130, :364-401). */
+typedef struct {
+  int32_t type;      /* ASLSD_BASIS_*                                             */
+  int32_t free_mask; /* bit v set: variable v is a free parameter                 */
+  double fixed[3];   /* value of variable v where bit v of free_mask is clear     */
+} aslsd_basis;
+
+/* Flags of the sum entry points (compute_f_sum / compute_diff_f_sum of
+ * mhp_exact_estimator.py:709-711, grad_alloc of mhp_stratified_estimator.py:1333). */
+enum {
+  ASLSD_F = 1,          /* function sums                                          */
+  ASLSD_DIFF = 2,       /* parameter-derivative sums                              */
+  ASLSD_GRAD_ALLOC = 4  /* allocation statistic = ||grad||_2 instead of f          */
+};
+
+/* ---- lifetime ------------------------------------------------------------------ */
+int aslsd_create(aslsd_ctx** out, int device);
+int aslsd_destroy(aslsd_ctx* ctx);
+const char* aslsd_last_error(const aslsd_ctx* ctx);
+/* Use the caller's CUDA stream (a cudaStream_t) for all subsequent work;
+ * NULL restores the context's own stream. */
+int aslsd_set_stream(aslsd_ctx* ctx, void* cuda_stream);
+/* CUDA-event duration (ms) and launch count of the pair / sample kernels of
+ * the last sum call, measured on the launching stream. */
+int aslsd_last_timing(const aslsd_ctx* ctx, double* kernel_ms, int64_t* n_launches);
+
+/* ---- events: replaces ProcessPath.__init__ data members ---------------------------
+ * stats/events/process_path.py:63-106 (list_times, T_f, n_events, list_times2end).
+ * times[i] is the sorted fp64 array of the n_events[i] events of type i. */
+int aslsd_set_events(aslsd_ctx* ctx, int d, const int64_t* n_events,
+                     const double* const* times, double T_f);
+
+/* ---- index maps: replaces time_ordering.get_kappa_varpi / get_lag_sizes ----------
+ * stats/events/time_ordering.py:9-84 and :87-119.  Two-pass: query lengths,
+ * then fill caller buffers.  All arrays are indexed [i*d + j].
+ *   kappa[i][j] : n_events[j] + 1 entries (terminal entry per :64-65)
+ *   varpi[i][j] : kappa[j][i][n_events[i]-1] + 2 entries (i != j), n_events[i] (i == j)
+ *   lag_sizes[i][j] : same length as varpi[i][j]; [0] = 0, [h] = n_events[i] - varpi[i][j][h]
+ * Any of the three output tables may be NULL to skip it. */
+int aslsd_index_map_sizes(aslsd_ctx* ctx, int64_t* kappa_len, int64_t* varpi_len);
+int aslsd_index_maps(aslsd_ctx* ctx, int64_t* const* kappa_out,
+                     int64_t* const* varpi_out, int64_t* const* lag_sizes_out);
+
+/* ---- model: replaces MHP.init_estimator / make_functionals ------------------------
+ * models/hawkes/linear/mhp.py:1525-1538, :475-540.  n_basis[k*d + i] bases of
+ * kernel phi_ki, concatenated in `bases` in row-major (k, i) order.  The
+ * parameter vector x_k of sub-problem k is [mu_k, params(phi_k0), ...] with the
+ * free variables of every basis in variable order (mhp.py:276-299, kernel.py:97-117). */
+int aslsd_set_model(aslsd_ctx* ctx, int d, const int32_t* n_basis,
+                    const aslsd_basis* bases);
+/* Number of parameters of x_k and of each kernel phi_ki (n_param[i], i < d). */
+int aslsd_model_n_param(const aslsd_ctx* ctx, int k, int32_t* n_param_k,
+                        int32_t* n_param);
+
+/* ---- exact sums: replaces MHPExactEstim.compute_objective -------------------------
+ * optimize/estimators/mhp_exact_estimator.py:709-761 and the five compute_*_sum
+ * methods :543-707.  Output `out` is packed term after term in the order the
+ * reference evaluates them (psi_i, upsilonzero_i, phi_i, upsilon_i_i for
+ * i = 0..d-1, then upsilon_i_j for i != j in itertools.product order); each term
+ * holds [sum_f, sum_diff_f(ix_func 1)[n1], sum_diff_f(ix_func 2)[n2]] where
+ * (n1, n2) = (n_param_ki, 1) for psi, (n_param_ki, 0) for upsilonzero / phi /
+ * upsilon_i_i and (n_param_ki, n_param_kj) for upsilon_i_j.
+ * m_lo / m_hi (length d, may be NULL for all events) restrict the *target*
+ * events of every term to a block of indices per dimension: a time-block shard;
+ * shard results add up to the full sums.
+ * n_pair_terms (may be NULL, one entry per term): number of in-window event
+ * pairs evaluated for the term (the unit of BASELINE.json's metric). */
+int aslsd_exact_out_len(const aslsd_ctx* ctx, int k, int64_t* out_len, int64_t* n_terms);
+int aslsd_exact_sums(aslsd_ctx* ctx, int k, const double* x_k, int flags,
+                     const int64_t* m_lo, const int64_t* m_hi, double* out,
+                     int64_t* n_pair_terms);
+
+/* Split form for multi-GPU: device-side raw accumulators (to be summed across
+ * ranks with one allreduce) and host-side assembly of the packed terms. */
+int aslsd_exact_raw_len(aslsd_ctx* ctx, int k, int64_t* raw_len);
+int aslsd_exact_raw_device(aslsd_ctx* ctx, int k, const double* x_k, int flags,
+                           const int64_t* m_lo, const int64_t* m_hi,
+                           double* raw_device, int64_t* n_pair_terms);
+int aslsd_exact_assemble(aslsd_ctx* ctx, int k, const double* x_k, int flags,
+                         const double* raw_host, double* out);
+
+/* ---- sampled sums: replaces the bodies of MHPStratEstim.estimate_sum_* ------------
+ * optimize/estimators/mhp_stratified_estimator.py:534-900 for one term.
+ * The (m, n) samples are generated on the host by the reference's own RNG code
+ * (utilities/useful_statistics.py:38-127) and consumed here unchanged.
+ *   term_kind: 0 psi_i, 1 upsilonzero_i, 2 phi_i, 3 upsilon_i_j (i == j allowed)
+ *   stratum_offsets: n_strata + 1 offsets into ix_m / ix_n
+ *   ix_n is ignored for single-index terms (psi, upsilonzero)
+ * Outputs, per stratum s (n_out = 1 + n1 + n2 as in aslsd_exact_sums):
+ *   mean_out[s*n_out + c]   mean over the stratum's samples of f (c = 0) and of
+ *                           every derivative (numpy.mean)
+ *   stat_mean[s], stat_std[s]  mean and population std (numpy.std, ddof = 0) of
+ *                           the allocation statistic: f, or ||grad f||_2 when
+ *                           ASLSD_GRAD_ALLOC is set (:605-635)
+ *   sum_out[s*n_out + c]    plain sums (used by the exact domain, :856-900) */
+int aslsd_sampled_sums(aslsd_ctx* ctx, int k, const double* x_k, int term_kind,
+                       int i, int j, int flags, int n_strata,
+                       const int64_t* stratum_offsets, const int64_t* ix_m,
+                       const int64_t* ix_n, double* mean_out, double* sum_out,
+                       double* stat_mean, double* stat_std);
+
+/* Fused allocation update of estimate_sum_adaptivedom (:637-645):
+ * rel_alloc[s] = size_s * sqrt(size_s / (size_s - 1)) * std_s, normalised;
+ * if every std is zero the default allocation is returned. */
+int aslsd_update_allocation(aslsd_ctx* ctx, int n_strata, const double* strata_sizes,
+                            const double* stat_std, const double* default_alloc,
+                            double* rel_alloc_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ASLSD_B200_H */

@@ -1,0 +1,146 @@
+"""Parity of the exact LSE sums computed by the CUDA pair kernels, through the
+C ABI, against (1) the reference's golden vectors, (2) the oracle on seeded
+inputs, (3) size-independent properties at larger sizes.
+
+Tolerance: relative 1e-10 per term (BASELINE.json north_star), fp64."""
+import numpy as np
+import pytest
+
+from cases import CASES, case_x
+from helpers import RTOL, load_golden, golden_times, assert_sums_close, iter_sum_entries
+from oracle import exact as OE
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope='module')
+def engine():
+    import aslsd_b200
+    return aslsd_b200.Engine(0)
+
+
+@pytest.mark.parametrize('name', sorted(CASES))
+def test_exact_sums_match_reference_golden(engine, name):
+    model = CASES[name][0]
+    g = load_golden('exact_' + name)
+    times, T_f = golden_times(g)
+    engine.set_events(times, T_f)
+    engine.set_model(model)
+    for k in range(model['d']):
+        sum_f, sum_diff_f = engine.exact_sums(k, g['k%d/x' % k])
+        worst = assert_sums_close(sum_f, sum_diff_f, g, 'k%d' % k, rtol=RTOL)
+        assert worst <= RTOL
+
+
+@pytest.mark.parametrize('name', ['exp2d', 'sbf2d3', 'gauss2d'])
+def test_function_only_flag(engine, name):
+    model = CASES[name][0]
+    g = load_golden('exact_' + name)
+    times, T_f = golden_times(g)
+    engine.set_events(times, T_f)
+    engine.set_model(model)
+    sum_f, _ = engine.exact_sums(0, g['k0/x'], compute_f_sum=True, compute_diff_f_sum=False)
+    for name_t, val in sum_f.items():
+        ref = g['k0/f/%s' % name_t]
+        assert abs(val - ref) <= RTOL * abs(ref)
+
+
+def _simulate_poisson_cluster(rng, d, T_f, rate):
+    # plain superposition of homogeneous streams: enough for a parity input
+    return [np.sort(rng.uniform(0, T_f, size=rng.poisson(rate * T_f))) for _ in range(d)]
+
+
+@pytest.mark.parametrize('name', ['exp2d', 'gauss2d', 'sbf2d3', 'sbf1d10', 'exp1d2b', 'gauss1d2b'])
+def test_exact_sums_match_windowed_oracle_medium(engine, name):
+    """~10^4 events per type: the oracle's windowed restatement (agrees with the
+    literal reference to ~1e-15, tests/test_oracle_golden.py)."""
+    model = CASES[name][0]
+    d = model['d']
+    rng = np.random.default_rng(99)
+    times = _simulate_poisson_cluster(rng, d, 4000., 2.0 if 'sbf' not in name else 1.0)
+    T_f = 4000.
+    engine.set_events(times, T_f)
+    engine.set_model(model)
+    xs = case_x(name)
+    for k in range(d):
+        sum_f, sum_diff_f, counts = engine.exact_sums(k, xs[k], count_pairs=True)
+        o_f, o_df, o_counts = OE.exact_sums_windowed(model, k, xs[k], times, T_f)
+        ref = {}
+        for label, val in iter_sum_entries(o_f, o_df):
+            ref['k/%s' % label] = val
+        assert_sums_close(sum_f, sum_diff_f, ref, 'k', rtol=RTOL)
+
+
+def test_shards_add_up_and_match_oracle_blocks(engine):
+    """Time-block shards of the target events add up to the full sums."""
+    name = 'sbf2d3'
+    model = CASES[name][0]
+    rng = np.random.default_rng(5)
+    times = _simulate_poisson_cluster(rng, 2, 3000., 1.5)
+    T_f = 3000.
+    engine.set_events(times, T_f)
+    engine.set_model(model)
+    x = case_x(name)[1]
+    full = engine.exact_sums_packed(1, x)
+    cuts = [0.0, 700., 1800., T_f + 1]
+    acc = np.zeros_like(full)
+    for a, b in zip(cuts[:-1], cuts[1:]):
+        ranges = [(int(np.searchsorted(t, a)), int(np.searchsorted(t, b))) for t in times]
+        part = engine.exact_sums_packed(1, x, ranges=ranges)
+        acc += part
+        o_f, o_df, _ = OE.exact_sums_windowed(model, 1, x, times, T_f, ranges=ranges)
+        from aslsd_b200.engine import unpack_terms
+        s_f, s_df = unpack_terms(engine.desc, 1, part)
+        ref = {'k/%s' % label: val for label, val in iter_sum_entries(o_f, o_df)}
+        assert_sums_close(s_f, s_df, ref, 'k', rtol=RTOL, atol=1e-13)
+    np.testing.assert_allclose(acc, full, rtol=1e-12, atol=1e-12)
+
+
+def test_split_raw_and_assemble_matches_fused(engine):
+    import torch
+    name = 'gauss2d'
+    model = CASES[name][0]
+    g = load_golden('exact_' + name)
+    times, T_f = golden_times(g)
+    engine.set_events(times, T_f)
+    engine.set_model(model)
+    x = g['k1/x']
+    fused = engine.exact_sums_packed(1, x)
+    raw = torch.zeros(engine.exact_raw_len(1), dtype=torch.float64, device='cuda:0')
+    engine.exact_raw_device(1, x, raw.data_ptr())
+    torch.cuda.synchronize()
+    out = engine.exact_assemble(1, x, raw.cpu().numpy())
+    np.testing.assert_array_equal(out, fused)
+
+
+def test_linearity_in_omega_for_sbf(engine):
+    """Size-independent property: with (beta, delta) fixed every sum is a
+    polynomial of degree <= 2 in omega; phi sums are linear."""
+    name = 'sbf1d10'
+    model = CASES[name][0]
+    rng = np.random.default_rng(3)
+    times = _simulate_poisson_cluster(rng, 1, 20000., 1.0)
+    engine.set_events(times, 20000.)
+    engine.set_model(model)
+    x = case_x(name)[0]
+    f1, _ = engine.exact_sums(0, x)
+    x2 = x.copy()
+    x2[1:] *= 2.0
+    f2, _ = engine.exact_sums(0, x2)
+    assert abs(f2['phi_0'] - 2 * f1['phi_0']) <= 1e-12 * abs(f1['phi_0'])
+    assert abs(f2['upsilon_0_0'] - 4 * f1['upsilon_0_0']) <= 1e-12 * abs(f1['upsilon_0_0'])
+    assert abs(f2['upsilonzero_0'] - 4 * f1['upsilonzero_0']) <= 1e-12 * abs(f1['upsilonzero_0'])
+
+
+def test_errors(engine):
+    import aslsd_b200
+    g = load_golden('exact_exp1d')
+    times, T_f = golden_times(g)
+    engine.set_events(times, T_f)
+    with pytest.raises(NotImplementedError):
+        engine.set_model({'d': 1, 'kernels': [[[{'type': 'exp'}, {'type': 'gauss'}]]]})
+    engine.set_model(CASES['exp1d'][0])
+    with pytest.raises(ValueError):
+        engine.exact_sums(0, [1.0, 0.2])
+    with pytest.raises(aslsd_b200.EngineError):
+        engine.exact_sums(0, [1.0, 0.2, -1.0])
