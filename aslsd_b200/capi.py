@@ -38,6 +38,7 @@ SYMBOLS = {
     'aslsd_last_error': (ctypes.c_char_p, [ctypes.c_void_p]),
     'aslsd_set_stream': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p]),
     'aslsd_last_timing': (ctypes.c_int, [ctypes.c_void_p, c_f64_p, c_i64_p]),
+    'aslsd_measure_fp64_peak': (ctypes.c_int, [ctypes.c_void_p, c_f64_p]),
     'aslsd_set_events': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, c_i64_p,
                                         ctypes.POINTER(c_f64_p), ctypes.c_double]),
     'aslsd_index_map_sizes': (ctypes.c_int, [ctypes.c_void_p, c_i64_p, c_i64_p]),
@@ -54,6 +55,7 @@ SYMBOLS = {
                                               c_i64_p, c_i64_p, ctypes.c_void_p, c_i64_p]),
     'aslsd_exact_assemble': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, c_f64_p, ctypes.c_int,
                                             c_f64_p, c_f64_p]),
+    'aslsd_last_eval_counts': (ctypes.c_int, [ctypes.c_void_p, c_i64_p, c_i64_p]),
     'aslsd_sampled_sums': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, c_f64_p, ctypes.c_int,
                                           ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                           c_i64_p, c_i64_p, c_i64_p, c_f64_p, c_f64_p, c_f64_p,

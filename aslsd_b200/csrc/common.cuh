@@ -116,6 +116,10 @@ struct aslsd_ctx {
   double last_ms = 0.;
   bool timing_pending = false;
   int64_t last_launches = 0;
+  // evaluation counters of the last exact-sum call (per item, on the device)
+  int64_t last_n_wu = 0;
+  int last_n_items = 0;
+  int last_fam_first[8] = {0}, last_fam_count[8] = {0};
 };
 
 struct DimDev {

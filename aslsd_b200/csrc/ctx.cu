@@ -241,3 +241,42 @@ extern "C" int aslsd_model_n_param(const aslsd_ctx* ctx, int k, int32_t* n_param
   if (n_param_k) *n_param_k = tot;
   return ASLSD_OK;
 }
+
+// ---- fp64 roofline denominator -----------------------------------------------------------------
+// MEASURED_PEAKS.json has no fp64 entry: a DFMA microbenchmark
+// with 8 independent chains per thread, enough resident warps to saturate the
+// fp64 pipe, timed with CUDA events on the context's stream.
+__global__ void __launch_bounds__(256)
+dfma_peak_kernel(double* out, int iters, double a, double b) {
+  double x0 = threadIdx.x * 1e-3, x1 = x0 + 1., x2 = x0 + 2., x3 = x0 + 3.;
+  double x4 = x0 + 4., x5 = x0 + 5., x6 = x0 + 6., x7 = x0 + 7.;
+  for (int i = 0; i < iters; ++i) {
+    x0 = fma(x0, a, b); x1 = fma(x1, a, b); x2 = fma(x2, a, b); x3 = fma(x3, a, b);
+    x4 = fma(x4, a, b); x5 = fma(x5, a, b); x6 = fma(x6, a, b); x7 = fma(x7, a, b);
+  }
+  double s = ((x0 + x1) + (x2 + x3)) + ((x4 + x5) + (x6 + x7));
+  if (s == 12345.678) out[0] = s;   // keep the chains alive
+}
+
+extern "C" int aslsd_measure_fp64_peak(aslsd_ctx* ctx, double* tflops) {
+  if (!ctx || !tflops) return ASLSD_ERR_ARG;
+  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  double* d_out = nullptr;
+  CUDA_TRY(ctx, cudaMalloc(&d_out, sizeof(double)));
+  const int iters = 1 << 14, blocks = 148 * 8, threads = 256;
+  double best = 0.;
+  for (int rep = 0; rep < 5; ++rep) {
+    cudaEventRecord(ctx->ev0, ctx->stream);
+    dfma_peak_kernel<<<blocks, threads, 0, ctx->stream>>>(d_out, iters, 0.999999, 1e-9);
+    cudaEventRecord(ctx->ev1, ctx->stream);
+    cudaError_t e = cudaEventSynchronize(ctx->ev1);
+    if (e != cudaSuccess) { cudaFree(d_out); CUDA_TRY(ctx, e); }
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
+    double flops = 2.0 * 8.0 * (double)iters * (double)blocks * (double)threads;
+    best = std::max(best, flops / (ms * 1e-3) * 1e-12);
+  }
+  cudaFree(d_out);
+  *tflops = best;
+  return ASLSD_OK;
+}

@@ -371,6 +371,9 @@ static int run_plan(aslsd_ctx* ctx, const ExactPlan& P, double* raw_device, unsi
   ctx->last_launches++;
   CUDA_TRY(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
   ctx->timing_pending = true;
+  ctx->last_n_wu = P.n_wu;
+  ctx->last_n_items = (int)n_items;
+  for (int f = 0; f < 8; ++f) { ctx->last_fam_first[f] = P.fam_first[f]; ctx->last_fam_count[f] = P.fam_count[f]; }
   CUDA_TRY(ctx, cudaGetLastError());
   return ASLSD_OK;
 }
@@ -610,4 +613,27 @@ extern "C" int aslsd_exact_sums(aslsd_ctx* ctx, int k, const double* x_k, int fl
   assemble(ctx, P, x_k, (const double*)ctx->h_pinned, out);
   if (n_pair_terms) rc = count_pair_terms(ctx, P, n_pair_terms);
   return rc;
+}
+
+// Number of closed-form evaluations of the last exact-sum call: basis-pair
+// evaluations of the pair kernels (upsilon, phi) and of the single kernels.
+extern "C" int aslsd_last_eval_counts(aslsd_ctx* ctx, int64_t* pair_evals, int64_t* single_evals) {
+  if (!ctx) return ASLSD_ERR_ARG;
+  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  std::vector<unsigned long long> h(std::max(1, ctx->last_n_items));
+  if (ctx->last_n_items > 0) {
+    CUDA_TRY(ctx, cudaMemcpyAsync(h.data(), ctx->d_counts + ctx->last_n_wu,
+                                  sizeof(unsigned long long) * ctx->last_n_items, cudaMemcpyDeviceToHost,
+                                  ctx->stream));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  }
+  int64_t pe = 0, se = 0;
+  for (int f = 0; f < 8; ++f) {
+    const bool pair = (f == ITEM_UPS_EXP || f == ITEM_UPS_GAUSS || f == ITEM_PHI_EXP || f == ITEM_PHI_GAUSS);
+    for (int x = 0; x < ctx->last_fam_count[f]; ++x)
+      (pair ? pe : se) += (int64_t)h[ctx->last_fam_first[f] + x];
+  }
+  if (pair_evals) *pair_evals = pe;
+  if (single_evals) *single_evals = se;
+  return ASLSD_OK;
 }

@@ -1,0 +1,83 @@
+"""Time-block sharding of the exact LSE sums over the GPUs of one box.
+
+One process per GPU (torch.distributed, NCCL over NVLink).  The observation
+window [0, T_f] is cut into ``world_size`` contiguous time blocks holding equal
+numbers of target events; rank g evaluates every term for the targets of its
+block only.  Sources are taken from the halo [block start - max lag, block
+end): the event times are replicated on every GPU (80 MB at 10^7 events), so
+the halo is purely logical and never needs an exchange.  All sums are additive
+over targets (mhp_exact_estimator.py:633, :667, :703), hence one allreduce of
+the raw accumulator vector combines the shards; the packed per-term sums are
+then assembled on every rank.
+"""
+import numpy as np
+
+from aslsd_b200.engine import unpack_terms
+
+
+def time_block_ranges(list_times, world_size):
+    """ranges[g][i] = (m_lo, m_hi): target events of type i owned by rank g.
+    Block boundaries are quantiles of the pooled event times, so that every
+    rank gets the same number of targets (hence, for a stationary stream, the
+    same number of in-window pairs)."""
+    if world_size == 1:
+        return [[(0, len(t)) for t in list_times]]
+    n_tot = sum(len(t) for t in list_times)
+    # quantiles of the pooled times without materialising the pooled sort:
+    # bisection on time for each cut
+    t_min = min(t[0] for t in list_times if len(t))
+    t_max = max(t[-1] for t in list_times if len(t))
+    cuts = []
+    for g in range(1, world_size):
+        target = n_tot * g // world_size
+        lo, hi = t_min, t_max
+        for _ in range(80):
+            mid = 0.5 * (lo + hi)
+            if sum(int(np.searchsorted(t, mid, side='left')) for t in list_times) < target:
+                lo = mid
+            else:
+                hi = mid
+        cuts.append(hi)
+    edges = [[0] + [int(np.searchsorted(t, c, side='left')) for c in cuts] + [len(t)]
+             for t in list_times]
+    return [[(edges[i][g], edges[i][g + 1]) for i in range(len(list_times))]
+            for g in range(world_size)]
+
+
+class ShardedExactSums:
+    """Exact sums of sub-problem k over ``dist`` ranks (one Engine per rank)."""
+
+    def __init__(self, engine, list_times, rank=0, world_size=1, dist=None, device=None):
+        import torch
+        self.torch = torch
+        self.engine = engine
+        self.rank, self.world_size, self.dist = rank, world_size, dist
+        self.device = device
+        self.ranges = time_block_ranges(list_times, world_size)[rank]
+        self._raw = {}
+
+    def raw_buffer(self, k):
+        if k not in self._raw:
+            n = self.engine.exact_raw_len(k)
+            self._raw[k] = self.torch.zeros(n, dtype=self.torch.float64, device=self.device)
+        return self._raw[k]
+
+    def launch(self, k, x_k, compute_f_sum=True, compute_diff_f_sum=True):
+        """Enqueue the shard's kernels and the allreduce; returns the device
+        tensor holding the combined raw accumulators (asynchronous)."""
+        raw = self.raw_buffer(k)
+        self.engine.set_stream(self.torch.cuda.current_stream().cuda_stream)
+        self.engine.exact_raw_device(k, x_k, raw.data_ptr(), compute_f_sum,
+                                     compute_diff_f_sum, ranges=self.ranges)
+        if self.world_size > 1:
+            self.dist.all_reduce(raw, op=self.dist.ReduceOp.SUM)
+        return raw
+
+    def packed(self, k, x_k, compute_f_sum=True, compute_diff_f_sum=True):
+        raw = self.launch(k, x_k, compute_f_sum, compute_diff_f_sum)
+        host = raw.cpu().numpy()     # synchronises the stream
+        return self.engine.exact_assemble(k, x_k, host, compute_f_sum, compute_diff_f_sum)
+
+    def sums(self, k, x_k, compute_f_sum=True, compute_diff_f_sum=True):
+        return unpack_terms(self.engine.desc, k,
+                            self.packed(k, x_k, compute_f_sum, compute_diff_f_sum))

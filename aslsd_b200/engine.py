@@ -96,6 +96,19 @@ class Engine:
         self._check(self._lib.aslsd_last_timing(self._ctx, ctypes.byref(ms), ctypes.byref(n)))
         return ms.value, n.value
 
+    def last_eval_counts(self):
+        """(pair-kernel, single-kernel) closed-form evaluations of the last
+        exact-sum call."""
+        a, b = ctypes.c_int64(), ctypes.c_int64()
+        self._check(self._lib.aslsd_last_eval_counts(self._ctx, ctypes.byref(a), ctypes.byref(b)))
+        return a.value, b.value
+
+    def measure_fp64_peak(self):
+        """Measured DFMA throughput in TFLOP/s (roofline denominator)."""
+        v = ctypes.c_double()
+        self._check(self._lib.aslsd_measure_fp64_peak(self._ctx, ctypes.byref(v)))
+        return v.value
+
     # ---- events ----------------------------------------------------------------------
     def set_events(self, list_times, T_f):
         times = [capi.as_f64(t) for t in list_times]

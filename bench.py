@@ -1,0 +1,346 @@
+"""Benchmark of the exact LSE gradient path (BASELINE.json metric:
+"exact LSE-gradient event-pair terms/sec at 1/2/4/8 B200").
+
+Workload: config C5 of SURVEY.md section 8d - a 10-dimensional MHP whose 100
+kernels are sums of 10 Gaussians (beta, delta fixed; omega free), ~10^7
+simulated events.  One step = one full exact evaluation (function value and
+all parameter derivatives of every term) for all d sub-problems k, i.e. what d
+calls of ``lse_k_grad_estimate`` compute; nothing is cached between steps.
+The unit counted is the in-window event pair of a named double sum (phi_i,
+upsilon_i_j) of one k.
+
+    python bench.py --gpus N --steps K --warmup W            # this engine
+    python bench.py --impl reference --gpus N --steps K ...  # CPU oracle arm
+
+N > 1 is launched under torchrun (one rank per GPU); the events are replicated,
+target events are sharded by time block, raw accumulators are combined with one
+NCCL allreduce per k (strong scaling: total work is fixed).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+# flops per closed-form evaluation, SURVEY 8d conventions (add/mul 1, FMA 2,
+# div/sqrt 10, EXP 25, NDTR 60): interior Gaussian upsilon value of one basis pair
+# = 1 EXP + 1 NDTR + 12; Gaussian phi value = 1 EXP + 4
+FLOPS_UPS_EVAL = 25 + 60 + 12
+FLOPS_PHI_EVAL = 25 + 4
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=3)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+    ap.add_argument('--T_f', type=float, default=1.1e6, help='observation window (1.1e6 -> ~10^7 events)')
+    ap.add_argument('--d', type=int, default=10)
+    ap.add_argument('--n_basis', type=int, default=10)
+    ap.add_argument('--cpu_sample_T', type=float, default=600., help='time slice of the CPU baseline sample')
+    ap.add_argument('--no_cpu_baseline', action='store_true')
+    return ap.parse_args()
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region."""
+    QUERY = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,'
+             'clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
+             'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, gpu_index):
+        self.gpu_index = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ['nvidia-smi', '-i', str(self.gpu_index), '--query-gpu=' + self.QUERY,
+                 '--format=csv,noheader,nounits', '-lms', '200'],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons = [], [], set()
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        for line in self.lines:
+            parts = [p.strip() for p in line.split(',')]
+            if len(parts) < 9:
+                continue
+            try:
+                sm.append(float(parts[1]))
+                smax.append(float(parts[2]))
+            except ValueError:
+                continue
+            for name, val in zip(names, parts[5:9]):
+                if val.lower().startswith('active'):
+                    reasons.add(name)
+        return {'sm_mhz': float(np.median(sm)) if sm else None,
+                'sm_max_mhz': float(np.max(smax)) if smax else None,
+                'reasons': sorted(reasons), 'samples': len(sm)}
+
+
+def load_measured_peaks():
+    path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(path):
+        with open(path) as f:
+            return json.load(f), 'measured'
+    return {'hbm_gbs': 6650.0}, 'fallback'
+
+
+def make_workload(args):
+    from aslsd_b200 import simulate
+    return simulate.config_c5(d=args.d, n_basis=args.n_basis, T_f=args.T_f, seed=1234)
+
+
+def cpu_oracle_rate(model, times, T_f, xs, sample_T, n_proc=1):
+    """Pair-terms/s of the numpy oracle (windowed restatement of the reference's
+    numpy path, oracle/exact.py) on a bounded sample: targets inside the first
+    ``sample_T`` time units, sub-problem k = 0, value + all derivatives."""
+    from oracle import exact as OE
+    ranges = [(0, int(np.searchsorted(t, sample_T))) for t in times]
+    if n_proc <= 1:
+        t0 = time.perf_counter()
+        _, _, n_pairs = OE.exact_sums_windowed(model, 0, xs[0], times, T_f, ranges=ranges)
+        dt = time.perf_counter() - t0
+        return sum(n_pairs.values()) / dt, dt, sum(n_pairs.values())
+    import multiprocessing as mp
+    cuts = np.linspace(0., sample_T, n_proc + 1)
+    jobs = []
+    for a, b in zip(cuts[:-1], cuts[1:]):
+        r = [(int(np.searchsorted(t, a)), int(np.searchsorted(t, b))) for t in times]
+        jobs.append((model, 0, xs[0], times, T_f, r))
+    ctx = mp.get_context('fork')
+    t0 = time.perf_counter()
+    with ctx.Pool(n_proc) as pool:
+        res = pool.starmap(_oracle_job, jobs)
+    dt = time.perf_counter() - t0
+    tot = sum(res)
+    return tot / dt, dt, tot
+
+
+def _oracle_job(model, k, x, times, T_f, ranges):
+    from oracle import exact as OE
+    # only the events the block can reach are needed
+    _, _, n_pairs = OE.exact_sums_windowed(model, k, x, times, T_f, ranges=ranges)
+    return sum(n_pairs.values())
+
+
+def run_reference(args):
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    from aslsd_b200 import simulate
+    # the sample only needs the events of the slice (plus nothing else: windowed sums)
+    sample_T = args.cpu_sample_T
+    model, times, T_f, xs = simulate.config_c5(d=args.d, n_basis=args.n_basis,
+                                               T_f=max(4 * sample_T, 2000.), seed=1234)
+    cores = os.cpu_count() or 1
+    n_proc = max(1, min(cores, 32))
+    rates, times_s = [], []
+    pairs = 0
+    for step in range(args.warmup + args.steps):
+        rate, dt, pairs = cpu_oracle_rate(model, times, T_f, xs, sample_T, n_proc=n_proc)
+        if step >= args.warmup:
+            rates.append(rate)
+            times_s.append(dt)
+    value = float(np.mean(rates))
+    line = {
+        'impl': 'reference', 'metric': 'exact LSE-gradient event-pair terms/sec',
+        'value': value, 'unit': 'pair-terms/s', 'n_gpus': args.gpus, 'steps': args.steps,
+        'warmup': args.warmup, 'ms_per_step': 1e3 * float(np.mean(times_s)),
+        'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None, 'dtype': 'f64',
+        'data': 'synthetic',
+        'config': {'workload': 'C5: %d-D SBF-Gaussian(%d) MHP, exact LSE value+gradient sums' %
+                   (args.d, args.n_basis),
+                   'note': 'reference is pure Python/numpy: timed as the oracle port '
+                           '(oracle/exact.py windowed restatement of its numpy path)'},
+        'cpu_baseline': {'value': value, 'unit': 'pair-terms/s', 'cores': n_proc, 'kind': 'port',
+                         'sample': 'sub-problem k=0, targets in the first %g time units of a C5 stream '
+                                   '(%d in-window pair-terms per step), split over %d processes' %
+                                   (sample_T, pairs, n_proc)},
+        'e2e': {'value': value, 'unit': 'pair-terms/s', 'h2d_bytes_per_step': 0,
+                'd2h_bytes_per_step': 0},
+        'gpu_launches': 0,
+    }
+    print(json.dumps(line))
+
+
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+    import aslsd_b200
+    from aslsd_b200.distributed import ShardedExactSums
+
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    if world > 1:
+        os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
+    torch.cuda.set_device(local_rank)
+    device = torch.device('cuda', local_rank)
+
+    model, times, T_f, xs = make_workload(args)
+    d = model['d']
+    n_events = int(sum(len(t) for t in times))
+    engine = aslsd_b200.Engine(local_rank)
+    engine.set_stream(torch.cuda.current_stream().cuda_stream)
+    engine.set_events(times, T_f)
+    engine.set_model(model)
+    sharded = ShardedExactSums(engine, times, rank=rank, world_size=world,
+                               dist=dist if world > 1 else None, device=device)
+
+    # work accounting (outside the timed region): in-window pair-terms of the
+    # whole job and closed-form evaluations of this rank
+    pair_terms = 0
+    if rank == 0:
+        for k in range(d):
+            _, counts = engine.exact_sums_packed(k, xs[k], count_pairs=True)
+            pair_terms += sum(counts.values())
+    fp64_peak = engine.measure_fp64_peak()
+
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=device)   # > 126 MB L2
+
+    def step():
+        outs = []
+        for k in range(d):
+            outs.append(sharded.launch(k, xs[k]))
+        return outs
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        flush.zero_()
+        step()
+    sync_all()
+
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+          for _ in range(args.steps)]
+    sync_all()
+    for s in range(args.steps):
+        flush.zero_()
+        ev[s][0].record()
+        step()
+        ev[s][1].record()
+    sync_all()
+    step_ms = [a.elapsed_time(b) for a, b in ev]
+    total_ms = float(sum(step_ms))
+    t_max = torch.tensor([total_ms], dtype=torch.float64, device=device)
+    if world > 1:
+        dist.all_reduce(t_max, op=dist.ReduceOp.MAX)
+    total_ms = float(t_max.item())
+    clocks = sampler.stop() if rank == 0 else None
+
+    # per-kernel accounting of one k (library CUDA events; same stream)
+    k_ms_sum, n_launch_step, evals_step = 0., 0, 0
+    for k in range(d):
+        sharded.launch(k, xs[k])
+        ms, nl = engine.last_timing()
+        pe, se = engine.last_eval_counts()
+        k_ms_sum += ms
+        n_launch_step += nl
+        evals_step += pe
+    torch.cuda.synchronize()
+
+    # end-to-end through the public API with host buffers: upload the events,
+    # evaluate every k, read the packed sums back
+    e2e_ms = []
+    h2d = 8 * n_events + sum(8 * len(x) for x in xs)
+    d2h = 0
+    for s in range(max(1, min(args.steps, 2))):
+        sync_all()
+        t0 = time.perf_counter()
+        engine.set_events(times, T_f)
+        d2h = 0
+        for k in range(d):
+            packed = sharded.packed(k, xs[k])
+            d2h += 8 * engine.exact_raw_len(k)
+        sync_all()
+        e2e_ms.append(1e3 * (time.perf_counter() - t0))
+    e2e_t = torch.tensor([float(np.mean(e2e_ms))], dtype=torch.float64, device=device)
+    if world > 1:
+        dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
+
+    if rank == 0:
+        peaks, peak_kind = load_measured_peaks()
+        ms_per_step = total_ms / args.steps
+        value = pair_terms / (ms_per_step * 1e-3)
+        # roofline of the dominant kernel (Gaussian upsilon pair kernel) on this rank
+        flops = evals_step * FLOPS_UPS_EVAL
+        achieved = flops / (k_ms_sum * 1e-3) * 1e-12 if k_ms_sum > 0 else None
+        line = {
+            'metric': 'exact LSE-gradient event-pair terms/sec',
+            'value': value, 'unit': 'pair-terms/s', 'n_gpus': world, 'steps': args.steps,
+            'warmup': args.warmup, 'ms_per_step': ms_per_step, 'higher_is_better': True,
+            'scaling': 'strong', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
+            'config': {'workload': 'C5: %d-D SBF-Gaussian(%d) MHP, %d simulated events, exact LSE '
+                                   'value+gradient sums of all %d sub-problems per step' %
+                                   (d, args.n_basis, n_events, d),
+                       'pair_terms_per_step': pair_terms, 'n_events': n_events, 'T_f': T_f,
+                       'l2': 'flushed between steps (256 MB write)',
+                       'sharding': 'time blocks of target events, events replicated, '
+                                   '1 NCCL allreduce per k' if world > 1 else 'single GPU'},
+            'roofline': {'bound': 'fp64', 'achieved': achieved, 'peak': fp64_peak, 'unit': 'TFLOP/s',
+                         'frac': (achieved / fp64_peak) if achieved else None, 'traffic': None,
+                         'kernel': 'pair_kernel<UPS_GAUSS> (+phi pair, single-index, finalize)',
+                         'peak_source': 'DFMA microbenchmark measured live (aslsd_measure_fp64_peak); '
+                                        'MEASURED_PEAKS.json has no fp64 entry',
+                         'algorithmic_flops_per_eval': FLOPS_UPS_EVAL,
+                         'evals_per_step_rank0': evals_step, 'kernel_ms_per_step_rank0': k_ms_sum,
+                         'hbm_peak_gbs': peaks.get('hbm_gbs'), 'hbm_peak_kind': peak_kind},
+            'e2e': {'value': pair_terms / (float(e2e_t.item()) * 1e-3), 'unit': 'pair-terms/s',
+                    'h2d_bytes_per_step': h2d * world, 'd2h_bytes_per_step': d2h * world,
+                    'ms_per_step': float(e2e_t.item())},
+            'gpu_launches': n_launch_step * args.steps,
+            'clocks': clocks,
+        }
+        if not args.no_cpu_baseline and world == 1:
+            rate, dt, pairs = cpu_oracle_rate(model, times, T_f, xs, args.cpu_sample_T, n_proc=1)
+            line['cpu_baseline'] = {
+                'value': rate, 'unit': 'pair-terms/s', 'cores': 1, 'kind': 'port',
+                'sample': 'numpy oracle (oracle/exact.py), sub-problem k=0, targets in the first %g time '
+                          'units (%d pair-terms, %.1f s); host has %d cores' %
+                          (args.cpu_sample_T, pairs, dt, os.cpu_count() or 0)}
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    a = parse_args()
+    if a.impl == 'reference':
+        run_reference(a)
+    else:
+        run_b200(a)

@@ -62,6 +62,10 @@ int aslsd_set_stream(aslsd_ctx* ctx, void* cuda_stream);
  * the last sum call, measured on the launching stream. */
 int aslsd_last_timing(const aslsd_ctx* ctx, double* kernel_ms, int64_t* n_launches);
 
+/* Measured fp64 FMA throughput of the device (TFLOP/s, 2 flops per DFMA): the
+ * roofline denominator of the pair kernels (no reference counterpart). */
+int aslsd_measure_fp64_peak(aslsd_ctx* ctx, double* tflops);
+
 /* ---- events: replaces ProcessPath.__init__ data members ---------------------------
  * stats/events/process_path.py:63-106 (list_times, T_f, n_events, list_times2end).
  * times[i] is the sorted fp64 array of the n_events[i] events of type i. */
@@ -116,6 +120,11 @@ int aslsd_exact_raw_device(aslsd_ctx* ctx, int k, const double* x_k, int flags,
                            double* raw_device, int64_t* n_pair_terms);
 int aslsd_exact_assemble(aslsd_ctx* ctx, int k, const double* x_k, int flags,
                          const double* raw_host, double* out);
+
+/* Closed-form evaluations performed by the last exact-sum call (basis-pair
+ * evaluations of the pair kernels / of the single-index kernels): the work
+ * count behind the roofline figures. */
+int aslsd_last_eval_counts(aslsd_ctx* ctx, int64_t* pair_evals, int64_t* single_evals);
 
 /* ---- sampled sums: replaces the bodies of MHPStratEstim.estimate_sum_* ------------
  * optimize/estimators/mhp_stratified_estimator.py:534-900 for one term.
