@@ -31,6 +31,11 @@ class Basis(ctypes.Structure):
                 ('fixed', ctypes.c_double * 3)]
 
 
+class SampleTerm(ctypes.Structure):
+    _fields_ = [('kind', ctypes.c_int32), ('i', ctypes.c_int32), ('j', ctypes.c_int32),
+                ('n_strata', ctypes.c_int32)]
+
+
 # every symbol declared in include/aslsd_b200.h: name -> (restype, argtypes)
 SYMBOLS = {
     'aslsd_create': (ctypes.c_int, [ctypes.POINTER(ctypes.c_void_p), ctypes.c_int]),
@@ -56,10 +61,12 @@ SYMBOLS = {
     'aslsd_exact_assemble': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, c_f64_p, ctypes.c_int,
                                             c_f64_p, c_f64_p]),
     'aslsd_last_eval_counts': (ctypes.c_int, [ctypes.c_void_p, c_i64_p, c_i64_p]),
+    'aslsd_sampled_n_out': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int,
+                                           ctypes.c_int, ctypes.c_int, c_i32_p]),
     'aslsd_sampled_sums': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, c_f64_p, ctypes.c_int,
-                                          ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
-                                          c_i64_p, c_i64_p, c_i64_p, c_f64_p, c_f64_p, c_f64_p,
-                                          c_f64_p]),
+                                          ctypes.c_int, ctypes.POINTER(SampleTerm), c_i64_p,
+                                          c_i64_p, c_i64_p, c_f64_p, c_f64_p, c_f64_p, c_f64_p,
+                                          c_f64_p, c_f64_p]),
     'aslsd_update_allocation': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, c_f64_p, c_f64_p,
                                                c_f64_p, c_f64_p]),
 }

@@ -18,7 +18,6 @@
 
 #define ASLSD_INV_SQRT_2PI 0.3989422804014326779
 #define ASLSD_SQRT2 1.4142135623730950488
-#define MASK_OWN_SAME (1 << 8)   // own basis has the same (beta, delta) as both cross bases
 
 __device__ __forceinline__ double std_pdf(double x) { return ASLSD_INV_SQRT_2PI * exp(-0.5 * x * x); }
 

@@ -69,6 +69,7 @@ enum {
 enum { C_G = 0, C_B1 = 1, C_D1 = 2, C_B2 = 3, C_D2 = 4, C_SW = 5, C_SB = 6, C_SD = 7 };
 // exponential upsilon reuses slots: B1 -> 1, B2 -> 3
 #define MASK(c) (1 << (c))
+#define MASK_OWN_SAME (1 << 8)   // own basis has the same (beta, delta) as both cross bases
 
 struct TermPlan {
   int kind;          // 0 psi, 1 upsilonzero, 2 phi, 3 upsilon

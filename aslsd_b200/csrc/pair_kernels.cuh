@@ -16,9 +16,7 @@
 
 #include "basis_math.cuh"
 
-#define PAIR_NT 256      // threads per CTA
-#define PAIR_TM 1024     // targets per tile
-#define PAIR_SMAX 2048   // staged source events per tile (16 KB)
+#include "pair_tiles.h"
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return (uint32_t)__cvta_generic_to_shared(p);

@@ -118,6 +118,7 @@ class Engine:
         self._check(self._lib.aslsd_set_events(self._ctx, d, capi.ptr_i64(n_events), ptrs,
                                                float(T_f)))
         self.d, self.n_events, self.T_f = d, n_events, float(T_f)
+        self._events_key = None
 
     def index_maps(self, want_kappa=True, want_varpi=True, want_lag_sizes=True):
         """kappa, varpi, lag_sizes as d x d lists of int64 arrays
@@ -150,6 +151,7 @@ class Engine:
         n_basis, bases = desc.c_arrays()
         self._check(self._lib.aslsd_set_model(self._ctx, desc.d, n_basis, bases))
         self.desc = desc
+        self._model_ref = None
         return desc
 
     # ---- exact sums ------------------------------------------------------------------
@@ -186,6 +188,83 @@ class Engine:
         if count_pairs:
             return sum_f, sum_diff_f, counts
         return sum_f, sum_diff_f
+
+    # ---- sampled sums ----------------------------------------------------------------
+    def sampled_n_out(self, k, kind, i, j):
+        n = ctypes.c_int32()
+        self._check(self._lib.aslsd_sampled_n_out(self._ctx, int(k), int(kind), int(i), int(j),
+                                                  ctypes.byref(n)))
+        return n.value
+
+    def sampled_sums(self, k, x_k, terms, stratum_offsets, ix_m, ix_n=None, strata_sizes=None,
+                     default_alloc=None, compute_diff_f_sum=True, grad_alloc=False):
+        """One launch for every stratum of every term of a compute_objective call
+        (mhp_stratified_estimator.py:1333-1386).
+
+        terms: list of (kind, i, j, n_strata); the strata of all terms are
+        concatenated and stratum s owns samples [stratum_offsets[s],
+        stratum_offsets[s+1]) of ix_m / ix_n.  Returns (sums, out_offsets,
+        stat_mean, stat_std, rel_alloc): sums[out_offsets[s]:out_offsets[s+1]] are
+        the plain sums of f and of its derivatives over stratum s."""
+        x = capi.as_f64(np.asarray(x_k, dtype=np.float64))
+        if len(x) != self.desc.n_param_k(k):
+            raise ValueError('x_k has %d entries, expected %d' % (len(x), self.desc.n_param_k(k)))
+        n_terms = len(terms)
+        arr = (capi.SampleTerm * max(n_terms, 1))()
+        n_strata, out_offsets = 0, [0]
+        for q, (kind, i, j, ns) in enumerate(terms):
+            arr[q].kind, arr[q].i, arr[q].j, arr[q].n_strata = int(kind), int(i), int(j), int(ns)
+            n_out = self.sampled_n_out(k, kind, i, j)
+            for _ in range(int(ns)):
+                out_offsets.append(out_offsets[-1] + n_out)
+            n_strata += int(ns)
+        offs = np.ascontiguousarray(stratum_offsets, dtype=np.int64)
+        if len(offs) != n_strata + 1:
+            raise ValueError('stratum_offsets must have n_strata + 1 entries')
+        m = np.ascontiguousarray(ix_m, dtype=np.int64)
+        n = None if ix_n is None else np.ascontiguousarray(ix_n, dtype=np.int64)
+        if len(m) != offs[-1] or (n is not None and len(n) != len(m)):
+            raise ValueError('sample arrays do not match stratum_offsets')
+        sums = np.zeros(out_offsets[-1], dtype=np.float64)
+        stat_mean = np.zeros(n_strata, dtype=np.float64)
+        stat_std = np.zeros(n_strata, dtype=np.float64)
+        with_alloc = strata_sizes is not None
+        sizes = capi.as_f64(strata_sizes) if with_alloc else None
+        dflt = capi.as_f64(default_alloc) if with_alloc else None
+        rel = np.zeros(n_strata, dtype=np.float64) if with_alloc else None
+        flags = capi.ASLSD_F | (capi.ASLSD_DIFF if compute_diff_f_sum else 0) | \
+            (capi.ASLSD_GRAD_ALLOC if grad_alloc else 0)
+        self._check(self._lib.aslsd_sampled_sums(
+            self._ctx, int(k), capi.ptr_f64(x), flags, n_terms, arr, capi.ptr_i64(offs),
+            capi.ptr_i64(m), capi.ptr_i64(n) if n is not None else None,
+            capi.ptr_f64(sizes) if with_alloc else None,
+            capi.ptr_f64(dflt) if with_alloc else None,
+            capi.ptr_f64(sums), capi.ptr_f64(stat_mean), capi.ptr_f64(stat_std),
+            capi.ptr_f64(rel) if with_alloc else None))
+        return sums, np.asarray(out_offsets, dtype=np.int64), stat_mean, stat_std, rel
+
+    def update_allocation(self, strata_sizes, stat_std, default_alloc):
+        sizes, std, dflt = (capi.as_f64(a) for a in (strata_sizes, stat_std, default_alloc))
+        out = np.zeros(len(sizes), dtype=np.float64)
+        self._check(self._lib.aslsd_update_allocation(self._ctx, len(sizes), capi.ptr_f64(sizes),
+                                                      capi.ptr_f64(std), capi.ptr_f64(dflt),
+                                                      capi.ptr_f64(out)))
+        return out
+
+    # ---- binding to a path / model (shared by the d estimators of a fit) -------------
+    def bind(self, process_path, model):
+        """Upload the events of ``process_path`` and describe ``model`` unless this
+        engine already holds them (the d estimators of a fit share one engine)."""
+        key = (id(process_path.list_times), float(process_path.T_f),
+               tuple(len(t) for t in process_path.list_times))
+        if getattr(self, '_events_key', None) != key:
+            self.set_events(process_path.list_times, process_path.T_f)
+            self._events_key = key
+            self._events_ref = process_path.list_times   # keeps id() unique
+        if getattr(self, '_model_ref', None) is not model:
+            self.set_model(model)
+            self._model_ref = model
+        return self.desc
 
     # split form (multi-GPU): raw accumulators stay on the device
     def exact_raw_len(self, k):

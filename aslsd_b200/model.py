@@ -17,6 +17,8 @@ import numpy as np
 from aslsd_b200 import capi
 
 _N_VARS = {'ExponentialKernel': 2, 'GaussianKernel': 3}
+# get_var_lower_bounds of basis_kernel_exponential.py:366-367 / basis_kernel_gaussian.py:426-427
+_LOWER_BOUNDS = {'ExponentialKernel': [1e-10, 1e-10], 'GaussianKernel': [1e-8, 1e-8, 0.]}
 _TYPE_ID = {'ExponentialKernel': capi.BASIS_EXPONENTIAL,
             'GaussianKernel': capi.BASIS_GAUSSIAN}
 _SHORT = {'exp': 'ExponentialKernel', 'gauss': 'GaussianKernel'}
@@ -73,6 +75,10 @@ class MHP:
     models/hawkes/linear/mhp.py:216-299."""
 
     def __init__(self, _kernel_matrix):
+        if isinstance(_kernel_matrix, dict):
+            # plain description {'d', 'kernels'}: build the mirror objects
+            _kernel_matrix = [[KernelModel([_basis_from_plain(b) for b in ker]) for ker in row]
+                              for row in _kernel_matrix['kernels']]
         self._kernel_matrix = [list(row) for row in _kernel_matrix]
         self.d = len(self._kernel_matrix)
         self.desc = describe_model(self)
@@ -85,6 +91,81 @@ class MHP:
         estimator.matrix_n_param = self.matrix_n_param
         estimator.ix_map = self.ix_map
         estimator.interval_map = self.interval_map
+
+    def lower_bounds(self, k):
+        """Lower bounds of x_k: 1e-10 for mu_k (mhp.py:1701), then the free
+        variables' bounds of every basis kernel."""
+        out = [1e-10]
+        for i in range(self.d):
+            for type_name, free_mask, _ in self.desc.bases[k][i]:
+                out += [b for v, b in enumerate(_LOWER_BOUNDS[type_name]) if (free_mask >> v) & 1]
+        return np.array(out)
+
+    def fit(self, process_path, x_0, n_iter=1000, solvers=None, solver_args=None,
+            exact_grad=False, estimators=None, is_log_lse=False, is_grad_target=False,
+            is_log_ixs=False, is_log_allocs=False, is_log_total_estimates=False,
+            is_log_strata_estimates=False, n_exact_single=None,
+            n_samples_adaptive_single=None, nonadaptive_sample_size_single=None,
+            single_strfs=None, n_samples_adaptive_double=None,
+            nonadaptive_sample_size_double=None, double_strfs=None, rng=None, seed=1234,
+            engine=None, callback=None):
+        """The estimator / solver loop of MHP.fit (mhp.py:1609-1804) for an
+        explicit starting point ``x_0`` (list of d parameter vectors): for each
+        dimension k, n_iter[k] iterations of gradient estimate -> solver step ->
+        projection on the parameter bounds, all k sharing one RNG.  Returns
+        ``(x, log)`` with ``log['param'][k]`` / ``log['grad'][k]`` the iterates."""
+        from aslsd_b200.estimators import MHPExactEstimB200, MHPStratEstimB200
+        from aslsd_b200.solvers import ADAM
+        d = self.d
+        if rng is None:
+            rng = np.random.default_rng(seed)
+        if not isinstance(n_iter, (list, np.ndarray)):
+            n_iter = [n_iter] * d
+        if estimators is None:
+            cls = MHPExactEstimB200 if exact_grad else MHPStratEstimB200
+            estimators = [cls(is_grad_target=is_grad_target, is_log_ixs=is_log_ixs,
+                              is_log_allocs=is_log_allocs,
+                              is_log_total_estimates=is_log_total_estimates,
+                              is_log_strata_estimates=is_log_strata_estimates,
+                              is_log_lse=is_log_lse, engine=engine) for _ in range(d)]
+        for k in range(d):
+            estimators[k].initialize(
+                k, n_iter[k], self, process_path, n_exact_single=n_exact_single,
+                n_samples_adaptive_single=n_samples_adaptive_single,
+                nonadaptive_sample_size_single=nonadaptive_sample_size_single,
+                single_strfs=single_strfs, n_samples_adaptive_double=n_samples_adaptive_double,
+                nonadaptive_sample_size_double=nonadaptive_sample_size_double,
+                double_strfs=double_strfs)
+        if solvers is None:
+            solvers = [ADAM(**(solver_args or {})) for _ in range(d)]
+        log = {'param': [], 'grad': []}
+        x = [None] * d
+        for k in range(d):
+            x_k = np.asarray(x_0[k], dtype=np.float64)
+            lower = self.lower_bounds(k)
+            params = np.zeros((n_iter[k] + 1, len(x_k)))
+            grads = np.zeros((n_iter[k], len(x_k)))
+            params[0] = x_k
+            for t in range(n_iter[k]):
+                g_t = estimators[k].lse_k_grad_estimate(x_k, rng=rng, grad_alloc=is_grad_target)
+                grads[t] = g_t
+                x_k = np.clip(solvers[k].iterate(t, x_k, g_t), lower, np.inf)
+                params[t + 1] = x_k
+                if callback is not None:
+                    callback(k, t, x_k, g_t)
+            log['param'].append(params)
+            log['grad'].append(grads)
+            x[k] = x_k
+        self.fit_estim = estimators
+        self.fitted_x = x
+        return x, log
+
+
+def _basis_from_plain(b):
+    cls = {'exp': ExponentialKernel, 'gauss': GaussianKernel}[b['type']]
+    fixed = b.get('fixed', {})
+    ixs = sorted(fixed)
+    return cls(fixed_indices=ixs, fixed_vars=[fixed[v] for v in ixs])
 
 
 class ModelDesc:

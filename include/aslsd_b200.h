@@ -127,28 +127,46 @@ int aslsd_exact_assemble(aslsd_ctx* ctx, int k, const double* x_k, int flags,
 int aslsd_last_eval_counts(aslsd_ctx* ctx, int64_t* pair_evals, int64_t* single_evals);
 
 /* ---- sampled sums: replaces the bodies of MHPStratEstim.estimate_sum_* ------------
- * optimize/estimators/mhp_stratified_estimator.py:534-900 for one term.
+ * optimize/estimators/mhp_stratified_estimator.py:534-900, for every term of one
+ * compute_objective call (:1333-1386) in a single launch.
  * The (m, n) samples are generated on the host by the reference's own RNG code
- * (utilities/useful_statistics.py:38-127) and consumed here unchanged.
- *   term_kind: 0 psi_i, 1 upsilonzero_i, 2 phi_i, 3 upsilon_i_j (i == j allowed)
- *   stratum_offsets: n_strata + 1 offsets into ix_m / ix_n
+ * (utilities/useful_statistics.py:38-127) and consumed here unchanged; the index
+ * -> time transforms are those of the compute_*_sum closures (:1097-1100,
+ * :1148-1151, :1196-1203, :1245-1252, :1300-1307).
+ *   terms[q]: a named term and the number of its strata in this batch; strata
+ *             of all terms are concatenated in order.
+ *     kind: 0 psi_i, 1 upsilonzero_i, 2 phi_i, 3 upsilon_i_j (i == j allowed)
+ *   stratum_offsets: n_strata_total + 1 offsets into ix_m / ix_n
  *   ix_n is ignored for single-index terms (psi, upsilonzero)
- * Outputs, per stratum s (n_out = 1 + n1 + n2 as in aslsd_exact_sums):
- *   mean_out[s*n_out + c]   mean over the stratum's samples of f (c = 0) and of
- *                           every derivative (numpy.mean)
+ * Per stratum s of a term with n_out = 1 + n1 + n2 outputs (as in aslsd_exact_sums;
+ * aslsd_sampled_n_out):
+ *   sum_out[off_s + c]      plain sum over the stratum's samples of f (c = 0) and
+ *                           of every derivative; off_s = running sum of n_out
+ *                           (the mean numpy.mean is sum / count)
  *   stat_mean[s], stat_std[s]  mean and population std (numpy.std, ddof = 0) of
  *                           the allocation statistic: f, or ||grad f||_2 when
  *                           ASLSD_GRAD_ALLOC is set (:605-635)
- *   sum_out[s*n_out + c]    plain sums (used by the exact domain, :856-900) */
-int aslsd_sampled_sums(aslsd_ctx* ctx, int k, const double* x_k, int term_kind,
-                       int i, int j, int flags, int n_strata,
-                       const int64_t* stratum_offsets, const int64_t* ix_m,
-                       const int64_t* ix_n, double* mean_out, double* sum_out,
-                       double* stat_mean, double* stat_std);
+ * Fused allocation update (:637-645), when strata_sizes, default_alloc and
+ * rel_alloc are given: maximal runs of consecutive strata of a term with
+ * strata_sizes[s] > 0 form one adaptive group;
+ *   rel_alloc[s] = size_s * sqrt(size_s / (size_s - 1)) * std_s, normalised over
+ * the group, or default_alloc[s] when every std of the group is zero.  Strata
+ * outside any group get default_alloc[s]. */
+typedef struct {
+  int32_t kind;
+  int32_t i, j;
+  int32_t n_strata;
+} aslsd_sample_term;
 
-/* Fused allocation update of estimate_sum_adaptivedom (:637-645):
- * rel_alloc[s] = size_s * sqrt(size_s / (size_s - 1)) * std_s, normalised;
- * if every std is zero the default allocation is returned. */
+int aslsd_sampled_n_out(const aslsd_ctx* ctx, int k, int term_kind, int i, int j, int32_t* n_out);
+int aslsd_sampled_sums(aslsd_ctx* ctx, int k, const double* x_k, int flags, int n_terms,
+                       const aslsd_sample_term* terms, const int64_t* stratum_offsets,
+                       const int64_t* ix_m, const int64_t* ix_n, const double* strata_sizes,
+                       const double* default_alloc, double* sum_out, double* stat_mean,
+                       double* stat_std, double* rel_alloc);
+
+/* Stand-alone allocation update of estimate_sum_adaptivedom (:637-645) for one
+ * group of strata. */
 int aslsd_update_allocation(aslsd_ctx* ctx, int n_strata, const double* strata_sizes,
                             const double* stat_std, const double* default_alloc,
                             double* rel_alloc_out);

@@ -10,6 +10,8 @@ for p in (ROOT, os.path.join(ROOT, 'tests'), os.path.join(ROOT, 'tests', 'golden
 
 
 def pytest_configure(config):
+    import ref_shim
+    ref_shim.make_importable()   # before aslsd_b200 is imported (see ref_shim)
     config.addinivalue_line('markers', 'gpu: needs a CUDA device (run on the B200 box)')
     config.addinivalue_line('markers', 'reference: needs the read-only reference tree '
                             '(/root/reference); skipped where it is absent')

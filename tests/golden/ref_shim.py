@@ -19,20 +19,32 @@ def reference_available():
     return os.path.isdir(os.path.join(REFERENCE_ROOT, 'optimize'))
 
 
+_shim_dir = None
+
+
+def make_importable():
+    """Put ``aslsd`` (the reference) on sys.path and stub matplotlib; no import
+    happens here.  Called from tests/conftest.py before ``aslsd_b200`` is first
+    imported, so that the B200 estimators can derive from the reference's ABC."""
+    global _shim_dir
+    if _shim_dir is not None or not reference_available():
+        return
+    for name in ('matplotlib', 'matplotlib.pyplot', 'matplotlib.animation',
+                 'matplotlib.ticker'):
+        if name not in sys.modules:
+            mod = types.ModuleType(name)
+            mod.__path__ = []
+            sys.modules[name] = mod
+    _shim_dir = tempfile.mkdtemp(prefix='aslsd_ref_')
+    os.symlink(REFERENCE_ROOT, os.path.join(_shim_dir, 'aslsd'))
+    sys.path.insert(0, _shim_dir)
+
+
 def import_reference():
     """Returns a namespace with the reference classes used by the tests."""
     if not reference_available():
         raise ImportError('reference tree not present at %s' % REFERENCE_ROOT)
-    if 'aslsd' not in sys.modules:
-        for name in ('matplotlib', 'matplotlib.pyplot', 'matplotlib.animation',
-                     'matplotlib.ticker'):
-            if name not in sys.modules:
-                mod = types.ModuleType(name)
-                mod.__path__ = []
-                sys.modules[name] = mod
-        shim_dir = tempfile.mkdtemp(prefix='aslsd_ref_')
-        os.symlink(REFERENCE_ROOT, os.path.join(shim_dir, 'aslsd'))
-        sys.path.insert(0, shim_dir)
+    make_importable()
     import warnings
     with warnings.catch_warnings():
         warnings.simplefilter('ignore')

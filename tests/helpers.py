@@ -43,3 +43,83 @@ def assert_sums_close(sum_f, sum_diff_f, golden, prefix, rtol=RTOL, atol=0.0):
                 float(np.max(err / np.maximum(np.abs(ref), 1e-300)))))
         worst = max(worst, float(np.max(err / np.maximum(np.abs(ref), 1e-300))))
     return worst
+
+
+# ---- stratified golden traces (tests/golden/make_golden_strat.py) ---------------------------
+def _flat_terms(est):
+    f = np.array([est.sum_f[name] for name in sorted(est.sum_f)], dtype=float)
+    parts = []
+    for name in sorted(est.sum_diff_f):
+        v = est.sum_diff_f[name]
+        parts += [np.ravel(v[1]), np.ravel(v[2])] if isinstance(v, list) else [np.ravel(v)]
+    return f, np.concatenate(parts).astype(float)
+
+
+def _flat_allocs(est):
+    out = [np.asarray(est.stratif[name].adaptive_rel_alloc, dtype=float)
+           for name in sorted(est.stratif) if est.stratif[name].n_adaptive_strata > 0]
+    return np.concatenate(out)
+
+
+def replay_strat_golden(name, engine, free_running=False, rtol=RTOL):
+    """Teacher-forced replay of a reference ASLSD trace: at every iteration the
+    estimator is evaluated at the reference's own iterate with the same seeded
+    Generator; per-term sums, gradient, LSE and adaptive allocations must match.
+    The RNG stream only stays aligned if every integer sample allocation is
+    identical, which the final generator state certifies.
+    ``free_running``: additionally take the ADAM steps from the computed
+    gradients and compare the trajectory (looser: errors feed back)."""
+    import aslsd_b200
+    from cases import CASES
+    g = load_golden(name)
+    case = str(g['case'])
+    model = CASES[case][0]
+    d = int(g['d'])
+    times = [np.asarray(g['times/%d' % i]) for i in range(d)]
+    T_f = float(g['T_f'])
+    kw = {str(k): int(v) for k, v in zip(g['kw_names'], g['kw_values'])}
+    n_iter = int(g['n_iter'])
+    grad_alloc = bool(g['grad_alloc'])
+    mirror = aslsd_b200.MHP(model)
+    path = aslsd_b200.ProcessPath(times, T_f, engine=engine) if hasattr(engine, 'index_maps') \
+        else _oracle_path(times, T_f)
+    rng = np.random.default_rng(int(g['seed']))
+    worst = 0.
+    for k in range(d):
+        est = aslsd_b200.MHPStratEstimB200(is_log_lse=True, engine=engine)
+        est.initialize(k, n_iter, mirror, path, **kw)
+        solver = aslsd_b200.ADAM()
+        lower = mirror.lower_bounds(k)
+        x_free = g['k%d/x' % k][0].copy()
+        for t in range(n_iter):
+            x_t = g['k%d/x' % k][t]
+            grad = est.lse_k_grad_estimate(x_t, rng=rng, grad_alloc=grad_alloc)
+            f, df = _flat_terms(est)
+            ref_f, ref_df = g['k%d/sum_f' % k][t], g['k%d/sum_diff_f' % k][t]
+            scale = np.abs(ref_df).max()
+            np.testing.assert_allclose(f, ref_f, rtol=rtol, atol=0., err_msg='%s k%d t%d sum_f' % (name, k, t))
+            np.testing.assert_allclose(df, ref_df, rtol=rtol, atol=1e-12 * scale,
+                                       err_msg='%s k%d t%d sum_diff_f' % (name, k, t))
+            np.testing.assert_allclose(grad, g['k%d/grad' % k][t], rtol=rtol, atol=rtol * scale / T_f,
+                                       err_msg='%s k%d t%d grad' % (name, k, t))
+            np.testing.assert_allclose(_flat_allocs(est), g['k%d/allocs' % k][t], rtol=1e-9, atol=1e-15,
+                                       err_msg='%s k%d t%d allocations' % (name, k, t))
+            worst = max(worst, float(np.max(np.abs(f - ref_f) / np.maximum(np.abs(ref_f), 1e-300))))
+            if free_running:
+                x_free = np.clip(solver.iterate(t, x_free, grad), lower, np.inf)
+                np.testing.assert_allclose(x_free, g['k%d/x' % k][t + 1], rtol=1e-7)
+        np.testing.assert_allclose(est.logged_lse, g['k%d/logged_lse' % k], rtol=rtol)
+    assert str(rng.bit_generator.state) == str(g['rng_final']), 'RNG stream diverged from the reference'
+    return worst
+
+
+def _oracle_path(times, T_f):
+    """ProcessPath-like container whose index maps come from the oracle (CPU tests)."""
+    import types
+    from oracle import time_ordering as OT
+    kappa, varpi = OT.kappa_varpi_closed_form(times, T_f)
+    return types.SimpleNamespace(
+        list_times=times, list_marks=None, T_f=T_f, d=len(times),
+        n_events=np.array([len(t) for t in times]), eta=np.array([len(t) for t in times]) / T_f,
+        list_times2end=[T_f - t for t in times], kappa=kappa, varpi=varpi,
+        lag_sizes=OT.lag_sizes(times, kappa, varpi))

@@ -1,0 +1,134 @@
+"""Parity of the sampled-lag kernel and the fused allocation update (CUDA,
+through the C ABI) against the stratified oracle and against golden traces of
+the reference's MHPStratEstim.  Tolerance: relative 1e-10 (fp64)."""
+import numpy as np
+import pytest
+
+from cases import CASES, case_x
+from helpers import RTOL, replay_strat_golden
+from oracle import stratified as OS
+
+pytestmark = pytest.mark.gpu
+
+NAMES = ['strat_exp1d', 'strat_exp2d', 'strat_exp2d_gradalloc', 'strat_gauss1d', 'strat_sbf2d3']
+
+
+@pytest.fixture(scope='module')
+def engine():
+    import aslsd_b200
+    return aslsd_b200.Engine(0)
+
+
+@pytest.mark.parametrize('name', NAMES)
+def test_replay_reference_trace_on_device(engine, name):
+    worst = replay_strat_golden(name, engine, free_running=(name == 'strat_exp1d'))
+    assert worst <= RTOL
+
+
+def _random_batch(rng, times, k, d, n_strata, n_per):
+    """Random (m, n) samples for every term kind, far lags included."""
+    terms, offsets, ms, ns = [], [0], [], []
+    for kind, i, j in [(0, 0, 0), (1, d - 1, d - 1), (2, 0, 0), (2, d - 1, d - 1), (3, 0, 0),
+                       (3, 0, d - 1), (3, d - 1, 0)]:
+        tgt, src = (k, i) if kind == 2 else (i, j)
+        terms.append((kind, i, j, n_strata))
+        for s in range(n_strata):
+            n_s = int(rng.integers(1, n_per))
+            m = rng.integers(1, len(times[tgt]), size=n_s)
+            if kind < 2:
+                n = np.zeros(n_s, dtype=np.int64)
+            else:
+                hi = np.searchsorted(times[src], times[tgt][m], side='left')
+                hi = np.maximum(hi, 1)
+                lag = rng.integers(1, 40 if s % 2 == 0 else 2000, size=n_s)
+                n = np.maximum(hi - lag, 0)
+            ms.append(m)
+            ns.append(n)
+            offsets.append(offsets[-1] + n_s)
+    return terms, np.array(offsets), np.concatenate(ms), np.concatenate(ns)
+
+
+@pytest.mark.parametrize('name', ['exp2d', 'gauss2d', 'sbf2d3', 'exp1d2b', 'gauss1d2b', 'sbf1d10'])
+@pytest.mark.parametrize('grad_alloc', [False, True])
+def test_sampled_sums_match_oracle(engine, name, grad_alloc):
+    model = CASES[name][0]
+    d = model['d']
+    rng = np.random.default_rng(11)
+    T_f = 3000.
+    times = [np.sort(rng.uniform(0, T_f, size=4000 + 500 * i)) for i in range(d)]
+    # a few targets close to T_f exercise the non-interior branches
+    for i in range(d):
+        times[i][-5:] = T_f - np.array([2.0, 1.0, 0.3, 0.05, 0.001]) * (1 + i)
+        times[i].sort()
+    engine.set_events(times, T_f)
+    engine.set_model(model)
+    for k in range(d):
+        x = case_x(name)[k]
+        terms, offsets, ix_m, ix_n = _random_batch(rng, times, k, d, n_strata=4, n_per=300)
+        n_strata = len(offsets) - 1
+        sizes = np.where(np.arange(n_strata) % 4 < 2, rng.integers(2, 10 ** 6, size=n_strata), 0).astype(float)
+        dflt = rng.uniform(size=n_strata)
+        sums, out_off, mean, std, rel = engine.sampled_sums(
+            k, x, terms, offsets, ix_m, ix_n, strata_sizes=sizes, default_alloc=dflt,
+            compute_diff_f_sum=True, grad_alloc=grad_alloc)
+        s_ix = 0
+        for kind, i, j, ns in terms:
+            for s in range(ns):
+                a, b = offsets[s_ix], offsets[s_ix + 1]
+                vals = OS.term_values(model, k, x, times, T_f, kind, i, j, ix_m[a:b], ix_n[a:b])
+                tot, o_mean, o_std = OS.stratum_statistics(vals, grad_alloc)
+                got = sums[out_off[s_ix]:out_off[s_ix + 1]]
+                scale = np.abs(vals).sum(axis=0)
+                assert np.all(np.abs(got - tot) <= RTOL * np.abs(tot) + 1e-13 * scale), (kind, i, j, s)
+                assert abs(mean[s_ix] - o_mean) <= RTOL * abs(o_mean) + 1e-300
+                assert abs(std[s_ix] - o_std) <= 1e-9 * abs(o_std) + 1e-14 * abs(o_mean)
+                s_ix += 1
+        # allocation groups: strata 0-1 of every term
+        for q in range(len(terms)):
+            a = 4 * q
+            want = OS.update_allocation(sizes[a:a + 2], std[a:a + 2], dflt[a:a + 2])
+            np.testing.assert_allclose(rel[a:a + 2], want, rtol=1e-12)
+            np.testing.assert_array_equal(rel[a + 2:a + 4], dflt[a + 2:a + 4])
+
+
+def test_update_allocation_entry_point(engine):
+    sizes = np.array([10., 200., 3000., 2.])
+    std = np.array([0.5, 0.1, 0.01, 3.])
+    dflt = np.array([.25, .25, .25, .25])
+    got = engine.update_allocation(sizes, std, dflt)
+    np.testing.assert_allclose(got, OS.update_allocation(sizes, std, dflt), rtol=1e-14)
+    # every std zero -> previous allocation kept (mhp_stratified_estimator.py:641-645)
+    np.testing.assert_array_equal(engine.update_allocation(sizes, np.zeros(4), dflt), dflt)
+    # a stratum of size 1 gives inf * 0 = nan upstream -> default allocation
+    np.testing.assert_array_equal(engine.update_allocation(np.array([1., 5.]), np.array([0., 1.]),
+                                                           np.array([.3, .7])), [.3, .7])
+
+
+def test_sampled_sums_reject_bad_indices(engine):
+    import aslsd_b200
+    rng = np.random.default_rng(0)
+    times = [np.sort(rng.uniform(0, 100, size=50))]
+    engine.set_events(times, 100.)
+    engine.set_model(CASES['exp1d'][0])
+    x = case_x('exp1d')[0]
+    with pytest.raises(aslsd_b200.EngineError):
+        engine.sampled_sums(0, x, [(3, 0, 0, 1)], [0, 2], [3, 50], [1, 2])
+    with pytest.raises(aslsd_b200.EngineError):
+        engine.sampled_sums(0, x, [(2, 0, 0, 1)], [0, 2], [3, 4], [-1, 2])
+    with pytest.raises(aslsd_b200.EngineError):
+        engine.sampled_sums(0, x, [(7, 0, 0, 1)], [0, 1], [3], [1])
+
+
+def test_mirror_fit_runs_on_device(engine):
+    """End-to-end ASLSD fit loop (host mirror + CUDA): the iterates follow the
+    reference's trajectory of the golden trace."""
+    import aslsd_b200
+    from helpers import load_golden
+    g = load_golden('strat_exp1d')
+    times = [np.asarray(g['times/0'])]
+    path = aslsd_b200.ProcessPath(times, float(g['T_f']), engine=engine)
+    model = aslsd_b200.MHP(CASES['exp1d'][0])
+    n_iter = int(g['n_iter'])
+    x, log = model.fit(path, [g['k0/x'][0]], n_iter=n_iter, seed=int(g['seed']), engine=engine)
+    np.testing.assert_allclose(log['param'][0], g['k0/x'], rtol=1e-7)
+    np.testing.assert_allclose(log['grad'][0], g['k0/grad'], rtol=1e-6, atol=1e-9)

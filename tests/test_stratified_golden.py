@@ -1,0 +1,51 @@
+"""Host-side ASLSD logic against the reference's golden traces (CPU).
+
+The estimator, stratification, sampling and solver mirrors of aslsd_b200 are
+driven with the oracle test double in place of the device
+(tests/oracle_engine.py): what is pinned here is the host logic and the
+stratified oracle itself; tests/test_gpu_stratified.py replays the same traces
+through the CUDA engine."""
+import numpy as np
+import pytest
+
+from helpers import replay_strat_golden
+from oracle_engine import OracleEngine
+
+NAMES = ['strat_exp1d', 'strat_exp2d', 'strat_exp2d_gradalloc', 'strat_gauss1d', 'strat_sbf2d3']
+
+
+@pytest.mark.parametrize('name', NAMES)
+def test_replay_reference_trace(name):
+    replay_strat_golden(name, OracleEngine(), free_running=(name == 'strat_exp1d'))
+
+
+def test_stratification_defaults_match_survey_geometry():
+    """Default geometry at N = 10^6 (measured on the reference)."""
+    import aslsd_b200
+    n = 1_000_000
+    s = aslsd_b200.GeneralStratification(n=n)
+    assert s.n_exact == 1000 and s.exact_domain[0] == n - 1000 and s.exact_domain[-1] == n - 1
+    assert s.n_adaptive_strata == 10 and s.adaptive_strata[-1][1] == n - 1001
+    assert list(s.adaptive_strata_sizes) == [1000] * 9 + [1001]
+    assert s.n_nonadaptive_strata == 10 and s.nonadaptive_strata[0][0] == 0
+    assert s.nonadaptive_strata[-1][1] == s.adaptive_strata[0][0] - 1
+    assert list(s.nonadaptive_abs_alloc) == [1000] * 10
+    assert s.ema_weight == .6 and np.isclose(s.adaptive_rel_alloc.sum(), 1.)
+    dstr = aslsd_b200.DoubleIxStratification(h_max=999_999)
+    assert [list(h) for h in dstr.adaptive_strata] == [[h, h] for h in range(1, 30)]
+    assert dstr.nonadaptive_strata[0][0] == 30 and dstr.nonadaptive_strata[-1][1] == 999_999
+    assert len(dstr.nonadaptive_strata) == 9
+    lag_sizes = [[np.concatenate([[0], n - np.arange(1, n)])]]
+    dstr.get_stratification_size(lag_sizes, 0, 0)
+    assert list(dstr.nonadaptive_abs_alloc) == [1111] * 9
+    assert dstr.n_samples_adaptive[0] == 10 ** 4
+
+
+def test_estimator_pickle_drops_device_handle():
+    import pickle
+    import aslsd_b200
+    est = aslsd_b200.MHPStratEstimB200(engine=OracleEngine())
+    clone = pickle.loads(pickle.dumps(est))
+    assert clone.engine is None and clone.t == 0
+    with pytest.raises(RuntimeError):
+        clone._bound_engine()
