@@ -165,14 +165,16 @@ __device__ __forceinline__ void eval_ups_exp(const UpsExpConst& K, int mask, dou
   const double e = exp(-K.b2 * s);
   double E = 0., omE = 1.;
   if (!INTERIOR) { E = exp(-K.bsum * t); omE = 1. - E; }
-  acc[C_G] += K.pr * e * omE;
+  // pr = beta1 beta2 / (beta1 + beta2) is folded into the host-side coefficient so
+  // that omega1 omega2 pr * (e (1 - E)) associates like the reference's expression
+  acc[C_G] += e * omE;
   if (mask & MASK(C_B1)) acc[C_B1] += e * (K.sh1 * omE + K.pr * t * E);
   if (mask & MASK(C_B2)) acc[C_B2] += e * (K.sh2 * omE + K.pr * ((t + s) * E - s));
   if (mask & (MASK(C_SW) | MASK(C_SB))) {
     const double eo = (mask & MASK_OWN_SAME) ? e : exp(-K.bo * s);
     double E2 = 0.;
     if (!INTERIOR) E2 = exp(-2. * K.bo * t);
-    if (mask & MASK(C_SW)) acc[C_SW] += K.bo * eo * (1. - E2);
+    if (mask & MASK(C_SW)) acc[C_SW] += eo * (1. - E2);   // omega beta folded into the coefficient
     if (mask & MASK(C_SB)) acc[C_SB] += 0.5 * eo * (1. - K.bo * s + E2 * (K.bo * (2. * t + s) - 1.));
   }
 }

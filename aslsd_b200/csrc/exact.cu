@@ -102,8 +102,8 @@ static void assemble(const aslsd_ctx* ctx, const SumPlan& P, const double* x_k, 
   for (int64_t c = 0; c < P.out_len; ++c) out[c] = 0.;
   for (size_t t = 0; t < P.terms.size(); ++t) {
     double* o = out + P.terms[t].out_off;
-    emit_term(ctx, P, t, x_k, [&](int c, int item, int comp, double coef) {
-      o[c] += coef * raw[(size_t)item * ASLSD_MAX_COMP + comp];
+    emit_term(ctx, P, t, x_k, [&](int c, int item, int comp, double coef, double outer) {
+      o[c] += outer * (coef * raw[(size_t)item * ASLSD_MAX_COMP + comp]);
     });
   }
 }

@@ -42,8 +42,12 @@ int build_plan(aslsd_ctx* ctx, int k, const double* x_k, int flags, const int64_
 int find_term(const aslsd_ctx* ctx, int kind, int i, int j);
 
 // Linear map raw components -> packed outputs of one term.  The sink is called
-// as sink(c, item, comp, coef): output c of the term (0 = function value,
-// 1.. = derivatives) receives coef * raw[item][comp]; item < 0 never reaches it.
+// as sink(c, item, comp, coef, outer): output c of the term (0 = function value,
+// 1.. = derivatives) receives outer * (coef * raw[item][comp]); item < 0 never
+// reaches it.  The two-level product follows the reference's association
+// (e.g. psi term: mu_k * (omega * (1 - e^{-beta t})), mhp_stratified_estimator.py
+// :1106-1108) so that per-sample values of near-constant strata come out
+// bit-identical and numpy's rounding residue in np.std is reproduced.
 template <class Sink>
 void emit_term(const aslsd_ctx* ctx, const SumPlan& P, size_t t, const double* x_k, Sink&& sink) {
   const int d = ctx->d;
@@ -53,10 +57,13 @@ void emit_term(const aslsd_ctx* ctx, const SumPlan& P, size_t t, const double* x
   const KernelHost& KU = ctx->kernels[d * d - 1];
   const TermPlan& T = P.terms[t];
   const int voff = P.term_val_off[t], doff = P.term_der_off[t];
-  auto put = [&](int c, int off, int slot, int comp, double coef) {
+  auto put = [&](int c, int off, int slot, int comp, double coef, double outer = 1.) {
     const int idx = P.slot_item[off + slot];
-    if (idx >= 0) sink(c, idx, comp, coef);
+    if (idx >= 0) sink(c, idx, comp, coef, outer);
   };
+  const bool ups_exp = KU.bases[0].type == ASLSD_BASIS_EXPONENTIAL;
+  // exponential upsilon: beta1 beta2 / (beta1 + beta2) multiplies every C_G component
+  auto prat = [&](const Vars& a, const Vars& b) { return ups_exp ? (a[1] * b[1]) / (a[1] + b[1]) : 1.; };
   if (T.kind == 0 || T.kind == 2) {
     // psi_i / phi_i: one item per basis of K[k][i]
     const KernelHost& K = ctx->kernels[k * d + T.i];
@@ -75,11 +82,11 @@ void emit_term(const aslsd_ctx* ctx, const SumPlan& P, size_t t, const double* x
         if (is_exp) { cv = w; cw = 1.; cb = w; }
         else { cv = w; cw = 1.; cb = w / (be * be); cd = -(w / be); }
       }
-      put(0, voff, (int)r, 0, scale * cv);
+      put(0, voff, (int)r, 0, cv, scale);
       if (T.kind == 0) put(1 + T.n1, voff, (int)r, 0, cv);   // d/d mu_k (ix_func 2)
       for (int v = 0; v < b.n_vars(); ++v) {
         if (!((b.free_mask >> v) & 1)) continue;
-        if (diff) put(1 + slot, voff, (int)r, v, scale * (v == 0 ? cw : (v == 1 ? cb : cd)));
+        if (diff) put(1 + slot, voff, (int)r, v, v == 0 ? cw : (v == 1 ? cb : cd), scale);
         ++slot;
       }
     }
@@ -89,7 +96,8 @@ void emit_term(const aslsd_ctx* ctx, const SumPlan& P, size_t t, const double* x
   if (T.kind == 3 && T.i != T.j) {
     const std::vector<Vars>&V1 = P.VU[T.i], &V2 = P.VU[T.j];
     for (int p = 0; p < Rn; ++p)
-      for (int q = 0; q < Rn; ++q) put(0, voff, p * Rn + q, C_G, V1[p][0] * V2[q][0]);
+      for (int q = 0; q < Rn; ++q)
+        put(0, voff, p * Rn + q, C_G, V1[p][0] * V2[q][0] * prat(V1[p], V2[q]));
     if (!diff) return;
     int slot = 0;
     for (int p = 0; p < Rn; ++p)
@@ -98,7 +106,8 @@ void emit_term(const aslsd_ctx* ctx, const SumPlan& P, size_t t, const double* x
         const int c = v == 0 ? C_G : (v == 1 ? C_B1 : C_D1);
         if (slot < T.n1)
           for (int q = 0; q < Rn; ++q)
-            put(1 + slot, voff, p * Rn + q, c, v == 0 ? V2[q][0] : V1[p][0] * V2[q][0]);
+            put(1 + slot, voff, p * Rn + q, c,
+                v == 0 ? V2[q][0] * prat(V1[p], V2[q]) : V1[p][0] * V2[q][0]);
         ++slot;
       }
     slot = 0;
@@ -108,7 +117,8 @@ void emit_term(const aslsd_ctx* ctx, const SumPlan& P, size_t t, const double* x
         const int c = v == 0 ? C_G : (v == 1 ? C_B2 : C_D2);
         if (slot < T.n2)
           for (int p = 0; p < Rn; ++p)
-            put(1 + T.n1 + slot, voff, p * Rn + q, c, v == 0 ? V1[p][0] : V1[p][0] * V2[q][0]);
+            put(1 + T.n1 + slot, voff, p * Rn + q, c,
+                v == 0 ? V1[p][0] * prat(V1[p], V2[q]) : V1[p][0] * V2[q][0]);
         ++slot;
       }
     return;
@@ -118,7 +128,7 @@ void emit_term(const aslsd_ctx* ctx, const SumPlan& P, size_t t, const double* x
   const std::vector<Vars>& VB = P.V[T.i];
   const KernelHost& KB = ctx->kernels[k * d + T.i];
   for (int p = 0; p < Rn; ++p)
-    for (int q = 0; q < Rn; ++q) put(0, voff, p * Rn + q, C_G, VA[p][0] * VA[q][0]);
+    for (int q = 0; q < Rn; ++q) put(0, voff, p * Rn + q, C_G, VA[p][0] * VA[q][0] * prat(VA[p], VA[q]));
   if (!diff) return;
   int slot = 0;
   for (int b = 0; b < Rn; ++b)
@@ -127,16 +137,16 @@ void emit_term(const aslsd_ctx* ctx, const SumPlan& P, size_t t, const double* x
       const double wb = VB[b][0];
       // own-basis closed form, then the cross terms with every other basis in
       // both slots (kernel.py:282-299)
-      if (v == 0) put(1 + slot, doff, b * Rn + b, C_SW, wb);
+      if (v == 0) put(1 + slot, doff, b * Rn + b, C_SW, ups_exp ? wb * VB[b][1] : wb);
       else put(1 + slot, doff, b * Rn + b, v == 1 ? C_SB : C_SD, wb * wb);
       for (int q = 0; q < Rn; ++q) {
         if (q == b) continue;
-        if (v == 0) put(1 + slot, doff, b * Rn + q, C_G, VB[q][0]);
+        if (v == 0) put(1 + slot, doff, b * Rn + q, C_G, VB[q][0] * prat(VB[b], VB[q]));
         else put(1 + slot, doff, b * Rn + q, v == 1 ? C_B1 : C_D1, wb * VB[q][0]);
       }
       for (int p = 0; p < Rn; ++p) {
         if (p == b) continue;
-        if (v == 0) put(1 + slot, doff, p * Rn + b, C_G, VB[p][0]);
+        if (v == 0) put(1 + slot, doff, p * Rn + b, C_G, VB[p][0] * prat(VB[p], VB[b]));
         else put(1 + slot, doff, p * Rn + b, v == 1 ? C_B2 : C_D2, VB[p][0] * wb);
       }
       ++slot;

@@ -12,10 +12,10 @@
 // one thread per sample (strided).  Per sample the thread evaluates the term's
 // work items (basis / basis-pair closed forms, basis_math.cuh) and applies the
 // linear map of plan.h to obtain the function value and every parameter
-// derivative; the per-stratum sums, the allocation statistic (f, or ||grad f||_2)
-// and its population standard deviation are reduced in the CTA.  A second tiny
-// kernel turns the standard deviations into the next relative allocation
-// (:637-645).
+// derivative; the per-stratum sums are reduced in the CTA.  The allocation
+// statistic (f, or ||grad f||_2) of every sample is kept, and two tiny kernels
+// turn it into numpy-faithful per-stratum mean / population std (:631-635) and
+// into the next relative allocation (:637-645).
 #include "basis_math.cuh"
 #include "plan.h"
 
@@ -37,7 +37,7 @@ struct SampleTermDev {
 
 struct SampleEntry {
   int32_t comp, c;
-  double coef;
+  double coef, outer;   // output c += outer * (coef * raw[comp]), each product rounded
 };
 
 struct StratumDev {
@@ -59,16 +59,71 @@ __global__ void item_const_kernel(const ItemDev* __restrict__ items, int n_items
   consts[x] = c;
 }
 
-__device__ __forceinline__ double block_sum(double v, double* s_w) {
+// numpy's float64 add.reduce (pairwise summation with 8 partial sums per block of
+// at most 128 elements; numpy/core/src/umath/loops_utils.h.src, DOUBLE_pairwise_sum)
+// restated operation for operation, so that np.mean / np.std of the reference
+// (mhp_stratified_estimator.py:631-635) are reproduced bit for bit on
+// bit-identical inputs.  The integer sample counts of the next iteration are a
+// truncation of the resulting allocations (:587), and in zero-variance strata
+// the reference's "standard deviation" is this summation's rounding residue.
+// DEV: sum of (a[i] - shift)^2, each step rounded as numpy rounds it (no FMA).
+template <bool DEV>
+__device__ double np_block_sum(const double* __restrict__ a, int64_t n, double shift) {
+  auto f = [&](int64_t i) -> double {
+    if (!DEV) return a[i];
+    const double dlt = __dsub_rn(a[i], shift);
+    return __dmul_rn(dlt, dlt);
+  };
+  if (n < 8) {
+    double res = 0.;
+    for (int64_t i = 0; i < n; ++i) res = __dadd_rn(res, f(i));
+    return res;
+  }
+  double r[8];
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-  __syncthreads();   // s_w may still be read from a previous call
-  if ((threadIdx.x & 31) == 0) s_w[threadIdx.x >> 5] = v;
-  __syncthreads();
-  double r = 0.;
+  for (int q = 0; q < 8; ++q) r[q] = f(q);
+  int64_t i;
+  for (i = 8; i < n - (n % 8); i += 8) {
 #pragma unroll
-  for (int w = 0; w < SAMP_NT / 32; ++w) r += s_w[w];
-  return r;
+    for (int q = 0; q < 8; ++q) r[q] = __dadd_rn(r[q], f(i + q));
+  }
+  double res = __dadd_rn(__dadd_rn(__dadd_rn(r[0], r[1]), __dadd_rn(r[2], r[3])),
+                         __dadd_rn(__dadd_rn(r[4], r[5]), __dadd_rn(r[6], r[7])));
+  for (; i < n; ++i) res = __dadd_rn(res, f(i));
+  return res;
+}
+
+// the recursion sum(a, n) = sum(a, n2) + sum(a + n2, n - n2), n2 = n/2 rounded down
+// to a multiple of 8, for n > 128, unrolled on an explicit stack
+template <bool DEV>
+__device__ double np_pairwise_sum(const double* __restrict__ a, int64_t n, double shift) {
+  struct Frame { int64_t off, n; int state; double left; };
+  Frame st[64];
+  int sp = 0;
+  double ret = 0.;
+  st[sp++] = Frame{0, n, 0, 0.};
+  while (sp > 0) {
+    Frame& fr = st[sp - 1];
+    if (fr.n <= 128) {
+      ret = np_block_sum<DEV>(a + fr.off, fr.n, shift);
+      --sp;
+      continue;
+    }
+    int64_t n2 = fr.n / 2;
+    n2 -= n2 % 8;
+    if (fr.state == 0) {
+      fr.state = 1;
+      st[sp++] = Frame{fr.off, n2, 0, 0.};
+    } else if (fr.state == 1) {
+      fr.left = ret;
+      fr.state = 2;
+      st[sp++] = Frame{fr.off + n2, fr.n - n2, 0, 0.};
+    } else {
+      ret = __dadd_rn(fr.left, ret);
+      --sp;
+    }
+  }
+  return ret;
 }
 
 __global__ void __launch_bounds__(SAMP_NT)
@@ -77,8 +132,7 @@ sampled_kernel(const DimDev* __restrict__ dims, const ItemDev* __restrict__ item
                const SampleEntry* __restrict__ entries, const SampleTermDev* __restrict__ terms,
                const StratumDev* __restrict__ strata, const int64_t* __restrict__ ix_m,
                const int64_t* __restrict__ ix_n, double T_f, int grad_alloc, double* __restrict__ scratch,
-               double* __restrict__ sum_out, double* __restrict__ stat_mean, double* __restrict__ stat_std) {
-  __shared__ double s_w[SAMP_NT / 32];
+               double* __restrict__ sum_out) {
   __shared__ double s_acc[(SAMP_NT / 32) * SAMP_MAX_OUT];
   const StratumDev S = strata[blockIdx.x];
   const SampleTermDev T = terms[S.term];
@@ -87,7 +141,6 @@ sampled_kernel(const DimDev* __restrict__ dims, const ItemDev* __restrict__ item
   const int n_out = T.n_out;
   double acc[SAMP_MAX_OUT], val[SAMP_MAX_OUT];
   for (int c = 0; c < n_out; ++c) acc[c] = 0.;
-  double stat_sum = 0.;
   for (int64_t x = S.begin + tid; x < S.end; x += SAMP_NT) {
     const int64_t m = ix_m[x];
     const double tm = Dt.t[m];
@@ -118,19 +171,18 @@ sampled_kernel(const DimDev* __restrict__ dims, const ItemDev* __restrict__ item
       }
       for (int e = ent_off[ix]; e < ent_off[ix + 1]; ++e) {
         const SampleEntry E = entries[e];
-        val[E.c] += E.coef * raw[E.comp];
+        val[E.c] = __dadd_rn(val[E.c], __dmul_rn(E.outer, __dmul_rn(E.coef, raw[E.comp])));
       }
     }
     double stat;
     if (grad_alloc) {
-      double g2 = 0.;
-      for (int c = 1; c < n_out; ++c) g2 += val[c] * val[c];
+      double g2 = 0.;   // grad_norm_vals += diff_f_vals**2, one parameter after the other (:615)
+      for (int c = 1; c < n_out; ++c) g2 = __dadd_rn(g2, __dmul_rn(val[c], val[c]));
       stat = sqrt(g2);
     } else {
       stat = val[0];
     }
     scratch[x] = stat;
-    stat_sum += stat;
     for (int c = 0; c < n_out; ++c) acc[c] += val[c];
   }
   // per-stratum sums of the function value and of every derivative
@@ -148,19 +200,24 @@ sampled_kernel(const DimDev* __restrict__ dims, const ItemDev* __restrict__ item
     for (int w = 0; w < SAMP_NT / 32; ++w) v += s_acc[w * SAMP_MAX_OUT + c];
     sum_out[S.out_off + c] = v;
   }
-  // allocation statistic: mean and population std (numpy.std, two passes)
-  const double n = (double)(S.end - S.begin);
-  const double mean = n > 0. ? block_sum(stat_sum, s_w) / n : 0.;
-  double dev = 0.;
-  for (int64_t x = S.begin + tid; x < S.end; x += SAMP_NT) {
-    const double dlt = scratch[x] - mean;   // written by this very thread above
-    dev += dlt * dlt;
-  }
-  const double var = n > 0. ? block_sum(dev, s_w) / n : 0.;
-  if (tid == 0) {
-    stat_mean[blockIdx.x] = mean;
-    stat_std[blockIdx.x] = sqrt(var);
-  }
+}
+
+// Allocation statistic of every stratum: numpy.mean and numpy.std (ddof = 0) of
+// the per-sample values left in `scratch`, in numpy's own summation order.  One
+// thread per stratum (a stratum holds 10^2 - 10^4 samples; strata run in parallel).
+__global__ void stat_kernel(const StratumDev* __restrict__ strata, int n_strata,
+                            const double* __restrict__ scratch, double* __restrict__ stat_mean,
+                            double* __restrict__ stat_std) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= n_strata) return;
+  const StratumDev S = strata[s];
+  const int64_t n = S.end - S.begin;
+  if (n <= 0) { stat_mean[s] = 0.; stat_std[s] = 0.; return; }
+  const double* a = scratch + S.begin;
+  const double mean = __ddiv_rn(np_pairwise_sum<false>(a, n, 0.), (double)n);
+  const double var = __ddiv_rn(np_pairwise_sum<true>(a, n, mean), (double)n);
+  stat_mean[s] = mean;
+  stat_std[s] = sqrt(var);
 }
 
 // rel_alloc[s] = size_s * sqrt(size_s / (size_s - 1)) * std_s, normalised over the
@@ -173,14 +230,14 @@ __global__ void allocation_kernel(const int32_t* __restrict__ group_first, const
   const int g = blockIdx.x * blockDim.x + threadIdx.x;
   if (g >= n_groups) return;
   const int a = group_first[g], n = group_count[g];
-  double tot = 0.;
   for (int s = a; s < a + n; ++s) {
     const double size = sizes[s];
-    const double r = size * sqrt(size / (size - 1.)) * stat_std[s];
-    rel_alloc[s] = r;
-    tot += r;
+    // strata_size * np.sqrt(strata_size / (strata_size - 1.)) * std, left to right
+    const double fpop = sqrt(__ddiv_rn(size, __dsub_rn(size, 1.)));
+    rel_alloc[s] = __dmul_rn(__dmul_rn(size, fpop), stat_std[s]);
   }
-  for (int s = a; s < a + n; ++s) rel_alloc[s] = tot > 0. ? rel_alloc[s] / tot : default_alloc[s];
+  const double tot = np_pairwise_sum<false>(rel_alloc + a, n, 0.);   // np.sum(rel_alloc)
+  for (int s = a; s < a + n; ++s) rel_alloc[s] = tot > 0. ? __ddiv_rn(rel_alloc[s], tot) : default_alloc[s];
 }
 
 struct Upload {
@@ -224,13 +281,13 @@ extern "C" int aslsd_sampled_sums(aslsd_ctx* ctx, int k, const double* x_k, int 
   int rc = build_plan(ctx, k, x_k, flags | ASLSD_F, nullptr, nullptr, true, P);
   if (rc) return rc;
   CUDA_TRY(ctx, cudaSetDevice(ctx->device));
-  const int d = ctx->d;
   // ---- host-side tables ----------------------------------------------------------------
   std::vector<int32_t> ent_off(P.items.size() + 1, 0);
   std::vector<std::vector<SampleEntry>> per_item(P.items.size());
   std::vector<SampleTermDev> tdev(n_terms);
   std::vector<StratumDev> sdev;
   std::vector<int32_t> group_first, group_count;
+  std::vector<bool> emitted(P.terms.size(), false);
   int64_t out_pos = 0, n_strata = 0;
   for (int q = 0; q < n_terms; ++q) n_strata += terms[q].n_strata;
   const int64_t n_samples = stratum_offsets[n_strata];
@@ -251,9 +308,12 @@ extern "C" int aslsd_sampled_sums(aslsd_ctx* ctx, int k, const double* x_k, int 
     if (D.n_out > SAMP_MAX_OUT)
       return aslsd_fail(ctx, ASLSD_ERR_UNSUPPORTED, "sampled sums: more than 127 parameters in one term");
     if (T.kind >= 2) need_n = true;
-    emit_term(ctx, P, (size_t)tix, x_k, [&](int c, int item, int comp, double coef) {
-      per_item[item].push_back(SampleEntry{comp, c, coef});
-    });
+    if (!emitted[tix]) {   // a term may appear more than once in a batch
+      emitted[tix] = true;
+      emit_term(ctx, P, (size_t)tix, x_k, [&](int c, int item, int comp, double coef, double outer) {
+        per_item[item].push_back(SampleEntry{comp, c, coef, outer});
+      });
+    }
     // index validation: an out-of-range sample would fault the device
     const int64_t n_tgt = ctx->n_events[D.tgt_dim], n_src = ctx->n_events[D.src_dim];
     int32_t group = -1;
@@ -294,7 +354,7 @@ extern "C" int aslsd_sampled_sums(aslsd_ctx* ctx, int k, const double* x_k, int 
     entries.insert(entries.end(), per_item[it].begin(), per_item[it].end());
   }
   ent_off[per_item.size()] = (int32_t)entries.size();
-  if (entries.empty()) entries.push_back(SampleEntry{0, 0, 0.});
+  if (entries.empty()) entries.push_back(SampleEntry{0, 0, 0., 0.});
   const size_t n_items = P.items.size();
   const size_t n_groups = group_first.size();
 
@@ -343,8 +403,11 @@ extern "C" int aslsd_sampled_sums(aslsd_ctx* ctx, int k, const double* x_k, int 
         (const int32_t*)(dp + o_entoff), (const SampleEntry*)(dp + o_ent), (const SampleTermDev*)(dp + o_terms),
         (const StratumDev*)(dp + o_strata), (const int64_t*)(dp + o_m),
         need_n ? (const int64_t*)(dp + o_n) : nullptr, ctx->T_f, (flags & ASLSD_GRAD_ALLOC) ? 1 : 0,
-        (double*)(dp + o_scratch), d_res + r_sum / sizeof(double), d_res + r_mean / sizeof(double),
-        d_res + r_std / sizeof(double));
+        (double*)(dp + o_scratch), d_res + r_sum / sizeof(double));
+    ctx->last_launches++;
+    stat_kernel<<<(unsigned)((n_strata + 63) / 64), 64, 0, ctx->stream>>>(
+        (const StratumDev*)(dp + o_strata), (int)n_strata, (const double*)(dp + o_scratch),
+        d_res + r_mean / sizeof(double), d_res + r_std / sizeof(double));
     ctx->last_launches++;
   }
   if (n_groups) {

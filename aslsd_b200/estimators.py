@@ -627,12 +627,13 @@ class MHPStratEstimB200(_B200Estimator):
             engine = self._bound_engine()
             ix_m = np.concatenate(all_m) if all_m else np.zeros(0, dtype=np.int64)
             ix_n = np.concatenate(all_n) if all_n else np.zeros(0, dtype=np.int64)
-            sums, out_off, _, stat_std, rel = engine.sampled_sums(
+            sums, out_off, stat_mean, stat_std, rel = engine.sampled_sums(
                 self.k, x, dev_terms, offsets, ix_m, ix_n, strata_sizes=sizes,
                 default_alloc=defaults, compute_diff_f_sum=bool(compute_diff_f_sum or grad_alloc),
                 grad_alloc=bool(grad_alloc))
         # ---- 3. fill the reference's result attributes -----------------------------------------------
         s_ix = 0
+        self.last_alloc_stat = {}   # name -> (mean, std, n_samples) of the allocation statistic per adaptive stratum
         for plan in plans:
             name = plan['name']
             strf = self.stratif[name]
@@ -661,6 +662,8 @@ class MHPStratEstimB200(_B200Estimator):
                     est = (block / counts[:, None]) * strata_sizes[:, None]   # size * mean
                 self._store(name, domain, est, do_f, do_diff)
                 if domain == 'adaptive':
+                    self.last_alloc_stat[name] = (stat_mean[s_ix:s_ix + n_strata].copy(),
+                                                  stat_std[s_ix:s_ix + n_strata].copy(), counts)
                     strf.adaptive_rel_alloc = rel[s_ix:s_ix + n_strata].copy()     # :740
                     if self.is_log_allocs:
                         self.logged_allocs[name][t_iter] = strf.adaptive_rel_alloc.copy()

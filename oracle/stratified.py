@@ -79,3 +79,32 @@ def update_allocation(strata_sizes, stat_std, default_alloc):
         rel = sizes * np.sqrt(sizes / (sizes - 1.)) * np.asarray(stat_std, dtype=float)
     tot = np.sum(rel)
     return rel / tot if tot > 0. else np.asarray(default_alloc, dtype=float).copy()
+
+
+def numpy_pairwise_sum(a):
+    """numpy's float64 add.reduce restated in scalar Python (pairwise summation:
+    blocks of at most 128 elements with 8 partial sums, halves split at a
+    multiple of 8).  The CUDA stat / allocation kernels restate the same
+    recursion; tests check this function bit for bit against np.sum."""
+    a = np.asarray(a, dtype=np.float64)
+    n = len(a)
+    if n < 8:
+        res = np.float64(0.)
+        for v in a:
+            res = res + v
+        return res
+    if n <= 128:
+        r = [a[q] for q in range(8)]
+        i = 8
+        while i < n - (n % 8):
+            for q in range(8):
+                r[q] = r[q] + a[i + q]
+            i += 8
+        res = ((r[0] + r[1]) + (r[2] + r[3])) + ((r[4] + r[5]) + (r[6] + r[7]))
+        while i < n:
+            res = res + a[i]
+            i += 1
+        return res
+    n2 = n // 2
+    n2 -= n2 % 8
+    return numpy_pairwise_sum(a[:n2]) + numpy_pairwise_sum(a[n2:])

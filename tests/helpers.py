@@ -61,12 +61,21 @@ def _flat_allocs(est):
     return np.concatenate(out)
 
 
-def replay_strat_golden(name, engine, free_running=False, rtol=RTOL):
+def replay_strat_golden(name, engine, mode='strict', free_running=False, rtol=RTOL):
     """Teacher-forced replay of a reference ASLSD trace: at every iteration the
     estimator is evaluated at the reference's own iterate with the same seeded
     Generator; per-term sums, gradient, LSE and adaptive allocations must match.
-    The RNG stream only stays aligned if every integer sample allocation is
-    identical, which the final generator state certifies.
+
+    mode 'strict': nothing but the evaluation point is forced.  The RNG stream
+        only stays aligned if every integer sample allocation is identical, which
+        the final generator state certifies.
+    mode 'forced': the allocation state (adaptive_rel_alloc / guess_rel_alloc) is
+        also reset to the reference's before every call, so the samples are the
+        reference's regardless of the allocations computed here; the computed
+        allocations are compared only for groups whose strata all have a
+        coefficient of variation above 1e-6.  (In a near-constant stratum the
+        reference's std is the rounding residue of its summation: a last-bit
+        difference in a per-sample value changes it by O(1), see DESIGN.md.)
     ``free_running``: additionally take the ADAM steps from the computed
     gradients and compare the trajectory (looser: errors feed back)."""
     import aslsd_b200
@@ -85,12 +94,14 @@ def replay_strat_golden(name, engine, free_running=False, rtol=RTOL):
         else _oracle_path(times, T_f)
     rng = np.random.default_rng(int(g['seed']))
     worst = 0.
+    n_checked = n_groups = 0
     for k in range(d):
         est = aslsd_b200.MHPStratEstimB200(is_log_lse=True, engine=engine)
         est.initialize(k, n_iter, mirror, path, **kw)
         solver = aslsd_b200.ADAM()
         lower = mirror.lower_bounds(k)
         x_free = g['k%d/x' % k][0].copy()
+        group_names = [nm for nm in sorted(est.stratif) if est.stratif[nm].n_adaptive_strata > 0]
         for t in range(n_iter):
             x_t = g['k%d/x' % k][t]
             grad = est.lse_k_grad_estimate(x_t, rng=rng, grad_alloc=grad_alloc)
@@ -102,14 +113,34 @@ def replay_strat_golden(name, engine, free_running=False, rtol=RTOL):
                                        err_msg='%s k%d t%d sum_diff_f' % (name, k, t))
             np.testing.assert_allclose(grad, g['k%d/grad' % k][t], rtol=rtol, atol=rtol * scale / T_f,
                                        err_msg='%s k%d t%d grad' % (name, k, t))
-            np.testing.assert_allclose(_flat_allocs(est), g['k%d/allocs' % k][t], rtol=1e-9, atol=1e-15,
-                                       err_msg='%s k%d t%d allocations' % (name, k, t))
+            ref_alloc = g['k%d/allocs' % k][t]
+            if mode == 'strict':
+                np.testing.assert_allclose(_flat_allocs(est), ref_alloc, rtol=1e-9, atol=1e-15,
+                                           err_msg='%s k%d t%d allocations' % (name, k, t))
+            else:
+                pos = 0
+                for nm in group_names:
+                    strf = est.stratif[nm]
+                    n_a = strf.n_adaptive_strata
+                    want = ref_alloc[pos:pos + n_a]
+                    mean, std, counts = est.last_alloc_stat[nm]
+                    n_groups += 1
+                    # a single-sample stratum has std == 0 exactly on both sides
+                    if np.all((std > 1e-6 * np.abs(mean)) | (mean == 0.) | (counts == 1)):
+                        n_checked += 1
+                        np.testing.assert_allclose(strf.adaptive_rel_alloc, want, rtol=1e-8, atol=1e-15,
+                                                   err_msg='%s k%d t%d allocation %s' % (name, k, t, nm))
+                    # force the reference's state for the next call (:566-570, :740)
+                    strf.adaptive_rel_alloc = want.copy()
+                    pos += n_a
             worst = max(worst, float(np.max(np.abs(f - ref_f) / np.maximum(np.abs(ref_f), 1e-300))))
             if free_running:
                 x_free = np.clip(solver.iterate(t, x_free, grad), lower, np.inf)
                 np.testing.assert_allclose(x_free, g['k%d/x' % k][t + 1], rtol=1e-7)
         np.testing.assert_allclose(est.logged_lse, g['k%d/logged_lse' % k], rtol=rtol)
     assert str(rng.bit_generator.state) == str(g['rng_final']), 'RNG stream diverged from the reference'
+    if mode != 'strict':
+        assert n_checked >= n_groups // 3, 'too few non-degenerate allocation groups compared'
     return worst
 
 

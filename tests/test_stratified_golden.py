@@ -16,7 +16,8 @@ NAMES = ['strat_exp1d', 'strat_exp2d', 'strat_exp2d_gradalloc', 'strat_gauss1d',
 
 @pytest.mark.parametrize('name', NAMES)
 def test_replay_reference_trace(name):
-    replay_strat_golden(name, OracleEngine(), free_running=(name == 'strat_exp1d'))
+    replay_strat_golden(name, OracleEngine(), mode='strict', free_running=(name == 'strat_exp1d'))
+    replay_strat_golden(name, OracleEngine(), mode='forced')
 
 
 def test_stratification_defaults_match_survey_geometry():
@@ -49,3 +50,18 @@ def test_estimator_pickle_drops_device_handle():
     assert clone.engine is None and clone.t == 0
     with pytest.raises(RuntimeError):
         clone._bound_engine()
+
+
+def test_numpy_summation_order_is_the_one_restated():
+    """np.sum / np.mean / np.std of a contiguous float64 array follow the pairwise
+    recursion that oracle.stratified.numpy_pairwise_sum (and the CUDA stat
+    kernel) restate: bit-for-bit on random data of many lengths."""
+    from oracle import stratified as OS
+    rng = np.random.default_rng(3)
+    for n in list(range(1, 40)) + [127, 128, 129, 255, 256, 257, 345, 1000, 1111, 4097, 10001]:
+        a = rng.normal(size=n) * 10. ** rng.integers(-3, 4, size=n)
+        assert OS.numpy_pairwise_sum(a) == np.sum(a), n
+        mean = OS.numpy_pairwise_sum(a) / n
+        assert mean == np.mean(a)
+        dev = (a - mean) * (a - mean)
+        assert np.sqrt(OS.numpy_pairwise_sum(dev) / n) == np.std(a), n
