@@ -66,7 +66,9 @@ class ShardedExactSums:
         """Enqueue the shard's kernels and the allreduce; returns the device
         tensor holding the combined raw accumulators (asynchronous)."""
         raw = self.raw_buffer(k)
-        self.engine.set_stream(self.torch.cuda.current_stream().cuda_stream)
+        if raw.is_cuda:
+            # the library's kernels and the NCCL all-reduce share torch's current stream
+            self.engine.set_stream(self.torch.cuda.current_stream().cuda_stream)
         self.engine.exact_raw_device(k, x_k, raw.data_ptr(), compute_f_sum,
                                      compute_diff_f_sum, ranges=self.ranges)
         if self.world_size > 1:

@@ -45,6 +45,21 @@ class OracleEngine:
                 out[off + 1:off + 1 + n1] = sum_diff_f[name]
         return out
 
+    # split form used by aslsd_b200.distributed: for the test double the "raw
+    # accumulators" are the packed per-term sums themselves (additive over shards)
+    def exact_raw_len(self, k):
+        return term_layout(self.desc, k)[1]
+
+    def exact_raw_device(self, k, x_k, raw_ptr, compute_f_sum=True, compute_diff_f_sum=True,
+                         ranges=None):
+        import ctypes
+        n = self.exact_raw_len(k)
+        buf = np.ctypeslib.as_array((ctypes.c_double * n).from_address(raw_ptr))
+        buf[:] = self.exact_sums_packed(k, x_k, compute_f_sum, compute_diff_f_sum, ranges=ranges)
+
+    def exact_assemble(self, k, x_k, raw_host, compute_f_sum=True, compute_diff_f_sum=True):
+        return np.array(raw_host, dtype=float)
+
     def sampled_sums(self, k, x_k, terms, stratum_offsets, ix_m, ix_n=None, strata_sizes=None,
                      default_alloc=None, compute_diff_f_sum=True, grad_alloc=False):
         self.n_calls += 1

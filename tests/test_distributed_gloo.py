@@ -1,0 +1,86 @@
+"""Time-block sharding over 2 ranks on CPU (gloo): block boundaries, the
+all-reduce of the per-shard accumulators and the assembly reproduce the
+single-rank sums.  The device is replaced by the oracle test double; the same
+code path runs with NCCL and the CUDA engine in bench.py --gpus N."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from cases import CASES, case_x
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(('127.0.0.1', 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, times, T_f, name, out_dir):
+    import sys
+    here = os.path.dirname(os.path.abspath(__file__))
+    for p in (os.path.dirname(here), here, os.path.join(here, 'golden')):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    import types
+    from oracle_engine import OracleEngine
+    from aslsd_b200.distributed import ShardedExactSums
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    engine = OracleEngine()
+    engine.bind(types.SimpleNamespace(list_times=times, T_f=T_f), CASES[name][0])
+    sharded = ShardedExactSums(engine, times, rank=rank, world_size=world, dist=dist,
+                               device=torch.device('cpu'))
+    x = case_x(name)[1]
+    packed = sharded.packed(1, x)
+    np.save(os.path.join(out_dir, 'rank%d.npy' % rank), packed)
+    np.save(os.path.join(out_dir, 'ranges%d.npy' % rank), np.array(sharded.ranges))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_time_block_ranges_partition_the_events():
+    from aslsd_b200.distributed import time_block_ranges
+    rng = np.random.default_rng(0)
+    times = [np.sort(rng.uniform(0, 100, size=n)) for n in (1000, 400, 2500)]
+    for world in (1, 2, 3, 8):
+        ranges = time_block_ranges(times, world)
+        assert len(ranges) == world
+        for i, t in enumerate(times):
+            assert ranges[0][i][0] == 0 and ranges[-1][i][1] == len(t)
+            for g in range(world - 1):
+                assert ranges[g][i][1] == ranges[g + 1][i][0]
+        # same cut time for every type, balanced target counts
+        loads = [sum(b - a for a, b in r) for r in ranges]
+        assert max(loads) - min(loads) <= len(times)
+        for g in range(world - 1):
+            cut_lo = max(times[i][ranges[g][i][1] - 1] for i in range(3) if ranges[g][i][1] > 0)
+            cut_hi = min(times[i][ranges[g][i][1]] for i in range(3) if ranges[g][i][1] < len(times[i]))
+            assert cut_lo < cut_hi
+
+
+@pytest.mark.timeout(300)
+def test_two_rank_shards_allreduce_to_the_full_sums(tmp_path):
+    from oracle import exact as OE
+    name = 'sbf2d3'
+    rng = np.random.default_rng(8)
+    T_f = 600.
+    times = [np.sort(rng.uniform(0, T_f, size=700)), np.sort(rng.uniform(0, T_f, size=500))]
+    port = _free_port()
+    mp.spawn(_worker, args=(2, port, times, T_f, name, str(tmp_path)), nprocs=2, join=True)
+    got = [np.load(os.path.join(tmp_path, 'rank%d.npy' % r)) for r in range(2)]
+    np.testing.assert_array_equal(got[0], got[1])          # every rank holds the combined sums
+    from oracle_engine import OracleEngine
+    import types
+    full = OracleEngine()
+    full.bind(types.SimpleNamespace(list_times=times, T_f=T_f), CASES[name][0])
+    want = full.exact_sums_packed(1, case_x(name)[1])
+    np.testing.assert_allclose(got[0], want, rtol=1e-12, atol=1e-13)
+    r0 = np.load(os.path.join(tmp_path, 'ranges0.npy'))
+    r1 = np.load(os.path.join(tmp_path, 'ranges1.npy'))
+    assert np.all(r0[:, 1] == r1[:, 0])
