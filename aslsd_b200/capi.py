@@ -15,6 +15,7 @@ LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), '_lib',
 ASLSD_F = 1
 ASLSD_DIFF = 2
 ASLSD_GRAD_ALLOC = 4
+OPT_CLASS_KERNEL = 1
 
 BASIS_EXPONENTIAL = 0
 BASIS_GAUSSIAN = 1
@@ -61,6 +62,18 @@ SYMBOLS = {
     'aslsd_exact_assemble': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, c_f64_p, ctypes.c_int,
                                             c_f64_p, c_f64_p]),
     'aslsd_last_eval_counts': (ctypes.c_int, [ctypes.c_void_p, c_i64_p, c_i64_p]),
+    'aslsd_last_work_counts': (ctypes.c_int, [ctypes.c_void_p, c_i64_p, ctypes.c_int]),
+    'aslsd_set_option': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int]),
+    'aslsd_exact_sums_batch': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, c_i32_p,
+                                              ctypes.POINTER(c_f64_p), ctypes.c_int, c_i64_p, c_i64_p,
+                                              ctypes.POINTER(c_f64_p), ctypes.POINTER(c_i64_p)]),
+    'aslsd_exact_raw_len_batch': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, c_i64_p]),
+    'aslsd_exact_raw_device_batch': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, c_i32_p,
+                                                    ctypes.POINTER(c_f64_p), ctypes.c_int, c_i64_p,
+                                                    c_i64_p, ctypes.c_void_p]),
+    'aslsd_exact_assemble_batch': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, c_i32_p,
+                                                  ctypes.POINTER(c_f64_p), ctypes.c_int, c_f64_p,
+                                                  ctypes.POINTER(c_f64_p)]),
     'aslsd_sampled_n_out': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int,
                                            ctypes.c_int, ctypes.c_int, c_i32_p]),
     'aslsd_sampled_sums': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, c_f64_p, ctypes.c_int,

@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <array>
 #include <string>
 #include <vector>
 
@@ -48,6 +49,7 @@ struct ItemDev {
   double t_int;          // targets with T - t_m >= t_int are interior
   double b1, d1, b2, d2; // beta / delta of the two bases (cross components)
   double bo, dlo;        // beta / delta of the own basis (sim-own components)
+  int64_t dst_row;       // row of the raw accumulator array this item adds into
 };
 
 enum {
@@ -112,6 +114,14 @@ struct aslsd_ctx {
   void* h_pinned = nullptr; size_t pinned_cap = 0;
   void* d_sample = nullptr; size_t sample_cap = 0;
 
+  std::vector<std::vector<double>> h_times;   // host copy of the event times (planning)
+  void* d_class = nullptr; size_t class_cap = 0;              // class-kernel tables
+  double* d_class_partials = nullptr; size_t class_partials_cap = 0;
+  bool use_class_kernel = true;
+  int64_t last_work[8] = {0};   // see aslsd_last_work_counts
+  int64_t last_n_wu_class = 0;
+  std::vector<std::array<int, 3>> last_class_cost;   // per class work unit: exp, normcdf, fma per event pair
+  size_t class_smem_set = 0;
   // timing
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   double last_ms = 0.;

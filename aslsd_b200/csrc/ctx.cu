@@ -64,6 +64,8 @@ extern "C" int aslsd_destroy(aslsd_ctx* ctx) {
   cudaFree(ctx->d_raw);
   cudaFree(ctx->d_counts);
   cudaFree(ctx->d_sample);
+  cudaFree(ctx->d_class);
+  cudaFree(ctx->d_class_partials);
   if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
   cudaEventDestroy(ctx->ev0);
   cudaEventDestroy(ctx->ev1);
@@ -126,6 +128,8 @@ extern "C" int aslsd_set_events(aslsd_ctx* ctx, int d, const int64_t* n_events,
   ctx->d = d;
   ctx->T_f = T_f;
   ctx->n_events.assign(n_events, n_events + d);
+  ctx->h_times.resize(d);
+  for (int i = 0; i < d; ++i) ctx->h_times[i].assign(times[i], times[i] + n_events[i]);
   ctx->off.assign(d + 1, 0);
   ctx->tab_off.assign(d + 1, 0);
   ctx->tab_len.assign(d, 1);

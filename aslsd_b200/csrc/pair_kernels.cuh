@@ -268,7 +268,7 @@ single_kernel(const DimDev* __restrict__ dims, const ItemDev* __restrict__ items
   block_reduce_store<ASLSD_MAX_COMP>(acc, n_eval, s_red, partials + wu * ASLSD_MAX_COMP, counts + wu);
 }
 
-// raw[item][c] = sum over the item's work units, in order.
+// raw[dst_row(item)][c] += sum over the item's work units, in order.
 __global__ void finalize_kernel(const ItemDev* __restrict__ items, int n_items,
                                 const double* __restrict__ partials,
                                 const unsigned long long* __restrict__ counts, double* __restrict__ raw,
@@ -280,7 +280,9 @@ __global__ void finalize_kernel(const ItemDev* __restrict__ items, int n_items,
   if (c < ASLSD_MAX_COMP) {
     double v = 0.;
     for (int w = 0; w < it.n_chunks; ++w) v += partials[(it.wu_first + w) * ASLSD_MAX_COMP + c];
-    raw[(int64_t)item * ASLSD_MAX_COMP + c] = v;
+    // every item owns its destination row (raw is zeroed before the launches; the
+    // class kernel's finalize adds the interior part of the same rows afterwards)
+    raw[it.dst_row * ASLSD_MAX_COMP + c] += v;
   } else {
     unsigned long long v = 0;
     for (int w = 0; w < it.n_chunks; ++w) v += counts[it.wu_first + w];

@@ -75,6 +75,26 @@ class ShardedExactSums:
             self.dist.all_reduce(raw, op=self.dist.ReduceOp.SUM)
         return raw
 
+    # ---- all sub-problems of a step in one launch sequence + one all-reduce ---------------
+    def launch_batch(self, ks, xs, compute_f_sum=True, compute_diff_f_sum=True):
+        key = ('batch', len(ks))
+        if key not in self._raw:
+            n = self.engine.exact_raw_len_batch(len(ks))
+            self._raw[key] = self.torch.zeros(n, dtype=self.torch.float64, device=self.device)
+        raw = self._raw[key]
+        if raw.is_cuda:
+            self.engine.set_stream(self.torch.cuda.current_stream().cuda_stream)
+        self.engine.exact_raw_device_batch(ks, xs, raw.data_ptr(), compute_f_sum,
+                                           compute_diff_f_sum, ranges=self.ranges)
+        if self.world_size > 1:
+            self.dist.all_reduce(raw, op=self.dist.ReduceOp.SUM)
+        return raw
+
+    def packed_batch(self, ks, xs, compute_f_sum=True, compute_diff_f_sum=True):
+        raw = self.launch_batch(ks, xs, compute_f_sum, compute_diff_f_sum)
+        host = raw.cpu().numpy()
+        return self.engine.exact_assemble_batch(ks, xs, host, compute_f_sum, compute_diff_f_sum)
+
     def packed(self, k, x_k, compute_f_sum=True, compute_diff_f_sum=True):
         raw = self.launch(k, x_k, compute_f_sum, compute_diff_f_sum)
         host = raw.cpu().numpy()     # synchronises the stream

@@ -96,6 +96,22 @@ class Engine:
         self._check(self._lib.aslsd_last_timing(self._ctx, ctypes.byref(ms), ctypes.byref(n)))
         return ms.value, n.value
 
+    def set_option(self, option, value):
+        self._check(self._lib.aslsd_set_option(self._ctx, int(option), int(value)))
+
+    def use_class_kernel(self, enabled=True):
+        """Shared-class kernel for the interior of Gaussian upsilon / phi value rows
+        (default on); off: every row goes through the per-item pair kernels."""
+        self.set_option(capi.OPT_CLASS_KERNEL, 1 if enabled else 0)
+
+    def last_work_counts(self):
+        """Work of the last exact-sum call (see aslsd_last_work_counts)."""
+        c = np.zeros(8, dtype=np.int64)
+        self._check(self._lib.aslsd_last_work_counts(self._ctx, capi.ptr_i64(c), 8))
+        names = ('pair_evals', 'single_evals', 'class_pairs', 'class_exp', 'class_normcdf',
+                 'class_fma', 'rows', 'items')
+        return dict(zip(names, (int(v) for v in c)))
+
     def last_eval_counts(self):
         """(pair-kernel, single-kernel) closed-form evaluations of the last
         exact-sum call."""
@@ -265,6 +281,58 @@ class Engine:
             self.set_model(model)
             self._model_ref = model
         return self.desc
+
+    def _batch_args(self, ks, xs):
+        xs = [capi.as_f64(np.asarray(x, dtype=np.float64)) for x in xs]
+        for k, x in zip(ks, xs):
+            if len(x) != self.desc.n_param_k(k):
+                raise ValueError('x_k has %d entries, expected %d' % (len(x), self.desc.n_param_k(k)))
+        k_arr = np.ascontiguousarray(ks, dtype=np.int32)
+        x_ptrs = (capi.c_f64_p * len(xs))(*[capi.ptr_f64(x) for x in xs])
+        return xs, k_arr, k_arr.ctypes.data_as(capi.c_i32_p), x_ptrs
+
+    def exact_sums_batch(self, ks, xs, compute_f_sum=True, compute_diff_f_sum=True, ranges=None,
+                         count_pairs=False):
+        """Packed sums of several sub-problems in one call; work items shared by
+        several of them (fixed beta / delta) are evaluated once."""
+        xs, k_arr, k_ptr, x_ptrs = self._batch_args(ks, xs)
+        outs = [np.zeros(term_layout(self.desc, k)[1], dtype=np.float64) for k in ks]
+        out_ptrs = (capi.c_f64_p * len(ks))(*[capi.ptr_f64(o) for o in outs])
+        flags = (capi.ASLSD_F if compute_f_sum else 0) | (capi.ASLSD_DIFF if compute_diff_f_sum else 0)
+        lo, hi, lo_p, hi_p = self._ranges(ranges)
+        cnts = cnt_ptrs = None
+        if count_pairs:
+            cnts = [np.zeros(len(term_layout(self.desc, k)[0]), dtype=np.int64) for k in ks]
+            cnt_ptrs = (capi.c_i64_p * len(ks))(*[capi.ptr_i64(c) for c in cnts])
+        self._check(self._lib.aslsd_exact_sums_batch(self._ctx, len(ks), k_ptr, x_ptrs, flags, lo_p,
+                                                     hi_p, out_ptrs, cnt_ptrs))
+        if count_pairs:
+            return outs, [{e[0]: int(c) for e, c in zip(term_layout(self.desc, k)[0], cnt)}
+                          for k, cnt in zip(ks, cnts)]
+        return outs
+
+    def exact_raw_len_batch(self, n_k):
+        n = ctypes.c_int64()
+        self._check(self._lib.aslsd_exact_raw_len_batch(self._ctx, int(n_k), ctypes.byref(n)))
+        return n.value
+
+    def exact_raw_device_batch(self, ks, xs, raw_device_ptr, compute_f_sum=True,
+                               compute_diff_f_sum=True, ranges=None):
+        xs, k_arr, k_ptr, x_ptrs = self._batch_args(ks, xs)
+        flags = (capi.ASLSD_F if compute_f_sum else 0) | (capi.ASLSD_DIFF if compute_diff_f_sum else 0)
+        lo, hi, lo_p, hi_p = self._ranges(ranges)
+        self._check(self._lib.aslsd_exact_raw_device_batch(
+            self._ctx, len(ks), k_ptr, x_ptrs, flags, lo_p, hi_p, ctypes.c_void_p(raw_device_ptr)))
+
+    def exact_assemble_batch(self, ks, xs, raw_host, compute_f_sum=True, compute_diff_f_sum=True):
+        xs, k_arr, k_ptr, x_ptrs = self._batch_args(ks, xs)
+        raw = capi.as_f64(raw_host)
+        outs = [np.zeros(term_layout(self.desc, k)[1], dtype=np.float64) for k in ks]
+        out_ptrs = (capi.c_f64_p * len(ks))(*[capi.ptr_f64(o) for o in outs])
+        flags = (capi.ASLSD_F if compute_f_sum else 0) | (capi.ASLSD_DIFF if compute_diff_f_sum else 0)
+        self._check(self._lib.aslsd_exact_assemble_batch(self._ctx, len(ks), k_ptr, x_ptrs, flags,
+                                                         capi.ptr_f64(raw), out_ptrs))
+        return outs
 
     # split form (multi-GPU): raw accumulators stay on the device
     def exact_raw_len(self, k):

@@ -51,6 +51,12 @@ enum {
   ASLSD_GRAD_ALLOC = 4  /* allocation statistic = ||grad||_2 instead of f          */
 };
 
+/* Options of aslsd_set_option. */
+enum {
+  ASLSD_OPT_CLASS_KERNEL = 1 /* 1 (default): interior targets of Gaussian upsilon / phi value
+                                rows go through the shared-class kernel; 0: per-item kernels only */
+};
+
 /* ---- lifetime ------------------------------------------------------------------ */
 int aslsd_create(aslsd_ctx** out, int device);
 int aslsd_destroy(aslsd_ctx* ctx);
@@ -61,6 +67,8 @@ int aslsd_set_stream(aslsd_ctx* ctx, void* cuda_stream);
 /* CUDA-event duration (ms) and launch count of the pair / sample kernels of
  * the last sum call, measured on the launching stream. */
 int aslsd_last_timing(const aslsd_ctx* ctx, double* kernel_ms, int64_t* n_launches);
+
+int aslsd_set_option(aslsd_ctx* ctx, int option, int value);
 
 /* Measured fp64 FMA throughput of the device (TFLOP/s, 2 flops per DFMA): the
  * roofline denominator of the pair kernels (no reference counterpart). */
@@ -112,19 +120,42 @@ int aslsd_exact_sums(aslsd_ctx* ctx, int k, const double* x_k, int flags,
                      const int64_t* m_lo, const int64_t* m_hi, double* out,
                      int64_t* n_pair_terms);
 
+/* Several sub-problems in one call: what d calls of lse_k_grad_estimate compute
+ * (the k loop of MHP.fit, models/hawkes/linear/mhp.py:1771-1787, or MHP.get_lse,
+ * :639-664).  Work items whose raw sums coincide - same event streams, target
+ * block, basis (beta, delta) and component mask; omega never enters - are
+ * evaluated once for the whole batch.  outs[q] / n_pair_terms[q] as in
+ * aslsd_exact_sums for sub-problem ks[q] with parameters xs[q]. */
+int aslsd_exact_sums_batch(aslsd_ctx* ctx, int n_k, const int* ks, const double* const* xs,
+                           int flags, const int64_t* m_lo, const int64_t* m_hi,
+                           double* const* outs, int64_t* const* n_pair_terms);
+
 /* Split form for multi-GPU: device-side raw accumulators (to be summed across
- * ranks with one allreduce) and host-side assembly of the packed terms. */
+ * ranks with one allreduce) and host-side assembly of the packed terms.
+ * raw_len is an upper bound that does not depend on the parameters. */
 int aslsd_exact_raw_len(aslsd_ctx* ctx, int k, int64_t* raw_len);
 int aslsd_exact_raw_device(aslsd_ctx* ctx, int k, const double* x_k, int flags,
                            const int64_t* m_lo, const int64_t* m_hi,
                            double* raw_device, int64_t* n_pair_terms);
 int aslsd_exact_assemble(aslsd_ctx* ctx, int k, const double* x_k, int flags,
                          const double* raw_host, double* out);
+int aslsd_exact_raw_len_batch(aslsd_ctx* ctx, int n_k, int64_t* raw_len);
+int aslsd_exact_raw_device_batch(aslsd_ctx* ctx, int n_k, const int* ks, const double* const* xs,
+                                 int flags, const int64_t* m_lo, const int64_t* m_hi,
+                                 double* raw_device);
+int aslsd_exact_assemble_batch(aslsd_ctx* ctx, int n_k, const int* ks, const double* const* xs,
+                               int flags, const double* raw_host, double* const* outs);
 
 /* Closed-form evaluations performed by the last exact-sum call (basis-pair
  * evaluations of the pair kernels / of the single-index kernels): the work
  * count behind the roofline figures. */
 int aslsd_last_eval_counts(aslsd_ctx* ctx, int64_t* pair_evals, int64_t* single_evals);
+/* Full work accounting of the last exact-sum call, counts[0..7] (n >= 8):
+ *   [0] basis-pair evaluations of the per-item pair kernels   [1] single-index evaluations
+ *   [2] event pairs visited by the shared-class kernel
+ *   [3] exp, [4] normcdf, [5] multiply-add evaluations of the shared-class kernel
+ *   [6] unique work items evaluated   [7] work items before de-duplication */
+int aslsd_last_work_counts(aslsd_ctx* ctx, int64_t* counts, int n);
 
 /* ---- sampled sums: replaces the bodies of MHPStratEstim.estimate_sum_* ------------
  * optimize/estimators/mhp_stratified_estimator.py:534-900, for every term of one

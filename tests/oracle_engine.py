@@ -60,6 +60,25 @@ class OracleEngine:
     def exact_assemble(self, k, x_k, raw_host, compute_f_sum=True, compute_diff_f_sum=True):
         return np.array(raw_host, dtype=float)
 
+    def exact_raw_len_batch(self, n_k):
+        return n_k * max(term_layout(self.desc, k)[1] for k in range(self.desc.d))
+
+    def exact_raw_device_batch(self, ks, xs, raw_ptr, compute_f_sum=True, compute_diff_f_sum=True,
+                               ranges=None):
+        import ctypes
+        n = self.exact_raw_len_batch(len(ks))
+        buf = np.ctypeslib.as_array((ctypes.c_double * n).from_address(raw_ptr))
+        buf[:] = 0.
+        stride = n // len(ks)
+        for q, (k, x) in enumerate(zip(ks, xs)):
+            packed = self.exact_sums_packed(k, x, compute_f_sum, compute_diff_f_sum, ranges=ranges)
+            buf[q * stride:q * stride + len(packed)] = packed
+
+    def exact_assemble_batch(self, ks, xs, raw_host, compute_f_sum=True, compute_diff_f_sum=True):
+        stride = len(raw_host) // len(ks)
+        return [np.array(raw_host[q * stride:q * stride + term_layout(self.desc, k)[1]], dtype=float)
+                for q, k in enumerate(ks)]
+
     def sampled_sums(self, k, x_k, terms, stratum_offsets, ix_m, ix_n=None, strata_sizes=None,
                      default_alloc=None, compute_diff_f_sum=True, grad_alloc=False):
         self.n_calls += 1

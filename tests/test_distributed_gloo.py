@@ -39,6 +39,8 @@ def _worker(rank, world, port, times, T_f, name, out_dir):
     x = case_x(name)[1]
     packed = sharded.packed(1, x)
     np.save(os.path.join(out_dir, 'rank%d.npy' % rank), packed)
+    both = sharded.packed_batch([0, 1], case_x(name))
+    np.save(os.path.join(out_dir, 'batch%d.npy' % rank), np.concatenate(both))
     np.save(os.path.join(out_dir, 'ranges%d.npy' % rank), np.array(sharded.ranges))
     dist.barrier()
     dist.destroy_process_group()
@@ -81,6 +83,9 @@ def test_two_rank_shards_allreduce_to_the_full_sums(tmp_path):
     full.bind(types.SimpleNamespace(list_times=times, T_f=T_f), CASES[name][0])
     want = full.exact_sums_packed(1, case_x(name)[1])
     np.testing.assert_allclose(got[0], want, rtol=1e-12, atol=1e-13)
+    batch = np.load(os.path.join(tmp_path, 'batch0.npy'))
+    want_all = np.concatenate([full.exact_sums_packed(k, case_x(name)[k]) for k in range(2)])
+    np.testing.assert_allclose(batch, want_all, rtol=1e-12, atol=1e-13)
     r0 = np.load(os.path.join(tmp_path, 'ranges0.npy'))
     r1 = np.load(os.path.join(tmp_path, 'ranges1.npy'))
     assert np.all(r0[:, 1] == r1[:, 0])

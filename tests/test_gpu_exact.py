@@ -113,6 +113,64 @@ def test_split_raw_and_assemble_matches_fused(engine):
     np.testing.assert_array_equal(out, fused)
 
 
+@pytest.mark.parametrize('name', ['sbf2d3', 'gauss2d', 'exp2d'])
+def test_batch_equals_per_k_and_shares_rows(engine, name):
+    """aslsd_exact_sums_batch: same packed sums as one call per k; with (beta, delta)
+    fixed the upsilon rows of the d sub-problems coincide and are evaluated once."""
+    model = CASES[name][0]
+    d = model['d']
+    rng = np.random.default_rng(21)
+    times = _simulate_poisson_cluster(rng, d, 3000., 1.5)
+    engine.set_events(times, 3000.)
+    engine.set_model(model)
+    xs = case_x(name)
+    singles = [engine.exact_sums_packed(k, xs[k]) for k in range(d)]
+    outs, counts = engine.exact_sums_batch(list(range(d)), xs, count_pairs=True)
+    work = engine.last_work_counts()
+    for k in range(d):
+        np.testing.assert_allclose(outs[k], singles[k], rtol=1e-13, atol=1e-300)
+        _, c1 = engine.exact_sums_packed(k, xs[k], count_pairs=True)
+        assert counts[k] == c1
+    assert work['rows'] <= work['items']
+    if name == 'sbf2d3':
+        # upsilon / upsilonzero rows (2 x 2 x 9 each) are shared by k = 0 and k = 1
+        assert work['items'] - work['rows'] >= 2 * 4 * 9
+        assert work['class_pairs'] > 0
+
+
+@pytest.mark.parametrize('name', ['sbf2d3', 'sbf1d10', 'gauss1d2b'])
+def test_class_kernel_agrees_with_item_kernels(engine, name):
+    """Shared-class kernel (interior of Gaussian upsilon / phi value rows) against the
+    per-item pair kernels on the same input, and both against the oracle."""
+    model = CASES[name][0]
+    d = model['d']
+    rng = np.random.default_rng(17)
+    times = _simulate_poisson_cluster(rng, d, 6000., 1.2)
+    T_f = 6000.
+    engine.set_events(times, T_f)
+    engine.set_model(model)
+    xs = case_x(name)
+    try:
+        for k in range(d):
+            engine.use_class_kernel(True)
+            a = engine.exact_sums_packed(k, xs[k])
+            wa = engine.last_work_counts()
+            engine.use_class_kernel(False)
+            b = engine.exact_sums_packed(k, xs[k])
+            wb = engine.last_work_counts()
+            np.testing.assert_allclose(a, b, rtol=1e-12, atol=1e-300)
+            assert wb['class_pairs'] == 0
+            if name != 'gauss1d2b':    # free beta / delta: not a class-kernel model
+                assert wa['class_pairs'] > 0 and wa['pair_evals'] < wb['pair_evals']
+            o_f, o_df, _ = OE.exact_sums_windowed(model, k, xs[k], times, T_f)
+            from aslsd_b200.engine import unpack_terms
+            s_f, s_df = unpack_terms(engine.desc, k, a)
+            ref = {'k/%s' % label: val for label, val in iter_sum_entries(o_f, o_df)}
+            assert_sums_close(s_f, s_df, ref, 'k', rtol=RTOL)
+    finally:
+        engine.use_class_kernel(True)
+
+
 def test_linearity_in_omega_for_sbf(engine):
     """Size-independent property: with (beta, delta) fixed every sum is a
     polynomial of degree <= 2 in omega; phi sums are linear."""
