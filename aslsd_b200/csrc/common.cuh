@@ -114,10 +114,19 @@ struct aslsd_ctx {
   void* h_pinned = nullptr; size_t pinned_cap = 0;
   void* d_sample = nullptr; size_t sample_cap = 0;
 
-  std::vector<std::vector<double>> h_times;   // host copy of the event times (planning)
+  // host copy of the event times (planning), inside one pinned staging block that is
+  // also the source of the host -> device copy
+  double* h_events = nullptr; size_t h_events_cap = 0;
+  std::vector<const double*> h_times;
+  size_t times_cap = 0, tab_cap = 0, dims_cap = 0;   // capacities of d_times / d_tab / d_dims
   void* d_class = nullptr; size_t class_cap = 0;              // class-kernel tables
   double* d_class_partials = nullptr; size_t class_partials_cap = 0;
   bool use_class_kernel = true;
+  // last batch plan (exact.cu): reused while the model, the events, the flags, the
+  // target block and the non-omega parameters stay the same (plans hold no results)
+  void* plan_cache = nullptr;
+  void (*plan_cache_free)(void*) = nullptr;
+  int64_t epoch = 0;   // bumped by set_events / set_model / set_option
   int64_t last_work[8] = {0};   // see aslsd_last_work_counts
   int64_t last_n_wu_class = 0;
   std::vector<std::array<int, 3>> last_class_cost;   // per class work unit: exp, normcdf, fma per event pair

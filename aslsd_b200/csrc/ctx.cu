@@ -63,10 +63,12 @@ extern "C" int aslsd_destroy(aslsd_ctx* ctx) {
   cudaFree(ctx->d_partials);
   cudaFree(ctx->d_raw);
   cudaFree(ctx->d_counts);
+  if (ctx->plan_cache && ctx->plan_cache_free) ctx->plan_cache_free(ctx->plan_cache);
   cudaFree(ctx->d_sample);
   cudaFree(ctx->d_class);
   cudaFree(ctx->d_class_partials);
   if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
+  if (ctx->h_events) cudaFreeHost(ctx->h_events);
   cudaEventDestroy(ctx->ev0);
   cudaEventDestroy(ctx->ev1);
   cudaStreamDestroy(ctx->own_stream);
@@ -118,57 +120,82 @@ extern "C" int aslsd_set_events(aslsd_ctx* ctx, int d, const int64_t* n_events,
                                 const double* const* times, double T_f) {
   if (!ctx || d <= 0 || !n_events || !times) return aslsd_fail(ctx, ASLSD_ERR_ARG, "set_events: bad arguments");
   CUDA_TRY(ctx, cudaSetDevice(ctx->device));
-  for (int i = 0; i < d; ++i) {
+  for (int i = 0; i < d; ++i)
     if (n_events[i] < 0 || n_events[i] >= (int64_t)2147483000)
       return aslsd_fail(ctx, ASLSD_ERR_ARG, "set_events: event count out of range");
-    for (int64_t m = 1; m < n_events[i]; ++m)
-      if (!(times[i][m] >= times[i][m - 1]))
-        return aslsd_fail(ctx, ASLSD_ERR_ARG, "set_events: times must be sorted");
+  // layout: every type starts on a 16 B boundary and is followed by >= 2 pad doubles
+  // so that aligned bulk copies may over-read
+  std::vector<int64_t> off(d + 1, 0), tab_off(d + 1, 0), tab_len(d, 1);
+  for (int i = 0; i < d; ++i) {
+    off[i + 1] = off[i] + ((n_events[i] + 1) / 2) * 2 + 2;
+    tab_len[i] = std::max<int64_t>(1, n_events[i] >> ASLSD_BUCKET_SHIFT);
+    tab_off[i + 1] = tab_off[i] + tab_len[i] + 1;
+  }
+  const size_t n_tot = (size_t)off[d];
+  // one pass over the caller's arrays: copy into the pinned block, check the order
+  if (n_tot > ctx->h_events_cap) {
+    if (ctx->h_events) CUDA_TRY(ctx, cudaFreeHost(ctx->h_events));
+    ctx->h_events = nullptr;
+    ctx->h_events_cap = 0;
+    CUDA_TRY(ctx, cudaMallocHost((void**)&ctx->h_events, sizeof(double) * (n_tot + n_tot / 8)));
+    ctx->h_events_cap = n_tot + n_tot / 8;
+  }
+  int rc;
+  if ((rc = ensure_device_buffer(ctx, (void**)&ctx->d_times, &ctx->times_cap, sizeof(double) * n_tot))) return rc;
+  if ((rc = ensure_device_buffer(ctx, (void**)&ctx->d_tab, &ctx->tab_cap, sizeof(int32_t) * (size_t)tab_off[d])))
+    return rc;
+  if ((rc = ensure_device_buffer(ctx, &ctx->d_dims, &ctx->dims_cap, sizeof(DimDev) * d))) return rc;
+  ctx->epoch++;
+  ctx->h_times.assign(d, nullptr);
+  bool sorted = true;
+  for (int i = 0; i < d; ++i) {
+    double* dst = ctx->h_events + off[i];
+    const double* src = times[i];
+    const int64_t n = n_events[i];
+    double prev = n ? src[0] : 0.;
+    bool ok = n == 0 || prev == prev;
+    for (int64_t m = 0; m < n; ++m) {
+      const double v = src[m];
+      ok &= (v >= prev);
+      prev = v;
+      dst[m] = v;
+    }
+    // pad with a huge finite value (the device side may over-read, never uses it)
+    for (int64_t m = n; m < off[i + 1] - off[i]; ++m) dst[m] = 1.7e308;
+    sorted &= ok;
+    ctx->h_times[i] = dst;
+    // the copy of this type overlaps the host pass over the next one
+    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_times + off[i], dst, sizeof(double) * (size_t)(off[i + 1] - off[i]),
+                                  cudaMemcpyHostToDevice, ctx->stream));
+  }
+  if (!sorted) {
+    cudaStreamSynchronize(ctx->stream);
+    ctx->d = 0;
+    return aslsd_fail(ctx, ASLSD_ERR_ARG, "set_events: times must be sorted");
   }
   ctx->d = d;
   ctx->T_f = T_f;
   ctx->n_events.assign(n_events, n_events + d);
-  ctx->h_times.resize(d);
-  for (int i = 0; i < d; ++i) ctx->h_times[i].assign(times[i], times[i] + n_events[i]);
-  ctx->off.assign(d + 1, 0);
-  ctx->tab_off.assign(d + 1, 0);
-  ctx->tab_len.assign(d, 1);
+  ctx->off = off;
+  ctx->tab_off = tab_off;
+  ctx->tab_len = tab_len;
   ctx->tab_t0.assign(d, 0.);
   ctx->tab_w.assign(d, 1.);
+  ctx->times_len = off[d];
+  std::vector<DimDev> dims(d);
   for (int i = 0; i < d; ++i) {
-    // every type starts on a 16 B boundary and is followed by >= 2 pad doubles so
-    // that aligned bulk copies may over-read
-    int64_t padded = ((n_events[i] + 1) / 2) * 2 + 2;
-    ctx->off[i + 1] = ctx->off[i] + padded;
-    int64_t nb = std::max<int64_t>(1, n_events[i] >> ASLSD_BUCKET_SHIFT);
-    ctx->tab_len[i] = nb;
-    ctx->tab_off[i + 1] = ctx->tab_off[i] + nb + 1;
     if (n_events[i] > 0) {
-      double t0 = times[i][0], t1 = times[i][n_events[i] - 1];
-      double w = (t1 - t0) / (double)nb;
+      const double t0 = times[i][0], t1 = times[i][n_events[i] - 1];
+      double w = (t1 - t0) / (double)tab_len[i];
       w = w * (1. + 1e-9) + 1e-300;
       if (!(w > 0.)) w = 1.;
       ctx->tab_t0[i] = t0;
       ctx->tab_w[i] = w;
     }
-  }
-  cudaFree(ctx->d_times); ctx->d_times = nullptr;
-  cudaFree(ctx->d_tab); ctx->d_tab = nullptr;
-  cudaFree(ctx->d_dims); ctx->d_dims = nullptr;
-  ctx->times_len = ctx->off[d];
-  CUDA_TRY(ctx, cudaMalloc(&ctx->d_times, sizeof(double) * ctx->times_len));
-  CUDA_TRY(ctx, cudaMemsetAsync(ctx->d_times, 0x7f, sizeof(double) * ctx->times_len, ctx->stream));
-  CUDA_TRY(ctx, cudaMalloc(&ctx->d_tab, sizeof(int32_t) * ctx->tab_off[d]));
-  CUDA_TRY(ctx, cudaMalloc(&ctx->d_dims, sizeof(DimDev) * d));
-  std::vector<DimDev> dims(d);
-  for (int i = 0; i < d; ++i) {
-    if (n_events[i] > 0)
-      CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_times + ctx->off[i], times[i], sizeof(double) * n_events[i],
-                                    cudaMemcpyHostToDevice, ctx->stream));
-    dims[i].t = ctx->d_times + ctx->off[i];
-    dims[i].tab = ctx->d_tab + ctx->tab_off[i];
+    dims[i].t = ctx->d_times + off[i];
+    dims[i].tab = ctx->d_tab + tab_off[i];
     dims[i].n = n_events[i];
-    dims[i].n_buckets = ctx->tab_len[i];
+    dims[i].n_buckets = tab_len[i];
     dims[i].t0 = ctx->tab_t0[i];
     dims[i].w = ctx->tab_w[i];
     dims[i].inv_w = 1. / ctx->tab_w[i];
@@ -176,14 +203,14 @@ extern "C" int aslsd_set_events(aslsd_ctx* ctx, int d, const int64_t* n_events,
   CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_dims, dims.data(), sizeof(DimDev) * d, cudaMemcpyHostToDevice,
                                 ctx->stream));
   for (int i = 0; i < d; ++i) {
-    int64_t nb = ctx->tab_len[i];
-    int threads = 256;
-    int blocks = (int)((nb + 1 + threads - 1) / threads);
+    const int64_t nb = tab_len[i];
+    const int threads = 256;
+    const int blocks = (int)((nb + 1 + threads - 1) / threads);
     build_bucket_table_kernel<<<blocks, threads, 0, ctx->stream>>>(
-        dims[i].t, dims[i].n, ctx->d_tab + ctx->tab_off[i], nb, dims[i].t0, dims[i].w);
+        dims[i].t, dims[i].n, ctx->d_tab + tab_off[i], nb, dims[i].t0, dims[i].w);
   }
   CUDA_TRY(ctx, cudaGetLastError());
-  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));   // `dims` is a stack object
   return ASLSD_OK;
 }
 
@@ -230,6 +257,7 @@ extern "C" int aslsd_set_model(aslsd_ctx* ctx, int d, const int32_t* n_basis, co
   }
   ctx->kernels.swap(ks);
   ctx->has_model = true;
+  ctx->epoch++;
   if (ctx->d == 0) ctx->d = d;
   return ASLSD_OK;
 }

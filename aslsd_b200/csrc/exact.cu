@@ -29,6 +29,9 @@ struct RowKey {
 };
 
 struct BatchPlan {
+  std::vector<double> key_rows, key_work;   // cache keys (see get_batch)
+  bool has_work = false;
+  bool device_resident = false;   // item / class tables of this plan are on the device
   int flags = 0;
   std::vector<int> ks;
   std::vector<SumPlan> plans;
@@ -69,7 +72,7 @@ static bool class_eligible(const ItemDev& it) {
 
 // first target index in [m_lo, m_hi) whose time to the end is below t_int
 static int64_t interior_end(const aslsd_ctx* ctx, int dim, int64_t m_lo, int64_t m_hi, double t_int) {
-  const std::vector<double>& t = ctx->h_times[dim];
+  const double* t = ctx->h_times[dim];
   int64_t lo = m_lo, hi = m_hi;
   while (lo < hi) {
     const int64_t mid = (lo + hi) >> 1;
@@ -289,6 +292,48 @@ static int build_batch(aslsd_ctx* ctx, int n_k, const int* ks, const double* con
   return ASLSD_OK;
 }
 
+// Plans are pure functions of (model, events, flags, target block, non-omega
+// parameters): the last one is kept and reused, with the omega-dependent variables
+// refreshed.  No result is cached - every call launches all of its kernels.
+static void free_batch(void* p) { delete (BatchPlan*)p; }
+
+static int get_batch(aslsd_ctx* ctx, int n_k, const int* ks, const double* const* xs, int flags,
+                     const int64_t* m_lo, const int64_t* m_hi, bool with_work, BatchPlan** out) {
+  std::vector<double> key_rows, key_work;
+  key_rows.push_back((double)ctx->epoch);
+  key_rows.push_back((double)n_k);
+  key_rows.push_back((double)flags);
+  for (int q = 0; q < n_k; ++q) {
+    key_rows.push_back((double)ks[q]);
+    plan_shape_key(ctx, ks[q], xs[q], key_rows);
+  }
+  key_work.push_back(ctx->use_class_kernel ? 1. : 0.);
+  for (int i = 0; i < ctx->d; ++i) {
+    key_work.push_back(m_lo ? (double)m_lo[i] : -1.);
+    key_work.push_back(m_hi ? (double)m_hi[i] : -1.);
+  }
+  BatchPlan* C = (BatchPlan*)ctx->plan_cache;
+  if (C && C->key_rows == key_rows && (!with_work || (C->has_work && C->key_work == key_work))) {
+    for (int q = 0; q < n_k; ++q) {
+      int rc = plan_vars(ctx, ks[q], xs[q], C->plans[q]);
+      if (rc) return rc;
+    }
+    *out = C;
+    return ASLSD_OK;
+  }
+  BatchPlan* B = new BatchPlan();
+  int rc = build_batch(ctx, n_k, ks, xs, flags, m_lo, m_hi, with_work, *B);
+  if (rc) { delete B; return rc; }
+  B->key_rows.swap(key_rows);
+  B->key_work.swap(key_work);
+  B->has_work = with_work;
+  if (ctx->plan_cache) free_batch(ctx->plan_cache);
+  ctx->plan_cache = B;
+  ctx->plan_cache_free = free_batch;
+  *out = B;
+  return ASLSD_OK;
+}
+
 template <int FAMILY>
 static void launch_pair(aslsd_ctx* ctx, const BatchPlan& B, const ItemDev* d_items) {
   if (B.fam_wu_count[FAMILY] == 0) return;
@@ -307,7 +352,7 @@ static void launch_single(aslsd_ctx* ctx, const BatchPlan& B, const ItemDev* d_i
 }
 
 // Launch everything; leaves raw[row][comp] in raw_device (zeroed here first).
-static int run_batch(aslsd_ctx* ctx, const BatchPlan& B, double* raw_device) {
+static int run_batch(aslsd_ctx* ctx, BatchPlan& B, double* raw_device) {
   CUDA_TRY(ctx, cudaSetDevice(ctx->device));
   const size_t n_items = B.items.size(), n_rows = B.rows.size();
   int rc;
@@ -325,7 +370,7 @@ static int run_batch(aslsd_ctx* ctx, const BatchPlan& B, double* raw_device) {
   if ((rc = ensure_device_buffer(ctx, (void**)&ctx->d_counts, &ctx->counts_cap,
                                  ((size_t)B.n_wu + n_items + (size_t)B.n_wu_class + 1) * sizeof(unsigned long long))))
     return rc;
-  if (n_items)
+  if (n_items && !B.device_resident)
     CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_items, B.items.data(), n_items * sizeof(ItemDev),
                                   cudaMemcpyHostToDevice, ctx->stream));
   // class-kernel tables: one block [terms | P classes | Q classes | products]
@@ -334,7 +379,11 @@ static int run_batch(aslsd_ctx* ctx, const BatchPlan& B, double* raw_device) {
   const size_t o_n = o_e + ((B.ecls.size() * sizeof(EClassDev) + 15) & ~(size_t)15);
   const size_t o_p = o_n + ((B.ncls.size() * sizeof(NClassDev) + 15) & ~(size_t)15);
   const size_t c_bytes = o_p + B.prods.size() * sizeof(ProdDev);
-  if (!B.cterms.empty()) {
+  if (!B.cterms.empty() && B.device_resident) {
+    if ((rc = ensure_device_buffer(ctx, (void**)&ctx->d_class_partials, &ctx->class_partials_cap,
+                                   (size_t)B.n_class_partials * sizeof(double)))) return rc;
+  }
+  if (!B.cterms.empty() && !B.device_resident) {
     if ((rc = ensure_device_buffer(ctx, &ctx->d_class, &ctx->class_cap, c_bytes))) return rc;
     if ((rc = ensure_device_buffer(ctx, (void**)&ctx->d_class_partials, &ctx->class_partials_cap,
                                    (size_t)B.n_class_partials * sizeof(double)))) return rc;
@@ -348,6 +397,7 @@ static int run_batch(aslsd_ctx* ctx, const BatchPlan& B, double* raw_device) {
     // the pinned staging block is reused by the caller once the copy has completed
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
   }
+  B.device_resident = true;
   // static per-pair costs of the class terms are turned into totals in aslsd_last_work_counts
   ctx->last_class_cost.clear();
   for (auto& T : B.cterms) {
@@ -488,7 +538,7 @@ extern "C" int aslsd_exact_out_len(const aslsd_ctx* ctx, int k, int64_t* out_len
 
 extern "C" int aslsd_set_option(aslsd_ctx* ctx, int option, int value) {
   if (!ctx) return ASLSD_ERR_ARG;
-  if (option == ASLSD_OPT_CLASS_KERNEL) { ctx->use_class_kernel = value != 0; return ASLSD_OK; }
+  if (option == ASLSD_OPT_CLASS_KERNEL) { ctx->use_class_kernel = value != 0; ctx->epoch++; return ASLSD_OK; }
   return aslsd_fail(ctx, ASLSD_ERR_ARG, "set_option: unknown option");
 }
 
@@ -498,8 +548,9 @@ extern "C" int aslsd_exact_sums_batch(aslsd_ctx* ctx, int n_k, const int* ks, co
   int rc = check_batch_args(ctx, n_k, ks, xs);
   if (rc) return rc;
   if (!outs) return aslsd_fail(ctx, ASLSD_ERR_ARG, "exact sums: bad arguments");
-  BatchPlan B;
-  if ((rc = build_batch(ctx, n_k, ks, xs, flags, m_lo, m_hi, true, B))) return rc;
+  BatchPlan* Bp = nullptr;
+  if ((rc = get_batch(ctx, n_k, ks, xs, flags, m_lo, m_hi, true, &Bp))) return rc;
+  BatchPlan& B = *Bp;
   const size_t raw_bytes = std::max<size_t>(1, B.rows.size()) * ASLSD_MAX_COMP * sizeof(double);
   CUDA_TRY(ctx, cudaSetDevice(ctx->device));
   if ((rc = ensure_device_buffer(ctx, (void**)&ctx->d_raw, &ctx->raw_cap, raw_bytes))) return rc;
@@ -544,9 +595,9 @@ extern "C" int aslsd_exact_raw_device_batch(aslsd_ctx* ctx, int n_k, const int* 
   int rc = check_batch_args(ctx, n_k, ks, xs);
   if (rc) return rc;
   if (!raw_device) return aslsd_fail(ctx, ASLSD_ERR_ARG, "exact_raw_device: bad arguments");
-  BatchPlan B;
-  if ((rc = build_batch(ctx, n_k, ks, xs, flags, m_lo, m_hi, true, B))) return rc;
-  return run_batch(ctx, B, raw_device);
+  BatchPlan* Bp = nullptr;
+  if ((rc = get_batch(ctx, n_k, ks, xs, flags, m_lo, m_hi, true, &Bp))) return rc;
+  return run_batch(ctx, *Bp, raw_device);
 }
 
 extern "C" int aslsd_exact_raw_device(aslsd_ctx* ctx, int k, const double* x_k, int flags, const int64_t* m_lo,
@@ -565,8 +616,9 @@ extern "C" int aslsd_exact_assemble_batch(aslsd_ctx* ctx, int n_k, const int* ks
   int rc = check_batch_args(ctx, n_k, ks, xs);
   if (rc) return rc;
   if (!raw_host || !outs) return aslsd_fail(ctx, ASLSD_ERR_ARG, "exact_assemble: bad arguments");
-  BatchPlan B;
-  if ((rc = build_batch(ctx, n_k, ks, xs, flags, nullptr, nullptr, false, B))) return rc;
+  BatchPlan* Bp = nullptr;
+  if ((rc = get_batch(ctx, n_k, ks, xs, flags, nullptr, nullptr, false, &Bp))) return rc;
+  BatchPlan& B = *Bp;
   for (int q = 0; q < n_k; ++q) assemble(ctx, B.plans[q], B.item_row[q], xs[q], raw_host, outs[q]);
   return ASLSD_OK;
 }

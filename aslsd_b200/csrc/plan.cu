@@ -212,6 +212,37 @@ static void plan_basis_items(SumPlan& P, std::vector<ItemDev> fam_items[8],
   P.term_der_off.push_back(P.term_val_off.back());
 }
 
+// parameter slices of x_k (mhp.py:276-299 interval_map) -> full variables of every basis
+int plan_vars(aslsd_ctx* ctx, int k, const double* x_k, SumPlan& P) {
+  const int d = ctx->d;
+  const KernelHost& KU = ctx->kernels[d * d - 1];
+  P.V.resize(d);
+  P.VU.resize(d);
+  std::vector<int> par_off(d + 1, 1);
+  for (int i = 0; i < d; ++i) par_off[i + 1] = par_off[i] + ctx->kernels[k * d + i].n_param();
+  for (int i = 0; i < d; ++i) {
+    kernel_vars(ctx->kernels[k * d + i], x_k + par_off[i], P.V[i]);
+    kernel_vars(KU, x_k + par_off[i], P.VU[i]);
+    for (auto& v : P.V[i])
+      if (!(v[1] > 0.)) return aslsd_fail(ctx, ASLSD_ERR_ARG, "exact sums: beta must be positive");
+  }
+  return ASLSD_OK;
+}
+
+// The non-omega variables of x_k (beta, delta of every basis, in order): together
+// with the model, the flags and the target block they determine the work items.
+void plan_shape_key(const aslsd_ctx* ctx, int k, const double* x_k, std::vector<double>& key) {
+  const int d = ctx->d;
+  int pos = 1;
+  for (int i = 0; i < d; ++i)
+    for (auto& b : ctx->kernels[k * d + i].bases)
+      for (int v = 0; v < b.n_vars(); ++v)
+        if ((b.free_mask >> v) & 1) {
+          if (v > 0) key.push_back(x_k[pos]);
+          ++pos;
+        }
+}
+
 int build_plan(aslsd_ctx* ctx, int k, const double* x_k, int flags, const int64_t* m_lo,
                const int64_t* m_hi, bool by_term, SumPlan& P) {
   const int d = ctx->d;
@@ -227,17 +258,8 @@ int build_plan(aslsd_ctx* ctx, int k, const double* x_k, int flags, const int64_
     lo[i] = m_lo ? std::max<int64_t>(0, m_lo[i]) : 0;
     hi[i] = m_hi ? std::min<int64_t>(ctx->n_events[i], m_hi[i]) : ctx->n_events[i];
   }
-  // parameter slices (mhp.py:276-299 interval_map)
-  P.V.resize(d);
-  P.VU.resize(d);
-  std::vector<int> par_off(d + 1, 1);
-  for (int i = 0; i < d; ++i) par_off[i + 1] = par_off[i] + ctx->kernels[k * d + i].n_param();
-  for (int i = 0; i < d; ++i) {
-    kernel_vars(ctx->kernels[k * d + i], x_k + par_off[i], P.V[i]);
-    kernel_vars(KU, x_k + par_off[i], P.VU[i]);
-    for (auto& v : P.V[i])
-      if (!(v[1] > 0.)) return aslsd_fail(ctx, ASLSD_ERR_ARG, "exact sums: beta must be positive");
-  }
+  int rc = plan_vars(ctx, k, x_k, P);
+  if (rc) return rc;
   std::vector<ItemDev> fam_items[8];
   std::vector<std::pair<int, ItemRef>> fixups;
   int64_t out = 0;

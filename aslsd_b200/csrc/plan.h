@@ -38,6 +38,12 @@ struct SumPlan {
 int build_plan(aslsd_ctx* ctx, int k, const double* x_k, int flags, const int64_t* m_lo,
                const int64_t* m_hi, bool by_term, SumPlan& P);
 
+// Re-derive the per-basis variables (P.V, P.VU) of an existing plan from a new x_k.
+int plan_vars(aslsd_ctx* ctx, int k, const double* x_k, SumPlan& P);
+// Append the non-omega variables of x_k to `key` (the work items depend on x_k only
+// through them).
+void plan_shape_key(const aslsd_ctx* ctx, int k, const double* x_k, std::vector<double>& key);
+
 // Index of a named term in SumPlan::terms (-1 if absent).
 int find_term(const aslsd_ctx* ctx, int kind, int i, int j);
 

@@ -88,7 +88,15 @@ class Engine:
             raise EngineError('aslsd_b200 error %d: %s' % (rc, msg))
 
     def set_stream(self, cuda_stream):
-        self._check(self._lib.aslsd_set_stream(self._ctx, ctypes.c_void_p(cuda_stream or 0)))
+        """Run all subsequent work on the caller's CUDA stream (a raw cudaStream_t
+        handle, e.g. ``torch.cuda.current_stream().cuda_stream``); ``None`` restores
+        the context's own stream.  Handle 0 is torch's default stream: it is mapped
+        to cudaStreamLegacy (0x1), since NULL means "own stream" in the C ABI."""
+        if cuda_stream is None:
+            handle = 0
+        else:
+            handle = int(cuda_stream) or 1
+        self._check(self._lib.aslsd_set_stream(self._ctx, ctypes.c_void_p(handle)))
 
     def last_timing(self):
         ms = ctypes.c_double()

@@ -62,7 +62,8 @@ int aslsd_create(aslsd_ctx** out, int device);
 int aslsd_destroy(aslsd_ctx* ctx);
 const char* aslsd_last_error(const aslsd_ctx* ctx);
 /* Use the caller's CUDA stream (a cudaStream_t) for all subsequent work;
- * NULL restores the context's own stream. */
+ * NULL restores the context's own (non-blocking) stream.  To run on the legacy
+ * default stream pass cudaStreamLegacy ((cudaStream_t)0x1). */
 int aslsd_set_stream(aslsd_ctx* ctx, void* cuda_stream);
 /* CUDA-event duration (ms) and launch count of the pair / sample kernels of
  * the last sum call, measured on the launching stream. */

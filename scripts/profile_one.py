@@ -1,14 +1,15 @@
-"""One exact-sum call on a reduced C5 stream (for ncu captures)."""
+"""One batched exact-sum call on a reduced C5 stream (for ncu captures)."""
 import sys
 sys.path.insert(0, '.')
 import aslsd_b200
 from aslsd_b200 import simulate
 
-T_f = float(sys.argv[1]) if len(sys.argv) > 1 else 2e4
+T_f = float(sys.argv[1]) if len(sys.argv) > 1 else 5e4
 model, times, T_f, xs = simulate.config_c5(T_f=T_f)
 eng = aslsd_b200.Engine(0)
 eng.set_events(times, T_f)
 eng.set_model(model)
-for rep in range(2):
-    eng.exact_sums_packed(0, xs[0])
-print('ok', eng.last_timing())
+d = model['d']
+for rep in range(3):
+    eng.exact_sums_batch(list(range(d)), xs)
+    print('rep', rep, eng.last_timing(), eng.last_work_counts())

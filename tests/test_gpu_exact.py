@@ -133,8 +133,9 @@ def test_batch_equals_per_k_and_shares_rows(engine, name):
         assert counts[k] == c1
     assert work['rows'] <= work['items']
     if name == 'sbf2d3':
-        # upsilon / upsilonzero rows (2 x 2 x 9 each) are shared by k = 0 and k = 1
-        assert work['items'] - work['rows'] >= 2 * 4 * 9
+        # per k: 2 x (3 psi + 9 upsilonzero + 3 phi + 9 upsilon_ii) + 2 x 9 cross = 66 items;
+        # upsilon (36), upsilonzero (18) and psi (6) rows are shared by k = 0 and k = 1
+        assert work['items'] == 132 and work['rows'] == 72
         assert work['class_pairs'] > 0
 
 
