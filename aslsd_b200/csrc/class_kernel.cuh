@@ -28,6 +28,7 @@
 #pragma once
 
 #include "basis_math.cuh"
+#include "fast_math.cuh"
 #include "pair_kernels.cuh"
 
 #define CK_NT 256
@@ -39,7 +40,7 @@
 struct EClassDev {   // P_e(s) = pn exp(-0.5 ((s - dd) isig)^2)
   double dd, isig, pn;
 };
-struct NClassDev {   // Q_n(s) = 1 - normcdf(c0 + c1 s); one != 0: Q = 1
+struct NClassDev {   // Q_n(s) = 1 - Phi(sqrt(2) (c0 + c1 s)) = erfc(c0 + c1 s) / 2; one != 0: Q = 1
   double c0, c1;
   int32_t one, pad;
 };
@@ -224,15 +225,16 @@ class_kernel(const DimDev* __restrict__ dims, const ClassTermDev* __restrict__ t
         const EClassDev A = s_e[e];
         const EClassDev B = s_e[min(e + 1, nE - 1)];
         const double za = (s - A.dd) * A.isig, zb = (s - B.dd) * B.isig;
-        const double va = A.pn * exp(-0.5 * za * za), vb = B.pn * exp(-0.5 * zb * zb);
+        const double va = A.pn * fm_exp_neg(-0.5 * za * za), vb = B.pn * fm_exp_neg(-0.5 * zb * zb);
         rowE[e] = live ? va : 0.;
         if (e + 1 < nE) rowE[e + 1] = live ? vb : 0.;
       }
       for (int n = 0; n < nN; n += 2) {
         const NClassDev A = s_n[n];
         const NClassDev B = s_n[min(n + 1, nN - 1)];
-        const double va = A.one ? 1. : 1. - normcdf(fma(A.c1, s, A.c0));
-        const double vb = B.one ? 1. : 1. - normcdf(fma(B.c1, s, B.c0));
+        // c0, c1 carry the 1/sqrt(2) of Phi(x) = 1 - erfc(x / sqrt(2)) / 2
+        const double va = A.one ? 1. : fm_half_erfc(fma(A.c1, s, A.c0));
+        const double vb = B.one ? 1. : fm_half_erfc(fma(B.c1, s, B.c0));
         rowN[n] = va;
         if (n + 1 < nN) rowN[n + 1] = vb;
       }

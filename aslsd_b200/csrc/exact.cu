@@ -136,8 +136,10 @@ static void build_class_terms(const aslsd_ctx* ctx, BatchPlan& B, const std::vec
         E.pn = 1. / (sig * SQRT_2PI);
         const double inv_bs = sig / (it.b1 * it.b2);
         const double r1 = (it.b2 * it.b2) / sig2, r2 = (it.b1 * it.b1) / sig2;
-        N.c0 = -(r1 * it.d1 + r2 * it.d2) * inv_bs;
-        N.c1 = r2 * inv_bs;
+        // lower limit lo = c0 + c1 s of the reference's gaussian_int; stored divided by
+        // sqrt(2): Q = 1 - Phi(lo) = erfc(lo / sqrt(2)) / 2
+        N.c0 = -(r1 * it.d1 + r2 * it.d2) * inv_bs / std::sqrt(2.);
+        N.c1 = r2 * inv_bs / std::sqrt(2.);
       }
       const size_t e_before = B.ecls.size(), n_before = B.ncls.size();
       const int e = find_or_add(B.ecls, (size_t)T.e_first, E, e_eq);
