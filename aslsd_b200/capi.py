@@ -15,7 +15,7 @@ LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), '_lib',
 ASLSD_F = 1
 ASLSD_DIFF = 2
 ASLSD_GRAD_ALLOC = 4
-OPT_CLASS_KERNEL = 1
+OPT_LAG_QUADRATURE = 1
 
 BASIS_EXPONENTIAL = 0
 BASIS_GAUSSIAN = 1

@@ -50,6 +50,7 @@ struct ItemDev {
   double b1, d1, b2, d2; // beta / delta of the two bases (cross components)
   double bo, dlo;        // beta / delta of the own basis (sim-own components)
   int64_t dst_row;       // row of the raw accumulator array this item adds into
+  int64_t n_int;         // single-index rows: interior targets taken as n_int x closed form
 };
 
 enum {
@@ -119,18 +120,20 @@ struct aslsd_ctx {
   double* h_events = nullptr; size_t h_events_cap = 0;
   std::vector<const double*> h_times;
   size_t times_cap = 0, tab_cap = 0, dims_cap = 0;   // capacities of d_times / d_tab / d_dims
-  void* d_class = nullptr; size_t class_cap = 0;              // class-kernel tables
-  double* d_class_partials = nullptr; size_t class_partials_cap = 0;
-  bool use_class_kernel = true;
+  // lag quadrature (lag_quadrature.cuh): stream / row tables, partial moments, node weights
+  void* d_qtab = nullptr; size_t qtab_cap = 0;
+  double* d_q_partials = nullptr; size_t q_partials_cap = 0;
+  double* d_q_weights = nullptr; size_t q_weights_cap = 0;
+  bool use_quadrature = true;
+  bool lq_tables_set = false;
+  size_t q_smem_set = 0;
   // last batch plan (exact.cu): reused while the model, the events, the flags, the
   // target block and the non-omega parameters stay the same (plans hold no results)
   void* plan_cache = nullptr;
   void (*plan_cache_free)(void*) = nullptr;
   int64_t epoch = 0;   // bumped by set_events / set_model / set_option
   int64_t last_work[8] = {0};   // see aslsd_last_work_counts
-  int64_t last_n_wu_class = 0;
-  std::vector<std::array<int, 3>> last_class_cost;   // per class work unit: exp, normcdf, fma per event pair
-  size_t class_smem_set = 0;
+  int64_t last_n_wu_q = 0;
   // timing
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   double last_ms = 0.;

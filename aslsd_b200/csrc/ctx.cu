@@ -65,8 +65,9 @@ extern "C" int aslsd_destroy(aslsd_ctx* ctx) {
   cudaFree(ctx->d_counts);
   if (ctx->plan_cache && ctx->plan_cache_free) ctx->plan_cache_free(ctx->plan_cache);
   cudaFree(ctx->d_sample);
-  cudaFree(ctx->d_class);
-  cudaFree(ctx->d_class_partials);
+  cudaFree(ctx->d_qtab);
+  cudaFree(ctx->d_q_partials);
+  cudaFree(ctx->d_q_weights);
   if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
   if (ctx->h_events) cudaFreeHost(ctx->h_events);
   cudaEventDestroy(ctx->ev0);

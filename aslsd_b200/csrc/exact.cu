@@ -1,5 +1,5 @@
 // Exact LSE sums: batching over sub-problems, de-duplication of identical work
-// items, class terms for the shared-class kernel, launches and assembly.
+// items, lag-quadrature streams, launches and assembly.
 // Replaces MHPExactEstim.compute_objective and its five compute_*_sum methods
 // (optimize/estimators/mhp_exact_estimator.py:543-761) for one or several k.
 //
@@ -10,12 +10,13 @@
 // evaluated once ("rows").  For the SBF models of the reference (beta, delta
 // fixed) every upsilon_i_j row is shared by all d sub-problems.
 //
-// Rows that are products of single-variable factors of the lag (Gaussian upsilon
-// value / own-basis d omega, Gaussian phi value) are served, for their interior
-// targets, by the shared-class kernel (class_kernel.cuh); their last few targets
-// (T_f - t_m within the kernels' reach) and all other rows by the per-item pair
-// kernels (pair_kernels.cuh).
-#include "class_kernel.cuh"
+// For the interior targets (T_f - t_m beyond the kernels' reach) every double-sum row
+// is a function of the lag alone: all rows of one ordered pair of event streams
+// share one pass over the event pairs (lag_quadrature.cuh).  The last few targets
+// of every row, and streams that do not qualify, go through the per-item pair
+// kernels (pair_kernels.cuh).  Single-index rows (psi, upsilon at lag zero) are
+// constant in the interior: count x closed form, per-target evaluation only near T_f.
+#include "lag_quadrature.cuh"
 #include "plan.h"
 
 #include <algorithm>
@@ -31,7 +32,7 @@ struct RowKey {
 struct BatchPlan {
   std::vector<double> key_rows, key_work;   // cache keys (see get_batch)
   bool has_work = false;
-  bool device_resident = false;   // item / class tables of this plan are on the device
+  bool device_resident = false;   // item / stream tables of this plan are on the device
   int flags = 0;
   std::vector<int> ks;
   std::vector<SumPlan> plans;
@@ -43,13 +44,13 @@ struct BatchPlan {
   int fam_first[8], fam_count[8];
   int64_t fam_wu_first[8], fam_wu_count[8];
   int64_t n_wu = 0;
-  // shared-class kernel
-  std::vector<ClassTermDev> cterms;
-  std::vector<EClassDev> ecls;
-  std::vector<NClassDev> ncls;
-  std::vector<ProdDev> prods;
-  int64_t n_wu_class = 0, n_class_partials = 0;
-  size_t class_smem = 0;
+  // lag quadrature
+  std::vector<QStreamDev> qstreams;
+  std::vector<ItemDev> qrows;                   // grouped by family; wu_first = stream index
+  int qfam_first[8], qfam_count[8];
+  int64_t n_wu_q = 0, n_q_partials = 0, n_q_weights = 0, n_q_evals = 0;
+  int q_jmax = 0;
+  size_t q_smem = 0;
 };
 
 static ItemDev canonical(const ItemDev& it) {
@@ -59,15 +60,6 @@ static ItemDev canonical(const ItemDev& it) {
   c.wu_first = 0;
   c.dst_row = 0;
   return c;
-}
-
-static bool class_eligible(const ItemDev& it) {
-  if (it.family == ITEM_PHI_GAUSS) return it.mask == MASK(0);
-  if (it.family != ITEM_UPS_GAUSS) return false;
-  const int allowed = MASK(C_G) | MASK(C_SW) | MASK_OWN_SAME;
-  if (it.mask & ~allowed) return false;
-  if ((it.mask & MASK(C_SW)) && !(it.mask & MASK_OWN_SAME)) return false;
-  return true;
 }
 
 // first target index in [m_lo, m_hi) whose time to the end is below t_int
@@ -81,113 +73,74 @@ static int64_t interior_end(const aslsd_ctx* ctx, int dim, int64_t m_lo, int64_t
   return lo;
 }
 
-template <class T, class Eq>
-static int find_or_add(std::vector<T>& v, size_t first, const T& x, Eq eq) {
-  for (size_t q = first; q < v.size(); ++q)
-    if (eq(v[q], x)) return (int)(q - first);
-  v.push_back(x);
-  return (int)(v.size() - 1 - first);
+static bool is_pair_family(int f) {
+  return f == ITEM_UPS_EXP || f == ITEM_UPS_GAUSS || f == ITEM_PHI_EXP || f == ITEM_PHI_GAUSS;
 }
 
-static const double SQRT_2PI = 2.50662827463100050242;
-
-// Turn the eligible rows of one (stream, target block) group into class terms.
-static void build_class_terms(const aslsd_ctx* ctx, BatchPlan& B, const std::vector<int64_t>& group,
-                              std::vector<bool>& fast, std::vector<int64_t>& boundary_from) {
-  const ItemDev first = B.rows[group[0]];
-  const bool is_phi = first.family == ITEM_PHI_GAUSS;
-  double t_int = 0.;
-  if (!is_phi)
-    for (int64_t r : group) t_int = std::max(t_int, B.rows[r].t_int);
-  const int64_t m_b = is_phi ? first.m_hi : interior_end(ctx, first.tgt_dim, first.m_lo, first.m_hi, t_int);
-  if (m_b - first.m_lo < CK_TM / 4) return;   // not worth a launch: the per-item kernels take it all
-  auto e_eq = [](const EClassDev& a, const EClassDev& b) { return a.dd == b.dd && a.isig == b.isig && a.pn == b.pn; };
-  auto n_eq = [](const NClassDev& a, const NClassDev& b) { return a.one == b.one && a.c0 == b.c0 && a.c1 == b.c1; };
-  size_t g = 0;
-  while (g < group.size()) {
-    ClassTermDev T;
-    std::memset(&T, 0, sizeof(T));
-    T.tgt_dim = first.tgt_dim;
-    T.src_dim = first.src_dim;
-    T.same = first.same;
-    T.m_lo = first.m_lo;
-    T.m_hi = m_b;
-    T.e_first = (int32_t)B.ecls.size();
-    T.n_first = (int32_t)B.ncls.size();
-    T.prod_first = (int32_t)B.prods.size();
-    T.s_lo = 1e300;
-    T.s_hi = 0.;
-    for (; g < group.size(); ++g) {
-      const ItemDev it = B.rows[group[g]];
-      // classes of this row
-      EClassDev E;
-      NClassDev N;
-      std::memset(&E, 0, sizeof(E));
-      std::memset(&N, 0, sizeof(N));
-      if (is_phi) {
-        E.dd = it.d1;
-        E.isig = 1. / it.b1;
-        E.pn = 1. / (it.b1 * SQRT_2PI);
-        N.one = 1;
-      } else {
-        const double sig2 = it.b1 * it.b1 + it.b2 * it.b2, sig = std::sqrt(sig2);
-        E.dd = it.d2 - it.d1;
-        E.isig = 1. / sig;
-        E.pn = 1. / (sig * SQRT_2PI);
-        const double inv_bs = sig / (it.b1 * it.b2);
-        const double r1 = (it.b2 * it.b2) / sig2, r2 = (it.b1 * it.b1) / sig2;
-        // lower limit lo = c0 + c1 s of the reference's gaussian_int; stored divided by
-        // sqrt(2): Q = 1 - Phi(lo) = erfc(lo / sqrt(2)) / 2
-        N.c0 = -(r1 * it.d1 + r2 * it.d2) * inv_bs / std::sqrt(2.);
-        N.c1 = r2 * inv_bs / std::sqrt(2.);
-      }
-      const size_t e_before = B.ecls.size(), n_before = B.ncls.size();
-      const int e = find_or_add(B.ecls, (size_t)T.e_first, E, e_eq);
-      const int n = find_or_add(B.ncls, (size_t)T.n_first, N, n_eq);
-      int n_one = -1;
-      const bool want_sw = !is_phi && (it.mask & MASK(C_SW));
-      if (want_sw) {
-        NClassDev one;
-        std::memset(&one, 0, sizeof(one));
-        one.one = 1;
-        n_one = find_or_add(B.ncls, (size_t)T.n_first, one, n_eq);
-      }
-      const int n_new = 1 + (want_sw ? 1 : 0);
-      const bool over = (int)(B.ecls.size() - T.e_first) > CK_MAX_CLASSES ||
-                        (int)(B.ncls.size() - T.n_first) > CK_MAX_CLASSES ||
-                        (int)(B.prods.size() - T.prod_first) + n_new > 32 * CK_MAXR;
-      if (over && B.prods.size() > (size_t)T.prod_first) {
-        B.ecls.resize(e_before);
-        B.ncls.resize(n_before);
-        break;   // close this class term, the row opens the next one
-      }
-      ProdDev P;
-      std::memset(&P, 0, sizeof(P));
-      P.e = (int16_t)e;
-      P.n = (int16_t)n;
-      P.dst = (int32_t)(group[g] * ASLSD_MAX_COMP + (is_phi ? 0 : C_G));
-      P.scale = 1.;
-      B.prods.push_back(P);
-      if (want_sw) {
-        // own-basis d/d omega: 2 P0(s) I0 with the verbatim (unshifted) limits; in the
-        // interior I0 = 1 - Phi(-sqrt(2) delta / beta) is a constant of the basis
-        const double lo0 = -std::sqrt(2.) * it.dlo / it.bo;
-        const double i0 = 1.0 - 0.5 * std::erfc(-lo0 / std::sqrt(2.));
-        P.n = (int16_t)n_one;
-        P.dst = (int32_t)(group[g] * ASLSD_MAX_COMP + C_SW);
-        P.scale = 2. * i0;
-        B.prods.push_back(P);
-      }
-      T.s_lo = std::min(T.s_lo, it.s_lo);
-      T.s_hi = std::max(T.s_hi, it.s_hi);
-      fast[group[g]] = true;
-      boundary_from[group[g]] = m_b;
+// Smallest length scale (in the lag) of the functions a row sums: the bin width of
+// its stream is a fixed fraction of it (lag_quadrature.cuh).
+static double row_scale(const ItemDev& it) {
+  const bool own = (it.mask & (MASK(C_SW) | MASK(C_SB) | MASK(C_SD))) != 0;
+  switch (it.family) {
+    case ITEM_PHI_EXP: return 1. / it.b1;
+    case ITEM_PHI_GAUSS: return it.b1;
+    case ITEM_UPS_EXP: return 1. / (own ? std::max(it.b2, it.bo) : it.b2);
+    default: {
+      // P(s): std sigma; lower limit of the integral: slope beta1 / (beta2 sigma) in s;
+      // own-basis forms: std sqrt(2) beta
+      const double sig = std::sqrt(it.b1 * it.b1 + it.b2 * it.b2);
+      double sc = std::min(sig, it.b2 * sig / it.b1);
+      if (own) sc = std::min(sc, std::sqrt(2.) * it.bo);
+      return sc;
     }
-    T.nE = (int32_t)(B.ecls.size() - T.e_first);
-    T.nN = (int32_t)(B.ncls.size() - T.n_first);
-    T.nProd = (int32_t)(B.prods.size() - T.prod_first);
-    B.class_smem = std::max(B.class_smem, class_smem_bytes(T.nE, T.nN, T.nProd));
-    B.cterms.push_back(T);
+  }
+}
+
+// Turn the pair rows of one (target stream, source stream, target block) into a
+// quadrature stream, if the geometry allows it.
+static void build_stream(const aslsd_ctx* ctx, BatchPlan& B, const std::vector<int64_t>& group,
+                         std::vector<bool>& fast, std::vector<int64_t>& boundary_from,
+                         std::vector<ItemDev> qfam[8]) {
+  const ItemDev first = B.rows[group[0]];
+  double t_int = 0., s_max = 0., scale = 1e300;
+  for (int64_t r : group) {
+    const ItemDev& it = B.rows[r];
+    const bool is_phi = it.family == ITEM_PHI_EXP || it.family == ITEM_PHI_GAUSS;
+    if (!is_phi) t_int = std::max(t_int, it.t_int);   // phi does not depend on T_f - t_m
+    s_max = std::max(s_max, it.s_hi);
+    scale = std::min(scale, row_scale(it));
+  }
+  if (!(scale > 0.) || !(s_max > 0.) || !std::isfinite(s_max) || !std::isfinite(t_int)) return;
+  const int64_t m_b = interior_end(ctx, first.tgt_dim, first.m_lo, first.m_hi, t_int);
+  if (m_b - first.m_lo < LQ_TM / 2) return;   // the per-item kernels take it all
+  const double h = LQ_SCALE_FRACTION * scale;
+  const double nb = std::floor(s_max / h) + 1.;
+  if (!(nb <= (double)LQ_JMAX)) return;
+  QStreamDev S;
+  std::memset(&S, 0, sizeof(S));
+  S.tgt_dim = first.tgt_dim;
+  S.src_dim = first.src_dim;
+  S.same = first.same;
+  S.J = (int32_t)nb;
+  S.m_lo = first.m_lo;
+  S.m_hi = m_b;
+  S.s_max = s_max;
+  S.h = h;
+  S.inv_h = 1. / h;
+  const int sx = (int)B.qstreams.size();
+  B.qstreams.push_back(S);
+  B.q_jmax = std::max(B.q_jmax, (int)S.J);
+  for (int64_t r : group) {
+    ItemDev it = B.rows[r];
+    it.dst_row = r;
+    it.wu_first = sx;
+    it.m_hi = m_b;
+    qfam[it.family].push_back(it);
+    fast[r] = true;
+    boundary_from[r] = m_b;
+    const int64_t j_lo = std::max<int64_t>(0, (int64_t)std::floor(it.s_lo / h) - 1);
+    const int64_t j_hi = std::min<int64_t>(S.J - 1, (int64_t)std::floor(it.s_hi / h) + 1);
+    B.n_q_evals += std::max<int64_t>(0, j_hi - j_lo + 1) * LQ_ND;
   }
 }
 
@@ -219,14 +172,15 @@ static int build_batch(aslsd_ctx* ctx, int n_k, const int* ks, const double* con
   const size_t n_rows = B.rows.size();
   std::vector<bool> fast(n_rows, false);
   std::vector<int64_t> boundary_from(n_rows, 0);
-  if (ctx->use_class_kernel) {
-    // group the eligible rows by (kind, streams, target block), in row order
-    std::map<std::array<int64_t, 6>, std::vector<int64_t>> groups;
-    std::vector<std::array<int64_t, 6>> order;
+  std::vector<ItemDev> qfam[8];
+  if (ctx->use_quadrature) {
+    // group the pair rows by (streams, target block), in row order
+    std::map<std::array<int64_t, 4>, std::vector<int64_t>> groups;
+    std::vector<std::array<int64_t, 4>> order;
     for (size_t r = 0; r < n_rows; ++r) {
       const ItemDev& it = B.rows[r];
-      if (!class_eligible(it) || it.m_hi <= it.m_lo) continue;
-      std::array<int64_t, 6> key = {it.family, it.tgt_dim, it.src_dim, it.same, it.m_lo, it.m_hi};
+      if (!is_pair_family(it.family) || it.m_hi <= it.m_lo) continue;
+      std::array<int64_t, 4> key = {it.tgt_dim, it.src_dim, it.m_lo, it.m_hi};
       auto f = groups.find(key);
       if (f == groups.end()) {
         order.push_back(key);
@@ -234,9 +188,14 @@ static int build_batch(aslsd_ctx* ctx, int n_k, const int* ks, const double* con
       }
       f->second.push_back((int64_t)r);
     }
-    for (auto& key : order) build_class_terms(ctx, B, groups[key], fast, boundary_from);
+    for (auto& key : order) build_stream(ctx, B, groups[key], fast, boundary_from, qfam);
   }
-  // ---- per-item kernels: non-class rows entirely, class rows beyond the interior -----------
+  for (int f = 0; f < 8; ++f) {
+    B.qfam_first[f] = (int)B.qrows.size();
+    B.qfam_count[f] = (int)qfam[f].size();
+    B.qrows.insert(B.qrows.end(), qfam[f].begin(), qfam[f].end());
+  }
+  // ---- per-item kernels: rows outside the quadrature entirely, the others beyond the interior ----
   std::vector<ItemDev> fam_items[8];
   for (size_t r = 0; r < n_rows; ++r) {
     ItemDev it = B.rows[r];
@@ -244,6 +203,11 @@ static int build_batch(aslsd_ctx* ctx, int n_k, const int* ks, const double* con
     if (fast[r]) {
       if (boundary_from[r] >= it.m_hi) continue;
       it.m_lo = boundary_from[r];
+    } else if (!is_pair_family(it.family) && it.m_hi > it.m_lo && std::isfinite(it.t_int)) {
+      // single-index rows are constant in the interior: n_int x closed form
+      const int64_t m_b = interior_end(ctx, it.tgt_dim, it.m_lo, it.m_hi, it.t_int);
+      it.n_int = m_b - it.m_lo;
+      it.m_lo = m_b;
     }
     fam_items[it.family].push_back(it);
   }
@@ -253,7 +217,7 @@ static int build_batch(aslsd_ctx* ctx, int n_k, const int* ks, const double* con
     B.fam_first[f] = base;
     B.fam_count[f] = (int)fam_items[f].size();
     B.fam_wu_first[f] = wu;
-    const bool pair = (f == ITEM_UPS_EXP || f == ITEM_UPS_GAUSS || f == ITEM_PHI_EXP || f == ITEM_PHI_GAUSS);
+    const bool pair = is_pair_family(f);
     int64_t tot_targets = 0;
     for (auto& it : fam_items[f]) tot_targets += std::max<int64_t>(0, it.m_hi - it.m_lo);
     // enough work units for a few waves of 148 SMs x 2 CTAs, each spanning whole tiles
@@ -264,6 +228,7 @@ static int build_batch(aslsd_ctx* ctx, int n_k, const int* ks, const double* con
     for (auto& it : fam_items[f]) {
       it.tpw = tpw;
       it.n_chunks = it.m_hi > it.m_lo ? (int)((it.m_hi - it.m_lo + tpw - 1) / tpw) : 0;
+      if (it.n_chunks == 0 && it.n_int > 0) it.n_chunks = 1;   // a CTA to add the interior constant
       it.wu_first = wu;
       wu += it.n_chunks;
       B.items.push_back(it);
@@ -272,24 +237,28 @@ static int build_batch(aslsd_ctx* ctx, int n_k, const int* ks, const double* con
     base += B.fam_count[f];
   }
   B.n_wu = wu;
-  // ---- class terms: work units of whole tiles, a few waves over the 148 SMs ----------------
+  // ---- quadrature streams: work units of whole tiles, a few waves over the 148 SMs ----------
   int64_t tot = 0;
-  for (auto& T : B.cterms) tot += T.m_hi - T.m_lo;
+  for (auto& S : B.qstreams) tot += S.m_hi - S.m_lo;
   int64_t tpw = (tot + 148 * 2 * 6 - 1) / (148 * 2 * 6);
-  tpw = std::max<int64_t>(CK_TM, std::min<int64_t>(tpw, 32 * CK_TM));
-  tpw = ((tpw + CK_TM - 1) / CK_TM) * CK_TM;
-  int64_t cwu = 0, part = 0;
-  for (auto& T : B.cterms) {
-    T.tpw = tpw;
-    T.n_chunks = (int32_t)((T.m_hi - T.m_lo + tpw - 1) / tpw);
-    T.wu_first = cwu;
-    T.part_first = part;
-    cwu += T.n_chunks;
-    part += (int64_t)T.n_chunks * T.nProd;
+  tpw = std::max<int64_t>(LQ_TM, std::min<int64_t>(tpw, 64 * LQ_TM));
+  tpw = ((tpw + LQ_TM - 1) / LQ_TM) * LQ_TM;
+  int64_t qwu = 0, part = 0, wts = 0;
+  for (auto& S : B.qstreams) {
+    S.tpw = tpw;
+    S.n_chunks = (int32_t)((S.m_hi - S.m_lo + tpw - 1) / tpw);
+    S.wu_first = qwu;
+    S.part_first = part;
+    S.w_first = wts;
+    qwu += S.n_chunks;
+    part += (int64_t)S.n_chunks * S.J * LQ_ND;
+    wts += (int64_t)S.J * LQ_ND;
   }
-  B.n_wu_class = cwu;
-  B.n_class_partials = part;
-  if (B.n_wu >= (int64_t)2147483647 || cwu >= (int64_t)2147483647)
+  B.n_wu_q = qwu;
+  B.n_q_partials = part;
+  B.n_q_weights = wts;
+  B.q_smem = B.q_jmax ? lq_smem_bytes(B.q_jmax) : 0;
+  if (B.n_wu >= (int64_t)2147483647 || qwu >= (int64_t)2147483647)
     return aslsd_fail(ctx, ASLSD_ERR_ARG, "exact sums: too many work units");
   return ASLSD_OK;
 }
@@ -309,7 +278,7 @@ static int get_batch(aslsd_ctx* ctx, int n_k, const int* ks, const double* const
     key_rows.push_back((double)ks[q]);
     plan_shape_key(ctx, ks[q], xs[q], key_rows);
   }
-  key_work.push_back(ctx->use_class_kernel ? 1. : 0.);
+  key_work.push_back(ctx->use_quadrature ? 1. : 0.);
   for (int i = 0; i < ctx->d; ++i) {
     key_work.push_back(m_lo ? (double)m_lo[i] : -1.);
     key_work.push_back(m_hi ? (double)m_hi[i] : -1.);
@@ -353,6 +322,30 @@ static void launch_single(aslsd_ctx* ctx, const BatchPlan& B, const ItemDev* d_i
   ctx->last_launches++;
 }
 
+static int upload_quadrature_tables(aslsd_ctx* ctx) {
+  if (ctx->lq_tables_set) return ASLSD_OK;
+  double x[LQ_ND], ct[LQ_ND * LQ_ND];
+  const double pi = 3.14159265358979323846;
+  for (int i = 0; i < LQ_ND; ++i) {
+    x[i] = std::cos(pi * (i + 0.5) / LQ_ND);
+    for (int d = 0; d < LQ_ND; ++d)
+      ct[i * LQ_ND + d] = (d == 0 ? 1. : 2.) / LQ_ND * std::cos(pi * d * (i + 0.5) / LQ_ND);
+  }
+  CUDA_TRY(ctx, cudaMemcpyToSymbol(LQ_X, x, sizeof(x)));
+  CUDA_TRY(ctx, cudaMemcpyToSymbol(LQ_CT, ct, sizeof(ct)));
+  ctx->lq_tables_set = true;
+  return ASLSD_OK;
+}
+
+template <int FAMILY>
+static void launch_quad(aslsd_ctx* ctx, const BatchPlan& B, const QStreamDev* d_streams, const ItemDev* d_qrows,
+                        double* raw_device) {
+  if (B.qfam_count[FAMILY] == 0) return;
+  lag_quad_kernel<FAMILY><<<(unsigned)B.qfam_count[FAMILY], LQ_QT, 0, ctx->stream>>>(
+      d_streams, d_qrows + B.qfam_first[FAMILY], ctx->d_q_weights, raw_device);
+  ctx->last_launches++;
+}
+
 // Launch everything; leaves raw[row][comp] in raw_device (zeroed here first).
 static int run_batch(aslsd_ctx* ctx, BatchPlan& B, double* raw_device) {
   CUDA_TRY(ctx, cudaSetDevice(ctx->device));
@@ -361,8 +354,11 @@ static int run_batch(aslsd_ctx* ctx, BatchPlan& B, double* raw_device) {
   ctx->last_launches = 0;
   ctx->last_n_wu = B.n_wu;
   ctx->last_n_items = (int)n_items;
-  ctx->last_n_wu_class = B.n_wu_class;
+  ctx->last_n_wu_q = B.n_wu_q;
   for (int f = 0; f < 8; ++f) { ctx->last_fam_first[f] = B.fam_first[f]; ctx->last_fam_count[f] = B.fam_count[f]; }
+  ctx->last_work[3] = B.n_q_evals;
+  ctx->last_work[4] = (int64_t)B.qstreams.size();
+  ctx->last_work[5] = B.n_q_weights / LQ_ND;
   ctx->last_work[6] = (int64_t)n_rows;
   ctx->last_work[7] = B.n_items_total;
   if ((rc = ensure_device_buffer(ctx, &ctx->d_items, &ctx->items_cap, std::max<size_t>(1, n_items) * sizeof(ItemDev))))
@@ -370,58 +366,52 @@ static int run_batch(aslsd_ctx* ctx, BatchPlan& B, double* raw_device) {
   if ((rc = ensure_device_buffer(ctx, (void**)&ctx->d_partials, &ctx->partials_cap,
                                  std::max<size_t>(1, (size_t)B.n_wu) * ASLSD_MAX_COMP * sizeof(double)))) return rc;
   if ((rc = ensure_device_buffer(ctx, (void**)&ctx->d_counts, &ctx->counts_cap,
-                                 ((size_t)B.n_wu + n_items + (size_t)B.n_wu_class + 1) * sizeof(unsigned long long))))
+                                 ((size_t)B.n_wu + n_items + (size_t)B.n_wu_q + 1) * sizeof(unsigned long long))))
     return rc;
   if (n_items && !B.device_resident)
     CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_items, B.items.data(), n_items * sizeof(ItemDev),
                                   cudaMemcpyHostToDevice, ctx->stream));
-  // class-kernel tables: one block [terms | P classes | Q classes | products]
-  const size_t o_t = 0;
-  const size_t o_e = o_t + ((B.cterms.size() * sizeof(ClassTermDev) + 15) & ~(size_t)15);
-  const size_t o_n = o_e + ((B.ecls.size() * sizeof(EClassDev) + 15) & ~(size_t)15);
-  const size_t o_p = o_n + ((B.ncls.size() * sizeof(NClassDev) + 15) & ~(size_t)15);
-  const size_t c_bytes = o_p + B.prods.size() * sizeof(ProdDev);
-  if (!B.cterms.empty() && B.device_resident) {
-    if ((rc = ensure_device_buffer(ctx, (void**)&ctx->d_class_partials, &ctx->class_partials_cap,
-                                   (size_t)B.n_class_partials * sizeof(double)))) return rc;
+  // quadrature tables: one block [streams | rows]
+  const bool quad = !B.qstreams.empty();
+  const size_t o_s = 0;
+  const size_t o_r = o_s + ((B.qstreams.size() * sizeof(QStreamDev) + 15) & ~(size_t)15);
+  const size_t q_bytes = o_r + B.qrows.size() * sizeof(ItemDev);
+  if (quad) {
+    if ((rc = upload_quadrature_tables(ctx))) return rc;
+    if ((rc = ensure_device_buffer(ctx, (void**)&ctx->d_q_partials, &ctx->q_partials_cap,
+                                   (size_t)B.n_q_partials * sizeof(double)))) return rc;
+    if ((rc = ensure_device_buffer(ctx, (void**)&ctx->d_q_weights, &ctx->q_weights_cap,
+                                   (size_t)B.n_q_weights * sizeof(double)))) return rc;
   }
-  if (!B.cterms.empty() && !B.device_resident) {
-    if ((rc = ensure_device_buffer(ctx, &ctx->d_class, &ctx->class_cap, c_bytes))) return rc;
-    if ((rc = ensure_device_buffer(ctx, (void**)&ctx->d_class_partials, &ctx->class_partials_cap,
-                                   (size_t)B.n_class_partials * sizeof(double)))) return rc;
-    if ((rc = ensure_pinned_buffer(ctx, c_bytes))) return rc;
+  if (quad && !B.device_resident) {
+    if ((rc = ensure_device_buffer(ctx, &ctx->d_qtab, &ctx->qtab_cap, q_bytes))) return rc;
+    if ((rc = ensure_pinned_buffer(ctx, q_bytes))) return rc;
     char* hp = (char*)ctx->h_pinned;
-    std::memcpy(hp + o_t, B.cterms.data(), B.cterms.size() * sizeof(ClassTermDev));
-    std::memcpy(hp + o_e, B.ecls.data(), B.ecls.size() * sizeof(EClassDev));
-    std::memcpy(hp + o_n, B.ncls.data(), B.ncls.size() * sizeof(NClassDev));
-    std::memcpy(hp + o_p, B.prods.data(), B.prods.size() * sizeof(ProdDev));
-    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_class, hp, c_bytes, cudaMemcpyHostToDevice, ctx->stream));
+    std::memcpy(hp + o_s, B.qstreams.data(), B.qstreams.size() * sizeof(QStreamDev));
+    std::memcpy(hp + o_r, B.qrows.data(), B.qrows.size() * sizeof(ItemDev));
+    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_qtab, hp, q_bytes, cudaMemcpyHostToDevice, ctx->stream));
     // the pinned staging block is reused by the caller once the copy has completed
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
   }
   B.device_resident = true;
-  // static per-pair costs of the class terms are turned into totals in aslsd_last_work_counts
-  ctx->last_class_cost.clear();
-  for (auto& T : B.cterms) {
-    int n_norm = 0;
-    for (int q = 0; q < T.nN; ++q) n_norm += B.ncls[T.n_first + q].one ? 0 : 1;
-    for (int w = 0; w < T.n_chunks; ++w) ctx->last_class_cost.push_back({T.nE, n_norm, T.nProd});
-  }
   const ItemDev* d_items = (const ItemDev*)ctx->d_items;
+  const QStreamDev* d_streams = (const QStreamDev*)((const char*)ctx->d_qtab + o_s);
+  const ItemDev* d_qrows = (const ItemDev*)((const char*)ctx->d_qtab + o_r);
   CUDA_TRY(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
   CUDA_TRY(ctx, cudaMemsetAsync(raw_device, 0, std::max<size_t>(1, n_rows) * ASLSD_MAX_COMP * sizeof(double),
                                 ctx->stream));
-  if (!B.cterms.empty()) {
-    const char* dc = (const char*)ctx->d_class;
-    if (B.class_smem > ctx->class_smem_set) {
-      CUDA_TRY(ctx, cudaFuncSetAttribute(class_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)B.class_smem));
-      ctx->class_smem_set = B.class_smem;
+  if (quad) {
+    if (B.q_smem > ctx->q_smem_set) {
+      CUDA_TRY(ctx, cudaFuncSetAttribute(lag_moment_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)B.q_smem));
+      ctx->q_smem_set = B.q_smem;
     }
-    class_kernel<<<(unsigned)B.n_wu_class, CK_NT, B.class_smem, ctx->stream>>>(
-        (const DimDev*)ctx->d_dims, (const ClassTermDev*)(dc + o_t), (int)B.cterms.size(),
-        (const EClassDev*)(dc + o_e), (const NClassDev*)(dc + o_n), (const ProdDev*)(dc + o_p),
-        ctx->d_class_partials, ctx->d_counts + B.n_wu + n_items);
+    lag_moment_kernel<<<(unsigned)B.n_wu_q, LQ_NT, B.q_smem, ctx->stream>>>(
+        (const DimDev*)ctx->d_dims, d_streams, (int)B.qstreams.size(), ctx->d_q_partials,
+        ctx->d_counts + B.n_wu + n_items);
+    ctx->last_launches++;
+    const dim3 wgrid((unsigned)((B.q_jmax + LQ_WB - 1) / LQ_WB), (unsigned)B.qstreams.size());
+    lag_weights_kernel<<<wgrid, LQ_WB * LQ_ND, 0, ctx->stream>>>(d_streams, ctx->d_q_partials, ctx->d_q_weights);
     ctx->last_launches++;
   }
   launch_pair<ITEM_UPS_GAUSS>(ctx, B, d_items);
@@ -439,12 +429,11 @@ static int run_batch(aslsd_ctx* ctx, BatchPlan& B, double* raw_device) {
                                                                   ctx->d_counts + B.n_wu);
     ctx->last_launches++;
   }
-  if (!B.cterms.empty()) {
-    const char* dc = (const char*)ctx->d_class;
-    class_finalize_kernel<<<(unsigned)B.cterms.size(), 128, 0, ctx->stream>>>(
-        (const ClassTermDev*)(dc + o_t), (int)B.cterms.size(), (const ProdDev*)(dc + o_p),
-        ctx->d_class_partials, raw_device);
-    ctx->last_launches++;
+  if (quad) {
+    launch_quad<ITEM_UPS_GAUSS>(ctx, B, d_streams, d_qrows, raw_device);
+    launch_quad<ITEM_UPS_EXP>(ctx, B, d_streams, d_qrows, raw_device);
+    launch_quad<ITEM_PHI_GAUSS>(ctx, B, d_streams, d_qrows, raw_device);
+    launch_quad<ITEM_PHI_EXP>(ctx, B, d_streams, d_qrows, raw_device);
   }
   CUDA_TRY(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
   ctx->timing_pending = true;
@@ -540,7 +529,7 @@ extern "C" int aslsd_exact_out_len(const aslsd_ctx* ctx, int k, int64_t* out_len
 
 extern "C" int aslsd_set_option(aslsd_ctx* ctx, int option, int value) {
   if (!ctx) return ASLSD_ERR_ARG;
-  if (option == ASLSD_OPT_CLASS_KERNEL) { ctx->use_class_kernel = value != 0; ctx->epoch++; return ASLSD_OK; }
+  if (option == ASLSD_OPT_LAG_QUADRATURE) { ctx->use_quadrature = value != 0; ctx->epoch++; return ASLSD_OK; }
   return aslsd_fail(ctx, ASLSD_ERR_ARG, "set_option: unknown option");
 }
 
@@ -636,14 +625,15 @@ extern "C" int aslsd_exact_assemble(aslsd_ctx* ctx, int k, const double* x_k, in
 // Work performed by the last exact-sum call (roofline accounting):
 //   [0] basis-pair closed-form evaluations of the per-item pair kernels
 //   [1] evaluations of the single-index kernels
-//   [2] event pairs visited by the shared-class kernel
-//   [3] exp evaluations, [4] normcdf evaluations, [5] multiply-adds of the shared-class kernel
+//   [2] event pairs binned by the lag-moment kernel
+//   [3] closed-form evaluations of the quadrature rows (row x node)
+//   [4] quadrature streams, [5] bins over all streams
 //   [6] rows (unique work items), [7] work items before de-duplication
 extern "C" int aslsd_last_work_counts(aslsd_ctx* ctx, int64_t* counts, int n) {
   if (!ctx || !counts || n < 8) return ASLSD_ERR_ARG;
   CUDA_TRY(ctx, cudaSetDevice(ctx->device));
   const size_t n_old = (size_t)ctx->last_n_wu + (size_t)ctx->last_n_items;
-  const size_t n_all = n_old + (size_t)ctx->last_n_wu_class;
+  const size_t n_all = n_old + (size_t)ctx->last_n_wu_q;
   std::vector<unsigned long long> h(std::max<size_t>(1, n_all));
   if (n_all) {
     CUDA_TRY(ctx, cudaMemcpyAsync(h.data(), ctx->d_counts, sizeof(unsigned long long) * n_all,
@@ -652,28 +642,16 @@ extern "C" int aslsd_last_work_counts(aslsd_ctx* ctx, int64_t* counts, int n) {
   }
   int64_t pe = 0, se = 0;
   for (int f = 0; f < 8; ++f) {
-    const bool pair = (f == ITEM_UPS_EXP || f == ITEM_UPS_GAUSS || f == ITEM_PHI_EXP || f == ITEM_PHI_GAUSS);
+    const bool pair = is_pair_family(f);
     for (int x = 0; x < ctx->last_fam_count[f]; ++x)
       (pair ? pe : se) += (int64_t)h[(size_t)ctx->last_n_wu + ctx->last_fam_first[f] + x];
   }
   counts[0] = pe;
   counts[1] = se;
-  int64_t pairs = 0, n_exp = 0, n_norm = 0, n_fma = 0;
-  for (int64_t w = 0; w < ctx->last_n_wu_class; ++w) {
-    const int64_t p = (int64_t)h[n_old + (size_t)w];
-    pairs += p;
-    if ((size_t)w < ctx->last_class_cost.size()) {
-      n_exp += p * ctx->last_class_cost[w][0];
-      n_norm += p * ctx->last_class_cost[w][1];
-      n_fma += p * ctx->last_class_cost[w][2];
-    }
-  }
+  int64_t pairs = 0;
+  for (int64_t w = 0; w < ctx->last_n_wu_q; ++w) pairs += (int64_t)h[n_old + (size_t)w];
   counts[2] = pairs;
-  counts[3] = n_exp;
-  counts[4] = n_norm;
-  counts[5] = n_fma;
-  counts[6] = ctx->last_work[6];
-  counts[7] = ctx->last_work[7];
+  for (int c = 3; c < 8; ++c) counts[c] = ctx->last_work[c];
   return ASLSD_OK;
 }
 

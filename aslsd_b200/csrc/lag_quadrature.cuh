@@ -1,0 +1,413 @@
+// Lag quadrature: the interior of every exact double sum in one pass over the event pairs.
+//
+// For a target m far enough from T_f every double-sum term of the LSE,
+//     sum_{m} sum_{n : t_n < t_m} f(t_m - t_n),           f = phi, d phi, Upsilon(+inf, .), d Upsilon(+inf, .)
+// (mhp_exact_estimator.py:611-707 with the closed forms of basis_kernel_gaussian.py /
+// basis_kernel_exponential.py), depends on the pair only through the lag s = t_m - t_n, and every f is
+// an entire function of s whose scale (beta, sigma, 1/beta ...) is known.  All terms that share the
+// ordered pair of event streams (target type, source type) therefore sum *different functions over the
+// same multiset of lags*.  That multiset is compressed once into a quadrature rule:
+//
+//   1. lag_moment_kernel   [0, s_max] is cut into J bins of width h (a fraction of the smallest scale);
+//                          with u in [-1, 1] the position of a lag inside its bin, the kernel accumulates
+//                          the Chebyshev moments  M[b][d] = sum_{pairs in bin b} T_d(u),  d < LQ_ND.
+//   2. lag_weights_kernel  W[b][i] = sum_d a_d T_d(x_i) M[b][d]  at the LQ_ND Chebyshev nodes x_i of the
+//                          bin: sum_pairs p(s) = sum_{b,i} W[b][i] p(s_{b,i}) exactly for every piecewise
+//                          polynomial p of degree < LQ_ND.
+//   3. lag_quad_kernel     every row (one basis / basis pair of one term) evaluates the reference's
+//                          closed form at the J * LQ_ND nodes and takes the dot product with W.
+//
+// Degree-11 interpolation on bins of 0.3 scale units reproduces these functions to ~1e-15 of their
+// maximum (scripts/quadrature_error.py), far inside the 1e-10 parity bar, and steps 1-2 do not depend on
+// the parameters at all.  The O(pairs) work drops from one exp + one erfc per (pair, basis pair) to ~2
+// fp64 instructions per (pair, Chebyshev degree); the closed forms are evaluated O(rows * J * LQ_ND) times.
+//
+// lag_moment_kernel, one CTA = (stream, block of targets), per tile of LQ_TM targets:
+//   a. per-target source range through the bucket table, exclusive scan, TMA bulk copy of the source
+//      window into shared memory (as in pair_kernels.cuh);
+//   b. counting sort of the tile's lags by bin, in chunks of LQ_UCAP pairs: thread-per-target
+//      enumeration, warp-private histograms, ranks from match.any (no atomics: the order inside a bin is
+//      fixed, the result is deterministic);
+//   c. every 8-lane group takes a bin: three-term recurrence, LQ_ND - 1 register accumulators per lane,
+//      transposed shuffle reduction, owner adds into the CTA's moment table;
+//   one partial table per work unit, reduced in fixed order by lag_weights_kernel.
+#pragma once
+
+#include "basis_math.cuh"
+#include "pair_kernels.cuh"
+
+#define LQ_NT 256                 // threads per CTA
+#define LQ_NW (LQ_NT / 32)
+#define LQ_K 2                    // targets per thread and tile
+#define LQ_TM (LQ_NT * LQ_K)
+#define LQ_UCAP 8192              // pairs sorted at a time (64 KB of bin coordinates)
+#define LQ_SMAX 2048              // staged source events per tile
+#define LQ_ND 12                  // Chebyshev terms = nodes per bin
+#define LQ_JMAX 1024              // bins per stream (212 KB of shared memory at the maximum)
+#define LQ_SCALE_FRACTION 0.3     // bin width in units of the smallest scale of the stream's rows
+#define LQ_MAGIC 6755399441055744.0   // 1.5 * 2^52: x + MAGIC holds rint(x) in its low word
+
+struct QStreamDev {
+  int32_t tgt_dim, src_dim, same, J;
+  int32_t n_chunks, pad;
+  int64_t m_lo, m_hi;      // interior target block
+  int64_t tpw;             // targets per work unit
+  int64_t wu_first;        // first work unit (prefix over streams)
+  int64_t part_first;      // partial moment tables: [chunk][J][LQ_ND] doubles
+  int64_t w_first;         // weights: [J][LQ_ND] doubles
+  double s_max, h, inv_h;
+};
+
+// x_i = cos(pi (i + 1/2) / ND) and a_d T_d(x_i) (a_0 = 1/ND, a_d = 2/ND), filled by the host
+__constant__ double LQ_X[LQ_ND];
+__constant__ double LQ_CT[LQ_ND * LQ_ND];   // [i][d]
+
+__host__ __device__ inline size_t lq_smem_bytes(int J) {
+  size_t b = 0;
+  b += (size_t)LQ_UCAP * sizeof(double);          // bin coordinates, sorted by bin
+  b += (size_t)(LQ_SMAX + 2) * sizeof(double);    // source window
+  b += (size_t)J * LQ_ND * sizeof(double);        // moment table
+  b += (size_t)LQ_NW * J * sizeof(int32_t);       // warp-private histograms / cursors
+  b += (size_t)(J + 1) * sizeof(int32_t);         // bin starts
+  return b + 64;
+}
+
+__device__ __forceinline__ int find_stream(const QStreamDev* __restrict__ streams, int n, int64_t wu) {
+  int lo = 0, hi = n;
+  while (hi - lo > 1) {
+    const int mid = (lo + hi) >> 1;
+    if (streams[mid].wu_first <= wu) lo = mid; else hi = mid;
+  }
+  return lo;
+}
+
+__global__ void __launch_bounds__(LQ_NT, 2)
+lag_moment_kernel(const DimDev* __restrict__ dims, const QStreamDev* __restrict__ streams, int n_streams,
+                  double* __restrict__ partials, unsigned long long* __restrict__ counts) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  __shared__ __align__(8) uint64_t s_bar;
+  __shared__ int64_t s_bounds[2];
+  __shared__ int32_t s_warp[LQ_NW];
+  __shared__ int32_t s_scan[LQ_NW];
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int64_t wu = blockIdx.x;
+  const QStreamDev S = streams[find_stream(streams, n_streams, wu)];
+  const int chunk = (int)(wu - S.wu_first);
+  const DimDev Dt = dims[S.tgt_dim], Ds = dims[S.src_dim];
+  const int64_t m_begin = S.m_lo + (int64_t)chunk * S.tpw;
+  const int64_t m_end = min(S.m_hi, m_begin + S.tpw);
+  const bool same = S.same != 0;
+  const int J = S.J;
+  const double inv_h = S.inv_h;
+
+  double* s_u = (double*)smem_raw;
+  double* s_src = s_u + LQ_UCAP;
+  double* s_M = s_src + (LQ_SMAX + 2);
+  int32_t* s_hist = (int32_t*)(s_M + (size_t)J * LQ_ND);
+  int32_t* s_bin = s_hist + LQ_NW * J;
+  int32_t* my_hist = s_hist + warp * J;
+
+  for (int x = tid; x < J * LQ_ND; x += LQ_NT) s_M[x] = 0.;
+  if (tid == 0) mbar_init(&s_bar, 1);
+  fence_proxy_async();
+  __syncthreads();
+  uint32_t parity = 0;
+  unsigned long long n_pairs = 0;
+  const unsigned lt_mask = (1u << lane) - 1u;
+
+  for (int64_t m0 = m_begin; m0 < m_end; m0 += LQ_TM) {
+    const int nt = (int)min((int64_t)LQ_TM, m_end - m0);
+    // ---- a. per-target source ranges ---------------------------------------------------------
+    double tm[LQ_K];
+    int64_t lo_abs[LQ_K];
+    int32_t cnt[LQ_K];
+    int32_t my_sum = 0;
+#pragma unroll
+    for (int u = 0; u < LQ_K; ++u) {
+      const int x = tid * LQ_K + u;
+      tm[u] = 0.;
+      lo_abs[u] = 0;
+      cnt[u] = 0;
+      if (x < nt) {
+        const double t = Dt.t[m0 + x];
+        tm[u] = t;
+        const int64_t hi = same ? (m0 + x) : dim_lower_bound(Ds, t);
+        const int64_t lo = min(dim_lower_bound(Ds, t - S.s_max), hi);
+        lo_abs[u] = lo;
+        cnt[u] = (int32_t)(hi - lo);
+        if (x == 0) s_bounds[0] = lo;
+        if (x == nt - 1) s_bounds[1] = hi;
+      }
+      my_sum += cnt[u];
+    }
+    int32_t incl = my_sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int32_t v = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += v;
+    }
+    if (lane == 31) s_warp[warp] = incl;
+    __syncthreads();
+    int32_t my_pre = incl - my_sum, total = 0;
+#pragma unroll
+    for (int w = 0; w < LQ_NW; ++w) {
+      const int32_t v = s_warp[w];
+      if (w < warp) my_pre += v;
+      total += v;
+    }
+    const int64_t src_first = s_bounds[0], src_end = s_bounds[1];
+    if (total == 0) { __syncthreads(); continue; }
+    // stage the source window
+    const int64_t a0 = src_first & ~(int64_t)1;
+    const int64_t n_stage = ((src_end - a0) + 1) & ~(int64_t)1;
+    const bool staged = n_stage <= LQ_SMAX;
+    if (staged) {
+      if (tid == 0) {
+        mbar_expect_tx(&s_bar, (uint32_t)(n_stage * sizeof(double)));
+        tma_load_1d(s_src, Ds.t + a0, (uint32_t)(n_stage * sizeof(double)), &s_bar);
+      }
+      mbar_wait(&s_bar, parity);
+      parity ^= 1;
+    }
+    const double* srcp = staged ? (s_src - a0) : Ds.t;
+    n_pairs += (unsigned long long)my_sum;
+
+    // ---- b / c. chunks of at most LQ_UCAP pairs -------------------------------------------------
+    for (int32_t c0 = 0; c0 < total; c0 += LQ_UCAP) {
+      // this thread's pairs with tile-wide index in [c0, c0 + LQ_UCAP)
+      const int32_t ra = min(max(c0 - my_pre, 0), my_sum);
+      const int32_t rb = min(max(c0 + LQ_UCAP - my_pre, 0), my_sum);
+      const int32_t rmax = __reduce_max_sync(0xffffffffu, rb - ra);
+      for (int x = tid; x < LQ_NW * J; x += LQ_NT) s_hist[x] = 0;
+      __syncthreads();
+      // pass 1: histogram; pass 2: placement.  Both walk the pairs in the same order.
+#pragma unroll 1
+      for (int pass = 0; pass < 2; ++pass) {
+#pragma unroll 1
+        for (int32_t q = 0; q < rmax; ++q) {
+          const int32_t r = ra + q;
+          const bool live = r < rb;
+          const bool second = r >= cnt[0];
+          const double t = second ? tm[1] : tm[0];
+          const int64_t n = second ? (lo_abs[1] + (r - cnt[0])) : (lo_abs[0] + r);
+          int b = J + lane;   // idle lanes: private pseudo-bins
+          double uu = 0.;
+          if (live) {
+            const double s = t - srcp[n];
+            const double xb = fma(s, inv_h, -0.5);
+            const double tr = xb + LQ_MAGIC;
+            b = min(max(__double2loint(tr), 0), J - 1);
+            uu = 2. * (xb - (double)b);
+          }
+          const unsigned peers = __match_any_sync(0xffffffffu, b);
+          const int rank = __popc(peers & lt_mask);
+          if (pass == 0) {
+            if (live && rank == 0) my_hist[b] += __popc(peers);
+          } else {
+            if (live) {
+              const int32_t base = my_hist[b];
+              s_u[base + rank] = uu;
+            }
+            __syncwarp();
+            if (live && rank == 0) my_hist[b] += __popc(peers);
+          }
+          __syncwarp();
+        }
+        __syncthreads();
+        if (pass == 0) {
+          // bin totals -> bin starts; per-warp cursors = start + counts of the lower warps
+          // (thread tid owns the jpt consecutive bins from tid * jpt)
+          const int jpt = (J + LQ_NT - 1) / LQ_NT;
+          int32_t tot = 0;
+          for (int q = 0; q < jpt; ++q) {
+            const int b = tid * jpt + q;
+            if (b < J) {
+#pragma unroll
+              for (int w = 0; w < LQ_NW; ++w) tot += s_hist[w * J + b];
+            }
+          }
+          int32_t inc = tot;
+#pragma unroll
+          for (int o = 1; o < 32; o <<= 1) {
+            const int32_t v = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += v;
+          }
+          if (lane == 31) s_scan[warp] = inc;
+          __syncthreads();
+          int32_t run = inc - tot;
+          for (int w = 0; w < warp; ++w) run += s_scan[w];
+          for (int q = 0; q < jpt; ++q) {
+            const int b = tid * jpt + q;
+            if (b < J) {
+              s_bin[b] = run;
+#pragma unroll
+              for (int w = 0; w < LQ_NW; ++w) {
+                const int32_t v = s_hist[w * J + b];
+                s_hist[w * J + b] = run;
+                run += v;
+              }
+              if (b == J - 1) s_bin[J] = run;
+            }
+          }
+          __syncthreads();
+        }
+      }
+      // ---- c. moments of every bin: 8 lanes per bin ---------------------------------------------
+      const int grp = lane >> 3, q8 = lane & 7;
+      for (int b0 = warp * 4; b0 < J; b0 += LQ_NW * 4) {
+        const int b = b0 + grp;
+        int32_t e0 = 0, e1 = 0;
+        if (b < J) { e0 = s_bin[b]; e1 = s_bin[b + 1]; }
+        double acc[LQ_ND];
+#pragma unroll
+        for (int d = 0; d < LQ_ND; ++d) acc[d] = 0.;
+        for (int32_t e = e0 + q8; e < e1; e += 8) {
+          const double uu = s_u[e];
+          const double two_u = uu + uu;
+          double tp = 1., tc = uu;
+          acc[1] += tc;
+#pragma unroll
+          for (int d = 2; d < LQ_ND; ++d) {
+            const double tn = fma(two_u, tc, -tp);
+            tp = tc;
+            tc = tn;
+            acc[d] += tn;
+          }
+        }
+        if (q8 == 0) acc[0] = (double)(e1 - e0);   // T_0 = 1: the bin count, exact
+        // transposed reduction over the 8 lanes: 12 -> 6 -> 3 values per lane
+        {
+          const bool up = (q8 & 4) != 0;
+#pragma unroll
+          for (int i = 0; i < 6; ++i) {
+            const double send = up ? acc[i] : acc[i + 6];
+            const double keep = up ? acc[i + 6] : acc[i];
+            acc[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+          }
+        }
+        {
+          const bool up = (q8 & 2) != 0;
+#pragma unroll
+          for (int i = 0; i < 3; ++i) {
+            const double send = up ? acc[i] : acc[i + 3];
+            const double keep = up ? acc[i + 3] : acc[i];
+            acc[i] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+          }
+        }
+#pragma unroll
+        for (int i = 0; i < 3; ++i) acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], 1);
+        if (b < J && (q8 & 1) == 0 && e1 > e0) {
+          const int d0 = ((q8 & 4) ? 6 : 0) + ((q8 & 2) ? 3 : 0);
+          double* Mb = s_M + (size_t)b * LQ_ND + d0;
+          Mb[0] += acc[0];
+          Mb[1] += acc[1];
+          Mb[2] += acc[2];
+        }
+      }
+      __syncthreads();
+    }
+    fence_proxy_async();   // generic reads of s_src before the next tile's async write
+    __syncthreads();
+  }
+  // ---- one partial moment table per work unit ---------------------------------------------------
+  double* out = partials + S.part_first + (int64_t)chunk * J * LQ_ND;
+  for (int x = tid; x < J * LQ_ND; x += LQ_NT) out[x] = s_M[x];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) n_pairs += __shfl_xor_sync(0xffffffffu, n_pairs, o);
+  __shared__ unsigned long long s_cnt[LQ_NW];
+  if (lane == 0) s_cnt[warp] = n_pairs;
+  __syncthreads();
+  if (tid == 0) {
+    unsigned long long c = 0;
+    for (int w = 0; w < LQ_NW; ++w) c += s_cnt[w];
+    counts[wu] = c;
+  }
+}
+
+// Moments of a stream (partials summed in work-unit order) -> node weights.
+// grid = (bins in groups of LQ_WB, streams); block = LQ_WB * LQ_ND threads.
+#define LQ_WB 16
+__global__ void __launch_bounds__(LQ_WB * LQ_ND)
+lag_weights_kernel(const QStreamDev* __restrict__ streams, const double* __restrict__ partials,
+                   double* __restrict__ weights) {
+  __shared__ double s_m[LQ_WB][LQ_ND];
+  const QStreamDev S = streams[blockIdx.y];
+  const int jb = threadIdx.x / LQ_ND, c = threadIdx.x % LQ_ND;
+  const int j = blockIdx.x * LQ_WB + jb;
+  if (blockIdx.x * LQ_WB >= S.J) return;
+  double v = 0.;
+  if (j < S.J) {
+    const double* p = partials + S.part_first + (int64_t)j * LQ_ND + c;
+    const int64_t stride = (int64_t)S.J * LQ_ND;
+    for (int w = 0; w < S.n_chunks; ++w) v += p[(int64_t)w * stride];
+  }
+  s_m[jb][c] = v;
+  __syncthreads();
+  if (j < S.J) {
+    double w = 0.;
+#pragma unroll
+    for (int d = 0; d < LQ_ND; ++d) w = fma(LQ_CT[c * LQ_ND + d], s_m[jb][d], w);
+    weights[S.w_first + (int64_t)j * LQ_ND + c] = w;
+  }
+}
+
+// Rows: the closed form of every row at the nodes of its stream, dotted with the weights.
+// One CTA per row; the row's ItemDev carries the stream index in wu_first.
+// FAMILY: ITEM_UPS_EXP, ITEM_UPS_GAUSS, ITEM_PHI_EXP, ITEM_PHI_GAUSS
+#define LQ_QT 128
+template <int FAMILY>
+__global__ void __launch_bounds__(LQ_QT)
+lag_quad_kernel(const QStreamDev* __restrict__ streams, const ItemDev* __restrict__ rows,
+                const double* __restrict__ weights, double* __restrict__ raw) {
+  __shared__ double s_red[(LQ_QT / 32) * ASLSD_MAX_COMP];
+  const ItemDev it = rows[blockIdx.x];
+  const QStreamDev S = streams[it.wu_first];
+  const int mask = it.mask;
+  UpsGaussConst KG;
+  UpsExpConst KE;
+  PhiConst KP;
+  if (FAMILY == ITEM_UPS_GAUSS) KG.init(it);
+  if (FAMILY == ITEM_UPS_EXP) KE.init(it);
+  if (FAMILY == ITEM_PHI_EXP || FAMILY == ITEM_PHI_GAUSS) KP.init(it);
+  // bins that meet the row's lag window
+  int j_lo = (int)floor(it.s_lo * S.inv_h) - 1, j_hi = (int)floor(it.s_hi * S.inv_h) + 1;
+  j_lo = max(j_lo, 0);
+  j_hi = min(j_hi, S.J - 1);
+  const double* W = weights + S.w_first;
+  double acc[ASLSD_MAX_COMP];
+#pragma unroll
+  for (int c = 0; c < ASLSD_MAX_COMP; ++c) acc[c] = 0.;
+  for (int q = j_lo * LQ_ND + threadIdx.x; q < (j_hi + 1) * LQ_ND; q += LQ_QT) {
+    const double w = W[q];
+    if (w == 0.) continue;
+    const int j = q / LQ_ND, i = q - j * LQ_ND;
+    const double s = S.h * ((double)j + 0.5 + 0.5 * LQ_X[i]);
+    double v[ASLSD_MAX_COMP];
+#pragma unroll
+    for (int c = 0; c < ASLSD_MAX_COMP; ++c) v[c] = 0.;
+    if (FAMILY == ITEM_UPS_GAUSS) eval_ups_gauss<true>(KG, mask, 0., s, v);
+    else if (FAMILY == ITEM_UPS_EXP) eval_ups_exp<true>(KE, mask, 0., s, v);
+    else if (FAMILY == ITEM_PHI_EXP) eval_phi_exp(KP, mask, s, v);
+    else eval_phi_gauss(KP, mask, s, v);
+#pragma unroll
+    for (int c = 0; c < ASLSD_MAX_COMP; ++c) acc[c] = fma(w, v[c], acc[c]);
+  }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int c = 0; c < ASLSD_MAX_COMP; ++c) {
+    double v = acc[c];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (lane == 0) s_red[warp * ASLSD_MAX_COMP + c] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < ASLSD_MAX_COMP) {
+    double v = 0.;
+#pragma unroll
+    for (int w = 0; w < LQ_QT / 32; ++w) v += s_red[w * ASLSD_MAX_COMP + threadIdx.x];
+    // every row owns its destination (the boundary targets of the same row are added by
+    // finalize_kernel, which runs before on the same stream)
+    raw[it.dst_row * ASLSD_MAX_COMP + threadIdx.x] += v;
+  }
+}

@@ -265,6 +265,21 @@ single_kernel(const DimDev* __restrict__ dims, const ItemDev* __restrict__ items
     }
     ++n_eval;
   }
+  if (chunk == 0 && tid == 0 && it.n_int > 0) {
+    // interior targets: the closed form no longer depends on T_f - t_m (upper limits at
+    // +infinity, exactly what fp64 gives there): one evaluation times their number
+    double v[ASLSD_MAX_COMP];
+#pragma unroll
+    for (int c = 0; c < ASLSD_MAX_COMP; ++c) v[c] = 0.;
+    const double t_far = 1e300;
+    if (FAMILY == ITEM_UPS0_GAUSS) eval_ups_gauss<true>(KG, mask, 0., 0., v);
+    else if (FAMILY == ITEM_UPS0_EXP) eval_ups_exp<true>(KE, mask, 0., 0., v);
+    else if (FAMILY == ITEM_PSI_EXP) eval_psi_exp(KP, mask, t_far, v);
+    else eval_psi_gauss(KP, mask, t_far, v);
+#pragma unroll
+    for (int c = 0; c < ASLSD_MAX_COMP; ++c) acc[c] += (double)it.n_int * v[c];
+    ++n_eval;
+  }
   block_reduce_store<ASLSD_MAX_COMP>(acc, n_eval, s_red, partials + wu * ASLSD_MAX_COMP, counts + wu);
 }
 

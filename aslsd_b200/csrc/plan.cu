@@ -202,7 +202,9 @@ static void plan_basis_items(SumPlan& P, std::vector<ItemDev> fam_items[8],
       *u_lo = std::min(*u_lo, it.s_lo);
       *u_hi = std::max(*u_hi, it.s_hi);
     }
-    it.t_int = 1e300;   // psi is evaluated per target
+    // phi has no T_f - t_m dependence; psi is constant once its upper limit saturates
+    if (is_phi) it.t_int = 1e300;
+    else it.t_int = is_exp ? C_INTERIOR / V[r][1] : V[r][2] + X_INTERIOR * V[r][1];
     const int sf = by_term ? 0 : it.family;
     fam_items[sf].push_back(it);
     const int idx = (int)fam_items[sf].size() - 1;

@@ -107,17 +107,17 @@ class Engine:
     def set_option(self, option, value):
         self._check(self._lib.aslsd_set_option(self._ctx, int(option), int(value)))
 
-    def use_class_kernel(self, enabled=True):
-        """Shared-class kernel for the interior of Gaussian upsilon / phi value rows
-        (default on); off: every row goes through the per-item pair kernels."""
-        self.set_option(capi.OPT_CLASS_KERNEL, 1 if enabled else 0)
+    def use_lag_quadrature(self, enabled=True):
+        """Lag quadrature for the interior targets of every double sum (default on);
+        off: every row goes through the per-item pair kernels."""
+        self.set_option(capi.OPT_LAG_QUADRATURE, 1 if enabled else 0)
 
     def last_work_counts(self):
         """Work of the last exact-sum call (see aslsd_last_work_counts)."""
         c = np.zeros(8, dtype=np.int64)
         self._check(self._lib.aslsd_last_work_counts(self._ctx, capi.ptr_i64(c), 8))
-        names = ('pair_evals', 'single_evals', 'class_pairs', 'class_exp', 'class_normcdf',
-                 'class_fma', 'rows', 'items')
+        names = ('pair_evals', 'single_evals', 'moment_pairs', 'quad_evals', 'streams', 'bins',
+                 'rows', 'items')
         return dict(zip(names, (int(v) for v in c)))
 
     def last_eval_counts(self):

@@ -9,8 +9,9 @@ calls of ``lse_k_grad_estimate`` compute, issued as ONE batched call
 (aslsd_exact_sums_batch); nothing is cached between steps.  Within a step the
 raw basis-pair sums that several sub-problems share (beta / delta are fixed in
 this model, so upsilon_i_j rows do not depend on k) are evaluated once, and the
-interior of every Gaussian row goes through the shared-class kernel; both are
-exact algebra, reported in ``config.work``.
+interior targets of every double sum go through the lag quadrature (one pass
+over the event pairs of each ordered pair of event streams, csrc/lag_quadrature.cuh);
+the work actually executed is reported in ``config.work``.
 The unit counted is the in-window event pair of a named double sum (phi_i,
 upsilon_i_j) of one k.
 
@@ -34,22 +35,22 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-# flops per closed-form evaluation, SURVEY 8d conventions (add/mul 1, FMA 2,
-# div/sqrt 10, EXP 25, NDTR 60): interior Gaussian upsilon value of one basis pair
-# = 1 EXP + 1 NDTR + 12 (per-item kernels); shared-class kernel: per event pair
-# and class 1 EXP + 4 (P class) or 1 NDTR + 3 (Q class), 2 per product
+# flops per unit of executed work, SURVEY 8d conventions (add/mul 1, FMA 2, div/sqrt 10,
+# EXP 25, NDTR 60).  Per-item pair kernels and quadrature rows: interior Gaussian upsilon
+# value of one basis pair = 1 EXP + 1 NDTR + 12.  Lag-moment kernel, per event pair:
+# lag, bin and bin coordinate (2 add, 1 FMA, 1 mul) twice (histogram and placement pass) +
+# three-term recurrence (LQ_ND - 2 FMA) + LQ_ND - 1 accumulations.
+LQ_ND = 12
 FLOPS_UPS_EVAL = 25 + 60 + 12
-FLOPS_PHI_EVAL = 25 + 4
-FLOPS_CLASS_EXP = 25 + 4
-FLOPS_CLASS_NDTR = 60 + 3
-FLOPS_CLASS_FMA = 2
+FLOPS_SINGLE_EVAL = 60 + 10
+FLOPS_MOMENT_PAIR = 2 * 5 + 2 * (LQ_ND - 2) + (LQ_ND - 1)
 
 
 def executed_flops(work):
-    """fp64 flops actually executed by the pair kernels of one call, from the
-    engine's own counters (aslsd_last_work_counts)."""
-    return (work['pair_evals'] * FLOPS_UPS_EVAL + work['class_exp'] * FLOPS_CLASS_EXP
-            + work['class_normcdf'] * FLOPS_CLASS_NDTR + work['class_fma'] * FLOPS_CLASS_FMA)
+    """fp64 flops actually executed by the kernels of one call, from the engine's own
+    counters (aslsd_last_work_counts)."""
+    return ((work['pair_evals'] + work['quad_evals']) * FLOPS_UPS_EVAL
+            + work['single_evals'] * FLOPS_SINGLE_EVAL + work['moment_pairs'] * FLOPS_MOMENT_PAIR)
 
 
 def parse_args():
@@ -64,7 +65,7 @@ def parse_args():
     ap.add_argument('--cpu_sample_T', type=float, default=600., help='time slice of the CPU baseline sample')
     ap.add_argument('--no_cpu_baseline', action='store_true')
     ap.add_argument('--per_k', action='store_true', help='one call per sub-problem (no sharing across k)')
-    ap.add_argument('--no_class_kernel', action='store_true', help='per-item pair kernels only')
+    ap.add_argument('--no_quadrature', action='store_true', help='per-item pair kernels only')
     return ap.parse_args()
 
 
@@ -229,7 +230,7 @@ def run_b200(args):
     engine.set_stream(torch.cuda.current_stream().cuda_stream)
     engine.set_events(times, T_f)
     engine.set_model(model)
-    engine.use_class_kernel(not args.no_class_kernel)
+    engine.use_lag_quadrature(not args.no_quadrature)
     ks = list(range(d))
     sharded = ShardedExactSums(engine, times, rank=rank, world_size=world,
                                dist=dist if world > 1 else None, device=device)
@@ -336,15 +337,18 @@ def run_b200(args):
                        'l2': 'flushed between steps (256 MB write)',
                        'work': dict(work, note='rank-0 counters of one step: rows = unique work items '
                                     'evaluated, items = work items of the d sub-problems before sharing; '
-                                    'class_* = shared-class kernel (event pairs, exp / normcdf / fma '
-                                    'evaluations), pair_evals = per-item kernel basis-pair evaluations'),
+                                    'moment_pairs = event pairs binned by the lag-moment kernel (streams, '
+                                    'bins: its quadrature streams / bins), quad_evals = closed-form '
+                                    'evaluations at quadrature nodes, pair_evals = per-item kernel '
+                                    'basis-pair evaluations (targets near T_f), single_evals = psi / '
+                                    'upsilonzero evaluations'),
                        'call': 'one call per k' if args.per_k else 'one batched call for all k',
                        'sharding': 'time blocks of target events, events replicated, '
                                    '1 NCCL allreduce per k' if world > 1 else 'single GPU'},
             'roofline': {'bound': 'fp64', 'achieved': achieved, 'peak': fp64_peak, 'unit': 'TFLOP/s',
                          'frac': (achieved / fp64_peak) if achieved else None, 'traffic': None,
-                         'kernel': 'class_kernel (+ per-item pair kernels on the boundary targets, '
-                                   'single-index kernels, finalize)',
+                         'kernel': 'lag_moment_kernel (+ weights, quadrature rows, per-item pair kernels '
+                                   'on the targets near T_f, single-index kernels, finalize)',
                          'reference_equivalent_tflops': pair_terms * 15700 / (ms_per_step * 1e-3) * 1e-12,
                          'reference_equivalent_note': 'pair-terms/s x 15 700 flops (SURVEY 8d figure for '
                                                       'one SBF-10 upsilon pair-term evaluated directly, '

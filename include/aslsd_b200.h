@@ -53,8 +53,9 @@ enum {
 
 /* Options of aslsd_set_option. */
 enum {
-  ASLSD_OPT_CLASS_KERNEL = 1 /* 1 (default): interior targets of Gaussian upsilon / phi value
-                                rows go through the shared-class kernel; 0: per-item kernels only */
+  ASLSD_OPT_LAG_QUADRATURE = 1 /* 1 (default): interior targets of every double sum go through the
+                                  lag quadrature (one pass per pair of event streams);
+                                  0: per-item pair kernels only */
 };
 
 /* ---- lifetime ------------------------------------------------------------------ */
