@@ -116,12 +116,16 @@ static void build_stream(const aslsd_ctx* ctx, BatchPlan& B, const std::vector<i
   const double h = LQ_SCALE_FRACTION * scale;
   const double nb = std::floor(s_max / h) + 1.;
   if (!(nb <= (double)LQ_JMAX)) return;
+  const int ucap = lq_pick_ucap((int)nb);
+  if (ucap == 0) return;
   QStreamDev S;
   std::memset(&S, 0, sizeof(S));
   S.tgt_dim = first.tgt_dim;
   S.src_dim = first.src_dim;
   S.same = first.same;
   S.J = (int32_t)nb;
+  S.ucap = ucap;
+  while ((1 << S.nbits) < S.J) ++S.nbits;
   S.m_lo = first.m_lo;
   S.m_hi = m_b;
   S.s_max = s_max;
@@ -130,6 +134,7 @@ static void build_stream(const aslsd_ctx* ctx, BatchPlan& B, const std::vector<i
   const int sx = (int)B.qstreams.size();
   B.qstreams.push_back(S);
   B.q_jmax = std::max(B.q_jmax, (int)S.J);
+  B.q_smem = std::max(B.q_smem, lq_smem_bytes(S.J, S.ucap));
   for (int64_t r : group) {
     ItemDev it = B.rows[r];
     it.dst_row = r;
@@ -257,7 +262,6 @@ static int build_batch(aslsd_ctx* ctx, int n_k, const int* ks, const double* con
   B.n_wu_q = qwu;
   B.n_q_partials = part;
   B.n_q_weights = wts;
-  B.q_smem = B.q_jmax ? lq_smem_bytes(B.q_jmax) : 0;
   if (B.n_wu >= (int64_t)2147483647 || qwu >= (int64_t)2147483647)
     return aslsd_fail(ctx, ASLSD_ERR_ARG, "exact sums: too many work units");
   return ASLSD_OK;

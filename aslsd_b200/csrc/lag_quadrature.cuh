@@ -22,12 +22,16 @@
 // the parameters at all.  The O(pairs) work drops from one exp + one erfc per (pair, basis pair) to ~2
 // fp64 instructions per (pair, Chebyshev degree); the closed forms are evaluated O(rows * J * LQ_ND) times.
 //
-// lag_moment_kernel, one CTA = (stream, block of targets), per tile of LQ_TM targets:
-//   a. per-target source range through the bucket table, exclusive scan, TMA bulk copy of the source
-//      window into shared memory (as in pair_kernels.cuh);
-//   b. counting sort of the tile's lags by bin, in chunks of LQ_UCAP pairs: thread-per-target
-//      enumeration, warp-private histograms, ranks from match.any (no atomics: the order inside a bin is
-//      fixed, the result is deterministic);
+// lag_moment_kernel, one CTA = (stream, block of targets), per tile of LQ_TM targets (one per thread):
+//   a. per-target source range through the bucket table, exclusive scan of the pair counts, TMA bulk
+//      copy of the source window into shared memory (as in pair_kernels.cuh);
+//   b. counting sort of the tile's lags by bin, in chunks of `ucap` pairs.  The pairs are enumerated
+//      densely (target-major; an owner table maps pair -> target), so every lane of every warp holds a
+//      pair.  Pass 1: bin and in-bin coordinate of each pair, rank among the equal bins of the warp
+//      step from ballots over the bits of the bin index (match.any measured ~300 cycles: XU pipe),
+//      running count in a warp-private histogram -> (bin, rank in warp) key.  Scan of the histograms.
+//      Pass 2: coordinates move to their sorted slots.  No atomics: the order inside a bin is fixed
+//      and the result is deterministic;
 //   c. every 8-lane group takes a bin: three-term recurrence, LQ_ND - 1 register accumulators per lane,
 //      transposed shuffle reduction, owner adds into the CTA's moment table;
 //   one partial table per work unit, reduced in fixed order by lag_weights_kernel.
@@ -36,20 +40,21 @@
 #include "basis_math.cuh"
 #include "pair_kernels.cuh"
 
-#define LQ_NT 256                 // threads per CTA
+#define LQ_NT 512                 // threads per CTA (one CTA per SM)
 #define LQ_NW (LQ_NT / 32)
-#define LQ_K 2                    // targets per thread and tile
-#define LQ_TM (LQ_NT * LQ_K)
-#define LQ_UCAP 8192              // pairs sorted at a time (64 KB of bin coordinates)
+#define LQ_TM LQ_NT               // targets per tile: one per thread
+#define LQ_UCAP_MAX 8192          // pairs sorted at a time
 #define LQ_SMAX 2048              // staged source events per tile
 #define LQ_ND 12                  // Chebyshev terms = nodes per bin
-#define LQ_JMAX 1024              // bins per stream (212 KB of shared memory at the maximum)
+#define LQ_JMAX 1024              // bins per stream
+#define LQ_SMEM_BUDGET (220 * 1024)
 #define LQ_SCALE_FRACTION 0.3     // bin width in units of the smallest scale of the stream's rows
 #define LQ_MAGIC 6755399441055744.0   // 1.5 * 2^52: x + MAGIC holds rint(x) in its low word
 
 struct QStreamDev {
   int32_t tgt_dim, src_dim, same, J;
-  int32_t n_chunks, pad;
+  int32_t n_chunks, ucap;  // work units; pairs sorted at a time (multiple of LQ_NT)
+  int32_t nbits, pad;      // bits of the bin index
   int64_t m_lo, m_hi;      // interior target block
   int64_t tpw;             // targets per work unit
   int64_t wu_first;        // first work unit (prefix over streams)
@@ -62,14 +67,27 @@ struct QStreamDev {
 __constant__ double LQ_X[LQ_ND];
 __constant__ double LQ_CT[LQ_ND * LQ_ND];   // [i][d]
 
-__host__ __device__ inline size_t lq_smem_bytes(int J) {
+// dynamic shared memory: [pair-order coordinates | sorted coordinates | source window | target times |
+//                         moment table | keys | pair-minus-source offsets | bin starts | owners | histograms]
+__host__ __device__ inline size_t lq_smem_bytes(int J, int ucap) {
   size_t b = 0;
-  b += (size_t)LQ_UCAP * sizeof(double);          // bin coordinates, sorted by bin
-  b += (size_t)(LQ_SMAX + 2) * sizeof(double);    // source window
-  b += (size_t)J * LQ_ND * sizeof(double);        // moment table
-  b += (size_t)LQ_NW * J * sizeof(int32_t);       // warp-private histograms / cursors
-  b += (size_t)(J + 1) * sizeof(int32_t);         // bin starts
+  b += (size_t)ucap * sizeof(double) * 2;
+  b += (size_t)(LQ_SMAX + 2) * sizeof(double);
+  b += (size_t)LQ_TM * sizeof(double);
+  b += (size_t)J * LQ_ND * sizeof(double);
+  b += (size_t)ucap * sizeof(uint32_t);
+  b += (size_t)LQ_TM * sizeof(int32_t);
+  b += (size_t)(J + 2) * sizeof(int32_t);
+  b += (size_t)ucap * sizeof(uint16_t);
+  b += (size_t)LQ_NW * J * sizeof(uint16_t);
   return b + 64;
+}
+
+// largest chunk (multiple of LQ_NT) that fits the budget; 0 if none does
+inline int lq_pick_ucap(int J) {
+  for (int u = LQ_UCAP_MAX; u >= LQ_NT; u -= LQ_NT)
+    if (lq_smem_bytes(J, u) <= (size_t)LQ_SMEM_BUDGET) return u;
+  return 0;
 }
 
 __device__ __forceinline__ int find_stream(const QStreamDev* __restrict__ streams, int n, int64_t wu) {
@@ -81,7 +99,7 @@ __device__ __forceinline__ int find_stream(const QStreamDev* __restrict__ stream
   return lo;
 }
 
-__global__ void __launch_bounds__(LQ_NT, 2)
+__global__ void __launch_bounds__(LQ_NT, 1)
 lag_moment_kernel(const DimDev* __restrict__ dims, const QStreamDev* __restrict__ streams, int n_streams,
                   double* __restrict__ partials, unsigned long long* __restrict__ counts) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -98,15 +116,20 @@ lag_moment_kernel(const DimDev* __restrict__ dims, const QStreamDev* __restrict_
   const int64_t m_begin = S.m_lo + (int64_t)chunk * S.tpw;
   const int64_t m_end = min(S.m_hi, m_begin + S.tpw);
   const bool same = S.same != 0;
-  const int J = S.J;
+  const int J = S.J, ucap = S.ucap, nbits = S.nbits;
   const double inv_h = S.inv_h;
 
-  double* s_u = (double*)smem_raw;
-  double* s_src = s_u + LQ_UCAP;
-  double* s_M = s_src + (LQ_SMAX + 2);
-  int32_t* s_hist = (int32_t*)(s_M + (size_t)J * LQ_ND);
-  int32_t* s_bin = s_hist + LQ_NW * J;
-  int32_t* my_hist = s_hist + warp * J;
+  double* s_val = (double*)smem_raw;
+  double* s_u = s_val + ucap;
+  double* s_src = s_u + ucap;
+  double* s_t = s_src + (LQ_SMAX + 2);
+  double* s_M = s_t + LQ_TM;
+  uint32_t* s_key = (uint32_t*)(s_M + (size_t)J * LQ_ND);
+  int32_t* s_off = (int32_t*)(s_key + ucap);
+  int32_t* s_bin = s_off + LQ_TM;
+  uint16_t* s_own = (uint16_t*)(s_bin + (J + 2));
+  uint16_t* s_hist = s_own + ucap;
+  uint16_t* my_hist = s_hist + warp * J;
 
   for (int x = tid; x < J * LQ_ND; x += LQ_NT) s_M[x] = 0.;
   if (tid == 0) mbar_init(&s_bar, 1);
@@ -119,29 +142,18 @@ lag_moment_kernel(const DimDev* __restrict__ dims, const QStreamDev* __restrict_
   for (int64_t m0 = m_begin; m0 < m_end; m0 += LQ_TM) {
     const int nt = (int)min((int64_t)LQ_TM, m_end - m0);
     // ---- a. per-target source ranges ---------------------------------------------------------
-    double tm[LQ_K];
-    int64_t lo_abs[LQ_K];
-    int32_t cnt[LQ_K];
-    int32_t my_sum = 0;
-#pragma unroll
-    for (int u = 0; u < LQ_K; ++u) {
-      const int x = tid * LQ_K + u;
-      tm[u] = 0.;
-      lo_abs[u] = 0;
-      cnt[u] = 0;
-      if (x < nt) {
-        const double t = Dt.t[m0 + x];
-        tm[u] = t;
-        const int64_t hi = same ? (m0 + x) : dim_lower_bound(Ds, t);
-        const int64_t lo = min(dim_lower_bound(Ds, t - S.s_max), hi);
-        lo_abs[u] = lo;
-        cnt[u] = (int32_t)(hi - lo);
-        if (x == 0) s_bounds[0] = lo;
-        if (x == nt - 1) s_bounds[1] = hi;
-      }
-      my_sum += cnt[u];
+    int64_t lo_abs = 0;
+    int32_t cnt = 0;
+    if (tid < nt) {
+      const double t = Dt.t[m0 + tid];
+      s_t[tid] = t;
+      const int64_t hi = same ? (m0 + tid) : dim_lower_bound(Ds, t);
+      lo_abs = min(dim_lower_bound(Ds, t - S.s_max), hi);
+      cnt = (int32_t)(hi - lo_abs);
+      if (tid == 0) s_bounds[0] = lo_abs;
+      if (tid == nt - 1) s_bounds[1] = hi;
     }
-    int32_t incl = my_sum;
+    int32_t incl = cnt;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
       const int32_t v = __shfl_up_sync(0xffffffffu, incl, o);
@@ -149,11 +161,11 @@ lag_moment_kernel(const DimDev* __restrict__ dims, const QStreamDev* __restrict_
     }
     if (lane == 31) s_warp[warp] = incl;
     __syncthreads();
-    int32_t my_pre = incl - my_sum, total = 0;
+    int32_t pre = incl - cnt, total = 0;
 #pragma unroll
     for (int w = 0; w < LQ_NW; ++w) {
       const int32_t v = s_warp[w];
-      if (w < warp) my_pre += v;
+      if (w < warp) pre += v;
       total += v;
     }
     const int64_t src_first = s_bounds[0], src_end = s_bounds[1];
@@ -167,92 +179,104 @@ lag_moment_kernel(const DimDev* __restrict__ dims, const QStreamDev* __restrict_
         mbar_expect_tx(&s_bar, (uint32_t)(n_stage * sizeof(double)));
         tma_load_1d(s_src, Ds.t + a0, (uint32_t)(n_stage * sizeof(double)), &s_bar);
       }
+    }
+    // source index (relative to a0) minus tile-wide pair index, per target
+    if (tid < nt) s_off[tid] = (int32_t)(lo_abs - a0) - pre;
+    if (staged) {
       mbar_wait(&s_bar, parity);
       parity ^= 1;
     }
-    const double* srcp = staged ? (s_src - a0) : Ds.t;
-    n_pairs += (unsigned long long)my_sum;
+    const double* srcp = staged ? s_src : (Ds.t + a0);
+    n_pairs += (unsigned long long)cnt;
 
-    // ---- b / c. chunks of at most LQ_UCAP pairs -------------------------------------------------
-    for (int32_t c0 = 0; c0 < total; c0 += LQ_UCAP) {
-      // this thread's pairs with tile-wide index in [c0, c0 + LQ_UCAP)
-      const int32_t ra = min(max(c0 - my_pre, 0), my_sum);
-      const int32_t rb = min(max(c0 + LQ_UCAP - my_pre, 0), my_sum);
-      const int32_t rmax = __reduce_max_sync(0xffffffffu, rb - ra);
-      for (int x = tid; x < LQ_NW * J; x += LQ_NT) s_hist[x] = 0;
+    // ---- b / c. chunks of at most ucap pairs ------------------------------------------------------
+    for (int32_t c0 = 0; c0 < total; c0 += ucap) {
+      const int32_t n_c = min(ucap, total - c0);
+      // owner table of the chunk; histograms to zero
+      {
+        const int32_t pa = max(pre, c0), pb = min(pre + cnt, c0 + n_c);
+        for (int32_t p = pa; p < pb; ++p) s_own[p - c0] = (uint16_t)tid;
+      }
+      for (int x = tid; x < (LQ_NW * J + 1) / 2; x += LQ_NT) ((uint32_t*)s_hist)[x] = 0u;
       __syncthreads();
-      // pass 1: histogram; pass 2: placement.  Both walk the pairs in the same order.
-#pragma unroll 1
-      for (int pass = 0; pass < 2; ++pass) {
-#pragma unroll 1
-        for (int32_t q = 0; q < rmax; ++q) {
-          const int32_t r = ra + q;
-          const bool live = r < rb;
-          const bool second = r >= cnt[0];
-          const double t = second ? tm[1] : tm[0];
-          const int64_t n = second ? (lo_abs[1] + (r - cnt[0])) : (lo_abs[0] + r);
-          int b = J + lane;   // idle lanes: private pseudo-bins
-          double uu = 0.;
-          if (live) {
-            const double s = t - srcp[n];
-            const double xb = fma(s, inv_h, -0.5);
-            const double tr = xb + LQ_MAGIC;
-            b = min(max(__double2loint(tr), 0), J - 1);
-            uu = 2. * (xb - (double)b);
-          }
-          const unsigned peers = __match_any_sync(0xffffffffu, b);
-          const int rank = __popc(peers & lt_mask);
-          if (pass == 0) {
-            if (live && rank == 0) my_hist[b] += __popc(peers);
-          } else {
-            if (live) {
-              const int32_t base = my_hist[b];
-              s_u[base + rank] = uu;
-            }
-            __syncwarp();
-            if (live && rank == 0) my_hist[b] += __popc(peers);
-          }
-          __syncwarp();
+      // pass 1: bin, coordinate, rank among the equal bins seen so far by this warp
+      for (int32_t q0 = warp * 32; q0 < n_c; q0 += LQ_NT) {
+        const int32_t q = q0 + lane;
+        const bool live = q < n_c;
+        int b = 0;
+        double uu = 0.;
+        if (live) {
+          const int x = s_own[q];
+          const double s = s_t[x] - srcp[s_off[x] + c0 + q];
+          const double xb = fma(s, inv_h, -0.5);
+          const double tr = xb + LQ_MAGIC;
+          b = __double2loint(tr);
+          uu = 2. * (xb - (tr - LQ_MAGIC));
+          if (b > J - 1) { b = J - 1; uu += 2.; }   // s == s_max up to rounding: stay in the last bin
+          b = max(b, 0);
         }
+        unsigned peers = __ballot_sync(0xffffffffu, live);
+        for (int k = 0; k < nbits; ++k) {
+          const bool bit = (b >> k) & 1;
+          const unsigned v = __ballot_sync(0xffffffffu, bit);
+          peers &= bit ? v : ~v;
+        }
+        const int rank = __popc(peers & lt_mask);
+        int base = 0;
+        if (live) base = my_hist[b];
+        __syncwarp();
+        if (live) {
+          if (rank == 0) my_hist[b] = (uint16_t)(base + __popc(peers));
+          s_key[q] = (uint32_t)b | ((uint32_t)(base + rank) << 10);
+          s_val[q] = uu;
+        }
+        __syncwarp();
+      }
+      __syncthreads();
+      // bin totals -> bin starts; per-warp cursors = start + counts of the lower warps
+      // (thread tid owns the jpt consecutive bins from tid * jpt)
+      {
+        const int jpt = (J + LQ_NT - 1) / LQ_NT;
+        int32_t tot = 0;
+        for (int q = 0; q < jpt; ++q) {
+          const int b = tid * jpt + q;
+          if (b < J) {
+#pragma unroll
+            for (int w = 0; w < LQ_NW; ++w) tot += s_hist[w * J + b];
+          }
+        }
+        int32_t inc = tot;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const int32_t v = __shfl_up_sync(0xffffffffu, inc, o);
+          if (lane >= o) inc += v;
+        }
+        if (lane == 31) s_scan[warp] = inc;
         __syncthreads();
-        if (pass == 0) {
-          // bin totals -> bin starts; per-warp cursors = start + counts of the lower warps
-          // (thread tid owns the jpt consecutive bins from tid * jpt)
-          const int jpt = (J + LQ_NT - 1) / LQ_NT;
-          int32_t tot = 0;
-          for (int q = 0; q < jpt; ++q) {
-            const int b = tid * jpt + q;
-            if (b < J) {
+        int32_t run = inc - tot;
+        for (int w = 0; w < warp; ++w) run += s_scan[w];
+        for (int q = 0; q < jpt; ++q) {
+          const int b = tid * jpt + q;
+          if (b < J) {
+            s_bin[b] = run;
 #pragma unroll
-              for (int w = 0; w < LQ_NW; ++w) tot += s_hist[w * J + b];
+            for (int w = 0; w < LQ_NW; ++w) {
+              const int32_t v = s_hist[w * J + b];
+              s_hist[w * J + b] = (uint16_t)run;
+              run += v;
             }
+            if (b == J - 1) s_bin[J] = run;
           }
-          int32_t inc = tot;
-#pragma unroll
-          for (int o = 1; o < 32; o <<= 1) {
-            const int32_t v = __shfl_up_sync(0xffffffffu, inc, o);
-            if (lane >= o) inc += v;
-          }
-          if (lane == 31) s_scan[warp] = inc;
-          __syncthreads();
-          int32_t run = inc - tot;
-          for (int w = 0; w < warp; ++w) run += s_scan[w];
-          for (int q = 0; q < jpt; ++q) {
-            const int b = tid * jpt + q;
-            if (b < J) {
-              s_bin[b] = run;
-#pragma unroll
-              for (int w = 0; w < LQ_NW; ++w) {
-                const int32_t v = s_hist[w * J + b];
-                s_hist[w * J + b] = run;
-                run += v;
-              }
-              if (b == J - 1) s_bin[J] = run;
-            }
-          }
-          __syncthreads();
         }
       }
+      __syncthreads();
+      // pass 2: coordinates to their sorted slots (pair q was ranked by warp (q / 32) % LQ_NW = warp)
+      for (int32_t q = tid; q < n_c; q += LQ_NT) {
+        const uint32_t key = s_key[q];
+        const int b = (int)(key & 1023u);
+        s_u[(int)my_hist[b] + (int)(key >> 10)] = s_val[q];
+      }
+      __syncthreads();
       // ---- c. moments of every bin: 8 lanes per bin ---------------------------------------------
       const int grp = lane >> 3, q8 = lane & 7;
       for (int b0 = warp * 4; b0 < J; b0 += LQ_NW * 4) {
