@@ -23,8 +23,11 @@
 // fp64 instructions per (pair, Chebyshev degree); the closed forms are evaluated O(rows * J * LQ_ND) times.
 //
 // lag_moment_kernel, one CTA = (stream, block of targets), per tile of LQ_TM targets (one per thread):
-//   a. per-target source range through the bucket table, exclusive scan of the pair counts, TMA bulk
-//      copy of the source window into shared memory (as in pair_kernels.cuh);
+//   a. the tile's source window sits in shared memory, fetched by one TMA bulk copy that was issued
+//      during the previous tile (the first source a tile can need is the window start of the previous
+//      tile's last target: no global search, two buffers); per-target source ranges by binary search
+//      in that window; exclusive scan of the pair counts.  A window that does not fit falls back to
+//      bucket-table searches and global reads for that tile;
 //   b. counting sort of the tile's lags by bin, in chunks of `ucap` pairs.  The pairs are enumerated
 //      densely (target-major; an owner table maps pair -> target), so every lane of every warp holds a
 //      pair.  Pass 1: bin and in-bin coordinate of each pair, rank among the equal bins of the warp
@@ -40,14 +43,19 @@
 #include "basis_math.cuh"
 #include "pair_kernels.cuh"
 
-#define LQ_NT 512                 // threads per CTA (one CTA per SM)
+#ifndef LQ_NT
+#define LQ_NT 512                 // threads per CTA
+#endif
+#ifndef LQ_CTAS
+#define LQ_CTAS 1                 // CTAs per SM the shared-memory budget is cut for
+#endif
 #define LQ_NW (LQ_NT / 32)
 #define LQ_TM LQ_NT               // targets per tile: one per thread
 #define LQ_UCAP_MAX 8192          // pairs sorted at a time
-#define LQ_SMAX 2048              // staged source events per tile
+#define LQ_SMAX 2048              // staged source events per tile (two buffers)
 #define LQ_ND 12                  // Chebyshev terms = nodes per bin
 #define LQ_JMAX 1024              // bins per stream
-#define LQ_SMEM_BUDGET (220 * 1024)
+#define LQ_SMEM_BUDGET ((LQ_CTAS == 1 ? 220 : 110) * 1024)
 #define LQ_SCALE_FRACTION 0.3     // bin width in units of the smallest scale of the stream's rows
 #define LQ_MAGIC 6755399441055744.0   // 1.5 * 2^52: x + MAGIC holds rint(x) in its low word
 
@@ -67,12 +75,12 @@ struct QStreamDev {
 __constant__ double LQ_X[LQ_ND];
 __constant__ double LQ_CT[LQ_ND * LQ_ND];   // [i][d]
 
-// dynamic shared memory: [pair-order coordinates | sorted coordinates | source window | target times |
-//                         moment table | keys | pair-minus-source offsets | bin starts | owners | histograms]
+// dynamic shared memory: [pair-order coordinates | sorted coordinates | 2 source windows | target times |
+//                         moment table | keys | source-minus-pair offsets | bin starts | owners | histograms]
 __host__ __device__ inline size_t lq_smem_bytes(int J, int ucap) {
   size_t b = 0;
   b += (size_t)ucap * sizeof(double) * 2;
-  b += (size_t)(LQ_SMAX + 2) * sizeof(double);
+  b += (size_t)(LQ_SMAX + 2) * sizeof(double) * 2;
   b += (size_t)LQ_TM * sizeof(double);
   b += (size_t)J * LQ_ND * sizeof(double);
   b += (size_t)ucap * sizeof(uint32_t);
@@ -99,12 +107,76 @@ __device__ __forceinline__ int find_stream(const QStreamDev* __restrict__ stream
   return lo;
 }
 
-__global__ void __launch_bounds__(LQ_NT, 1)
+// first index in [0, n) of the sorted shared array with win[idx] >= x (n if none)
+__device__ __forceinline__ int smem_lower_bound(const double* win, int n, double x) {
+  int lo = 0, len = n;
+  while (len > 0) {
+    const int half = len >> 1;
+    const bool go = win[lo + half] < x;
+    lo = go ? lo + half + 1 : lo;
+    len = go ? len - half - 1 : half;
+  }
+  return lo;
+}
+
+// lanes of the warp whose b equals this lane's, from ballots over NB bits
+template <int NB>
+__device__ __forceinline__ unsigned match_bins(int b) {
+  unsigned peers = 0xffffffffu;
+#pragma unroll
+  for (int k = 0; k < NB; ++k) {
+    const bool bit = (b & (1 << k)) != 0;
+    const unsigned v = __ballot_sync(0xffffffffu, bit);
+    peers &= bit ? v : ~v;
+  }
+  return peers;
+}
+
+// Pass 1 of the counting sort over the n_c pairs of a chunk (see the file header).
+template <int NB, bool STAGED>
+__device__ __forceinline__ void lq_pass1(int n_c, int c0, int J, double inv_h, const uint16_t* s_own,
+                                         const double* s_t, const int32_t* s_off, const double* s_win,
+                                         const double* __restrict__ g_win, uint16_t* my_hist,
+                                         uint32_t* s_key, double* s_val) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const unsigned lt_mask = (1u << lane) - 1u;
+  const int n_steps = (n_c + 31) >> 5;
+  for (int st = warp; st < n_steps; st += LQ_NW) {
+    const int q = st * 32 + lane;
+    const int left = n_c - st * 32;   // live lanes of this step (warp-uniform)
+    const unsigned live_mask = left >= 32 ? 0xffffffffu : ((1u << left) - 1u);
+    const bool live = q < n_c;
+    const int qq = live ? q : n_c - 1;   // idle lanes redo the last pair and store nothing
+    const int x = s_own[qq];
+    const int n = s_off[x] + c0 + qq;
+    const double s = s_t[x] - (STAGED ? s_win[n] : g_win[n]);
+    const double xb = fma(s, inv_h, -0.5);
+    const double tr = xb + LQ_MAGIC;
+    int b = __double2loint(tr);
+    double uu = xb - (tr - LQ_MAGIC);
+    uu += uu;
+    if (b > J - 1) { b = J - 1; uu += 2.; }   // s == s_max up to rounding: stay in the last bin
+    b = max(b, 0);
+    const unsigned peers = match_bins<NB>(b) & live_mask;
+    const int rank = __popc(peers & lt_mask);
+    const int base = my_hist[b];
+    __syncwarp();
+    if (live) {
+      if (rank == 0) my_hist[b] = (uint16_t)(base + __popc(peers));
+      s_key[q] = (uint32_t)b | ((uint32_t)(base + rank) << 10);
+      s_val[q] = uu;
+    }
+    __syncwarp();
+  }
+}
+
+__global__ void __launch_bounds__(LQ_NT, LQ_CTAS)
 lag_moment_kernel(const DimDev* __restrict__ dims, const QStreamDev* __restrict__ streams, int n_streams,
                   double* __restrict__ partials, unsigned long long* __restrict__ counts) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  __shared__ __align__(8) uint64_t s_bar;
-  __shared__ int64_t s_bounds[2];
+  __shared__ __align__(8) uint64_t s_bar[2];
+  __shared__ int64_t s_a0[2];        // first source index of each window buffer
+  __shared__ int64_t s_next_lo;      // window start of the tile's last target
   __shared__ int32_t s_warp[LQ_NW];
   __shared__ int32_t s_scan[LQ_NW];
 
@@ -118,11 +190,12 @@ lag_moment_kernel(const DimDev* __restrict__ dims, const QStreamDev* __restrict_
   const bool same = S.same != 0;
   const int J = S.J, ucap = S.ucap, nbits = S.nbits;
   const double inv_h = S.inv_h;
+  const int64_t n_src_padded = ((Ds.n + 1) & ~(int64_t)1) + 2;   // set_events pads every type (ctx.cu)
 
   double* s_val = (double*)smem_raw;
   double* s_u = s_val + ucap;
-  double* s_src = s_u + ucap;
-  double* s_t = s_src + (LQ_SMAX + 2);
+  double* s_src = s_u + ucap;                       // two buffers of LQ_SMAX + 2
+  double* s_t = s_src + 2 * (LQ_SMAX + 2);
   double* s_M = s_t + LQ_TM;
   uint32_t* s_key = (uint32_t*)(s_M + (size_t)J * LQ_ND);
   int32_t* s_off = (int32_t*)(s_key + ucap);
@@ -132,26 +205,58 @@ lag_moment_kernel(const DimDev* __restrict__ dims, const QStreamDev* __restrict_
   uint16_t* my_hist = s_hist + warp * J;
 
   for (int x = tid; x < J * LQ_ND; x += LQ_NT) s_M[x] = 0.;
-  if (tid == 0) mbar_init(&s_bar, 1);
-  fence_proxy_async();
+  if (tid == 0) {
+    mbar_init(&s_bar[0], 1);
+    mbar_init(&s_bar[1], 1);
+    fence_proxy_async();
+    // window of the first tile: starts at the first source its first target can reach
+    int64_t a0 = 0;
+    if (m_begin < m_end) a0 = dim_lower_bound(Ds, Dt.t[m_begin] - S.s_max) & ~(int64_t)1;
+    s_a0[0] = a0;
+    const int64_t n_stage = min((int64_t)LQ_SMAX, n_src_padded - a0);
+    if (m_begin < m_end) {
+      mbar_expect_tx(&s_bar[0], (uint32_t)(n_stage * sizeof(double)));
+      tma_load_1d(s_src, Ds.t + a0, (uint32_t)(n_stage * sizeof(double)), &s_bar[0]);
+    }
+  }
   __syncthreads();
-  uint32_t parity = 0;
+  uint32_t parity = 0u;   // bit b: phase of window buffer b
   unsigned long long n_pairs = 0;
-  const unsigned lt_mask = (1u << lane) - 1u;
+  double t_mine = (m_begin + tid < m_end) ? Dt.t[m_begin + tid] : 0.;
 
-  for (int64_t m0 = m_begin; m0 < m_end; m0 += LQ_TM) {
+  int tile = 0;
+  for (int64_t m0 = m_begin; m0 < m_end; m0 += LQ_TM, ++tile) {
     const int nt = (int)min((int64_t)LQ_TM, m_end - m0);
+    const int buf = tile & 1;
+    double* win = s_src + buf * (LQ_SMAX + 2);
     // ---- a. per-target source ranges ---------------------------------------------------------
+    const double t = t_mine;
+    if (tid < nt) s_t[tid] = t;
+    if (m0 + LQ_TM + tid < m_end) t_mine = Dt.t[m0 + LQ_TM + tid];   // next tile's target, in flight
+    mbar_wait(&s_bar[buf], (parity >> buf) & 1u);
+    parity ^= 1u << buf;
+    __syncthreads();
+    const int64_t a0 = s_a0[buf];
+    const int n_win = (int)min((int64_t)LQ_SMAX, n_src_padded - a0);
+    // the window serves the tile if it reaches the end of the stream or the last target (same type:
+    // by index, ties in time included; other types: by time, the searches are lower bounds)
+    const double t_last = s_t[nt - 1];
+    const bool staged = (a0 + n_win >= Ds.n) ||
+                        (same ? (a0 + n_win >= m0 + nt - 1) : (win[n_win - 1] >= t_last));
+    const int n_valid = (int)min((int64_t)n_win, Ds.n - a0);   // entries that are events, not padding
     int64_t lo_abs = 0;
     int32_t cnt = 0;
     if (tid < nt) {
-      const double t = Dt.t[m0 + tid];
-      s_t[tid] = t;
-      const int64_t hi = same ? (m0 + tid) : dim_lower_bound(Ds, t);
-      lo_abs = min(dim_lower_bound(Ds, t - S.s_max), hi);
+      int64_t hi;
+      if (staged) {
+        hi = same ? (m0 + tid) : a0 + smem_lower_bound(win, n_valid, t);
+        lo_abs = min(a0 + (int64_t)smem_lower_bound(win, n_valid, t - S.s_max), hi);
+      } else {
+        hi = same ? (m0 + tid) : dim_lower_bound(Ds, t);
+        lo_abs = min(dim_lower_bound(Ds, t - S.s_max), hi);
+      }
       cnt = (int32_t)(hi - lo_abs);
-      if (tid == 0) s_bounds[0] = lo_abs;
-      if (tid == nt - 1) s_bounds[1] = hi;
+      if (tid == nt - 1) s_next_lo = lo_abs;
     }
     int32_t incl = cnt;
 #pragma unroll
@@ -168,25 +273,19 @@ lag_moment_kernel(const DimDev* __restrict__ dims, const QStreamDev* __restrict_
       if (w < warp) pre += v;
       total += v;
     }
-    const int64_t src_first = s_bounds[0], src_end = s_bounds[1];
-    if (total == 0) { __syncthreads(); continue; }
-    // stage the source window
-    const int64_t a0 = src_first & ~(int64_t)1;
-    const int64_t n_stage = ((src_end - a0) + 1) & ~(int64_t)1;
-    const bool staged = n_stage <= LQ_SMAX;
-    if (staged) {
-      if (tid == 0) {
-        mbar_expect_tx(&s_bar, (uint32_t)(n_stage * sizeof(double)));
-        tma_load_1d(s_src, Ds.t + a0, (uint32_t)(n_stage * sizeof(double)), &s_bar);
-      }
+    // next tile's window into the other buffer (its readers finished before the previous tile's
+    // closing barrier)
+    if (tid == 0 && m0 + LQ_TM < m_end) {
+      const int64_t a1 = s_next_lo & ~(int64_t)1;
+      s_a0[buf ^ 1] = a1;
+      const int64_t n_stage = min((int64_t)LQ_SMAX, n_src_padded - a1);
+      mbar_expect_tx(&s_bar[buf ^ 1], (uint32_t)(n_stage * sizeof(double)));
+      tma_load_1d(s_src + (buf ^ 1) * (LQ_SMAX + 2), Ds.t + a1, (uint32_t)(n_stage * sizeof(double)),
+                  &s_bar[buf ^ 1]);
     }
     // source index (relative to a0) minus tile-wide pair index, per target
     if (tid < nt) s_off[tid] = (int32_t)(lo_abs - a0) - pre;
-    if (staged) {
-      mbar_wait(&s_bar, parity);
-      parity ^= 1;
-    }
-    const double* srcp = staged ? s_src : (Ds.t + a0);
+    const double* g_win = Ds.t + a0;
     n_pairs += (unsigned long long)cnt;
 
     // ---- b / c. chunks of at most ucap pairs ------------------------------------------------------
@@ -200,37 +299,11 @@ lag_moment_kernel(const DimDev* __restrict__ dims, const QStreamDev* __restrict_
       for (int x = tid; x < (LQ_NW * J + 1) / 2; x += LQ_NT) ((uint32_t*)s_hist)[x] = 0u;
       __syncthreads();
       // pass 1: bin, coordinate, rank among the equal bins seen so far by this warp
-      for (int32_t q0 = warp * 32; q0 < n_c; q0 += LQ_NT) {
-        const int32_t q = q0 + lane;
-        const bool live = q < n_c;
-        int b = 0;
-        double uu = 0.;
-        if (live) {
-          const int x = s_own[q];
-          const double s = s_t[x] - srcp[s_off[x] + c0 + q];
-          const double xb = fma(s, inv_h, -0.5);
-          const double tr = xb + LQ_MAGIC;
-          b = __double2loint(tr);
-          uu = 2. * (xb - (tr - LQ_MAGIC));
-          if (b > J - 1) { b = J - 1; uu += 2.; }   // s == s_max up to rounding: stay in the last bin
-          b = max(b, 0);
-        }
-        unsigned peers = __ballot_sync(0xffffffffu, live);
-        for (int k = 0; k < nbits; ++k) {
-          const bool bit = (b >> k) & 1;
-          const unsigned v = __ballot_sync(0xffffffffu, bit);
-          peers &= bit ? v : ~v;
-        }
-        const int rank = __popc(peers & lt_mask);
-        int base = 0;
-        if (live) base = my_hist[b];
-        __syncwarp();
-        if (live) {
-          if (rank == 0) my_hist[b] = (uint16_t)(base + __popc(peers));
-          s_key[q] = (uint32_t)b | ((uint32_t)(base + rank) << 10);
-          s_val[q] = uu;
-        }
-        __syncwarp();
+      if (staged) {
+        if (nbits <= 7) lq_pass1<7, true>(n_c, c0, J, inv_h, s_own, s_t, s_off, win, g_win, my_hist, s_key, s_val);
+        else lq_pass1<10, true>(n_c, c0, J, inv_h, s_own, s_t, s_off, win, g_win, my_hist, s_key, s_val);
+      } else {
+        lq_pass1<10, false>(n_c, c0, J, inv_h, s_own, s_t, s_off, win, g_win, my_hist, s_key, s_val);
       }
       __syncthreads();
       // bin totals -> bin starts; per-warp cursors = start + counts of the lower warps
@@ -331,7 +404,7 @@ lag_moment_kernel(const DimDev* __restrict__ dims, const QStreamDev* __restrict_
       }
       __syncthreads();
     }
-    fence_proxy_async();   // generic reads of s_src before the next tile's async write
+    fence_proxy_async();   // generic reads of this window before a later tile's async write
     __syncthreads();
   }
   // ---- one partial moment table per work unit ---------------------------------------------------
