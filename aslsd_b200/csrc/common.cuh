@@ -131,7 +131,8 @@ struct aslsd_ctx {
   // target block and the non-omega parameters stay the same (plans hold no results)
   void* plan_cache = nullptr;
   void (*plan_cache_free)(void*) = nullptr;
-  int64_t epoch = 0;   // bumped by set_events / set_model / set_option
+  int64_t model_epoch = 0;    // bumped by set_model / set_option
+  int64_t events_epoch = 0;   // bumped by set_events
   int64_t last_work[8] = {0};   // see aslsd_last_work_counts
   int64_t last_n_wu_q = 0;
   // timing

@@ -4,7 +4,9 @@
 #include "common.cuh"
 
 #include <algorithm>
+#include <atomic>
 #include <cstring>
+#include <thread>
 
 int aslsd_fail(aslsd_ctx* ctx, int code, const std::string& msg) {
   if (ctx) ctx->err = msg;
@@ -146,29 +148,69 @@ extern "C" int aslsd_set_events(aslsd_ctx* ctx, int d, const int64_t* n_events,
   if ((rc = ensure_device_buffer(ctx, (void**)&ctx->d_tab, &ctx->tab_cap, sizeof(int32_t) * (size_t)tab_off[d])))
     return rc;
   if ((rc = ensure_device_buffer(ctx, &ctx->d_dims, &ctx->dims_cap, sizeof(DimDev) * d))) return rc;
-  ctx->epoch++;
+  ctx->events_epoch++;
+  if (d != ctx->d) ctx->model_epoch++;
   ctx->h_times.assign(d, nullptr);
-  bool sorted = true;
+  // Host pass (copy into the pinned block + order check) split into segments over a few
+  // threads; the thread that completes a type issues its host -> device copy, so the
+  // transfer of one type overlaps the host pass over the others.
+  struct Seg { int dim; int64_t a, b; };
+  std::vector<Seg> segs;
+  const int64_t seg_len = 1 << 19;
+  std::vector<std::atomic<int>> left(d);
   for (int i = 0; i < d; ++i) {
-    double* dst = ctx->h_events + off[i];
-    const double* src = times[i];
     const int64_t n = n_events[i];
-    double prev = n ? src[0] : 0.;
-    bool ok = n == 0 || prev == prev;
-    for (int64_t m = 0; m < n; ++m) {
-      const double v = src[m];
-      ok &= (v >= prev);
-      prev = v;
-      dst[m] = v;
+    int n_seg = 0;
+    for (int64_t a = 0; a < n || (a == 0 && n_seg == 0); a += seg_len) {
+      segs.push_back(Seg{i, a, std::min<int64_t>(n, a + seg_len)});
+      ++n_seg;
     }
-    // pad with a huge finite value (the device side may over-read, never uses it)
-    for (int64_t m = n; m < off[i + 1] - off[i]; ++m) dst[m] = 1.7e308;
-    sorted &= ok;
-    ctx->h_times[i] = dst;
-    // the copy of this type overlaps the host pass over the next one
-    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_times + off[i], dst, sizeof(double) * (size_t)(off[i + 1] - off[i]),
-                                  cudaMemcpyHostToDevice, ctx->stream));
+    left[i].store(n_seg);
+    ctx->h_times[i] = ctx->h_events + off[i];
   }
+  std::atomic<size_t> next(0);
+  std::atomic<int> bad(0), cuda_err(0);
+  auto worker = [&]() {
+    cudaSetDevice(ctx->device);
+    for (;;) {
+      const size_t q = next.fetch_add(1);
+      if (q >= segs.size()) break;
+      const Seg sg = segs[q];
+      double* dst = ctx->h_events + off[sg.dim];
+      const double* src = times[sg.dim];
+      bool ok = true;
+      if (sg.b > sg.a) {
+        double prev = sg.a > 0 ? src[sg.a - 1] : src[0];
+        ok = prev == prev;
+        for (int64_t m = sg.a; m < sg.b; ++m) {
+          const double v = src[m];
+          ok &= (v >= prev);
+          prev = v;
+          dst[m] = v;
+        }
+      }
+      if (!ok) bad.store(1);
+      if (left[sg.dim].fetch_sub(1) == 1) {
+        // last segment of this type: pad with a huge finite value (the device side may
+        // over-read, never uses it) and start the copy
+        const int64_t len = off[sg.dim + 1] - off[sg.dim];
+        for (int64_t m = n_events[sg.dim]; m < len; ++m) dst[m] = 1.7e308;
+        if (cudaMemcpyAsync(ctx->d_times + off[sg.dim], dst, sizeof(double) * (size_t)len,
+                            cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess)
+          cuda_err.store(1);
+      }
+    }
+  };
+  {
+    const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
+    const size_t n_thr = std::min<size_t>({(size_t)hw, (size_t)8, segs.size()});
+    std::vector<std::thread> pool;
+    for (size_t q = 1; q < n_thr; ++q) pool.emplace_back(worker);
+    worker();
+    for (auto& th : pool) th.join();
+  }
+  if (cuda_err.load()) return aslsd_fail(ctx, ASLSD_ERR_CUDA, "set_events: host -> device copy failed");
+  const bool sorted = bad.load() == 0;
   if (!sorted) {
     cudaStreamSynchronize(ctx->stream);
     ctx->d = 0;
@@ -258,7 +300,7 @@ extern "C" int aslsd_set_model(aslsd_ctx* ctx, int d, const int32_t* n_basis, co
   }
   ctx->kernels.swap(ks);
   ctx->has_model = true;
-  ctx->epoch++;
+  ctx->model_epoch++;
   if (ctx->d == 0) ctx->d = d;
   return ASLSD_OK;
 }

@@ -39,6 +39,7 @@ struct BatchPlan {
   std::vector<std::vector<int64_t>> item_row;   // per plan: item -> row
   std::vector<ItemDev> rows;                    // canonical item of every row
   int64_t n_items_total = 0;                    // work items before de-duplication
+  std::vector<int64_t> lo, hi;                  // target block per dimension (build_work)
   // per-item kernels
   std::vector<ItemDev> items;                   // device items, grouped by family
   int fam_first[8], fam_count[8];
@@ -149,15 +150,18 @@ static void build_stream(const aslsd_ctx* ctx, BatchPlan& B, const std::vector<i
   }
 }
 
-static int build_batch(aslsd_ctx* ctx, int n_k, const int* ks, const double* const* xs, int flags,
-                       const int64_t* m_lo, const int64_t* m_hi, bool with_work, BatchPlan& B) {
+// Rows: the work items of every sub-problem and their de-duplication.  Pure function of
+// the model, the flags and the non-omega parameters (target ranges are patched in by
+// build_work), so it survives a change of the event streams.
+static int build_rows(aslsd_ctx* ctx, int n_k, const int* ks, const double* const* xs, int flags,
+                      BatchPlan& B) {
   B.flags = flags;
   B.ks.assign(ks, ks + n_k);
   B.plans.resize(n_k);
   B.item_row.resize(n_k);
   std::map<RowKey, int64_t> index;
   for (int q = 0; q < n_k; ++q) {
-    int rc = build_plan(ctx, ks[q], xs[q], flags, m_lo, m_hi, false, B.plans[q]);
+    int rc = build_plan(ctx, ks[q], xs[q], flags, nullptr, nullptr, false, B.plans[q]);
     if (rc) return rc;
     const SumPlan& P = B.plans[q];
     B.item_row[q].resize(P.items.size());
@@ -173,7 +177,29 @@ static int build_batch(aslsd_ctx* ctx, int n_k, const int* ks, const double* con
       B.item_row[q][x] = found->second;
     }
   }
-  if (!with_work) return ASLSD_OK;
+  return ASLSD_OK;
+}
+
+// Work: target ranges, quadrature streams, per-item work units.  Depends on the events.
+static int build_work(aslsd_ctx* ctx, const int64_t* m_lo, const int64_t* m_hi, BatchPlan& B) {
+  B.items.clear();
+  B.qstreams.clear();
+  B.qrows.clear();
+  B.n_wu = B.n_wu_q = B.n_q_partials = B.n_q_weights = B.n_q_evals = 0;
+  B.q_jmax = 0;
+  B.q_smem = 0;
+  B.device_resident = false;
+  const int d = ctx->d;
+  B.lo.resize(d);
+  B.hi.resize(d);
+  for (int i = 0; i < d; ++i) {
+    B.lo[i] = m_lo ? std::max<int64_t>(0, m_lo[i]) : 0;
+    B.hi[i] = m_hi ? std::min<int64_t>(ctx->n_events[i], m_hi[i]) : ctx->n_events[i];
+  }
+  for (auto& it : B.rows) {
+    it.m_lo = B.lo[it.tgt_dim];
+    it.m_hi = B.hi[it.tgt_dim];
+  }
   const size_t n_rows = B.rows.size();
   std::vector<bool> fast(n_rows, false);
   std::vector<int64_t> boundary_from(n_rows, 0);
@@ -267,45 +293,48 @@ static int build_batch(aslsd_ctx* ctx, int n_k, const int* ks, const double* con
   return ASLSD_OK;
 }
 
-// Plans are pure functions of (model, events, flags, target block, non-omega
-// parameters): the last one is kept and reused, with the omega-dependent variables
-// refreshed.  No result is cached - every call launches all of its kernels.
+// The last batch plan is kept.  Its rows are a pure function of (model, flags, sub-problems,
+// non-omega parameters); its work part also of (events, target block, options).  Each part is
+// rebuilt only when its inputs change, and the omega-dependent variables are refreshed on
+// every call.  No result is cached - every call launches all of its kernels.
 static void free_batch(void* p) { delete (BatchPlan*)p; }
 
 static int get_batch(aslsd_ctx* ctx, int n_k, const int* ks, const double* const* xs, int flags,
                      const int64_t* m_lo, const int64_t* m_hi, bool with_work, BatchPlan** out) {
   std::vector<double> key_rows, key_work;
-  key_rows.push_back((double)ctx->epoch);
+  key_rows.push_back((double)ctx->model_epoch);
   key_rows.push_back((double)n_k);
   key_rows.push_back((double)flags);
   for (int q = 0; q < n_k; ++q) {
     key_rows.push_back((double)ks[q]);
     plan_shape_key(ctx, ks[q], xs[q], key_rows);
   }
+  key_work.push_back((double)ctx->events_epoch);
   key_work.push_back(ctx->use_quadrature ? 1. : 0.);
   for (int i = 0; i < ctx->d; ++i) {
     key_work.push_back(m_lo ? (double)m_lo[i] : -1.);
     key_work.push_back(m_hi ? (double)m_hi[i] : -1.);
   }
   BatchPlan* C = (BatchPlan*)ctx->plan_cache;
-  if (C && C->key_rows == key_rows && (!with_work || (C->has_work && C->key_work == key_work))) {
-    for (int q = 0; q < n_k; ++q) {
-      int rc = plan_vars(ctx, ks[q], xs[q], C->plans[q]);
-      if (rc) return rc;
-    }
-    *out = C;
-    return ASLSD_OK;
+  int rc;
+  if (C && C->key_rows == key_rows) {
+    for (int q = 0; q < n_k; ++q)
+      if ((rc = plan_vars(ctx, ks[q], xs[q], C->plans[q]))) return rc;
+  } else {
+    BatchPlan* B = new BatchPlan();
+    if ((rc = build_rows(ctx, n_k, ks, xs, flags, *B))) { delete B; return rc; }
+    B->key_rows.swap(key_rows);
+    if (ctx->plan_cache) free_batch(ctx->plan_cache);
+    ctx->plan_cache = C = B;
+    ctx->plan_cache_free = free_batch;
   }
-  BatchPlan* B = new BatchPlan();
-  int rc = build_batch(ctx, n_k, ks, xs, flags, m_lo, m_hi, with_work, *B);
-  if (rc) { delete B; return rc; }
-  B->key_rows.swap(key_rows);
-  B->key_work.swap(key_work);
-  B->has_work = with_work;
-  if (ctx->plan_cache) free_batch(ctx->plan_cache);
-  ctx->plan_cache = B;
-  ctx->plan_cache_free = free_batch;
-  *out = B;
+  if (with_work && !(C->has_work && C->key_work == key_work)) {
+    C->has_work = false;
+    if ((rc = build_work(ctx, m_lo, m_hi, *C))) return rc;
+    C->key_work.swap(key_work);
+    C->has_work = true;
+  }
+  *out = C;
   return ASLSD_OK;
 }
 
@@ -445,7 +474,9 @@ static int run_batch(aslsd_ctx* ctx, BatchPlan& B, double* raw_device) {
   return ASLSD_OK;
 }
 
-static int count_pair_terms(aslsd_ctx* ctx, const SumPlan& P, int64_t* n_pair_terms) {
+// lo / hi: target block per dimension
+static int count_pair_terms(aslsd_ctx* ctx, const SumPlan& P, const std::vector<int64_t>& lo,
+                            const std::vector<int64_t>& hi, int64_t* n_pair_terms) {
   const size_t nt = P.terms.size();
   unsigned long long* d_cnt = nullptr;
   CUDA_TRY(ctx, cudaMalloc(&d_cnt, nt * sizeof(unsigned long long)));
@@ -455,14 +486,7 @@ static int count_pair_terms(aslsd_ctx* ctx, const SumPlan& P, int64_t* n_pair_te
     if (T.kind < 2 || P.term_s_hi[t] < 0.) continue;
     int tgt = T.kind == 2 ? P.k : T.i;
     int src = T.kind == 2 ? T.i : T.j;
-    // target block of the term: recover from any of its items
-    int64_t m_lo = 0, m_hi = 0;
-    int n_slots = (T.kind == 2) ? (int)ctx->kernels[P.k * ctx->d + T.i].bases.size()
-                                : (int)(ctx->kernels[0].bases.size() * ctx->kernels[0].bases.size());
-    for (int s = 0; s < n_slots; ++s) {
-      int idx = P.slot_item[P.term_val_off[t] + s];
-      if (idx >= 0) { m_lo = P.items[idx].m_lo; m_hi = P.items[idx].m_hi; break; }
-    }
+    const int64_t m_lo = lo[tgt], m_hi = hi[tgt];
     if (m_hi <= m_lo) continue;
     int64_t blocks = std::min<int64_t>((m_hi - m_lo + 255) / 256, 148 * 8);
     count_pairs_kernel<<<(unsigned)blocks, 256, 0, ctx->stream>>>((const DimDev*)ctx->d_dims, tgt, src,
@@ -533,7 +557,7 @@ extern "C" int aslsd_exact_out_len(const aslsd_ctx* ctx, int k, int64_t* out_len
 
 extern "C" int aslsd_set_option(aslsd_ctx* ctx, int option, int value) {
   if (!ctx) return ASLSD_ERR_ARG;
-  if (option == ASLSD_OPT_LAG_QUADRATURE) { ctx->use_quadrature = value != 0; ctx->epoch++; return ASLSD_OK; }
+  if (option == ASLSD_OPT_LAG_QUADRATURE) { ctx->use_quadrature = value != 0; ctx->model_epoch++; return ASLSD_OK; }
   return aslsd_fail(ctx, ASLSD_ERR_ARG, "set_option: unknown option");
 }
 
@@ -557,7 +581,7 @@ extern "C" int aslsd_exact_sums_batch(aslsd_ctx* ctx, int n_k, const int* ks, co
     assemble(ctx, B.plans[q], B.item_row[q], xs[q], (const double*)ctx->h_pinned, outs[q]);
   if (n_pair_terms)
     for (int q = 0; q < n_k && !rc; ++q)
-      if (n_pair_terms[q]) rc = count_pair_terms(ctx, B.plans[q], n_pair_terms[q]);
+      if (n_pair_terms[q]) rc = count_pair_terms(ctx, B.plans[q], B.lo, B.hi, n_pair_terms[q]);
   return rc;
 }
 
@@ -601,9 +625,9 @@ extern "C" int aslsd_exact_raw_device(aslsd_ctx* ctx, int k, const double* x_k, 
   const double* xs[1] = {x_k};
   int rc = aslsd_exact_raw_device_batch(ctx, 1, &k, xs, flags, m_lo, m_hi, raw_device);
   if (rc || !n_pair_terms) return rc;
-  SumPlan P;
-  if ((rc = build_plan(ctx, k, x_k, flags, m_lo, m_hi, false, P))) return rc;
-  return count_pair_terms(ctx, P, n_pair_terms);
+  BatchPlan* Bp = nullptr;
+  if ((rc = get_batch(ctx, 1, &k, xs, flags, m_lo, m_hi, true, &Bp))) return rc;
+  return count_pair_terms(ctx, Bp->plans[0], Bp->lo, Bp->hi, n_pair_terms);
 }
 
 extern "C" int aslsd_exact_assemble_batch(aslsd_ctx* ctx, int n_k, const int* ks, const double* const* xs,
