@@ -115,7 +115,8 @@ static void build_stream(const aslsd_ctx* ctx, BatchPlan& B, const std::vector<i
   const int64_t m_b = interior_end(ctx, first.tgt_dim, first.m_lo, first.m_hi, t_int);
   if (m_b - first.m_lo < LQ_TM / 2) return;   // the per-item kernels take it all
   const double h = LQ_SCALE_FRACTION * scale;
-  const double nb = std::floor(s_max / h) + 1.;
+  // bins [j h, (j + 1) h) up to s_max, plus one: a lag can exceed s_max by a rounding error
+  const double nb = std::floor(s_max / h) + 2.;
   if (!(nb <= (double)LQ_JMAX)) return;
   const int ucap = lq_pick_ucap((int)nb);
   if (ucap == 0) return;

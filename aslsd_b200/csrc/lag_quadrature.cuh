@@ -75,18 +75,15 @@ struct QStreamDev {
 __constant__ double LQ_X[LQ_ND];
 __constant__ double LQ_CT[LQ_ND * LQ_ND];   // [i][d]
 
-// dynamic shared memory: [pair-order coordinates | sorted coordinates | 2 source windows | target times |
-//                         moment table | keys | source-minus-pair offsets | bin starts | owners | histograms]
+// dynamic shared memory: [pair-order lags / coordinates | sorted coordinates | 2 source windows |
+//                         moment table | keys | bin starts | histograms]
 __host__ __device__ inline size_t lq_smem_bytes(int J, int ucap) {
   size_t b = 0;
   b += (size_t)ucap * sizeof(double) * 2;
   b += (size_t)(LQ_SMAX + 2) * sizeof(double) * 2;
-  b += (size_t)LQ_TM * sizeof(double);
   b += (size_t)J * LQ_ND * sizeof(double);
   b += (size_t)ucap * sizeof(uint32_t);
-  b += (size_t)LQ_TM * sizeof(int32_t);
   b += (size_t)(J + 2) * sizeof(int32_t);
-  b += (size_t)ucap * sizeof(uint16_t);
   b += (size_t)LQ_NW * J * sizeof(uint16_t);
   return b + 64;
 }
@@ -120,51 +117,77 @@ __device__ __forceinline__ int smem_lower_bound(const double* win, int n, double
 }
 
 // lanes of the warp whose b equals this lane's, from ballots over NB bits
+// (per bit: test, vote, select, and-not-xor)
+template <int K>
+__device__ __forceinline__ void match_bit(int b, unsigned& peers) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      ".reg .b32 t, v, m;\n"
+      "and.b32 t, %1, %2;\n"
+      "setp.ne.u32 p, t, 0;\n"
+      "vote.sync.ballot.b32 v, p, 0xffffffff;\n"
+      "selp.b32 m, 0xffffffff, 0, p;\n"
+      "lop3.b32 %0, %0, v, m, 0x90;\n"   // peers & ~(v ^ m)
+      "}\n"
+      : "+r"(peers)
+      : "r"(b), "n"(1 << K));
+}
 template <int NB>
 __device__ __forceinline__ unsigned match_bins(int b) {
   unsigned peers = 0xffffffffu;
-#pragma unroll
-  for (int k = 0; k < NB; ++k) {
-    const bool bit = (b & (1 << k)) != 0;
-    const unsigned v = __ballot_sync(0xffffffffu, bit);
-    peers &= bit ? v : ~v;
-  }
+  match_bit<0>(b, peers); match_bit<1>(b, peers); match_bit<2>(b, peers); match_bit<3>(b, peers);
+  match_bit<4>(b, peers); match_bit<5>(b, peers); match_bit<6>(b, peers);
+  if (NB > 7) { match_bit<7>(b, peers); match_bit<8>(b, peers); match_bit<9>(b, peers); }
   return peers;
 }
 
-// Pass 1 of the counting sort over the n_c pairs of a chunk (see the file header).
-template <int NB, bool STAGED>
-__device__ __forceinline__ void lq_pass1(int n_c, int c0, int J, double inv_h, const uint16_t* s_own,
-                                         const double* s_t, const int32_t* s_off, const double* s_win,
-                                         const double* __restrict__ g_win, uint16_t* my_hist,
-                                         uint32_t* s_key, double* s_val) {
+// bin index and position inside the bin (v in [-1/2, 1/2]; the Chebyshev variable is 2 v)
+__device__ __forceinline__ void lq_bin(double s, double inv_h, int& b, double& v) {
+  const double xb = fma(s, inv_h, -0.5);
+  const double tr = xb + LQ_MAGIC;
+  b = __double2loint(tr);
+  v = xb - (tr - LQ_MAGIC);
+}
+
+// Pass 1 of the counting sort over the n_c pairs of a chunk (see the file header): s_val holds
+// the lags in pair order on entry, the bin positions on exit.  Two warp steps per iteration:
+// the ballots of the two are independent, the histogram updates are ordered.
+template <int NB>
+__device__ __forceinline__ void lq_pass1(int n_c, double inv_h, uint16_t* my_hist, uint32_t* s_key,
+                                         double* s_val) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const unsigned lt_mask = (1u << lane) - 1u;
   const int n_steps = (n_c + 31) >> 5;
-  for (int st = warp; st < n_steps; st += LQ_NW) {
-    const int q = st * 32 + lane;
-    const int left = n_c - st * 32;   // live lanes of this step (warp-uniform)
-    const unsigned live_mask = left >= 32 ? 0xffffffffu : ((1u << left) - 1u);
-    const bool live = q < n_c;
-    const int qq = live ? q : n_c - 1;   // idle lanes redo the last pair and store nothing
-    const int x = s_own[qq];
-    const int n = s_off[x] + c0 + qq;
-    const double s = s_t[x] - (STAGED ? s_win[n] : g_win[n]);
-    const double xb = fma(s, inv_h, -0.5);
-    const double tr = xb + LQ_MAGIC;
-    int b = __double2loint(tr);
-    double uu = xb - (tr - LQ_MAGIC);
-    uu += uu;
-    if (b > J - 1) { b = J - 1; uu += 2.; }   // s == s_max up to rounding: stay in the last bin
-    b = max(b, 0);
-    const unsigned peers = match_bins<NB>(b) & live_mask;
-    const int rank = __popc(peers & lt_mask);
-    const int base = my_hist[b];
+  for (int st = warp; st < n_steps; st += 2 * LQ_NW) {
+    const int qa = st * 32 + lane, qb = qa + LQ_NW * 32;
+    const bool live_a = qa < n_c, live_b = qb < n_c;
+    // idle lanes (last steps of a chunk) redo pair 0 and are masked out of every peer set
+    const int left_a = n_c - st * 32, left_b = left_a - LQ_NW * 32;
+    const unsigned mask_a = left_a >= 32 ? 0xffffffffu : ((1u << left_a) - 1u);
+    const unsigned mask_b = left_b >= 32 ? 0xffffffffu : (left_b <= 0 ? 0u : ((1u << left_b) - 1u));
+    const double sa = s_val[live_a ? qa : 0], sb = s_val[live_b ? qb : 0];
+    int ba, bb;
+    double va, vb;
+    lq_bin(sa, inv_h, ba, va);
+    lq_bin(sb, inv_h, bb, vb);
+    const unsigned pa = match_bins<NB>(ba) & mask_a;
+    const unsigned pb = match_bins<NB>(bb) & mask_b;
+    const int ra = __popc(pa & lt_mask), rb = __popc(pb & lt_mask);
+    const int base_a = my_hist[ba];
     __syncwarp();
-    if (live) {
-      if (rank == 0) my_hist[b] = (uint16_t)(base + __popc(peers));
-      s_key[q] = (uint32_t)b | ((uint32_t)(base + rank) << 10);
-      s_val[q] = uu;
+    if (live_a) {
+      if (ra == 0) my_hist[ba] = (uint16_t)(base_a + __popc(pa));
+      s_key[qa] = (uint32_t)ba | ((uint32_t)(base_a + ra) << 10);
+      s_val[qa] = va;
+    }
+    __syncwarp();
+    const int base_b = my_hist[bb];
+    __syncwarp();
+    if (live_b) {
+      if (rb == 0) my_hist[bb] = (uint16_t)(base_b + __popc(pb));
+      s_key[qb] = (uint32_t)bb | ((uint32_t)(base_b + rb) << 10);
+      s_val[qb] = vb;
     }
     __syncwarp();
   }
@@ -177,6 +200,7 @@ lag_moment_kernel(const DimDev* __restrict__ dims, const QStreamDev* __restrict_
   __shared__ __align__(8) uint64_t s_bar[2];
   __shared__ int64_t s_a0[2];        // first source index of each window buffer
   __shared__ int64_t s_next_lo;      // window start of the tile's last target
+  __shared__ double s_tlast;         // time of the tile's last target
   __shared__ int32_t s_warp[LQ_NW];
   __shared__ int32_t s_scan[LQ_NW];
 
@@ -195,13 +219,10 @@ lag_moment_kernel(const DimDev* __restrict__ dims, const QStreamDev* __restrict_
   double* s_val = (double*)smem_raw;
   double* s_u = s_val + ucap;
   double* s_src = s_u + ucap;                       // two buffers of LQ_SMAX + 2
-  double* s_t = s_src + 2 * (LQ_SMAX + 2);
-  double* s_M = s_t + LQ_TM;
+  double* s_M = s_src + 2 * (LQ_SMAX + 2);
   uint32_t* s_key = (uint32_t*)(s_M + (size_t)J * LQ_ND);
-  int32_t* s_off = (int32_t*)(s_key + ucap);
-  int32_t* s_bin = s_off + LQ_TM;
-  uint16_t* s_own = (uint16_t*)(s_bin + (J + 2));
-  uint16_t* s_hist = s_own + ucap;
+  int32_t* s_bin = (int32_t*)(s_key + ucap);
+  uint16_t* s_hist = (uint16_t*)(s_bin + (J + 2));
   uint16_t* my_hist = s_hist + warp * J;
 
   for (int x = tid; x < J * LQ_ND; x += LQ_NT) s_M[x] = 0.;
@@ -231,7 +252,7 @@ lag_moment_kernel(const DimDev* __restrict__ dims, const QStreamDev* __restrict_
     double* win = s_src + buf * (LQ_SMAX + 2);
     // ---- a. per-target source ranges ---------------------------------------------------------
     const double t = t_mine;
-    if (tid < nt) s_t[tid] = t;
+    if (tid == nt - 1) s_tlast = t;
     if (m0 + LQ_TM + tid < m_end) t_mine = Dt.t[m0 + LQ_TM + tid];   // next tile's target, in flight
     mbar_wait(&s_bar[buf], (parity >> buf) & 1u);
     parity ^= 1u << buf;
@@ -240,7 +261,7 @@ lag_moment_kernel(const DimDev* __restrict__ dims, const QStreamDev* __restrict_
     const int n_win = (int)min((int64_t)LQ_SMAX, n_src_padded - a0);
     // the window serves the tile if it reaches the end of the stream or the last target (same type:
     // by index, ties in time included; other types: by time, the searches are lower bounds)
-    const double t_last = s_t[nt - 1];
+    const double t_last = s_tlast;
     const bool staged = (a0 + n_win >= Ds.n) ||
                         (same ? (a0 + n_win >= m0 + nt - 1) : (win[n_win - 1] >= t_last));
     const int n_valid = (int)min((int64_t)n_win, Ds.n - a0);   // entries that are events, not padding
@@ -283,28 +304,28 @@ lag_moment_kernel(const DimDev* __restrict__ dims, const QStreamDev* __restrict_
       tma_load_1d(s_src + (buf ^ 1) * (LQ_SMAX + 2), Ds.t + a1, (uint32_t)(n_stage * sizeof(double)),
                   &s_bar[buf ^ 1]);
     }
-    // source index (relative to a0) minus tile-wide pair index, per target
-    if (tid < nt) s_off[tid] = (int32_t)(lo_abs - a0) - pre;
-    const double* g_win = Ds.t + a0;
+    const double* my_src = (staged ? (const double*)win : (Ds.t + a0)) + (lo_abs - a0);
     n_pairs += (unsigned long long)cnt;
 
     // ---- b / c. chunks of at most ucap pairs ------------------------------------------------------
     for (int32_t c0 = 0; c0 < total; c0 += ucap) {
       const int32_t n_c = min(ucap, total - c0);
-      // owner table of the chunk; histograms to zero
+      // lags of the chunk in pair order (target-major), written by the targets' threads;
+      // histograms to zero
       {
-        const int32_t pa = max(pre, c0), pb = min(pre + cnt, c0 + n_c);
-        for (int32_t p = pa; p < pb; ++p) s_own[p - c0] = (uint16_t)tid;
+        const int32_t ra = min(max(c0 - pre, 0), cnt), rb = min(max(c0 + n_c - pre, 0), cnt);
+        double* dst = s_val + (pre - c0);
+        if (staged) {
+          for (int32_t r = ra; r < rb; ++r) dst[r] = t - my_src[r];
+        } else {
+          for (int32_t r = ra; r < rb; ++r) dst[r] = t - __ldg(my_src + r);
+        }
       }
       for (int x = tid; x < (LQ_NW * J + 1) / 2; x += LQ_NT) ((uint32_t*)s_hist)[x] = 0u;
       __syncthreads();
-      // pass 1: bin, coordinate, rank among the equal bins seen so far by this warp
-      if (staged) {
-        if (nbits <= 7) lq_pass1<7, true>(n_c, c0, J, inv_h, s_own, s_t, s_off, win, g_win, my_hist, s_key, s_val);
-        else lq_pass1<10, true>(n_c, c0, J, inv_h, s_own, s_t, s_off, win, g_win, my_hist, s_key, s_val);
-      } else {
-        lq_pass1<10, false>(n_c, c0, J, inv_h, s_own, s_t, s_off, win, g_win, my_hist, s_key, s_val);
-      }
+      // pass 1: bin, position in the bin, rank among the equal bins seen so far by this warp
+      if (nbits <= 7) lq_pass1<7>(n_c, inv_h, my_hist, s_key, s_val);
+      else lq_pass1<10>(n_c, inv_h, my_hist, s_key, s_val);
       __syncthreads();
       // bin totals -> bin starts; per-warp cursors = start + counts of the lower warps
       // (thread tid owns the jpt consecutive bins from tid * jpt)
@@ -360,7 +381,8 @@ lag_moment_kernel(const DimDev* __restrict__ dims, const QStreamDev* __restrict_
 #pragma unroll
         for (int d = 0; d < LQ_ND; ++d) acc[d] = 0.;
         for (int32_t e = e0 + q8; e < e1; e += 8) {
-          const double uu = s_u[e];
+          const double vv = s_u[e];
+          const double uu = vv + vv;
           const double two_u = uu + uu;
           double tp = 1., tc = uu;
           acc[1] += tc;
