@@ -114,10 +114,14 @@ static void build_stream(const aslsd_ctx* ctx, BatchPlan& B, const std::vector<i
   if (!(scale > 0.) || !(s_max > 0.) || !std::isfinite(s_max) || !std::isfinite(t_int)) return;
   const int64_t m_b = interior_end(ctx, first.tgt_dim, first.m_lo, first.m_hi, t_int);
   if (m_b - first.m_lo < LQ_TM / 2) return;   // the per-item kernels take it all
-  const double h = LQ_SCALE_FRACTION * scale;
-  // bins [j h, (j + 1) h) up to s_max, plus one: a lag can exceed s_max by a rounding error
-  const double nb = std::floor(s_max / h) + 2.;
+  // bins [j h, (j + 1) h) up to s_max plus a spare one (a lag can exceed s_max by a rounding
+  // error); the count is rounded up to a multiple of 32 - the moment kernel hands bins to
+  // groups of lanes in rounds of 64 - and the bins shrink accordingly
+  const double h_max = LQ_SCALE_FRACTION * scale;
+  double nb = std::floor(s_max / h_max) + 2.;
   if (!(nb <= (double)LQ_JMAX)) return;
+  nb = std::min<double>(LQ_JMAX, 32. * std::ceil(nb / 32.));
+  const double h = s_max / (nb - 1.5);
   const int ucap = lq_pick_ucap((int)nb);
   if (ucap == 0) return;
   QStreamDev S;

@@ -17,8 +17,8 @@
 //   3. lag_quad_kernel     every row (one basis / basis pair of one term) evaluates the reference's
 //                          closed form at the J * LQ_ND nodes and takes the dot product with W.
 //
-// Degree-11 interpolation on bins of 0.3 scale units reproduces these functions to ~1e-15 of their
-// maximum (scripts/quadrature_error.py), far inside the 1e-10 parity bar, and steps 1-2 do not depend on
+// Degree-11 interpolation on bins of at most 0.5 scale units reproduces these functions to ~1e-13 of
+// their maximum (scripts/quadrature_error.py), far inside the 1e-10 parity bar, and steps 1-2 do not depend on
 // the parameters at all.  The O(pairs) work drops from one exp + one erfc per (pair, basis pair) to ~2
 // fp64 instructions per (pair, Chebyshev degree); the closed forms are evaluated O(rows * J * LQ_ND) times.
 //
@@ -56,7 +56,7 @@
 #define LQ_ND 12                  // Chebyshev terms = nodes per bin
 #define LQ_JMAX 1024              // bins per stream
 #define LQ_SMEM_BUDGET ((LQ_CTAS == 1 ? 220 : 110) * 1024)
-#define LQ_SCALE_FRACTION 0.3     // bin width in units of the smallest scale of the stream's rows
+#define LQ_SCALE_FRACTION 0.5     // largest bin width in units of the smallest scale of the stream's rows
 #define LQ_MAGIC 6755399441055744.0   // 1.5 * 2^52: x + MAGIC holds rint(x) in its low word
 
 struct QStreamDev {
@@ -104,16 +104,16 @@ __device__ __forceinline__ int find_stream(const QStreamDev* __restrict__ stream
   return lo;
 }
 
-// first index in [0, n) of the sorted shared array with win[idx] >= x (n if none)
-__device__ __forceinline__ int smem_lower_bound(const double* win, int n, double x) {
-  int lo = 0, len = n;
-  while (len > 0) {
-    const int half = len >> 1;
-    const bool go = win[lo + half] < x;
-    lo = go ? lo + half + 1 : lo;
-    len = go ? len - half - 1 : half;
+// first index in [0, n) of the sorted shared array with win[idx] >= x (n if none);
+// p2 = largest power of two <= n (warp-uniform trip count, no data-dependent branch)
+__device__ __forceinline__ int smem_lower_bound(const double* win, int n, int p2, double x) {
+  int pos = 0;
+  for (int step = p2; step > 0; step >>= 1) {
+    const int np = pos + step;
+    const double v = win[min(np, n) - 1];
+    pos = (np <= n && v < x) ? np : pos;
   }
-  return lo;
+  return pos;
 }
 
 // lanes of the warp whose b equals this lane's, from ballots over NB bits
@@ -137,7 +137,9 @@ template <int NB>
 __device__ __forceinline__ unsigned match_bins(int b) {
   unsigned peers = 0xffffffffu;
   match_bit<0>(b, peers); match_bit<1>(b, peers); match_bit<2>(b, peers); match_bit<3>(b, peers);
-  match_bit<4>(b, peers); match_bit<5>(b, peers); match_bit<6>(b, peers);
+  match_bit<4>(b, peers);
+  if (NB > 5) match_bit<5>(b, peers);
+  if (NB > 6) match_bit<6>(b, peers);
   if (NB > 7) { match_bit<7>(b, peers); match_bit<8>(b, peers); match_bit<9>(b, peers); }
   return peers;
 }
@@ -267,11 +269,12 @@ lag_moment_kernel(const DimDev* __restrict__ dims, const QStreamDev* __restrict_
     const int n_valid = (int)min((int64_t)n_win, Ds.n - a0);   // entries that are events, not padding
     int64_t lo_abs = 0;
     int32_t cnt = 0;
+    const int p2 = n_valid > 0 ? (1 << (31 - __clz(n_valid))) : 0;
     if (tid < nt) {
       int64_t hi;
       if (staged) {
-        hi = same ? (m0 + tid) : a0 + smem_lower_bound(win, n_valid, t);
-        lo_abs = min(a0 + (int64_t)smem_lower_bound(win, n_valid, t - S.s_max), hi);
+        hi = same ? (m0 + tid) : a0 + smem_lower_bound(win, n_valid, p2, t);
+        lo_abs = min(a0 + (int64_t)smem_lower_bound(win, n_valid, p2, t - S.s_max), hi);
       } else {
         hi = same ? (m0 + tid) : dim_lower_bound(Ds, t);
         lo_abs = min(dim_lower_bound(Ds, t - S.s_max), hi);
@@ -304,7 +307,8 @@ lag_moment_kernel(const DimDev* __restrict__ dims, const QStreamDev* __restrict_
       tma_load_1d(s_src + (buf ^ 1) * (LQ_SMAX + 2), Ds.t + a1, (uint32_t)(n_stage * sizeof(double)),
                   &s_bar[buf ^ 1]);
     }
-    const double* my_src = (staged ? (const double*)win : (Ds.t + a0)) + (lo_abs - a0);
+    const double* my_win = win + (int)(lo_abs - a0);    // shared (staged tiles)
+    const double* my_glb = Ds.t + lo_abs;               // global (fallback)
     n_pairs += (unsigned long long)cnt;
 
     // ---- b / c. chunks of at most ucap pairs ------------------------------------------------------
@@ -316,15 +320,23 @@ lag_moment_kernel(const DimDev* __restrict__ dims, const QStreamDev* __restrict_
         const int32_t ra = min(max(c0 - pre, 0), cnt), rb = min(max(c0 + n_c - pre, 0), cnt);
         double* dst = s_val + (pre - c0);
         if (staged) {
-          for (int32_t r = ra; r < rb; ++r) dst[r] = t - my_src[r];
+          int32_t r = ra;
+          for (; r + 1 < rb; r += 2) {
+            const double s0 = my_win[r], s1 = my_win[r + 1];
+            dst[r] = t - s0;
+            dst[r + 1] = t - s1;
+          }
+          if (r < rb) dst[r] = t - my_win[r];
         } else {
-          for (int32_t r = ra; r < rb; ++r) dst[r] = t - __ldg(my_src + r);
+          for (int32_t r = ra; r < rb; ++r) dst[r] = t - __ldg(my_glb + r);
         }
       }
       for (int x = tid; x < (LQ_NW * J + 1) / 2; x += LQ_NT) ((uint32_t*)s_hist)[x] = 0u;
       __syncthreads();
       // pass 1: bin, position in the bin, rank among the equal bins seen so far by this warp
-      if (nbits <= 7) lq_pass1<7>(n_c, inv_h, my_hist, s_key, s_val);
+      if (nbits <= 5) lq_pass1<5>(n_c, inv_h, my_hist, s_key, s_val);
+      else if (nbits == 6) lq_pass1<6>(n_c, inv_h, my_hist, s_key, s_val);
+      else if (nbits == 7) lq_pass1<7>(n_c, inv_h, my_hist, s_key, s_val);
       else lq_pass1<10>(n_c, inv_h, my_hist, s_key, s_val);
       __syncthreads();
       // bin totals -> bin starts; per-warp cursors = start + counts of the lower warps
@@ -380,7 +392,22 @@ lag_moment_kernel(const DimDev* __restrict__ dims, const QStreamDev* __restrict_
         double acc[LQ_ND];
 #pragma unroll
         for (int d = 0; d < LQ_ND; ++d) acc[d] = 0.;
-        for (int32_t e = e0 + q8; e < e1; e += 8) {
+        // two independent recurrences per iteration (the chain is latency-bound)
+        int32_t e = e0 + q8;
+        for (; e + 8 < e1; e += 16) {
+          const double ua = s_u[e] + s_u[e], ub = s_u[e + 8] + s_u[e + 8];
+          const double two_a = ua + ua, two_b = ub + ub;
+          double pa = 1., ca = ua, pb = 1., cb = ub;
+          acc[1] += ca + cb;
+#pragma unroll
+          for (int d = 2; d < LQ_ND; ++d) {
+            const double na = fma(two_a, ca, -pa), nb = fma(two_b, cb, -pb);
+            pa = ca; ca = na;
+            pb = cb; cb = nb;
+            acc[d] += na + nb;
+          }
+        }
+        if (e < e1) {
           const double vv = s_u[e];
           const double uu = vv + vv;
           const double two_u = uu + uu;
