@@ -16,6 +16,7 @@ ASLSD_F = 1
 ASLSD_DIFF = 2
 ASLSD_GRAD_ALLOC = 4
 OPT_LAG_QUADRATURE = 1
+OPT_WEIGHT_CACHE = 2
 
 BASIS_EXPONENTIAL = 0
 BASIS_GAUSSIAN = 1
@@ -44,6 +45,7 @@ SYMBOLS = {
     'aslsd_last_error': (ctypes.c_char_p, [ctypes.c_void_p]),
     'aslsd_set_stream': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p]),
     'aslsd_last_timing': (ctypes.c_int, [ctypes.c_void_p, c_f64_p, c_i64_p]),
+    'aslsd_last_moment_timing': (ctypes.c_int, [ctypes.c_void_p, c_f64_p]),
     'aslsd_measure_fp64_peak': (ctypes.c_int, [ctypes.c_void_p, c_f64_p]),
     'aslsd_set_events': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, c_i64_p,
                                         ctypes.POINTER(c_f64_p), ctypes.c_double]),

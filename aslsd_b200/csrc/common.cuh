@@ -125,6 +125,8 @@ struct aslsd_ctx {
   double* d_q_partials = nullptr; size_t q_partials_cap = 0;
   double* d_q_weights = nullptr; size_t q_weights_cap = 0;
   bool use_quadrature = true;
+  bool cache_weights = true;        // reuse the node weights while plan and events stay the same
+  bool last_weights_reused = false;
   bool lq_tables_set = false;
   size_t q_smem_set = 0;
   // last batch plan (exact.cu): reused while the model, the events, the flags, the
@@ -136,9 +138,10 @@ struct aslsd_ctx {
   int64_t last_work[8] = {0};   // see aslsd_last_work_counts
   int64_t last_n_wu_q = 0;
   // timing
-  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-  double last_ms = 0.;
-  bool timing_pending = false;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;     // around all kernels of a sum call
+  cudaEvent_t ev_q0 = nullptr, ev_q1 = nullptr; // around the lag-moment kernel
+  double last_ms = 0., last_moment_ms = 0.;
+  bool timing_pending = false, moment_timing_pending = false;
   int64_t last_launches = 0;
   // evaluation counters of the last exact-sum call (per item, on the device)
   int64_t last_n_wu = 0;

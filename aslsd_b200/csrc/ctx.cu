@@ -45,7 +45,8 @@ extern "C" int aslsd_create(aslsd_ctx** out, int device) {
   ctx->device = device;
   if (cudaSetDevice(device) != cudaSuccess ||
       cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) != cudaSuccess ||
-      cudaEventCreate(&ctx->ev0) != cudaSuccess || cudaEventCreate(&ctx->ev1) != cudaSuccess) {
+      cudaEventCreate(&ctx->ev0) != cudaSuccess || cudaEventCreate(&ctx->ev1) != cudaSuccess ||
+      cudaEventCreate(&ctx->ev_q0) != cudaSuccess || cudaEventCreate(&ctx->ev_q1) != cudaSuccess) {
     delete ctx;
     return ASLSD_ERR_CUDA;
   }
@@ -74,6 +75,8 @@ extern "C" int aslsd_destroy(aslsd_ctx* ctx) {
   if (ctx->h_events) cudaFreeHost(ctx->h_events);
   cudaEventDestroy(ctx->ev0);
   cudaEventDestroy(ctx->ev1);
+  cudaEventDestroy(ctx->ev_q0);
+  cudaEventDestroy(ctx->ev_q1);
   cudaStreamDestroy(ctx->own_stream);
   delete ctx;
   return ASLSD_OK;
@@ -302,6 +305,20 @@ extern "C" int aslsd_set_model(aslsd_ctx* ctx, int d, const int32_t* n_basis, co
   ctx->has_model = true;
   ctx->model_epoch++;
   if (ctx->d == 0) ctx->d = d;
+  return ASLSD_OK;
+}
+
+extern "C" int aslsd_last_moment_timing(const aslsd_ctx* ctx_, double* kernel_ms) {
+  aslsd_ctx* ctx = const_cast<aslsd_ctx*>(ctx_);
+  if (!ctx || !kernel_ms) return ASLSD_ERR_ARG;
+  if (ctx->moment_timing_pending) {
+    float ms = 0.f;
+    if (cudaEventSynchronize(ctx->ev_q1) == cudaSuccess &&
+        cudaEventElapsedTime(&ms, ctx->ev_q0, ctx->ev_q1) == cudaSuccess)
+      ctx->last_moment_ms = ms;
+    ctx->moment_timing_pending = false;
+  }
+  *kernel_ms = ctx->last_moment_ms;
   return ASLSD_OK;
 }
 

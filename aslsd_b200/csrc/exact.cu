@@ -33,6 +33,7 @@ struct BatchPlan {
   std::vector<double> key_rows, key_work;   // cache keys (see get_batch)
   bool has_work = false;
   bool device_resident = false;   // item / stream tables of this plan are on the device
+  bool weights_valid = false;     // the context's node weights were computed for this work part
   int flags = 0;
   std::vector<int> ks;
   std::vector<SumPlan> plans;
@@ -194,6 +195,7 @@ static int build_work(aslsd_ctx* ctx, const int64_t* m_lo, const int64_t* m_hi, 
   B.q_jmax = 0;
   B.q_smem = 0;
   B.device_resident = false;
+  B.weights_valid = false;
   const int d = ctx->d;
   B.lo.resize(d);
   B.hi.resize(d);
@@ -438,19 +440,31 @@ static int run_batch(aslsd_ctx* ctx, BatchPlan& B, double* raw_device) {
   CUDA_TRY(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
   CUDA_TRY(ctx, cudaMemsetAsync(raw_device, 0, std::max<size_t>(1, n_rows) * ASLSD_MAX_COMP * sizeof(double),
                                 ctx->stream));
-  if (quad) {
+  // The node weights depend on the event streams and on the bin grids only (not on omega, not
+  // on the evaluation point as long as the windows stay): with the weight cache on, a repeated
+  // evaluation on the same plan - the iterations of a fit with fixed (beta, delta) - skips the
+  // pass over the event pairs.
+  const bool reuse_weights = quad && ctx->cache_weights && B.weights_valid;
+  ctx->last_weights_reused = reuse_weights;
+  ctx->moment_timing_pending = false;
+  ctx->last_moment_ms = 0.;
+  if (quad && !reuse_weights) {
     if (B.q_smem > ctx->q_smem_set) {
       CUDA_TRY(ctx, cudaFuncSetAttribute(lag_moment_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)B.q_smem));
       ctx->q_smem_set = B.q_smem;
     }
+    CUDA_TRY(ctx, cudaEventRecord(ctx->ev_q0, ctx->stream));
     lag_moment_kernel<<<(unsigned)B.n_wu_q, LQ_NT, B.q_smem, ctx->stream>>>(
         (const DimDev*)ctx->d_dims, d_streams, (int)B.qstreams.size(), ctx->d_q_partials,
         ctx->d_counts + B.n_wu + n_items);
+    CUDA_TRY(ctx, cudaEventRecord(ctx->ev_q1, ctx->stream));
+    ctx->moment_timing_pending = true;
     ctx->last_launches++;
     const dim3 wgrid((unsigned)((B.q_jmax + LQ_WB - 1) / LQ_WB), (unsigned)B.qstreams.size());
     lag_weights_kernel<<<wgrid, LQ_WB * LQ_ND, 0, ctx->stream>>>(d_streams, ctx->d_q_partials, ctx->d_q_weights);
     ctx->last_launches++;
+    B.weights_valid = true;
   }
   launch_pair<ITEM_UPS_GAUSS>(ctx, B, d_items);
   launch_pair<ITEM_UPS_EXP>(ctx, B, d_items);
@@ -563,6 +577,7 @@ extern "C" int aslsd_exact_out_len(const aslsd_ctx* ctx, int k, int64_t* out_len
 extern "C" int aslsd_set_option(aslsd_ctx* ctx, int option, int value) {
   if (!ctx) return ASLSD_ERR_ARG;
   if (option == ASLSD_OPT_LAG_QUADRATURE) { ctx->use_quadrature = value != 0; ctx->model_epoch++; return ASLSD_OK; }
+  if (option == ASLSD_OPT_WEIGHT_CACHE) { ctx->cache_weights = value != 0; ctx->model_epoch++; return ASLSD_OK; }
   return aslsd_fail(ctx, ASLSD_ERR_ARG, "set_option: unknown option");
 }
 
@@ -682,7 +697,8 @@ extern "C" int aslsd_last_work_counts(aslsd_ctx* ctx, int64_t* counts, int n) {
   counts[0] = pe;
   counts[1] = se;
   int64_t pairs = 0;
-  for (int64_t w = 0; w < ctx->last_n_wu_q; ++w) pairs += (int64_t)h[n_old + (size_t)w];
+  if (!ctx->last_weights_reused)
+    for (int64_t w = 0; w < ctx->last_n_wu_q; ++w) pairs += (int64_t)h[n_old + (size_t)w];
   counts[2] = pairs;
   for (int c = 3; c < 8; ++c) counts[c] = ctx->last_work[c];
   return ASLSD_OK;

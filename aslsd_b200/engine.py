@@ -104,6 +104,12 @@ class Engine:
         self._check(self._lib.aslsd_last_timing(self._ctx, ctypes.byref(ms), ctypes.byref(n)))
         return ms.value, n.value
 
+    def last_moment_timing(self):
+        """Duration (ms) of the lag-moment kernel of the last exact-sum call."""
+        ms = ctypes.c_double()
+        self._check(self._lib.aslsd_last_moment_timing(self._ctx, ctypes.byref(ms)))
+        return ms.value
+
     def set_option(self, option, value):
         self._check(self._lib.aslsd_set_option(self._ctx, int(option), int(value)))
 
@@ -111,6 +117,12 @@ class Engine:
         """Lag quadrature for the interior targets of every double sum (default on);
         off: every row goes through the per-item pair kernels."""
         self.set_option(capi.OPT_LAG_QUADRATURE, 1 if enabled else 0)
+
+    def use_weight_cache(self, enabled=True):
+        """Keep the quadrature weights between calls on the same plan and events (default
+        on): the iterations of a fit with fixed (beta, delta) then skip the pass over the
+        event pairs.  Off: every call recomputes them (benchmark setting)."""
+        self.set_option(capi.OPT_WEIGHT_CACHE, 1 if enabled else 0)
 
     def last_work_counts(self):
         """Work of the last exact-sum call (see aslsd_last_work_counts)."""

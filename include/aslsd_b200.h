@@ -53,9 +53,13 @@ enum {
 
 /* Options of aslsd_set_option. */
 enum {
-  ASLSD_OPT_LAG_QUADRATURE = 1 /* 1 (default): interior targets of every double sum go through the
+  ASLSD_OPT_LAG_QUADRATURE = 1, /* 1 (default): interior targets of every double sum go through the
                                   lag quadrature (one pass per pair of event streams);
                                   0: per-item pair kernels only */
+  ASLSD_OPT_WEIGHT_CACHE = 2   /* 1 (default): the quadrature weights - a function of the event streams
+                                  and the lag windows only - are kept between calls while the events,
+                                  the model, the target block and the non-omega parameters stay the
+                                  same (the iterations of a fit); 0: recomputed on every call */
 };
 
 /* ---- lifetime ------------------------------------------------------------------ */
@@ -69,6 +73,9 @@ int aslsd_set_stream(aslsd_ctx* ctx, void* cuda_stream);
 /* CUDA-event duration (ms) and launch count of the pair / sample kernels of
  * the last sum call, measured on the launching stream. */
 int aslsd_last_timing(const aslsd_ctx* ctx, double* kernel_ms, int64_t* n_launches);
+/* CUDA-event duration (ms) of the lag-moment kernel of the last exact-sum call (0 if it did
+ * not run: quadrature off, no eligible stream, or cached weights reused). */
+int aslsd_last_moment_timing(const aslsd_ctx* ctx, double* kernel_ms);
 
 int aslsd_set_option(aslsd_ctx* ctx, int option, int value);
 

@@ -221,6 +221,78 @@ def test_lag_quadrature_random_parameters(engine, family):
         engine.use_lag_quadrature(True)
 
 
+def test_lag_quadrature_unbalanced_rates_and_many_bins(engine):
+    """A slow target stream against a fast source stream (the source window of a tile does not
+    fit the staged buffer: global-memory fallback of the moment kernel) and a wide spread of
+    decay rates (hundreds of bins: 10-bit ranks, small sort chunks)."""
+    rng = np.random.default_rng(77)
+    from aslsd_b200.engine import unpack_terms
+    T_f = 2500.
+    times = [np.sort(rng.uniform(0, T_f, size=600)), np.sort(rng.uniform(0, T_f, size=24000))]
+    model = {'d': 2, 'kernels': [[[{'type': 'exp'}] for _ in range(2)] for _ in range(2)]}
+    engine.set_events(times, T_f)
+    engine.set_model(model)
+    try:
+        for k, x in enumerate([np.array([0.5, 0.2, 0.3, 0.1, 3.0]), np.array([0.4, 0.1, 1.0, 0.2, 0.8])]):
+            engine.use_lag_quadrature(True)
+            a = engine.exact_sums_packed(k, x)
+            wa = engine.last_work_counts()
+            engine.use_lag_quadrature(False)
+            b = engine.exact_sums_packed(k, x)
+            fa, dfa = unpack_terms(engine.desc, k, a)
+            fb, dfb = unpack_terms(engine.desc, k, b)
+            ref = {'k/%s' % label: val for label, val in iter_sum_entries(fb, dfb)}
+            assert_sums_close(fa, dfa, ref, 'k', rtol=1e-11, atol=1e-10)
+            assert wa['moment_pairs'] > 0 and wa['bins'] > 128 * wa['streams'] / 2
+            o_f, o_df, _ = OE.exact_sums_windowed(model, k, x, times, T_f)
+            ref = {'k/%s' % label: val for label, val in iter_sum_entries(o_f, o_df)}
+            assert_sums_close(fa, dfa, ref, 'k', rtol=RTOL, atol=1e-10)
+    finally:
+        engine.use_lag_quadrature(True)
+
+
+def test_weight_cache_reuses_the_quadrature(engine):
+    """With the weight cache on, a second evaluation on the same events and (beta, delta)
+    skips the pass over the event pairs and gives the same sums; a new omega is honoured;
+    new events invalidate the weights."""
+    name = 'sbf2d3'
+    model = CASES[name][0]
+    rng = np.random.default_rng(8)
+    times = _simulate_poisson_cluster(rng, 2, 5000., 1.2)
+    engine.set_events(times, 5000.)
+    engine.set_model(model)
+    xs = case_x(name)
+    try:
+        engine.use_weight_cache(False)
+        ref0 = engine.exact_sums_packed(0, xs[0])
+        assert engine.last_work_counts()['moment_pairs'] > 0
+        ref0b = engine.exact_sums_packed(0, xs[0])
+        assert engine.last_work_counts()['moment_pairs'] > 0
+        np.testing.assert_array_equal(ref0, ref0b)      # deterministic
+        engine.use_weight_cache(True)
+        a = engine.exact_sums_packed(0, xs[0])
+        assert engine.last_work_counts()['moment_pairs'] > 0
+        b = engine.exact_sums_packed(0, xs[0])
+        assert engine.last_work_counts()['moment_pairs'] == 0
+        np.testing.assert_array_equal(a, ref0)
+        np.testing.assert_array_equal(b, ref0)
+        x2 = xs[0].copy()
+        x2[1:] *= 1.3
+        c = engine.exact_sums_packed(0, x2)
+        assert engine.last_work_counts()['moment_pairs'] == 0
+        engine.use_weight_cache(False)
+        np.testing.assert_array_equal(c, engine.exact_sums_packed(0, x2))
+        engine.use_weight_cache(True)
+        engine.exact_sums_packed(0, xs[0])
+        times2 = _simulate_poisson_cluster(rng, 2, 5000., 1.2)
+        engine.set_events(times2, 5000.)
+        d2 = engine.exact_sums_packed(0, xs[0])
+        assert engine.last_work_counts()['moment_pairs'] > 0
+        assert abs(d2[0] - ref0[0]) > 0
+    finally:
+        engine.use_weight_cache(True)
+
+
 def test_linearity_in_omega_for_sbf(engine):
     """Size-independent property: with (beta, delta) fixed every sum is a
     polynomial of degree <= 2 in omega; phi sums are linear."""
