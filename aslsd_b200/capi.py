@@ -46,6 +46,7 @@ SYMBOLS = {
     'aslsd_set_stream': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p]),
     'aslsd_last_timing': (ctypes.c_int, [ctypes.c_void_p, c_f64_p, c_i64_p]),
     'aslsd_last_moment_timing': (ctypes.c_int, [ctypes.c_void_p, c_f64_p]),
+    'aslsd_exact_raw_used': (ctypes.c_int, [ctypes.c_void_p, c_i64_p]),
     'aslsd_measure_fp64_peak': (ctypes.c_int, [ctypes.c_void_p, c_f64_p]),
     'aslsd_set_events': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, c_i64_p,
                                         ctypes.POINTER(c_f64_p), ctypes.c_double]),

@@ -623,6 +623,14 @@ extern "C" int aslsd_exact_raw_len_batch(aslsd_ctx* ctx, int n_k, int64_t* raw_l
   return ASLSD_OK;
 }
 
+// Number of doubles of the raw buffer actually written by the last raw_device call (rows x
+// ASLSD_MAX_COMP): the prefix to all-reduce / copy to the host.  Same on every rank.
+extern "C" int aslsd_exact_raw_used(aslsd_ctx* ctx, int64_t* raw_used) {
+  if (!ctx || !raw_used) return ASLSD_ERR_ARG;
+  *raw_used = ctx->last_work[6] * ASLSD_MAX_COMP;
+  return ASLSD_OK;
+}
+
 extern "C" int aslsd_exact_raw_len(aslsd_ctx* ctx, int k, int64_t* raw_len) {
   if (!ctx || !ctx->has_model || k < 0 || k >= ctx->d) return ASLSD_ERR_ARG;
   return aslsd_exact_raw_len_batch(ctx, 1, raw_len);

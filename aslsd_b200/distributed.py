@@ -71,6 +71,7 @@ class ShardedExactSums:
             self.engine.set_stream(self.torch.cuda.current_stream().cuda_stream)
         self.engine.exact_raw_device(k, x_k, raw.data_ptr(), compute_f_sum,
                                      compute_diff_f_sum, ranges=self.ranges)
+        raw = raw[:self.engine.exact_raw_used()]     # the rows this model has (same on all ranks)
         if self.world_size > 1:
             self.dist.all_reduce(raw, op=self.dist.ReduceOp.SUM)
         return raw
@@ -86,6 +87,7 @@ class ShardedExactSums:
             self.engine.set_stream(self.torch.cuda.current_stream().cuda_stream)
         self.engine.exact_raw_device_batch(ks, xs, raw.data_ptr(), compute_f_sum,
                                            compute_diff_f_sum, ranges=self.ranges)
+        raw = raw[:self.engine.exact_raw_used()]     # the rows this model has (same on all ranks)
         if self.world_size > 1:
             self.dist.all_reduce(raw, op=self.dist.ReduceOp.SUM)
         return raw

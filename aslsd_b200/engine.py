@@ -331,6 +331,12 @@ class Engine:
                           for k, cnt in zip(ks, cnts)]
         return outs
 
+    def exact_raw_used(self):
+        """Doubles of the raw buffer written by the last raw_device call."""
+        n = ctypes.c_int64()
+        self._check(self._lib.aslsd_exact_raw_used(self._ctx, ctypes.byref(n)))
+        return n.value
+
     def exact_raw_len_batch(self, n_k):
         n = ctypes.c_int64()
         self._check(self._lib.aslsd_exact_raw_len_batch(self._ctx, int(n_k), ctypes.byref(n)))

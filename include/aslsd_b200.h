@@ -148,6 +148,9 @@ int aslsd_exact_raw_device(aslsd_ctx* ctx, int k, const double* x_k, int flags,
                            double* raw_device, int64_t* n_pair_terms);
 int aslsd_exact_assemble(aslsd_ctx* ctx, int k, const double* x_k, int flags,
                          const double* raw_host, double* out);
+/* Doubles of the raw buffer written by the last raw_device call (a prefix of raw_len): the
+ * part to all-reduce and to copy to the host. */
+int aslsd_exact_raw_used(aslsd_ctx* ctx, int64_t* raw_used);
 int aslsd_exact_raw_len_batch(aslsd_ctx* ctx, int n_k, int64_t* raw_len);
 int aslsd_exact_raw_device_batch(aslsd_ctx* ctx, int n_k, const int* ks, const double* const* xs,
                                  int flags, const int64_t* m_lo, const int64_t* m_hi,

@@ -50,12 +50,16 @@ class OracleEngine:
     def exact_raw_len(self, k):
         return term_layout(self.desc, k)[1]
 
+    def exact_raw_used(self):
+        return self._raw_used
+
     def exact_raw_device(self, k, x_k, raw_ptr, compute_f_sum=True, compute_diff_f_sum=True,
                          ranges=None):
         import ctypes
         n = self.exact_raw_len(k)
         buf = np.ctypeslib.as_array((ctypes.c_double * n).from_address(raw_ptr))
         buf[:] = self.exact_sums_packed(k, x_k, compute_f_sum, compute_diff_f_sum, ranges=ranges)
+        self._raw_used = n
 
     def exact_assemble(self, k, x_k, raw_host, compute_f_sum=True, compute_diff_f_sum=True):
         return np.array(raw_host, dtype=float)
@@ -73,6 +77,7 @@ class OracleEngine:
         for q, (k, x) in enumerate(zip(ks, xs)):
             packed = self.exact_sums_packed(k, x, compute_f_sum, compute_diff_f_sum, ranges=ranges)
             buf[q * stride:q * stride + len(packed)] = packed
+        self._raw_used = n
 
     def exact_assemble_batch(self, ks, xs, raw_host, compute_f_sum=True, compute_diff_f_sum=True):
         stride = len(raw_host) // len(ks)
