@@ -59,6 +59,11 @@ SYMBOLS = {
     'aslsd_exact_out_len': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, c_i64_p, c_i64_p]),
     'aslsd_exact_sums': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, c_f64_p, ctypes.c_int,
                                         c_i64_p, c_i64_p, c_f64_p, c_i64_p]),
+    'aslsd_set_weights': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, c_i32_p,
+                                         ctypes.POINTER(c_f64_p)]),
+    'aslsd_exact_sums_weighted': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, c_f64_p, ctypes.c_int,
+                                                 c_i64_p, c_i64_p, c_i32_p,
+                                                 ctypes.POINTER(ctypes.c_uint8), c_f64_p, c_i64_p]),
     'aslsd_exact_raw_len': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, c_i64_p]),
     'aslsd_exact_raw_device': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, c_f64_p, ctypes.c_int,
                                               c_i64_p, c_i64_p, ctypes.c_void_p, c_i64_p]),

@@ -51,6 +51,8 @@ struct ItemDev {
   double bo, dlo;        // beta / delta of the own basis (sim-own components)
   int64_t dst_row;       // row of the raw accumulator array this item adds into
   int64_t n_int;         // single-index rows: interior targets taken as n_int x closed form
+  int64_t wa_off, wb_off; // per-event weights of the targets / sources: offsets (in doubles) into the
+                          // context's weight block, -1 = no weight (marked models, aslsd_set_weights)
 };
 
 enum {
@@ -102,6 +104,13 @@ struct aslsd_ctx {
   int32_t* d_tab = nullptr;
   // device copies of the per-dimension metadata
   void* d_dims = nullptr;          // DimDev[d]
+
+  // per-event weight vectors (impact values of marked models) and how the next plan uses them
+  double* d_weights = nullptr; size_t weights_cap = 0;
+  std::vector<int64_t> weight_off;    // offset of vector v in d_weights
+  std::vector<int> weight_dim;        // event type of vector v
+  const int32_t* roles = nullptr;     // [5 * d] weight vector per (role, type), see aslsd_exact_sums_weighted
+  const uint8_t* term_mask = nullptr; // per term: 0 = skip
 
   // model
   bool has_model = false;

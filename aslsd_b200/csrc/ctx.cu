@@ -68,6 +68,7 @@ extern "C" int aslsd_destroy(aslsd_ctx* ctx) {
   cudaFree(ctx->d_counts);
   if (ctx->plan_cache && ctx->plan_cache_free) ctx->plan_cache_free(ctx->plan_cache);
   cudaFree(ctx->d_sample);
+  cudaFree(ctx->d_weights);
   cudaFree(ctx->d_qtab);
   cudaFree(ctx->d_q_partials);
   cudaFree(ctx->d_q_weights);
@@ -152,6 +153,8 @@ extern "C" int aslsd_set_events(aslsd_ctx* ctx, int d, const int64_t* n_events,
     return rc;
   if ((rc = ensure_device_buffer(ctx, &ctx->d_dims, &ctx->dims_cap, sizeof(DimDev) * d))) return rc;
   ctx->events_epoch++;
+  ctx->weight_off.clear();     // weight vectors belong to the previous events
+  ctx->weight_dim.clear();
   if (d != ctx->d) ctx->model_epoch++;
   ctx->h_times.assign(d, nullptr);
   // Host pass (copy into the pinned block + order check) split into segments over a few
@@ -257,6 +260,34 @@ extern "C" int aslsd_set_events(aslsd_ctx* ctx, int d, const int64_t* n_events,
   }
   CUDA_TRY(ctx, cudaGetLastError());
   CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));   // `dims` is a stack object
+  return ASLSD_OK;
+}
+
+// Per-event weight vectors: the impact values I_ki(xi^i_n) of a marked model and their
+// parameter derivatives, evaluated by the reference's own impact objects on the host
+// (functionals/impact_functions/impact_function.py:116-131) once per evaluation point.
+extern "C" int aslsd_set_weights(aslsd_ctx* ctx, int n_vec, const int32_t* dims, const double* const* vals) {
+  if (!ctx || n_vec < 0 || (n_vec > 0 && (!dims || !vals)))
+    return aslsd_fail(ctx, ASLSD_ERR_ARG, "set_weights: bad arguments");
+  if (ctx->d == 0 || !ctx->d_times) return aslsd_fail(ctx, ASLSD_ERR_ARG, "set_weights: no events set");
+  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  std::vector<int64_t> off(n_vec + 1, 0);
+  for (int v = 0; v < n_vec; ++v) {
+    if (dims[v] < 0 || dims[v] >= ctx->d || !vals[v])
+      return aslsd_fail(ctx, ASLSD_ERR_ARG, "set_weights: bad event type");
+    off[v + 1] = off[v] + ctx->n_events[dims[v]];
+  }
+  int rc;
+  const size_t bytes = std::max<size_t>(1, (size_t)off[n_vec]) * sizeof(double);
+  if ((rc = ensure_device_buffer(ctx, (void**)&ctx->d_weights, &ctx->weights_cap, bytes))) return rc;
+  if ((rc = ensure_pinned_buffer(ctx, bytes))) return rc;
+  double* hp = (double*)ctx->h_pinned;
+  for (int v = 0; v < n_vec; ++v)
+    std::memcpy(hp + off[v], vals[v], sizeof(double) * (size_t)(off[v + 1] - off[v]));
+  CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_weights, hp, bytes, cudaMemcpyHostToDevice, ctx->stream));
+  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));   // the pinned block is reused
+  ctx->weight_off.assign(off.begin(), off.end() - 1);
+  ctx->weight_dim.assign(dims, dims + n_vec);
   return ASLSD_OK;
 }
 

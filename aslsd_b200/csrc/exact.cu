@@ -218,6 +218,7 @@ static int build_work(aslsd_ctx* ctx, const int64_t* m_lo, const int64_t* m_hi, 
     for (size_t r = 0; r < n_rows; ++r) {
       const ItemDev& it = B.rows[r];
       if (!is_pair_family(it.family) || it.m_hi <= it.m_lo) continue;
+      if (it.wa_off >= 0 || it.wb_off >= 0) continue;   // per-event weights: per-item kernels
       std::array<int64_t, 4> key = {it.tgt_dim, it.src_dim, it.m_lo, it.m_hi};
       auto f = groups.find(key);
       if (f == groups.end()) {
@@ -241,7 +242,7 @@ static int build_work(aslsd_ctx* ctx, const int64_t* m_lo, const int64_t* m_hi, 
     if (fast[r]) {
       if (boundary_from[r] >= it.m_hi) continue;
       it.m_lo = boundary_from[r];
-    } else if (!is_pair_family(it.family) && it.m_hi > it.m_lo && std::isfinite(it.t_int)) {
+    } else if (!is_pair_family(it.family) && it.m_hi > it.m_lo && std::isfinite(it.t_int) && it.wa_off < 0) {
       // single-index rows are constant in the interior: n_int x closed form
       const int64_t m_b = interior_end(ctx, it.tgt_dim, it.m_lo, it.m_hi, it.t_int);
       it.n_int = m_b - it.m_lo;
@@ -350,7 +351,7 @@ static void launch_pair(aslsd_ctx* ctx, const BatchPlan& B, const ItemDev* d_ite
   if (B.fam_wu_count[FAMILY] == 0) return;
   pair_kernel<FAMILY><<<(unsigned)B.fam_wu_count[FAMILY], PAIR_NT, 0, ctx->stream>>>(
       (const DimDev*)ctx->d_dims, d_items + B.fam_first[FAMILY], B.fam_count[FAMILY], ctx->T_f,
-      ctx->d_partials, ctx->d_counts, B.fam_wu_first[FAMILY]);
+      ctx->d_partials, ctx->d_counts, B.fam_wu_first[FAMILY], ctx->d_weights);
   ctx->last_launches++;
 }
 template <int FAMILY>
@@ -358,7 +359,7 @@ static void launch_single(aslsd_ctx* ctx, const BatchPlan& B, const ItemDev* d_i
   if (B.fam_wu_count[FAMILY] == 0) return;
   single_kernel<FAMILY><<<(unsigned)B.fam_wu_count[FAMILY], PAIR_NT, 0, ctx->stream>>>(
       (const DimDev*)ctx->d_dims, d_items + B.fam_first[FAMILY], B.fam_count[FAMILY], ctx->T_f,
-      ctx->d_partials, ctx->d_counts, B.fam_wu_first[FAMILY]);
+      ctx->d_partials, ctx->d_counts, B.fam_wu_first[FAMILY], ctx->d_weights);
   ctx->last_launches++;
 }
 
@@ -612,6 +613,40 @@ extern "C" int aslsd_exact_sums(aslsd_ctx* ctx, int k, const double* x_k, int fl
   double* outs[1] = {out};
   int64_t* cnts[1] = {n_pair_terms};
   return aslsd_exact_sums_batch(ctx, 1, &k, xs, flags, m_lo, m_hi, outs, n_pair_terms ? cnts : nullptr);
+}
+
+// Marked models (MTLH): the same terms with per-event weights.  roles[r * d + i] names the weight
+// vector (index into aslsd_set_weights, -1 = none) applied to
+//   r = 0: the sources of phi_i            (I_ki(xi^i_n),            mtlh_exact_estimator.py:838)
+//   r = 1: the targets of upsilon_i_*      (I_ki(xi^i_m),            :896-897, :950)
+//   r = 2: the sources of upsilon_*_i      (I_ki(xi^i_n))
+//   r = 3: the targets of psi_i            (K_i term: I_ki(xi^i_m),  :707-753)
+//   r = 4: the targets of upsilonzero_i    (I_ki(xi^i_m)^2,          :755-805)
+// term_mask (may be NULL): one byte per term in output order, 0 = leave the term at zero.  The
+// derivatives with respect to the impact parameters are value sums with one weight vector
+// replaced by the derivative of the impact (host side: aslsd_b200/mtlh.py).
+extern "C" int aslsd_exact_sums_weighted(aslsd_ctx* ctx, int k, const double* x_k, int flags,
+                                         const int64_t* m_lo, const int64_t* m_hi, const int32_t* roles,
+                                         const uint8_t* term_mask, double* out, int64_t* n_pair_terms) {
+  if (!ctx || !x_k || !out || !roles) return aslsd_fail(ctx, ASLSD_ERR_ARG, "exact_sums_weighted: bad arguments");
+  if (!ctx->has_model) return aslsd_fail(ctx, ASLSD_ERR_ARG, "exact sums: no model set");
+  const int d = ctx->d;
+  for (int r = 0; r < 5; ++r)
+    for (int i = 0; i < d; ++i) {
+      const int v = roles[r * d + i];
+      if (v < 0) continue;
+      if (v >= (int)ctx->weight_off.size() || ctx->weight_dim[v] != i)
+        return aslsd_fail(ctx, ASLSD_ERR_ARG, "exact_sums_weighted: weight vector of another event type");
+    }
+  // plans built with weights are never reused for other calls
+  ctx->model_epoch++;
+  ctx->roles = roles;
+  ctx->term_mask = term_mask;
+  const int rc = aslsd_exact_sums(ctx, k, x_k, flags, m_lo, m_hi, out, n_pair_terms);
+  ctx->roles = nullptr;
+  ctx->term_mask = nullptr;
+  ctx->model_epoch++;
+  return rc;
 }
 
 // Split form for multi-GPU: device-side raw rows (summed across ranks by the caller's

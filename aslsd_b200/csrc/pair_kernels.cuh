@@ -94,7 +94,8 @@ __device__ __forceinline__ void block_reduce_store(double* acc, unsigned long lo
 template <int FAMILY>
 __global__ void __launch_bounds__(PAIR_NT, 2)
 pair_kernel(const DimDev* __restrict__ dims, const ItemDev* __restrict__ items, int n_items, double T_f,
-            double* __restrict__ partials, unsigned long long* __restrict__ counts, int64_t wu_base) {
+            double* __restrict__ partials, unsigned long long* __restrict__ counts, int64_t wu_base,
+            const double* __restrict__ weights) {
   __shared__ __align__(16) double s_src[PAIR_SMAX + 2];
   __shared__ double s_t[PAIR_TM];
   __shared__ int64_t s_lo[PAIR_TM];       // lo(m): first in-window source of target m
@@ -114,6 +115,7 @@ pair_kernel(const DimDev* __restrict__ dims, const ItemDev* __restrict__ items, 
   const int64_t m_end = min(it.m_hi, m_begin + it.tpw);
   const int mask = it.mask;
   const bool same = it.same != 0;
+  const bool weighted = it.wa_off >= 0 || it.wb_off >= 0;
 
   UpsGaussConst KG;
   UpsExpConst KE;
@@ -204,17 +206,29 @@ pair_kernel(const DimDev* __restrict__ dims, const ItemDev* __restrict__ items, 
       const double tm = s_t[lo];
       const int64_t n = s_lo[lo] + (p - s_pre[lo]);
       const double s = tm - srcp[n];
-      if (FAMILY == ITEM_UPS_GAUSS) {
-        if (interior) eval_ups_gauss<true>(KG, mask, 0., s, acc);
-        else eval_ups_gauss<false>(KG, mask, T_f - tm, s, acc);
-      } else if (FAMILY == ITEM_UPS_EXP) {
-        if (interior) eval_ups_exp<true>(KE, mask, 0., s, acc);
-        else eval_ups_exp<false>(KE, mask, T_f - tm, s, acc);
-      } else if (FAMILY == ITEM_PHI_EXP) {
-        eval_phi_exp(KP, mask, s, acc);
-      } else {
-        eval_phi_gauss(KP, mask, s, acc);
+      // per-event weights of a marked model: impact of the target times impact of the source
+      // (mtlh_exact_estimator.py:838, :896-897); 1 for unmarked models
+      double w = 1.;
+      if (weighted) {
+        if (it.wa_off >= 0) w = weights[it.wa_off + m0 + lo];
+        if (it.wb_off >= 0) w *= weights[it.wb_off + n];
       }
+      double v[ASLSD_MAX_COMP];
+#pragma unroll
+      for (int c = 0; c < ASLSD_MAX_COMP; ++c) v[c] = 0.;
+      if (FAMILY == ITEM_UPS_GAUSS) {
+        if (interior) eval_ups_gauss<true>(KG, mask, 0., s, v);
+        else eval_ups_gauss<false>(KG, mask, T_f - tm, s, v);
+      } else if (FAMILY == ITEM_UPS_EXP) {
+        if (interior) eval_ups_exp<true>(KE, mask, 0., s, v);
+        else eval_ups_exp<false>(KE, mask, T_f - tm, s, v);
+      } else if (FAMILY == ITEM_PHI_EXP) {
+        eval_phi_exp(KP, mask, s, v);
+      } else {
+        eval_phi_gauss(KP, mask, s, v);
+      }
+#pragma unroll
+      for (int c = 0; c < ASLSD_MAX_COMP; ++c) acc[c] = fma(w, v[c], acc[c]);
     }
     n_eval += (unsigned long long)((total - tid + PAIR_NT - 1) / PAIR_NT) * (tid < total ? 1 : 0);
     fence_proxy_async();   // generic reads of s_src before the next tile's async write
@@ -228,7 +242,8 @@ pair_kernel(const DimDev* __restrict__ dims, const ItemDev* __restrict__ items, 
 template <int FAMILY>
 __global__ void __launch_bounds__(PAIR_NT, 2)
 single_kernel(const DimDev* __restrict__ dims, const ItemDev* __restrict__ items, int n_items, double T_f,
-              double* __restrict__ partials, unsigned long long* __restrict__ counts, int64_t wu_base) {
+              double* __restrict__ partials, unsigned long long* __restrict__ counts, int64_t wu_base,
+              const double* __restrict__ weights) {
   __shared__ double s_red[(PAIR_NT / 32) * ASLSD_MAX_COMP];
   const int tid = threadIdx.x;
   const int64_t wu = (int64_t)blockIdx.x + wu_base;
@@ -252,17 +267,23 @@ single_kernel(const DimDev* __restrict__ dims, const ItemDev* __restrict__ items
   for (int64_t m = m_begin + tid; m < m_end; m += PAIR_NT) {
     const double t = T_f - Dt.t[m];
     const bool interior = t >= it.t_int;
+    const double w = it.wa_off >= 0 ? weights[it.wa_off + m] : 1.;   // marked models
+    double v[ASLSD_MAX_COMP];
+#pragma unroll
+    for (int c = 0; c < ASLSD_MAX_COMP; ++c) v[c] = 0.;
     if (FAMILY == ITEM_UPS0_GAUSS) {
-      if (interior) eval_ups_gauss<true>(KG, mask, 0., 0., acc);
-      else eval_ups_gauss<false>(KG, mask, t, 0., acc);
+      if (interior) eval_ups_gauss<true>(KG, mask, 0., 0., v);
+      else eval_ups_gauss<false>(KG, mask, t, 0., v);
     } else if (FAMILY == ITEM_UPS0_EXP) {
-      if (interior) eval_ups_exp<true>(KE, mask, 0., 0., acc);
-      else eval_ups_exp<false>(KE, mask, t, 0., acc);
+      if (interior) eval_ups_exp<true>(KE, mask, 0., 0., v);
+      else eval_ups_exp<false>(KE, mask, t, 0., v);
     } else if (FAMILY == ITEM_PSI_EXP) {
-      eval_psi_exp(KP, mask, t, acc);
+      eval_psi_exp(KP, mask, t, v);
     } else {
-      eval_psi_gauss(KP, mask, t, acc);
+      eval_psi_gauss(KP, mask, t, v);
     }
+#pragma unroll
+    for (int c = 0; c < ASLSD_MAX_COMP; ++c) acc[c] = fma(w, v[c], acc[c]);
     ++n_eval;
   }
   if (chunk == 0 && tid == 0 && it.n_int > 0) {

@@ -65,6 +65,12 @@ static void own_window(int type, const Vars& v, double* s_hi, double* t_int) {
 
 struct ItemRef { int fam, idx; };
 
+// Per-event weights (marked models) and activity of the term being planned.
+struct TermWeights {
+  int64_t wa = -1, wb = -1;   // offsets into the context's weight block
+  bool active = true;         // false: the term is masked out, its slots stay empty
+};
+
 // Build the work items of an upsilon-type term.
 //   VA1/VA2: variables of the value closure (structure KU), VB: variables of the
 //   derivative closure of a same-type term (K[k][i]); merged when equal.
@@ -72,7 +78,8 @@ static void plan_upsilon(const aslsd_ctx* ctx, SumPlan& P, std::vector<ItemDev> 
                          std::vector<std::pair<int, ItemRef>>& fixups, const KernelHost& KU,
                          const std::vector<Vars>& VA1, const std::vector<Vars>& VA2,
                          const KernelHost* KB, const std::vector<Vars>* VB, int tgt, int src, bool single,
-                         int64_t m_lo, int64_t m_hi, bool diff, bool by_term, double* u_lo, double* u_hi) {
+                         int64_t m_lo, int64_t m_hi, bool diff, bool by_term, double* u_lo, double* u_hi,
+                         const TermWeights& W) {
   const int R1 = (int)KU.bases.size(), R2 = R1;
   const bool sim = (KB != nullptr);
   const bool merged = sim && vars_equal(VA1, *VB);
@@ -83,8 +90,11 @@ static void plan_upsilon(const aslsd_ctx* ctx, SumPlan& P, std::vector<ItemDev> 
   *u_lo = 1e300;
   *u_hi = 0.;
   auto emit = [&](int p, int q, const Vars& v1, const Vars& v2, int mask, bool own, const Vars& vo) {
+    if (!W.active) return -1;
     ItemDev it;
     std::memset(&it, 0, sizeof(it));
+    it.wa_off = W.wa;
+    it.wb_off = W.wb;
     it.family = fam;
     it.tgt_dim = tgt;
     it.src_dim = src;
@@ -172,15 +182,23 @@ static void plan_upsilon(const aslsd_ctx* ctx, SumPlan& P, std::vector<ItemDev> 
 static void plan_basis_items(SumPlan& P, std::vector<ItemDev> fam_items[8],
                              std::vector<std::pair<int, ItemRef>>& fixups, const KernelHost& K,
                              const std::vector<Vars>& V, bool is_phi, int tgt, int src, int64_t m_lo,
-                             int64_t m_hi, bool diff, bool by_term, double* u_lo, double* u_hi) {
+                             int64_t m_hi, bool diff, bool by_term, double* u_lo, double* u_hi,
+                             const TermWeights& W) {
   P.term_val_off.push_back((int)P.slot_item.size());
   *u_lo = 1e300;
   *u_hi = 0.;
   for (size_t r = 0; r < K.bases.size(); ++r) {
     const BasisHost& b = K.bases[r];
     const bool is_exp = b.type == ASLSD_BASIS_EXPONENTIAL;
+    if (!W.active) {
+      fixups.push_back({(int)P.slot_item.size(), ItemRef{0, -1}});
+      P.slot_item.push_back(-1);
+      continue;
+    }
     ItemDev it;
     std::memset(&it, 0, sizeof(it));
+    it.wa_off = W.wa;
+    it.wb_off = W.wb;
     it.family = is_phi ? (is_exp ? ITEM_PHI_EXP : ITEM_PHI_GAUSS) : (is_exp ? ITEM_PSI_EXP : ITEM_PSI_GAUSS);
     it.tgt_dim = tgt;
     it.src_dim = src;
@@ -273,6 +291,20 @@ int build_plan(aslsd_ctx* ctx, int k, const double* x_k, int flags, const int64_
     P.terms.push_back(t);
   };
   double ul, uh;
+  // weights / activity of a term: role 0 phi sources, 1 upsilon targets, 2 upsilon sources,
+  // 3 psi targets, 4 upsilonzero targets (aslsd_exact_sums_weighted)
+  auto weight_of = [&](int role, int dim) -> int64_t {
+    if (!ctx->roles || by_term) return -1;
+    const int v = ctx->roles[role * d + dim];
+    return v < 0 ? -1 : ctx->weight_off[v];
+  };
+  auto term_w = [&](int64_t wa, int64_t wb) {
+    TermWeights W;
+    W.wa = wa;
+    W.wb = wb;
+    W.active = by_term || !ctx->term_mask || ctx->term_mask[P.terms.size() - 1] != 0;
+    return W;
+  };
   // in term order the single storage list gives every term a contiguous item range
   auto close_term = [&](size_t first) {
     if (!by_term) return;
@@ -286,27 +318,29 @@ int build_plan(aslsd_ctx* ctx, int k, const double* x_k, int flags, const int64_
     // psi_i (:543-578)
     add_term(0, i, i, np, 1);
     first = fam_items[0].size();
-    plan_basis_items(P, fam_items, fixups, Kki, P.V[i], false, i, i, lo[i], hi[i], diff, by_term, &ul, &uh);
+    plan_basis_items(P, fam_items, fixups, Kki, P.V[i], false, i, i, lo[i], hi[i], diff, by_term, &ul, &uh,
+                     term_w(weight_of(3, i), -1));
     close_term(first);
     P.term_s_lo.push_back(0.); P.term_s_hi.push_back(-1.);
     // upsilonzero_i (:580-609)
     add_term(1, i, i, np, 0);
     first = fam_items[0].size();
     plan_upsilon(ctx, P, fam_items, fixups, KU, P.VU[i], P.VU[i], &Kki, &P.V[i], i, i, true, lo[i], hi[i], diff,
-                 by_term, &ul, &uh);
+                 by_term, &ul, &uh, term_w(weight_of(4, i), -1));
     close_term(first);
     P.term_s_lo.push_back(0.); P.term_s_hi.push_back(-1.);
     // phi_i (:611-638): targets of type k, sources of type i
     add_term(2, i, i, np, 0);
     first = fam_items[0].size();
-    plan_basis_items(P, fam_items, fixups, Kki, P.V[i], true, k, i, lo[k], hi[k], diff, by_term, &ul, &uh);
+    plan_basis_items(P, fam_items, fixups, Kki, P.V[i], true, k, i, lo[k], hi[k], diff, by_term, &ul, &uh,
+                     term_w(-1, weight_of(0, i)));
     close_term(first);
     P.term_s_lo.push_back(ul); P.term_s_hi.push_back(uh);
     // upsilon_i_i (:675-707)
     add_term(3, i, i, np, 0);
     first = fam_items[0].size();
     plan_upsilon(ctx, P, fam_items, fixups, KU, P.VU[i], P.VU[i], &Kki, &P.V[i], i, i, false, lo[i], hi[i], diff,
-                 by_term, &ul, &uh);
+                 by_term, &ul, &uh, term_w(weight_of(1, i), weight_of(2, i)));
     close_term(first);
     P.term_s_lo.push_back(ul); P.term_s_hi.push_back(uh);
   }
@@ -317,7 +351,7 @@ int build_plan(aslsd_ctx* ctx, int k, const double* x_k, int flags, const int64_
       add_term(3, i, j, ctx->kernels[k * d + i].n_param(), ctx->kernels[k * d + j].n_param());
       const size_t first = fam_items[0].size();
       plan_upsilon(ctx, P, fam_items, fixups, KU, P.VU[i], P.VU[j], nullptr, nullptr, i, j, false, lo[i], hi[i],
-                   diff, by_term, &ul, &uh);
+                   diff, by_term, &ul, &uh, term_w(weight_of(1, i), weight_of(2, j)));
       close_term(first);
       P.term_s_lo.push_back(ul); P.term_s_hi.push_back(uh);
     }

@@ -225,6 +225,46 @@ class Engine:
             return sum_f, sum_diff_f, counts
         return sum_f, sum_diff_f
 
+    # ---- marked models: per-event weights ---------------------------------------------
+    def set_weights(self, vectors):
+        """Upload per-event weight vectors: ``vectors`` is a list of (event type, values)
+        with one value per event of that type.  They are referred to by position in
+        ``exact_sums_weighted``."""
+        vals = [capi.as_f64(np.asarray(v, dtype=np.float64)) for _, v in vectors]
+        dims = np.ascontiguousarray([int(i) for i, _ in vectors], dtype=np.int32)
+        for (i, _), v in zip(vectors, vals):
+            if len(v) != self.n_events[i]:
+                raise ValueError('weight vector of type %d has %d entries, expected %d'
+                                 % (i, len(v), self.n_events[i]))
+        ptrs = (capi.c_f64_p * max(1, len(vals)))(*[capi.ptr_f64(v) for v in vals])
+        self._check(self._lib.aslsd_set_weights(self._ctx, len(vals),
+                                                dims.ctypes.data_as(capi.c_i32_p), ptrs))
+
+    def exact_sums_weighted(self, k, x_k, roles, term_mask=None, compute_f_sum=True,
+                            compute_diff_f_sum=True, ranges=None):
+        """Packed sums of ``exact_sums_packed`` with per-event weights
+        (aslsd_exact_sums_weighted): ``roles`` is a (5, d) integer array of weight
+        vector positions (-1: unweighted); ``term_mask`` an optional boolean array over
+        the terms in output order."""
+        x = capi.as_f64(np.asarray(x_k, dtype=np.float64))
+        if len(x) != self.desc.n_param_k(k):
+            raise ValueError('x_k has %d entries, expected %d' % (len(x), self.desc.n_param_k(k)))
+        layout, out_len = term_layout(self.desc, k)
+        roles = np.ascontiguousarray(roles, dtype=np.int32).reshape(5 * self.d)
+        mask = mask_p = None
+        if term_mask is not None:
+            mask = np.ascontiguousarray(term_mask, dtype=np.uint8)
+            if len(mask) != len(layout):
+                raise ValueError('term_mask must have one entry per term')
+            mask_p = mask.ctypes.data_as(ctypes.POINTER(ctypes.c_uint8))
+        out = np.zeros(out_len, dtype=np.float64)
+        flags = (capi.ASLSD_F if compute_f_sum else 0) | (capi.ASLSD_DIFF if compute_diff_f_sum else 0)
+        lo, hi, lo_p, hi_p = self._ranges(ranges)
+        self._check(self._lib.aslsd_exact_sums_weighted(
+            self._ctx, int(k), capi.ptr_f64(x), flags, lo_p, hi_p,
+            roles.ctypes.data_as(capi.c_i32_p), mask_p, capi.ptr_f64(out), None))
+        return out
+
     # ---- sampled sums ----------------------------------------------------------------
     def sampled_n_out(self, k, kind, i, j):
         n = ctypes.c_int32()

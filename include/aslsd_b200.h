@@ -129,6 +129,21 @@ int aslsd_exact_sums(aslsd_ctx* ctx, int k, const double* x_k, int flags,
                      const int64_t* m_lo, const int64_t* m_hi, double* out,
                      int64_t* n_pair_terms);
 
+/* ---- marked models: replaces the pair sums of MTLHExactEstim.compute_objective -------
+ * optimize/estimators/mtlh_exact_estimator.py:685-971 for constant baselines.  The impact
+ * functions stay the reference's Python (functionals/impact_functions/impact_function.py:
+ * 116-131): the caller evaluates I_ki(xi^i) and its parameter derivatives per event and hands
+ * them over as weight vectors; vector v holds one double per event of type dims[v].
+ * aslsd_exact_sums_weighted computes the terms of aslsd_exact_sums with every event pair /
+ * event weighted by the vectors that `roles` names (5 * d entries, -1 = unweighted):
+ *   roles[0*d+i] sources of phi_i, [1*d+i] targets of upsilon_i_*, [2*d+i] sources of
+ *   upsilon_*_i, [3*d+i] targets of psi_i (the K_i term), [4*d+i] targets of upsilonzero_i.
+ * term_mask (may be NULL): one byte per term in output order, 0 = term left at zero. */
+int aslsd_set_weights(aslsd_ctx* ctx, int n_vec, const int32_t* dims, const double* const* vals);
+int aslsd_exact_sums_weighted(aslsd_ctx* ctx, int k, const double* x_k, int flags,
+                              const int64_t* m_lo, const int64_t* m_hi, const int32_t* roles,
+                              const uint8_t* term_mask, double* out, int64_t* n_pair_terms);
+
 /* Several sub-problems in one call: what d calls of lse_k_grad_estimate compute
  * (the k loop of MHP.fit, models/hawkes/linear/mhp.py:1771-1787, or MHP.get_lse,
  * :639-664).  Work items whose raw sums coincide - same event streams, target

@@ -57,6 +57,43 @@ CASES = {
 }
 
 
+# Marked models (MTLH): name -> (model incl. impacts, x_k per k, number of events per type, T_f).
+# Constant baselines; linear impact 1 + <a, xi> on marks uniform in [0, 1]^q
+# (basis_impact_linear.py:36-41); kernels as above.
+def _linear(q=1):
+    return {'type': 'linear', 'mark_dim': q}
+
+
+def mtlh_model(d, make_kernel, make_impact):
+    return {'d': d, 'kernels': [[make_kernel() for _ in range(d)] for _ in range(d)],
+            'impacts': [[make_impact() for _ in range(d)] for _ in range(d)]}
+
+
+MTLH_CASES = {
+    'mtlh_exp2d': (mtlh_model(2, exp_kernel, _linear),
+                   [[.8, .3, 1., .2, 1.5, .5, .7], [.6, .25, 2., .1, 1.3, .4, .9]], [60, 45], 50.),
+    'mtlh_exp1d_m2': (mtlh_model(1, exp_kernel, lambda: _linear(2)),
+                      [[1.1, .35, .9, .6, .3]], [80], 60.),
+    'mtlh_gauss1d': (mtlh_model(1, gauss_kernel, _linear),
+                     [[.9, .4, .5, 2., .8]], [70], 60.),
+    'mtlh_sbf2d3': (mtlh_model(2, lambda: sbf_gauss_kernel(3), _linear),
+                    [[.5, .2, .1, .1, .1, .2, .05, .6, .3], [.4, .05, .1, .2, .2, .1, .1, .2, .7]],
+                    [55, 65], 60.),
+    'mtlh_exp2d_const': (mtlh_model(2, exp_kernel, lambda: {'type': 'constant'}),
+                         [[.8, .3, 1., .2, 1.5], [.6, .25, 2., .1, 1.3]], [50, 40], 40.),
+}
+
+
+def mtlh_inputs(name):
+    """Seeded event times and marks of an MTLH case."""
+    model, xs, n_events, T_f = MTLH_CASES[name]
+    rng = np.random.default_rng(321)
+    times = [np.sort(rng.uniform(0, T_f, size=n)) for n in n_events]
+    q = max(imp.get('mark_dim', 1) for row in model['impacts'] for imp in row)
+    marks = [rng.uniform(0, 1, size=(n, q)) for n in n_events]
+    return times, marks, T_f
+
+
 def case_x(name):
     """Evaluation points: truth * (1 + 0.1 U(-1, 1)), default_rng(12)
     (SURVEY section 8d)."""

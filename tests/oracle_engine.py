@@ -45,6 +45,88 @@ class OracleEngine:
                 out[off + 1:off + 1 + n1] = sum_diff_f[name]
         return out
 
+    # ---- marked models: per-event weights (aslsd_set_weights / aslsd_exact_sums_weighted) ----
+    def set_weights(self, vectors):
+        self.weights = [(int(i), np.asarray(v, dtype=float)) for i, v in vectors]
+
+    def exact_sums_weighted(self, k, x_k, roles, term_mask=None, compute_f_sum=True,
+                            compute_diff_f_sum=True, ranges=None):
+        """Literal O(N^2) weighted sums in the packed layout of exact_sums_packed."""
+        from oracle import functionals as F
+        self.n_calls += 1
+        model, times, T_f = self.plain, self.times, self.T_f
+        d = model['d']
+        K = model['kernels']
+        KU = OE.ups_kernel(model)
+        imap = OE.interval_map(model, k)
+        roles = np.asarray(roles).reshape(5, d)
+        x_k = np.asarray(x_k, dtype=float)
+
+        def wv(role, dim, n):
+            v = roles[role][dim]
+            if v < 0:
+                return np.ones(n)
+            assert self.weights[v][0] == dim
+            return self.weights[v][1]
+        layout, out_len = term_layout(self.desc, k)
+        out = np.zeros(out_len)
+        mask = np.ones(len(layout), dtype=bool) if term_mask is None else np.asarray(term_mask, dtype=bool)
+        for (name, off, n1, n2, n_func), on in zip(layout, mask):
+            if not on:
+                continue
+            kind, rest = name.split('_', 1)
+            idx = [int(v) for v in rest.split('_')]
+            i = idx[0]
+            x_ki = x_k[imap[i][0]:imap[i][1]]
+            t2e = T_f - times[i]
+            if kind == 'psi':
+                w = wv(3, i, len(times[i]))
+                s_psi = np.sum(F.psi(K[k][i], t2e, x_ki) * w)
+                out[off] = x_k[0] * s_psi
+                for p in range(n1):
+                    out[off + 1 + p] = x_k[0] * np.sum(F.diff_psi(K[k][i], t2e, p, x_ki) * w)
+                out[off + 1 + n1] = s_psi
+            elif kind == 'upsilonzero':
+                w = wv(4, i, len(times[i]))
+                out[off] = np.sum(F.upsilon(KU, KU, t2e, 0., x_ki, x_ki) * w)
+                for p in range(n1):
+                    out[off + 1 + p] = np.sum(F.diff_sim_upsilon(K[k][i], t2e, 0., p, x_ki) * w)
+            elif kind == 'phi':
+                tk, ti = times[k], times[i]
+                w = wv(0, i, len(ti))
+                for m in range(len(tk)):
+                    hi = m if i == k else np.searchsorted(ti, tk[m], side='left')
+                    if hi == 0:
+                        continue
+                    s = tk[m] - ti[:hi]
+                    out[off] += np.sum(F.phi(K[k][i], s, x_ki) * w[:hi])
+                    for p in range(n1):
+                        out[off + 1 + p] += np.sum(F.diff_phi(K[k][i], s, p, x_ki) * w[:hi])
+            else:
+                j = idx[1]
+                x_kj = x_k[imap[j][0]:imap[j][1]]
+                ti, tj = times[i], times[j]
+                wa, wb = wv(1, i, len(ti)), wv(2, j, len(tj))
+                for m in range(len(ti)):
+                    hi = m if i == j else np.searchsorted(tj, ti[m], side='left')
+                    if hi == 0:
+                        continue
+                    s = ti[m] - tj[:hi]
+                    tt = (T_f - ti[m]) * np.ones(hi)
+                    loc = wa[m] * wb[:hi]
+                    out[off] += np.sum(F.upsilon(KU, KU, tt, s, x_ki, x_kj) * loc)
+                    if i == j:
+                        for p in range(n1):
+                            out[off + 1 + p] += np.sum(F.diff_sim_upsilon(K[k][i], tt, s, p, x_ki) * loc)
+                    else:
+                        for p in range(n1):
+                            out[off + 1 + p] += np.sum(
+                                F.diff_cross_upsilon(KU, KU, tt, s, 1, p, x_ki, x_kj) * loc)
+                        for p in range(n2):
+                            out[off + 1 + n1 + p] += np.sum(
+                                F.diff_cross_upsilon(KU, KU, tt, s, 2, p, x_ki, x_kj) * loc)
+        return out
+
     # split form used by aslsd_b200.distributed: for the test double the "raw
     # accumulators" are the packed per-term sums themselves (additive over shards)
     def exact_raw_len(self, k):

@@ -1,0 +1,78 @@
+"""MTLHExactEstimB200 against the live reference (CPU, oracle-backed engine double): the host
+logic of the marked-model estimator - impact evaluation by the reference's own closures, weight
+roles, term masks, nested result blocks, recombination - and the plug-in into MTLH.fit."""
+import copy
+
+import numpy as np
+import pytest
+
+import ref_shim
+from cases import MTLH_CASES, mtlh_inputs
+from oracle import mtlh_exact as OM
+from oracle_engine import OracleEngine
+
+pytestmark = pytest.mark.reference
+
+
+def _reference_setup(name):
+    import make_golden_mtlh
+    ref_shim.make_importable()
+    from aslsd.stats.events.process_path import ProcessPath
+    model, xs, n_events, T_f = MTLH_CASES[name]
+    mtlh = make_golden_mtlh.build_reference_mtlh(model)
+    times, marks, T_f = mtlh_inputs(name)
+    return model, xs, mtlh, ProcessPath(times, T_f, list_marks=marks)
+
+
+@pytest.mark.parametrize('name', ['mtlh_exp2d', 'mtlh_gauss1d', 'mtlh_exp1d_m2'])
+def test_estimator_state_matches_reference_estimator(name):
+    import aslsd_b200
+    from aslsd.optimize.estimators.mtlh_exact_estimator import MTLHExactEstim
+    model, xs, mtlh, path = _reference_setup(name)
+    for k in range(model['d']):
+        x = np.asarray(xs[k], dtype=float)
+        ref_est = MTLHExactEstim(is_log_lse=True)
+        ref_est.initialize(k, 3, mtlh, path)
+        new_est = aslsd_b200.MTLHExactEstimB200(is_log_lse=True, engine=OracleEngine())
+        new_est.initialize(k, 3, mtlh, path)
+        g_ref = ref_est.lse_k_grad_estimate(x)
+        g_new = new_est.lse_k_grad_estimate(x)
+        a = OM.flatten(ref_est.M_term, ref_est.diff_M_term, ref_est.sum_f, ref_est.sum_diff_f, 'k')
+        b = OM.flatten(new_est.M_term, new_est.diff_M_term, new_est.sum_f, new_est.sum_diff_f, 'k')
+        assert sorted(a) == sorted(b)
+        for key in a:
+            np.testing.assert_allclose(b[key], a[key], rtol=1e-10, atol=1e-12, err_msg=key)
+        np.testing.assert_allclose(g_new, g_ref, rtol=1e-10, atol=1e-12)
+        np.testing.assert_allclose(new_est.logged_lse, ref_est.logged_lse, rtol=1e-10)
+        np.testing.assert_allclose(new_est.lse_k_estimate(x), ref_est.lse_k_estimate(x), rtol=1e-10)
+
+
+def test_plugs_into_reference_mtlh_fit():
+    """A single instance passed to MTLH.fit(estimators=...) is deep-copied per dimension and
+    drives the reference's own solver loop to the same iterates as its MTLHExactEstim."""
+    import aslsd_b200
+    from aslsd.optimize.estimators.estimator import Estimator
+    assert issubclass(aslsd_b200.MTLHExactEstimB200, Estimator)
+    model, xs, mtlh, path = _reference_setup('mtlh_exp2d')
+    x_0 = [np.asarray(x, dtype=float) for x in xs]
+    mu_ref, ker_ref, imp_ref = mtlh.fit(path, x_0=copy.deepcopy(x_0), n_iter=4, exact_grad=True, seed=3)
+    import make_golden_mtlh
+    mtlh2 = make_golden_mtlh.build_reference_mtlh(model)
+    mu_new, ker_new, imp_new = mtlh2.fit(path, x_0=copy.deepcopy(x_0), n_iter=4, seed=3,
+                                         estimators=aslsd_b200.MTLHExactEstimB200(engine=OracleEngine()))
+    flat = lambda mu, ker, imp: np.concatenate(
+        [np.ravel(np.asarray(v, dtype=float)) for v in list(mu) + [c for row in ker for c in row]
+         + [c for row in imp for c in row]])
+    np.testing.assert_allclose(flat(mu_new, ker_new, imp_new), flat(mu_ref, ker_ref, imp_ref), rtol=1e-8)
+
+
+def test_unsupported_baselines_raise():
+    """Baselines other than ConstantBaseline are outside the device's scope: loud refusal."""
+    import types
+    import aslsd_b200
+    model, xs, mtlh, path = _reference_setup('mtlh_exp1d_m2')
+    other = type('CosineBaseline', (), {})()
+    mtlh._baselines_vec = [types.SimpleNamespace(_basis_mus=[other])]
+    est = aslsd_b200.MTLHExactEstimB200(engine=OracleEngine())
+    with pytest.raises(NotImplementedError):
+        est.initialize(0, 3, mtlh, path)
