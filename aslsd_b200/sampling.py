@@ -38,14 +38,28 @@ def sample_double_ix_stratum(i, j, h_inf, h_sup, n_samples, kappa, varpi, n_even
     # distinct lags in order of first occurrence, with their multiplicities
     distinct, first_pos, counts = np.unique(lags, return_index=True, return_counts=True)
     order = np.argsort(first_pos, kind='stable')
-    list_m, list_n = [], []
-    for h, n_h in zip(distinct[order], counts[order]):
-        first = varpi[i][j][h]
-        pop = n_events[i] - first
-        m = first + rng.choice(pop, n_h, replace=bool(n_h > pop))
-        list_m.append(m)
-        list_n.append(kap[m] - h + 1)
-    return {'m': np.concatenate(list_m), 'n': np.concatenate(list_n)}
+    hs, n_hs = distinct[order], counts[order]
+    firsts = np.asarray(varpi[i][j])[hs]
+    pops = n_events[i] - firsts
+    m_all = np.empty(int(n_hs.sum()), dtype=np.int64)
+    offs = np.concatenate([[0], np.cumsum(n_hs)])
+    # A lag drawn once costs the reference one ``rng.choice(pop, 1, replace=False)``, which is a
+    # single bounded draw (Floyd's algorithm with one element, nothing to shuffle:
+    # numpy/random/_generator.pyx).  ``rng.integers(0, pops)`` with an array of bounds issues the
+    # same bounded draws in the same order, so runs of such lags are sampled in one call and the
+    # generator stays bit-identical to the reference's (tests/test_sampling_stream.py); lags
+    # drawn several times take the reference's call one by one.
+    multi = np.flatnonzero(n_hs != 1)
+    start = 0
+    for stop in list(multi) + [len(hs)]:
+        if stop > start:
+            m_all[offs[start:stop]] = firsts[start:stop] + rng.integers(0, pops[start:stop], dtype=np.int64)
+        if stop < len(hs):
+            n_h, pop = int(n_hs[stop]), int(pops[stop])
+            m_all[offs[stop]:offs[stop + 1]] = firsts[stop] + rng.choice(pop, n_h, replace=bool(n_h > pop))
+        start = stop + 1
+    h_all = np.repeat(hs, n_hs)
+    return {'m': m_all, 'n': kap[m_all] - h_all + 1}
 
 
 def sample_double_ix_stratified(i, j, strata, n_samples, kappa, varpi, n_events, rng):
