@@ -47,6 +47,8 @@ SYMBOLS = {
     'aslsd_last_timing': (ctypes.c_int, [ctypes.c_void_p, c_f64_p, c_i64_p]),
     'aslsd_last_moment_timing': (ctypes.c_int, [ctypes.c_void_p, c_f64_p]),
     'aslsd_exact_raw_used': (ctypes.c_int, [ctypes.c_void_p, c_i64_p]),
+    'aslsd_exact_max_lag': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, c_i32_p, ctypes.POINTER(c_f64_p),
+                                           ctypes.c_int, c_f64_p]),
     'aslsd_measure_fp64_peak': (ctypes.c_int, [ctypes.c_void_p, c_f64_p]),
     'aslsd_set_events': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, c_i64_p,
                                         ctypes.POINTER(c_f64_p), ctypes.c_double]),

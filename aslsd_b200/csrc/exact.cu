@@ -188,6 +188,8 @@ static int build_rows(aslsd_ctx* ctx, int n_k, const int* ks, const double* cons
 
 // Work: target ranges, quadrature streams, per-item work units.  Depends on the events.
 static int build_work(aslsd_ctx* ctx, const int64_t* m_lo, const int64_t* m_hi, BatchPlan& B) {
+  if (!ctx->d_times || (int)ctx->n_events.size() != ctx->d)
+    return aslsd_fail(ctx, ASLSD_ERR_ARG, "exact sums: no events set");
   B.items.clear();
   B.qstreams.clear();
   B.qrows.clear();
@@ -655,6 +657,23 @@ extern "C" int aslsd_exact_sums_weighted(aslsd_ctx* ctx, int k, const double* x_
 extern "C" int aslsd_exact_raw_len_batch(aslsd_ctx* ctx, int n_k, int64_t* raw_len) {
   if (!ctx || !ctx->has_model || n_k <= 0) return ASLSD_ERR_ARG;
   if (raw_len) *raw_len = (int64_t)n_k * max_rows(ctx) * ASLSD_MAX_COMP;
+  return ASLSD_OK;
+}
+
+// Largest lag any term of the batch can reach at these parameters: the halo a time-block shard
+// needs before its first target (events further back contribute to none of its sums).  Needs
+// the model only, not the events.
+extern "C" int aslsd_exact_max_lag(aslsd_ctx* ctx, int n_k, const int* ks, const double* const* xs, int flags,
+                                   double* max_lag) {
+  int rc = check_batch_args(ctx, n_k, ks, xs);
+  if (rc) return rc;
+  if (!max_lag) return aslsd_fail(ctx, ASLSD_ERR_ARG, "exact_max_lag: bad arguments");
+  BatchPlan* Bp = nullptr;
+  if ((rc = get_batch(ctx, n_k, ks, xs, flags, nullptr, nullptr, false, &Bp))) return rc;
+  double w = 0.;
+  for (auto& it : Bp->rows)
+    if (is_pair_family(it.family)) w = std::max(w, it.s_hi);
+  *max_lag = w;
   return ASLSD_OK;
 }
 

@@ -267,7 +267,10 @@ int build_plan(aslsd_ctx* ctx, int k, const double* x_k, int flags, const int64_
                const int64_t* m_hi, bool by_term, SumPlan& P) {
   const int d = ctx->d;
   if (!ctx->has_model) return aslsd_fail(ctx, ASLSD_ERR_ARG, "exact sums: no model set");
-  if (!ctx->d_times) return aslsd_fail(ctx, ASLSD_ERR_ARG, "exact sums: no events set");
+  const bool have_events = ctx->d_times != nullptr && (int)ctx->n_events.size() == d;
+  // the work items themselves do not depend on the events: target ranges are patched in by
+  // the caller (build_work); only the by-term plans of the sampled sums read them here
+  if (!have_events && by_term) return aslsd_fail(ctx, ASLSD_ERR_ARG, "sampled sums: no events set");
   if (k < 0 || k >= d) return aslsd_fail(ctx, ASLSD_ERR_ARG, "exact sums: bad k");
   P.k = k;
   P.flags = flags;
@@ -276,7 +279,8 @@ int build_plan(aslsd_ctx* ctx, int k, const double* x_k, int flags, const int64_
   std::vector<int64_t> lo(d), hi(d);
   for (int i = 0; i < d; ++i) {
     lo[i] = m_lo ? std::max<int64_t>(0, m_lo[i]) : 0;
-    hi[i] = m_hi ? std::min<int64_t>(ctx->n_events[i], m_hi[i]) : ctx->n_events[i];
+    const int64_t n_i = have_events ? ctx->n_events[i] : 0;
+    hi[i] = m_hi ? std::min<int64_t>(n_i, m_hi[i]) : n_i;
   }
   int rc = plan_vars(ctx, k, x_k, P);
   if (rc) return rc;

@@ -4,11 +4,15 @@ One process per GPU (torch.distributed, NCCL over NVLink).  The observation
 window [0, T_f] is cut into ``world_size`` contiguous time blocks holding equal
 numbers of target events; rank g evaluates every term for the targets of its
 block only.  Sources are taken from the halo [block start - max lag, block
-end): the event times are replicated on every GPU (80 MB at 10^7 events), so
-the halo is purely logical and never needs an exchange.  All sums are additive
-over targets (mhp_exact_estimator.py:633, :667, :703), hence one allreduce of
-the raw accumulator vector combines the shards; the packed per-term sums are
-then assembled on every rank.
+end).  Two ways to hold the events:
+  * ``ShardedExactSums(engine, list_times, ...)`` after ``engine.set_events(all events)``:
+    replicated events (80 MB at 10^7 events), the halo is purely logical;
+  * ``sharded.set_events(list_times, T_f, ks, xs)``: every rank uploads only its block plus
+    the halo of ``engine.exact_max_lag(ks, xs)`` time units before it (1/world_size of the
+    host -> device traffic); re-upload when the parameters widen the kernels' reach.
+Neither needs an exchange of events.  All sums are additive over targets
+(mhp_exact_estimator.py:633, :667, :703), hence one allreduce of the raw accumulator
+vector combines the shards; the packed per-term sums are then assembled on every rank.
 """
 import numpy as np
 
@@ -44,6 +48,21 @@ def time_block_ranges(list_times, world_size):
             for g in range(world_size)]
 
 
+def block_slices(list_times, block, max_lag):
+    """Events a rank must hold for its target block ``block[i] = (lo, hi)``: per type the
+    events from ``max_lag`` time units before the block's earliest target up to the block's end.
+    Returns (local event arrays, target ranges inside them)."""
+    starts = [np.asarray(t)[b[0]] for t, b in zip(list_times, block) if b[1] > b[0]]
+    local, ranges = [], []
+    for t, (lo, hi) in zip(list_times, block):
+        t = np.asarray(t)
+        first = int(np.searchsorted(t, min(starts) - max_lag, side='left')) if starts else lo
+        first = min(first, lo)
+        local.append(t[first:hi])
+        ranges.append((lo - first, hi - first))
+    return local, ranges
+
+
 class ShardedExactSums:
     """Exact sums of sub-problem k over ``dist`` ranks (one Engine per rank)."""
 
@@ -55,6 +74,18 @@ class ShardedExactSums:
         self.device = device
         self.ranges = time_block_ranges(list_times, world_size)[rank]
         self._raw = {}
+        self.max_lag = None
+
+    def set_events(self, list_times, T_f, ks, xs, slack=1.0):
+        """Upload this rank's time block of ``list_times`` plus the halo its first targets can
+        reach (``slack`` x the largest lag of the sub-problems ``ks`` at ``xs``) and point the
+        target ranges at the block inside the uploaded slice."""
+        block = time_block_ranges(list_times, self.world_size)[self.rank]
+        self.max_lag = slack * self.engine.exact_max_lag(ks, xs)
+        local, ranges = block_slices(list_times, block, self.max_lag)
+        self.engine.set_events(local, T_f)
+        self.ranges = ranges
+        return ranges
 
     def raw_buffer(self, k):
         if k not in self._raw:

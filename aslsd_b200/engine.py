@@ -371,6 +371,14 @@ class Engine:
                           for k, cnt in zip(ks, cnts)]
         return outs
 
+    def exact_max_lag(self, ks, xs, compute_f_sum=True, compute_diff_f_sum=True):
+        """Largest lag any double sum of these sub-problems reaches (halo of a time block)."""
+        xs, k_arr, k_ptr, x_ptrs = self._batch_args(ks, xs)
+        flags = (capi.ASLSD_F if compute_f_sum else 0) | (capi.ASLSD_DIFF if compute_diff_f_sum else 0)
+        w = ctypes.c_double()
+        self._check(self._lib.aslsd_exact_max_lag(self._ctx, len(ks), k_ptr, x_ptrs, flags, ctypes.byref(w)))
+        return w.value
+
     def exact_raw_used(self):
         """Doubles of the raw buffer written by the last raw_device call."""
         n = ctypes.c_int64()

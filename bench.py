@@ -323,12 +323,15 @@ def run_b200(args):
     # end-to-end through the public API with host buffers: upload the events,
     # evaluate every k, read the packed sums back
     e2e_ms = []
-    h2d = 8 * n_events + sum(8 * len(x) for x in xs)
+    h2d = sum(8 * len(x) for x in xs)
     d2h = 0
     for s in range(1 + max(1, args.steps)):      # first pass untimed (buffer growth)
         sync_all()
         t0 = time.perf_counter()
-        engine.set_events(times, T_f)
+        if world > 1 and not args.per_k:
+            sharded.set_events(times, T_f, ks, xs)     # this rank's time block + max-lag halo only
+        else:
+            engine.set_events(times, T_f)
         d2h = 0
         if args.per_k:
             for k in range(d):
@@ -340,6 +343,9 @@ def run_b200(args):
         sync_all()
         if s > 0:
             e2e_ms.append(1e3 * (time.perf_counter() - t0))
+    h2d_events = torch.tensor([8. * float(sum(engine.n_events))], dtype=torch.float64, device=device)
+    if world > 1:
+        dist.all_reduce(h2d_events, op=dist.ReduceOp.SUM)
     e2e_t = torch.tensor([float(np.mean(e2e_ms))], dtype=torch.float64, device=device)
     if world > 1:
         dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
@@ -380,8 +386,9 @@ def run_b200(args):
                                              'what one more iteration of a fit at fixed (beta, delta) costs; '
                                              'not the headline',
                        'call': 'one call per k' if args.per_k else 'one batched call for all k',
-                       'sharding': 'time blocks of target events, events replicated, '
-                                   '1 NCCL allreduce per k' if world > 1 else 'single GPU'},
+                       'sharding': 'time blocks of target events; value: events replicated on every GPU; '
+                                   'e2e: every rank uploads its block + max-lag halo only; 1 NCCL allreduce '
+                                   'of the raw rows per step' if world > 1 else 'single GPU'},
             'roofline': {'bound': 'fp64', 'achieved': achieved, 'peak': fp64_peak, 'unit': 'TFLOP/s',
                          'frac': (achieved / fp64_peak) if achieved else None,
                          'traffic': 241.3e6 if (world == 1 and not args.no_quadrature and not args.per_k) else None,
@@ -408,7 +415,7 @@ def run_b200(args):
                          'executed_flops_per_step_rank0': flops, 'kernel_ms_per_step_rank0': k_ms_sum,
                          'hbm_peak_gbs': peaks.get('hbm_gbs'), 'hbm_peak_kind': peak_kind},
             'e2e': {'value': pair_terms / (float(e2e_t.item()) * 1e-3), 'unit': 'pair-terms/s',
-                    'h2d_bytes_per_step': h2d * world, 'd2h_bytes_per_step': d2h * world,
+                    'h2d_bytes_per_step': int(h2d_events.item()) + h2d * world, 'd2h_bytes_per_step': d2h * world,
                     'ms_per_step': float(e2e_t.item())},
             'gpu_launches': n_launch_step * args.steps,
             'clocks': clocks,

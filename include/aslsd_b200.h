@@ -163,6 +163,10 @@ int aslsd_exact_raw_device(aslsd_ctx* ctx, int k, const double* x_k, int flags,
                            double* raw_device, int64_t* n_pair_terms);
 int aslsd_exact_assemble(aslsd_ctx* ctx, int k, const double* x_k, int flags,
                          const double* raw_host, double* out);
+/* Largest lag any double sum of the batch reaches at these parameters (needs the model, not the
+ * events): the halo of earlier events a time-block shard must hold before its first target. */
+int aslsd_exact_max_lag(aslsd_ctx* ctx, int n_k, const int* ks, const double* const* xs, int flags,
+                        double* max_lag);
 /* Doubles of the raw buffer written by the last raw_device call (a prefix of raw_len): the
  * part to all-reduce and to copy to the host. */
 int aslsd_exact_raw_used(aslsd_ctx* ctx, int64_t* raw_used);

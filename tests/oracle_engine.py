@@ -27,6 +27,24 @@ class OracleEngine:
         self.plain = self.desc.to_plain()
         return self.desc
 
+    def set_events(self, list_times, T_f):
+        self.times = [np.asarray(t, dtype=float) for t in list_times]
+        self.T_f = float(T_f)
+
+    def exact_max_lag(self, ks, xs, compute_f_sum=True, compute_diff_f_sum=True):
+        """Largest window of the oracle's windowed sums (oracle/exact.py phi_window / ups_window)."""
+        w = 0.
+        d = self.plain['d']
+        KU = OE.ups_kernel(self.plain)
+        for k, x in zip(ks, xs):
+            imap = OE.interval_map(self.plain, k)
+            par = [np.asarray(x, dtype=float)[a:b] for a, b in imap]
+            for i in range(d):
+                w = max(w, OE.phi_window(self.plain['kernels'][k][i], par[i]))
+                for j in range(d):
+                    w = max(w, OE.ups_window(KU, KU, par[i], par[j]))
+        return w
+
     def exact_sums_packed(self, k, x_k, compute_f_sum=True, compute_diff_f_sum=True,
                           ranges=None, count_pairs=False):
         self.n_calls += 1

@@ -42,6 +42,11 @@ def _worker(rank, world, port, times, T_f, name, out_dir):
     both = sharded.packed_batch([0, 1], case_x(name))
     np.save(os.path.join(out_dir, 'batch%d.npy' % rank), np.concatenate(both))
     np.save(os.path.join(out_dir, 'ranges%d.npy' % rank), np.array(sharded.ranges))
+    # second mode: every rank holds only its block plus the halo of the largest lag
+    local_ranges = sharded.set_events(times, T_f, [0, 1], case_x(name))
+    sliced = sharded.packed_batch([0, 1], case_x(name))
+    np.save(os.path.join(out_dir, 'sliced%d.npy' % rank), np.concatenate(sliced))
+    np.save(os.path.join(out_dir, 'held%d.npy' % rank), np.array([len(t) for t in engine.times]))
     dist.barrier()
     dist.destroy_process_group()
 
@@ -86,6 +91,11 @@ def test_two_rank_shards_allreduce_to_the_full_sums(tmp_path):
     batch = np.load(os.path.join(tmp_path, 'batch0.npy'))
     want_all = np.concatenate([full.exact_sums_packed(k, case_x(name)[k]) for k in range(2)])
     np.testing.assert_allclose(batch, want_all, rtol=1e-12, atol=1e-13)
+    sliced = np.load(os.path.join(tmp_path, 'sliced1.npy'))
+    np.testing.assert_allclose(sliced, want_all, rtol=1e-12, atol=1e-13)
+    held = [np.load(os.path.join(tmp_path, 'held%d.npy' % r)) for r in range(2)]
+    # rank 1 holds its half plus a halo, not the whole path
+    assert np.all(held[1] < np.array([700, 500])) and np.all(held[0] < np.array([700, 500]))
     r0 = np.load(os.path.join(tmp_path, 'ranges0.npy'))
     r1 = np.load(os.path.join(tmp_path, 'ranges1.npy'))
     assert np.all(r0[:, 1] == r1[:, 0])

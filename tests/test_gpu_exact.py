@@ -96,6 +96,34 @@ def test_shards_add_up_and_match_oracle_blocks(engine):
     np.testing.assert_allclose(acc, full, rtol=1e-12, atol=1e-12)
 
 
+def test_time_block_slices_with_halo_add_up(engine):
+    """Each shard holds only its time block plus the halo of the largest lag
+    (aslsd_exact_max_lag): the shard sums still add up to the full sums."""
+    from aslsd_b200.distributed import block_slices, time_block_ranges
+    name = 'sbf2d3'
+    model = CASES[name][0]
+    rng = np.random.default_rng(15)
+    T_f = 4000.
+    times = _simulate_poisson_cluster(rng, 2, T_f, 1.5)
+    xs = case_x(name)
+    engine.set_events(times, T_f)
+    engine.set_model(model)
+    full = engine.exact_sums_batch([0, 1], xs)
+    max_lag = engine.exact_max_lag([0, 1], xs)
+    assert 0. < max_lag < 40.
+    acc = [np.zeros_like(f) for f in full]
+    held = 0
+    for block in time_block_ranges(times, 3):
+        local, ranges = block_slices(times, block, max_lag)
+        held += sum(len(t) for t in local)
+        engine.set_events(local, T_f)
+        for a, part in zip(acc, engine.exact_sums_batch([0, 1], xs, ranges=ranges)):
+            a += part
+    for a, f in zip(acc, full):
+        np.testing.assert_allclose(a, f, rtol=1e-11, atol=1e-10)
+    assert held < 1.1 * sum(len(t) for t in times)     # blocks + small halos, not 3 copies
+
+
 def test_split_raw_and_assemble_matches_fused(engine):
     import torch
     name = 'gauss2d'
