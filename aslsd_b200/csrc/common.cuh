@@ -145,7 +145,7 @@ struct aslsd_ctx {
   int64_t model_epoch = 0;    // bumped by set_model / set_option
   int64_t events_epoch = 0;   // bumped by set_events
   int64_t last_work[8] = {0};   // see aslsd_last_work_counts
-  int64_t last_n_wu_q = 0;
+  int64_t last_n_wu_q = 0, last_n_bgroups = 0;
   // timing
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;     // around all kernels of a sum call
   cudaEvent_t ev_q0 = nullptr, ev_q1 = nullptr; // around the lag-moment kernel

@@ -50,6 +50,8 @@ struct BatchPlan {
   std::vector<QStreamDev> qstreams;
   std::vector<ItemDev> qrows;                   // grouped by family; wu_first = stream index
   int qfam_first[8], qfam_count[8];
+  std::vector<BoundaryGroupDev> bgroups;        // targets near T_f of the quadrature rows, by family
+  int bfam_first[8], bfam_count[8];
   int64_t n_wu_q = 0, n_q_partials = 0, n_q_weights = 0, n_q_evals = 0;
   int q_jmax = 0;
   size_t q_smem = 0;
@@ -193,6 +195,7 @@ static int build_work(aslsd_ctx* ctx, const int64_t* m_lo, const int64_t* m_hi, 
   B.items.clear();
   B.qstreams.clear();
   B.qrows.clear();
+  B.bgroups.clear();
   B.n_wu = B.n_wu_q = B.n_q_partials = B.n_q_weights = B.n_q_evals = 0;
   B.q_jmax = 0;
   B.q_smem = 0;
@@ -234,6 +237,27 @@ static int build_work(aslsd_ctx* ctx, const int64_t* m_lo, const int64_t* m_hi, 
   for (int f = 0; f < 8; ++f) {
     B.qfam_first[f] = (int)B.qrows.size();
     B.qfam_count[f] = (int)qfam[f].size();
+    B.bfam_first[f] = (int)B.bgroups.size();
+    // rows of one stream are contiguous inside a family: one boundary group per (family, stream)
+    // whose targets reach beyond the interior
+    for (size_t x = 0; x < qfam[f].size();) {
+      size_t y = x;
+      while (y < qfam[f].size() && qfam[f][y].wu_first == qfam[f][x].wu_first) ++y;
+      const QStreamDev& S = B.qstreams[(size_t)qfam[f][x].wu_first];
+      const int64_t m_end = B.hi[S.tgt_dim];
+      if (S.m_hi < m_end) {
+        BoundaryGroupDev G;
+        std::memset(&G, 0, sizeof(G));
+        G.stream = (int32_t)qfam[f][x].wu_first;
+        G.row_first = (int32_t)(B.qrows.size() + x);
+        G.row_count = (int32_t)(y - x);
+        G.m_lo = S.m_hi;
+        G.m_hi = m_end;
+        B.bgroups.push_back(G);
+      }
+      x = y;
+    }
+    B.bfam_count[f] = (int)B.bgroups.size() - B.bfam_first[f];
     B.qrows.insert(B.qrows.end(), qfam[f].begin(), qfam[f].end());
   }
   // ---- per-item kernels: rows outside the quadrature entirely, the others beyond the interior ----
@@ -242,8 +266,7 @@ static int build_work(aslsd_ctx* ctx, const int64_t* m_lo, const int64_t* m_hi, 
     ItemDev it = B.rows[r];
     it.dst_row = (int64_t)r;
     if (fast[r]) {
-      if (boundary_from[r] >= it.m_hi) continue;
-      it.m_lo = boundary_from[r];
+      continue;   // interior: lag quadrature; targets near T_f: lag_boundary_kernel
     } else if (!is_pair_family(it.family) && it.m_hi > it.m_lo && std::isfinite(it.t_int) && it.wa_off < 0) {
       // single-index rows are constant in the interior: n_int x closed form
       const int64_t m_b = interior_end(ctx, it.tgt_dim, it.m_lo, it.m_hi, it.t_int);
@@ -389,6 +412,17 @@ static void launch_quad(aslsd_ctx* ctx, const BatchPlan& B, const QStreamDev* d_
   ctx->last_launches++;
 }
 
+template <int FAMILY>
+static void launch_boundary(aslsd_ctx* ctx, const BatchPlan& B, const QStreamDev* d_streams,
+                            const BoundaryGroupDev* d_groups, const ItemDev* d_qrows, double* raw_device,
+                            unsigned long long* d_cnt) {
+  if (B.bfam_count[FAMILY] == 0) return;
+  lag_boundary_kernel<FAMILY><<<(unsigned)B.bfam_count[FAMILY], LB_NT, 0, ctx->stream>>>(
+      (const DimDev*)ctx->d_dims, d_streams, d_groups + B.bfam_first[FAMILY], d_qrows, ctx->T_f, raw_device,
+      d_cnt + B.bfam_first[FAMILY]);
+  ctx->last_launches++;
+}
+
 // Launch everything; leaves raw[row][comp] in raw_device (zeroed here first).
 static int run_batch(aslsd_ctx* ctx, BatchPlan& B, double* raw_device) {
   CUDA_TRY(ctx, cudaSetDevice(ctx->device));
@@ -409,7 +443,8 @@ static int run_batch(aslsd_ctx* ctx, BatchPlan& B, double* raw_device) {
   if ((rc = ensure_device_buffer(ctx, (void**)&ctx->d_partials, &ctx->partials_cap,
                                  std::max<size_t>(1, (size_t)B.n_wu) * ASLSD_MAX_COMP * sizeof(double)))) return rc;
   if ((rc = ensure_device_buffer(ctx, (void**)&ctx->d_counts, &ctx->counts_cap,
-                                 ((size_t)B.n_wu + n_items + (size_t)B.n_wu_q + 1) * sizeof(unsigned long long))))
+                                 ((size_t)B.n_wu + n_items + (size_t)B.n_wu_q + B.bgroups.size() + 1) *
+                                     sizeof(unsigned long long))))
     return rc;
   if (n_items && !B.device_resident)
     CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_items, B.items.data(), n_items * sizeof(ItemDev),
@@ -418,7 +453,8 @@ static int run_batch(aslsd_ctx* ctx, BatchPlan& B, double* raw_device) {
   const bool quad = !B.qstreams.empty();
   const size_t o_s = 0;
   const size_t o_r = o_s + ((B.qstreams.size() * sizeof(QStreamDev) + 15) & ~(size_t)15);
-  const size_t q_bytes = o_r + B.qrows.size() * sizeof(ItemDev);
+  const size_t o_g = o_r + ((B.qrows.size() * sizeof(ItemDev) + 15) & ~(size_t)15);
+  const size_t q_bytes = o_g + B.bgroups.size() * sizeof(BoundaryGroupDev);
   if (quad) {
     if ((rc = upload_quadrature_tables(ctx))) return rc;
     if ((rc = ensure_device_buffer(ctx, (void**)&ctx->d_q_partials, &ctx->q_partials_cap,
@@ -432,6 +468,7 @@ static int run_batch(aslsd_ctx* ctx, BatchPlan& B, double* raw_device) {
     char* hp = (char*)ctx->h_pinned;
     std::memcpy(hp + o_s, B.qstreams.data(), B.qstreams.size() * sizeof(QStreamDev));
     std::memcpy(hp + o_r, B.qrows.data(), B.qrows.size() * sizeof(ItemDev));
+    std::memcpy(hp + o_g, B.bgroups.data(), B.bgroups.size() * sizeof(BoundaryGroupDev));
     CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_qtab, hp, q_bytes, cudaMemcpyHostToDevice, ctx->stream));
     // the pinned staging block is reused by the caller once the copy has completed
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
@@ -440,6 +477,7 @@ static int run_batch(aslsd_ctx* ctx, BatchPlan& B, double* raw_device) {
   const ItemDev* d_items = (const ItemDev*)ctx->d_items;
   const QStreamDev* d_streams = (const QStreamDev*)((const char*)ctx->d_qtab + o_s);
   const ItemDev* d_qrows = (const ItemDev*)((const char*)ctx->d_qtab + o_r);
+  const BoundaryGroupDev* d_groups = (const BoundaryGroupDev*)((const char*)ctx->d_qtab + o_g);
   CUDA_TRY(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
   CUDA_TRY(ctx, cudaMemsetAsync(raw_device, 0, std::max<size_t>(1, n_rows) * ASLSD_MAX_COMP * sizeof(double),
                                 ctx->stream));
@@ -489,7 +527,13 @@ static int run_batch(aslsd_ctx* ctx, BatchPlan& B, double* raw_device) {
     launch_quad<ITEM_UPS_EXP>(ctx, B, d_streams, d_qrows, raw_device);
     launch_quad<ITEM_PHI_GAUSS>(ctx, B, d_streams, d_qrows, raw_device);
     launch_quad<ITEM_PHI_EXP>(ctx, B, d_streams, d_qrows, raw_device);
+    unsigned long long* d_bcnt = ctx->d_counts + B.n_wu + n_items + B.n_wu_q;
+    launch_boundary<ITEM_UPS_GAUSS>(ctx, B, d_streams, d_groups, d_qrows, raw_device, d_bcnt);
+    launch_boundary<ITEM_UPS_EXP>(ctx, B, d_streams, d_groups, d_qrows, raw_device, d_bcnt);
+    launch_boundary<ITEM_PHI_GAUSS>(ctx, B, d_streams, d_groups, d_qrows, raw_device, d_bcnt);
+    launch_boundary<ITEM_PHI_EXP>(ctx, B, d_streams, d_groups, d_qrows, raw_device, d_bcnt);
   }
+  ctx->last_n_bgroups = (int64_t)B.bgroups.size();
   CUDA_TRY(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
   ctx->timing_pending = true;
   CUDA_TRY(ctx, cudaGetLastError());
@@ -743,7 +787,7 @@ extern "C" int aslsd_last_work_counts(aslsd_ctx* ctx, int64_t* counts, int n) {
   if (!ctx || !counts || n < 8) return ASLSD_ERR_ARG;
   CUDA_TRY(ctx, cudaSetDevice(ctx->device));
   const size_t n_old = (size_t)ctx->last_n_wu + (size_t)ctx->last_n_items;
-  const size_t n_all = n_old + (size_t)ctx->last_n_wu_q;
+  const size_t n_all = n_old + (size_t)ctx->last_n_wu_q + (size_t)ctx->last_n_bgroups;
   std::vector<unsigned long long> h(std::max<size_t>(1, n_all));
   if (n_all) {
     CUDA_TRY(ctx, cudaMemcpyAsync(h.data(), ctx->d_counts, sizeof(unsigned long long) * n_all,
@@ -756,6 +800,8 @@ extern "C" int aslsd_last_work_counts(aslsd_ctx* ctx, int64_t* counts, int n) {
     for (int x = 0; x < ctx->last_fam_count[f]; ++x)
       (pair ? pe : se) += (int64_t)h[(size_t)ctx->last_n_wu + ctx->last_fam_first[f] + x];
   }
+  for (int64_t g = 0; g < ctx->last_n_bgroups; ++g)
+    pe += (int64_t)h[n_old + (size_t)ctx->last_n_wu_q + (size_t)g];
   counts[0] = pe;
   counts[1] = se;
   int64_t pairs = 0;

@@ -557,3 +557,115 @@ lag_quad_kernel(const QStreamDev* __restrict__ streams, const ItemDev* __restric
     raw[it.dst_row * ASLSD_MAX_COMP + threadIdx.x] += v;
   }
 }
+
+// Targets near T_f (T_f - t_m below the stream's t_int): the closed forms depend on (T_f - t_m, s),
+// so these few targets are evaluated pair by pair - but once per stream, not once per row: one CTA
+// = (stream, family) stages the (lag, time-to-end) pairs of the boundary targets in shared memory
+// and every warp walks rows over them.  Each row is owned by one warp of one CTA: plain
+// read-modify-write of its raw components, fixed order.
+#define LB_NT 256
+#define LB_PCAP 2048
+struct BoundaryGroupDev {
+  int32_t stream, row_first, row_count, pad;
+  int64_t m_lo, m_hi;      // boundary targets
+};
+
+template <int FAMILY>
+__global__ void __launch_bounds__(LB_NT)
+lag_boundary_kernel(const DimDev* __restrict__ dims, const QStreamDev* __restrict__ streams,
+                    const BoundaryGroupDev* __restrict__ groups, const ItemDev* __restrict__ rows, double T_f,
+                    double* __restrict__ raw, unsigned long long* __restrict__ counts) {
+  __shared__ double s_s[LB_PCAP];
+  __shared__ double s_tt[LB_PCAP];
+  __shared__ int32_t s_warp[LB_NT / 32];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const BoundaryGroupDev G = groups[blockIdx.x];
+  const QStreamDev S = streams[G.stream];
+  const DimDev Dt = dims[S.tgt_dim], Ds = dims[S.src_dim];
+  const bool same = S.same != 0;
+  unsigned long long n_eval = 0;
+  for (int64_t m0 = G.m_lo; m0 < G.m_hi; m0 += LB_NT) {
+    const int64_t m = m0 + tid;
+    double t_m = 0.;
+    int64_t lo = 0;
+    int32_t cnt = 0;
+    if (m < G.m_hi) {
+      t_m = Dt.t[m];
+      const int64_t hi = same ? m : dim_lower_bound(Ds, t_m);
+      lo = min(dim_lower_bound(Ds, t_m - S.s_max), hi);
+      cnt = (int32_t)(hi - lo);
+    }
+    int32_t incl = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int32_t v = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += v;
+    }
+    __syncthreads();     // previous tile's readers of s_warp / pair buffers are done
+    if (lane == 31) s_warp[warp] = incl;
+    __syncthreads();
+    int32_t pre = incl - cnt, total = 0;
+#pragma unroll
+    for (int w = 0; w < LB_NT / 32; ++w) {
+      const int32_t v = s_warp[w];
+      if (w < warp) pre += v;
+      total += v;
+    }
+    for (int32_t c0 = 0; c0 < total; c0 += LB_PCAP) {
+      const int32_t n_c = min(LB_PCAP, total - c0);
+      const int32_t ra = min(max(c0 - pre, 0), cnt), rb = min(max(c0 + n_c - pre, 0), cnt);
+      for (int32_t r = ra; r < rb; ++r) {
+        s_s[pre - c0 + r] = t_m - Ds.t[lo + r];
+        s_tt[pre - c0 + r] = T_f - t_m;
+      }
+      __syncthreads();
+      for (int row = warp; row < G.row_count; row += LB_NT / 32) {
+        const ItemDev it = rows[G.row_first + row];
+        const int mask = it.mask;
+        UpsGaussConst KG;
+        UpsExpConst KE;
+        PhiConst KP;
+        if (FAMILY == ITEM_UPS_GAUSS) KG.init(it);
+        if (FAMILY == ITEM_UPS_EXP) KE.init(it);
+        if (FAMILY == ITEM_PHI_EXP || FAMILY == ITEM_PHI_GAUSS) KP.init(it);
+        double acc[ASLSD_MAX_COMP];
+#pragma unroll
+        for (int c = 0; c < ASLSD_MAX_COMP; ++c) acc[c] = 0.;
+        for (int32_t p = lane; p < n_c; p += 32) {
+          const double s = s_s[p];
+          if (s < it.s_lo || s > it.s_hi) continue;   // the row's own lag window
+          const double t = s_tt[p];
+          if (FAMILY == ITEM_UPS_GAUSS) eval_ups_gauss<false>(KG, mask, t, s, acc);
+          else if (FAMILY == ITEM_UPS_EXP) eval_ups_exp<false>(KE, mask, t, s, acc);
+          else if (FAMILY == ITEM_PHI_EXP) eval_phi_exp(KP, mask, s, acc);
+          else eval_phi_gauss(KP, mask, s, acc);
+          ++n_eval;
+        }
+#pragma unroll
+        for (int c = 0; c < ASLSD_MAX_COMP; ++c) {
+          double v = acc[c];
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+          acc[c] = v;
+        }
+        if (lane < ASLSD_MAX_COMP) {
+          double v = 0.;
+#pragma unroll
+          for (int c = 0; c < ASLSD_MAX_COMP; ++c) v = (lane == c) ? acc[c] : v;
+          raw[it.dst_row * ASLSD_MAX_COMP + lane] += v;
+        }
+      }
+      __syncthreads();
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) n_eval += __shfl_xor_sync(0xffffffffu, n_eval, o);
+  __shared__ unsigned long long s_cnt[LB_NT / 32];
+  if (lane == 0) s_cnt[warp] = n_eval;
+  __syncthreads();
+  if (tid == 0) {
+    unsigned long long c = 0;
+    for (int w = 0; w < LB_NT / 32; ++w) c += s_cnt[w];
+    counts[blockIdx.x] = c;
+  }
+}
