@@ -33,6 +33,12 @@ class Basis(ctypes.Structure):
                 ('fixed', ctypes.c_double * 3)]
 
 
+class Pcg64(ctypes.Structure):
+    _fields_ = [('state_hi', ctypes.c_uint64), ('state_lo', ctypes.c_uint64),
+                ('inc_hi', ctypes.c_uint64), ('inc_lo', ctypes.c_uint64),
+                ('has_uint32', ctypes.c_int32), ('uinteger', ctypes.c_uint32)]
+
+
 class SampleTerm(ctypes.Structure):
     _fields_ = [('kind', ctypes.c_int32), ('i', ctypes.c_int32), ('j', ctypes.c_int32),
                 ('n_strata', ctypes.c_int32)]
@@ -61,6 +67,10 @@ SYMBOLS = {
     'aslsd_exact_out_len': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, c_i64_p, c_i64_p]),
     'aslsd_exact_sums': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, c_f64_p, ctypes.c_int,
                                         c_i64_p, c_i64_p, c_f64_p, c_i64_p]),
+    'aslsd_rng_choice': (ctypes.c_int, [ctypes.POINTER(Pcg64), ctypes.c_int64, ctypes.c_int64,
+                                        ctypes.c_int, c_i64_p]),
+    'aslsd_sample_double_ix': (ctypes.c_int, [ctypes.POINTER(Pcg64), ctypes.c_int64, c_i64_p, c_i64_p,
+                                              c_i64_p, c_i64_p, c_i64_p, ctypes.c_int64, c_i64_p, c_i64_p]),
     'aslsd_set_weights': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, c_i32_p,
                                          ctypes.POINTER(c_f64_p)]),
     'aslsd_exact_sums_weighted': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, c_f64_p, ctypes.c_int,

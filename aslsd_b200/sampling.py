@@ -13,7 +13,41 @@ same ``rng.choice`` calls, in the same order and with the same arguments, as
 in first-occurrence order).  Sampling stays on the host by design (BASELINE.json
 north_star); the device consumes the flat (m, n) arrays these return.
 """
+import ctypes
+
 import numpy as np
+
+from aslsd_b200 import capi
+
+_MASK64 = (1 << 64) - 1
+
+
+def _native_state(rng):
+    """(library, aslsd_pcg64) for a numpy Generator on PCG64, else None.  The native sampler
+    (csrc/sampler.cu) restates that generator bit for bit; other bit generators keep the numpy
+    path below, which issues the reference's calls one by one."""
+    try:
+        state = rng.bit_generator.state
+    except AttributeError:
+        return None
+    if state.get('bit_generator') != 'PCG64':
+        return None
+    try:
+        lib = capi.load_library()
+    except (RuntimeError, OSError):
+        return None
+    inner = state['state']
+    g = capi.Pcg64(inner['state'] >> 64, inner['state'] & _MASK64, inner['inc'] >> 64,
+                   inner['inc'] & _MASK64, int(state['has_uint32']), int(state['uinteger']))
+    return lib, g
+
+
+def _store_state(rng, g):
+    rng.bit_generator.state = {
+        'bit_generator': 'PCG64',
+        'state': {'state': (int(g.state_hi) << 64) | int(g.state_lo),
+                  'inc': (int(g.inc_hi) << 64) | int(g.inc_lo)},
+        'has_uint32': int(g.has_uint32), 'uinteger': int(g.uinteger)}
 
 
 def sample_single_ix_stratified(strata, n_samples, rng):
@@ -63,5 +97,26 @@ def sample_double_ix_stratum(i, j, h_inf, h_sup, n_samples, kappa, varpi, n_even
 
 
 def sample_double_ix_stratified(i, j, strata, n_samples, kappa, varpi, n_events, rng):
-    return [sample_double_ix_stratum(i, j, h_inf, h_sup, n, kappa, varpi, n_events, rng)
-            for (h_inf, h_sup), n in zip(strata, n_samples)]
+    """All strata of a term.  With a PCG64 generator one native call draws them all
+    (aslsd_sample_double_ix: the same draws as the loop below, tests/test_sampling_stream.py)."""
+    native = _native_state(rng) if len(strata) else None
+    if native is None:
+        return [sample_double_ix_stratum(i, j, h_inf, h_sup, n, kappa, varpi, n_events, rng)
+                for (h_inf, h_sup), n in zip(strata, n_samples)]
+    lib, g = native
+    h_inf = np.ascontiguousarray([s[0] for s in strata], dtype=np.int64)
+    h_sup = np.ascontiguousarray([s[1] for s in strata], dtype=np.int64)
+    n_s = np.ascontiguousarray(n_samples, dtype=np.int64)
+    var = np.ascontiguousarray(varpi[i][j], dtype=np.int64)
+    kap = np.ascontiguousarray(kappa[j][i], dtype=np.int64)
+    total = int(n_s.sum())
+    m = np.empty(total, dtype=np.int64)
+    n = np.empty(total, dtype=np.int64)
+    rc = lib.aslsd_sample_double_ix(ctypes.byref(g), len(strata), capi.ptr_i64(h_inf), capi.ptr_i64(h_sup),
+                                    capi.ptr_i64(n_s), capi.ptr_i64(var), capi.ptr_i64(kap),
+                                    int(n_events[i]), capi.ptr_i64(m), capi.ptr_i64(n))
+    if rc != 0:
+        raise ValueError('Cannot take a larger sample than population when replace is False')
+    _store_state(rng, g)
+    offs = np.concatenate([[0], np.cumsum(n_s)])
+    return [{'m': m[offs[q]:offs[q + 1]], 'n': n[offs[q]:offs[q + 1]]} for q in range(len(strata))]

@@ -129,6 +129,27 @@ int aslsd_exact_sums(aslsd_ctx* ctx, int k, const double* x_k, int flags,
                      const int64_t* m_lo, const int64_t* m_hi, double* out,
                      int64_t* n_pair_terms);
 
+/* ---- host-side index sampling: replaces utilities/useful_statistics.py:38-127 ---------
+ * sample_single_ix_stratified / sample_double_ix_stratum / sample_double_ix_stratified draw with
+ * numpy's Generator(PCG64); these entry points restate that generator and Generator.choice bit
+ * for bit, start from the caller's generator state and return the advanced state, so one native
+ * call replaces the thousands of rng.choice calls of a term without changing a single draw.
+ * State layout: numpy's rng.bit_generator.state ('state', 'inc' as two 64-bit halves each,
+ * 'has_uint32', 'uinteger').  Host code only; no device is touched. */
+typedef struct {
+  uint64_t state_hi, state_lo, inc_hi, inc_lo;
+  int32_t has_uint32;
+  uint32_t uinteger;
+} aslsd_pcg64;
+/* Generator.choice(pop, size, replace=replace) (no p, shuffle=True) into out[size]. */
+int aslsd_rng_choice(aslsd_pcg64* gen, int64_t pop, int64_t size, int replace, int64_t* out);
+/* All strata of one double-sum term (targets of type i, sources of type j): stratum s covers
+ * the index lags [h_inf[s], h_sup[s]] and gets n_samples[s] pairs, written one stratum after
+ * the other to m_out / n_out.  varpi_ij = varpi[i][j], kappa_ji = kappa[j][i]. */
+int aslsd_sample_double_ix(aslsd_pcg64* gen, int64_t n_strata, const int64_t* h_inf,
+                           const int64_t* h_sup, const int64_t* n_samples, const int64_t* varpi_ij,
+                           const int64_t* kappa_ji, int64_t n_events_i, int64_t* m_out, int64_t* n_out);
+
 /* ---- marked models: replaces the pair sums of MTLHExactEstim.compute_objective -------
  * optimize/estimators/mtlh_exact_estimator.py:685-971 for constant baselines.  The impact
  * functions stay the reference's Python (functionals/impact_functions/impact_function.py:

@@ -44,3 +44,53 @@ def test_vectorised_sampler_keeps_the_reference_stream():
             np.testing.assert_array_equal(got['m'], want['m'])
             np.testing.assert_array_equal(got['n'], want['n'])
             assert str(a.bit_generator.state) == str(b.bit_generator.state)
+
+
+def test_native_choice_is_numpy_choice():
+    """aslsd_rng_choice against Generator.choice: Floyd's algorithm, the tail shuffle for large
+    samples, with and without replacement, odd generator phases (32-bit output buffer)."""
+    import ctypes
+    from aslsd_b200 import capi
+    lib = capi.load_library()
+    cases = [(10, 3), (1, 1), (5, 5), (1000, 1), (1000, 37), (9999, 500), (10001, 150), (10001, 201),
+             (10001, 300), (50000, 999), (50000, 1001), (50000, 20000), (200000, 1), (123457, 12),
+             (70000, 70000), (3, 0)]
+    for seed in (1, 2):
+        for pop, n in cases:
+            for replace in (False, True):
+                if replace and pop == 0:
+                    continue
+                a, b = np.random.default_rng(seed), np.random.default_rng(seed)
+                if seed == 2:
+                    a.integers(0, 7), b.integers(0, 7)      # leave half of a 64-bit draw buffered
+                want = a.choice(pop, n, replace=replace)
+                lib_g = sampling._native_state(b)
+                assert lib_g is not None
+                g = lib_g[1]
+                out = np.empty(n, dtype=np.int64)
+                rc = lib.aslsd_rng_choice(ctypes.byref(g), pop, n, int(replace), capi.ptr_i64(out))
+                assert rc == 0
+                sampling._store_state(b, g)
+                np.testing.assert_array_equal(out, want, err_msg='pop %d n %d replace %s' % (pop, n, replace))
+                assert str(a.bit_generator.state) == str(b.bit_generator.state)
+
+
+def test_native_term_sampler_keeps_the_reference_stream():
+    from oracle import time_ordering as OT
+    rng0 = np.random.default_rng(11)
+    T_f = 500.
+    times = [np.sort(rng0.uniform(0, T_f, size=n)) for n in (20000, 12000)]
+    kappa, varpi = OT.kappa_varpi_closed_form(times, T_f)
+    n_events = np.array([len(t) for t in times])
+    for (i, j) in ((0, 0), (0, 1), (1, 0), (1, 1)):
+        h_max = int(kappa[j][i][n_events[i] - 1]) + 1
+        strata = [(1, 1), (2, 2), (3, 3), (4, 10), (11, 60), (61, 400), (401, h_max)]
+        n_samples = [300, 20, 12000 if i == 0 else 7000, 150, 400, 900, 2500]
+        a, b = np.random.default_rng(5), np.random.default_rng(5)
+        got = sampling.sample_double_ix_stratified(i, j, strata, n_samples, kappa, varpi, n_events, a)
+        want = [_reference_stratum(i, j, lo, hi, n, kappa, varpi, n_events, b)
+                for (lo, hi), n in zip(strata, n_samples)]
+        for g_s, w_s in zip(got, want):
+            np.testing.assert_array_equal(g_s['m'], w_s['m'])
+            np.testing.assert_array_equal(g_s['n'], w_s['n'])
+        assert str(a.bit_generator.state) == str(b.bit_generator.state)
