@@ -10,11 +10,11 @@ from aslsd_b200.model import (MHP, KernelModel, ExponentialKernel,  # noqa: F401
                               GaussianKernel, describe_model)
 
 from aslsd_b200.estimators import MHPExactEstimB200, MHPStratEstimB200  # noqa: F401
-from aslsd_b200.mtlh import MTLH, MTLHExactEstimB200  # noqa: F401
+from aslsd_b200.mtlh import MTLH, MTLHExactEstimB200, MTLHStratEstimB200  # noqa: F401
 from aslsd_b200.stratifications import (GeneralStratification,  # noqa: F401
                                         DoubleIxStratification)
 from aslsd_b200.solvers import ADAM  # noqa: F401
 
-__all__ = ['MHPExactEstimB200', 'MHPStratEstimB200', 'MTLH', 'MTLHExactEstimB200', 'GeneralStratification',
+__all__ = ['MHPExactEstimB200', 'MHPStratEstimB200', 'MTLH', 'MTLHExactEstimB200', 'MTLHStratEstimB200', 'GeneralStratification',
            'DoubleIxStratification', 'ADAM', 'Engine', 'EngineError', 'ProcessPath', 'get_kappa_varpi', 'get_lag_sizes',
            'MHP', 'KernelModel', 'ExponentialKernel', 'GaussianKernel', 'describe_model']

@@ -100,6 +100,10 @@ SYMBOLS = {
                                           ctypes.c_int, ctypes.POINTER(SampleTerm), c_i64_p,
                                           c_i64_p, c_i64_p, c_f64_p, c_f64_p, c_f64_p, c_f64_p,
                                           c_f64_p, c_f64_p]),
+    'aslsd_sampled_sums_weighted': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, c_f64_p, ctypes.c_int,
+                                                   ctypes.c_int, ctypes.POINTER(SampleTerm), c_i64_p,
+                                                   c_i64_p, c_i64_p, c_f64_p, c_f64_p, c_i32_p, c_f64_p,
+                                                   c_f64_p, c_f64_p, c_f64_p]),
     'aslsd_update_allocation': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, c_f64_p, c_f64_p,
                                                c_f64_p, c_f64_p]),
 }

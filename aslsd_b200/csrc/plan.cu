@@ -298,7 +298,7 @@ int build_plan(aslsd_ctx* ctx, int k, const double* x_k, int flags, const int64_
   // weights / activity of a term: role 0 phi sources, 1 upsilon targets, 2 upsilon sources,
   // 3 psi targets, 4 upsilonzero targets (aslsd_exact_sums_weighted)
   auto weight_of = [&](int role, int dim) -> int64_t {
-    if (!ctx->roles || by_term) return -1;
+    if (!ctx->roles) return -1;
     const int v = ctx->roles[role * d + dim];
     return v < 0 ? -1 : ctx->weight_off[v];
   };

@@ -132,13 +132,16 @@ sampled_kernel(const DimDev* __restrict__ dims, const ItemDev* __restrict__ item
                const SampleEntry* __restrict__ entries, const SampleTermDev* __restrict__ terms,
                const StratumDev* __restrict__ strata, const int64_t* __restrict__ ix_m,
                const int64_t* __restrict__ ix_n, double T_f, int grad_alloc, double* __restrict__ scratch,
-               double* __restrict__ sum_out) {
+               double* __restrict__ sum_out, const double* __restrict__ weights) {
   __shared__ double s_acc[(SAMP_NT / 32) * SAMP_MAX_OUT];
   const StratumDev S = strata[blockIdx.x];
   const SampleTermDev T = terms[S.term];
   const DimDev Dt = dims[T.tgt_dim], Ds = dims[T.src_dim];
   const int tid = threadIdx.x;
   const int n_out = T.n_out;
+  // per-event weights of a marked model (all items of a term share them)
+  const int64_t wa_off = T.item_count > 0 ? items[T.item_first].wa_off : -1;
+  const int64_t wb_off = T.item_count > 0 ? items[T.item_first].wb_off : -1;
   double acc[SAMP_MAX_OUT], val[SAMP_MAX_OUT];
   for (int c = 0; c < n_out; ++c) acc[c] = 0.;
   for (int64_t x = S.begin + tid; x < S.end; x += SAMP_NT) {
@@ -173,6 +176,13 @@ sampled_kernel(const DimDev* __restrict__ dims, const ItemDev* __restrict__ item
         const SampleEntry E = entries[e];
         val[E.c] = __dadd_rn(val[E.c], __dmul_rn(E.outer, __dmul_rn(E.coef, raw[E.comp])));
       }
+    }
+    if (wa_off >= 0 || wb_off >= 0) {
+      // f = kernel functional x impact functional, impact product first
+      // (mtlh_stratified_estimator.py:1530-1533, :686 np.prod over the two functions)
+      double w = wa_off >= 0 ? weights[wa_off + m] : 1.;
+      if (wb_off >= 0) w = __dmul_rn(w, weights[wb_off + ix_n[x]]);
+      for (int c = 0; c < n_out; ++c) val[c] = __dmul_rn(val[c], w);
     }
     double stat;
     if (grad_alloc) {
@@ -403,7 +413,7 @@ extern "C" int aslsd_sampled_sums(aslsd_ctx* ctx, int k, const double* x_k, int 
         (const int32_t*)(dp + o_entoff), (const SampleEntry*)(dp + o_ent), (const SampleTermDev*)(dp + o_terms),
         (const StratumDev*)(dp + o_strata), (const int64_t*)(dp + o_m),
         need_n ? (const int64_t*)(dp + o_n) : nullptr, ctx->T_f, (flags & ASLSD_GRAD_ALLOC) ? 1 : 0,
-        (double*)(dp + o_scratch), d_res + r_sum / sizeof(double));
+        (double*)(dp + o_scratch), d_res + r_sum / sizeof(double), ctx->d_weights);
     ctx->last_launches++;
     stat_kernel<<<(unsigned)((n_strata + 63) / 64), 64, 0, ctx->stream>>>(
         (const StratumDev*)(dp + o_strata), (int)n_strata, (const double*)(dp + o_scratch),
@@ -430,6 +440,29 @@ extern "C" int aslsd_sampled_sums(aslsd_ctx* ctx, int k, const double* x_k, int 
       rel_alloc[s] = (sdev[s].alloc_group >= 0) ? ra[s] : (default_alloc ? default_alloc[s] : 0.);
   }
   return ASLSD_OK;
+}
+
+// Marked models: the sampled sums with per-event weights (roles as in
+// aslsd_exact_sums_weighted); replaces the products with the impact functional in
+// MTLHStratEstim.estimate_sum_*dom (optimize/estimators/mtlh_stratified_estimator.py:615-1025).
+extern "C" int aslsd_sampled_sums_weighted(aslsd_ctx* ctx, int k, const double* x_k, int flags, int n_terms,
+                                           const aslsd_sample_term* terms, const int64_t* stratum_offsets,
+                                           const int64_t* ix_m, const int64_t* ix_n, const double* strata_sizes,
+                                           const double* default_alloc, const int32_t* roles, double* sum_out,
+                                           double* stat_mean, double* stat_std, double* rel_alloc) {
+  if (!ctx || !roles) return aslsd_fail(ctx, ASLSD_ERR_ARG, "sampled_sums_weighted: bad arguments");
+  const int d = ctx->d;
+  for (int r = 0; r < 5; ++r)
+    for (int i = 0; i < d; ++i) {
+      const int v = roles[r * d + i];
+      if (v >= 0 && (v >= (int)ctx->weight_off.size() || ctx->weight_dim[v] != i))
+        return aslsd_fail(ctx, ASLSD_ERR_ARG, "sampled_sums_weighted: weight vector of another event type");
+    }
+  ctx->roles = roles;
+  const int rc = aslsd_sampled_sums(ctx, k, x_k, flags, n_terms, terms, stratum_offsets, ix_m, ix_n, strata_sizes,
+                                    default_alloc, sum_out, stat_mean, stat_std, rel_alloc);
+  ctx->roles = nullptr;
+  return rc;
 }
 
 // Stand-alone form of the allocation update for callers that keep their own

@@ -273,7 +273,7 @@ class Engine:
         return n.value
 
     def sampled_sums(self, k, x_k, terms, stratum_offsets, ix_m, ix_n=None, strata_sizes=None,
-                     default_alloc=None, compute_diff_f_sum=True, grad_alloc=False):
+                     default_alloc=None, compute_diff_f_sum=True, grad_alloc=False, roles=None):
         """One launch for every stratum of every term of a compute_objective call
         (mhp_stratified_estimator.py:1333-1386).
 
@@ -310,13 +310,24 @@ class Engine:
         rel = np.zeros(n_strata, dtype=np.float64) if with_alloc else None
         flags = capi.ASLSD_F | (capi.ASLSD_DIFF if compute_diff_f_sum else 0) | \
             (capi.ASLSD_GRAD_ALLOC if grad_alloc else 0)
-        self._check(self._lib.aslsd_sampled_sums(
-            self._ctx, int(k), capi.ptr_f64(x), flags, n_terms, arr, capi.ptr_i64(offs),
-            capi.ptr_i64(m), capi.ptr_i64(n) if n is not None else None,
-            capi.ptr_f64(sizes) if with_alloc else None,
-            capi.ptr_f64(dflt) if with_alloc else None,
-            capi.ptr_f64(sums), capi.ptr_f64(stat_mean), capi.ptr_f64(stat_std),
-            capi.ptr_f64(rel) if with_alloc else None))
+        if roles is None:
+            self._check(self._lib.aslsd_sampled_sums(
+                self._ctx, int(k), capi.ptr_f64(x), flags, n_terms, arr, capi.ptr_i64(offs),
+                capi.ptr_i64(m), capi.ptr_i64(n) if n is not None else None,
+                capi.ptr_f64(sizes) if with_alloc else None,
+                capi.ptr_f64(dflt) if with_alloc else None,
+                capi.ptr_f64(sums), capi.ptr_f64(stat_mean), capi.ptr_f64(stat_std),
+                capi.ptr_f64(rel) if with_alloc else None))
+        else:
+            # marked models: per-event weights by role (see exact_sums_weighted)
+            roles = np.ascontiguousarray(roles, dtype=np.int32).reshape(5 * self.d)
+            self._check(self._lib.aslsd_sampled_sums_weighted(
+                self._ctx, int(k), capi.ptr_f64(x), flags, n_terms, arr, capi.ptr_i64(offs),
+                capi.ptr_i64(m), capi.ptr_i64(n) if n is not None else None,
+                capi.ptr_f64(sizes) if with_alloc else None,
+                capi.ptr_f64(dflt) if with_alloc else None, roles.ctypes.data_as(capi.c_i32_p),
+                capi.ptr_f64(sums), capi.ptr_f64(stat_mean), capi.ptr_f64(stat_std),
+                capi.ptr_f64(rel) if with_alloc else None))
         return sums, np.asarray(out_offsets, dtype=np.int64), stat_mean, stat_std, rel
 
     def update_allocation(self, strata_sizes, stat_std, default_alloc):

@@ -1,4 +1,4 @@
-"""Marked, time-dependent-baseline linear Hawkes models (MTLH) on the B200: exact LSE sums.
+"""Marked, time-dependent-baseline linear Hawkes models (MTLH) on the B200: exact and stratified LSE sums.
 
 ``MTLHExactEstimB200`` exposes the interface ``MTLH.fit(..., estimators=...)`` drives
 (models/hawkes/linear/mtlh.py:2368-2397) and leaves behind the state of the reference's
@@ -19,8 +19,8 @@ Division of labour (BASELINE.json north_star: the functionals stay the reference
     impact parameters (:847-853, :907-918, :963-971) are the same value sums with one weight
     vector replaced by the derivative of the impact;
   * baselines: constant only (K = mu psi, M = mu^2: basis_baseline_constant.py:30-65); other
-    baselines raise NotImplementedError, as do the sampled (stratified) estimators for marked
-    models.
+    baselines raise NotImplementedError.
+``MTLHStratEstimB200`` (below) is the stratified counterpart (MTLHStratEstim).
 
 ``MTLH`` below is the plain-data mirror of the reference model's parameter book-keeping
 (mtlh.py:336-635, :983-1077, :1971-1996) used where the reference package is absent.
@@ -389,6 +389,446 @@ class MTLHExactEstimB200(_B200Estimator):
                             verbose=False):
         self.compute_objective(x_k, compute_f_sum=self.is_log_lse, compute_diff_f_sum=True,
                                verbose=verbose)
+        grad = self.recombine_grad_lse_k()
+        self.grad_lse_k = grad
+        if self.is_log_lse:
+            self.lse_k = self.recombine_lse_k()
+            self.logged_lse[self.t] = self.lse_k
+        return grad
+
+
+class MTLHStratEstimB200(MTLHExactEstimB200):
+    """Stratified (ASLSD) estimates of LSE_k and its gradient for a marked model
+    (MTLHStratEstim, optimize/estimators/mtlh_stratified_estimator.py).
+
+    Same division of labour as the exact estimator: index sampling (the reference's RNG call
+    sequence, ``aslsd_b200.sampling``), impact values per event and the baseline term on the
+    host; every sampled kernel functional, its product with the impact functional, the
+    per-stratum sums, the allocation statistic (np.std of f per adaptive stratum, :719-724) and
+    the allocation update on the device (``aslsd_sampled_sums_weighted``).  The derivative
+    blocks with respect to the impact parameters are value-only launches on the same samples
+    with one weight vector replaced by the derivative of the impact.
+
+    Scope: what runs in the reference - ``grad_alloc=False`` (the ``fit`` default,
+    mtlh.py:2428-2429; ``True`` fails upstream with an object-dtype cast, :720) and one
+    adaptive iteration per call (``n_adaptive_iters == 1``, the stratifications' default; the
+    multi-iteration branch indexes an integer, :770).
+    """
+
+    KIND = {'K': 0, 'upsilonzero': 1, 'phi': 2, 'upsilon': 3}
+
+    # ---- stratifications (:76-169) -----------------------------------------------------------
+    def initialize(self, k, n_iter, model, data, n_exact_single=None,
+                   n_samples_adaptive_single=None, nonadaptive_sample_size_single=None,
+                   single_strfs=None, n_samples_adaptive_double=None,
+                   nonadaptive_sample_size_double=None, double_strfs=None):
+        from aslsd_b200.stratifications import DoubleIxStratification, GeneralStratification
+        self.k = k
+        self.n_iter = n_iter
+        _check_constant_baselines(model)
+        self.initialize_model_data(model, data)
+        if self.list_marks is None:
+            raise ValueError('a marked model needs ProcessPath.list_marks')
+        d = self.d
+        single = {}
+        for key, val in (('n_exact', n_exact_single), ('n_samples_adaptive', n_samples_adaptive_single),
+                         ('nonadaptive_sample_size', nonadaptive_sample_size_single)):
+            if val is not None:
+                single[key] = val
+        double = {}
+        for key, val in (('n_samples_adaptive', n_samples_adaptive_double),
+                         ('nonadaptive_sample_size', nonadaptive_sample_size_double)):
+            if val is not None:
+                double[key] = val
+        single_strfs = single_strfs or {}
+        double_strfs = double_strfs or {}
+        self.stratif = {}
+        self.stratif['mu'] = single_strfs.get('mu_stratification') or \
+            GeneralStratification(n=self.n_events[k], **single)
+        for key, prefix in (('K_stratification', 'K_'), ('upsilonzero_stratification', 'upsilonzero_')):
+            given = single_strfs.get(key, [None] * d)
+            for i in range(d):
+                self.stratif[prefix + str(i)] = given[i] or GeneralStratification(n=self.n_events[i],
+                                                                                  **single)
+        given = double_strfs.get('upsilon_stratification', [[None] * d for _ in range(d)])
+        for i, j in itertools.product(range(d), range(d)):
+            strf = given[i][j]
+            if strf is None:
+                strf = DoubleIxStratification(h_max=self.kappa[j][i][self.n_events[i] - 1] + 1, **double)
+                strf.get_stratification_size(self.lag_sizes, i, j)
+            self.stratif['upsilon_%d_%d' % (i, j)] = strf
+        given = double_strfs.get('phi_stratification', [None] * d)
+        for i in range(d):
+            strf = given[i]
+            if strf is None:
+                strf = DoubleIxStratification(h_max=self.kappa[i][k][self.n_events[k] - 1] + 1, **double)
+                strf.get_stratification_size(self.lag_sizes, k, i)
+            self.stratif['phi_%d' % i] = strf
+        for name, strf in self.stratif.items():
+            if getattr(strf, 'n_adaptive_iters', 1) != 1:
+                raise NotImplementedError('stratification %s: several adaptive iterations per call '
+                                          'are not served (they fail upstream too)' % name)
+        self.list_log_names = self.get_list_log_names()
+        self.make_param_indexing()
+        self.initialize_logs()
+        if self.is_log_ixs:
+            self.logged_ixs = {name: {'adaptive': [None] * n_iter, 'nonadaptive': [None] * n_iter}
+                               for name in self.list_log_names}
+        if self.is_log_allocs:
+            self.logged_allocs = {name: [None] * n_iter for name in self.list_log_names}
+
+    def term_list(self):
+        """(log_name, family, i, j) in the order compute_objective evaluates - and draws
+        samples for - the terms (:1648-1700)."""
+        d = self.d
+        terms = [('mu', 'mu', self.k, self.k)]
+        for i in range(d):
+            terms += [('K_%d' % i, 'K', i, i), ('upsilonzero_%d' % i, 'upsilonzero', i, i),
+                      ('phi_%d' % i, 'phi', i, i), ('upsilon_%d_%d' % (i, i), 'upsilon', i, i)]
+        for i, j in itertools.product(range(d), range(d)):
+            if i != j:
+                terms.append(('upsilon_%d_%d' % (i, j), 'upsilon', i, j))
+        return terms
+
+    def clear_estimates(self):
+        super().clear_estimates()
+        null = self.make_null_sumarray
+        for attr in ('vecsum_f_adaptive', 'sum_f_adaptive', 'vecsum_f_nonadaptive', 'sum_f_nonadaptive',
+                     'sum_f_exact', 'vecsum_diff_f_adaptive', 'sum_diff_f_adaptive',
+                     'vecsum_diff_f_nonadaptive', 'sum_diff_f_nonadaptive', 'sum_diff_f_exact'):
+            setattr(self, attr, {})
+        for name in self.list_log_names:
+            strf = self.stratif[name]
+            args = (self.n_f[name], self.list_n_param[name])
+            kw = dict(vec_n_func=self.vec_n_func[name])
+            self.vecsum_f_adaptive[name] = np.zeros(strf.n_adaptive_strata)
+            self.vecsum_f_nonadaptive[name] = np.zeros(strf.n_nonadaptive_strata)
+            self.sum_f_adaptive[name] = self.sum_f_nonadaptive[name] = self.sum_f_exact[name] = 0.
+            self.vecsum_diff_f_adaptive[name] = null(*args, n_strata=strf.n_adaptive_strata, **kw)
+            self.vecsum_diff_f_nonadaptive[name] = null(*args, n_strata=strf.n_nonadaptive_strata, **kw)
+            self.sum_diff_f_adaptive[name] = null(*args, **kw)
+            self.sum_diff_f_nonadaptive[name] = null(*args, **kw)
+            self.sum_diff_f_exact[name] = null(*args, **kw)
+
+    def _draw(self, family, i, j, strata, n_samples, rng):
+        from aslsd_b200 import sampling
+        if family in ('mu', 'K', 'upsilonzero'):
+            raw = sampling.sample_single_ix_stratified(strata, n_samples, rng)
+            return raw, [(np.asarray(ix), None) for ix in raw]
+        tgt, src = (self.k, i) if family == 'phi' else (i, j)
+        raw = sampling.sample_double_ix_stratified(tgt, src, strata, n_samples, self.kappa, self.varpi,
+                                                   self.n_events, rng)
+        return raw, [(np.asarray(s['m']), np.asarray(s['n'])) for s in raw]
+
+    # ---- the estimates -------------------------------------------------------------------------
+    def compute_objective(self, x_k, compute_f_sum=False, compute_diff_f_sum=True, grad_alloc=True,
+                          rng=None, seed=None, count_iter=True):
+        if grad_alloc:
+            raise NotImplementedError('grad_alloc=True fails in the reference for marked models '
+                                      '(mtlh_stratified_estimator.py:720); use grad_alloc=False')
+        self.clear_estimates()
+        if rng is None:
+            rng = np.random.default_rng(seed)
+        d, k = self.d, self.k
+        x = np.asarray(x_k, dtype=np.float64)
+        x_mu, x_ker, x_imp = self.xk2matrix_params(k, x)
+        x_mu = np.asarray(x_mu, dtype=float)
+        n_imp = [len(x_imp[i]) for i in range(d)]
+        t_iter = self.t
+        if compute_f_sum:
+            self.M_term = float(self.M[k](self.T_f, x_mu))
+        if compute_diff_f_sum:
+            for r in range(len(x_mu)):
+                self.diff_M_term[r] = float(self.diff_M[k](self.T_f, r, x_mu))
+        # ---- 1. draw every sample, term after term (host RNG, reference order) ----------------
+        plans = []
+        for name, family, i, j in self.term_list():
+            strf = self.stratif[name]
+            plan = {'name': name, 'family': family, 'i': i, 'j': j, 'blocks': [], 'chunks': []}
+            if strf.n_adaptive_strata > 0:
+                n_a = strf.n_adaptive_strata
+                rel_alloc = (strf.ema_weight * strf.adaptive_rel_alloc
+                             + (1. - strf.ema_weight) * strf.guess_rel_alloc)           # :645-646
+                strf.guess_rel_alloc = copy.deepcopy(rel_alloc)                         # :649
+                n_samples = [min(strf.adaptive_strata_sizes[s],
+                                 max(1, int(rel_alloc[s] * (n_a + strf.n_samples_adaptive[0]))))
+                             for s in range(n_a)]                                       # :668
+                raw, flat = self._draw(family, i, j, strf.adaptive_strata, n_samples, rng)
+                if self.is_log_ixs:
+                    self.logged_ixs[name]['adaptive'][t_iter] = [[s] for s in raw]
+                plan['chunks'] += flat
+                plan['blocks'].append(('adaptive', n_a))
+                plan['default_alloc'] = np.asarray(rel_alloc, dtype=float)
+            if strf.n_nonadaptive_strata > 0:
+                raw, flat = self._draw(family, i, j, strf.nonadaptive_strata, strf.nonadaptive_abs_alloc, rng)
+                if self.is_log_ixs:
+                    self.logged_ixs[name]['nonadaptive'][t_iter] = raw
+                plan['chunks'] += flat
+                plan['blocks'].append(('nonadaptive', strf.n_nonadaptive_strata))
+            if strf.n_exact > 0:
+                plan['chunks'].append((np.asarray(strf.exact_domain), None))
+                plan['blocks'].append(('exact', 1))
+            plans.append(plan)
+        # which sums every domain produces (:629-634, :893-894, :983-984): f is always needed
+        # here (grad_alloc is False; n_func = 2 forces it with the derivatives)
+        do_f = True
+        do_diff = bool(compute_diff_f_sum)
+        # ---- 2. baseline term on the host (constant in t: O(samples)) ---------------------------
+        self._estimate_mu(plans[0], x_mu, compute_f_sum, do_diff)
+        # ---- 3. impact values per event, weight vectors ------------------------------------------
+        marks = [np.asarray(m, dtype=float) for m in self.list_marks]
+        w = [np.asarray(self.impact[k][i](marks[i], np.asarray(x_imp[i], dtype=float)), dtype=float)
+             * np.ones(len(marks[i])) for i in range(d)]
+        dw = [[np.asarray(self.diff_impact[k][i](marks[i], r, np.asarray(x_imp[i], dtype=float)),
+                          dtype=float) * np.ones(len(marks[i])) for r in range(n_imp[i])] for i in range(d)]
+        vectors, ix_w, ix_w2, ix_dw, ix_2wdw = [], [], [], [], []
+        for i in range(d):
+            ix_w.append(len(vectors)); vectors.append((i, w[i]))
+            ix_w2.append(len(vectors)); vectors.append((i, w[i] ** 2))
+            ix_dw.append([]); ix_2wdw.append([])
+            if do_diff:
+                for r in range(n_imp[i]):
+                    ix_dw[i].append(len(vectors)); vectors.append((i, dw[i][r]))
+                    ix_2wdw[i].append(len(vectors)); vectors.append((i, 2. * w[i] * dw[i][r]))
+        engine = self._bound_engine()
+        engine.set_weights(vectors)
+        x_dev = x[:1 + sum(self.matrix_n_param_ker[k])]
+        base = np.array([ix_w, ix_w, ix_w, ix_w, ix_w2], dtype=np.int32)
+        # ---- 4. one launch for every kernel-side output of every term ----------------------------
+        dev_plans = [p for p in plans[1:] if p['chunks']]
+        self._plans_cache = dev_plans
+        res = self._launch(engine, x_dev, dev_plans, base, do_diff, with_alloc=True)
+        for plan in dev_plans:
+            self._store_kernel_side(plan, res[plan['name']], do_f, do_diff, t_iter)
+        # ---- 5. impact-side derivatives: value-only launches with one weight replaced ------------
+        if do_diff:
+            by_name = {p['name']: p for p in dev_plans}
+            for p_dim in range(d):
+                for r in range(n_imp[p_dim]):
+                    roles = base.copy()
+                    roles[1][p_dim] = ix_dw[p_dim][r]
+                    roles[3][p_dim] = ix_dw[p_dim][r]
+                    roles[4][p_dim] = ix_2wdw[p_dim][r]
+                    names = ['K_%d' % p_dim, 'upsilonzero_%d' % p_dim] + ['upsilon_%d_%d' % (p_dim, j) for j in range(d)]
+                    sel = [by_name[n] for n in names if n in by_name]
+                    va = self._launch(engine, x_dev, sel, roles, False, with_alloc=False)
+                    roles = base.copy()
+                    roles[0][p_dim] = ix_dw[p_dim][r]
+                    roles[2][p_dim] = ix_dw[p_dim][r]
+                    names = ['phi_%d' % p_dim] + ['upsilon_%d_%d' % (i, p_dim) for i in range(d)]
+                    sel = [by_name[n] for n in names if n in by_name]
+                    vb = self._launch(engine, x_dev, sel, roles, False, with_alloc=False)
+                    self._store_impact_side(p_dim, r, va, vb)
+        # ---- 6. totals (:1065-1094) ----------------------------------------------------------------
+        for plan in plans[1:]:
+            name = plan['name']
+            if compute_f_sum:
+                self.sum_f[name] = (self.sum_f_adaptive[name] + self.sum_f_nonadaptive[name]
+                                    + self.sum_f_exact[name])
+            if do_diff:
+                self._add_domains(name)
+        self.log_estimates()
+        if count_iter:
+            self.t += 1
+
+    # per-stratum estimate: size * mean for sampled strata, plain sum on the exact domain
+    def _scale(self, plan, block_sums):
+        """block_sums: (n_strata_total, n_out) plain per-stratum sums in block order ->
+        list of (domain, estimates (n_strata, n_out))."""
+        strf = self.stratif[plan['name']]
+        counts = np.array([len(m) for m, _ in plan['chunks']], dtype=float)
+        out, s = [], 0
+        for domain, n_strata in plan['blocks']:
+            blk = block_sums[s:s + n_strata]
+            if domain == 'exact':
+                est = blk
+            else:
+                sizes = np.asarray(strf.adaptive_strata_sizes if domain == 'adaptive'
+                                   else strf.nonadaptive_strata_sizes, dtype=float)
+                est = (blk / counts[s:s + n_strata, None]) * sizes[:, None]
+            out.append((domain, est))
+            s += n_strata
+        return out
+
+    def _launch(self, engine, x_dev, sel_plans, roles, with_diff, with_alloc):
+        """One sampled launch over the strata of ``sel_plans``; returns
+        {name: (per-stratum sums (n_strata, n_out), stat_std, rel_alloc)}."""
+        if not sel_plans:
+            return {}
+        dev_terms, offsets, all_m, all_n, sizes, defaults = [], [0], [], [], [], []
+        for plan in sel_plans:
+            strf = self.stratif[plan['name']]
+            for m, n in plan['chunks']:
+                all_m.append(m)
+                all_n.append(n if n is not None else np.zeros(len(m), dtype=np.int64))
+                offsets.append(offsets[-1] + len(m))
+            for domain, n_strata in plan['blocks']:
+                if domain == 'adaptive':
+                    sizes += [float(s) for s in strf.adaptive_strata_sizes]
+                    defaults += [float(a) for a in plan['default_alloc']]
+                else:
+                    sizes += [0.] * n_strata
+                    defaults += [0.] * n_strata
+            dev_terms.append((self.KIND[plan['family']], plan['i'], plan['j'], len(plan['chunks'])))
+        sums, out_off, stat_mean, stat_std, rel = engine.sampled_sums(
+            self.k, x_dev, dev_terms, offsets, np.concatenate(all_m), np.concatenate(all_n),
+            strata_sizes=sizes if with_alloc else None, default_alloc=defaults if with_alloc else None,
+            compute_diff_f_sum=with_diff, grad_alloc=False, roles=roles)
+        out, s_ix = {}, 0
+        for plan in sel_plans:
+            n_s = len(plan['chunks'])
+            block = np.stack([sums[out_off[s_ix + s]:out_off[s_ix + s + 1]] for s in range(n_s)])
+            out[plan['name']] = (block, stat_std[s_ix:s_ix + n_s],
+                                 None if rel is None else rel[s_ix:s_ix + n_s])
+            s_ix += n_s
+        return out
+
+    def _store_kernel_side(self, plan, result, do_f, do_diff, t_iter):
+        """Function value and kernel / baseline derivative blocks (ix_f = 0) of one term."""
+        name, family = plan['name'], plan['family']
+        strf = self.stratif[name]
+        block, stat_std, rel = result
+        nk_i = self.matrix_n_param_ker[self.k][plan['i']]
+        s = 0
+        for domain, est in self._scale(plan, block):
+            n_strata = est.shape[0]
+            if domain == 'exact':
+                self.sum_f_exact[name] = est[0, 0]
+            else:
+                getattr(self, 'vecsum_f_' + domain)[name] = est[:, 0].copy()
+                getattr(self, 'sum_f_' + domain)[name] = est[:, 0].sum()
+            if do_diff:
+                # device layout: [f, d/d kernel params of ix_func 1 (, ix_func 2 or baseline)]
+                if family == 'K':
+                    parts = {1: est[:, 1:1 + nk_i], 2: est[:, 1 + nk_i:2 + nk_i]}
+                elif family == 'upsilon' and plan['i'] != plan['j']:
+                    nk_j = self.matrix_n_param_ker[self.k][plan['j']]
+                    parts = {1: est[:, 1:1 + nk_i], 2: est[:, 1 + nk_i:1 + nk_i + nk_j]}
+                else:
+                    parts = {None: est[:, 1:1 + nk_i]}
+                for ix_func, arr in parts.items():
+                    per_param = arr.T.copy()
+                    self._put(name, domain, 0, ix_func, per_param)
+            if domain == 'adaptive':
+                strf.adaptive_rel_alloc = np.array(rel[s:s + n_strata], dtype=float)      # :861
+                if self.is_log_allocs:
+                    self.logged_allocs[name][t_iter] = strf.adaptive_rel_alloc.copy()
+            s += n_strata
+
+    def _put(self, name, domain, ix_f, ix_func, per_param):
+        """per_param: (n_param, n_strata) estimates of one derivative block of one domain."""
+        def assign(container, value):
+            if ix_func is None:
+                container[name][ix_f] = value
+            else:
+                container[name][ix_f][ix_func] = value
+        if domain != 'exact':
+            assign(getattr(self, 'vecsum_diff_f_' + domain), per_param)
+        assign(getattr(self, 'sum_diff_f_' + domain), per_param.sum(axis=1))
+
+    def _store_impact_side(self, p, r, va, vb):
+        """Derivative with respect to the r-th impact parameter of I_kp (ix_f = 1) from the
+        value-only launches va (target weight differentiated) and vb (source weight)."""
+        d = self.d
+        by_name = {}
+        for res in (va, vb):
+            for name, (block, _, _) in res.items():
+                by_name.setdefault(name, []).append(block)
+
+        def domains(name, blocks):
+            plan = next(pl for pl in self._plans_cache if pl['name'] == name)
+            total = sum(blocks)
+            return self._scale(plan, total)
+        for name, blocks in by_name.items():
+            family = name.split('_')[0]
+            for domain, est in domains(name, blocks):
+                vals = est[:, 0]                 # (n_strata,) estimates of sum f x dI
+                if family == 'upsilon':
+                    i, j = (int(v) for v in name.split('_')[1:])
+                    if i == j:
+                        self._put_row(name, domain, 1, None, r, vals)
+                    else:
+                        self._put_row(name, domain, 1, 1 if i == p else 2, r, vals)
+                else:
+                    self._put_row(name, domain, 1, None, r, vals)
+
+    def _put_row(self, name, domain, ix_f, ix_func, r, vals):
+        def target(container):
+            return container[name][ix_f] if ix_func is None else container[name][ix_f][ix_func]
+        if domain != 'exact':
+            target(getattr(self, 'vecsum_diff_f_' + domain))[r] = vals
+        target(getattr(self, 'sum_diff_f_' + domain))[r] = vals.sum()
+
+    def _add_domains(self, name):
+        parts = (self.sum_diff_f_adaptive[name], self.sum_diff_f_nonadaptive[name], self.sum_diff_f_exact[name])
+        for ix_f in range(self.n_f[name]):
+            if self.vec_n_func[name][ix_f] is None:
+                self.sum_diff_f[name][ix_f] = parts[0][ix_f] + parts[1][ix_f] + parts[2][ix_f]
+            else:
+                for ix_func in (1, 2):
+                    self.sum_diff_f[name][ix_f][ix_func] = (parts[0][ix_f][ix_func] + parts[1][ix_f][ix_func]
+                                                            + parts[2][ix_f][ix_func])
+
+    def _estimate_mu(self, plan, x_mu, compute_f_sum, do_diff):
+        """estimate_sum of the 'mu' term (:1273-1316) with the model's own baseline closures."""
+        name = 'mu'
+        strf = self.stratif[name]
+        t_k = np.asarray(self.list_times[self.k])
+        n_mu = len(x_mu)
+        s = 0
+        for domain, n_strata in plan['blocks']:
+            f_est = np.zeros(n_strata)
+            d_est = np.zeros((n_mu, n_strata))
+            std = np.zeros(n_strata)
+            for q in range(n_strata):
+                ix = plan['chunks'][s + q][0]
+                f_vals = np.asarray(self.mu[self.k](t_k[ix], x_mu), dtype=float) * np.ones(len(ix))
+                scale = 1.
+                if domain == 'adaptive':
+                    scale = strf.adaptive_strata_sizes[q]
+                elif domain == 'nonadaptive':
+                    scale = strf.nonadaptive_strata_sizes[q]
+                f_est[q] = np.sum(f_vals) if domain == 'exact' else scale * np.mean(f_vals)
+                std[q] = np.std(f_vals)
+                for r in range(n_mu):
+                    dv = np.asarray(self.diff_mu[self.k](t_k[ix], r, x_mu), dtype=float) * np.ones(len(ix))
+                    d_est[r, q] = np.sum(dv) if domain == 'exact' else scale * np.mean(dv)
+            if domain == 'exact':
+                self.sum_f_exact[name] = f_est[0]
+            else:
+                getattr(self, 'vecsum_f_' + domain)[name] = f_est
+                getattr(self, 'sum_f_' + domain)[name] = f_est.sum()
+            if do_diff:
+                self._put(name, domain, 0, None, d_est)
+            if domain == 'adaptive':
+                sizes = np.asarray(strf.adaptive_strata_sizes, dtype=float)
+                with np.errstate(divide='ignore', invalid='ignore'):
+                    rel = sizes * np.sqrt(sizes / (sizes - 1.)) * std                     # :725-729
+                tot = np.sum(rel)
+                strf.adaptive_rel_alloc = rel / tot if tot > 0. else plan['default_alloc'].copy()
+                if self.is_log_allocs:
+                    self.logged_allocs[name][self.t] = strf.adaptive_rel_alloc.copy()
+            s += n_strata
+        if compute_f_sum:
+            self.sum_f[name] = self.sum_f_adaptive[name] + self.sum_f_nonadaptive[name] + self.sum_f_exact[name]
+        if do_diff:
+            self._add_domains(name)
+
+    # ---- LSE and gradient (:1708-1745) -------------------------------------------------------------
+    def lse_k_estimate(self, x_k, compute_diff_f_sum=False, grad_alloc=True, rng=None, seed=None,
+                       count_iter=True):
+        if rng is None:
+            rng = np.random.default_rng(seed)
+        self.compute_objective(x_k, compute_f_sum=True, compute_diff_f_sum=compute_diff_f_sum,
+                               grad_alloc=grad_alloc, rng=rng, count_iter=count_iter)
+        self.lse_k = self.recombine_lse_k()
+        return self.lse_k
+
+    def lse_k_grad_estimate(self, x_k, grad_alloc=True, rng=None, seed=None, count_iter=True):
+        if rng is None:
+            rng = np.random.default_rng(seed)
+        self.compute_objective(x_k, compute_f_sum=self.is_log_lse, compute_diff_f_sum=True,
+                               grad_alloc=grad_alloc, rng=rng, count_iter=count_iter)
         grad = self.recombine_grad_lse_k()
         self.grad_lse_k = grad
         if self.is_log_lse:

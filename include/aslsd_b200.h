@@ -248,6 +248,15 @@ int aslsd_sampled_sums(aslsd_ctx* ctx, int k, const double* x_k, int flags, int 
                        const double* default_alloc, double* sum_out, double* stat_mean,
                        double* stat_std, double* rel_alloc);
 
+/* Sampled sums with the same weights (MTLHStratEstim.estimate_sum_*dom,
+ * optimize/estimators/mtlh_stratified_estimator.py:615-1025): arguments of aslsd_sampled_sums
+ * plus `roles`; every per-sample output is multiplied by weight(target) * weight(source). */
+int aslsd_sampled_sums_weighted(aslsd_ctx* ctx, int k, const double* x_k, int flags, int n_terms,
+                                const aslsd_sample_term* terms, const int64_t* stratum_offsets,
+                                const int64_t* ix_m, const int64_t* ix_n, const double* strata_sizes,
+                                const double* default_alloc, const int32_t* roles, double* sum_out,
+                                double* stat_mean, double* stat_std, double* rel_alloc);
+
 /* Stand-alone allocation update of estimate_sum_adaptivedom (:637-645) for one
  * group of strata. */
 int aslsd_update_allocation(aslsd_ctx* ctx, int n_strata, const double* strata_sizes,

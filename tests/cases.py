@@ -84,6 +84,16 @@ MTLH_CASES = {
 }
 
 
+# stratified traces of marked models: name -> (case of MTLH_CASES, events per type, T_f,
+# stratification keywords, iterations, RNG seed)
+_MTLH_KW = dict(n_exact_single=20, n_samples_adaptive_single=200, nonadaptive_sample_size_single=100,
+                n_samples_adaptive_double=300, nonadaptive_sample_size_double=200)
+MTLH_STRAT = {
+    'mtlh_exp2d': ('mtlh_exp2d', [900, 700], 400., _MTLH_KW, 4, 3),
+    'mtlh_gauss1d': ('mtlh_gauss1d', [1200], 700., _MTLH_KW, 4, 5),
+}
+
+
 def mtlh_inputs(name):
     """Seeded event times and marks of an MTLH case."""
     model, xs, n_events, T_f = MTLH_CASES[name]

@@ -185,8 +185,23 @@ class OracleEngine:
                 for q, k in enumerate(ks)]
 
     def sampled_sums(self, k, x_k, terms, stratum_offsets, ix_m, ix_n=None, strata_sizes=None,
-                     default_alloc=None, compute_diff_f_sum=True, grad_alloc=False):
+                     default_alloc=None, compute_diff_f_sum=True, grad_alloc=False, roles=None):
         self.n_calls += 1
+        if roles is not None:
+            roles = np.asarray(roles).reshape(5, self.plain['d'])
+
+        def weight(kind, i, j, m, n):
+            """per-sample weight of a marked model (aslsd_sampled_sums_weighted)"""
+            def vec(role, dim, ix):
+                v = roles[role][dim]
+                return 1. if v < 0 else self.weights[v][1][ix]
+            if kind == 0:
+                return vec(3, i, m)
+            if kind == 1:
+                return vec(4, i, m)
+            if kind == 2:
+                return vec(0, i, n)
+            return vec(1, i, m) * vec(2, j, n)
         sums, out_off, means, stds = [], [0], [], []
         s_ix = 0
         groups = []
@@ -196,6 +211,9 @@ class OracleEngine:
                 a, b = stratum_offsets[s_ix], stratum_offsets[s_ix + 1]
                 vals = OS.term_values(self.plain, k, x_k, self.times, self.T_f, kind, i, j,
                                       ix_m[a:b], None if ix_n is None else ix_n[a:b])
+                if roles is not None:
+                    w = weight(kind, i, j, ix_m[a:b], None if ix_n is None else ix_n[a:b])
+                    vals = vals * (np.asarray(w, dtype=float) * np.ones(b - a))[:, None]
                 if not compute_diff_f_sum:
                     vals[:, 1:] = 0.
                 tot, mean, std = OS.stratum_statistics(vals, grad_alloc)

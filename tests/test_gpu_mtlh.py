@@ -109,3 +109,13 @@ def test_unit_weights_reproduce_the_unmarked_sums(engine):
             assert np.all(part[seg] == 0.)
     with pytest.raises(Exception):
         engine.exact_sums_weighted(0, x, np.array([[1, 0]] * 5, dtype=np.int32))   # wrong event types
+
+
+@pytest.mark.parametrize('name', ['mtlh_exp2d', 'mtlh_gauss1d'])
+def test_mtlh_stratified_replays_reference_trace(engine, name):
+    """MTLHStratEstimB200 on the device against traces of the reference's MTLHStratEstim: the
+    samples are the reference's (same Generator stream to the last draw), every estimate within
+    1e-10, the adaptive allocations within 1e-9."""
+    from mtlh_replay import replay
+    worst = replay(name, engine)
+    assert worst <= RTOL

@@ -66,6 +66,29 @@ def test_plugs_into_reference_mtlh_fit():
     np.testing.assert_allclose(flat(mu_new, ker_new, imp_new), flat(mu_ref, ker_ref, imp_ref), rtol=1e-8)
 
 
+def test_stratified_estimator_plugs_into_reference_mtlh_fit():
+    """MTLH.fit's default is the stratified estimator (mtlh.py:2379-2386): the B200 counterpart
+    follows the same iterates (same samples from the shared Generator, same ADAM steps)."""
+    import aslsd_b200
+    import make_golden_mtlh
+    import make_golden_mtlh_strat as MS
+    from aslsd.stats.events.process_path import ProcessPath
+    model, times, marks, T_f, kw, n_iter, seed = MS.strat_inputs('mtlh_exp2d')
+    path = ProcessPath(times, T_f, list_marks=marks)
+    xs = MTLH_CASES['mtlh_exp2d'][1]
+    x_0 = [np.asarray(x, dtype=float) for x in xs]
+    ref_model = make_golden_mtlh.build_reference_mtlh(model)
+    mu_ref, ker_ref, imp_ref = ref_model.fit(path, x_0=copy.deepcopy(x_0), n_iter=5, seed=9, **kw)
+    new_model = make_golden_mtlh.build_reference_mtlh(model)
+    mu_new, ker_new, imp_new = new_model.fit(
+        path, x_0=copy.deepcopy(x_0), n_iter=5, seed=9,
+        estimators=aslsd_b200.MTLHStratEstimB200(engine=OracleEngine()), **kw)
+    flat = lambda mu, ker, imp: np.concatenate(
+        [np.ravel(np.asarray(v, dtype=float)) for v in list(mu) + [c for row in ker for c in row]
+         + [c for row in imp for c in row]])
+    np.testing.assert_allclose(flat(mu_new, ker_new, imp_new), flat(mu_ref, ker_ref, imp_ref), rtol=1e-8)
+
+
 def test_unsupported_baselines_raise():
     """Baselines other than ConstantBaseline are outside the device's scope: loud refusal."""
     import types
