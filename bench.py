@@ -171,6 +171,33 @@ def _oracle_job(model, k, x, times, T_f, ranges):
     return sum(n_pairs.values())
 
 
+def aslsd_epochs(engine):
+    """Second part of BASELINE.json's metric: seconds per epoch of an ASLSD fit (one stratified
+    gradient estimate + ADAM step for every k), configs C3 and C4 of SURVEY 8d (~10^6 events)."""
+    import aslsd_b200
+    from aslsd_b200 import simulate
+    configs = {
+        'C3: 1-D Gaussian, ~10^6 events': ({'d': 1, 'kernels': [[[{'type': 'gauss'}]]]}, [1.5],
+                                           [[[.5, .5, 3.]]], 3.33e5),
+        'C4: 1-D SBF-Gaussian(10), ~10^6 events': (simulate.sbf_gauss_model(1, 10), [1.0],
+                                                   [[simulate.random_mixture_weights(10, coeff=0.5)]], 5e5),
+    }
+    out = {}
+    for name, (model, mu, kp, T_f) in configs.items():
+        times = simulate.simulate_mhp(model, mu, kp, T_f, seed=1234)
+        path = aslsd_b200.ProcessPath(times, T_f, engine=engine)
+        mirror = aslsd_b200.MHP(model)
+        x0 = [np.concatenate([[mu[0]], np.asarray(kp[0][0], float)])
+              * (1 + 0.1 * np.random.default_rng(12).uniform(-1, 1, size=1 + len(kp[0][0])))]
+        mirror.fit(path, [x.copy() for x in x0], n_iter=3, engine=engine, seed=1)
+        n_iter = 20
+        t0 = time.perf_counter()
+        mirror.fit(path, [x.copy() for x in x0], n_iter=n_iter, engine=engine, seed=1)
+        out[name] = {'s_per_epoch': (time.perf_counter() - t0) / n_iter,
+                     'n_events': int(sum(len(t) for t in times))}
+    return out
+
+
 def run_reference(args):
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
@@ -421,6 +448,12 @@ def run_b200(args):
             'clocks': clocks,
         }
         if not args.no_cpu_baseline and world == 1:
+            # stratified (ASLSD) fit epochs on their own engine (the C5 events stay untouched)
+            line['config']['aslsd_fit'] = dict(
+                aslsd_epochs(aslsd_b200.Engine(local_rank)),
+                note='s/epoch of an ASLSD fit (MHPStratEstimB200 + ADAM through the mirror fit loop, '
+                     'host sampling with the reference\'s RNG stream, sampled-lag kernel on the device); '
+                     'reported beside the headline metric')
             rate, dt, pairs = cpu_oracle_rate(model, times, T_f, xs, args.cpu_sample_T, n_proc=1)
             line['cpu_baseline'] = {
                 'value': rate, 'unit': 'pair-terms/s', 'cores': 1, 'kind': 'port',
