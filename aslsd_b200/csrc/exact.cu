@@ -246,14 +246,18 @@ static int build_work(aslsd_ctx* ctx, const int64_t* m_lo, const int64_t* m_hi, 
       const QStreamDev& S = B.qstreams[(size_t)qfam[f][x].wu_first];
       const int64_t m_end = B.hi[S.tgt_dim];
       if (S.m_hi < m_end) {
-        BoundaryGroupDev G;
-        std::memset(&G, 0, sizeof(G));
-        G.stream = (int32_t)qfam[f][x].wu_first;
-        G.row_first = (int32_t)(B.qrows.size() + x);
-        G.row_count = (int32_t)(y - x);
-        G.m_lo = S.m_hi;
-        G.m_hi = m_end;
-        B.bgroups.push_back(G);
+        // a few CTAs per stream: each takes a slice of the rows (one warp per row at a time)
+        const size_t rows_per_group = 4 * (LB_NT / 32);
+        for (size_t z = x; z < y; z += rows_per_group) {
+          BoundaryGroupDev G;
+          std::memset(&G, 0, sizeof(G));
+          G.stream = (int32_t)qfam[f][x].wu_first;
+          G.row_first = (int32_t)(B.qrows.size() + z);
+          G.row_count = (int32_t)std::min(rows_per_group, y - z);
+          G.m_lo = S.m_hi;
+          G.m_hi = m_end;
+          B.bgroups.push_back(G);
+        }
       }
       x = y;
     }
