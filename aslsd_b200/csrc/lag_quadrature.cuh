@@ -35,7 +35,7 @@
 //      running count in a warp-private histogram -> (bin, rank in warp) key.  Scan of the histograms.
 //      Pass 2: coordinates move to their sorted slots.  No atomics: the order inside a bin is fixed
 //      and the result is deterministic;
-//   c. every 8-lane group takes a bin: three-term recurrence, LQ_ND - 1 register accumulators per lane,
+//   c. every group of LQ_GS lanes takes a bin: three-term recurrence, LQ_ND - 1 register accumulators per lane,
 //      transposed shuffle reduction, owner adds into the CTA's moment table;
 //   one partial table per work unit, reduced in fixed order by lag_weights_kernel.
 #pragma once
@@ -44,12 +44,13 @@
 #include "pair_kernels.cuh"
 
 #ifndef LQ_NT
-#define LQ_NT 512                 // threads per CTA
+#define LQ_NT 512                 // threads per CTA (1024 measured slower: 17.3 vs 14.8 ms)
 #endif
 #ifndef LQ_CTAS
 #define LQ_CTAS 1                 // CTAs per SM the shared-memory budget is cut for
 #endif
 #define LQ_NW (LQ_NT / 32)
+#define LQ_GS (LQ_NT >= 1024 ? 16 : 8)   // lanes per bin in the moment pass (one round covers 64 bins)
 #define LQ_TM LQ_NT               // targets per tile: one per thread
 #define LQ_UCAP_MAX 8192          // pairs sorted at a time
 #define LQ_SMAX 2048              // staged source events per tile (two buffers)
@@ -383,9 +384,9 @@ lag_moment_kernel(const DimDev* __restrict__ dims, const QStreamDev* __restrict_
         s_u[(int)my_hist[b] + (int)(key >> 10)] = s_val[q];
       }
       __syncthreads();
-      // ---- c. moments of every bin: 8 lanes per bin ---------------------------------------------
-      const int grp = lane >> 3, q8 = lane & 7;
-      for (int b0 = warp * 4; b0 < J; b0 += LQ_NW * 4) {
+      // ---- c. moments of every bin: LQ_GS lanes per bin -------------------------------------------
+      const int grp = lane / LQ_GS, qg = lane % LQ_GS;
+      for (int b0 = warp * (32 / LQ_GS); b0 < J; b0 += LQ_NW * (32 / LQ_GS)) {
         const int b = b0 + grp;
         int32_t e0 = 0, e1 = 0;
         if (b < J) { e0 = s_bin[b]; e1 = s_bin[b + 1]; }
@@ -393,9 +394,9 @@ lag_moment_kernel(const DimDev* __restrict__ dims, const QStreamDev* __restrict_
 #pragma unroll
         for (int d = 0; d < LQ_ND; ++d) acc[d] = 0.;
         // two independent recurrences per iteration (the chain is latency-bound)
-        int32_t e = e0 + q8;
-        for (; e + 8 < e1; e += 16) {
-          const double ua = s_u[e] + s_u[e], ub = s_u[e + 8] + s_u[e + 8];
+        int32_t e = e0 + qg;
+        for (; e + LQ_GS < e1; e += 2 * LQ_GS) {
+          const double ua = s_u[e] + s_u[e], ub = s_u[e + LQ_GS] + s_u[e + LQ_GS];
           const double two_a = ua + ua, two_b = ub + ub;
           double pa = 1., ca = ua, pb = 1., cb = ub;
           acc[1] += ca + cb;
@@ -421,30 +422,34 @@ lag_moment_kernel(const DimDev* __restrict__ dims, const QStreamDev* __restrict_
             acc[d] += tn;
           }
         }
-        if (q8 == 0) acc[0] = (double)(e1 - e0);   // T_0 = 1: the bin count, exact
-        // transposed reduction over the 8 lanes: 12 -> 6 -> 3 values per lane
+        if (qg == 0) acc[0] = (double)(e1 - e0);   // T_0 = 1: the bin count, exact
+        // transposed reduction over the group's lanes: 12 -> 6 -> 3 values per lane on the two
+        // widest exchanges, plain butterflies on the rest
         {
-          const bool up = (q8 & 4) != 0;
+          const bool up = (qg & (LQ_GS / 2)) != 0;
 #pragma unroll
           for (int i = 0; i < 6; ++i) {
             const double send = up ? acc[i] : acc[i + 6];
             const double keep = up ? acc[i + 6] : acc[i];
-            acc[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+            acc[i] = keep + __shfl_xor_sync(0xffffffffu, send, LQ_GS / 2);
           }
         }
         {
-          const bool up = (q8 & 2) != 0;
+          const bool up = (qg & (LQ_GS / 4)) != 0;
 #pragma unroll
           for (int i = 0; i < 3; ++i) {
             const double send = up ? acc[i] : acc[i + 3];
             const double keep = up ? acc[i + 3] : acc[i];
-            acc[i] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+            acc[i] = keep + __shfl_xor_sync(0xffffffffu, send, LQ_GS / 4);
           }
         }
 #pragma unroll
-        for (int i = 0; i < 3; ++i) acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], 1);
-        if (b < J && (q8 & 1) == 0 && e1 > e0) {
-          const int d0 = ((q8 & 4) ? 6 : 0) + ((q8 & 2) ? 3 : 0);
+        for (int o = LQ_GS / 8; o > 0; o >>= 1) {
+#pragma unroll
+          for (int i = 0; i < 3; ++i) acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], o);
+        }
+        if (b < J && (qg & (LQ_GS / 4 - 1)) == 0 && e1 > e0) {
+          const int d0 = ((qg & (LQ_GS / 2)) ? 6 : 0) + ((qg & (LQ_GS / 4)) ? 3 : 0);
           double* Mb = s_M + (size_t)b * LQ_ND + d0;
           Mb[0] += acc[0];
           Mb[1] += acc[1];
