@@ -225,6 +225,18 @@ class Engine:
             return sum_f, sum_diff_f, counts
         return sum_f, sum_diff_f
 
+    # ---- per-event sums (intensity at the jumps, compensator) --------------------------
+    def point_sums(self, k, x_k, kind):
+        """(d, n_events[k]) array: row i = sum over the earlier type-i events of phi_ki
+        (kind 'phi') or psi_ki (kind 'psi') at every event of type k."""
+        x = capi.as_f64(np.asarray(x_k, dtype=np.float64))
+        if len(x) != self.desc.n_param_k(k):
+            raise ValueError('x_k has %d entries, expected %d' % (len(x), self.desc.n_param_k(k)))
+        out = np.zeros((self.d, int(self.n_events[k])), dtype=np.float64)
+        self._check(self._lib.aslsd_point_sums(self._ctx, int(k), capi.ptr_f64(x),
+                                               {'phi': 0, 'psi': 1}[kind], capi.ptr_f64(out)))
+        return out
+
     # ---- marked models: per-event weights ---------------------------------------------
     def set_weights(self, vectors):
         """Upload per-event weight vectors: ``vectors`` is a list of (event type, values)

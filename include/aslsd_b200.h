@@ -129,6 +129,13 @@ int aslsd_exact_sums(aslsd_ctx* ctx, int k, const double* x_k, int flags,
                      const int64_t* m_lo, const int64_t* m_hi, double* out,
                      int64_t* n_pair_terms);
 
+/* ---- per-event sums: replaces the O(N^2) loops of MHP.get_intensity_at_jumps ----------
+ * (models/hawkes/linear/mhp.py:669-690) and of get_residuals_k_mhp (stats/residual_analysis/
+ * goodness_of_fit.py:169-228).  out is d arrays of n_events[k] doubles, one after the other:
+ *   kind 0: out[i][m] = sum over the type-i events before t^k_m of phi_ki(t^k_m - t^i_n)
+ *   kind 1: out[i][m] = the same sum of psi_ki (kernel part of the compensator at t^k_m). */
+int aslsd_point_sums(aslsd_ctx* ctx, int k, const double* x_k, int kind, double* out);
+
 /* ---- host-side index sampling: replaces utilities/useful_statistics.py:38-127 ---------
  * sample_single_ix_stratified / sample_double_ix_stratum / sample_double_ix_stratified draw with
  * numpy's Generator(PCG64); these entry points restate that generator and Generator.choice bit
