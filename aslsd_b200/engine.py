@@ -181,6 +181,26 @@ class Engine:
                                               for i in range(d)]
         return nest(kap), nest(var), nest(lag)
 
+    def index_maps_kernel_time(self):
+        """(kernel ms, algorithmic bytes) of one index-map launch with the three tables left on
+        the device (roofline accounting of the HBM-bound searchsorted kernel: per ordered pair
+        i != j read 8 (N_i + N_j), write 8 (N_j + 1) + 16 (H + 1) bytes)."""
+        d = self.d
+        klen = np.zeros(d * d, dtype=np.int64)
+        vlen = np.zeros(d * d, dtype=np.int64)
+        self._check(self._lib.aslsd_index_map_sizes(self._ctx, capi.ptr_i64(klen), capi.ptr_i64(vlen)))
+        nulls = (capi.c_i64_p * (d * d))()
+        self._check(self._lib.aslsd_index_maps(self._ctx, nulls, nulls, nulls))
+        ms, _ = self.last_timing()
+        n = self.n_events
+        nbytes = 0
+        for i in range(d):
+            for j in range(d):
+                nbytes += 8 * int(klen[i * d + j]) + 16 * int(vlen[i * d + j])
+                if i != j:
+                    nbytes += 8 * int(n[i] + n[j])
+        return ms, nbytes
+
     # ---- model -----------------------------------------------------------------------
     def set_model(self, model):
         desc = describe_model(model)

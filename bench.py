@@ -274,6 +274,10 @@ def run_b200(args):
             _, counts = engine.exact_sums_packed(k, xs[k], count_pairs=True)
             pair_terms += sum(counts.values())
     fp64_peak = engine.measure_fp64_peak()
+    idx_ms, idx_bytes = (None, None)
+    if rank == 0:
+        engine.index_maps_kernel_time()
+        idx_ms, idx_bytes = engine.index_maps_kernel_time()
 
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=device)   # > 126 MB L2
 
@@ -407,6 +411,12 @@ def run_b200(args):
                                     'evaluations at quadrature nodes, pair_evals = per-item kernel '
                                     'basis-pair evaluations (targets near T_f), single_evals = psi / '
                                     'upsilonzero evaluations'),
+                       'index_maps': {'kernel_ms': idx_ms, 'algorithmic_bytes': idx_bytes,
+                                      'GBps': idx_bytes / (idx_ms * 1e-3) * 1e-9 if idx_ms else None,
+                                      'frac_of_hbm_peak': (idx_bytes / (idx_ms * 1e-3) * 1e-9 / peaks.get('hbm_gbs'))
+                                      if idx_ms else None,
+                                      'note': 'kappa / varpi / lag_sizes of all d^2 ordered pairs in one launch '
+                                              '(HBM-bound batched searchsorted), tables left on the device'},
                        'fit_iteration_ms': fit_iter_ms,
                        'fit_iteration_note': 'same step with the quadrature weights kept between calls '
                                              '(ASLSD_OPT_WEIGHT_CACHE, the default outside this benchmark): '
