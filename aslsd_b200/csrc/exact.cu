@@ -52,7 +52,7 @@ struct BatchPlan {
   int qfam_first[8], qfam_count[8];
   std::vector<BoundaryGroupDev> bgroups;        // targets near T_f of the quadrature rows, by family
   int bfam_first[8], bfam_count[8];
-  int64_t n_wu_q = 0, n_q_partials = 0, n_q_weights = 0, n_q_evals = 0;
+  int64_t n_wu_q = 0, n_wu_q_plain = 0, n_q_partials = 0, n_q_weights = 0, n_q_evals = 0;
   int q_jmax = 0;
   size_t q_smem = 0;
 };
@@ -125,7 +125,8 @@ static void build_stream(const aslsd_ctx* ctx, BatchPlan& B, const std::vector<i
   if (!(nb <= (double)LQ_JMAX)) return;
   nb = std::min<double>(LQ_JMAX, 32. * std::ceil(nb / 32.));
   const double h = s_max / (nb - 1.5);
-  const int ucap = lq_pick_ucap((int)nb);
+  const bool weighted = first.wa_off >= 0 || first.wb_off >= 0;
+  const int ucap = lq_pick_ucap((int)nb, weighted);
   if (ucap == 0) return;
   QStreamDev S;
   std::memset(&S, 0, sizeof(S));
@@ -134,6 +135,8 @@ static void build_stream(const aslsd_ctx* ctx, BatchPlan& B, const std::vector<i
   S.same = first.same;
   S.J = (int32_t)nb;
   S.ucap = ucap;
+  S.wa_off = first.wa_off;
+  S.wb_off = first.wb_off;
   while ((1 << S.nbits) < S.J) ++S.nbits;
   S.m_lo = first.m_lo;
   S.m_hi = m_b;
@@ -143,7 +146,7 @@ static void build_stream(const aslsd_ctx* ctx, BatchPlan& B, const std::vector<i
   const int sx = (int)B.qstreams.size();
   B.qstreams.push_back(S);
   B.q_jmax = std::max(B.q_jmax, (int)S.J);
-  B.q_smem = std::max(B.q_smem, lq_smem_bytes(S.J, S.ucap));
+  B.q_smem = std::max(B.q_smem, lq_smem_bytes(S.J, S.ucap, weighted));
   for (int64_t r : group) {
     ItemDev it = B.rows[r];
     it.dst_row = r;
@@ -218,13 +221,13 @@ static int build_work(aslsd_ctx* ctx, const int64_t* m_lo, const int64_t* m_hi, 
   std::vector<ItemDev> qfam[8];
   if (ctx->use_quadrature) {
     // group the pair rows by (streams, target block), in row order
-    std::map<std::array<int64_t, 4>, std::vector<int64_t>> groups;
-    std::vector<std::array<int64_t, 4>> order;
+    // (marked models: also by the pair of weight vectors - weighted moments)
+    std::map<std::array<int64_t, 6>, std::vector<int64_t>> groups;
+    std::vector<std::array<int64_t, 6>> order;
     for (size_t r = 0; r < n_rows; ++r) {
       const ItemDev& it = B.rows[r];
       if (!is_pair_family(it.family) || it.m_hi <= it.m_lo) continue;
-      if (it.wa_off >= 0 || it.wb_off >= 0) continue;   // per-event weights: per-item kernels
-      std::array<int64_t, 4> key = {it.tgt_dim, it.src_dim, it.m_lo, it.m_hi};
+      std::array<int64_t, 6> key = {it.tgt_dim, it.src_dim, it.m_lo, it.m_hi, it.wa_off, it.wb_off};
       auto f = groups.find(key);
       if (f == groups.end()) {
         order.push_back(key);
@@ -232,7 +235,11 @@ static int build_work(aslsd_ctx* ctx, const int64_t* m_lo, const int64_t* m_hi, 
       }
       f->second.push_back((int64_t)r);
     }
-    for (auto& key : order) build_stream(ctx, B, groups[key], fast, boundary_from, qfam);
+    // unweighted streams first: the two kinds are launched separately
+    for (int pass = 0; pass < 2; ++pass)
+      for (auto& key : order)
+        if ((key[4] >= 0 || key[5] >= 0) == (pass == 1))
+          build_stream(ctx, B, groups[key], fast, boundary_from, qfam);
   }
   for (int f = 0; f < 8; ++f) {
     B.qfam_first[f] = (int)B.qrows.size();
@@ -323,6 +330,9 @@ static int build_work(aslsd_ctx* ctx, const int64_t* m_lo, const int64_t* m_hi, 
     wts += (int64_t)S.J * LQ_ND;
   }
   B.n_wu_q = qwu;
+  B.n_wu_q_plain = qwu;
+  for (auto& S : B.qstreams)
+    if (S.wa_off >= 0 || S.wb_off >= 0) { B.n_wu_q_plain = S.wu_first; break; }
   B.n_q_partials = part;
   B.n_q_weights = wts;
   if (B.n_wu >= (int64_t)2147483647 || qwu >= (int64_t)2147483647)
@@ -423,7 +433,7 @@ static void launch_boundary(aslsd_ctx* ctx, const BatchPlan& B, const QStreamDev
   if (B.bfam_count[FAMILY] == 0) return;
   lag_boundary_kernel<FAMILY><<<(unsigned)B.bfam_count[FAMILY], LB_NT, 0, ctx->stream>>>(
       (const DimDev*)ctx->d_dims, d_streams, d_groups + B.bfam_first[FAMILY], d_qrows, ctx->T_f, raw_device,
-      d_cnt + B.bfam_first[FAMILY]);
+      d_cnt + B.bfam_first[FAMILY], ctx->d_weights);
   ctx->last_launches++;
 }
 
@@ -495,17 +505,28 @@ static int run_batch(aslsd_ctx* ctx, BatchPlan& B, double* raw_device) {
   ctx->last_moment_ms = 0.;
   if (quad && !reuse_weights) {
     if (B.q_smem > ctx->q_smem_set) {
-      CUDA_TRY(ctx, cudaFuncSetAttribute(lag_moment_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+      CUDA_TRY(ctx, cudaFuncSetAttribute(lag_moment_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)B.q_smem));
+      CUDA_TRY(ctx, cudaFuncSetAttribute(lag_moment_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)B.q_smem));
       ctx->q_smem_set = B.q_smem;
     }
     CUDA_TRY(ctx, cudaEventRecord(ctx->ev_q0, ctx->stream));
-    lag_moment_kernel<<<(unsigned)B.n_wu_q, LQ_NT, B.q_smem, ctx->stream>>>(
-        (const DimDev*)ctx->d_dims, d_streams, (int)B.qstreams.size(), ctx->d_q_partials,
-        ctx->d_counts + B.n_wu + n_items);
+    unsigned long long* d_qcnt = ctx->d_counts + B.n_wu + n_items;
+    if (B.n_wu_q_plain > 0) {
+      lag_moment_kernel<false><<<(unsigned)B.n_wu_q_plain, LQ_NT, B.q_smem, ctx->stream>>>(
+          (const DimDev*)ctx->d_dims, d_streams, (int)B.qstreams.size(), ctx->d_q_partials, d_qcnt,
+          ctx->d_weights, 0);
+      ctx->last_launches++;
+    }
+    if (B.n_wu_q > B.n_wu_q_plain) {
+      lag_moment_kernel<true><<<(unsigned)(B.n_wu_q - B.n_wu_q_plain), LQ_NT, B.q_smem, ctx->stream>>>(
+          (const DimDev*)ctx->d_dims, d_streams, (int)B.qstreams.size(), ctx->d_q_partials, d_qcnt,
+          ctx->d_weights, B.n_wu_q_plain);
+      ctx->last_launches++;
+    }
     CUDA_TRY(ctx, cudaEventRecord(ctx->ev_q1, ctx->stream));
     ctx->moment_timing_pending = true;
-    ctx->last_launches++;
     const dim3 wgrid((unsigned)((B.q_jmax + LQ_WB - 1) / LQ_WB), (unsigned)B.qstreams.size());
     lag_weights_kernel<<<wgrid, LQ_WB * LQ_ND, 0, ctx->stream>>>(d_streams, ctx->d_q_partials, ctx->d_q_weights);
     ctx->last_launches++;

@@ -69,6 +69,8 @@ struct QStreamDev {
   int64_t wu_first;        // first work unit (prefix over streams)
   int64_t part_first;      // partial moment tables: [chunk][J][LQ_ND] doubles
   int64_t w_first;         // weights: [J][LQ_ND] doubles
+  int64_t wa_off, wb_off;  // per-event weights of targets / sources (marked models), -1 = none:
+                           // the moments become sum of weight(m) weight(n) T_d(u)
   double s_max, h, inv_h;
 };
 
@@ -78,9 +80,9 @@ __constant__ double LQ_CT[LQ_ND * LQ_ND];   // [i][d]
 
 // dynamic shared memory: [pair-order lags / coordinates | sorted coordinates | 2 source windows |
 //                         moment table | keys | bin starts | histograms]
-__host__ __device__ inline size_t lq_smem_bytes(int J, int ucap) {
+__host__ __device__ inline size_t lq_smem_bytes(int J, int ucap, bool weighted) {
   size_t b = 0;
-  b += (size_t)ucap * sizeof(double) * 2;
+  b += (size_t)ucap * sizeof(double) * (weighted ? 4 : 2);   // + pair weights in both orders
   b += (size_t)(LQ_SMAX + 2) * sizeof(double) * 2;
   b += (size_t)J * LQ_ND * sizeof(double);
   b += (size_t)ucap * sizeof(uint32_t);
@@ -90,9 +92,9 @@ __host__ __device__ inline size_t lq_smem_bytes(int J, int ucap) {
 }
 
 // largest chunk (multiple of LQ_NT) that fits the budget; 0 if none does
-inline int lq_pick_ucap(int J) {
+inline int lq_pick_ucap(int J, bool weighted) {
   for (int u = LQ_UCAP_MAX; u >= LQ_NT; u -= LQ_NT)
-    if (lq_smem_bytes(J, u) <= (size_t)LQ_SMEM_BUDGET) return u;
+    if (lq_smem_bytes(J, u, weighted) <= (size_t)LQ_SMEM_BUDGET) return u;
   return 0;
 }
 
@@ -196,9 +198,13 @@ __device__ __forceinline__ void lq_pass1(int n_c, double inv_h, uint16_t* my_his
   }
 }
 
+// WEIGHTED: streams of marked models (per-event weights); launched separately from the
+// unweighted streams so that those keep their register budget
+template <bool WEIGHTED>
 __global__ void __launch_bounds__(LQ_NT, LQ_CTAS)
 lag_moment_kernel(const DimDev* __restrict__ dims, const QStreamDev* __restrict__ streams, int n_streams,
-                  double* __restrict__ partials, unsigned long long* __restrict__ counts) {
+                  double* __restrict__ partials, unsigned long long* __restrict__ counts,
+                  const double* __restrict__ weights, int64_t wu_base) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ __align__(8) uint64_t s_bar[2];
   __shared__ int64_t s_a0[2];        // first source index of each window buffer
@@ -208,7 +214,7 @@ lag_moment_kernel(const DimDev* __restrict__ dims, const QStreamDev* __restrict_
   __shared__ int32_t s_scan[LQ_NW];
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int64_t wu = blockIdx.x;
+  const int64_t wu = (int64_t)blockIdx.x + wu_base;
   const QStreamDev S = streams[find_stream(streams, n_streams, wu)];
   const int chunk = (int)(wu - S.wu_first);
   const DimDev Dt = dims[S.tgt_dim], Ds = dims[S.src_dim];
@@ -219,9 +225,12 @@ lag_moment_kernel(const DimDev* __restrict__ dims, const QStreamDev* __restrict_
   const double inv_h = S.inv_h;
   const int64_t n_src_padded = ((Ds.n + 1) & ~(int64_t)1) + 2;   // set_events pads every type (ctx.cu)
 
+  const bool weighted = WEIGHTED;
   double* s_val = (double*)smem_raw;
   double* s_u = s_val + ucap;
-  double* s_src = s_u + ucap;                       // two buffers of LQ_SMAX + 2
+  double* s_wv = s_u + ucap;                        // pair weights, pair order (weighted streams)
+  double* s_wu = s_wv + (weighted ? ucap : 0);      // pair weights, sorted by bin
+  double* s_src = s_wu + (weighted ? ucap : 0);     // two buffers of LQ_SMAX + 2
   double* s_M = s_src + 2 * (LQ_SMAX + 2);
   uint32_t* s_key = (uint32_t*)(s_M + (size_t)J * LQ_ND);
   int32_t* s_bin = (int32_t*)(s_key + ucap);
@@ -320,6 +329,13 @@ lag_moment_kernel(const DimDev* __restrict__ dims, const QStreamDev* __restrict_
       {
         const int32_t ra = min(max(c0 - pre, 0), cnt), rb = min(max(c0 + n_c - pre, 0), cnt);
         double* dst = s_val + (pre - c0);
+        if (weighted) {
+          // weight(target) x weight(source) per pair (mtlh_exact_estimator.py:838, :896-897)
+          const double w_m = (S.wa_off >= 0 && tid < nt) ? weights[S.wa_off + m0 + tid] : 1.;
+          double* dw = s_wv + (pre - c0);
+          for (int32_t r = ra; r < rb; ++r)
+            dw[r] = S.wb_off >= 0 ? w_m * weights[S.wb_off + lo_abs + r] : w_m;
+        }
         if (staged) {
           int32_t r = ra;
           for (; r + 1 < rb; r += 2) {
@@ -381,7 +397,9 @@ lag_moment_kernel(const DimDev* __restrict__ dims, const QStreamDev* __restrict_
       for (int32_t q = tid; q < n_c; q += LQ_NT) {
         const uint32_t key = s_key[q];
         const int b = (int)(key & 1023u);
-        s_u[(int)my_hist[b] + (int)(key >> 10)] = s_val[q];
+        const int pos = (int)my_hist[b] + (int)(key >> 10);
+        s_u[pos] = s_val[q];
+        if (weighted) s_wu[pos] = s_wv[q];
       }
       __syncthreads();
       // ---- c. moments of every bin: LQ_GS lanes per bin -------------------------------------------
@@ -395,6 +413,23 @@ lag_moment_kernel(const DimDev* __restrict__ dims, const QStreamDev* __restrict_
         for (int d = 0; d < LQ_ND; ++d) acc[d] = 0.;
         // two independent recurrences per iteration (the chain is latency-bound)
         int32_t e = e0 + qg;
+        if (weighted) {
+          for (; e < e1; e += LQ_GS) {
+            const double w = s_wu[e];
+            const double uu = s_u[e] + s_u[e];
+            const double two_u = uu + uu;
+            double tp = 1., tc = uu;
+            acc[0] += w;
+            acc[1] = fma(w, tc, acc[1]);
+#pragma unroll
+            for (int d = 2; d < LQ_ND; ++d) {
+              const double tn = fma(two_u, tc, -tp);
+              tp = tc;
+              tc = tn;
+              acc[d] = fma(w, tn, acc[d]);
+            }
+          }
+        }
         for (; e + LQ_GS < e1; e += 2 * LQ_GS) {
           const double ua = s_u[e] + s_u[e], ub = s_u[e + LQ_GS] + s_u[e + LQ_GS];
           const double two_a = ua + ua, two_b = ub + ub;
@@ -422,7 +457,7 @@ lag_moment_kernel(const DimDev* __restrict__ dims, const QStreamDev* __restrict_
             acc[d] += tn;
           }
         }
-        if (qg == 0) acc[0] = (double)(e1 - e0);   // T_0 = 1: the bin count, exact
+        if (qg == 0 && !weighted) acc[0] = (double)(e1 - e0);   // T_0 = 1: the bin count, exact
         // transposed reduction over the group's lanes: 12 -> 6 -> 3 values per lane on the two
         // widest exchanges, plain butterflies on the rest
         {
@@ -569,7 +604,7 @@ lag_quad_kernel(const QStreamDev* __restrict__ streams, const ItemDev* __restric
 // and every warp walks rows over them.  Each row is owned by one warp of one CTA: plain
 // read-modify-write of its raw components, fixed order.
 #define LB_NT 256
-#define LB_PCAP 2048
+#define LB_PCAP 1536
 struct BoundaryGroupDev {
   int32_t stream, row_first, row_count, pad;
   int64_t m_lo, m_hi;      // boundary targets
@@ -579,9 +614,11 @@ template <int FAMILY>
 __global__ void __launch_bounds__(LB_NT)
 lag_boundary_kernel(const DimDev* __restrict__ dims, const QStreamDev* __restrict__ streams,
                     const BoundaryGroupDev* __restrict__ groups, const ItemDev* __restrict__ rows, double T_f,
-                    double* __restrict__ raw, unsigned long long* __restrict__ counts) {
+                    double* __restrict__ raw, unsigned long long* __restrict__ counts,
+                    const double* __restrict__ weights) {
   __shared__ double s_s[LB_PCAP];
   __shared__ double s_tt[LB_PCAP];
+  __shared__ double s_w[LB_PCAP];
   __shared__ int32_t s_warp[LB_NT / 32];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const BoundaryGroupDev G = groups[blockIdx.x];
@@ -619,9 +656,12 @@ lag_boundary_kernel(const DimDev* __restrict__ dims, const QStreamDev* __restric
     for (int32_t c0 = 0; c0 < total; c0 += LB_PCAP) {
       const int32_t n_c = min(LB_PCAP, total - c0);
       const int32_t ra = min(max(c0 - pre, 0), cnt), rb = min(max(c0 + n_c - pre, 0), cnt);
+      const bool weighted = S.wa_off >= 0 || S.wb_off >= 0;
+      const double w_m = (S.wa_off >= 0 && m < G.m_hi) ? weights[S.wa_off + m] : 1.;
       for (int32_t r = ra; r < rb; ++r) {
         s_s[pre - c0 + r] = t_m - Ds.t[lo + r];
         s_tt[pre - c0 + r] = T_f - t_m;
+        if (weighted) s_w[pre - c0 + r] = S.wb_off >= 0 ? w_m * weights[S.wb_off + lo + r] : w_m;
       }
       __syncthreads();
       for (int row = warp; row < G.row_count; row += LB_NT / 32) {
@@ -640,10 +680,16 @@ lag_boundary_kernel(const DimDev* __restrict__ dims, const QStreamDev* __restric
           const double s = s_s[p];
           if (s < it.s_lo || s > it.s_hi) continue;   // the row's own lag window
           const double t = s_tt[p];
-          if (FAMILY == ITEM_UPS_GAUSS) eval_ups_gauss<false>(KG, mask, t, s, acc);
-          else if (FAMILY == ITEM_UPS_EXP) eval_ups_exp<false>(KE, mask, t, s, acc);
-          else if (FAMILY == ITEM_PHI_EXP) eval_phi_exp(KP, mask, s, acc);
-          else eval_phi_gauss(KP, mask, s, acc);
+          double v[ASLSD_MAX_COMP];
+#pragma unroll
+          for (int c = 0; c < ASLSD_MAX_COMP; ++c) v[c] = 0.;
+          if (FAMILY == ITEM_UPS_GAUSS) eval_ups_gauss<false>(KG, mask, t, s, v);
+          else if (FAMILY == ITEM_UPS_EXP) eval_ups_exp<false>(KE, mask, t, s, v);
+          else if (FAMILY == ITEM_PHI_EXP) eval_phi_exp(KP, mask, s, v);
+          else eval_phi_gauss(KP, mask, s, v);
+          const double w = weighted ? s_w[p] : 1.;
+#pragma unroll
+          for (int c = 0; c < ASLSD_MAX_COMP; ++c) acc[c] = fma(w, v[c], acc[c]);
           ++n_eval;
         }
 #pragma unroll

@@ -77,6 +77,39 @@ def test_mtlh_exact_matches_oracle_medium(engine):
                                    rtol=RTOL, atol=1e-12)
 
 
+def test_weighted_lag_quadrature_agrees_with_item_kernels(engine):
+    """Marked models go through the lag quadrature too (weighted moments): same sums as the
+    per-item pair kernels, and the moment pass really ran."""
+    import aslsd_b200
+    from cases import sbf_gauss_kernel
+    d = 2
+    model = {'d': d, 'kernels': [[sbf_gauss_kernel(3) for _ in range(d)] for _ in range(d)],
+             'impacts': [[{'type': 'linear', 'mark_dim': 1} for _ in range(d)] for _ in range(d)]}
+    rng = np.random.default_rng(9)
+    T_f = 5000.
+    times = [np.sort(rng.uniform(0, T_f, size=n)) for n in (6000, 4500)]
+    marks = [rng.uniform(0, 1, size=(len(t), 1)) for t in times]
+    mirror = aslsd_b200.MTLH(model)
+    path = aslsd_b200.ProcessPath(times, T_f, list_marks=marks, engine=engine)
+    x = np.array([.5, .2, .1, .1, .1, .2, .05, .6, .3])
+    states = []
+    try:
+        for quadrature in (True, False):
+            engine.use_lag_quadrature(quadrature)
+            est = aslsd_b200.MTLHExactEstimB200(engine=engine)
+            est.initialize(0, 3, mirror, path)
+            est.lse_k_estimate(x, compute_diff_f_sum=True)
+            work = engine.last_work_counts()
+            assert (work['moment_pairs'] > 0) == quadrature
+            states.append(_flat_state(est, 'k'))
+    finally:
+        engine.use_lag_quadrature(True)
+    for key in states[0]:
+        ref = states[1][key]
+        np.testing.assert_allclose(states[0][key], ref, rtol=1e-11,
+                                   atol=1e-12 * np.max(np.abs(ref), initial=1.), err_msg=key)
+
+
 def test_unit_weights_reproduce_the_unmarked_sums(engine):
     """aslsd_exact_sums_weighted with all-ones weights equals aslsd_exact_sums (per-item kernels)."""
     from cases import CASES, case_x
