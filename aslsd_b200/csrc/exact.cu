@@ -115,6 +115,17 @@ static void build_stream(const aslsd_ctx* ctx, BatchPlan& B, const std::vector<i
     scale = std::min(scale, row_scale(it));
   }
   if (!(scale > 0.) || !(s_max > 0.) || !std::isfinite(s_max) || !std::isfinite(t_int)) return;
+  // the moment kernel counts the pairs of a tile (LQ_TM targets x their windows) in 32 bits: a
+  // reach that could hold ~2^31 / LQ_TM sources per target (16 x the mean density as margin for
+  // clustering) stays with the per-item kernels, which count in 64 bits
+  {
+    const int64_t n_src = ctx->n_events[first.src_dim];
+    const double* ts = ctx->h_times[first.src_dim];
+    const double span = n_src > 1 ? ts[n_src - 1] - ts[0] : 0.;
+    const double per_target = span > 0. ? std::min<double>((double)n_src, 16. * (double)n_src * s_max / span)
+                                        : (double)n_src;
+    if (per_target * (double)LQ_TM >= 2.0e9) return;
+  }
   const int64_t m_b = interior_end(ctx, first.tgt_dim, first.m_lo, first.m_hi, t_int);
   if (m_b - first.m_lo < LQ_TM / 2) return;   // the per-item kernels take it all
   // bins [j h, (j + 1) h) up to s_max plus a spare one (a lag can exceed s_max by a rounding

@@ -210,7 +210,7 @@ lag_moment_kernel(const DimDev* __restrict__ dims, const QStreamDev* __restrict_
   __shared__ int64_t s_a0[2];        // first source index of each window buffer
   __shared__ int64_t s_next_lo;      // window start of the tile's last target
   __shared__ double s_tlast;         // time of the tile's last target
-  __shared__ int32_t s_warp[LQ_NW];
+  __shared__ int32_t s_warp[LQ_NW];    // pair counts of a tile fit 32 bits (host guard, build_stream)
   __shared__ int32_t s_scan[LQ_NW];
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -619,7 +619,7 @@ lag_boundary_kernel(const DimDev* __restrict__ dims, const QStreamDev* __restric
   __shared__ double s_s[LB_PCAP];
   __shared__ double s_tt[LB_PCAP];
   __shared__ double s_w[LB_PCAP];
-  __shared__ int32_t s_warp[LB_NT / 32];
+  __shared__ int64_t s_warp[LB_NT / 32];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const BoundaryGroupDev G = groups[blockIdx.x];
   const QStreamDev S = streams[G.stream];
@@ -637,25 +637,26 @@ lag_boundary_kernel(const DimDev* __restrict__ dims, const QStreamDev* __restric
       lo = min(dim_lower_bound(Ds, t_m - S.s_max), hi);
       cnt = (int32_t)(hi - lo);
     }
-    int32_t incl = cnt;
+    int64_t incl = cnt;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
-      const int32_t v = __shfl_up_sync(0xffffffffu, incl, o);
+      const int64_t v = __shfl_up_sync(0xffffffffu, incl, o);
       if (lane >= o) incl += v;
     }
     __syncthreads();     // previous tile's readers of s_warp / pair buffers are done
     if (lane == 31) s_warp[warp] = incl;
     __syncthreads();
-    int32_t pre = incl - cnt, total = 0;
+    int64_t pre = incl - cnt, total = 0;
 #pragma unroll
     for (int w = 0; w < LB_NT / 32; ++w) {
-      const int32_t v = s_warp[w];
+      const int64_t v = s_warp[w];
       if (w < warp) pre += v;
       total += v;
     }
-    for (int32_t c0 = 0; c0 < total; c0 += LB_PCAP) {
-      const int32_t n_c = min(LB_PCAP, total - c0);
-      const int32_t ra = min(max(c0 - pre, 0), cnt), rb = min(max(c0 + n_c - pre, 0), cnt);
+    for (int64_t c0 = 0; c0 < total; c0 += LB_PCAP) {
+      const int32_t n_c = (int32_t)min((int64_t)LB_PCAP, total - c0);
+      const int32_t ra = (int32_t)min(max(c0 - pre, (int64_t)0), (int64_t)cnt);
+      const int32_t rb = (int32_t)min(max(c0 + n_c - pre, (int64_t)0), (int64_t)cnt);
       const bool weighted = S.wa_off >= 0 || S.wb_off >= 0;
       const double w_m = (S.wa_off >= 0 && m < G.m_hi) ? weights[S.wa_off + m] : 1.;
       for (int32_t r = ra; r < rb; ++r) {

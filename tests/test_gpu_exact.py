@@ -279,6 +279,31 @@ def test_lag_quadrature_unbalanced_rates_and_many_bins(engine):
         engine.use_lag_quadrature(True)
 
 
+def test_long_memory_kernel_pairs_with_every_earlier_event(engine):
+    """An exponential kernel whose reach exceeds the observation window: every target pairs
+    with every earlier event (2 x 10^8 pairs per stream, thousands of sort chunks per tile, the
+    whole path near T_f in units of the kernel)."""
+    from aslsd_b200.engine import unpack_terms
+    rng = np.random.default_rng(31)
+    T_f = 1000.
+    times = [np.sort(rng.uniform(0, T_f, size=20000))]
+    model = {'d': 1, 'kernels': [[[{'type': 'exp'}, {'type': 'exp'}]]]}
+    engine.set_events(times, T_f)
+    engine.set_model(model)
+    x = np.array([0.5, 0.3, 0.002, 0.2, 1.5])
+    try:
+        engine.use_lag_quadrature(True)
+        a = engine.exact_sums_packed(0, x)
+        engine.use_lag_quadrature(False)
+        b = engine.exact_sums_packed(0, x)
+    finally:
+        engine.use_lag_quadrature(True)
+    fa, dfa = unpack_terms(engine.desc, 0, a)
+    fb, dfb = unpack_terms(engine.desc, 0, b)
+    ref = {'k/%s' % label: val for label, val in iter_sum_entries(fb, dfb)}
+    assert_sums_close(fa, dfa, ref, 'k', rtol=1e-11, atol=1e-9)
+
+
 def test_weight_cache_reuses_the_quadrature(engine):
     """With the weight cache on, a second evaluation on the same events and (beta, delta)
     skips the pass over the event pairs and gives the same sums; a new omega is honoured;
