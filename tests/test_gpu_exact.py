@@ -377,3 +377,54 @@ def test_errors(engine):
         engine.exact_sums(0, [1.0, 0.2])
     with pytest.raises(aslsd_b200.EngineError):
         engine.exact_sums(0, [1.0, 0.2, -1.0])
+
+
+@pytest.fixture(scope='module')
+def c5():
+    """BASELINE.json's full-size configuration: 10-D SBF-Gaussian(10), ~10^7 events."""
+    from aslsd_b200 import simulate
+    return simulate.config_c5(d=10, n_basis=10, T_f=1.1e6, seed=1234)
+
+
+def test_full_size_properties_c5(engine, c5):
+    """Size-independent properties at the full benchmark size (the oracle cannot run there):
+    time-block shards add up to the full sums; phi sums are linear and upsilon sums quadratic in
+    omega; the lag quadrature agrees with the per-item pair kernels on every term of a
+    sub-problem."""
+    from aslsd_b200.distributed import time_block_ranges
+    from aslsd_b200.engine import unpack_terms
+    model, times, T_f, xs = c5
+    d = model['d']
+    engine.set_events(times, T_f)
+    engine.set_model(model)
+    ks = list(range(d))
+    full = engine.exact_sums_batch(ks, xs)
+    # (a) three time blocks add up
+    acc = [np.zeros_like(f) for f in full]
+    for block in time_block_ranges(times, 3):
+        for a, part in zip(acc, engine.exact_sums_batch(ks, xs, ranges=block)):
+            a += part
+    for a, f in zip(acc, full):
+        np.testing.assert_allclose(a, f, rtol=1e-11, atol=1e-9)
+    # (b) scaling in omega (beta, delta are fixed in this model: every kernel parameter is an omega)
+    k = 3
+    f1, _ = unpack_terms(engine.desc, k, full[k])
+    x2 = xs[k].copy()
+    x2[1:] *= 2.0
+    f2, _ = engine.exact_sums(k, x2)
+    for i in range(d):
+        assert abs(f2['phi_%d' % i] - 2 * f1['phi_%d' % i]) <= 1e-11 * abs(f1['phi_%d' % i])
+        assert abs(f2['upsilonzero_%d' % i] - 4 * f1['upsilonzero_%d' % i]) <= 1e-11 * abs(f1['upsilonzero_%d' % i])
+        for j in range(d):
+            name = 'upsilon_%d_%d' % (i, j)
+            assert abs(f2[name] - 4 * f1[name]) <= 1e-11 * abs(f1[name])
+    # (c) quadrature against the per-item pair kernels, one sub-problem, every term
+    try:
+        engine.use_lag_quadrature(False)
+        slow = engine.exact_sums_packed(k, xs[k])
+    finally:
+        engine.use_lag_quadrature(True)
+    fa, dfa = unpack_terms(engine.desc, k, full[k])
+    fb, dfb = unpack_terms(engine.desc, k, slow)
+    ref = {'k/%s' % label: val for label, val in iter_sum_entries(fb, dfb)}
+    assert_sums_close(fa, dfa, ref, 'k', rtol=1e-11, atol=1e-9)
