@@ -28,13 +28,14 @@
 //      tile's last target: no global search, two buffers); per-target source ranges by binary search
 //      in that window; exclusive scan of the pair counts.  A window that does not fit falls back to
 //      bucket-table searches and global reads for that tile;
-//   b. counting sort of the tile's lags by bin, in chunks of `ucap` pairs.  The pairs are enumerated
-//      densely (target-major; an owner table maps pair -> target), so every lane of every warp holds a
-//      pair.  Pass 1: bin and in-bin coordinate of each pair, rank among the equal bins of the warp
-//      step from ballots over the bits of the bin index (match.any measured ~300 cycles: XU pipe),
-//      running count in a warp-private histogram -> (bin, rank in warp) key.  Scan of the histograms.
-//      Pass 2: coordinates move to their sorted slots.  No atomics: the order inside a bin is fixed
-//      and the result is deterministic;
+//   b. counting sort of the tile's lags by bin, in chunks of `ucap` pairs.  Every target's thread
+//      writes the lags of its pairs target-major into shared memory, so that afterwards every lane
+//      of every warp holds a pair.  Pass 1 (two warp steps interleaved): bin and in-bin coordinate
+//      of each pair, rank among the equal bins of the warp step from ballots over the bits of the
+//      bin index (match.any measured ~300 cycles: XU pipe; shared-memory atomics 2 cycles per
+//      lane), running count in a warp-private histogram -> (bin, rank in warp) key.  Scan of the
+//      histograms.  Pass 2: coordinates move to their sorted slots.  No atomics: the order inside a
+//      bin is fixed and the result is deterministic;
 //   c. every group of LQ_GS lanes takes a bin: three-term recurrence, LQ_ND - 1 register accumulators per lane,
 //      transposed shuffle reduction, owner adds into the CTA's moment table;
 //   one partial table per work unit, reduced in fixed order by lag_weights_kernel.
