@@ -428,3 +428,69 @@ def test_full_size_properties_c5(engine, c5):
     fb, dfb = unpack_terms(engine.desc, k, slow)
     ref = {'k/%s' % label: val for label, val in iter_sum_entries(fb, dfb)}
     assert_sums_close(fa, dfa, ref, 'k', rtol=1e-11, atol=1e-9)
+
+
+def _config(name):
+    """Configurations C2-C4 of BASELINE.json / SURVEY 8d at their named sizes."""
+    from aslsd_b200 import simulate
+    exp = lambda: [{'type': 'exp'}]
+    if name == 'C2':      # 2-D exponential, ~10^5 events (fit_exp2d.py:34-51)
+        model = {'d': 2, 'kernels': [[exp(), exp()], [exp(), exp()]]}
+        mu, kp, T_f = [1.5, 1.], [[[.2, 1.], [.6, 1.5]], [[.7, 2.], [.1, 1.3]]], 7.7e3
+    elif name == 'C3':    # 1-D Gaussian, ~10^6 events (fit_gauss1d.py:31-34)
+        model = {'d': 1, 'kernels': [[[{'type': 'gauss'}]]]}
+        mu, kp, T_f = [1.5], [[[.5, .5, 3.]]], 3.33e5
+    else:                 # C4: 1-D SBF-Gaussian(10), ~10^6 events (fit_sbgauss1d10r.py:60-63)
+        model = simulate.sbf_gauss_model(1, 10)
+        mu, kp, T_f = [1.0], [[simulate.random_mixture_weights(10, coeff=0.5)]], 5e5
+    times = simulate.simulate_mhp(model, mu, kp, T_f, seed=1234)
+    d = model['d']
+    rng = np.random.default_rng(12)
+    xs = []
+    for k in range(d):
+        x = np.concatenate([[mu[k]]] + [np.asarray(kp[k][i], float) for i in range(d)])
+        xs.append(x * (1 + 0.1 * rng.uniform(-1, 1, size=len(x))))
+    return model, times, T_f, xs
+
+
+@pytest.mark.parametrize('name', ['C2', 'C3', 'C4'])
+def test_named_configurations_at_full_size(engine, name):
+    """BASELINE.json's other configurations at their named sizes (10^5 - 10^6 events), where the
+    O(N^2) oracle cannot run: the lag quadrature against the per-item pair kernels on every term
+    and derivative, time-block shards adding up, and (C2: "exact vs stratified LSE gradient") the
+    stratified estimate scattering around the exact gradient."""
+    import aslsd_b200
+    from aslsd_b200.distributed import time_block_ranges
+    from aslsd_b200.engine import unpack_terms
+    model, times, T_f, xs = _config(name)
+    d = model['d']
+    assert sum(len(t) for t in times) > (8e4 if name == 'C2' else 8e5)
+    engine.set_events(times, T_f)
+    engine.set_model(model)
+    for k in range(d):
+        fast = engine.exact_sums_packed(k, xs[k])
+        assert engine.last_work_counts()['moment_pairs'] > 0
+        try:
+            engine.use_lag_quadrature(False)
+            slow = engine.exact_sums_packed(k, xs[k])
+        finally:
+            engine.use_lag_quadrature(True)
+        fa, dfa = unpack_terms(engine.desc, k, fast)
+        fb, dfb = unpack_terms(engine.desc, k, slow)
+        ref = {'k/%s' % label: val for label, val in iter_sum_entries(fb, dfb)}
+        assert_sums_close(fa, dfa, ref, 'k', rtol=1e-11, atol=1e-8)
+        acc = np.zeros_like(fast)
+        for block in time_block_ranges(times, 4):
+            acc += engine.exact_sums_packed(k, xs[k], ranges=block)
+        np.testing.assert_allclose(acc, fast, rtol=1e-11, atol=1e-8)
+    if name == 'C2':
+        path = aslsd_b200.ProcessPath(times, T_f, engine=engine)
+        mirror = aslsd_b200.MHP(model)
+        exact = aslsd_b200.MHPExactEstimB200(engine=engine, reference_recombine=False)
+        exact.initialize(0, 2, mirror, path)
+        g_exact = exact.lse_k_grad_estimate(xs[0])
+        rng = np.random.default_rng(2)
+        strat = aslsd_b200.MHPStratEstimB200(engine=engine, reference_adaptive_grad=False)
+        strat.initialize(0, 40, mirror, path)
+        g = np.mean([strat.lse_k_grad_estimate(xs[0], rng=rng, grad_alloc=False) for _ in range(40)], axis=0)
+        assert np.linalg.norm(g - g_exact) <= 0.25 * np.linalg.norm(g_exact)
