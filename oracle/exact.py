@@ -174,8 +174,12 @@ def basis_phi_support(b, v):
 
 
 def basis_ups_support(b1, v1, b2, v2):
-    if b1['type'] == 'exp':
+    if b2['type'] == 'exp':
+        # exp x exp and gauss x exp decay like exp(-beta_2 s)
         return 0., C_EXP / v2[1]
+    if b1['type'] == 'exp':
+        # exp x gauss: the Gaussian factor sits at u + s around delta_2 with u >= 0
+        return 0., max(0., v2[2]) + Z_GAUSS * v2[1]
     sig = np.sqrt(v1[1] ** 2 + v2[1] ** 2)
     dd = v2[2] - v1[2]
     return max(0., dd - Z_GAUSS * sig), dd + Z_GAUSS * sig

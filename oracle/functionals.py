@@ -276,9 +276,98 @@ _PHI = {'exp': exp_phi, 'gauss': gauss_phi}
 _DPHI = {'exp': exp_diff_phi, 'gauss': gauss_diff_phi}
 _PSI = {'exp': exp_psi, 'gauss': gauss_psi}
 _DPSI = {'exp': exp_diff_psi, 'gauss': gauss_diff_psi}
-_UPS = {('exp', 'exp'): exp_exp_upsilon, ('gauss', 'gauss'): gauss_gauss_upsilon}
+# ----------------------------------------------------------------------------
+# mixed families: verbatim, including the overflow guards
+# ----------------------------------------------------------------------------
+def exp_gauss_upsilon(t, s, v1, v2):
+    """basis_kernel_exponential.py:30-39"""
+    w1, b1 = v1[0], v1[1]
+    w2, b2, d2 = v2
+    d_s = d2 - s - b1 * b2 ** 2
+    return (w1 * w2 * b1 * np.exp(-b1 * (d2 - s - 0.5 * b1 * b2 ** 2))
+            * nint(-d_s / b2, (t - d_s) / b2))
+
+
+def exp_gauss_diff_cross(t, s, ix_func, ix, v1, v2):
+    """basis_kernel_exponential.py:89-156"""
+    w1, b1 = v1[0], v1[1]
+    w2, b2, d2 = v2
+    d_s = d2 - s - b1 * b2 ** 2
+    arg = -b1 * (d2 - s - 0.5 * b1 * b2 ** 2)
+    with np.errstate(over='ignore', invalid='ignore'):
+        e = np.exp(arg)
+        J = nint(-d_s / b2, (t - d_s) / b2)
+        if ix_func == 1:
+            if ix == 0:
+                return np.where(arg > 10 ** 2, 0., w2 * b1 * e * J)
+            if ix == 1:
+                cdf_term = (1. / b1 - d2 + s + 0.5 * b1 * b2 ** 2) * J
+                pdf_term = b2 * (npdf((t - d_s) / b2) - npdf(-d_s / b2))
+                return np.where(arg > 10 ** 2, 0., w1 * w2 * b1 * e * (cdf_term + pdf_term))
+        elif ix_func == 2:
+            if ix == 0:
+                return np.where(arg > 10 ** 2, 0., w1 * b1 * e * J)
+            if ix == 1:
+                cdf_term = (b2 * b1 ** 2) * J
+                pdf_term = ((b1 + (d2 - s - t) / b2 ** 2) * npdf((t - d_s) / b2)
+                            - (b1 + (d2 - s) / b2 ** 2) * npdf(-d_s / b2))
+                return np.where(arg > 10 ** 2, 0., w2 * w1 * b1 * e * (cdf_term + pdf_term))
+            if ix == 2:
+                cdf_term = b1 * J
+                pdf_term = (1. / b2) * (npdf((t - d_s) / b2) - npdf(-d_s / b2))
+                return -np.where(arg > 10 ** 2, 0., w2 * w1 * b1 * e * (cdf_term + pdf_term))
+    raise ValueError((ix_func, ix))
+
+
+def gauss_exp_upsilon(t, s, v1, v2):
+    """basis_kernel_gaussian.py:40-50"""
+    w1, b1, d1 = v1
+    w2, b2 = v2[0], v2[1]
+    d_s = d1 - b2 * b1 ** 2
+    return (w1 * w2 * b2 * np.exp(-b2 * (d1 + s - 0.5 * b2 * b1 ** 2))
+            * nint(-d_s / b1, (t - d_s) / b1))
+
+
+def gauss_exp_diff_cross(t, s, ix_func, ix, v1, v2):
+    """basis_kernel_gaussian.py:151-213 (the beta_1 / delta_1 branches shift d_s by s:
+    transcribed as they are)"""
+    w1, b1, d1 = v1
+    w2, b2 = v2[0], v2[1]
+    arg = -b2 * (d1 + s - 0.5 * b2 * b1 ** 2)
+    e = np.exp(arg)
+    if ix_func == 1:
+        if ix == 0:
+            d_s = d1 - b2 * b1 ** 2
+            return np.where(arg > 10 ** 2, 0., w2 * b2 * e * nint(-d_s / b1, (t - d_s) / b1))
+        if ix == 1:
+            d_s = d1 + s - b2 * b1 ** 2
+            cdf_term = b1 * (b2 ** 2) * nint(-d_s / b1, (t - d_s) / b1)
+            pdf_term = ((b2 - ((t - d1) / b1 ** 2)) * npdf((t - d_s) / b1)
+                        - (b2 + (d1 / b1 ** 2)) * npdf(-d_s / b1))
+            return w1 * w2 * b2 * e * (cdf_term + pdf_term)
+        if ix == 2:
+            d_s = (d1 + s - b2 * b1 ** 2) / b1
+            cdf_term = -b2 * nint(-d_s, t / b1 - d_s)
+            pdf_term = (-1. / b1) * (npdf(t / b1 - d_s) - npdf(-d_s))
+            return w1 * w2 * b2 * e * (cdf_term + pdf_term)
+    elif ix_func == 2:
+        if ix == 0:
+            d_s = d1 - b2 * b1 ** 2
+            return w1 * b2 * e * nint(-d_s / b1, (t - d_s) / b1)
+        if ix == 1:
+            d_s = (d1 - b2 * b1 ** 2) / b1
+            cdf_term = ((1. / b2) - d1 - s + 0.5 * b2 * b1 ** 2) * nint(-d_s, (t / b1) - d_s)
+            pdf_term = b1 * (npdf((t / b1) - d_s) - npdf(-d_s))
+            return w2 * w1 * b2 * e * (cdf_term + pdf_term)
+    raise ValueError((ix_func, ix))
+
+
+_UPS = {('exp', 'exp'): exp_exp_upsilon, ('gauss', 'gauss'): gauss_gauss_upsilon,
+        ('exp', 'gauss'): exp_gauss_upsilon, ('gauss', 'exp'): gauss_exp_upsilon}
 _DCROSS = {('exp', 'exp'): exp_exp_diff_cross,
-           ('gauss', 'gauss'): gauss_gauss_diff_cross}
+           ('gauss', 'gauss'): gauss_gauss_diff_cross,
+           ('exp', 'gauss'): exp_gauss_diff_cross,
+           ('gauss', 'exp'): gauss_exp_diff_cross}
 _DSIM = {'exp': exp_diff_sim, 'gauss': gauss_diff_sim}
 
 

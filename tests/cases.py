@@ -54,6 +54,12 @@ CASES = {
     'gauss1d2b': (square(1, lambda: [{'type': 'gauss', 'fixed': {2: 1.0}},
                                      {'type': 'gauss', 'fixed': {1: 0.4}}]), [.7],
                   [[[.2, .5, .25, 2.5]]], 120.),
+    # mixed families inside one kernel (exponential + Gaussian basis): upsilon of unlike pairs
+    # (basis_kernel_exponential.py:30-39, :89-156; basis_kernel_gaussian.py:40-50, :151-213)
+    'mix1d': (square(1, lambda: [{'type': 'exp'}, {'type': 'gauss'}]), [.8],
+              [[[.2, 1.2, .25, .5, 2.]]], 100.),
+    'mix2d': (square(2, lambda: [{'type': 'exp'}, {'type': 'gauss', 'fixed': {1: 0.6}}]), [.6, .5],
+              [[[.15, 1., .2, 1.5], [.1, 2., .15, 1.]], [[.2, .8, .1, 2.5], [.05, 1.5, .2, .5]]], 70.),
 }
 
 
