@@ -179,6 +179,118 @@ __device__ __forceinline__ void eval_ups_exp(const UpsExpConst& K, int mask, dou
   }
 }
 
+// Mixed pairs.  be: beta of the exponential basis; bg, dg: beta, delta of the Gaussian one.
+//   exp x gauss  basis_kernel_exponential.py:30-39 (upsilon), :89-156 (diff_cross_upsilon)
+//   gauss x exp  basis_kernel_gaussian.py:40-50 (upsilon), :151-213 (diff_cross_upsilon)
+// The exponential's beta multiplies the value on the host (like pr above) and the derivative
+// components here.  Slot C_SW carries the value under the reference's overflow guard
+// (np.where(arg > 10**2, 0., ...)), which its omega derivatives apply and its value does not.
+struct UpsMixConst {
+  double be, bg, dg, inv_bg, inv_bg2, bbg2, half_bbg2;
+  __device__ void init_eg(const ItemDev& it) { set(it.b1, it.b2, it.d2); }
+  __device__ void init_ge(const ItemDev& it) { set(it.b2, it.b1, it.d1); }
+  __device__ void set(double be_, double bg_, double dg_) {
+    be = be_; bg = bg_; dg = dg_;
+    inv_bg = 1. / bg;
+    inv_bg2 = 1. / (bg * bg);
+    bbg2 = be * bg * bg;
+    half_bbg2 = 0.5 * be * bg * bg;
+  }
+};
+
+// upsilon, exponential (basis 1) x Gaussian (basis 2).  acc slots: C_G, C_B1, C_B2, C_D2, C_SW.
+template <bool INTERIOR>
+__device__ __forceinline__ void eval_ups_eg(const UpsMixConst& K, int mask, double t, double s, double* acc) {
+  const double d_s = K.dg - s - K.bbg2;
+  const double arg = -K.be * (K.dg - s - K.half_bbg2);
+  const double e = exp(arg);
+  const double lo = -d_s * K.inv_bg;
+  double hi = 0., J;
+  if (INTERIOR) {
+    J = 1.0 - normcdf(lo);
+  } else {
+    hi = (t - d_s) * K.inv_bg;
+    J = normcdf(hi) - normcdf(lo);
+  }
+  acc[C_G] += e * J;
+  if (!(mask & (MASK(C_B1) | MASK(C_B2) | MASK(C_D2) | MASK(C_SW)))) return;
+  if (arg > 100.) return;   // every derivative branch is zeroed there
+  if (mask & MASK(C_SW)) acc[C_SW] += e * J;
+  if (!(mask & (MASK(C_B1) | MASK(C_B2) | MASK(C_D2)))) return;
+  const double p_lo = std_pdf(lo);
+  const double p_hi = INTERIOR ? 0. : std_pdf(hi);
+  const double be_e = K.be * e;
+  if (mask & MASK(C_B1)) {
+    const double cdf_term = (1. / K.be - K.dg + s + K.half_bbg2) * J;
+    const double pdf_term = K.bg * (p_hi - p_lo);
+    acc[C_B1] += be_e * (cdf_term + pdf_term);
+  }
+  if (mask & MASK(C_B2)) {
+    const double cdf_term = (K.bg * K.be * K.be) * J;
+    double pdf_term = -(K.be + (K.dg - s) * K.inv_bg2) * p_lo;
+    if (!INTERIOR) pdf_term += (K.be + (K.dg - s - t) * K.inv_bg2) * p_hi;
+    acc[C_B2] += be_e * (cdf_term + pdf_term);
+  }
+  if (mask & MASK(C_D2)) {
+    const double cdf_term = K.be * J;
+    const double pdf_term = K.inv_bg * (p_hi - p_lo);
+    acc[C_D2] -= be_e * (cdf_term + pdf_term);
+  }
+}
+
+// upsilon, Gaussian (basis 1) x exponential (basis 2).  acc slots: C_G, C_B1, C_D1, C_B2, C_SW.
+// The beta_1 / delta_1 branches of the reference shift the integration limits by s
+// (basis_kernel_gaussian.py:176, :186); transcribed as they are.
+template <bool INTERIOR>
+__device__ __forceinline__ void eval_ups_ge(const UpsMixConst& K, int mask, double t, double s, double* acc) {
+  const double d0 = K.dg - K.bbg2;
+  const double arg = -K.be * (K.dg + s - K.half_bbg2);
+  const double e = exp(arg);
+  const double lo = -d0 * K.inv_bg;
+  double hi = 0., J;
+  if (INTERIOR) {
+    J = 1.0 - normcdf(lo);
+  } else {
+    hi = (t - d0) * K.inv_bg;
+    J = normcdf(hi) - normcdf(lo);
+  }
+  acc[C_G] += e * J;
+  if ((mask & MASK(C_SW)) && !(arg > 100.)) acc[C_SW] += e * J;
+  if (!(mask & (MASK(C_B1) | MASK(C_D1) | MASK(C_B2)))) return;
+  const double be_e = K.be * e;
+  if (mask & (MASK(C_B1) | MASK(C_D1))) {
+    const double d1s = K.dg + s - K.bbg2;
+    const double lo1 = -d1s * K.inv_bg;
+    const double p_lo1 = std_pdf(lo1);
+    double hi1 = 0., J1, p_hi1 = 0.;
+    if (INTERIOR) {
+      J1 = 1.0 - normcdf(lo1);
+    } else {
+      hi1 = (t - d1s) * K.inv_bg;
+      J1 = normcdf(hi1) - normcdf(lo1);
+      p_hi1 = std_pdf(hi1);
+    }
+    if (mask & MASK(C_B1)) {
+      const double cdf_term = K.bg * (K.be * K.be) * J1;
+      double pdf_term = -(K.be + K.dg * K.inv_bg2) * p_lo1;
+      if (!INTERIOR) pdf_term += (K.be - (t - K.dg) * K.inv_bg2) * p_hi1;
+      acc[C_B1] += be_e * (cdf_term + pdf_term);
+    }
+    if (mask & MASK(C_D1)) {
+      const double cdf_term = -K.be * J1;
+      const double pdf_term = -K.inv_bg * (p_hi1 - p_lo1);
+      acc[C_D1] += be_e * (cdf_term + pdf_term);
+    }
+  }
+  if (mask & MASK(C_B2)) {
+    const double p_lo = std_pdf(lo);
+    const double p_hi = INTERIOR ? 0. : std_pdf(hi);
+    const double cdf_term = (1. / K.be - K.dg - s + K.half_bbg2) * J;
+    const double pdf_term = K.bg * (p_hi - p_lo);
+    acc[C_B2] += be_e * (cdf_term + pdf_term);
+  }
+}
+
 // phi.  exponential: slots 0 = e^{-beta s}, 1 = e^{-beta s} (1 - beta s)
 //       gaussian   : slots 0 = pdf, 1 = pdf (z^2 - 1), 2 = pdf (s - delta) / beta^2
 struct PhiConst {

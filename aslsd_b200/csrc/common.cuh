@@ -63,12 +63,25 @@ enum {
   ITEM_PSI_EXP = 4,
   ITEM_PSI_GAUSS = 5,
   ITEM_UPS0_EXP = 6,   // upsilon at lag zero: one evaluation per target
-  ITEM_UPS0_GAUSS = 7
+  ITEM_UPS0_GAUSS = 7,
+  // mixed pairs: basis 1 exponential x basis 2 Gaussian (EG) and the converse (GE)
+  ITEM_UPS_EG = 8,
+  ITEM_UPS_GE = 9,
+  ITEM_UPS0_EG = 10,
+  ITEM_UPS0_GE = 11,
+  ITEM_N_FAMILIES = 12
 };
+
+__host__ __device__ inline bool item_pair_family(int f) {
+  return f == ITEM_UPS_EXP || f == ITEM_UPS_GAUSS || f == ITEM_PHI_EXP || f == ITEM_PHI_GAUSS ||
+         f == ITEM_UPS_EG || f == ITEM_UPS_GE;
+}
 
 // Raw component slots.
 //   upsilon exp  : 0 G, 1 B1, 2 B2, 5 SW, 6 SB
 //   upsilon gauss: 0 G, 1 B1, 2 D1, 3 B2, 4 D2, 5 SW, 6 SB, 7 SD
+//   upsilon exp x gauss: 0 G, 1 B1, 3 B2, 4 D2, 5 G with the reference's overflow guard
+//   upsilon gauss x exp: 0 G, 1 B1, 2 D1, 3 B2, 5 G with the reference's overflow guard
 //   phi exp      : 0 E0, 1 EB            phi gauss: 0 P, 1 PB, 2 PD
 //   psi exp      : 0 I, 1 IB             psi gauss: 0 I, 1 IB, 2 ID
 enum { C_G = 0, C_B1 = 1, C_D1 = 2, C_B2 = 3, C_D2 = 4, C_SW = 5, C_SB = 6, C_SD = 7 };
@@ -155,7 +168,7 @@ struct aslsd_ctx {
   // evaluation counters of the last exact-sum call (per item, on the device)
   int64_t last_n_wu = 0;
   int last_n_items = 0;
-  int last_fam_first[8] = {0}, last_fam_count[8] = {0};
+  int last_fam_first[ITEM_N_FAMILIES] = {0}, last_fam_count[ITEM_N_FAMILIES] = {0};
 };
 
 struct DimDev {

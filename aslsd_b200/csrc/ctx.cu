@@ -326,10 +326,6 @@ extern "C" int aslsd_set_model(aslsd_ctx* ctx, int d, const int32_t* n_basis, co
       if (K.bases[r].type != KU.bases[r].type || K.bases[r].free_mask != KU.bases[r].free_mask)
         return aslsd_fail(ctx, ASLSD_ERR_UNSUPPORTED,
                           "set_model: all kernels must have the same basis structure");
-      for (size_t q = 0; q < KU.bases.size(); ++q)
-        if (K.bases[r].type != KU.bases[q].type)
-          return aslsd_fail(ctx, ASLSD_ERR_UNSUPPORTED,
-                            "set_model: mixed exponential x gaussian interactions are not supported");
     }
   }
   ctx->kernels.swap(ks);

@@ -43,15 +43,15 @@ struct BatchPlan {
   std::vector<int64_t> lo, hi;                  // target block per dimension (build_work)
   // per-item kernels
   std::vector<ItemDev> items;                   // device items, grouped by family
-  int fam_first[8], fam_count[8];
-  int64_t fam_wu_first[8], fam_wu_count[8];
+  int fam_first[ITEM_N_FAMILIES], fam_count[ITEM_N_FAMILIES];
+  int64_t fam_wu_first[ITEM_N_FAMILIES], fam_wu_count[ITEM_N_FAMILIES];
   int64_t n_wu = 0;
   // lag quadrature
   std::vector<QStreamDev> qstreams;
   std::vector<ItemDev> qrows;                   // grouped by family; wu_first = stream index
-  int qfam_first[8], qfam_count[8];
+  int qfam_first[ITEM_N_FAMILIES], qfam_count[ITEM_N_FAMILIES];
   std::vector<BoundaryGroupDev> bgroups;        // targets near T_f of the quadrature rows, by family
-  int bfam_first[8], bfam_count[8];
+  int bfam_first[ITEM_N_FAMILIES], bfam_count[ITEM_N_FAMILIES];
   int64_t n_wu_q = 0, n_wu_q_plain = 0, n_q_partials = 0, n_q_weights = 0, n_q_evals = 0;
   int q_jmax = 0;
   size_t q_smem = 0;
@@ -77,9 +77,7 @@ static int64_t interior_end(const aslsd_ctx* ctx, int dim, int64_t m_lo, int64_t
   return lo;
 }
 
-static bool is_pair_family(int f) {
-  return f == ITEM_UPS_EXP || f == ITEM_UPS_GAUSS || f == ITEM_PHI_EXP || f == ITEM_PHI_GAUSS;
-}
+static bool is_pair_family(int f) { return item_pair_family(f); }
 
 // Smallest length scale (in the lag) of the functions a row sums: the bin width of
 // its stream is a fixed fraction of it (lag_quadrature.cuh).
@@ -89,6 +87,10 @@ static double row_scale(const ItemDev& it) {
     case ITEM_PHI_EXP: return 1. / it.b1;
     case ITEM_PHI_GAUSS: return it.b1;
     case ITEM_UPS_EXP: return 1. / (own ? std::max(it.b2, it.bo) : it.b2);
+    // e^{beta1 s} against a Gaussian tail of std beta2 / e^{-beta2 s} against limits of slope 1 / beta1
+    // (0.7: the product of the two factors varies faster than either one)
+    case ITEM_UPS_EG: return 0.7 * std::min(1. / it.b1, it.b2);
+    case ITEM_UPS_GE: return 0.7 * std::min(1. / it.b2, it.b1);
     default: {
       // P(s): std sigma; lower limit of the integral: slope beta1 / (beta2 sigma) in s;
       // own-basis forms: std sqrt(2) beta
@@ -104,7 +106,7 @@ static double row_scale(const ItemDev& it) {
 // quadrature stream, if the geometry allows it.
 static void build_stream(const aslsd_ctx* ctx, BatchPlan& B, const std::vector<int64_t>& group,
                          std::vector<bool>& fast, std::vector<int64_t>& boundary_from,
-                         std::vector<ItemDev> qfam[8]) {
+                         std::vector<ItemDev> qfam[ITEM_N_FAMILIES]) {
   const ItemDev first = B.rows[group[0]];
   double t_int = 0., s_max = 0., scale = 1e300;
   for (int64_t r : group) {
@@ -229,7 +231,7 @@ static int build_work(aslsd_ctx* ctx, const int64_t* m_lo, const int64_t* m_hi, 
   const size_t n_rows = B.rows.size();
   std::vector<bool> fast(n_rows, false);
   std::vector<int64_t> boundary_from(n_rows, 0);
-  std::vector<ItemDev> qfam[8];
+  std::vector<ItemDev> qfam[ITEM_N_FAMILIES];
   if (ctx->use_quadrature) {
     // group the pair rows by (streams, target block), in row order
     // (marked models: also by the pair of weight vectors - weighted moments)
@@ -252,7 +254,7 @@ static int build_work(aslsd_ctx* ctx, const int64_t* m_lo, const int64_t* m_hi, 
         if ((key[4] >= 0 || key[5] >= 0) == (pass == 1))
           build_stream(ctx, B, groups[key], fast, boundary_from, qfam);
   }
-  for (int f = 0; f < 8; ++f) {
+  for (int f = 0; f < ITEM_N_FAMILIES; ++f) {
     B.qfam_first[f] = (int)B.qrows.size();
     B.qfam_count[f] = (int)qfam[f].size();
     B.bfam_first[f] = (int)B.bgroups.size();
@@ -283,7 +285,7 @@ static int build_work(aslsd_ctx* ctx, const int64_t* m_lo, const int64_t* m_hi, 
     B.qrows.insert(B.qrows.end(), qfam[f].begin(), qfam[f].end());
   }
   // ---- per-item kernels: rows outside the quadrature entirely, the others beyond the interior ----
-  std::vector<ItemDev> fam_items[8];
+  std::vector<ItemDev> fam_items[ITEM_N_FAMILIES];
   for (size_t r = 0; r < n_rows; ++r) {
     ItemDev it = B.rows[r];
     it.dst_row = (int64_t)r;
@@ -299,7 +301,7 @@ static int build_work(aslsd_ctx* ctx, const int64_t* m_lo, const int64_t* m_hi, 
   }
   int base = 0;
   int64_t wu = 0;
-  for (int f = 0; f < 8; ++f) {
+  for (int f = 0; f < ITEM_N_FAMILIES; ++f) {
     B.fam_first[f] = base;
     B.fam_count[f] = (int)fam_items[f].size();
     B.fam_wu_first[f] = wu;
@@ -457,7 +459,7 @@ static int run_batch(aslsd_ctx* ctx, BatchPlan& B, double* raw_device) {
   ctx->last_n_wu = B.n_wu;
   ctx->last_n_items = (int)n_items;
   ctx->last_n_wu_q = B.n_wu_q;
-  for (int f = 0; f < 8; ++f) { ctx->last_fam_first[f] = B.fam_first[f]; ctx->last_fam_count[f] = B.fam_count[f]; }
+  for (int f = 0; f < ITEM_N_FAMILIES; ++f) { ctx->last_fam_first[f] = B.fam_first[f]; ctx->last_fam_count[f] = B.fam_count[f]; }
   ctx->last_work[3] = B.n_q_evals;
   ctx->last_work[4] = (int64_t)B.qstreams.size();
   ctx->last_work[5] = B.n_q_weights / LQ_ND;
@@ -545,10 +547,14 @@ static int run_batch(aslsd_ctx* ctx, BatchPlan& B, double* raw_device) {
   }
   launch_pair<ITEM_UPS_GAUSS>(ctx, B, d_items);
   launch_pair<ITEM_UPS_EXP>(ctx, B, d_items);
+  launch_pair<ITEM_UPS_EG>(ctx, B, d_items);
+  launch_pair<ITEM_UPS_GE>(ctx, B, d_items);
   launch_pair<ITEM_PHI_GAUSS>(ctx, B, d_items);
   launch_pair<ITEM_PHI_EXP>(ctx, B, d_items);
   launch_single<ITEM_UPS0_GAUSS>(ctx, B, d_items);
   launch_single<ITEM_UPS0_EXP>(ctx, B, d_items);
+  launch_single<ITEM_UPS0_EG>(ctx, B, d_items);
+  launch_single<ITEM_UPS0_GE>(ctx, B, d_items);
   launch_single<ITEM_PSI_GAUSS>(ctx, B, d_items);
   launch_single<ITEM_PSI_EXP>(ctx, B, d_items);
   if (n_items) {
@@ -561,11 +567,15 @@ static int run_batch(aslsd_ctx* ctx, BatchPlan& B, double* raw_device) {
   if (quad) {
     launch_quad<ITEM_UPS_GAUSS>(ctx, B, d_streams, d_qrows, raw_device);
     launch_quad<ITEM_UPS_EXP>(ctx, B, d_streams, d_qrows, raw_device);
+    launch_quad<ITEM_UPS_EG>(ctx, B, d_streams, d_qrows, raw_device);
+    launch_quad<ITEM_UPS_GE>(ctx, B, d_streams, d_qrows, raw_device);
     launch_quad<ITEM_PHI_GAUSS>(ctx, B, d_streams, d_qrows, raw_device);
     launch_quad<ITEM_PHI_EXP>(ctx, B, d_streams, d_qrows, raw_device);
     unsigned long long* d_bcnt = ctx->d_counts + B.n_wu + n_items + B.n_wu_q;
     launch_boundary<ITEM_UPS_GAUSS>(ctx, B, d_streams, d_groups, d_qrows, raw_device, d_bcnt);
     launch_boundary<ITEM_UPS_EXP>(ctx, B, d_streams, d_groups, d_qrows, raw_device, d_bcnt);
+    launch_boundary<ITEM_UPS_EG>(ctx, B, d_streams, d_groups, d_qrows, raw_device, d_bcnt);
+    launch_boundary<ITEM_UPS_GE>(ctx, B, d_streams, d_groups, d_qrows, raw_device, d_bcnt);
     launch_boundary<ITEM_PHI_GAUSS>(ctx, B, d_streams, d_groups, d_qrows, raw_device, d_bcnt);
     launch_boundary<ITEM_PHI_EXP>(ctx, B, d_streams, d_groups, d_qrows, raw_device, d_bcnt);
   }
@@ -831,7 +841,7 @@ extern "C" int aslsd_last_work_counts(aslsd_ctx* ctx, int64_t* counts, int n) {
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
   }
   int64_t pe = 0, se = 0;
-  for (int f = 0; f < 8; ++f) {
+  for (int f = 0; f < ITEM_N_FAMILIES; ++f) {
     const bool pair = is_pair_family(f);
     for (int x = 0; x < ctx->last_fam_count[f]; ++x)
       (pair ? pe : se) += (int64_t)h[(size_t)ctx->last_n_wu + ctx->last_fam_first[f] + x];

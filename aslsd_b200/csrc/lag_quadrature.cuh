@@ -541,7 +541,7 @@ lag_weights_kernel(const QStreamDev* __restrict__ streams, const double* __restr
 
 // Rows: the closed form of every row at the nodes of its stream, dotted with the weights.
 // One CTA per row; the row's ItemDev carries the stream index in wu_first.
-// FAMILY: ITEM_UPS_EXP, ITEM_UPS_GAUSS, ITEM_PHI_EXP, ITEM_PHI_GAUSS
+// FAMILY: ITEM_UPS_EXP, ITEM_UPS_GAUSS, ITEM_UPS_EG, ITEM_UPS_GE, ITEM_PHI_EXP, ITEM_PHI_GAUSS
 #define LQ_QT 128
 template <int FAMILY>
 __global__ void __launch_bounds__(LQ_QT)
@@ -554,8 +554,11 @@ lag_quad_kernel(const QStreamDev* __restrict__ streams, const ItemDev* __restric
   UpsGaussConst KG;
   UpsExpConst KE;
   PhiConst KP;
+  UpsMixConst KM;
   if (FAMILY == ITEM_UPS_GAUSS) KG.init(it);
   if (FAMILY == ITEM_UPS_EXP) KE.init(it);
+  if (FAMILY == ITEM_UPS_EG) KM.init_eg(it);
+  if (FAMILY == ITEM_UPS_GE) KM.init_ge(it);
   if (FAMILY == ITEM_PHI_EXP || FAMILY == ITEM_PHI_GAUSS) KP.init(it);
   // bins that meet the row's lag window
   int j_lo = (int)floor(it.s_lo * S.inv_h) - 1, j_hi = (int)floor(it.s_hi * S.inv_h) + 1;
@@ -575,6 +578,8 @@ lag_quad_kernel(const QStreamDev* __restrict__ streams, const ItemDev* __restric
     for (int c = 0; c < ASLSD_MAX_COMP; ++c) v[c] = 0.;
     if (FAMILY == ITEM_UPS_GAUSS) eval_ups_gauss<true>(KG, mask, 0., s, v);
     else if (FAMILY == ITEM_UPS_EXP) eval_ups_exp<true>(KE, mask, 0., s, v);
+    else if (FAMILY == ITEM_UPS_EG) eval_ups_eg<true>(KM, mask, 0., s, v);
+    else if (FAMILY == ITEM_UPS_GE) eval_ups_ge<true>(KM, mask, 0., s, v);
     else if (FAMILY == ITEM_PHI_EXP) eval_phi_exp(KP, mask, s, v);
     else eval_phi_gauss(KP, mask, s, v);
 #pragma unroll
@@ -672,8 +677,11 @@ lag_boundary_kernel(const DimDev* __restrict__ dims, const QStreamDev* __restric
         UpsGaussConst KG;
         UpsExpConst KE;
         PhiConst KP;
+        UpsMixConst KM;
         if (FAMILY == ITEM_UPS_GAUSS) KG.init(it);
         if (FAMILY == ITEM_UPS_EXP) KE.init(it);
+        if (FAMILY == ITEM_UPS_EG) KM.init_eg(it);
+        if (FAMILY == ITEM_UPS_GE) KM.init_ge(it);
         if (FAMILY == ITEM_PHI_EXP || FAMILY == ITEM_PHI_GAUSS) KP.init(it);
         double acc[ASLSD_MAX_COMP];
 #pragma unroll
@@ -687,6 +695,8 @@ lag_boundary_kernel(const DimDev* __restrict__ dims, const QStreamDev* __restric
           for (int c = 0; c < ASLSD_MAX_COMP; ++c) v[c] = 0.;
           if (FAMILY == ITEM_UPS_GAUSS) eval_ups_gauss<false>(KG, mask, t, s, v);
           else if (FAMILY == ITEM_UPS_EXP) eval_ups_exp<false>(KE, mask, t, s, v);
+          else if (FAMILY == ITEM_UPS_EG) eval_ups_eg<false>(KM, mask, t, s, v);
+          else if (FAMILY == ITEM_UPS_GE) eval_ups_ge<false>(KM, mask, t, s, v);
           else if (FAMILY == ITEM_PHI_EXP) eval_phi_exp(KP, mask, s, v);
           else eval_phi_gauss(KP, mask, s, v);
           const double w = weighted ? s_w[p] : 1.;

@@ -90,7 +90,7 @@ __device__ __forceinline__ void block_reduce_store(double* acc, unsigned long lo
   }
 }
 
-// FAMILY: ITEM_UPS_EXP, ITEM_UPS_GAUSS, ITEM_PHI_EXP, ITEM_PHI_GAUSS
+// FAMILY: ITEM_UPS_EXP, ITEM_UPS_GAUSS, ITEM_UPS_EG, ITEM_UPS_GE, ITEM_PHI_EXP, ITEM_PHI_GAUSS
 template <int FAMILY>
 __global__ void __launch_bounds__(PAIR_NT, 2)
 pair_kernel(const DimDev* __restrict__ dims, const ItemDev* __restrict__ items, int n_items, double T_f,
@@ -120,8 +120,11 @@ pair_kernel(const DimDev* __restrict__ dims, const ItemDev* __restrict__ items, 
   UpsGaussConst KG;
   UpsExpConst KE;
   PhiConst KP;
+  UpsMixConst KM;
   if (FAMILY == ITEM_UPS_GAUSS) KG.init(it);
   if (FAMILY == ITEM_UPS_EXP) KE.init(it);
+  if (FAMILY == ITEM_UPS_EG) KM.init_eg(it);
+  if (FAMILY == ITEM_UPS_GE) KM.init_ge(it);
   if (FAMILY == ITEM_PHI_EXP || FAMILY == ITEM_PHI_GAUSS) KP.init(it);
 
   double acc[ASLSD_MAX_COMP];
@@ -222,6 +225,12 @@ pair_kernel(const DimDev* __restrict__ dims, const ItemDev* __restrict__ items, 
       } else if (FAMILY == ITEM_UPS_EXP) {
         if (interior) eval_ups_exp<true>(KE, mask, 0., s, v);
         else eval_ups_exp<false>(KE, mask, T_f - tm, s, v);
+      } else if (FAMILY == ITEM_UPS_EG) {
+        if (interior) eval_ups_eg<true>(KM, mask, 0., s, v);
+        else eval_ups_eg<false>(KM, mask, T_f - tm, s, v);
+      } else if (FAMILY == ITEM_UPS_GE) {
+        if (interior) eval_ups_ge<true>(KM, mask, 0., s, v);
+        else eval_ups_ge<false>(KM, mask, T_f - tm, s, v);
       } else if (FAMILY == ITEM_PHI_EXP) {
         eval_phi_exp(KP, mask, s, v);
       } else {
@@ -238,7 +247,7 @@ pair_kernel(const DimDev* __restrict__ dims, const ItemDev* __restrict__ items, 
 }
 
 // Single-index sums: psi_i (one evaluation per target) and upsilon at lag zero.
-// FAMILY: ITEM_PSI_EXP, ITEM_PSI_GAUSS, ITEM_UPS0_EXP, ITEM_UPS0_GAUSS
+// FAMILY: ITEM_PSI_EXP, ITEM_PSI_GAUSS, ITEM_UPS0_EXP, ITEM_UPS0_GAUSS, ITEM_UPS0_EG, ITEM_UPS0_GE
 template <int FAMILY>
 __global__ void __launch_bounds__(PAIR_NT, 2)
 single_kernel(const DimDev* __restrict__ dims, const ItemDev* __restrict__ items, int n_items, double T_f,
@@ -257,8 +266,11 @@ single_kernel(const DimDev* __restrict__ dims, const ItemDev* __restrict__ items
   UpsGaussConst KG;
   UpsExpConst KE;
   PhiConst KP;
+  UpsMixConst KM;
   if (FAMILY == ITEM_UPS0_GAUSS) KG.init(it);
   if (FAMILY == ITEM_UPS0_EXP) KE.init(it);
+  if (FAMILY == ITEM_UPS0_EG) KM.init_eg(it);
+  if (FAMILY == ITEM_UPS0_GE) KM.init_ge(it);
   if (FAMILY == ITEM_PSI_EXP || FAMILY == ITEM_PSI_GAUSS) KP.init(it);
   double acc[ASLSD_MAX_COMP];
 #pragma unroll
@@ -277,6 +289,12 @@ single_kernel(const DimDev* __restrict__ dims, const ItemDev* __restrict__ items
     } else if (FAMILY == ITEM_UPS0_EXP) {
       if (interior) eval_ups_exp<true>(KE, mask, 0., 0., v);
       else eval_ups_exp<false>(KE, mask, t, 0., v);
+    } else if (FAMILY == ITEM_UPS0_EG) {
+      if (interior) eval_ups_eg<true>(KM, mask, 0., 0., v);
+      else eval_ups_eg<false>(KM, mask, t, 0., v);
+    } else if (FAMILY == ITEM_UPS0_GE) {
+      if (interior) eval_ups_ge<true>(KM, mask, 0., 0., v);
+      else eval_ups_ge<false>(KM, mask, t, 0., v);
     } else if (FAMILY == ITEM_PSI_EXP) {
       eval_psi_exp(KP, mask, t, v);
     } else {
@@ -295,6 +313,8 @@ single_kernel(const DimDev* __restrict__ dims, const ItemDev* __restrict__ items
     const double t_far = 1e300;
     if (FAMILY == ITEM_UPS0_GAUSS) eval_ups_gauss<true>(KG, mask, 0., 0., v);
     else if (FAMILY == ITEM_UPS0_EXP) eval_ups_exp<true>(KE, mask, 0., 0., v);
+    else if (FAMILY == ITEM_UPS0_EG) eval_ups_eg<true>(KM, mask, 0., 0., v);
+    else if (FAMILY == ITEM_UPS0_GE) eval_ups_ge<true>(KM, mask, 0., 0., v);
     else if (FAMILY == ITEM_PSI_EXP) eval_psi_exp(KP, mask, t_far, v);
     else eval_psi_gauss(KP, mask, t_far, v);
 #pragma unroll

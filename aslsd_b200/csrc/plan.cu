@@ -37,12 +37,14 @@ static bool vars_equal(const std::vector<Vars>& a, const std::vector<Vars>& b) {
   return true;
 }
 
-static void ups_window(int type, const Vars& v1, const Vars& v2, double* s_lo, double* s_hi, double* t_int) {
-  if (type == ASLSD_BASIS_EXPONENTIAL) {
+static void ups_window(int type1, int type2, const Vars& v1, const Vars& v2, double* s_lo, double* s_hi,
+                       double* t_int) {
+  const bool e1 = type1 == ASLSD_BASIS_EXPONENTIAL, e2 = type2 == ASLSD_BASIS_EXPONENTIAL;
+  if (e1 && e2) {
     *s_lo = 0.;
     *s_hi = C_EXP / v2[1];
     *t_int = C_INTERIOR / (v1[1] + v2[1]);
-  } else {
+  } else if (!e1 && !e2) {
     const double sig = std::sqrt(v1[1] * v1[1] + v2[1] * v2[1]);
     const double dd = v2[2] - v1[2];
     *s_lo = std::max(0., dd - Z_GAUSS * sig);
@@ -50,6 +52,19 @@ static void ups_window(int type, const Vars& v1, const Vars& v2, double* s_lo, d
     const double bs = v1[1] * v2[1] / sig;
     const double r1 = v2[1] * v2[1] / (sig * sig), r2 = v1[1] * v1[1] / (sig * sig);
     *t_int = X_INTERIOR * bs + r1 * v1[2] + r2 * std::max(v2[2], 0.);
+  } else if (e1) {
+    // exponential x Gaussian: the exponential (from 0) convolved with the Gaussian bump at delta2:
+    // beyond delta2 + z beta2 the product e^{beta1 s} x (Gaussian tail) is below e^{-z^2 / 2};
+    // upper limit (t - delta2 + s + beta1 beta2^2) / beta2 >= X for every s >= 0
+    *s_lo = 0.;
+    *s_hi = std::max(0., v2[2]) + Z_GAUSS * v2[1];
+    *t_int = std::max(0., v2[2]) + X_INTERIOR * v2[1];
+  } else {
+    // Gaussian x exponential: e^{-beta2 s} times a factor that depends on s only through the
+    // limits of the (verbatim) beta1 / delta1 branches, (t - delta1 - s + beta2 beta1^2) / beta1
+    *s_lo = 0.;
+    *s_hi = C_EXP / v2[1];
+    *t_int = std::max(0., v1[2]) + *s_hi + X_INTERIOR * v1[1];
   }
 }
 
@@ -74,7 +89,7 @@ struct TermWeights {
 // Build the work items of an upsilon-type term.
 //   VA1/VA2: variables of the value closure (structure KU), VB: variables of the
 //   derivative closure of a same-type term (K[k][i]); merged when equal.
-static void plan_upsilon(const aslsd_ctx* ctx, SumPlan& P, std::vector<ItemDev> fam_items[8],
+static void plan_upsilon(const aslsd_ctx* ctx, SumPlan& P, std::vector<ItemDev> fam_items[ITEM_N_FAMILIES],
                          std::vector<std::pair<int, ItemRef>>& fixups, const KernelHost& KU,
                          const std::vector<Vars>& VA1, const std::vector<Vars>& VA2,
                          const KernelHost* KB, const std::vector<Vars>* VB, int tgt, int src, bool single,
@@ -83,18 +98,24 @@ static void plan_upsilon(const aslsd_ctx* ctx, SumPlan& P, std::vector<ItemDev> 
   const int R1 = (int)KU.bases.size(), R2 = R1;
   const bool sim = (KB != nullptr);
   const bool merged = sim && vars_equal(VA1, *VB);
-  const int type = KU.bases[0].type;
-  const int fam = single ? (type == ASLSD_BASIS_EXPONENTIAL ? ITEM_UPS0_EXP : ITEM_UPS0_GAUSS)
-                         : (type == ASLSD_BASIS_EXPONENTIAL ? ITEM_UPS_EXP : ITEM_UPS_GAUSS);
-  const int sf = by_term ? 0 : fam;   // storage list: one per family, or a single one in term order
+  // family of the basis pair (p, q); all kernels share KU's sequence of basis types (aslsd_set_model)
+  auto pair_family = [&](int p, int q) {
+    const bool e1 = KU.bases[p].type == ASLSD_BASIS_EXPONENTIAL, e2 = KU.bases[q].type == ASLSD_BASIS_EXPONENTIAL;
+    if (e1 && e2) return single ? ITEM_UPS0_EXP : ITEM_UPS_EXP;
+    if (!e1 && !e2) return single ? ITEM_UPS0_GAUSS : ITEM_UPS_GAUSS;
+    if (e1) return single ? ITEM_UPS0_EG : ITEM_UPS_EG;
+    return single ? ITEM_UPS0_GE : ITEM_UPS_GE;
+  };
   *u_lo = 1e300;
   *u_hi = 0.;
   auto emit = [&](int p, int q, const Vars& v1, const Vars& v2, int mask, bool own, const Vars& vo) {
-    if (!W.active) return -1;
+    if (!W.active) return ItemRef{0, -1};
     ItemDev it;
     std::memset(&it, 0, sizeof(it));
     it.wa_off = W.wa;
     it.wb_off = W.wb;
+    const int fam = pair_family(p, q);
+    const int sf = by_term ? 0 : fam;   // storage list: one per family, or a single one in term order
     it.family = fam;
     it.tgt_dim = tgt;
     it.src_dim = src;
@@ -103,21 +124,26 @@ static void plan_upsilon(const aslsd_ctx* ctx, SumPlan& P, std::vector<ItemDev> 
     it.m_hi = m_hi;
     it.b1 = v1[1]; it.d1 = v1[2]; it.b2 = v2[1]; it.d2 = v2[2];
     it.bo = vo[1]; it.dlo = vo[2];
-    ups_window(type, v1, v2, &it.s_lo, &it.s_hi, &it.t_int);
+    ups_window(KU.bases[p].type, KU.bases[q].type, v1, v2, &it.s_lo, &it.s_hi, &it.t_int);
     if (own) {
       double oh, ot;
-      own_window(type, vo, &oh, &ot);
+      own_window(KU.bases[p].type, vo, &oh, &ot);
       it.s_lo = 0.;
       it.s_hi = std::max(it.s_hi, oh);
       it.t_int = std::max(it.t_int, ot);
       if (vo[1] == v1[1] && vo[1] == v2[1] && vo[2] == v1[2] && vo[2] == v2[2]) mask |= MASK_OWN_SAME;
     }
     it.mask = mask;
-    if (!by_term && it.s_hi < 0.) return -1;   // empty lag window: contributes exactly zero
+    if (!by_term && it.s_hi < 0.) return ItemRef{sf, -1};   // empty lag window: contributes exactly zero
     *u_lo = std::min(*u_lo, it.s_lo);
     *u_hi = std::max(*u_hi, it.s_hi);
     fam_items[sf].push_back(it);
-    return (int)fam_items[sf].size() - 1;
+    return ItemRef{sf, (int)fam_items[sf].size() - 1};
+  };
+  // mixed pairs: the omega derivatives read the guarded copy of the value (slot C_SW)
+  auto guard_mask = [&](int p, int q, const std::vector<BasisHost>& B) {
+    if (KU.bases[p].type == KU.bases[q].type) return 0;
+    return ((B[p].free_mask | B[q].free_mask) & 1) ? MASK(C_SW) : 0;
   };
   const std::vector<BasisHost>& BU = KU.bases;
   // value set (and, when merged or for cross terms, the derivative components too)
@@ -131,6 +157,7 @@ static void plan_upsilon(const aslsd_ctx* ctx, SumPlan& P, std::vector<ItemDev> 
         if ((BU[p].free_mask >> 2) & 1) mask |= MASK(C_D1);
         if ((BU[q].free_mask >> 1) & 1) mask |= MASK(C_B2);
         if ((BU[q].free_mask >> 2) & 1) mask |= MASK(C_D2);
+        mask |= guard_mask(p, q, BU);
       }
       if (diff && merged) {
         const std::vector<BasisHost>& BB = KB->bases;
@@ -139,6 +166,7 @@ static void plan_upsilon(const aslsd_ctx* ctx, SumPlan& P, std::vector<ItemDev> 
           if ((BB[p].free_mask >> 2) & 1) mask |= MASK(C_D1);
           if ((BB[q].free_mask >> 1) & 1) mask |= MASK(C_B2);
           if ((BB[q].free_mask >> 2) & 1) mask |= MASK(C_D2);
+          mask |= guard_mask(p, q, BB);
         } else {
           if ((BB[p].free_mask >> 0) & 1) mask |= MASK(C_SW);
           if ((BB[p].free_mask >> 1) & 1) mask |= MASK(C_SB);
@@ -146,9 +174,9 @@ static void plan_upsilon(const aslsd_ctx* ctx, SumPlan& P, std::vector<ItemDev> 
           own = (mask & (MASK(C_SW) | MASK(C_SB) | MASK(C_SD))) != 0;
         }
       }
-      int idx = emit(p, q, VA1[p], VA2[q], mask, own, own ? (*VB)[p] : VA1[p]);
-      fixups.push_back({(int)P.slot_item.size(), ItemRef{sf, idx}});
-      P.slot_item.push_back(idx);
+      const ItemRef ref = emit(p, q, VA1[p], VA2[q], mask, own, own ? (*VB)[p] : VA1[p]);
+      fixups.push_back({(int)P.slot_item.size(), ref});
+      P.slot_item.push_back(ref.idx);
     }
   // separate derivative set of a same-type term whose own kernel differs from KU
   P.term_der_off.push_back((int)P.slot_item.size());
@@ -163,15 +191,16 @@ static void plan_upsilon(const aslsd_ctx* ctx, SumPlan& P, std::vector<ItemDev> 
           if ((BB[p].free_mask >> 2) & 1) mask |= MASK(C_D1);
           if ((BB[q].free_mask >> 1) & 1) mask |= MASK(C_B2);
           if ((BB[q].free_mask >> 2) & 1) mask |= MASK(C_D2);
+          mask |= guard_mask(p, q, BB);
         } else {
           if ((BB[p].free_mask >> 0) & 1) mask |= MASK(C_SW);
           if ((BB[p].free_mask >> 1) & 1) mask |= MASK(C_SB);
           if ((BB[p].free_mask >> 2) & 1) mask |= MASK(C_SD);
           own = (mask & (MASK(C_SW) | MASK(C_SB) | MASK(C_SD))) != 0;
         }
-        int idx = emit(p, q, (*VB)[p], (*VB)[q], mask, own, (*VB)[p]);
-        fixups.push_back({(int)P.slot_item.size(), ItemRef{sf, idx}});
-        P.slot_item.push_back(idx);
+        const ItemRef ref = emit(p, q, (*VB)[p], (*VB)[q], mask, own, (*VB)[p]);
+        fixups.push_back({(int)P.slot_item.size(), ref});
+        P.slot_item.push_back(ref.idx);
       }
   } else if (sim && merged) {
     P.term_der_off.back() = P.term_val_off.back();
@@ -179,7 +208,7 @@ static void plan_upsilon(const aslsd_ctx* ctx, SumPlan& P, std::vector<ItemDev> 
   if (*u_lo > *u_hi) { *u_lo = 0.; *u_hi = -1.; }
 }
 
-static void plan_basis_items(SumPlan& P, std::vector<ItemDev> fam_items[8],
+static void plan_basis_items(SumPlan& P, std::vector<ItemDev> fam_items[ITEM_N_FAMILIES],
                              std::vector<std::pair<int, ItemRef>>& fixups, const KernelHost& K,
                              const std::vector<Vars>& V, bool is_phi, int tgt, int src, int64_t m_lo,
                              int64_t m_hi, bool diff, bool by_term, double* u_lo, double* u_hi,
@@ -284,7 +313,7 @@ int build_plan(aslsd_ctx* ctx, int k, const double* x_k, int flags, const int64_
   }
   int rc = plan_vars(ctx, k, x_k, P);
   if (rc) return rc;
-  std::vector<ItemDev> fam_items[8];
+  std::vector<ItemDev> fam_items[ITEM_N_FAMILIES];
   std::vector<std::pair<int, ItemRef>> fixups;
   int64_t out = 0;
   auto add_term = [&](int kind, int i, int j, int n1, int n2) {
@@ -362,7 +391,7 @@ int build_plan(aslsd_ctx* ctx, int k, const double* x_k, int flags, const int64_
   P.out_len = out;
   if (by_term) {
     P.items.swap(fam_items[0]);
-    for (int f = 0; f < 8; ++f) { P.fam_first[f] = 0; P.fam_count[f] = 0; P.fam_wu_first[f] = 0; P.fam_wu_count[f] = 0; }
+    for (int f = 0; f < ITEM_N_FAMILIES; ++f) { P.fam_first[f] = 0; P.fam_count[f] = 0; P.fam_wu_first[f] = 0; P.fam_wu_count[f] = 0; }
     P.n_wu = 0;
     for (auto& fx : fixups) P.slot_item[fx.first] = fx.second.idx;
     return ASLSD_OK;
@@ -370,11 +399,11 @@ int build_plan(aslsd_ctx* ctx, int k, const double* x_k, int flags, const int64_
   // concatenate the families and assign work units
   int base = 0;
   int64_t wu = 0;
-  for (int f = 0; f < 8; ++f) {
+  for (int f = 0; f < ITEM_N_FAMILIES; ++f) {
     P.fam_first[f] = base;
     P.fam_count[f] = (int)fam_items[f].size();
     P.fam_wu_first[f] = wu;
-    const bool pair = (f == ITEM_UPS_EXP || f == ITEM_UPS_GAUSS || f == ITEM_PHI_EXP || f == ITEM_PHI_GAUSS);
+    const bool pair = item_pair_family(f);
     int64_t tot_targets = 0;
     for (auto& it : fam_items[f]) tot_targets += std::max<int64_t>(0, it.m_hi - it.m_lo);
     // enough work units for a few waves of 148 SMs x 2 CTAs, each spanning whole tiles

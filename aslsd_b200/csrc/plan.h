@@ -19,8 +19,8 @@ struct SumPlan {
   int k = -1, flags = 0;
   std::vector<TermPlan> terms;
   std::vector<ItemDev> items;       // grouped by family (exact) or by term (sampled)
-  int fam_first[8], fam_count[8];
-  int64_t fam_wu_first[8], fam_wu_count[8];
+  int fam_first[ITEM_N_FAMILIES], fam_count[ITEM_N_FAMILIES];
+  int64_t fam_wu_first[ITEM_N_FAMILIES], fam_wu_count[ITEM_N_FAMILIES];
   int64_t n_wu = 0;
   // per-term tables of item indices (-1: empty window, contributes zero)
   std::vector<int> slot_item;
@@ -67,9 +67,21 @@ void emit_term(const aslsd_ctx* ctx, const SumPlan& P, size_t t, const double* x
     const int idx = P.slot_item[off + slot];
     if (idx >= 0) sink(c, idx, comp, coef, outer);
   };
-  const bool ups_exp = KU.bases[0].type == ASLSD_BASIS_EXPONENTIAL;
-  // exponential upsilon: beta1 beta2 / (beta1 + beta2) multiplies every C_G component
-  auto prat = [&](const Vars& a, const Vars& b) { return ups_exp ? (a[1] * b[1]) / (a[1] + b[1]) : 1.; };
+  // factor of every value component (C_G) of the basis pair (p, q), by the types of the two bases:
+  // exp x exp beta1 beta2 / (beta1 + beta2), exp x gauss beta1, gauss x exp beta2, gauss x gauss 1
+  auto is_exp = [&](int r) { return KU.bases[r].type == ASLSD_BASIS_EXPONENTIAL; };
+  auto prat = [&](int p, int q, const Vars& a, const Vars& b) {
+    if (is_exp(p)) return is_exp(q) ? (a[1] * b[1]) / (a[1] + b[1]) : a[1];
+    return is_exp(q) ? b[1] : 1.;
+  };
+  // component read by the derivative in omega of basis `side` (1 or 2) of the pair: mixed pairs
+  // keep the value under the reference's overflow guard in slot C_SW (basis_math.cuh); the
+  // gauss x exp form does not guard its omega_2 derivative (basis_kernel_gaussian.py:196-198)
+  auto omega_comp = [&](int p, int q, int side) {
+    if (is_exp(p) == is_exp(q)) return (int)C_G;
+    if (!is_exp(p) && side == 2) return (int)C_G;
+    return (int)C_SW;
+  };
   if (T.kind == 0 || T.kind == 2) {
     // psi_i / phi_i: one item per basis of K[k][i]
     const KernelHost& K = ctx->kernels[k * d + T.i];
@@ -103,28 +115,26 @@ void emit_term(const aslsd_ctx* ctx, const SumPlan& P, size_t t, const double* x
     const std::vector<Vars>&V1 = P.VU[T.i], &V2 = P.VU[T.j];
     for (int p = 0; p < Rn; ++p)
       for (int q = 0; q < Rn; ++q)
-        put(0, voff, p * Rn + q, C_G, V1[p][0] * V2[q][0] * prat(V1[p], V2[q]));
+        put(0, voff, p * Rn + q, C_G, V1[p][0] * V2[q][0] * prat(p, q, V1[p], V2[q]));
     if (!diff) return;
     int slot = 0;
     for (int p = 0; p < Rn; ++p)
       for (int v = 0; v < KU.bases[p].n_vars(); ++v) {
         if (!((KU.bases[p].free_mask >> v) & 1)) continue;
-        const int c = v == 0 ? C_G : (v == 1 ? C_B1 : C_D1);
         if (slot < T.n1)
           for (int q = 0; q < Rn; ++q)
-            put(1 + slot, voff, p * Rn + q, c,
-                v == 0 ? V2[q][0] * prat(V1[p], V2[q]) : V1[p][0] * V2[q][0]);
+            put(1 + slot, voff, p * Rn + q, v == 0 ? omega_comp(p, q, 1) : (v == 1 ? C_B1 : C_D1),
+                v == 0 ? V2[q][0] * prat(p, q, V1[p], V2[q]) : V1[p][0] * V2[q][0]);
         ++slot;
       }
     slot = 0;
     for (int q = 0; q < Rn; ++q)
       for (int v = 0; v < KU.bases[q].n_vars(); ++v) {
         if (!((KU.bases[q].free_mask >> v) & 1)) continue;
-        const int c = v == 0 ? C_G : (v == 1 ? C_B2 : C_D2);
         if (slot < T.n2)
           for (int p = 0; p < Rn; ++p)
-            put(1 + T.n1 + slot, voff, p * Rn + q, c,
-                v == 0 ? V1[p][0] * prat(V1[p], V2[q]) : V1[p][0] * V2[q][0]);
+            put(1 + T.n1 + slot, voff, p * Rn + q, v == 0 ? omega_comp(p, q, 2) : (v == 1 ? C_B2 : C_D2),
+                v == 0 ? V1[p][0] * prat(p, q, V1[p], V2[q]) : V1[p][0] * V2[q][0]);
         ++slot;
       }
     return;
@@ -134,7 +144,7 @@ void emit_term(const aslsd_ctx* ctx, const SumPlan& P, size_t t, const double* x
   const std::vector<Vars>& VB = P.V[T.i];
   const KernelHost& KB = ctx->kernels[k * d + T.i];
   for (int p = 0; p < Rn; ++p)
-    for (int q = 0; q < Rn; ++q) put(0, voff, p * Rn + q, C_G, VA[p][0] * VA[q][0] * prat(VA[p], VA[q]));
+    for (int q = 0; q < Rn; ++q) put(0, voff, p * Rn + q, C_G, VA[p][0] * VA[q][0] * prat(p, q, VA[p], VA[q]));
   if (!diff) return;
   int slot = 0;
   for (int b = 0; b < Rn; ++b)
@@ -143,16 +153,16 @@ void emit_term(const aslsd_ctx* ctx, const SumPlan& P, size_t t, const double* x
       const double wb = VB[b][0];
       // own-basis closed form, then the cross terms with every other basis in
       // both slots (kernel.py:282-299)
-      if (v == 0) put(1 + slot, doff, b * Rn + b, C_SW, ups_exp ? wb * VB[b][1] : wb);
+      if (v == 0) put(1 + slot, doff, b * Rn + b, C_SW, is_exp(b) ? wb * VB[b][1] : wb);
       else put(1 + slot, doff, b * Rn + b, v == 1 ? C_SB : C_SD, wb * wb);
       for (int q = 0; q < Rn; ++q) {
         if (q == b) continue;
-        if (v == 0) put(1 + slot, doff, b * Rn + q, C_G, VB[q][0] * prat(VB[b], VB[q]));
+        if (v == 0) put(1 + slot, doff, b * Rn + q, omega_comp(b, q, 1), VB[q][0] * prat(b, q, VB[b], VB[q]));
         else put(1 + slot, doff, b * Rn + q, v == 1 ? C_B1 : C_D1, wb * VB[q][0]);
       }
       for (int p = 0; p < Rn; ++p) {
         if (p == b) continue;
-        if (v == 0) put(1 + slot, doff, p * Rn + b, C_G, VB[p][0] * prat(VB[p], VB[b]));
+        if (v == 0) put(1 + slot, doff, p * Rn + b, omega_comp(p, b, 2), VB[p][0] * prat(p, b, VB[p], VB[b]));
         else put(1 + slot, doff, p * Rn + b, v == 1 ? C_B2 : C_D2, VB[p][0] * wb);
       }
       ++slot;

@@ -28,6 +28,7 @@ union ItemConst {
   UpsGaussConst g;
   UpsExpConst e;
   PhiConst p;
+  UpsMixConst m;
 };
 
 struct SampleTermDev {
@@ -54,6 +55,8 @@ __global__ void item_const_kernel(const ItemDev* __restrict__ items, int n_items
   switch (it.family) {
     case ITEM_UPS_GAUSS: case ITEM_UPS0_GAUSS: c.g.init(it); break;
     case ITEM_UPS_EXP: case ITEM_UPS0_EXP: c.e.init(it); break;
+    case ITEM_UPS_EG: case ITEM_UPS0_EG: c.m.init_eg(it); break;
+    case ITEM_UPS_GE: case ITEM_UPS0_GE: c.m.init_ge(it); break;
     default: c.p.init(it); break;
   }
   consts[x] = c;
@@ -166,6 +169,14 @@ sampled_kernel(const DimDev* __restrict__ dims, const ItemDev* __restrict__ item
         case ITEM_UPS_EXP: case ITEM_UPS0_EXP:
           if (interior) eval_ups_exp<true>(consts[ix].e, mask, 0., s, raw);
           else eval_ups_exp<false>(consts[ix].e, mask, t, s, raw);
+          break;
+        case ITEM_UPS_EG: case ITEM_UPS0_EG:
+          if (interior) eval_ups_eg<true>(consts[ix].m, mask, 0., s, raw);
+          else eval_ups_eg<false>(consts[ix].m, mask, t, s, raw);
+          break;
+        case ITEM_UPS_GE: case ITEM_UPS0_GE:
+          if (interior) eval_ups_ge<true>(consts[ix].m, mask, 0., s, raw);
+          else eval_ups_ge<false>(consts[ix].m, mask, t, s, raw);
           break;
         case ITEM_PHI_EXP: eval_phi_exp(consts[ix].p, mask, s, raw); break;
         case ITEM_PHI_GAUSS: eval_phi_gauss(consts[ix].p, mask, s, raw); break;

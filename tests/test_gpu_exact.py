@@ -204,7 +204,7 @@ def test_lag_quadrature_agrees_with_item_kernels(engine, name):
         engine.use_lag_quadrature(True)
 
 
-@pytest.mark.parametrize('family', ['exp', 'gauss'])
+@pytest.mark.parametrize('family', ['exp', 'gauss', 'mix'])
 def test_lag_quadrature_random_parameters(engine, family):
     """Random (beta, delta) over two decades of scale, clustered event times with exact
     ties: quadrature against the per-item kernels."""
@@ -218,11 +218,18 @@ def test_lag_quadrature_random_parameters(engine, family):
                 def draw():
                     return [0.3 * rng.uniform(), 10 ** rng.uniform(-0.5, 0.7),
                             0.3 * rng.uniform(), 10 ** rng.uniform(-0.5, 0.7)]
-            else:
+            elif family == 'gauss':
                 basis = [{'type': 'gauss'}, {'type': 'gauss'}]
                 def draw():
                     return [0.3 * rng.uniform(), 10 ** rng.uniform(-0.7, 0.3), rng.uniform(0., 4.),
                             0.3 * rng.uniform(), 10 ** rng.uniform(-0.7, 0.3), rng.uniform(0., 4.)]
+            else:
+                # exponential x Gaussian pairs in both orders; beta_exp * beta_gauss stays moderate
+                # (beyond ~3 the reference's own cdf differences lose their digits)
+                basis = [{'type': 'exp'}, {'type': 'gauss'}]
+                def draw():
+                    return [0.3 * rng.uniform(), 10 ** rng.uniform(-0.5, 0.3),
+                            0.3 * rng.uniform(), 10 ** rng.uniform(-0.7, 0.0), rng.uniform(0., 4.)]
             model = {'d': d, 'kernels': [[basis for _ in range(d)] for _ in range(d)]}
             T_f = 3000.
             times = []
@@ -370,8 +377,13 @@ def test_errors(engine):
     g = load_golden('exact_exp1d')
     times, T_f = golden_times(g)
     engine.set_events(times, T_f)
+    # kernels of different basis structure: the reference's late-bound upsilon closures would
+    # read one kernel's parameters with another one's functional
+    engine.set_events([times[0], times[0][::2]], T_f)
     with pytest.raises(NotImplementedError):
-        engine.set_model({'d': 1, 'kernels': [[[{'type': 'exp'}, {'type': 'gauss'}]]]})
+        engine.set_model({'d': 2, 'kernels': [[[{'type': 'exp'}], [{'type': 'exp'}]],
+                                              [[{'type': 'exp'}], [{'type': 'gauss'}]]]})
+    engine.set_events(times, T_f)
     engine.set_model(CASES['exp1d'][0])
     with pytest.raises(ValueError):
         engine.exact_sums(0, [1.0, 0.2])
