@@ -5,7 +5,7 @@ argument meaning and error behaviour) over a C-ABI CUDA library
 (include/aslsd_b200.h).  There is no CPU fallback.
 """
 from aslsd_b200.engine import Engine, EngineError  # noqa: F401
-from aslsd_b200.events import ProcessPath, get_kappa_varpi, get_lag_sizes  # noqa: F401
+from aslsd_b200.events import Episodes, ProcessPath, get_kappa_varpi, get_lag_sizes  # noqa: F401
 from aslsd_b200.model import (MHP, KernelModel, ExponentialKernel,  # noqa: F401
                               GaussianKernel, describe_model)
 
@@ -18,5 +18,5 @@ from aslsd_b200.residuals import get_intensity_at_jumps, get_residuals, get_resi
 
 __all__ = ['get_intensity_at_jumps', 'get_residuals', 'get_residuals_k',
            'MHPExactEstimB200', 'MHPStratEstimB200', 'MTLH', 'MTLHExactEstimB200', 'MTLHStratEstimB200', 'GeneralStratification',
-           'DoubleIxStratification', 'ADAM', 'Engine', 'EngineError', 'ProcessPath', 'get_kappa_varpi', 'get_lag_sizes',
+           'DoubleIxStratification', 'ADAM', 'Engine', 'EngineError', 'Episodes', 'ProcessPath', 'get_kappa_varpi', 'get_lag_sizes',
            'MHP', 'KernelModel', 'ExponentialKernel', 'GaussianKernel', 'describe_model']

@@ -517,12 +517,14 @@ static int run_batch(aslsd_ctx* ctx, BatchPlan& B, double* raw_device) {
   ctx->moment_timing_pending = false;
   ctx->last_moment_ms = 0.;
   if (quad && !reuse_weights) {
-    if (B.q_smem > ctx->q_smem_set) {
+    if (ctx->q_smem_set == 0) {
+      // the attribute belongs to the function, not to this context: every context asks for the
+      // same ceiling, so contexts with different bin counts never lower each other's limit
       CUDA_TRY(ctx, cudaFuncSetAttribute(lag_moment_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)B.q_smem));
+                                         (int)LQ_SMEM_BUDGET));
       CUDA_TRY(ctx, cudaFuncSetAttribute(lag_moment_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)B.q_smem));
-      ctx->q_smem_set = B.q_smem;
+                                         (int)LQ_SMEM_BUDGET));
+      ctx->q_smem_set = LQ_SMEM_BUDGET;
     }
     CUDA_TRY(ctx, cudaEventRecord(ctx->ev_q0, ctx->stream));
     unsigned long long* d_qcnt = ctx->d_counts + B.n_wu + n_items;

@@ -49,9 +49,9 @@ except Exception:   # the reference package is absent (e.g. on the GPU box)
 KIND_PSI, KIND_UPSILONZERO, KIND_PHI, KIND_UPSILON = 0, 1, 2, 3
 
 
-def _default_engine():
-    from aslsd_b200.events import default_engine
-    return default_engine()
+def _engine_for(data):
+    from aslsd_b200.events import engine_for
+    return engine_for(data)
 
 
 class _B200Estimator(_RefEstimator):
@@ -102,7 +102,7 @@ class _B200Estimator(_RefEstimator):
         self.lag_sizes = data.lag_sizes
         model.init_estimator(self, self.k)
         if self.engine is None:
-            self.engine = getattr(data, 'engine', None) or _default_engine()
+            self.engine = _engine_for(data)
         self._model, self._path = model, data
         self.desc = self.engine.bind(data, model)
 

@@ -25,6 +25,51 @@ def default_engine():
     return _default_engine
 
 
+def _path_key(data):
+    return (id(data.list_times), float(data.T_f), tuple(len(t) for t in data.list_times))
+
+
+def engine_for(data):
+    """Device context for the events of ``data``: the path's own ``engine`` attribute if it has
+    one, the process-wide default engine while that one is free or already holds this path, and
+    otherwise a new engine that is kept on the path object.  Several live paths (the episodes of
+    ``fit_episodes``, mhp.py:1806-2008) thus stay resident on the device side by side instead of
+    being re-uploaded every time the fit loop moves from one path to the next."""
+    own = getattr(data, 'engine', None)
+    if own is not None:
+        return own
+    eng = default_engine()
+    held = getattr(eng, '_events_key', None)
+    if held is None or held == _path_key(data):
+        return eng
+    eng = Engine(eng.device if hasattr(eng, 'device') else 0)
+    try:
+        data.engine = eng
+    except AttributeError:   # a path type with __slots__: fall back to sharing the default engine
+        return default_engine()
+    return eng
+
+
+class Episodes:
+    """Several paths of the same process observed independently (stats/events/episodes.py:13-80):
+    the container ``fit_episodes`` iterates over."""
+
+    def __init__(self, list_paths=None, T_f=1.):
+        self.list_paths = [] if list_paths is None else list(list_paths)
+        self.n_episodes = len(self.list_paths)
+        self.T_f = T_f
+        self.d = self.list_paths[0].d if self.n_episodes else 0
+        self.list_n_events = np.zeros((self.d, self.n_episodes))
+        self.list_eta = np.zeros((self.d, self.n_episodes))
+        for ix, path in enumerate(self.list_paths):
+            self.list_n_events[:, ix] = path.n_events
+            self.list_eta[:, ix] = path.eta
+        if self.n_episodes > 0:
+            self.average_n_events = np.mean(self.list_n_events, axis=1)
+            self.total_n_events = np.sum(self.list_n_events, axis=1, dtype=int)
+            self.average_eta = np.mean(self.list_eta, axis=1)
+
+
 def get_kappa_varpi(list_times, T_f, engine=None):
     """kappa[j][i][m]: index of the latest type-j event strictly before t^i_m;
     varpi[i][j][h]: first m such that t^i_m has at least h type-j predecessors."""

@@ -161,6 +161,106 @@ class MHP:
         return x, log
 
 
+    def fit_episodes(self, episodes, x_0, n_iter=1000, solvers=None, solver_args=None,
+                     exact_grad=False, estimators=None, is_log_lse=False, is_grad_target=False,
+                     is_log_ixs=False, is_log_allocs=False, is_log_total_estimates=False,
+                     is_log_strata_estimates=False, n_exact_single=None,
+                     n_samples_adaptive_single=None, nonadaptive_sample_size_single=None,
+                     single_strfs=None, n_samples_adaptive_double=None,
+                     nonadaptive_sample_size_double=None, double_strfs=None, rng=None, seed=1234,
+                     process_group=None, callback=None):
+        """The loop of MHP.fit_episodes (mhp.py:1806-2008): one estimator per (k, path), the
+        gradient of an iteration is the mean of the per-path gradient estimates
+        (``np.mean(g_per_path, axis=0)``, :1983-1989), then solver step and projection as in
+        ``fit``.  Every path keeps its own device context (``events.engine_for``), so the events
+        of all episodes stay resident.
+
+        ``estimators``: None, one estimator (copied for every (k, path)) or a d x n_episodes
+        nested list, like upstream.  ``process_group``: a ``torch.distributed`` group - the
+        episodes are dealt round-robin to its ranks, each rank evaluates its own paths and one
+        all-reduce per iteration sums the per-path gradients (the extra data-parallel axis of
+        SURVEY 8f row 4); every rank returns the same iterates.
+
+        Deviation from upstream, on purpose: the reference calls
+        ``lse_k_grad_estimate(x_k, rng)`` (:1986), which binds the Generator to ``grad_alloc`` and
+        leaves ``rng=None`` - the stratified estimator then draws from fresh OS entropy at every
+        call (mhp_stratified_estimator.py:1409-1413) and a fit is not reproducible.  Here the
+        Generator is passed as ``rng`` (and ``grad_alloc=True``, which is what a truthy Generator
+        amounts to); with exact estimators the two coincide."""
+        import copy
+        from aslsd_b200.estimators import MHPExactEstimB200, MHPStratEstimB200
+        from aslsd_b200.solvers import ADAM
+        d = self.d
+        n_episodes = episodes.n_episodes
+        if n_episodes == 0:
+            raise ValueError('fit_episodes: no episodes')
+        if rng is None:
+            rng = np.random.default_rng(seed)
+        if not isinstance(n_iter, (list, np.ndarray)):
+            n_iter = [n_iter] * d
+        rank, world = 0, 1
+        if process_group is not None:
+            import torch.distributed as dist
+            rank, world = dist.get_rank(process_group), dist.get_world_size(process_group)
+        mine = [ix for ix in range(n_episodes) if ix % world == rank]
+        if estimators is None:
+            cls = MHPExactEstimB200 if exact_grad else MHPStratEstimB200
+            estimators = [[cls(is_grad_target=is_grad_target, is_log_ixs=is_log_ixs,
+                               is_log_allocs=is_log_allocs,
+                               is_log_total_estimates=is_log_total_estimates,
+                               is_log_strata_estimates=is_log_strata_estimates,
+                               is_log_lse=is_log_lse) for _ in range(n_episodes)] for _ in range(d)]
+        elif not isinstance(estimators, (list, tuple)):
+            estimators = [[copy.deepcopy(estimators) for _ in range(n_episodes)] for _ in range(d)]
+        for k in range(d):
+            for ix in mine:
+                estimators[k][ix].initialize(
+                    k, n_iter[k], self, episodes.list_paths[ix], n_exact_single=n_exact_single,
+                    n_samples_adaptive_single=n_samples_adaptive_single,
+                    nonadaptive_sample_size_single=nonadaptive_sample_size_single,
+                    single_strfs=single_strfs, n_samples_adaptive_double=n_samples_adaptive_double,
+                    nonadaptive_sample_size_double=nonadaptive_sample_size_double,
+                    double_strfs=double_strfs)
+        if solvers is None:
+            solvers = [ADAM(**(solver_args or {})) for _ in range(d)]
+        elif not isinstance(solvers, (list, tuple)):
+            solvers = [copy.deepcopy(solvers) for _ in range(d)]
+        log = {'param': [], 'grad': []}
+        x = [None] * d
+        for k in range(d):
+            x_k = np.asarray(x_0[k], dtype=np.float64)
+            lower = self.lower_bounds(k)
+            params = np.zeros((n_iter[k] + 1, len(x_k)))
+            grads = np.zeros((n_iter[k], len(x_k)))
+            params[0] = x_k
+            for t in range(n_iter[k]):
+                g_per_path = np.zeros((n_episodes, len(x_k)))
+                for ix in mine:
+                    g_per_path[ix] = estimators[k][ix].lse_k_grad_estimate(x_k, rng=rng, grad_alloc=True)
+                if world > 1:
+                    import torch
+                    import torch.distributed as dist
+                    buf = torch.from_numpy(g_per_path)
+                    if dist.get_backend(process_group) == 'nccl':
+                        dev = buf.cuda()
+                        dist.all_reduce(dev, group=process_group)
+                        g_per_path = dev.cpu().numpy()
+                    else:
+                        dist.all_reduce(buf, group=process_group)
+                g_t = np.mean(g_per_path, axis=0)
+                grads[t] = g_t
+                x_k = np.clip(solvers[k].iterate(t, x_k, g_t), lower, np.inf)
+                params[t + 1] = x_k
+                if callback is not None:
+                    callback(k, t, x_k, g_t)
+            log['param'].append(params)
+            log['grad'].append(grads)
+            x[k] = x_k
+        self.fit_estim = estimators
+        self.fitted_x = x
+        return x, log
+
+
 def _basis_from_plain(b):
     cls = {'exp': ExponentialKernel, 'gauss': GaussianKernel}[b['type']]
     fixed = b.get('fixed', {})

@@ -31,6 +31,11 @@ class OracleEngine:
         self.times = [np.asarray(t, dtype=float) for t in list_times]
         self.T_f = float(T_f)
 
+    def index_maps(self, want_kappa=True, want_varpi=True, want_lag_sizes=True):
+        from oracle import time_ordering as OT
+        kappa, varpi = OT.kappa_varpi_closed_form(self.times, self.T_f)
+        return kappa, varpi, OT.lag_sizes(self.times, kappa, varpi)
+
     def exact_max_lag(self, ks, xs, compute_f_sum=True, compute_diff_f_sum=True):
         """Largest window of the oracle's windowed sums (oracle/exact.py phi_window / ups_window)."""
         w = 0.

@@ -99,3 +99,53 @@ def test_two_rank_shards_allreduce_to_the_full_sums(tmp_path):
     r0 = np.load(os.path.join(tmp_path, 'ranges0.npy'))
     r1 = np.load(os.path.join(tmp_path, 'ranges1.npy'))
     assert np.all(r0[:, 1] == r1[:, 0])
+
+
+def _episodes_worker(rank, world, port, paths, T_f, name, out_dir):
+    import sys
+    here = os.path.dirname(os.path.abspath(__file__))
+    for p in (os.path.dirname(here), here, os.path.join(here, 'golden')):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    import aslsd_b200
+    from aslsd_b200.events import Episodes, ProcessPath
+    from oracle_engine import OracleEngine
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    x, log = _fit_episodes(paths, T_f, name, dist.group.WORLD)
+    np.save(os.path.join(out_dir, 'x%d.npy' % rank), np.concatenate(x))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def _fit_episodes(paths, T_f, name, group):
+    import aslsd_b200
+    from aslsd_b200.events import Episodes, ProcessPath
+    from oracle_engine import OracleEngine
+    model = CASES[name][0]
+    d = model['d']
+    objs = []
+    for times in paths:
+        eng = OracleEngine()
+        objs.append(ProcessPath(times, T_f, engine=eng))
+    ests = [[aslsd_b200.MHPExactEstimB200(engine=p.engine) for p in objs] for _ in range(d)]
+    mirror = aslsd_b200.MHP(model)
+    return mirror.fit_episodes(Episodes(objs, T_f=T_f), [np.asarray(v, float) for v in case_x(name)],
+                               n_iter=4, estimators=ests, process_group=group)
+
+
+@pytest.mark.timeout(300)
+def test_fit_episodes_sharded_over_two_ranks(tmp_path):
+    """Episodes dealt to 2 ranks, per-path gradients all-reduced: same iterates as one process."""
+    name = 'exp2d'
+    rng = np.random.default_rng(21)
+    T_f = 80.
+    paths = [[np.sort(rng.uniform(0, T_f, size=60 + 7 * q)), np.sort(rng.uniform(0, T_f, size=45 + 5 * q))]
+             for q in range(3)]
+    port = _free_port()
+    mp.spawn(_episodes_worker, args=(2, port, paths, T_f, name, str(tmp_path)), nprocs=2, join=True)
+    got = [np.load(os.path.join(tmp_path, 'x%d.npy' % r)) for r in range(2)]
+    np.testing.assert_array_equal(got[0], got[1])
+    x, _ = _fit_episodes(paths, T_f, name, None)
+    np.testing.assert_allclose(got[0], np.concatenate(x), rtol=1e-12)

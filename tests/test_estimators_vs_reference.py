@@ -169,3 +169,46 @@ def test_mirror_fit_matches_reference_fit(ref):
                         engine=OracleEngine(), **STRAT_KW)
     np.testing.assert_allclose(x[0][0], float(mu_ref[0]), rtol=1e-8)
     np.testing.assert_allclose(x[0][1:], np.asarray(ker_ref[0][0], float), rtol=1e-8)
+
+
+def test_fit_episodes_matches_reference(ref):
+    """MHP.fit_episodes (mhp.py:1806-2008) with exact estimators: the mirror loop reproduces the
+    reference's iterates, and the B200 estimators plug into the reference's own fit_episodes."""
+    import aslsd_b200
+    from aslsd.stats.events.episodes import Episodes
+    model, mu, kp, _ = CASES['exp2d']
+    d = model['d']
+    mhp = ref_shim.build_reference_model(ref, model)
+    arr = np.empty((d, d), dtype=object)
+    for a in range(d):
+        for b in range(d):
+            arr[a][b] = np.asarray(kp[a][b], dtype=float)
+    paths = [mhp.simulate(50., mu=np.asarray(mu, float), kernel_param=arr, seed=100 + q, verbose=False)
+             for q in range(3)]
+    episodes = Episodes(list_paths=paths, T_f=50.)
+    x_0 = [np.array(x, dtype=object) for x in case_x('exp2d')]
+    mu_ref, ker_ref = mhp.fit_episodes(episodes, x_0=copy.deepcopy(x_0), n_iter=5, exact_grad=True)
+    # (1) the B200 estimators inside the reference's loop; one oracle engine per path
+    engines = [OracleEngine() for _ in paths]
+    ests = [[aslsd_b200.MHPExactEstimB200(engine=engines[q]) for q in range(3)] for _ in range(d)]
+    mhp2 = ref_shim.build_reference_model(ref, model)
+    mu_new, ker_new = mhp2.fit_episodes(episodes, x_0=copy.deepcopy(x_0), n_iter=5, estimators=ests)
+    np.testing.assert_allclose(np.asarray(mu_new, float), np.asarray(mu_ref, float), rtol=1e-9)
+    for a in range(d):
+        for b in range(d):
+            np.testing.assert_allclose(np.asarray(ker_new[a][b], float), np.asarray(ker_ref[a][b], float),
+                                       rtol=1e-9)
+    # (2) the mirror loop
+    mirror = aslsd_b200.MHP(model)
+    engines = [OracleEngine() for _ in paths]
+    ests = [[aslsd_b200.MHPExactEstimB200(engine=engines[q]) for q in range(3)] for _ in range(d)]
+    x, log = mirror.fit_episodes(aslsd_b200.Episodes(paths, T_f=50.),
+                                 [np.asarray(v, float) for v in case_x('exp2d')], n_iter=5, estimators=ests)
+    for k in range(d):
+        np.testing.assert_allclose(x[k][0], float(mu_ref[k]), rtol=1e-9)
+        pos = 1
+        for i in range(d):
+            ref_ki = np.asarray(ker_ref[k][i], float)
+            np.testing.assert_allclose(x[k][pos:pos + len(ref_ki)], ref_ki, rtol=1e-9)
+            pos += len(ref_ki)
+        assert log['grad'][k].shape == (5, len(x[k]))
