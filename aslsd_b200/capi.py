@@ -17,6 +17,7 @@ ASLSD_DIFF = 2
 ASLSD_GRAD_ALLOC = 4
 OPT_LAG_QUADRATURE = 1
 OPT_WEIGHT_CACHE = 2
+OPT_ASYNC_EVENTS = 3
 
 BASIS_EXPONENTIAL = 0
 BASIS_GAUSSIAN = 1

@@ -140,7 +140,16 @@ struct aslsd_ctx {
   // host copy of the event times (planning), inside one pinned staging block that is
   // also the source of the host -> device copy
   double* h_events = nullptr; size_t h_events_cap = 0;
+  double* h_pad = nullptr;         // a few page-locked pad values (uploads from the caller's own pinned arrays)
+  // order check of page-locked inputs: done on the device behind the transfer; the verdict
+  // (h_flag, valid once ev_flag has completed) is collected by events_verdict()
+  int* d_flag = nullptr;
+  int* h_flag = nullptr;
+  cudaEvent_t ev_flag = nullptr;
+  bool verdict_pending = false;
+  bool async_events = false;       // ASLSD_OPT_ASYNC_EVENTS
   std::vector<const double*> h_times;
+  std::vector<unsigned char> h_dims;   // host copy of the DimDev table (source of an async upload)
   size_t times_cap = 0, tab_cap = 0, dims_cap = 0;   // capacities of d_times / d_tab / d_dims
   // lag quadrature (lag_quadrature.cuh): stream / row tables, partial moments, node weights
   void* d_qtab = nullptr; size_t qtab_cap = 0;
@@ -177,9 +186,14 @@ struct DimDev {
   int64_t n;
   int64_t n_buckets;
   double t0, w, inv_w;
+  const int* bad;      // verdict of the device-side order check of this upload (shared by all types):
+                       // kernels whose indexing relies on sorted times return at once when it is set
 };
 
 int aslsd_fail(aslsd_ctx* ctx, int code, const std::string& msg);
+// Collect the verdict of a device-side order check (see aslsd_set_events).  wait = false: only if
+// it is already there.  On a violation the context drops its events and the error is returned.
+int events_verdict(aslsd_ctx* ctx, bool wait);
 #define CUDA_TRY(ctx, expr)                                                        \
   do {                                                                             \
     cudaError_t _e = (expr);                                                       \

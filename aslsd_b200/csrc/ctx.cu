@@ -5,8 +5,13 @@
 
 #include <algorithm>
 #include <atomic>
+#include <cstdlib>
 #include <cstring>
 #include <thread>
+
+#ifndef ASLSD_STAGE_THREADS
+#define ASLSD_STAGE_THREADS 8
+#endif
 
 int aslsd_fail(aslsd_ctx* ctx, int code, const std::string& msg) {
   if (ctx) ctx->err = msg;
@@ -46,7 +51,11 @@ extern "C" int aslsd_create(aslsd_ctx** out, int device) {
   if (cudaSetDevice(device) != cudaSuccess ||
       cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) != cudaSuccess ||
       cudaEventCreate(&ctx->ev0) != cudaSuccess || cudaEventCreate(&ctx->ev1) != cudaSuccess ||
-      cudaEventCreate(&ctx->ev_q0) != cudaSuccess || cudaEventCreate(&ctx->ev_q1) != cudaSuccess) {
+      cudaEventCreate(&ctx->ev_q0) != cudaSuccess || cudaEventCreate(&ctx->ev_q1) != cudaSuccess ||
+      cudaEventCreateWithFlags(&ctx->ev_flag, cudaEventDisableTiming) != cudaSuccess ||
+      cudaMalloc((void**)&ctx->d_flag, sizeof(int)) != cudaSuccess ||
+      cudaMallocHost((void**)&ctx->h_flag, sizeof(int)) != cudaSuccess ||
+      cudaMemset(ctx->d_flag, 0, sizeof(int)) != cudaSuccess) {
     delete ctx;
     return ASLSD_ERR_CUDA;
   }
@@ -74,6 +83,10 @@ extern "C" int aslsd_destroy(aslsd_ctx* ctx) {
   cudaFree(ctx->d_q_weights);
   if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
   if (ctx->h_events) cudaFreeHost(ctx->h_events);
+  if (ctx->h_pad) cudaFreeHost(ctx->h_pad);
+  if (ctx->h_flag) cudaFreeHost(ctx->h_flag);
+  cudaFree(ctx->d_flag);
+  cudaEventDestroy(ctx->ev_flag);
   cudaEventDestroy(ctx->ev0);
   cudaEventDestroy(ctx->ev1);
   cudaEventDestroy(ctx->ev_q0);
@@ -89,7 +102,13 @@ extern "C" const char* aslsd_last_error(const aslsd_ctx* ctx) {
 
 extern "C" int aslsd_set_stream(aslsd_ctx* ctx, void* cuda_stream) {
   if (!ctx) return ASLSD_ERR_ARG;
-  ctx->stream = cuda_stream ? (cudaStream_t)cuda_stream : ctx->own_stream;
+  cudaStream_t next = cuda_stream ? (cudaStream_t)cuda_stream : ctx->own_stream;
+  if (next != ctx->stream) {
+    // uploads and kernels already enqueued are ordered on the old stream only
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  }
+  ctx->stream = next;
   return ASLSD_OK;
 }
 
@@ -123,6 +142,31 @@ __global__ void build_bucket_table_kernel(const double* __restrict__ t, int64_t 
   tab[g] = (int32_t)lo;
 }
 
+// flag |= 1 if t is not non-decreasing (NaNs count as violations)
+__global__ void check_sorted_kernel(const double* __restrict__ t, int64_t n, int* flag) {
+  bool bad = false;
+  for (int64_t m = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; m < n; m += (int64_t)gridDim.x * blockDim.x)
+    bad |= !(t[m] >= t[m > 0 ? m - 1 : 0]);
+  if (__syncthreads_or(bad) && threadIdx.x == 0) atomicOr(flag, 1);
+}
+
+int events_verdict(aslsd_ctx* ctx, bool wait) {
+  if (!ctx->verdict_pending) return ASLSD_OK;
+  if (!wait) {
+    const cudaError_t q = cudaEventQuery(ctx->ev_flag);
+    if (q == cudaErrorNotReady) return ASLSD_OK;
+    if (q != cudaSuccess) return aslsd_fail(ctx, ASLSD_ERR_CUDA, "set_events: order check failed to run");
+  } else {
+    CUDA_TRY(ctx, cudaEventSynchronize(ctx->ev_flag));
+  }
+  ctx->verdict_pending = false;
+  if (*ctx->h_flag == 0) return ASLSD_OK;
+  cudaStreamSynchronize(ctx->stream);
+  ctx->d = 0;
+  ctx->events_epoch++;
+  return aslsd_fail(ctx, ASLSD_ERR_ARG, "set_events: times must be sorted");
+}
+
 extern "C" int aslsd_set_events(aslsd_ctx* ctx, int d, const int64_t* n_events,
                                 const double* const* times, double T_f) {
   if (!ctx || d <= 0 || !n_events || !times) return aslsd_fail(ctx, ASLSD_ERR_ARG, "set_events: bad arguments");
@@ -139,13 +183,35 @@ extern "C" int aslsd_set_events(aslsd_ctx* ctx, int d, const int64_t* n_events,
     tab_off[i + 1] = tab_off[i] + tab_len[i] + 1;
   }
   const size_t n_tot = (size_t)off[d];
-  // one pass over the caller's arrays: copy into the pinned block, check the order
-  if (n_tot > ctx->h_events_cap) {
+  // the pinned staging block may still feed the copies of the previous call
+  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  ctx->verdict_pending = false;    // the events it was about are replaced
+  // Arrays that are already page-locked (cudaHostAlloc / cudaHostRegister, e.g. pinned torch
+  // tensors) are uploaded from where they are and read in place by the host-side planning: no
+  // staging copy, and their order is checked on the device behind the transfer (the host never
+  // streams through them).  They must stay valid and unchanged until the next aslsd_set_events.
+  std::vector<char> in_place(d, 0);
+  size_t n_staged = 0;
+  for (int i = 0; i < d; ++i) {
+    cudaPointerAttributes attr;
+    if (n_events[i] > 0 && times[i] && cudaPointerGetAttributes(&attr, times[i]) == cudaSuccess &&
+        attr.type == cudaMemoryTypeHost)
+      in_place[i] = 1;
+    else
+      n_staged += (size_t)(off[i + 1] - off[i]);
+  }
+  cudaGetLastError();   // older runtimes flag unregistered host memory as an error
+  // one pass over the other arrays: copy into the pinned block, check the order
+  if (n_staged > 0 && n_tot > ctx->h_events_cap) {
     if (ctx->h_events) CUDA_TRY(ctx, cudaFreeHost(ctx->h_events));
     ctx->h_events = nullptr;
     ctx->h_events_cap = 0;
     CUDA_TRY(ctx, cudaMallocHost((void**)&ctx->h_events, sizeof(double) * (n_tot + n_tot / 8)));
     ctx->h_events_cap = n_tot + n_tot / 8;
+  }
+  if (!ctx->h_pad) {
+    CUDA_TRY(ctx, cudaMallocHost((void**)&ctx->h_pad, sizeof(double) * 4));
+    for (int q = 0; q < 4; ++q) ctx->h_pad[q] = 1.7e308;
   }
   int rc;
   if ((rc = ensure_device_buffer(ctx, (void**)&ctx->d_times, &ctx->times_cap, sizeof(double) * n_tot))) return rc;
@@ -157,6 +223,9 @@ extern "C" int aslsd_set_events(aslsd_ctx* ctx, int d, const int64_t* n_events,
   ctx->weight_dim.clear();
   if (d != ctx->d) ctx->model_epoch++;
   ctx->h_times.assign(d, nullptr);
+  bool any_in_place = false;
+  for (int i = 0; i < d; ++i) any_in_place |= in_place[i] != 0;
+  CUDA_TRY(ctx, cudaMemsetAsync(ctx->d_flag, 0, sizeof(int), ctx->stream));
   // Host pass (copy into the pinned block + order check) split into segments over a few
   // threads; the thread that completes a type issues its host -> device copy, so the
   // transfer of one type overlaps the host pass over the others.
@@ -167,12 +236,22 @@ extern "C" int aslsd_set_events(aslsd_ctx* ctx, int d, const int64_t* n_events,
   for (int i = 0; i < d; ++i) {
     const int64_t n = n_events[i];
     int n_seg = 0;
-    for (int64_t a = 0; a < n || (a == 0 && n_seg == 0); a += seg_len) {
+    for (int64_t a = 0; !in_place[i] && (a < n || (a == 0 && n_seg == 0)); a += seg_len) {
       segs.push_back(Seg{i, a, std::min<int64_t>(n, a + seg_len)});
       ++n_seg;
     }
     left[i].store(n_seg);
-    ctx->h_times[i] = ctx->h_events + off[i];
+    ctx->h_times[i] = in_place[i] ? times[i] : ctx->h_events + off[i];
+    if (in_place[i]) {
+      // the transfer starts now and runs while the threads below check the order
+      const int64_t len = off[i + 1] - off[i];
+      CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_times + off[i], times[i], sizeof(double) * (size_t)n,
+                                    cudaMemcpyHostToDevice, ctx->stream));
+      CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_times + off[i] + n, ctx->h_pad, sizeof(double) * (size_t)(len - n),
+                                    cudaMemcpyHostToDevice, ctx->stream));
+      check_sorted_kernel<<<(unsigned)std::min<int64_t>(1184, (n + 255) / 256), 256, 0, ctx->stream>>>(
+          ctx->d_times + off[i], n, ctx->d_flag);
+    }
   }
   std::atomic<size_t> next(0);
   std::atomic<int> bad(0), cuda_err(0);
@@ -182,21 +261,22 @@ extern "C" int aslsd_set_events(aslsd_ctx* ctx, int d, const int64_t* n_events,
       const size_t q = next.fetch_add(1);
       if (q >= segs.size()) break;
       const Seg sg = segs[q];
-      double* dst = ctx->h_events + off[sg.dim];
+      const bool stage = !in_place[sg.dim];
+      double* dst = stage ? ctx->h_events + off[sg.dim] : nullptr;
       const double* src = times[sg.dim];
       bool ok = true;
-      if (sg.b > sg.a) {
-        double prev = sg.a > 0 ? src[sg.a - 1] : src[0];
-        ok = prev == prev;
-        for (int64_t m = sg.a; m < sg.b; ++m) {
-          const double v = src[m];
-          ok &= (v >= prev);
-          prev = v;
-          dst[m] = v;
-        }
+      // cache-sized chunks: a branch-free (vectorisable) order check, then a plain memcpy of the
+      // chunk while it is still in cache.  v >= prev is false for NaNs on either side.
+      const int64_t chunk = 4096;
+      for (int64_t c = sg.a; c < sg.b; c += chunk) {
+        const int64_t e = std::min<int64_t>(sg.b, c + chunk);
+        int okc = src[c] >= (c > 0 ? src[c - 1] : src[0]);
+        for (int64_t m = c + 1; m < e; ++m) okc &= (int)(src[m] >= src[m - 1]);
+        ok &= okc != 0;
+        if (stage) std::memcpy(dst + c, src + c, sizeof(double) * (size_t)(e - c));
       }
       if (!ok) bad.store(1);
-      if (left[sg.dim].fetch_sub(1) == 1) {
+      if (left[sg.dim].fetch_sub(1) == 1 && stage) {
         // last segment of this type: pad with a huge finite value (the device side may
         // over-read, never uses it) and start the copy
         const int64_t len = off[sg.dim + 1] - off[sg.dim];
@@ -209,7 +289,9 @@ extern "C" int aslsd_set_events(aslsd_ctx* ctx, int d, const int64_t* n_events,
   };
   {
     const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
-    const size_t n_thr = std::min<size_t>({(size_t)hw, (size_t)8, segs.size()});
+    size_t cap = ASLSD_STAGE_THREADS;
+    if (const char* e = std::getenv("ASLSD_STAGE_THREADS")) cap = std::max(1, std::atoi(e));
+    const size_t n_thr = std::min<size_t>({(size_t)hw, cap, std::max<size_t>(1, segs.size())});
     std::vector<std::thread> pool;
     for (size_t q = 1; q < n_thr; ++q) pool.emplace_back(worker);
     worker();
@@ -231,7 +313,8 @@ extern "C" int aslsd_set_events(aslsd_ctx* ctx, int d, const int64_t* n_events,
   ctx->tab_t0.assign(d, 0.);
   ctx->tab_w.assign(d, 1.);
   ctx->times_len = off[d];
-  std::vector<DimDev> dims(d);
+  ctx->h_dims.assign(sizeof(DimDev) * (size_t)d, 0);
+  DimDev* dims = reinterpret_cast<DimDev*>(ctx->h_dims.data());
   for (int i = 0; i < d; ++i) {
     if (n_events[i] > 0) {
       const double t0 = times[i][0], t1 = times[i][n_events[i] - 1];
@@ -248,8 +331,9 @@ extern "C" int aslsd_set_events(aslsd_ctx* ctx, int d, const int64_t* n_events,
     dims[i].t0 = ctx->tab_t0[i];
     dims[i].w = ctx->tab_w[i];
     dims[i].inv_w = 1. / ctx->tab_w[i];
+    dims[i].bad = ctx->d_flag;
   }
-  CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_dims, dims.data(), sizeof(DimDev) * d, cudaMemcpyHostToDevice,
+  CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_dims, dims, sizeof(DimDev) * d, cudaMemcpyHostToDevice,
                                 ctx->stream));
   for (int i = 0; i < d; ++i) {
     const int64_t nb = tab_len[i];
@@ -259,7 +343,17 @@ extern "C" int aslsd_set_events(aslsd_ctx* ctx, int d, const int64_t* n_events,
         dims[i].t, dims[i].n, ctx->d_tab + tab_off[i], nb, dims[i].t0, dims[i].w);
   }
   CUDA_TRY(ctx, cudaGetLastError());
-  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));   // `dims` is a stack object
+  // no synchronisation here: the copies and the table kernels are ordered before whatever the
+  // caller enqueues next on this stream, and they overlap its host-side planning
+  if (any_in_place) {
+    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->h_flag, ctx->d_flag, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(ctx, cudaEventRecord(ctx->ev_flag, ctx->stream));
+    ctx->verdict_pending = true;
+    // ASLSD_OPT_ASYNC_EVENTS off: wait for the device's verdict, so that an order violation is
+    // reported by this call like for pageable inputs; on: the next call that waits for the
+    // device reports it
+    if (!ctx->async_events) return events_verdict(ctx, true);
+  }
   return ASLSD_OK;
 }
 
@@ -271,6 +365,7 @@ extern "C" int aslsd_set_weights(aslsd_ctx* ctx, int n_vec, const int32_t* dims,
     return aslsd_fail(ctx, ASLSD_ERR_ARG, "set_weights: bad arguments");
   if (ctx->d == 0 || !ctx->d_times) return aslsd_fail(ctx, ASLSD_ERR_ARG, "set_weights: no events set");
   CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  if (int vrc = events_verdict(ctx, true)) return vrc;
   std::vector<int64_t> off(n_vec + 1, 0);
   for (int v = 0; v < n_vec; ++v) {
     if (dims[v] < 0 || dims[v] >= ctx->d || !vals[v])

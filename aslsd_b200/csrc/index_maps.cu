@@ -93,6 +93,7 @@ static int compute_lag_counts(aslsd_ctx* ctx, std::vector<int64_t>& H) {
 extern "C" int aslsd_index_map_sizes(aslsd_ctx* ctx, int64_t* kappa_len, int64_t* varpi_len) {
   if (!ctx || ctx->d == 0 || !ctx->d_times) return aslsd_fail(ctx, ASLSD_ERR_ARG, "index maps: no events set");
   CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  if (int vrc = events_verdict(ctx, true)) return vrc;
   std::vector<int64_t> H;
   int rc = compute_lag_counts(ctx, H);
   if (rc) return rc;
@@ -109,6 +110,7 @@ extern "C" int aslsd_index_maps(aslsd_ctx* ctx, int64_t* const* kappa_out, int64
                                 int64_t* const* lag_sizes_out) {
   if (!ctx || ctx->d == 0 || !ctx->d_times) return aslsd_fail(ctx, ASLSD_ERR_ARG, "index maps: no events set");
   CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  if (int vrc = events_verdict(ctx, true)) return vrc;
   const int d = ctx->d;
   std::vector<int64_t> H;
   int rc = compute_lag_counts(ctx, H);

@@ -219,6 +219,7 @@ lag_moment_kernel(const DimDev* __restrict__ dims, const QStreamDev* __restrict_
   const QStreamDev S = streams[find_stream(streams, n_streams, wu)];
   const int chunk = (int)(wu - S.wu_first);
   const DimDev Dt = dims[S.tgt_dim], Ds = dims[S.src_dim];
+  if (*Dt.bad) return;   // unsorted upload (aslsd_set_events): the verdict reaches the host later
   const int64_t m_begin = S.m_lo + (int64_t)chunk * S.tpw;
   const int64_t m_end = min(S.m_hi, m_begin + S.tpw);
   const bool same = S.same != 0;
@@ -630,6 +631,7 @@ lag_boundary_kernel(const DimDev* __restrict__ dims, const QStreamDev* __restric
   const BoundaryGroupDev G = groups[blockIdx.x];
   const QStreamDev S = streams[G.stream];
   const DimDev Dt = dims[S.tgt_dim], Ds = dims[S.src_dim];
+  if (*Dt.bad) return;   // unsorted upload (aslsd_set_events): the verdict reaches the host later
   const bool same = S.same != 0;
   unsigned long long n_eval = 0;
   for (int64_t m0 = G.m_lo; m0 < G.m_hi; m0 += LB_NT) {

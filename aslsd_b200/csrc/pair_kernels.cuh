@@ -111,6 +111,7 @@ pair_kernel(const DimDev* __restrict__ dims, const ItemDev* __restrict__ items, 
   const ItemDev it = items[it_ix];
   const int chunk = (int)(wu - it.wu_first);
   const DimDev Dt = dims[it.tgt_dim], Ds = dims[it.src_dim];
+  if (*Dt.bad) return;   // unsorted upload (aslsd_set_events): the verdict reaches the host later
   const int64_t m_begin = it.m_lo + (int64_t)chunk * it.tpw;
   const int64_t m_end = min(it.m_hi, m_begin + it.tpw);
   const int mask = it.mask;

@@ -77,6 +77,7 @@ extern "C" int aslsd_point_sums(aslsd_ctx* ctx, int k, const double* x_k, int ki
   if (!ctx->has_model) return aslsd_fail(ctx, ASLSD_ERR_ARG, "point_sums: no model set");
   if (!ctx->d_times || (int)ctx->n_events.size() != ctx->d)
     return aslsd_fail(ctx, ASLSD_ERR_ARG, "point_sums: no events set");
+  if (int vrc = events_verdict(ctx, true)) return vrc;
   const int d = ctx->d;
   if (k < 0 || k >= d) return aslsd_fail(ctx, ASLSD_ERR_ARG, "point_sums: bad k");
   SumPlan P;

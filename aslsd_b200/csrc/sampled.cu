@@ -298,6 +298,7 @@ extern "C" int aslsd_sampled_sums(aslsd_ctx* ctx, int k, const double* x_k, int 
   if (!ctx || !x_k || n_terms < 0 || (n_terms && (!terms || !stratum_offsets || !sum_out)))
     return aslsd_fail(ctx, ASLSD_ERR_ARG, "sampled sums: bad arguments");
   if (n_terms == 0) return ASLSD_OK;
+  if (int vrc = events_verdict(ctx, true)) return vrc;
   SumPlan P;
   int rc = build_plan(ctx, k, x_k, flags | ASLSD_F, nullptr, nullptr, true, P);
   if (rc) return rc;

@@ -124,6 +124,14 @@ class Engine:
         event pairs.  Off: every call recomputes them (benchmark setting)."""
         self.set_option(capi.OPT_WEIGHT_CACHE, 1 if enabled else 0)
 
+    def use_async_events(self, enabled=True):
+        """Page-locked event arrays are uploaded in place and checked for order on the device.
+        Off (default): ``set_events`` waits for that verdict and raises on unsorted times, as it
+        does for pageable arrays.  On: it returns once the transfer is enqueued, so the planning
+        of the next call overlaps the transfer; unsorted times then raise at the next call that
+        waits for the device."""
+        self.set_option(capi.OPT_ASYNC_EVENTS, 1 if enabled else 0)
+
     def last_work_counts(self):
         """Work of the last exact-sum call (see aslsd_last_work_counts)."""
         c = np.zeros(8, dtype=np.int64)
@@ -155,6 +163,8 @@ class Engine:
                                                float(T_f)))
         self.d, self.n_events, self.T_f = d, n_events, float(T_f)
         self._events_key = None
+        # page-locked arrays are read in place by the library (no staging copy): keep them alive
+        self._events_arrays = times
 
     def index_maps(self, want_kappa=True, want_varpi=True, want_lag_sizes=True):
         """kappa, varpi, lag_sizes as d x d lists of int64 arrays

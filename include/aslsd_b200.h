@@ -56,10 +56,16 @@ enum {
   ASLSD_OPT_LAG_QUADRATURE = 1, /* 1 (default): interior targets of every double sum go through the
                                   lag quadrature (one pass per pair of event streams);
                                   0: per-item pair kernels only */
-  ASLSD_OPT_WEIGHT_CACHE = 2   /* 1 (default): the quadrature weights - a function of the event streams
+  ASLSD_OPT_WEIGHT_CACHE = 2,  /* 1 (default): the quadrature weights - a function of the event streams
                                   and the lag windows only - are kept between calls while the events,
                                   the model, the target block and the non-omega parameters stay the
                                   same (the iterations of a fit); 0: recomputed on every call */
+  ASLSD_OPT_ASYNC_EVENTS = 3   /* page-locked inputs of aslsd_set_events are checked for order on the
+                                  device, behind their transfer.  0 (default): aslsd_set_events waits
+                                  for that verdict; 1: it returns as soon as the transfer is enqueued
+                                  and a violation is reported (ASLSD_ERR_ARG, the context then has no
+                                  events) by the next call that waits for the device - results of
+                                  calls made in between are void */
 };
 
 /* ---- lifetime ------------------------------------------------------------------ */
@@ -85,7 +91,13 @@ int aslsd_measure_fp64_peak(aslsd_ctx* ctx, double* tflops);
 
 /* ---- events: replaces ProcessPath.__init__ data members ---------------------------
  * stats/events/process_path.py:63-106 (list_times, T_f, n_events, list_times2end).
- * times[i] is the sorted fp64 array of the n_events[i] events of type i. */
+ * times[i] is the sorted fp64 array of the n_events[i] events of type i.
+ * Pageable arrays are copied into the context's own page-locked block (and checked for order)
+ * by a few host threads and uploaded from there; the call returns with the transfers enqueued.
+ * Arrays that are already page-locked (cudaHostAlloc / cudaHostRegister) are uploaded from
+ * where they are, checked for order on the device (ASLSD_OPT_ASYNC_EVENTS) and read in place
+ * by the host-side planning: they must stay valid and unchanged until the next
+ * aslsd_set_events or aslsd_destroy. */
 int aslsd_set_events(aslsd_ctx* ctx, int d, const int64_t* n_events,
                      const double* const* times, double T_f);
 
