@@ -27,20 +27,36 @@ def time_block_ranges(list_times, world_size):
     if world_size == 1:
         return [[(0, len(t)) for t in list_times]]
     n_tot = sum(len(t) for t in list_times)
-    # quantiles of the pooled times without materialising the pooled sort: bisection on time,
-    # all cuts at once (one vectorised searchsorted per type and step)
+    # Quantiles of the pooled times without materialising the pooled sort: a bracketing search on
+    # the cut time, all cuts at once (one vectorised searchsorted per type and step), alternating
+    # an interpolation step (event counts are close to linear in time) with a bisection step.
+    # A cut is accepted once the number of events below it is within `tol` of its quantile:
+    # any cut time partitions the events consistently, the count only balances the load.
     t_min = min(t[0] for t in list_times if len(t))
     t_max = max(t[-1] for t in list_times if len(t))
-    targets = np.array([n_tot * g // world_size for g in range(1, world_size)], dtype=np.int64)
+    targets = np.array([n_tot * g // world_size for g in range(1, world_size)], dtype=np.float64)
+    tol = max(len(list_times), n_tot >> 16)
     lo = np.full(world_size - 1, t_min, dtype=np.float64)
     hi = np.full(world_size - 1, t_max, dtype=np.float64)
-    for _ in range(64):
-        mid = 0.5 * (lo + hi)
-        below = sum(np.searchsorted(t, mid, side='left') for t in list_times)
+    c_lo = np.zeros(world_size - 1)
+    c_hi = np.full(world_size - 1, float(n_tot))
+    done = np.zeros(world_size - 1, dtype=bool)
+    for it in range(128):
+        if it % 2 == 0:
+            frac = np.clip((targets - c_lo) / np.maximum(c_hi - c_lo, 1.), 0.02, 0.98)
+        else:
+            frac = 0.5
+        mid = np.where(done, hi, lo + frac * (hi - lo))
+        below = sum(np.searchsorted(t, mid, side='left') for t in list_times).astype(np.float64)
+        hit = np.abs(below - targets) <= tol
         go_up = below < targets
-        lo = np.where(go_up, mid, lo)
-        hi = np.where(go_up, hi, mid)
-        if np.all(hi - lo <= 1e-12 * max(abs(t_max), 1.)):
+        # an accepted cut collapses its bracket onto itself
+        lo = np.where(done, lo, np.where(hit | go_up, mid, lo))
+        hi = np.where(done, hi, np.where(hit | ~go_up, mid, hi))
+        c_lo = np.where(done, c_lo, np.where(hit | go_up, below, c_lo))
+        c_hi = np.where(done, c_hi, np.where(hit | ~go_up, below, c_hi))
+        done |= hit
+        if np.all(done | (hi - lo <= 1e-12 * max(abs(t_max), 1.))):
             break
     cuts = list(hi)
     edges = [[0] + [int(np.searchsorted(t, c, side='left')) for c in cuts] + [len(t)]

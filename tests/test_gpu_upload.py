@@ -84,3 +84,37 @@ def test_unsorted_page_locked_inputs_are_rejected(engine, async_events, defect):
     a = engine.exact_sums_packed(0, case_x(name)[0])
     engine.set_events(good, T_f)
     np.testing.assert_array_equal(a, engine.exact_sums_packed(0, case_x(name)[0]))
+
+
+def test_views_into_page_locked_arrays_are_uploaded_in_place(engine):
+    """The time-block shards of ShardedExactSums.set_events are slices of the caller's arrays:
+    interior pointers of a page-locked allocation, at odd offsets too."""
+    import types
+    from aslsd_b200.distributed import ShardedExactSums
+    name = 'sbf2d3'
+    model = CASES[name][0]
+    rng = np.random.default_rng(9)
+    T_f = 4000.
+    times = [np.sort(rng.uniform(0, T_f, size=n)) for n in (9001, 7000)]
+    xs = case_x(name)
+    engine.set_model(model)
+    engine.set_events(times, T_f)
+    want = engine.exact_sums_batch([0, 1], xs)
+    engine.use_async_events(True)
+    pinned = _pinned(times)
+    # rank 1 of 3: its block plus the max-lag halo, cut out of the pinned arrays
+    import torch
+    # no collective: the shards are summed below
+    fake_dist = types.SimpleNamespace(all_reduce=lambda *a, **k: None, ReduceOp=types.SimpleNamespace(SUM=None))
+    parts = []
+    for rank in range(3):
+        sh = ShardedExactSums(engine, pinned, rank=rank, world_size=3, dist=fake_dist,
+                              device=torch.device('cuda', 0))
+        sh.set_events(pinned, T_f, [0, 1], xs)
+        assert all(len(t) < len(p) for t, p in zip(engine._events_arrays, pinned))
+        raw = sh.launch_batch([0, 1], xs)
+        parts.append(raw.cpu().numpy().copy())
+    total = parts[0] + parts[1] + parts[2]
+    got = engine.exact_assemble_batch([0, 1], xs, total)
+    for a, b in zip(got, want):
+        np.testing.assert_allclose(a, b, rtol=1e-12, atol=1e-12)
