@@ -98,14 +98,46 @@ int choice_no_replace(Pcg& g, int64_t pop, int64_t size, int64_t* out, std::vect
                       std::vector<uint64_t>& set) {
   if (size < 0 || pop < 0 || size > pop) return ASLSD_ERR_ARG;
   if (size == 0) return ASLSD_OK;
+  if (size == 1) {
+    // Floyd's algorithm with one element: a single bounded draw on [0, pop - 1], nothing to shuffle
+    out[0] = (int64_t)g.bounded((uint64_t)(pop - 1));
+    return ASLSD_OK;
+  }
   if (pop > 10000 && size > pop / 50) {
-    // tail shuffle of arange(pop)
-    scratch.resize((size_t)pop);
-    for (int64_t q = 0; q < pop; ++q) scratch[(size_t)q] = q;
+    // tail shuffle of arange(pop): i from pop - 1 down to first, j uniform on [0, i], swap
     int64_t first = pop - size;
     if (first < 1) first = 1;
-    shuffle_int(g, pop, first, scratch.data());
-    for (int64_t q = 0; q < size; ++q) out[q] = scratch[(size_t)(pop - size + q)];
+    if (size * 4 >= pop) {
+      scratch.resize((size_t)pop);
+      for (int64_t q = 0; q < pop; ++q) scratch[(size_t)q] = q;
+      shuffle_int(g, pop, first, scratch.data());
+      for (int64_t q = 0; q < size; ++q) out[q] = scratch[(size_t)(pop - size + q)];
+      return ASLSD_OK;
+    }
+    // The same swaps without materialising arange(pop): position i is final once its own step
+    // is done (later steps only touch positions below it), so only the displaced values at the
+    // swap targets j are kept, in an open-addressing map (absent key = identity).
+    uint64_t mask = (uint64_t)(2 * size);
+    mask |= mask >> 1; mask |= mask >> 2; mask |= mask >> 4; mask |= mask >> 8; mask |= mask >> 16; mask |= mask >> 32;
+    set.assign(2 * ((size_t)mask + 1), ~(uint64_t)0);   // (key, value) pairs
+    auto slot = [&](uint64_t key) {
+      uint64_t loc = (key * 0x9E3779B97F4A7C15ULL >> 20) & mask;
+      while (set[2 * loc] != ~(uint64_t)0 && set[2 * loc] != key) loc = (loc + 1) & mask;
+      return loc;
+    };
+    for (int64_t i = pop - 1; i >= first; --i) {
+      const uint64_t li = slot((uint64_t)i);
+      const int64_t vi = set[2 * li] == (uint64_t)i ? (int64_t)set[2 * li + 1] : i;
+      const int64_t j = (int64_t)g.bounded((uint64_t)i);
+      int64_t vj = vi;
+      if (j != i) {
+        const uint64_t lj = slot((uint64_t)j);
+        vj = set[2 * lj] == (uint64_t)j ? (int64_t)set[2 * lj + 1] : j;
+        set[2 * lj] = (uint64_t)j;
+        set[2 * lj + 1] = (uint64_t)vi;
+      }
+      out[i - (pop - size)] = vj;
+    }
     return ASLSD_OK;
   }
   // Floyd's algorithm; set size = smallest power of two above 1.2 * size
@@ -180,7 +212,8 @@ extern "C" int aslsd_sample_double_ix(aslsd_pcg64* gen, int64_t n_strata, const 
       if (width <= 0 && ns > 0) return ASLSD_ERR_ARG;
       lags.resize((size_t)ns);
       for (int64_t q = 0; q < ns; ++q) lags[(size_t)q] = (int64_t)g.bounded((uint64_t)(width - 1));
-      count.assign((size_t)width, 0);
+      // `count` is all zero between strata: only the touched entries are reset below
+      if ((int64_t)count.size() < width) count.resize((size_t)width, 0);
       order.clear();
       for (int64_t q = 0; q < ns; ++q) {
         if (count[(size_t)lags[(size_t)q]]++ == 0) order.push_back(lags[(size_t)q]);
@@ -201,6 +234,7 @@ extern "C" int aslsd_sample_double_ix(aslsd_pcg64* gen, int64_t n_strata, const 
           n[w + q] = kappa_ji[m[w + q]] - h + 1;
         }
         w += n_h;
+        count[(size_t)rel] = 0;
       }
     }
     pos += ns;

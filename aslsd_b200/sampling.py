@@ -51,12 +51,32 @@ def _store_state(rng, g):
 
 
 def sample_single_ix_stratified(strata, n_samples, rng):
-    """samples[s] = lo_s + choice(hi_s - lo_s + 1, n_samples[s], replace=False)."""
-    out = []
-    for (lo, hi), n in zip(strata, n_samples):
+    """samples[s] = lo_s + choice(hi_s - lo_s + 1, n_samples[s], replace=False).  With a PCG64
+    generator the draws are made by the native restatement of ``Generator.choice``
+    (aslsd_rng_choice: same values, same final state, tests/test_sampling_stream.py) - numpy
+    builds arange(population) for every large stratum, the native tail shuffle only touches the
+    sampled positions."""
+    for lo, hi in strata:
         if lo > hi:
             raise ValueError('m_inf should be smaller than m_sup')
-        out.append(lo + rng.choice(hi - lo + 1, size=n, replace=False))
+    native = _native_state(rng) if len(strata) else None
+    if native is None:
+        return [lo + rng.choice(hi - lo + 1, size=n, replace=False) for (lo, hi), n in zip(strata, n_samples)]
+    lib, g = native
+    out = []
+    for (lo, hi), n in zip(strata, n_samples):
+        n = int(n)
+        pop = int(hi) - int(lo) + 1
+        if n > pop:
+            raise ValueError('Cannot take a larger sample than population when replace is False')
+        buf = np.empty(n, dtype=np.int64)
+        rc = lib.aslsd_rng_choice(ctypes.byref(g), pop, n, 0, capi.ptr_i64(buf))
+        if rc != 0:
+            raise ValueError('Cannot take a larger sample than population when replace is False')
+        if lo:
+            buf += int(lo)
+        out.append(buf)
+    _store_state(rng, g)
     return out
 
 

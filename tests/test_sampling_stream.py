@@ -53,7 +53,7 @@ def test_native_choice_is_numpy_choice():
     from aslsd_b200 import capi
     lib = capi.load_library()
     cases = [(10, 3), (1, 1), (5, 5), (1000, 1), (1000, 37), (9999, 500), (10001, 150), (10001, 201),
-             (10001, 300), (50000, 999), (50000, 1001), (50000, 20000), (200000, 1), (123457, 12),
+             (10001, 300), (50000, 999), (50000, 1001), (50000, 12000), (50000, 12600), (50000, 20000), (10001, 2400), (10001, 2600), (200000, 1), (123457, 12),
              (70000, 70000), (3, 0)]
     for seed in (1, 2):
         for pop, n in cases:
@@ -93,4 +93,19 @@ def test_native_term_sampler_keeps_the_reference_stream():
         for g_s, w_s in zip(got, want):
             np.testing.assert_array_equal(g_s['m'], w_s['m'])
             np.testing.assert_array_equal(g_s['n'], w_s['n'])
+        assert str(a.bit_generator.state) == str(b.bit_generator.state)
+
+
+def test_native_single_index_sampler_keeps_the_reference_stream():
+    """sample_single_ix_stratified through the native choice: numpy's values and final state."""
+    strata = [(0, 49), (50, 20049), (20050, 70049), (70050, 70050), (70051, 200000)]
+    n_samples = [50, 300, 1500, 1, np.int64(40000)]
+    for seed in (3, 4):
+        a, b = np.random.default_rng(seed), np.random.default_rng(seed)
+        if seed == 4:
+            a.integers(0, 7), b.integers(0, 7)
+        want = [lo + a.choice(hi - lo + 1, size=n, replace=False) for (lo, hi), n in zip(strata, n_samples)]
+        got = sampling.sample_single_ix_stratified(strata, n_samples, b)
+        for w, g in zip(want, got):
+            np.testing.assert_array_equal(g, w)
         assert str(a.bit_generator.state) == str(b.bit_generator.state)
