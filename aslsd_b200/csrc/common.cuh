@@ -135,6 +135,10 @@ struct aslsd_ctx {
   double* d_raw = nullptr; size_t raw_cap = 0;
   unsigned long long* d_counts = nullptr; size_t counts_cap = 0;
   void* h_pinned = nullptr; size_t pinned_cap = 0;
+  // page-locked staging of the plan tables (items, streams, rows, boundary groups); ev_tables marks
+  // the end of their last transfer, so the block is rewritten only once the device has read it
+  void* h_tables = nullptr; size_t tables_cap = 0;
+  cudaEvent_t ev_tables = nullptr; bool tables_in_flight = false;
   void* d_sample = nullptr; size_t sample_cap = 0;
 
   // host copy of the event times (planning), inside one pinned staging block that is

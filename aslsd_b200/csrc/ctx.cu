@@ -53,6 +53,7 @@ extern "C" int aslsd_create(aslsd_ctx** out, int device) {
       cudaEventCreate(&ctx->ev0) != cudaSuccess || cudaEventCreate(&ctx->ev1) != cudaSuccess ||
       cudaEventCreate(&ctx->ev_q0) != cudaSuccess || cudaEventCreate(&ctx->ev_q1) != cudaSuccess ||
       cudaEventCreateWithFlags(&ctx->ev_flag, cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&ctx->ev_tables, cudaEventDisableTiming) != cudaSuccess ||
       cudaMalloc((void**)&ctx->d_flag, sizeof(int)) != cudaSuccess ||
       cudaMallocHost((void**)&ctx->h_flag, sizeof(int)) != cudaSuccess ||
       cudaMemset(ctx->d_flag, 0, sizeof(int)) != cudaSuccess) {
@@ -85,6 +86,8 @@ extern "C" int aslsd_destroy(aslsd_ctx* ctx) {
   if (ctx->h_events) cudaFreeHost(ctx->h_events);
   if (ctx->h_pad) cudaFreeHost(ctx->h_pad);
   if (ctx->h_flag) cudaFreeHost(ctx->h_flag);
+  if (ctx->h_tables) cudaFreeHost(ctx->h_tables);
+  cudaEventDestroy(ctx->ev_tables);
   cudaFree(ctx->d_flag);
   cudaEventDestroy(ctx->ev_flag);
   cudaEventDestroy(ctx->ev0);

@@ -23,6 +23,9 @@
 #include <cmath>
 #include <cstring>
 #include <atomic>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include <map>
 #include <thread>
 
@@ -55,6 +58,8 @@ struct BatchPlan {
   std::vector<BoundaryGroupDev> bgroups;        // targets near T_f of the quadrature rows, by family
   int bfam_first[ITEM_N_FAMILIES], bfam_count[ITEM_N_FAMILIES];
   int64_t n_wu_q = 0, n_wu_q_plain = 0, n_q_partials = 0, n_q_weights = 0, n_q_evals = 0;
+  // scratch of build_work, kept between calls (no reallocation when only the events change)
+  std::vector<ItemDev> scratch_q[ITEM_N_FAMILIES], scratch_f[ITEM_N_FAMILIES];
   int q_jmax = 0;
   size_t q_smem = 0;
 };
@@ -108,7 +113,7 @@ static double row_scale(const ItemDev& it) {
 // quadrature stream, if the geometry allows it.
 static void build_stream(const aslsd_ctx* ctx, BatchPlan& B, const std::vector<int64_t>& group,
                          std::vector<bool>& fast, std::vector<int64_t>& boundary_from,
-                         std::vector<ItemDev> qfam[ITEM_N_FAMILIES]) {
+                         std::vector<ItemDev>* qfam) {
   const ItemDev first = B.rows[group[0]];
   double t_int = 0., s_max = 0., scale = 1e300;
   for (int64_t r : group) {
@@ -233,7 +238,8 @@ static int build_work(aslsd_ctx* ctx, const int64_t* m_lo, const int64_t* m_hi, 
   const size_t n_rows = B.rows.size();
   std::vector<bool> fast(n_rows, false);
   std::vector<int64_t> boundary_from(n_rows, 0);
-  std::vector<ItemDev> qfam[ITEM_N_FAMILIES];
+  std::vector<ItemDev>* qfam = B.scratch_q;
+  for (int f = 0; f < ITEM_N_FAMILIES; ++f) qfam[f].clear();
   if (ctx->use_quadrature) {
     // group the pair rows by (streams, target block), in row order
     // (marked models: also by the pair of weight vectors - weighted moments)
@@ -287,7 +293,8 @@ static int build_work(aslsd_ctx* ctx, const int64_t* m_lo, const int64_t* m_hi, 
     B.qrows.insert(B.qrows.end(), qfam[f].begin(), qfam[f].end());
   }
   // ---- per-item kernels: rows outside the quadrature entirely, the others beyond the interior ----
-  std::vector<ItemDev> fam_items[ITEM_N_FAMILIES];
+  std::vector<ItemDev>* fam_items = B.scratch_f;
+  for (int f = 0; f < ITEM_N_FAMILIES; ++f) fam_items[f].clear();
   for (size_t r = 0; r < n_rows; ++r) {
     ItemDev it = B.rows[r];
     it.dst_row = (int64_t)r;
@@ -398,7 +405,12 @@ static int get_batch(aslsd_ctx* ctx, int n_k, const int* ks, const double* const
   }
   if (with_work && !(C->has_work && C->key_work == key_work)) {
     C->has_work = false;
+    const auto t0 = std::chrono::steady_clock::now();
     if ((rc = build_work(ctx, m_lo, m_hi, *C))) return rc;
+    if (std::getenv("ASLSD_TRACE"))
+      std::fprintf(stderr, "[aslsd] build_work %.3f ms (%zu rows, %zu streams)\n",
+                   1e3 * std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count(),
+                   C->rows.size(), C->qstreams.size());
     C->key_work.swap(key_work);
     C->has_work = true;
   }
@@ -459,7 +471,16 @@ static void launch_boundary(aslsd_ctx* ctx, const BatchPlan& B, const QStreamDev
 }
 
 // Launch everything; leaves raw[row][comp] in raw_device (zeroed here first).
+static int run_batch_impl(aslsd_ctx* ctx, BatchPlan& B, double* raw_device);
 static int run_batch(aslsd_ctx* ctx, BatchPlan& B, double* raw_device) {
+  const auto t0 = std::chrono::steady_clock::now();
+  const int rc = run_batch_impl(ctx, B, raw_device);
+  if (std::getenv("ASLSD_TRACE"))
+    std::fprintf(stderr, "[aslsd] run_batch host side %.3f ms\n",
+                 1e3 * std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count());
+  return rc;
+}
+static int run_batch_impl(aslsd_ctx* ctx, BatchPlan& B, double* raw_device) {
   CUDA_TRY(ctx, cudaSetDevice(ctx->device));
   const size_t n_items = B.items.size(), n_rows = B.rows.size();
   int rc;
@@ -481,10 +502,7 @@ static int run_batch(aslsd_ctx* ctx, BatchPlan& B, double* raw_device) {
                                  ((size_t)B.n_wu + n_items + (size_t)B.n_wu_q + B.bgroups.size() + 1) *
                                      sizeof(unsigned long long))))
     return rc;
-  if (n_items && !B.device_resident)
-    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_items, B.items.data(), n_items * sizeof(ItemDev),
-                                  cudaMemcpyHostToDevice, ctx->stream));
-  // quadrature tables: one block [streams | rows]
+  // quadrature tables: one block [streams | rows | boundary groups]
   const bool quad = !B.qstreams.empty();
   const size_t o_s = 0;
   const size_t o_r = o_s + ((B.qstreams.size() * sizeof(QStreamDev) + 15) & ~(size_t)15);
@@ -497,16 +515,37 @@ static int run_batch(aslsd_ctx* ctx, BatchPlan& B, double* raw_device) {
     if ((rc = ensure_device_buffer(ctx, (void**)&ctx->d_q_weights, &ctx->q_weights_cap,
                                    (size_t)B.n_q_weights * sizeof(double)))) return rc;
   }
-  if (quad && !B.device_resident) {
-    if ((rc = ensure_device_buffer(ctx, &ctx->d_qtab, &ctx->qtab_cap, q_bytes))) return rc;
-    if ((rc = ensure_pinned_buffer(ctx, q_bytes))) return rc;
-    char* hp = (char*)ctx->h_pinned;
-    std::memcpy(hp + o_s, B.qstreams.data(), B.qstreams.size() * sizeof(QStreamDev));
-    std::memcpy(hp + o_r, B.qrows.data(), B.qrows.size() * sizeof(ItemDev));
-    std::memcpy(hp + o_g, B.bgroups.data(), B.bgroups.size() * sizeof(BoundaryGroupDev));
-    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_qtab, hp, q_bytes, cudaMemcpyHostToDevice, ctx->stream));
-    // the pinned staging block is reused by the caller once the copy has completed
-    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  if (!B.device_resident && (n_items || quad)) {
+    // all plan tables go through one page-locked block of their own and two asynchronous
+    // transfers: no wait for the stream here (an event upload may still be in flight on it)
+    const size_t i_bytes = (n_items * sizeof(ItemDev) + 15) & ~(size_t)15;
+    const size_t need = i_bytes + (quad ? q_bytes : 0);
+    if (ctx->tables_in_flight) {
+      CUDA_TRY(ctx, cudaEventSynchronize(ctx->ev_tables));
+      ctx->tables_in_flight = false;
+    }
+    if (need > ctx->tables_cap) {
+      if (ctx->h_tables) CUDA_TRY(ctx, cudaFreeHost(ctx->h_tables));
+      ctx->h_tables = nullptr;
+      ctx->tables_cap = 0;
+      CUDA_TRY(ctx, cudaMallocHost(&ctx->h_tables, need + need / 4));
+      ctx->tables_cap = need + need / 4;
+    }
+    char* hp = (char*)ctx->h_tables;
+    if (n_items) {
+      std::memcpy(hp, B.items.data(), n_items * sizeof(ItemDev));
+      CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_items, hp, n_items * sizeof(ItemDev), cudaMemcpyHostToDevice, ctx->stream));
+    }
+    if (quad) {
+      if ((rc = ensure_device_buffer(ctx, &ctx->d_qtab, &ctx->qtab_cap, q_bytes))) return rc;
+      char* hq = hp + i_bytes;
+      std::memcpy(hq + o_s, B.qstreams.data(), B.qstreams.size() * sizeof(QStreamDev));
+      std::memcpy(hq + o_r, B.qrows.data(), B.qrows.size() * sizeof(ItemDev));
+      std::memcpy(hq + o_g, B.bgroups.data(), B.bgroups.size() * sizeof(BoundaryGroupDev));
+      CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_qtab, hq, q_bytes, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    CUDA_TRY(ctx, cudaEventRecord(ctx->ev_tables, ctx->stream));
+    ctx->tables_in_flight = true;
   }
   B.device_resident = true;
   const ItemDev* d_items = (const ItemDev*)ctx->d_items;
@@ -647,7 +686,8 @@ static void assemble_all(const aslsd_ctx* ctx, const BatchPlan& B, int n_k, cons
     for (int q = 0; q < n_k; ++q) assemble(ctx, B.plans[q], B.item_row[q], xs[q], raw, outs[q]);
     return;
   }
-  const int n_thr = std::min<int>(n_k, std::max(1u, std::min(8u, std::thread::hardware_concurrency())));
+  // (4: several ranks of a box run this at the same time)
+  const int n_thr = std::min<int>(n_k, std::max(1u, std::min(4u, std::thread::hardware_concurrency())));
   std::atomic<int> next(0);
   auto worker = [&]() {
     for (int q = next.fetch_add(1); q < n_k; q = next.fetch_add(1))
