@@ -199,6 +199,94 @@ __device__ __forceinline__ void lq_pass1(int n_c, double inv_h, uint16_t* my_his
   }
 }
 
+// Chebyshev moments of the sorted positions s_u[e0 + qg], s_u[e0 + qg + LQ_GS], ... < e1, added to
+// acc[1..] (acc[0], the count, is the caller's: exact for unweighted streams).  Two independent
+// recurrences per iteration (the chain is latency-bound).
+template <bool WEIGHTED>
+__device__ __forceinline__ void lq_accumulate(const double* __restrict__ s_u, const double* __restrict__ s_wu,
+                                              int32_t e0, int32_t e1, int qg, double* acc) {
+  int32_t e = e0 + qg;
+  if (WEIGHTED) {
+    for (; e < e1; e += LQ_GS) {
+      const double w = s_wu[e];
+      const double uu = s_u[e] + s_u[e];
+      const double two_u = uu + uu;
+      double tp = 1., tc = uu;
+      acc[0] += w;
+      acc[1] = fma(w, tc, acc[1]);
+#pragma unroll
+      for (int d = 2; d < LQ_ND; ++d) {
+        const double tn = fma(two_u, tc, -tp);
+        tp = tc;
+        tc = tn;
+        acc[d] = fma(w, tn, acc[d]);
+      }
+    }
+  } else {
+  for (; e + LQ_GS < e1; e += 2 * LQ_GS) {
+    const double ua = s_u[e] + s_u[e], ub = s_u[e + LQ_GS] + s_u[e + LQ_GS];
+    const double two_a = ua + ua, two_b = ub + ub;
+    double pa = 1., ca = ua, pb = 1., cb = ub;
+    acc[1] += ca + cb;
+#pragma unroll
+    for (int d = 2; d < LQ_ND; ++d) {
+      const double na = fma(two_a, ca, -pa), nb = fma(two_b, cb, -pb);
+      pa = ca; ca = na;
+      pb = cb; cb = nb;
+      acc[d] += na + nb;
+    }
+  }
+  if (e < e1) {
+    const double vv = s_u[e];
+    const double uu = vv + vv;
+    const double two_u = uu + uu;
+    double tp = 1., tc = uu;
+    acc[1] += tc;
+#pragma unroll
+    for (int d = 2; d < LQ_ND; ++d) {
+      const double tn = fma(two_u, tc, -tp);
+      tp = tc;
+      tc = tn;
+      acc[d] += tn;
+    }
+  }
+  }
+}
+
+// Transposed reduction of acc[LQ_ND] over the LQ_GS lanes of a group (12 -> 6 -> 3 values per
+// lane on the two widest exchanges, plain butterflies on the rest), then Mb[d] += the sums.
+__device__ __forceinline__ void lq_reduce_store(double* acc, int qg, bool store, double* Mb) {
+  {
+    const bool up = (qg & (LQ_GS / 2)) != 0;
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {
+      const double send = up ? acc[i] : acc[i + 6];
+      const double keep = up ? acc[i + 6] : acc[i];
+      acc[i] = keep + __shfl_xor_sync(0xffffffffu, send, LQ_GS / 2);
+    }
+  }
+  {
+    const bool up = (qg & (LQ_GS / 4)) != 0;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      const double send = up ? acc[i] : acc[i + 3];
+      const double keep = up ? acc[i + 3] : acc[i];
+      acc[i] = keep + __shfl_xor_sync(0xffffffffu, send, LQ_GS / 4);
+    }
+  }
+#pragma unroll
+  for (int o = LQ_GS / 8; o > 0; o >>= 1) {
+#pragma unroll
+    for (int i = 0; i < 3; ++i) acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], o);
+  }
+  if (store && (qg & (LQ_GS / 4 - 1)) == 0) {
+    const int d0 = ((qg & (LQ_GS / 2)) ? 6 : 0) + ((qg & (LQ_GS / 4)) ? 3 : 0);
+    Mb[d0] += acc[0];
+    Mb[d0 + 1] += acc[1];
+    Mb[d0 + 2] += acc[2];
+  }
+}
+
 // WEIGHTED: streams of marked models (per-event weights); launched separately from the
 // unweighted streams so that those keep their register budget
 template <bool WEIGHTED>
@@ -258,6 +346,14 @@ lag_moment_kernel(const DimDev* __restrict__ dims, const QStreamDev* __restrict_
   uint32_t parity = 0u;   // bit b: phase of window buffer b
   unsigned long long n_pairs = 0;
   double t_mine = (m_begin + tid < m_end) ? Dt.t[m_begin + tid] : 0.;
+
+  // bins per pass of the moment stage = groups of LQ_GS lanes in the CTA
+  const int grp = lane / LQ_GS, qg = lane % LQ_GS;
+  const bool one_bin = J <= LQ_NW * (32 / LQ_GS);
+  const int my_bin = warp * (32 / LQ_GS) + grp;
+  double racc[LQ_ND];
+#pragma unroll
+  for (int d = 0; d < LQ_ND; ++d) racc[d] = 0.;
 
   int tile = 0;
   for (int64_t m0 = m_begin; m0 < m_end; m0 += LQ_TM, ++tile) {
@@ -405,97 +501,33 @@ lag_moment_kernel(const DimDev* __restrict__ dims, const QStreamDev* __restrict_
       }
       __syncthreads();
       // ---- c. moments of every bin: LQ_GS lanes per bin -------------------------------------------
-      const int grp = lane / LQ_GS, qg = lane % LQ_GS;
-      for (int b0 = warp * (32 / LQ_GS); b0 < J; b0 += LQ_NW * (32 / LQ_GS)) {
-        const int b = b0 + grp;
+      if (one_bin) {
+        // every group of lanes owns one bin for the whole work unit: the partial sums stay in
+        // registers across chunks and tiles and are reduced once, at the end
         int32_t e0 = 0, e1 = 0;
-        if (b < J) { e0 = s_bin[b]; e1 = s_bin[b + 1]; }
-        double acc[LQ_ND];
+        if (my_bin < J) { e0 = s_bin[my_bin]; e1 = s_bin[my_bin + 1]; }
+        lq_accumulate<WEIGHTED>(s_u, s_wu, e0, e1, qg, racc);
+        if (!WEIGHTED && qg == 0) racc[0] += (double)(e1 - e0);   // T_0 = 1: the bin count, exact
+      } else {
+        for (int b0 = warp * (32 / LQ_GS); b0 < J; b0 += LQ_NW * (32 / LQ_GS)) {
+          const int b = b0 + grp;
+          int32_t e0 = 0, e1 = 0;
+          if (b < J) { e0 = s_bin[b]; e1 = s_bin[b + 1]; }
+          double acc[LQ_ND];
 #pragma unroll
-        for (int d = 0; d < LQ_ND; ++d) acc[d] = 0.;
-        // two independent recurrences per iteration (the chain is latency-bound)
-        int32_t e = e0 + qg;
-        if (weighted) {
-          for (; e < e1; e += LQ_GS) {
-            const double w = s_wu[e];
-            const double uu = s_u[e] + s_u[e];
-            const double two_u = uu + uu;
-            double tp = 1., tc = uu;
-            acc[0] += w;
-            acc[1] = fma(w, tc, acc[1]);
-#pragma unroll
-            for (int d = 2; d < LQ_ND; ++d) {
-              const double tn = fma(two_u, tc, -tp);
-              tp = tc;
-              tc = tn;
-              acc[d] = fma(w, tn, acc[d]);
-            }
-          }
-        }
-        for (; e + LQ_GS < e1; e += 2 * LQ_GS) {
-          const double ua = s_u[e] + s_u[e], ub = s_u[e + LQ_GS] + s_u[e + LQ_GS];
-          const double two_a = ua + ua, two_b = ub + ub;
-          double pa = 1., ca = ua, pb = 1., cb = ub;
-          acc[1] += ca + cb;
-#pragma unroll
-          for (int d = 2; d < LQ_ND; ++d) {
-            const double na = fma(two_a, ca, -pa), nb = fma(two_b, cb, -pb);
-            pa = ca; ca = na;
-            pb = cb; cb = nb;
-            acc[d] += na + nb;
-          }
-        }
-        if (e < e1) {
-          const double vv = s_u[e];
-          const double uu = vv + vv;
-          const double two_u = uu + uu;
-          double tp = 1., tc = uu;
-          acc[1] += tc;
-#pragma unroll
-          for (int d = 2; d < LQ_ND; ++d) {
-            const double tn = fma(two_u, tc, -tp);
-            tp = tc;
-            tc = tn;
-            acc[d] += tn;
-          }
-        }
-        if (qg == 0 && !weighted) acc[0] = (double)(e1 - e0);   // T_0 = 1: the bin count, exact
-        // transposed reduction over the group's lanes: 12 -> 6 -> 3 values per lane on the two
-        // widest exchanges, plain butterflies on the rest
-        {
-          const bool up = (qg & (LQ_GS / 2)) != 0;
-#pragma unroll
-          for (int i = 0; i < 6; ++i) {
-            const double send = up ? acc[i] : acc[i + 6];
-            const double keep = up ? acc[i + 6] : acc[i];
-            acc[i] = keep + __shfl_xor_sync(0xffffffffu, send, LQ_GS / 2);
-          }
-        }
-        {
-          const bool up = (qg & (LQ_GS / 4)) != 0;
-#pragma unroll
-          for (int i = 0; i < 3; ++i) {
-            const double send = up ? acc[i] : acc[i + 3];
-            const double keep = up ? acc[i + 3] : acc[i];
-            acc[i] = keep + __shfl_xor_sync(0xffffffffu, send, LQ_GS / 4);
-          }
-        }
-#pragma unroll
-        for (int o = LQ_GS / 8; o > 0; o >>= 1) {
-#pragma unroll
-          for (int i = 0; i < 3; ++i) acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], o);
-        }
-        if (b < J && (qg & (LQ_GS / 4 - 1)) == 0 && e1 > e0) {
-          const int d0 = ((qg & (LQ_GS / 2)) ? 6 : 0) + ((qg & (LQ_GS / 4)) ? 3 : 0);
-          double* Mb = s_M + (size_t)b * LQ_ND + d0;
-          Mb[0] += acc[0];
-          Mb[1] += acc[1];
-          Mb[2] += acc[2];
+          for (int d = 0; d < LQ_ND; ++d) acc[d] = 0.;
+          lq_accumulate<WEIGHTED>(s_u, s_wu, e0, e1, qg, acc);
+          if (!WEIGHTED && qg == 0) acc[0] = (double)(e1 - e0);
+          lq_reduce_store(acc, qg, b < J && e1 > e0, s_M + (size_t)min(b, J - 1) * LQ_ND);
         }
       }
       __syncthreads();
     }
     fence_proxy_async();   // generic reads of this window before a later tile's async write
+    __syncthreads();
+  }
+  if (one_bin) {
+    lq_reduce_store(racc, qg, my_bin < J, s_M + (size_t)min(my_bin, J - 1) * LQ_ND);
     __syncthreads();
   }
   // ---- one partial moment table per work unit ---------------------------------------------------

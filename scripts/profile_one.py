@@ -9,6 +9,7 @@ model, times, T_f, xs = simulate.config_c5(T_f=T_f)
 eng = aslsd_b200.Engine(0)
 eng.set_events(times, T_f)
 eng.set_model(model)
+eng.use_weight_cache(False)     # every call runs the moment kernel
 d = model['d']
 for rep in range(3):
     eng.exact_sums_batch(list(range(d)), xs)

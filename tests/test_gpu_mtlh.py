@@ -128,7 +128,8 @@ def test_unit_weights_reproduce_the_unmarked_sums(engine):
     engine.set_weights([(0, np.ones(800)), (1, np.ones(800))])
     roles = np.array([[0, 1]] * 5, dtype=np.int32)
     weighted = engine.exact_sums_weighted(0, x, roles)
-    np.testing.assert_allclose(weighted, plain, rtol=1e-13, atol=1e-300)
+    # (the weighted and the plain moment kernels associate their sums differently)
+    np.testing.assert_allclose(weighted, plain, rtol=1e-12, atol=1e-300)
     # masked terms stay at zero, the others are unchanged
     from aslsd_b200.engine import term_layout
     layout, _ = term_layout(engine.desc, 0)
