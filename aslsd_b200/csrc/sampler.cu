@@ -189,7 +189,7 @@ extern "C" int aslsd_sample_double_ix(aslsd_pcg64* gen, int64_t n_strata, const 
   if (!gen || n_strata < 0 || (n_strata > 0 && (!h_inf || !h_sup || !n_samples || !varpi_ij || !kappa_ji)))
     return ASLSD_ERR_ARG;
   Pcg g(*gen);
-  std::vector<int64_t> scratch, lags, order, count;
+  std::vector<int64_t> scratch, lags, order, count, ckey, slot_of;
   std::vector<uint64_t> set;
   int64_t pos = 0;
   for (int64_t s = 0; s < n_strata; ++s) {
@@ -203,8 +203,9 @@ extern "C" int aslsd_sample_double_ix(aslsd_pcg64* gen, int64_t n_strata, const 
       if (rc) return rc;
       for (int64_t q = 0; q < ns; ++q) {
         m[q] += first;
-        n[q] = kappa_ji[m[q]] - (h - 1);
+        __builtin_prefetch(&kappa_ji[m[q]]);
       }
+      for (int64_t q = 0; q < ns; ++q) n[q] = kappa_ji[m[q]] - (h - 1);
     } else {
       // lags with replacement, then one choice per distinct lag in order of first occurrence
       // (collections.Counter keeps insertion order)
@@ -212,15 +213,33 @@ extern "C" int aslsd_sample_double_ix(aslsd_pcg64* gen, int64_t n_strata, const 
       if (width <= 0 && ns > 0) return ASLSD_ERR_ARG;
       lags.resize((size_t)ns);
       for (int64_t q = 0; q < ns; ++q) lags[(size_t)q] = (int64_t)g.bounded((uint64_t)(width - 1));
-      // `count` is all zero between strata: only the touched entries are reset below
-      if ((int64_t)count.size() < width) count.resize((size_t)width, 0);
+      // multiplicity of every distinct lag, in order of first occurrence: a small open-addressing
+      // table (a dense array over the lag range would be megabytes for the outer strata)
+      uint64_t cmask = (uint64_t)(2 * ns + 1);
+      cmask |= cmask >> 1; cmask |= cmask >> 2; cmask |= cmask >> 4; cmask |= cmask >> 8; cmask |= cmask >> 16;
+      cmask |= cmask >> 32;
+      ckey.assign((size_t)cmask + 1, -1);
+      count.assign((size_t)cmask + 1, 0);
       order.clear();
+      slot_of.clear();
       for (int64_t q = 0; q < ns; ++q) {
-        if (count[(size_t)lags[(size_t)q]]++ == 0) order.push_back(lags[(size_t)q]);
+        const int64_t lag = lags[(size_t)q];
+        uint64_t loc = ((uint64_t)lag * 0x9E3779B97F4A7C15ULL >> 24) & cmask;
+        while (ckey[loc] != -1 && ckey[loc] != lag) loc = (loc + 1) & cmask;
+        if (ckey[loc] == -1) {
+          ckey[loc] = lag;
+          order.push_back(lag);
+          slot_of.push_back((int64_t)loc);
+        }
+        ++count[loc];
       }
+      // varpi[h] and kappa[m] are scattered reads into tables of the size of the event streams:
+      // prefetched ahead of their use
+      for (size_t o = 0; o < order.size(); ++o) __builtin_prefetch(&varpi_ij[h_inf[s] + order[o]]);
       int64_t w = 0;
-      for (int64_t rel : order) {
-        const int64_t h = h_inf[s] + rel, n_h = count[(size_t)rel];
+      for (size_t o = 0; o < order.size(); ++o) {
+        const int64_t rel = order[o];
+        const int64_t h = h_inf[s] + rel, n_h = count[(size_t)slot_of[o]];
         const int64_t first = varpi_ij[h], pop = n_events_i - first;
         if (n_h <= pop) {
           int rc = choice_no_replace(g, pop, n_h, m + w, scratch, set);
@@ -231,11 +250,12 @@ extern "C" int aslsd_sample_double_ix(aslsd_pcg64* gen, int64_t n_strata, const 
         }
         for (int64_t q = 0; q < n_h; ++q) {
           m[w + q] += first;
-          n[w + q] = kappa_ji[m[w + q]] - h + 1;
+          __builtin_prefetch(&kappa_ji[m[w + q]]);
+          n[w + q] = h;          // the lag, until kappa has arrived
         }
         w += n_h;
-        count[(size_t)rel] = 0;
       }
+      for (int64_t q = 0; q < ns; ++q) n[q] = kappa_ji[m[q]] - n[q] + 1;
     }
     pos += ns;
   }
