@@ -165,35 +165,51 @@ __device__ __forceinline__ void lq_pass1(int n_c, double inv_h, uint16_t* my_his
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const unsigned lt_mask = (1u << lane) - 1u;
   const int n_steps = (n_c + 31) >> 5;
-  for (int st = warp; st < n_steps; st += 2 * LQ_NW) {
+  const int n_full = n_c >> 5;   // steps whose 32 pairs all exist
+  int st = warp;
+  // full steps, two per iteration: no lane masks, no liveness tests
+  for (; st + LQ_NW < n_full; st += 2 * LQ_NW) {
     const int qa = st * 32 + lane, qb = qa + LQ_NW * 32;
-    const bool live_a = qa < n_c, live_b = qb < n_c;
-    // idle lanes (last steps of a chunk) redo pair 0 and are masked out of every peer set
-    const int left_a = n_c - st * 32, left_b = left_a - LQ_NW * 32;
-    const unsigned mask_a = left_a >= 32 ? 0xffffffffu : ((1u << left_a) - 1u);
-    const unsigned mask_b = left_b >= 32 ? 0xffffffffu : (left_b <= 0 ? 0u : ((1u << left_b) - 1u));
-    const double sa = s_val[live_a ? qa : 0], sb = s_val[live_b ? qb : 0];
+    const double sa = s_val[qa], sb = s_val[qb];
     int ba, bb;
     double va, vb;
     lq_bin(sa, inv_h, ba, va);
     lq_bin(sb, inv_h, bb, vb);
-    const unsigned pa = match_bins<NB>(ba) & mask_a;
-    const unsigned pb = match_bins<NB>(bb) & mask_b;
+    const unsigned pa = match_bins<NB>(ba);
+    const unsigned pb = match_bins<NB>(bb);
     const int ra = __popc(pa & lt_mask), rb = __popc(pb & lt_mask);
+    const int base_a = my_hist[ba];
+    __syncwarp();
+    if (ra == 0) my_hist[ba] = (uint16_t)(base_a + __popc(pa));
+    s_key[qa] = (uint32_t)ba | ((uint32_t)(base_a + ra) << 10);
+    s_val[qa] = va;
+    __syncwarp();
+    const int base_b = my_hist[bb];
+    __syncwarp();
+    if (rb == 0) my_hist[bb] = (uint16_t)(base_b + __popc(pb));
+    s_key[qb] = (uint32_t)bb | ((uint32_t)(base_b + rb) << 10);
+    s_val[qb] = vb;
+    __syncwarp();
+  }
+  // the remaining steps of this warp (at most two, the last one of the chunk possibly partial):
+  // idle lanes redo pair 0 and are masked out of every peer set
+  for (; st < n_steps; st += LQ_NW) {
+    const int qa = st * 32 + lane;
+    const bool live_a = qa < n_c;
+    const int left_a = n_c - st * 32;
+    const unsigned mask_a = left_a >= 32 ? 0xffffffffu : ((1u << left_a) - 1u);
+    const double sa = s_val[live_a ? qa : 0];
+    int ba;
+    double va;
+    lq_bin(sa, inv_h, ba, va);
+    const unsigned pa = match_bins<NB>(ba) & mask_a;
+    const int ra = __popc(pa & lt_mask);
     const int base_a = my_hist[ba];
     __syncwarp();
     if (live_a) {
       if (ra == 0) my_hist[ba] = (uint16_t)(base_a + __popc(pa));
       s_key[qa] = (uint32_t)ba | ((uint32_t)(base_a + ra) << 10);
       s_val[qa] = va;
-    }
-    __syncwarp();
-    const int base_b = my_hist[bb];
-    __syncwarp();
-    if (live_b) {
-      if (rb == 0) my_hist[bb] = (uint16_t)(base_b + __popc(pb));
-      s_key[qb] = (uint32_t)bb | ((uint32_t)(base_b + rb) << 10);
-      s_val[qb] = vb;
     }
     __syncwarp();
   }
