@@ -393,12 +393,19 @@ lag_moment_kernel(const DimDev* __restrict__ dims, const QStreamDev* __restrict_
     const int n_valid = (int)min((int64_t)n_win, Ds.n - a0);   // entries that are events, not padding
     int64_t lo_abs = 0;
     int32_t cnt = 0;
-    const int p2 = n_valid > 0 ? (1 << (31 - __clz(n_valid))) : 0;
+    // every threshold of the tile is <= t_last: the searches stop at the first power of two (minus
+    // one: one step less) whose entry reaches it
+    int n_search = n_valid;
+    if (staged && !same) {
+      if (n_valid > 511 && win[510] >= t_last) n_search = 511;
+      else if (n_valid > 1023 && win[1022] >= t_last) n_search = 1023;
+    }
+    const int p2 = n_search > 0 ? (1 << (31 - __clz(n_search))) : 0;
     if (tid < nt) {
       int64_t hi;
       if (staged) {
-        hi = same ? (m0 + tid) : a0 + smem_lower_bound(win, n_valid, p2, t);
-        lo_abs = min(a0 + (int64_t)smem_lower_bound(win, n_valid, p2, t - S.s_max), hi);
+        hi = same ? (m0 + tid) : a0 + smem_lower_bound(win, n_search, p2, t);
+        lo_abs = min(a0 + (int64_t)smem_lower_bound(win, n_search, p2, t - S.s_max), hi);
       } else {
         hi = same ? (m0 + tid) : dim_lower_bound(Ds, t);
         lo_abs = min(dim_lower_bound(Ds, t - S.s_max), hi);
@@ -474,35 +481,40 @@ lag_moment_kernel(const DimDev* __restrict__ dims, const QStreamDev* __restrict_
       // (thread tid owns the jpt consecutive bins from tid * jpt)
       {
         const int jpt = (J + LQ_NT - 1) / LQ_NT;
-        int32_t tot = 0;
-        for (int q = 0; q < jpt; ++q) {
-          const int b = tid * jpt + q;
-          if (b < J) {
+        const bool owns_bins = warp * 32 * jpt < J;   // warp-uniform: the other warps only meet the barrier
+        int32_t tot = 0, inc = 0;
+        if (owns_bins) {
+          for (int q = 0; q < jpt; ++q) {
+            const int b = tid * jpt + q;
+            if (b < J) {
 #pragma unroll
-            for (int w = 0; w < LQ_NW; ++w) tot += s_hist[w * J + b];
-          }
-        }
-        int32_t inc = tot;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-          const int32_t v = __shfl_up_sync(0xffffffffu, inc, o);
-          if (lane >= o) inc += v;
-        }
-        if (lane == 31) s_scan[warp] = inc;
-        __syncthreads();
-        int32_t run = inc - tot;
-        for (int w = 0; w < warp; ++w) run += s_scan[w];
-        for (int q = 0; q < jpt; ++q) {
-          const int b = tid * jpt + q;
-          if (b < J) {
-            s_bin[b] = run;
-#pragma unroll
-            for (int w = 0; w < LQ_NW; ++w) {
-              const int32_t v = s_hist[w * J + b];
-              s_hist[w * J + b] = (uint16_t)run;
-              run += v;
+              for (int w = 0; w < LQ_NW; ++w) tot += s_hist[w * J + b];
             }
-            if (b == J - 1) s_bin[J] = run;
+          }
+          inc = tot;
+#pragma unroll
+          for (int o = 1; o < 32; o <<= 1) {
+            const int32_t v = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += v;
+          }
+          if (lane == 31) s_scan[warp] = inc;
+        }
+        __syncthreads();
+        if (owns_bins) {
+          int32_t run = inc - tot;
+          for (int w = 0; w < warp; ++w) run += s_scan[w];
+          for (int q = 0; q < jpt; ++q) {
+            const int b = tid * jpt + q;
+            if (b < J) {
+              s_bin[b] = run;
+#pragma unroll
+              for (int w = 0; w < LQ_NW; ++w) {
+                const int32_t v = s_hist[w * J + b];
+                s_hist[w * J + b] = (uint16_t)run;
+                run += v;
+              }
+              if (b == J - 1) s_bin[J] = run;
+            }
           }
         }
       }
