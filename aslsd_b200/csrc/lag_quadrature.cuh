@@ -120,6 +120,16 @@ __device__ __forceinline__ int smem_lower_bound(const double* win, int n, int p2
   return pos;
 }
 
+// the same over exactly 2^K - 1 entries: no bounds to test, fully unrolled
+template <int K>
+__device__ __forceinline__ int smem_lower_bound_full(const double* win, double x) {
+  int pos = 0;
+#pragma unroll
+  for (int step = 1 << (K - 1); step > 0; step >>= 1)
+    if (win[pos + step - 1] < x) pos += step;
+  return pos;
+}
+
 // lanes of the warp whose b equals this lane's, from ballots over NB bits
 // (per bit: test, vote, select, and-not-xor)
 template <int K>
@@ -396,7 +406,7 @@ lag_moment_kernel(const DimDev* __restrict__ dims, const QStreamDev* __restrict_
     // every threshold of the tile is <= t_last: the searches stop at the first power of two (minus
     // one: one step less) whose entry reaches it
     int n_search = n_valid;
-    if (staged && !same) {
+    if (staged) {
       if (n_valid > 511 && win[510] >= t_last) n_search = 511;
       else if (n_valid > 1023 && win[1022] >= t_last) n_search = 1023;
     }
@@ -404,8 +414,20 @@ lag_moment_kernel(const DimDev* __restrict__ dims, const QStreamDev* __restrict_
     if (tid < nt) {
       int64_t hi;
       if (staged) {
-        hi = same ? (m0 + tid) : a0 + smem_lower_bound(win, n_search, p2, t);
-        lo_abs = min(a0 + (int64_t)smem_lower_bound(win, n_search, p2, t - S.s_max), hi);
+        const double x_lo = t - S.s_max;
+        int r_hi, r_lo;
+        if (n_search == 1023) {
+          r_hi = same ? 0 : smem_lower_bound_full<10>(win, t);
+          r_lo = smem_lower_bound_full<10>(win, x_lo);
+        } else if (n_search == 511) {
+          r_hi = same ? 0 : smem_lower_bound_full<9>(win, t);
+          r_lo = smem_lower_bound_full<9>(win, x_lo);
+        } else {
+          r_hi = same ? 0 : smem_lower_bound(win, n_search, p2, t);
+          r_lo = smem_lower_bound(win, n_search, p2, x_lo);
+        }
+        hi = same ? (m0 + tid) : a0 + r_hi;
+        lo_abs = min(a0 + (int64_t)r_lo, hi);
       } else {
         hi = same ? (m0 + tid) : dim_lower_bound(Ds, t);
         lo_abs = min(dim_lower_bound(Ds, t - S.s_max), hi);
