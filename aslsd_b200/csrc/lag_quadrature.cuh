@@ -130,6 +130,19 @@ __device__ __forceinline__ int smem_lower_bound_full(const double* win, double x
   return pos;
 }
 
+// two such searches at once: the two dependent chains of shared-memory loads overlap
+template <int K>
+__device__ __forceinline__ void smem_lower_bound_full2(const double* win, double xa, double xb, int& pa, int& pb) {
+  pa = 0;
+  pb = 0;
+#pragma unroll
+  for (int step = 1 << (K - 1); step > 0; step >>= 1) {
+    const double va = win[pa + step - 1], vb = win[pb + step - 1];
+    if (va < xa) pa += step;
+    if (vb < xb) pb += step;
+  }
+}
+
 // lanes of the warp whose b equals this lane's, from ballots over NB bits
 // (per bit: test, vote, select, and-not-xor)
 template <int K>
@@ -417,11 +430,11 @@ lag_moment_kernel(const DimDev* __restrict__ dims, const QStreamDev* __restrict_
         const double x_lo = t - S.s_max;
         int r_hi, r_lo;
         if (n_search == 1023) {
-          r_hi = same ? 0 : smem_lower_bound_full<10>(win, t);
-          r_lo = smem_lower_bound_full<10>(win, x_lo);
+          if (same) { r_hi = 0; r_lo = smem_lower_bound_full<10>(win, x_lo); }
+          else smem_lower_bound_full2<10>(win, t, x_lo, r_hi, r_lo);
         } else if (n_search == 511) {
-          r_hi = same ? 0 : smem_lower_bound_full<9>(win, t);
-          r_lo = smem_lower_bound_full<9>(win, x_lo);
+          if (same) { r_hi = 0; r_lo = smem_lower_bound_full<9>(win, x_lo); }
+          else smem_lower_bound_full2<9>(win, t, x_lo, r_hi, r_lo);
         } else {
           r_hi = same ? 0 : smem_lower_bound(win, n_search, p2, t);
           r_lo = smem_lower_bound(win, n_search, p2, x_lo);
