@@ -434,10 +434,10 @@ def run_b200(args):
                                    'of the raw rows per step' if world > 1 else 'single GPU'},
             'roofline': {'bound': 'fp64', 'achieved': achieved, 'peak': fp64_peak, 'unit': 'TFLOP/s',
                          'frac': (achieved / fp64_peak) if achieved else None,
-                         'traffic': 241.3e6 if (world == 1 and not args.no_quadrature and not args.per_k) else None,
+                         'traffic': 249.8e6 if (world == 1 and not args.no_quadrature and not args.per_k) else None,
                          'traffic_note': 'dram__bytes_read.sum + dram__bytes_write.sum of lag_moment_kernel from '
-                                         'the ncu --set full capture of this command (profiles/r1_v8_*): 219.8 + '
-                                         '21.4 MB per launch; algorithmic bytes %.0f MB (each event time read once '
+                                         'the ncu --set full capture of this workload (profiles/r1_end_lag_moment_kernel_*): 226.5 + '
+                                         '23.3 MB per launch; algorithmic bytes %.0f MB (each event time read once '
                                          'per stream it belongs to) - the 80 MB of events stay in L2' % (n_src_tgt / 1e6),
                          'kernel': 'lag_moment_kernel',
                          'kernel_ms': m_ms_sum, 'kernel_share_of_step': (m_ms_sum / k_ms_sum) if k_ms_sum else None,
