@@ -41,6 +41,11 @@ STRAT_CASES = {
                      dict(n_exact_single=100, n_samples_adaptive_single=200,
                           nonadaptive_sample_size_single=300, n_samples_adaptive_double=600,
                           nonadaptive_sample_size_double=270)),
+    # exponential + Gaussian basis in one kernel: the mixed upsilon closed forms, sampled
+    'strat_mix1d': ('mix1d', 300., 20, False,
+                    dict(n_exact_single=100, n_samples_adaptive_single=200,
+                         nonadaptive_sample_size_single=300, n_samples_adaptive_double=600,
+                         nonadaptive_sample_size_double=270)),
 }
 SEED = 4321
 
@@ -64,9 +69,11 @@ def flat_allocs(est):
     return np.concatenate(out)
 
 
-def make_strat(ref):
+def make_strat(ref, only=None):
     from aslsd.optimize.solvers.adam import ADAM
     for name, (case, T_f, n_iter, grad_alloc, kw) in STRAT_CASES.items():
+        if only and name not in only:
+            continue
         model, mu, kp, _ = CASES[case]
         d = model['d']
         import ref_shim
@@ -118,4 +125,4 @@ def make_strat(ref):
 
 if __name__ == '__main__':
     import ref_shim
-    make_strat(ref_shim.import_reference())
+    make_strat(ref_shim.import_reference(), only=sys.argv[1:] or None)

@@ -10,7 +10,7 @@ from oracle import stratified as OS
 
 pytestmark = pytest.mark.gpu
 
-NAMES = ['strat_exp1d', 'strat_exp2d', 'strat_exp2d_gradalloc', 'strat_gauss1d', 'strat_sbf2d3']
+NAMES = ['strat_exp1d', 'strat_exp2d', 'strat_exp2d_gradalloc', 'strat_gauss1d', 'strat_sbf2d3', 'strat_mix1d']
 
 
 @pytest.fixture(scope='module')

@@ -11,7 +11,7 @@ import pytest
 from helpers import replay_strat_golden
 from oracle_engine import OracleEngine
 
-NAMES = ['strat_exp1d', 'strat_exp2d', 'strat_exp2d_gradalloc', 'strat_gauss1d', 'strat_sbf2d3']
+NAMES = ['strat_exp1d', 'strat_exp2d', 'strat_exp2d_gradalloc', 'strat_gauss1d', 'strat_sbf2d3', 'strat_mix1d']
 
 
 @pytest.mark.parametrize('name', NAMES)
