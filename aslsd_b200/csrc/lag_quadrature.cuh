@@ -26,18 +26,23 @@
 //   a. the tile's source window sits in shared memory, fetched by one TMA bulk copy that was issued
 //      during the previous tile (the first source a tile can need is the window start of the previous
 //      tile's last target: no global search, two buffers); per-target source ranges by binary search
-//      in that window; exclusive scan of the pair counts.  A window that does not fit falls back to
-//      bucket-table searches and global reads for that tile;
+//      in that window (bounded by the part of it the tile can reach; for the usual 511 / 1023
+//      entries unrolled, without bound tests, the two searches of a target interleaved); exclusive
+//      scan of the pair counts.  A window that does not fit falls back to bucket-table searches and
+//      global reads for that tile;
 //   b. counting sort of the tile's lags by bin, in chunks of `ucap` pairs.  Every target's thread
 //      writes the lags of its pairs target-major into shared memory, so that afterwards every lane
-//      of every warp holds a pair.  Pass 1 (two warp steps interleaved): bin and in-bin coordinate
+//      of every warp holds a pair.  Pass 1 (two warp steps interleaved, full steps without lane
+//      masks, the partial last step peeled): bin and in-bin coordinate
 //      of each pair, rank among the equal bins of the warp step from ballots over the bits of the
 //      bin index (match.any measured ~300 cycles: XU pipe; shared-memory atomics 2 cycles per
 //      lane), running count in a warp-private histogram -> (bin, rank in warp) key.  Scan of the
 //      histograms.  Pass 2: coordinates move to their sorted slots.  No atomics: the order inside a
 //      bin is fixed and the result is deterministic;
 //   c. every group of LQ_GS lanes takes a bin: three-term recurrence, LQ_ND - 1 register accumulators per lane,
-//      transposed shuffle reduction, owner adds into the CTA's moment table;
+//      transposed shuffle reduction, owner adds into the CTA's moment table.  With at most
+//      LQ_NW * 32 / LQ_GS = 64 bins every group owns one bin for the whole work unit: its sums stay
+//      in registers across chunks and tiles and are reduced once, before the partial table is written;
 //   one partial table per work unit, reduced in fixed order by lag_weights_kernel.
 #pragma once
 
