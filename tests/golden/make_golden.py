@@ -132,8 +132,8 @@ if __name__ == '__main__':
     ref = ref_shim.import_reference()
     make_exact(ref)
     make_index_maps(ref)
-    try:
-        import make_golden_strat
-        make_golden_strat.make_strat(ref)
-    except ImportError:
-        print('stratified traces: generator not present yet')
+    import make_golden_strat
+    make_golden_strat.make_strat(ref)
+    # the other generators (marked models, residuals, recursion values) are run the same way:
+    #   python make_golden_mtlh.py; python make_golden_mtlh_strat.py;
+    #   python make_golden_residuals.py; python make_golden_recexp.py
