@@ -14,9 +14,10 @@ from aslsd_b200.mtlh import MTLH, MTLHExactEstimB200, MTLHStratEstimB200  # noqa
 from aslsd_b200.stratifications import (GeneralStratification,  # noqa: F401
                                         DoubleIxStratification)
 from aslsd_b200.solvers import ADAM  # noqa: F401
-from aslsd_b200.residuals import get_intensity_at_jumps, get_residuals, get_residuals_k  # noqa: F401
+from aslsd_b200.residuals import (get_intensity_at_jumps, get_residuals, get_residuals_k,  # noqa: F401
+                                  get_residuals_k_mtlh, get_residuals_mtlh)
 
-__all__ = ['get_intensity_at_jumps', 'get_residuals', 'get_residuals_k',
+__all__ = ['get_intensity_at_jumps', 'get_residuals', 'get_residuals_k', 'get_residuals_k_mtlh', 'get_residuals_mtlh',
            'MHPExactEstimB200', 'MHPStratEstimB200', 'MTLH', 'MTLHExactEstimB200', 'MTLHStratEstimB200', 'GeneralStratification',
            'DoubleIxStratification', 'ADAM', 'Engine', 'EngineError', 'Episodes', 'ProcessPath', 'get_kappa_varpi', 'get_lag_sizes',
            'MHP', 'KernelModel', 'ExponentialKernel', 'GaussianKernel', 'describe_model']

@@ -1,4 +1,5 @@
-"""Intensity at the jump times and residuals of a fitted MHP, on the B200.
+"""Intensity at the jump times and residuals of a fitted MHP (and residuals of a fitted marked
+model with constant baselines), on the B200.
 
 Same results as the two O(N^2) Python loops that follow a fit in the reference:
   * ``MHP.get_intensity_at_jumps(process_path, mu, kernel_param)``
@@ -49,6 +50,32 @@ def get_residuals_k(model, process_path, k, mu, kernel_param, engine=None, refer
         kernel_part[:, 0] = 0.
     poisson = float(mu[k]) * (t_k[1:] - t_k[:-1])
     return poisson + (kernel_part[:, 1:] - kernel_part[:, :-1]).sum(axis=0)
+
+
+def get_residuals_k_mtlh(model, process_path, k, mu_k, kernel_param_k, expected_impact_k, engine=None):
+    """Residuals of a marked model with constant baselines, as
+    ``goodness_of_fit.get_residuals_k_mtlh`` (stats/residual_analysis/goodness_of_fit.py:245-301,
+    what ``MTLH.get_residuals`` returns without sampling) computes them:
+        r^k_m = mu_k t^k_{m+1} - mu_k t^k_m + sum_i e_ki [Psi_ki(m + 1) - Psi_ki(m)],
+    with e_ki = ``expected_impact_matrix[k][i]`` the expected impact (the reference's
+    ``MTLH.make_expected_impact``) - the marks of the individual events do not enter - and without
+    the first-residual quirk of the MHP version (:271-276 always evaluate the first value).
+    ``mu_k``: the constant baseline of type k; ``kernel_param_k[i]``: parameters of phi_ki."""
+    engine = _bind(model, process_path, engine)
+    d = engine.d
+    t_k = np.asarray(process_path.list_times[k], dtype=np.float64)
+    x_k = np.concatenate([[float(mu_k)]] + [np.asarray(kernel_param_k[i], dtype=np.float64) for i in range(d)])
+    kernel_part = engine.point_sums(k, x_k, 'psi') * np.asarray(expected_impact_k, dtype=np.float64)[:, None]
+    poisson = float(mu_k) * t_k[1:] - float(mu_k) * t_k[:-1]
+    return poisson + (kernel_part[:, 1:] - kernel_part[:, :-1]).sum(axis=0)
+
+
+def get_residuals_mtlh(model, process_path, mu, kernel_param, expected_impact_matrix, engine=None):
+    """All event types: ``mu[k]`` the constant baselines, ``kernel_param[k][i]``,
+    ``expected_impact_matrix[k][i]`` as in ``goodness_of_fit.get_residuals_mtlh`` (:304-322)."""
+    engine = _bind(model, process_path, engine)
+    return [get_residuals_k_mtlh(model, process_path, k, np.ravel(mu[k])[0], kernel_param[k],
+                                 expected_impact_matrix[k], engine=engine) for k in range(engine.d)]
 
 
 def get_residuals(model, process_path, mu, kernel_param, engine=None):

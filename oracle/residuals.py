@@ -40,3 +40,24 @@ def residuals_k(model, k, mu, kernel_param, times):
                                                  np.asarray(kernel_param[k][i], dtype=float)))
     poisson = float(mu[k]) * (tk[1:] - tk[:-1])
     return poisson + (kernel_part[:, 1:] - kernel_part[:, :-1]).sum(axis=0)
+
+
+def residuals_k_mtlh(model, k, mu_k, kernel_param_k, expected_impact_k, times):
+    """goodness_of_fit.py:245-301 for a constant baseline (compensator mu t,
+    basis_baseline_constant.py): kernel_part[i][m] = e_ki x (sum of psi_ki over the type-i events
+    strictly before t^k_m).  Unlike the MHP version above the value at the first type-k event that
+    has type-i predecessors is always computed (:271-276), and the events carry no individual
+    weight: the impact enters through its expectation e_ki only."""
+    d = model['d']
+    tk = times[k]
+    kernel_part = np.zeros((d, len(tk)))
+    for i in range(d):
+        ti = times[i]
+        for m in range(len(tk)):
+            hi = m if i == k else np.searchsorted(ti, tk[m], side='left')
+            if hi > 0:
+                kernel_part[i][m] = expected_impact_k[i] * np.sum(
+                    F.psi(model['kernels'][k][i], tk[m] - ti[:hi], np.asarray(kernel_param_k[i], dtype=float)))
+    poisson = float(mu_k) * tk[1:] - float(mu_k) * tk[:-1]
+    return poisson + (kernel_part[:, 1:] - kernel_part[:, :-1]).sum(axis=0)
+

@@ -36,6 +36,31 @@ class OracleEngine:
         kappa, varpi = OT.kappa_varpi_closed_form(self.times, self.T_f)
         return kappa, varpi, OT.lag_sizes(self.times, kappa, varpi)
 
+    @property
+    def d(self):
+        return self.plain['d']
+
+    @property
+    def n_events(self):
+        return np.array([len(t) for t in self.times])
+
+    def point_sums(self, k, x_k, kind):
+        """(d, N_k): row i = sum over the type-i events strictly before t^k_m of phi_ki / psi_ki."""
+        from oracle import functionals as F
+        x = np.asarray(x_k, dtype=float)
+        imap = OE.interval_map(self.plain, k)
+        fn = F.phi if kind == 'phi' else F.psi
+        tk = self.times[k]
+        out = np.zeros((self.plain['d'], len(tk)))
+        for i in range(self.plain['d']):
+            ti = self.times[i]
+            par = x[imap[i][0]:imap[i][1]]
+            for m in range(len(tk)):
+                hi = m if i == k else np.searchsorted(ti, tk[m], side='left')
+                if hi > 0:
+                    out[i][m] = np.sum(fn(self.plain['kernels'][k][i], tk[m] - ti[:hi], par))
+        return out
+
     def exact_max_lag(self, ks, xs, compute_f_sum=True, compute_diff_f_sum=True):
         """Largest window of the oracle's windowed sums (oracle/exact.py phi_window / ups_window)."""
         w = 0.
