@@ -33,6 +33,7 @@ call per ``compute_objective``.  There is no CPU fallback.
 """
 import copy
 import itertools
+import os
 import pickle
 
 import numpy as np
@@ -223,6 +224,65 @@ class _B200Estimator(_RefEstimator):
                 grad[ix_param] = self.recombine_diff_lse_theta_kpr(p, r)
         return grad
 
+    # ---- stratifications (mhp_stratified_estimator.py:39-117; the exact estimator of the
+    # reference builds them too, mhp_exact_estimator.py:39-117, and writes them with save) ----------
+    def set_singlesum_estimation(self, n_exact=None, n_samples_adaptive=None,
+                                 nonadaptive_sample_size=None, **kwargs):
+        d = self.d
+        local = {}
+        if n_exact is not None:
+            local['n_exact'] = n_exact
+        if n_samples_adaptive is not None:
+            local['n_samples_adaptive'] = n_samples_adaptive
+        if nonadaptive_sample_size is not None:
+            local['nonadaptive_sample_size'] = nonadaptive_sample_size
+        for key, prefix in (('psi_stratification', 'psi_'),
+                            ('upsilonzero_stratification', 'upsilonzero_')):
+            given = kwargs.get(key, [None] * d)
+            for i in range(d):
+                strf = given[i]
+                if strf is None:
+                    strf = GeneralStratification(n=self.n_events[i], **local)
+                self.stratif[prefix + str(i)] = strf
+
+    def set_doublesum_estimation(self, n_samples_adaptive=None, nonadaptive_sample_size=None,
+                                 **kwargs):
+        d, k = self.d, self.k
+        local = {}
+        if n_samples_adaptive is not None:
+            local['n_samples_adaptive'] = n_samples_adaptive
+        if nonadaptive_sample_size is not None:
+            local['nonadaptive_sample_size'] = nonadaptive_sample_size
+        given = kwargs.get('upsilon_stratification', [[None] * d for _ in range(d)])
+        for i, j in itertools.product(range(d), range(d)):
+            strf = given[i][j]
+            if strf is None:
+                strf = DoubleIxStratification(h_max=self.kappa[j][i][self.n_events[i] - 1] + 1,
+                                              **local)
+                strf.get_stratification_size(self.lag_sizes, i, j)
+            self.stratif['upsilon_%d_%d' % (i, j)] = strf
+        given = kwargs.get('phi_stratification', [None] * d)
+        for i in range(d):
+            strf = given[i]
+            if strf is None:
+                strf = DoubleIxStratification(h_max=self.kappa[i][k][self.n_events[k] - 1] + 1,
+                                              **local)
+                strf.get_stratification_size(self.lag_sizes, k, i)
+            self.stratif['phi_%d' % i] = strf
+
+    def set_stratification(self, n_exact_single=None, n_samples_adaptive_single=None,
+                           nonadaptive_sample_size_single=None, single_strfs=None,
+                           n_samples_adaptive_double=None, nonadaptive_sample_size_double=None,
+                           double_strfs=None):
+        self.stratif = {}
+        self.set_singlesum_estimation(n_exact=n_exact_single,
+                                      n_samples_adaptive=n_samples_adaptive_single,
+                                      nonadaptive_sample_size=nonadaptive_sample_size_single,
+                                      **(single_strfs or {}))
+        self.set_doublesum_estimation(n_samples_adaptive=n_samples_adaptive_double,
+                                      nonadaptive_sample_size=nonadaptive_sample_size_double,
+                                      **(double_strfs or {}))
+
     def get_log(self):
         logs = {}
         if self.is_log_lse:
@@ -233,14 +293,89 @@ class _B200Estimator(_RefEstimator):
             logs['allocs'] = copy.deepcopy(self.logged_allocs)
         return logs
 
-    def save(self, file, **kwargs):
-        with open(file, 'wb', **kwargs) as f:
-            pickle.dump(self, f)
+    # ---- serialization: the reference's file layout (mhp_stratified_estimator.py:1509-1689,
+    # mhp_exact_estimator.py:793-935), so that ``MHP.save`` / ``MHP.load_fit_estimators``
+    # (mhp.py:2428-2437, :2489-2506) work with these estimators and files written by either
+    # implementation load into the other.  Device handles, the model and the path are not saved;
+    # ``load`` takes them as arguments like the reference's.
+    _BASIC_ATTRS = ('is_grad_target', 'is_log_ixs', 'is_log_allocs', 'is_log_total_estimates',
+                    'is_log_strata_estimates', 'is_log_lse', 'k', 'n_iter')
+    _STATE_ATTRS = ('t', 'mu_term', 'diff_mu_term', 'sum_f', 'sum_diff_f')
+    _TOTAL_LOG_ATTRS = ('mu_term_log', 'diff_mu_term_log', 'sum_f_log', 'sum_diff_f_log')
+    _STRATA_LOG_ATTRS = ()
+    _STRATIFICATIONS_OPTIONAL = False   # exact estimators of marked models keep none
 
-    def load(self, file, **kwargs):
-        with open(file, 'rb') as f:
-            other = pickle.load(f)
-        self.__dict__.update(vars(other))
+    @staticmethod
+    def _part(file, suffix):
+        return file[:-7] + '_' + suffix + '.pickle' if file.endswith('.pickle') else file + '_' + suffix
+
+    def _saved_stratifications(self):
+        return self.stratif
+
+    def save(self, file, **kwargs):
+        def dump(suffix, obj):
+            with open(self._part(file, suffix), 'wb', **kwargs) as f:
+                pickle.dump(obj, f)
+        dump('basic_attr', {a: getattr(self, a) for a in self._BASIC_ATTRS})
+        stratif = self._saved_stratifications()
+        for name in self.list_log_names:
+            if name in stratif or not self._STRATIFICATIONS_OPTIONAL:
+                stratif[name].save(self._part(file, 'strf_' + name))
+        dump('current_state', {a: getattr(self, a) for a in self._STATE_ATTRS})
+        general = {}
+        if self.is_log_ixs:
+            general['logged_ixs'] = self.logged_ixs
+        if self.is_log_allocs:
+            general['logged_allocs'] = self.logged_allocs
+        if self.is_log_lse:
+            general['logged_lse'] = self.logged_lse
+        if general:
+            dump('general_logs', general)
+        estimates = {}
+        if self.is_log_total_estimates:
+            estimates.update({a: getattr(self, a) for a in self._TOTAL_LOG_ATTRS})
+        if self.is_log_strata_estimates:
+            estimates.update({a: getattr(self, a) for a in self._STRATA_LOG_ATTRS})
+        if estimates:
+            dump('estimates_logs', estimates)
+
+    def load(self, file, model, process_path, **kwargs):
+        def read(suffix, required=True):
+            try:
+                with open(self._part(file, suffix), 'rb') as f:
+                    return pickle.load(f)
+            except FileNotFoundError:
+                if required:
+                    raise
+                return {}
+        for attr, val in read('basic_attr').items():
+            setattr(self, attr, val)
+        self.initialize_model_data(model, process_path)
+        self.stratif = {}
+        for names, cls in ((self.get_singlesum_lognames(), GeneralStratification),
+                           (self.get_doublesum_lognames(), DoubleIxStratification)):
+            for name in names:
+                if self._STRATIFICATIONS_OPTIONAL and not os.path.exists(self._part(file, 'strf_' + name)):
+                    continue
+                strf = cls()
+                strf.load(self._part(file, 'strf_' + name))
+                self.stratif[name] = strf
+        self.list_log_names = self.get_list_log_names()
+        self.make_param_indexing()
+        for attr, val in read('current_state').items():
+            setattr(self, attr, val)
+        general = read('general_logs', required=False)
+        names = self.list_log_names
+        self.logged_ixs = (general['logged_ixs'] if self.is_log_ixs else
+                           {name: {'adaptive': None, 'nonadaptive': None} for name in names})
+        self.logged_allocs = (general['logged_allocs'] if self.is_log_allocs else
+                              {name: None for name in names})
+        if self.is_log_lse:
+            self.logged_lse = general['logged_lse']
+        # upstream opens the estimates file unconditionally and fails when no estimate log was
+        # kept (:1680-1689); here the file is optional like the general logs
+        for attr, val in read('estimates_logs', required=False).items():
+            setattr(self, attr, val)
 
 
 class MHPExactEstimB200(_B200Estimator):
@@ -267,9 +402,23 @@ class MHPExactEstimB200(_B200Estimator):
         self.n_iter = n_iter
         self.initialize_model_data(model, data)
         self.stratif = {}
+        self._strf_kwargs = dict(n_exact_single=n_exact_single,
+                                 n_samples_adaptive_single=n_samples_adaptive_single,
+                                 nonadaptive_sample_size_single=nonadaptive_sample_size_single,
+                                 single_strfs=single_strfs,
+                                 n_samples_adaptive_double=n_samples_adaptive_double,
+                                 nonadaptive_sample_size_double=nonadaptive_sample_size_double,
+                                 double_strfs=double_strfs)
         self.list_log_names = self.get_list_log_names()
         self.make_param_indexing()
         self.initialize_logs()
+
+    def _saved_stratifications(self):
+        """The reference's exact estimator carries (unused) stratifications and its ``load`` expects
+        their files; they are built here only when the estimator is saved (O(sum of lag ranges))."""
+        if not self.stratif:
+            self.set_stratification(**getattr(self, '_strf_kwargs', {}))
+        return self.stratif
 
     def initialize_logs(self):
         n_iter = self.n_iter
@@ -389,62 +538,14 @@ class MHPStratEstimB200(_B200Estimator):
         self.sum_diff_f_exact = {}
 
     # ---- stratification (mhp_stratified_estimator.py:55-204) ------------------------------
-    def set_singlesum_estimation(self, n_exact=None, n_samples_adaptive=None,
-                                 nonadaptive_sample_size=None, **kwargs):
-        d = self.d
-        local = {}
-        if n_exact is not None:
-            local['n_exact'] = n_exact
-        if n_samples_adaptive is not None:
-            local['n_samples_adaptive'] = n_samples_adaptive
-        if nonadaptive_sample_size is not None:
-            local['nonadaptive_sample_size'] = nonadaptive_sample_size
-        for key, prefix in (('psi_stratification', 'psi_'),
-                            ('upsilonzero_stratification', 'upsilonzero_')):
-            given = kwargs.get(key, [None] * d)
-            for i in range(d):
-                strf = given[i]
-                if strf is None:
-                    strf = GeneralStratification(n=self.n_events[i], **local)
-                self.stratif[prefix + str(i)] = strf
-
-    def set_doublesum_estimation(self, n_samples_adaptive=None, nonadaptive_sample_size=None,
-                                 **kwargs):
-        d, k = self.d, self.k
-        local = {}
-        if n_samples_adaptive is not None:
-            local['n_samples_adaptive'] = n_samples_adaptive
-        if nonadaptive_sample_size is not None:
-            local['nonadaptive_sample_size'] = nonadaptive_sample_size
-        given = kwargs.get('upsilon_stratification', [[None] * d for _ in range(d)])
-        for i, j in itertools.product(range(d), range(d)):
-            strf = given[i][j]
-            if strf is None:
-                strf = DoubleIxStratification(h_max=self.kappa[j][i][self.n_events[i] - 1] + 1,
-                                              **local)
-                strf.get_stratification_size(self.lag_sizes, i, j)
-            self.stratif['upsilon_%d_%d' % (i, j)] = strf
-        given = kwargs.get('phi_stratification', [None] * d)
-        for i in range(d):
-            strf = given[i]
-            if strf is None:
-                strf = DoubleIxStratification(h_max=self.kappa[i][k][self.n_events[k] - 1] + 1,
-                                              **local)
-                strf.get_stratification_size(self.lag_sizes, k, i)
-            self.stratif['phi_%d' % i] = strf
-
-    def set_stratification(self, n_exact_single=None, n_samples_adaptive_single=None,
-                           nonadaptive_sample_size_single=None, single_strfs=None,
-                           n_samples_adaptive_double=None, nonadaptive_sample_size_double=None,
-                           double_strfs=None):
-        self.stratif = {}
-        self.set_singlesum_estimation(n_exact=n_exact_single,
-                                      n_samples_adaptive=n_samples_adaptive_single,
-                                      nonadaptive_sample_size=nonadaptive_sample_size_single,
-                                      **(single_strfs or {}))
-        self.set_doublesum_estimation(n_samples_adaptive=n_samples_adaptive_double,
-                                      nonadaptive_sample_size=nonadaptive_sample_size_double,
-                                      **(double_strfs or {}))
+    _STATE_ATTRS = ('t', 'mu_term', 'diff_mu_term', 'sum_f', 'vecsum_f_adaptive', 'sum_f_adaptive',
+                    'vecsum_f_nonadaptive', 'sum_f_nonadaptive', 'sum_f_exact', 'sum_diff_f',
+                    'vecsum_diff_f_adaptive', 'sum_diff_f_adaptive', 'vecsum_diff_f_nonadaptive',
+                    'sum_diff_f_nonadaptive', 'sum_diff_f_exact')
+    _STRATA_LOG_ATTRS = ('vecsum_f_adaptive_log', 'sum_f_adaptive_log', 'vecsum_f_nonadaptive_log',
+                         'sum_f_nonadaptive_log', 'sum_f_exact_log', 'vecsum_diff_f_adaptive_log',
+                         'sum_diff_f_adaptive_log', 'vecsum_diff_f_nonadaptive_log',
+                         'sum_diff_f_nonadaptive_log', 'sum_diff_f_exact_log')
 
     def initialize(self, k, n_iter, model, data, n_exact_single=None,
                    n_samples_adaptive_single=None, nonadaptive_sample_size_single=None,

@@ -127,6 +127,13 @@ def _check_constant_baselines(model):
 class MTLHExactEstimB200(_B200Estimator):
     """Exact LSE_k and gradient of a marked model (MTLHExactEstim) on the device."""
 
+    # save / load: the file layout of mtlh_exact_estimator.py:1058-1209 with the attributes this
+    # estimator really has (upstream lists mu_term / diff_mu_term, which its marked estimators
+    # never set, so its own save raises AttributeError)
+    _STATE_ATTRS = ('t', 'M_term', 'diff_M_term', 'sum_f', 'sum_diff_f')
+    _TOTAL_LOG_ATTRS = ('M_term_log', 'sum_f_log')
+    _STRATIFICATIONS_OPTIONAL = True
+
     def initialize(self, k, n_iter, model, data, n_exact_single=None,
                    n_samples_adaptive_single=None, nonadaptive_sample_size_single=None,
                    single_strfs=None, n_samples_adaptive_double=None,
@@ -416,6 +423,11 @@ class MTLHStratEstimB200(MTLHExactEstimB200):
     """
 
     KIND = {'K': 0, 'upsilonzero': 1, 'phi': 2, 'upsilon': 3}
+    _STATE_ATTRS = MTLHExactEstimB200._STATE_ATTRS + (
+        'vecsum_f_adaptive', 'sum_f_adaptive', 'vecsum_f_nonadaptive', 'sum_f_nonadaptive', 'sum_f_exact',
+        'vecsum_diff_f_adaptive', 'sum_diff_f_adaptive', 'vecsum_diff_f_nonadaptive',
+        'sum_diff_f_nonadaptive', 'sum_diff_f_exact')
+    _STRATIFICATIONS_OPTIONAL = False
 
     # ---- stratifications (:76-169) -----------------------------------------------------------
     def initialize(self, k, n_iter, model, data, n_exact_single=None,
