@@ -224,6 +224,35 @@ class _B200Estimator(_RefEstimator):
                 grad[ix_param] = self.recombine_diff_lse_theta_kpr(p, r)
         return grad
 
+    # ---- the reference's per-term entry points (mhp_exact_estimator.py:543-707,
+    # mhp_stratified_estimator.py:1081-1331).  compute_objective batches all terms into one device
+    # call; these evaluate one term each for callers that use them directly.  The parameters of the
+    # kernels a term does not involve are placeholders (ones): they only enter terms that are not
+    # stored.
+    def _x_with(self, blocks, mu_k=1.):
+        x = np.ones(self.n_param_k)
+        x[0] = mu_k
+        for i, x_ki in blocks:
+            lo, hi = self.interval_map[self.k][i]
+            x[lo:hi] = np.asarray(x_ki, dtype=np.float64)
+        return x
+
+    def compute_psi_sum(self, i, x_ki, mu_k, **kwargs):
+        self._compute_terms(self._x_with([(i, x_ki)], mu_k), [('psi_%d' % i, KIND_PSI, i, i)], **kwargs)
+
+    def compute_upsilonzero_sum(self, i, x_ki, **kwargs):
+        self._compute_terms(self._x_with([(i, x_ki)]), [('upsilonzero_%d' % i, KIND_UPSILONZERO, i, i)], **kwargs)
+
+    def compute_phi_sum(self, i, x_ki, **kwargs):
+        self._compute_terms(self._x_with([(i, x_ki)]), [('phi_%d' % i, KIND_PHI, i, i)], **kwargs)
+
+    def compute_cross_upsilon_sum(self, i, j, x_ki, x_kj, **kwargs):
+        self._compute_terms(self._x_with([(i, x_ki), (j, x_kj)]),
+                            [('upsilon_%d_%d' % (i, j), KIND_UPSILON, i, j)], **kwargs)
+
+    def compute_sim_upsilon_sum(self, i, x_ki, **kwargs):
+        self._compute_terms(self._x_with([(i, x_ki)]), [('upsilon_%d_%d' % (i, i), KIND_UPSILON, i, i)], **kwargs)
+
     # ---- stratifications (mhp_stratified_estimator.py:39-117; the exact estimator of the
     # reference builds them too, mhp_exact_estimator.py:39-117, and writes them with save) ----------
     def set_singlesum_estimation(self, n_exact=None, n_samples_adaptive=None,
@@ -480,6 +509,20 @@ class MHPExactEstimB200(_B200Estimator):
         if count_iter:
             self.t += 1
 
+    def _compute_terms(self, x, terms, compute_f_sum=False, compute_diff_f_sum=True, verbose=False,
+                       **kwargs):
+        """The reference's per-term methods set the value whenever the derivatives are asked for
+        (:557-558).  The device evaluates the whole sub-problem; only ``terms`` are stored."""
+        if not (compute_f_sum or compute_diff_f_sum):
+            return
+        engine = self._bound_engine()
+        packed = engine.exact_sums_packed(self.k, x, True, compute_diff_f_sum)
+        sum_f, sum_diff_f = unpack_terms(engine.desc, self.k, packed)
+        for name, _, _, _ in terms:
+            self.sum_f[name] = sum_f[name]
+            if compute_diff_f_sum:
+                self.sum_diff_f[name] = sum_diff_f[name]
+
     def recombine_grad_lse_k(self):
         if not self.reference_recombine:
             return super().recombine_grad_lse_k()
@@ -678,11 +721,20 @@ class MHPStratEstimB200(_B200Estimator):
         x = np.asarray(x_k, dtype=np.float64)
         self.compute_mu_term(x[0], compute_f_sum=compute_f_sum,
                              compute_diff_f_sum=compute_diff_f_sum)
+        self.last_alloc_stat = {}   # name -> (mean, std, n_samples) of the allocation statistic per adaptive stratum
+        self._estimate_terms(x, self.term_list(), compute_f_sum, compute_diff_f_sum, grad_alloc, rng)
+        self.log_estimates()
+        if count_iter:
+            self.t += 1
+
+    def _estimate_terms(self, x, terms, compute_f_sum, compute_diff_f_sum, grad_alloc, rng):
+        """estimate_sum (:902-971) of the given terms: samples drawn term after term, one device
+        launch for all of them, results into the reference's attributes."""
         t_iter = self.t
         # ---- 1. draw every sample, term after term (host RNG, reference order) ----------
         plans = []
         dev_terms, offsets, all_m, all_n, sizes, defaults = [], [0], [], [], [], []
-        for name, kind, i, j in self.term_list():
+        for name, kind, i, j in terms:
             strf = self.stratif[name]
             plan = {'name': name, 'blocks': []}   # blocks: (domain, n_strata, counts)
             chunks = []
@@ -734,7 +786,8 @@ class MHPStratEstimB200(_B200Estimator):
                 grad_alloc=bool(grad_alloc))
         # ---- 3. fill the reference's result attributes -----------------------------------------------
         s_ix = 0
-        self.last_alloc_stat = {}   # name -> (mean, std, n_samples) of the allocation statistic per adaptive stratum
+        if not hasattr(self, 'last_alloc_stat'):
+            self.last_alloc_stat = {}
         for plan in plans:
             name = plan['name']
             strf = self.stratif[name]
@@ -783,9 +836,12 @@ class MHPStratEstimB200(_B200Estimator):
                     for ix_func in (1, 2):
                         self.sum_diff_f[name][ix_func] = (parts[0][ix_func] + parts[1][ix_func]
                                                           + parts[2][ix_func])
-        self.log_estimates()
-        if count_iter:
-            self.t += 1
+
+    def _compute_terms(self, x, terms, compute_f_sum=False, compute_diff_f_sum=True, grad_alloc=True,
+                       rng=None, seed=None, **kwargs):
+        if rng is None:
+            rng = np.random.default_rng(seed)
+        self._estimate_terms(x, terms, compute_f_sum, compute_diff_f_sum, grad_alloc, rng)
 
     def _store(self, name, domain, est, do_f, do_diff):
         """est[s, c]: estimate of the sum over stratum s of output c (0 = f, then

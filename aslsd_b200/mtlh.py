@@ -134,6 +134,10 @@ class MTLHExactEstimB200(_B200Estimator):
     _TOTAL_LOG_ATTRS = ('M_term_log', 'sum_f_log')
     _STRATIFICATIONS_OPTIONAL = True
 
+    def _compute_terms(self, *args, **kwargs):
+        raise NotImplementedError('marked models: the terms are evaluated together by compute_objective '
+                                  '(one device call); the per-term entry points are not served')
+
     def initialize(self, k, n_iter, model, data, n_exact_single=None,
                    n_samples_adaptive_single=None, nonadaptive_sample_size_single=None,
                    single_strfs=None, n_samples_adaptive_double=None,

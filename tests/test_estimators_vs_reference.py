@@ -360,3 +360,54 @@ def test_exact_estimator_save_load_two_dimensions(ref, tmp_path):
         _assert_same(est.sum_diff_f_log, back.sum_diff_f_log, 'sum_diff_f_log')
         np.testing.assert_allclose(back.recombine_grad_lse_k(), g, rtol=1e-13)
         np.testing.assert_allclose(back.lse_k_grad_estimate(x), g, rtol=1e-12)
+
+
+def test_per_term_entry_points_match_reference(ref):
+    """compute_{psi,upsilonzero,phi,sim_upsilon,cross_upsilon}_sum called one by one
+    (mhp_exact_estimator.py:543-707, mhp_stratified_estimator.py:1081-1331): same sums in the same
+    attributes and, for the stratified estimator, the same draws from the shared Generator."""
+    import aslsd_b200
+    name = 'exp2d'
+    model, mhp, path = _simulate(ref, name, 150.)
+    k = 1
+    x = np.asarray(case_x(name)[k], dtype=float)
+    x_k0, x_k1, mu_k = x[1:3], x[3:5], x[0]
+
+    def run(est, **kw):
+        est.clear_estimates()
+        est.compute_psi_sum(0, x_k0, mu_k, **kw)
+        est.compute_phi_sum(1, x_k1, **kw)
+        est.compute_cross_upsilon_sum(0, 1, x_k0, x_k1, **kw)
+        est.compute_sim_upsilon_sum(1, x_k1, **kw)
+        est.compute_upsilonzero_sum(0, x_k0, **kw)
+
+    touched = ['psi_0', 'phi_1', 'upsilon_0_1', 'upsilon_1_1', 'upsilonzero_0']
+    # exact
+    a = ref.MHPExactEstim()
+    a.initialize(k, 2, mhp, path)
+    b = aslsd_b200.MHPExactEstimB200(engine=OracleEngine())
+    b.initialize(k, 2, mhp, path)
+    run(a)
+    run(b)
+    for log_name in a.list_log_names:
+        _assert_same(a.sum_f[log_name], b.sum_f[log_name], 'sum_f ' + log_name)
+        _assert_same(a.sum_diff_f[log_name], b.sum_diff_f[log_name], 'sum_diff_f ' + log_name)
+        if log_name not in touched:
+            assert b.sum_f[log_name] == 0.
+    # stratified
+    a = ref.MHPStratEstim()
+    a.initialize(k, 3, mhp, path, **STRAT_KW)
+    b = aslsd_b200.MHPStratEstimB200(engine=OracleEngine())
+    b.initialize(k, 3, mhp, path, **STRAT_KW)
+    rng_a, rng_b = np.random.default_rng(21), np.random.default_rng(21)
+    for _ in range(2):
+        run(a, rng=rng_a, grad_alloc=False, compute_f_sum=True)
+        run(b, rng=rng_b, grad_alloc=False, compute_f_sum=True)
+        assert rng_a.bit_generator.state == rng_b.bit_generator.state
+        for log_name in a.list_log_names:
+            for attr in ('sum_f', 'sum_diff_f', 'vecsum_f_adaptive', 'sum_f_nonadaptive', 'sum_f_exact',
+                         'sum_diff_f_adaptive', 'sum_diff_f_nonadaptive', 'sum_diff_f_exact'):
+                _assert_same(getattr(a, attr)[log_name], getattr(b, attr)[log_name], attr + ' ' + log_name)
+            if a.stratif[log_name].n_adaptive_strata:
+                np.testing.assert_allclose(b.stratif[log_name].adaptive_rel_alloc,
+                                           a.stratif[log_name].adaptive_rel_alloc, rtol=1e-9, atol=1e-15)
