@@ -312,6 +312,20 @@ class _B200Estimator(_RefEstimator):
                                       nonadaptive_sample_size=nonadaptive_sample_size_double,
                                       **(double_strfs or {}))
 
+    def get_lse_k_components_log(self):
+        """(n_iter x n_terms table, names): what each term added to LSE_k at every iteration
+        (mhp_stratified_estimator.py:476-517; needs is_log_total_estimates)."""
+        d, T_f = self.d, self.T_f
+        weights = [('psi_%d' % i, 2.) for i in range(d)]
+        weights += [('upsilon_%d_%d' % (i, j), 2.) for i, j in itertools.product(range(d), range(d))]
+        weights += [('phi_%d' % i, -2.) for i in range(d)]
+        weights += [('upsilonzero_%d' % i, 1.) for i in range(d)]
+        table = np.zeros((self.n_iter, 1 + len(weights)))
+        table[:, 0] = self.mu_term_log
+        for col, (name, w) in enumerate(weights, start=1):
+            table[:, col] = w * (self.sum_f_log[name] / T_f)
+        return table, ['mu_term'] + [name for name, _ in weights]
+
     def get_log(self):
         logs = {}
         if self.is_log_lse:

@@ -266,6 +266,10 @@ def test_stratified_estimator_logs_match_reference(ref, name, T_f, tmp_path):
         assert len(log_attrs) == 14 and sorted(log_attrs) == sorted(a for a in vars(est_new) if a.endswith('_log'))
         for attr in log_attrs:
             _assert_same(getattr(est_ref, attr), getattr(est_new, attr), attr)
+        table_ref, names_ref = est_ref.get_lse_k_components_log()
+        table_new, names_new = est_new.get_lse_k_components_log()
+        assert names_new == names_ref
+        _assert_same(table_ref, table_new, 'lse_k components')
         # the objective alone (lse_k_estimate, :1391-1405), drawn from the same generator state
         np.testing.assert_allclose(est_new.lse_k_estimate(x, rng=rng_new, grad_alloc=False, count_iter=False),
                                    est_ref.lse_k_estimate(x, rng=rng_ref, grad_alloc=False, count_iter=False),
