@@ -25,7 +25,6 @@ NCCL allreduce per k (strong scaling: total work is fixed).
 import argparse
 import json
 import os
-import subprocess
 import sys
 import threading
 import time
