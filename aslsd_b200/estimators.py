@@ -379,8 +379,9 @@ class _B200Estimator(_RefEstimator):
             estimates.update({a: getattr(self, a) for a in self._TOTAL_LOG_ATTRS})
         if self.is_log_strata_estimates:
             estimates.update({a: getattr(self, a) for a in self._STRATA_LOG_ATTRS})
-        if estimates:
-            dump('estimates_logs', estimates)
+        # written even when empty: upstream's load opens this file unconditionally (:1680-1689), so its
+        # own files do not load back unless an estimate log was kept
+        dump('estimates_logs', estimates)
 
     def load(self, file, model, process_path, **kwargs):
         def read(suffix, required=True):

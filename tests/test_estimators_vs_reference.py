@@ -415,3 +415,25 @@ def test_per_term_entry_points_match_reference(ref):
             if a.stratif[log_name].n_adaptive_strata:
                 np.testing.assert_allclose(b.stratif[log_name].adaptive_rel_alloc,
                                            a.stratif[log_name].adaptive_rel_alloc, rtol=1e-9, atol=1e-15)
+
+
+def test_reference_model_save_writes_the_b200_estimators(ref, tmp_path):
+    """MHP.save (mhp.py:2380-2437) saves fit_estim[k] inside a bare try/except: an estimator whose
+    save raises is silently dropped.  After a fit with the B200 estimators the per-k files are there
+    and the reference's own estimator class reads them back."""
+    import aslsd_b200
+    model, mhp, path = _simulate(ref, 'exp2d', 120.)
+    x_0 = [np.array(x, dtype=object) for x in case_x('exp2d')]
+    mhp.fit(path, x_0=copy.deepcopy(x_0), n_iter=3, seed=99, write=True,
+            estimators=aslsd_b200.MHPStratEstimB200(engine=OracleEngine(), is_log_lse=True), **STRAT_KW)
+    assert isinstance(mhp.fit_estim[0], aslsd_b200.MHPStratEstimB200)
+    prefix = str(tmp_path / 'model')
+    mhp.save(prefix)
+    for k in range(2):
+        file_k = prefix + '_estimator_%d' % k
+        assert os.path.exists(file_k + '_basic_attr') and os.path.exists(file_k + '_strf_upsilon_0_1')
+        back = ref.MHPStratEstim()
+        back.load(file_k, mhp, path)
+        assert back.t == 3 and back.k == k
+        np.testing.assert_array_equal(back.logged_lse, mhp.fit_estim[k].logged_lse)
+        _assert_same(back.sum_diff_f, mhp.fit_estim[k].sum_diff_f, 'sum_diff_f')
