@@ -63,6 +63,27 @@ CASES = {
 }
 
 
+# Three event types: the sub-problem index k differs from both i and j in most upsilon_i_j terms,
+# which never happens for d <= 2 and is the rule in the 10-dimensional configuration C5.
+# Distinct parameters in every cell so that a swapped (k, i) / (k, j) slice cannot go unnoticed.
+CASES_3D = {
+    'exp3d': (square(3, exp_kernel), [.7, .5, .6],
+              [[[.15, 1.], [.2, 1.6], [.1, 2.2]],
+               [[.25, 1.3], [.1, .9], [.15, 1.9]],
+               [[.05, 2.5], [.2, 1.1], [.2, 1.4]]], 45.),
+    'sbf3d2': (square(3, lambda: sbf_gauss_kernel(2, beta=0.4, spacing=1.5)), [.6, .5, .7],
+               [[[.15, .05], [.1, .1], [.05, .15]],
+                [[.1, .15], [.2, .05], [.05, .05]],
+                [[.05, .1], [.15, .1], [.1, .2]]], 45.),
+    'gauss3d': (square(3, gauss_kernel), [.6, .7, .5],
+                [[[.15, .5, 1.], [.2, .7, 2.], [.1, .4, 1.5]],
+                 [[.2, .6, .5], [.1, .5, 2.5], [.15, .8, 1.]],
+                 [[.1, .45, 2.], [.15, .65, .8], [.2, .55, 1.2]]], 40.),
+}
+CASES.update(CASES_3D)
+NAMES_2D = sorted(set(CASES) - set(CASES_3D))   # the cases of the first golden set
+
+
 # Marked models (MTLH): name -> (model incl. impacts, x_k per k, number of events per type, T_f).
 # Constant baselines; linear impact 1 + <a, xi> on marks uniform in [0, 1]^q
 # (basis_impact_linear.py:36-41); kernels as above.

@@ -26,7 +26,7 @@ sys.path.insert(0, os.path.dirname(HERE))
 sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
 
 import ref_shim  # noqa: E402
-from cases import CASES, case_x, flatten_sums  # noqa: E402
+from cases import CASES, CASES_3D, case_x, flatten_sums  # noqa: E402
 
 
 def kernel_param_array(kp, d):
@@ -44,8 +44,10 @@ def simulate(ref, mhp, model, mu, kp, T_f, seed=1234):
                         verbose=False)
 
 
-def make_exact(ref):
+def make_exact(ref, names=None):
     for name, (model, mu, kp, T_f) in CASES.items():
+        if names is not None and name not in names:
+            continue
         d = model['d']
         mhp = ref_shim.build_reference_model(ref, model)
         path = simulate(ref, mhp, model, mu, kp, T_f)
@@ -130,6 +132,9 @@ def make_index_maps(ref):
 
 if __name__ == '__main__':
     ref = ref_shim.import_reference()
+    if sys.argv[1:] == ['3d']:     # only the three-type cases (added after the first set)
+        make_exact(ref, names=set(CASES_3D))
+        sys.exit(0)
     make_exact(ref)
     make_index_maps(ref)
     import make_golden_strat

@@ -52,7 +52,7 @@ STRAT_KW = dict(n_exact_single=50, n_samples_adaptive_single=60, nonadaptive_sam
 
 @pytest.mark.parametrize('name,T_f,grad_alloc', [('exp1d', 600., False), ('exp2d', 150., False),
                                                  ('exp2d', 150., True), ('sbf2d3', 300., False),
-                                                 ('gauss1d', 300., True)])
+                                                 ('gauss1d', 300., True), ('sbf3d2', 120., False)])
 def test_stratified_estimator_tracks_reference(ref, name, T_f, grad_alloc):
     import aslsd_b200
     model, mhp, path = _simulate(ref, name, T_f)
@@ -109,7 +109,8 @@ def test_stratified_estimator_tracks_reference(ref, name, T_f, grad_alloc):
         assert set(est_new.get_log()) == set(est_ref.get_log())
 
 
-@pytest.mark.parametrize('name,T_f', [('exp2d', 60.), ('sbf2d3', 100.), ('gauss1d', 100.)])
+@pytest.mark.parametrize('name,T_f', [('exp2d', 60.), ('sbf2d3', 100.), ('gauss1d', 100.), ('exp3d', 50.),
+                                      ('gauss3d', 40.)])
 def test_exact_estimator_matches_reference(ref, name, T_f):
     import aslsd_b200
     model, mhp, path = _simulate(ref, name, T_f)
