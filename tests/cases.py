@@ -111,6 +111,17 @@ MTLH_CASES = {
 }
 
 
+# three event types, distinct parameters in every cell (see CASES_3D)
+MTLH_CASES_3D = {
+    'mtlh_exp3d': (mtlh_model(3, exp_kernel, _linear),
+                   [[.7, .15, 1., .2, 1.6, .1, 2.2, .5, .7, .3],
+                    [.5, .25, 1.3, .1, .9, .15, 1.9, .4, .9, .6],
+                    [.6, .05, 2.5, .2, 1.1, .2, 1.4, .8, .2, .5]], [45, 38, 52], 40.),
+}
+MTLH_NAMES_2D = sorted(MTLH_CASES)
+MTLH_CASES.update(MTLH_CASES_3D)
+
+
 # stratified traces of marked models: name -> (case of MTLH_CASES, events per type, T_f,
 # stratification keywords, iterations, RNG seed)
 _MTLH_KW = dict(n_exact_single=20, n_samples_adaptive_single=200, nonadaptive_sample_size_single=100,

@@ -67,6 +67,8 @@ def main():
     from aslsd.stats.events.process_path import ProcessPath
     from aslsd.optimize.estimators.mtlh_exact_estimator import MTLHExactEstim
     for name, (model, xs, n_events, T_f) in MTLH_CASES.items():
+        if sys.argv[1:] and name not in sys.argv[1:]:
+            continue
         d = model['d']
         mtlh = build_reference_mtlh(model)
         times, marks, T_f = mtlh_inputs(name)

@@ -6,7 +6,7 @@ Tolerance: relative 1e-10 per entry (BASELINE.json north_star), fp64."""
 import numpy as np
 import pytest
 
-from cases import MTLH_CASES, mtlh_inputs
+from cases import MTLH_CASES, MTLH_NAMES_2D, mtlh_inputs
 from helpers import RTOL, load_golden
 from oracle import mtlh_exact as OM
 
@@ -23,7 +23,7 @@ def _flat_state(est, prefix):
     return OM.flatten(est.M_term, est.diff_M_term, est.sum_f, est.sum_diff_f, prefix)
 
 
-@pytest.mark.parametrize('name', sorted(MTLH_CASES))
+@pytest.mark.parametrize('name', MTLH_NAMES_2D)
 def test_mtlh_exact_matches_reference_golden(engine, name):
     import aslsd_b200
     model, xs, n_events, T_f = MTLH_CASES[name]

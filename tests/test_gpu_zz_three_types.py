@@ -125,6 +125,12 @@ def test_estimators_on_three_types(engine, name):
             np.testing.assert_allclose(g_dev, g_cpu, rtol=1e-9, atol=1e-9 * np.abs(g_cpu).max())
 
 
+def test_marked_model_matches_reference_golden(engine):
+    """mtlh_exp3d: golden vector of the reference's MTLHExactEstim with three event types."""
+    import test_gpu_mtlh as TM
+    TM.test_mtlh_exact_matches_reference_golden(engine, 'mtlh_exp3d')
+
+
 if __name__ == '__main__':
     # dry run of the test bodies that only need the engine interface, on the oracle test double
     from oracle_engine import OracleEngine

@@ -24,7 +24,7 @@ def _reference_setup(name):
     return model, xs, mtlh, ProcessPath(times, T_f, list_marks=marks)
 
 
-@pytest.mark.parametrize('name', ['mtlh_exp2d', 'mtlh_gauss1d', 'mtlh_exp1d_m2'])
+@pytest.mark.parametrize('name', ['mtlh_exp2d', 'mtlh_gauss1d', 'mtlh_exp1d_m2', 'mtlh_exp3d'])
 def test_estimator_state_matches_reference_estimator(name):
     import aslsd_b200
     from aslsd.optimize.estimators.mtlh_exact_estimator import MTLHExactEstim
