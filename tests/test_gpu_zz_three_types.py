@@ -77,7 +77,8 @@ def test_exact_sums_match_windowed_oracle_medium(engine, name):
     ks = list(range(d))
     batch = engine.exact_sums_batch(ks, xs)
     for k in ks:
-        np.testing.assert_allclose(batch[k], engine.exact_sums_packed(k, xs[k]), rtol=1e-12, atol=1e-12)
+        # (the quadrature bins of a batch differ from those of a single k: test_gpu_exact.py)
+        np.testing.assert_allclose(batch[k], engine.exact_sums_packed(k, xs[k]), rtol=1e-10, atol=1e-9)
     # time-block shards add up
     from aslsd_b200.distributed import time_block_ranges
     acc = np.zeros_like(batch[1])
