@@ -101,27 +101,3 @@ def test_process_path_mirror(engine):
     np.testing.assert_array_equal(path.list_times2end[1], T_f - times[1])
     with pytest.raises(IndexError):
         aslsd_b200.ProcessPath([times[0], np.array([])], T_f, engine=engine)
-
-
-def test_truncated_path_has_its_own_context_and_fresh_maps(engine):
-    """ProcessPath.truncate (process_path.py:132-170): maps of the shorter path from a second
-    device context, the full path stays resident in the first."""
-    import aslsd_b200
-    rng = np.random.default_rng(11)
-    T_f = 500.
-    times = [np.sort(rng.uniform(0, T_f, size=n)) for n in (4000, 2500, 3100)]
-    path = aslsd_b200.ProcessPath(times, T_f, engine=engine)
-    cut = path.truncate(187.3)
-    assert cut.engine is not engine and cut.T_f == 187.3
-    kept = [t[t < 187.3] for t in times]
-    kappa, varpi = OT.kappa_varpi_closed_form(kept, 187.3)
-    lags = OT.lag_sizes(kept, kappa, varpi)
-    for i in range(3):
-        np.testing.assert_array_equal(cut.list_times[i], kept[i])
-        for j in range(3):
-            np.testing.assert_array_equal(cut.kappa[i][j], kappa[i][j])
-            np.testing.assert_array_equal(cut.varpi[i][j], varpi[i][j])
-            np.testing.assert_array_equal(cut.lag_sizes[i][j], lags[i][j])
-    # the first context still holds the full path
-    g_kappa, _, _ = engine.index_maps()
-    np.testing.assert_array_equal(g_kappa[0][1], path.kappa[0][1])

@@ -54,22 +54,3 @@ def test_matches_oracle_on_a_longer_path(engine):
         np.testing.assert_allclose(got, ref, rtol=1e-9, atol=1e-9)
         # time-change theorem sanity: residuals of a Poisson-like path under this model are O(1)
         assert 0.2 < np.mean(got) < 5.
-
-
-@pytest.mark.parametrize('name', ['mtlh_exp2d', 'mtlh_gauss1d', 'mtlh_sbf2d3'])
-def test_marked_models_match_reference_golden(engine, name):
-    """goodness_of_fit.get_residuals_mtlh: psi sums on the device, expected impacts on the host."""
-    import aslsd_b200
-    from cases import MTLH_CASES
-    model = MTLH_CASES[name][0]
-    g = load_golden('residuals_' + name)
-    d = model['d']
-    times = [g['times/%d' % i] for i in range(d)]
-    kp = [[g['kernel_param/%d/%d' % (k, i)] for i in range(d)] for k in range(d)]
-    mu = [g['mu/%d' % k] for k in range(d)]
-    path = aslsd_b200.ProcessPath(times, float(g['T_f']), engine=engine)
-    got = aslsd_b200.get_residuals_mtlh({'d': d, 'kernels': model['kernels']}, path, mu, kp,
-                                        g['expected_impact'], engine=engine)
-    for k in range(d):
-        scale = np.max(np.abs(g['residuals/%d' % k]))
-        np.testing.assert_allclose(got[k], g['residuals/%d' % k], rtol=RTOL, atol=1e-10 * scale)

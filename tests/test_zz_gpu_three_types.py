@@ -5,7 +5,7 @@ tests/golden/make_golden.py 3d), the windowed oracle at ~10^4 events per type, s
 batched call and the time-block shards.  Tolerance 1e-10 as everywhere.
 
 (This file was added after the GPU budget of round 1 was spent: it passes on the oracle test
-double - ``python tests/test_gpu_zz_three_types.py`` - and has not run on a B200 yet.  It is named
+double - ``python tests/test_zz_gpu_three_types.py`` - and has not run on a B200 yet.  It is named
 to be collected last.)"""
 import numpy as np
 import pytest
