@@ -180,6 +180,27 @@ extern "C" int aslsd_rng_choice(aslsd_pcg64* gen, int64_t pop, int64_t size, int
   return rc;
 }
 
+// All strata of one single-sum term: sample_single_ix_stratified (useful_statistics.py:38-60),
+// lo[s] + choice(hi[s] - lo[s] + 1, n_samples[s], replace=False) for every stratum in turn.
+extern "C" int aslsd_sample_single_ix(aslsd_pcg64* gen, int64_t n_strata, const int64_t* lo, const int64_t* hi,
+                                      const int64_t* n_samples, int64_t* out) {
+  if (!gen || n_strata < 0 || (n_strata > 0 && (!lo || !hi || !n_samples))) return ASLSD_ERR_ARG;
+  Pcg g(*gen);
+  std::vector<int64_t> scratch;
+  std::vector<uint64_t> set;
+  int64_t pos = 0;
+  for (int64_t s = 0; s < n_strata; ++s) {
+    const int64_t ns = n_samples[s], pop = hi[s] - lo[s] + 1;
+    if (ns < 0 || (ns > 0 && !out)) return ASLSD_ERR_ARG;
+    const int rc = choice_no_replace(g, pop, ns, out + pos, scratch, set);
+    if (rc) return rc;
+    for (int64_t q = 0; q < ns; ++q) out[pos + q] += lo[s];
+    pos += ns;
+  }
+  g.store(gen);
+  return ASLSD_OK;
+}
+
 // All strata of one double-sum term: sample_double_ix_stratified (useful_statistics.py:112-127)
 // over sample_double_ix_stratum (:73-109).  varpi_ij = varpi[i][j], kappa_ji = kappa[j][i].
 // Stratum s writes n_samples[s] pairs at m_out / n_out + sum(n_samples[:s]).

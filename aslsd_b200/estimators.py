@@ -716,15 +716,24 @@ class MHPStratEstimB200(_B200Estimator):
 
     # ---- sampling plan of one term -------------------------------------------------------------
     def _draw(self, kind, i, j, strata, n_samples, rng):
-        """Samples of the given strata as a list of (m, n) arrays (n is None for
-        single-index terms); RNG consumption as in the compute_*_sum closures."""
+        """Samples of the given strata: (per-stratum list for the index log or None, all m in one
+        array, all n in one array - None for single-index terms -, samples per stratum); RNG
+        consumption as in the compute_*_sum closures."""
         if kind in (KIND_PSI, KIND_UPSILONZERO):
-            raw = sampling.sample_single_ix_stratified(strata, n_samples, rng)
-            return raw, [(np.asarray(ix), None) for ix in raw]
-        tgt, src = (self.k, i) if kind == KIND_PHI else (i, j)
-        raw = sampling.sample_double_ix_stratified(tgt, src, strata, n_samples, self.kappa,
-                                                   self.varpi, self.n_events, rng)
-        return raw, [(np.asarray(s['m']), np.asarray(s['n'])) for s in raw]
+            m, counts = sampling.sample_single_ix_stratified(strata, n_samples, rng, flat=True)
+            n = None
+        else:
+            tgt, src = (self.k, i) if kind == KIND_PHI else (i, j)
+            m, n, counts = sampling.sample_double_ix_stratified(tgt, src, strata, n_samples, self.kappa,
+                                                                self.varpi, self.n_events, rng, flat=True)
+        raw = None
+        if self.is_log_ixs:     # the reference logs one array (single) / one {'m', 'n'} dict (double) per stratum
+            offs = np.concatenate([[0], np.cumsum(counts)])
+            if n is None:
+                raw = [m[offs[q]:offs[q + 1]] for q in range(len(counts))]
+            else:
+                raw = [{'m': m[offs[q]:offs[q + 1]], 'n': n[offs[q]:offs[q + 1]]} for q in range(len(counts))]
+        return raw, m, n, counts
 
     def compute_objective(self, x_k, compute_f_sum=False, compute_diff_f_sum=True,
                           grad_alloc=True, rng=None, seed=None, count_iter=True):
@@ -748,11 +757,17 @@ class MHPStratEstimB200(_B200Estimator):
         t_iter = self.t
         # ---- 1. draw every sample, term after term (host RNG, reference order) ----------
         plans = []
-        dev_terms, offsets, all_m, all_n, sizes, defaults = [], [0], [], [], [], []
+        dev_terms, all_m, all_n, all_counts, sizes, defaults = [], [], [], [], [], []
+
+        def add(m, n, counts, size_vec, default_vec):
+            all_m.append(m)
+            all_n.append(n if n is not None else np.zeros(len(m), dtype=np.int64))
+            all_counts.append(np.asarray(counts, dtype=np.int64))
+            sizes.append(size_vec)
+            defaults.append(default_vec)
         for name, kind, i, j in terms:
             strf = self.stratif[name]
-            plan = {'name': name, 'blocks': []}   # blocks: (domain, n_strata, counts)
-            chunks = []
+            plan = {'name': name, 'blocks': [], 'counts': []}   # blocks: (domain, n_strata)
             if strf.n_adaptive_strata > 0:
                 n_a = strf.n_adaptive_strata
                 rel_alloc = (strf.ema_weight * strf.adaptive_rel_alloc
@@ -761,44 +776,40 @@ class MHPStratEstimB200(_B200Estimator):
                 n_samples = [min(strf.adaptive_strata_sizes[s],
                                  max(1, int(rel_alloc[s] * (n_a + strf.n_samples_adaptive[0]))))
                              for s in range(n_a)]                                  # :587
-                raw, flat = self._draw(kind, i, j, strf.adaptive_strata, n_samples, rng)
+                raw, m, n, counts = self._draw(kind, i, j, strf.adaptive_strata, n_samples, rng)
                 if self.is_log_ixs:
                     self.logged_ixs[name]['adaptive'][t_iter] = [[s] for s in raw]
-                chunks += flat
-                sizes += [float(s) for s in strf.adaptive_strata_sizes]
-                defaults += [float(a) for a in rel_alloc]
+                add(m, n, counts, np.asarray(strf.adaptive_strata_sizes, dtype=np.float64),
+                    np.asarray(rel_alloc, dtype=np.float64))
                 plan['blocks'].append(('adaptive', n_a))
+                plan['counts'].append(counts)
             if strf.n_nonadaptive_strata > 0:
-                raw, flat = self._draw(kind, i, j, strf.nonadaptive_strata,
-                                       strf.nonadaptive_abs_alloc, rng)
+                raw, m, n, counts = self._draw(kind, i, j, strf.nonadaptive_strata,
+                                               strf.nonadaptive_abs_alloc, rng)
                 if self.is_log_ixs:
                     self.logged_ixs[name]['nonadaptive'][t_iter] = raw
-                chunks += flat
-                sizes += [0.] * strf.n_nonadaptive_strata
-                defaults += [0.] * strf.n_nonadaptive_strata
+                add(m, n, counts, np.zeros(strf.n_nonadaptive_strata), np.zeros(strf.n_nonadaptive_strata))
                 plan['blocks'].append(('nonadaptive', strf.n_nonadaptive_strata))
+                plan['counts'].append(counts)
             if strf.n_exact > 0:
-                chunks.append((np.asarray(strf.exact_domain), None))
-                sizes.append(0.)
-                defaults.append(0.)
+                m = np.asarray(strf.exact_domain)
+                add(m, None, [len(m)], np.zeros(1), np.zeros(1))
                 plan['blocks'].append(('exact', 1))
-            for m, n in chunks:
-                all_m.append(m)
-                all_n.append(n if n is not None else np.zeros(len(m), dtype=np.int64))
-                offsets.append(offsets[-1] + len(m))
-            plan['counts'] = [len(m) for m, _ in chunks]
-            if chunks:
-                dev_terms.append((kind, i, j, len(chunks)))
+                plan['counts'].append(np.array([len(m)], dtype=np.int64))
+            n_chunks = sum(n_strata for _, n_strata in plan['blocks'])
+            if n_chunks:
+                dev_terms.append((kind, i, j, n_chunks))
             plans.append(plan)
         # ---- 2. one launch ----------------------------------------------------------------------
         if dev_terms:
             engine = self._bound_engine()
-            ix_m = np.concatenate(all_m) if all_m else np.zeros(0, dtype=np.int64)
-            ix_n = np.concatenate(all_n) if all_n else np.zeros(0, dtype=np.int64)
+            ix_m = np.concatenate(all_m)
+            ix_n = np.concatenate(all_n)
+            offsets = np.concatenate([[0], np.cumsum(np.concatenate(all_counts))])
             sums, out_off, stat_mean, stat_std, rel = engine.sampled_sums(
-                self.k, x, dev_terms, offsets, ix_m, ix_n, strata_sizes=sizes,
-                default_alloc=defaults, compute_diff_f_sum=bool(compute_diff_f_sum or grad_alloc),
-                grad_alloc=bool(grad_alloc))
+                self.k, x, dev_terms, offsets, ix_m, ix_n, strata_sizes=np.concatenate(sizes),
+                default_alloc=np.concatenate(defaults),
+                compute_diff_f_sum=bool(compute_diff_f_sum or grad_alloc), grad_alloc=bool(grad_alloc))
         # ---- 3. fill the reference's result attributes -----------------------------------------------
         s_ix = 0
         if not hasattr(self, 'last_alloc_stat'):
@@ -807,8 +818,7 @@ class MHPStratEstimB200(_B200Estimator):
             name = plan['name']
             strf = self.stratif[name]
             n_func, n_param = self.n_func[name], self.n_param[name]
-            c_ix = 0
-            for domain, n_strata in plan['blocks']:
+            for (domain, n_strata), counts in zip(plan['blocks'], plan['counts']):
                 # which sums each domain produces (:549-554, :795-796, :872-873)
                 do_f, do_diff = compute_f_sum, compute_diff_f_sum
                 if domain == 'adaptive':
@@ -820,9 +830,9 @@ class MHPStratEstimB200(_B200Estimator):
                     do_f = True
                 if domain == 'adaptive' and not grad_alloc and self.reference_adaptive_grad:
                     do_diff = False   # reference quirk: see __init__
-                block = np.stack([sums[out_off[s_ix + s]:out_off[s_ix + s + 1]]
-                                  for s in range(n_strata)])          # (n_strata, n_out)
-                counts = np.asarray(plan['counts'][c_ix:c_ix + n_strata], dtype=np.float64)
+                # the strata of a term are contiguous and have the same number of outputs
+                block = sums[out_off[s_ix]:out_off[s_ix + n_strata]].reshape(n_strata, -1)   # (n_strata, n_out)
+                counts = np.asarray(counts, dtype=np.float64)
                 if domain == 'exact':
                     est = block                                          # plain sums (:883)
                 else:
@@ -837,7 +847,6 @@ class MHPStratEstimB200(_B200Estimator):
                     if self.is_log_allocs:
                         self.logged_allocs[name][t_iter] = strf.adaptive_rel_alloc.copy()
                 s_ix += n_strata
-                c_ix += n_strata
             # totals (:947-967)
             if compute_f_sum:
                 self.sum_f[name] = (self.sum_f_adaptive[name] + self.sum_f_nonadaptive[name]

@@ -50,34 +50,39 @@ def _store_state(rng, g):
         'has_uint32': int(g.has_uint32), 'uinteger': int(g.uinteger)}
 
 
-def sample_single_ix_stratified(strata, n_samples, rng):
+def sample_single_ix_stratified(strata, n_samples, rng, flat=False):
     """samples[s] = lo_s + choice(hi_s - lo_s + 1, n_samples[s], replace=False).  With a PCG64
-    generator the draws are made by the native restatement of ``Generator.choice``
-    (aslsd_rng_choice: same values, same final state, tests/test_sampling_stream.py) - numpy
+    generator all strata are drawn by one native call (aslsd_sample_single_ix: the restatement of
+    ``Generator.choice``, same values and same final state, tests/test_sampling_stream.py) - numpy
     builds arange(population) for every large stratum, the native tail shuffle only touches the
-    sampled positions."""
+    sampled positions.  ``flat``: return (all samples in one array, samples per stratum) instead of
+    one array per stratum."""
     for lo, hi in strata:
         if lo > hi:
             raise ValueError('m_inf should be smaller than m_sup')
     native = _native_state(rng) if len(strata) else None
     if native is None:
-        return [lo + rng.choice(hi - lo + 1, size=n, replace=False) for (lo, hi), n in zip(strata, n_samples)]
+        out = [lo + rng.choice(hi - lo + 1, size=n, replace=False) for (lo, hi), n in zip(strata, n_samples)]
+        if not flat:
+            return out
+        counts = np.array([len(a) for a in out], dtype=np.int64)
+        return (np.concatenate(out).astype(np.int64) if out else np.zeros(0, dtype=np.int64)), counts
     lib, g = native
-    out = []
-    for (lo, hi), n in zip(strata, n_samples):
-        n = int(n)
-        pop = int(hi) - int(lo) + 1
-        if n > pop:
-            raise ValueError('Cannot take a larger sample than population when replace is False')
-        buf = np.empty(n, dtype=np.int64)
-        rc = lib.aslsd_rng_choice(ctypes.byref(g), pop, n, 0, capi.ptr_i64(buf))
-        if rc != 0:
-            raise ValueError('Cannot take a larger sample than population when replace is False')
-        if lo:
-            buf += int(lo)
-        out.append(buf)
+    bounds = np.ascontiguousarray(strata, dtype=np.int64).reshape(len(strata), 2)
+    lo, hi = np.ascontiguousarray(bounds[:, 0]), np.ascontiguousarray(bounds[:, 1])
+    n_s = np.ascontiguousarray(n_samples, dtype=np.int64)
+    if np.any(n_s > hi - lo + 1):
+        raise ValueError('Cannot take a larger sample than population when replace is False')
+    buf = np.empty(int(n_s.sum()), dtype=np.int64)
+    rc = lib.aslsd_sample_single_ix(ctypes.byref(g), len(strata), capi.ptr_i64(lo), capi.ptr_i64(hi),
+                                    capi.ptr_i64(n_s), capi.ptr_i64(buf))
+    if rc != 0:
+        raise ValueError('Cannot take a larger sample than population when replace is False')
     _store_state(rng, g)
-    return out
+    if flat:
+        return buf, n_s
+    offs = np.concatenate([[0], np.cumsum(n_s)])
+    return [buf[offs[q]:offs[q + 1]] for q in range(len(strata))]
 
 
 def sample_double_ix_stratum(i, j, h_inf, h_sup, n_samples, kappa, varpi, n_events, rng):
@@ -116,13 +121,21 @@ def sample_double_ix_stratum(i, j, h_inf, h_sup, n_samples, kappa, varpi, n_even
     return {'m': m_all, 'n': kap[m_all] - h_all + 1}
 
 
-def sample_double_ix_stratified(i, j, strata, n_samples, kappa, varpi, n_events, rng):
+def sample_double_ix_stratified(i, j, strata, n_samples, kappa, varpi, n_events, rng, flat=False):
     """All strata of a term.  With a PCG64 generator one native call draws them all
-    (aslsd_sample_double_ix: the same draws as the loop below, tests/test_sampling_stream.py)."""
+    (aslsd_sample_double_ix: the same draws as the loop below, tests/test_sampling_stream.py).
+    ``flat``: return (m, n, samples per stratum) with all strata in one pair of arrays."""
     native = _native_state(rng) if len(strata) else None
     if native is None:
-        return [sample_double_ix_stratum(i, j, h_inf, h_sup, n, kappa, varpi, n_events, rng)
-                for (h_inf, h_sup), n in zip(strata, n_samples)]
+        out = [sample_double_ix_stratum(i, j, h_inf, h_sup, n, kappa, varpi, n_events, rng)
+               for (h_inf, h_sup), n in zip(strata, n_samples)]
+        if not flat:
+            return out
+        counts = np.array([len(s['m']) for s in out], dtype=np.int64)
+        if not out:
+            return np.zeros(0, dtype=np.int64), np.zeros(0, dtype=np.int64), counts
+        return (np.concatenate([s['m'] for s in out]).astype(np.int64),
+                np.concatenate([s['n'] for s in out]).astype(np.int64), counts)
     lib, g = native
     h_inf = np.ascontiguousarray([s[0] for s in strata], dtype=np.int64)
     h_sup = np.ascontiguousarray([s[1] for s in strata], dtype=np.int64)
@@ -138,5 +151,7 @@ def sample_double_ix_stratified(i, j, strata, n_samples, kappa, varpi, n_events,
     if rc != 0:
         raise ValueError('Cannot take a larger sample than population when replace is False')
     _store_state(rng, g)
+    if flat:
+        return m, n, n_s
     offs = np.concatenate([[0], np.cumsum(n_s)])
     return [{'m': m[offs[q]:offs[q + 1]], 'n': n[offs[q]:offs[q + 1]]} for q in range(len(strata))]

@@ -162,6 +162,11 @@ typedef struct {
 } aslsd_pcg64;
 /* Generator.choice(pop, size, replace=replace) (no p, shuffle=True) into out[size]. */
 int aslsd_rng_choice(aslsd_pcg64* gen, int64_t pop, int64_t size, int replace, int64_t* out);
+/* All strata of one single-sum term (utilities/useful_statistics.py:38-60,
+ * sample_single_ix_stratified): stratum s covers the indices [lo[s], hi[s]] and gets
+ * n_samples[s] of them without replacement, written one stratum after the other to out. */
+int aslsd_sample_single_ix(aslsd_pcg64* gen, int64_t n_strata, const int64_t* lo, const int64_t* hi,
+                           const int64_t* n_samples, int64_t* out);
 /* All strata of one double-sum term (targets of type i, sources of type j): stratum s covers
  * the index lags [h_inf[s], h_sup[s]] and gets n_samples[s] pairs, written one stratum after
  * the other to m_out / n_out.  varpi_ij = varpi[i][j], kappa_ji = kappa[j][i]. */

@@ -3,6 +3,7 @@ call-by-call sampler (utilities/useful_statistics.py:73-109): same samples, same
 from collections import Counter
 
 import numpy as np
+import pytest
 
 from aslsd_b200 import sampling
 
@@ -109,3 +110,45 @@ def test_native_single_index_sampler_keeps_the_reference_stream():
         for w, g in zip(want, got):
             np.testing.assert_array_equal(g, w)
         assert str(a.bit_generator.state) == str(b.bit_generator.state)
+        # flat mode: the same draws in one array, with the counts per stratum
+        c = np.random.default_rng(seed)
+        if seed == 4:
+            c.integers(0, 7)
+        flat, counts = sampling.sample_single_ix_stratified(strata, n_samples, c, flat=True)
+        np.testing.assert_array_equal(flat, np.concatenate(want))
+        np.testing.assert_array_equal(counts, [len(w) for w in want])
+        assert str(a.bit_generator.state) == str(c.bit_generator.state)
+    # an empty stratum list, a zero-size sample, and a request larger than the population
+    rng = np.random.default_rng(0)
+    assert sampling.sample_single_ix_stratified([], [], rng) == []
+    got = sampling.sample_single_ix_stratified([(5, 9), (10, 12)], [0, 3], rng)
+    assert len(got[0]) == 0 and sorted(got[1]) == [10, 11, 12]
+    with pytest.raises(ValueError):
+        sampling.sample_single_ix_stratified([(5, 9)], [6], rng)
+    with pytest.raises(ValueError):
+        sampling.sample_single_ix_stratified([(9, 5)], [1], rng)
+
+
+def test_flat_double_index_sampler_is_the_list_form():
+    rng = np.random.default_rng(5)
+    n_i, n_j = 4000, 3500
+    t_i, t_j = np.sort(rng.uniform(0, 100., n_i)), np.sort(rng.uniform(0, 100., n_j))
+    from oracle import time_ordering as OT
+    kappa, varpi = OT.kappa_varpi_closed_form([t_i, t_j], 100.)
+    strata = [(1, 1), (2, 2), (3, 3), (4, 40), (41, 900), (901, int(kappa[1][0][n_i - 1]) + 1)]
+    n_samples = [30, 30, 30, 200, 200, 200]
+    for native in (True, False):
+        a, b = np.random.default_rng(8), np.random.default_rng(8)
+        if not native:     # a generator the native sampler does not restate: the numpy path
+            a, b = (np.random.Generator(np.random.Philox(8)) for _ in range(2))
+        want = sampling.sample_double_ix_stratified(0, 1, strata, n_samples, kappa, varpi, [n_i, n_j], a)
+        m, n, counts = sampling.sample_double_ix_stratified(0, 1, strata, n_samples, kappa, varpi, [n_i, n_j], b,
+                                                            flat=True)
+        np.testing.assert_array_equal(m, np.concatenate([w['m'] for w in want]))
+        np.testing.assert_array_equal(n, np.concatenate([w['n'] for w in want]))
+        np.testing.assert_array_equal(counts, n_samples)
+        assert str(a.bit_generator.state) == str(b.bit_generator.state)
+        w1 = sampling.sample_single_ix_stratified([(0, 99), (100, 4000)], [10, 50], a)
+        f1, c1 = sampling.sample_single_ix_stratified([(0, 99), (100, 4000)], [10, 50], b, flat=True)
+        np.testing.assert_array_equal(f1, np.concatenate(w1))
+        np.testing.assert_array_equal(c1, [10, 50])
