@@ -42,6 +42,14 @@ def exercise(name, engine):
         engine.point_sums(k, xs[k], 'phi')
         engine.point_sums(k, xs[k], 'psi')
     engine.exact_sums_batch(ks, xs)
+    work = engine.last_work_counts()
+    # the plan itself is host work: items of the d sub-problems before sharing, unique rows after
+    R = len(model['kernels'][0][0])
+    assert work['items'] == d * (d * (2 * R + 2 * R * R) + d * (d - 1) * R * R), (name, work)
+    assert work['rows'] <= work['items']
+    if name in ('sbf2d3', 'sbf3d2'):
+        # (beta, delta) fixed: upsilon, upsilonzero and psi rows do not depend on k, phi rows do
+        assert work['rows'] == d * d * R * R + d * R * R + d * R + d * d * R, (name, work)
     engine.exact_sums_batch(ks, xs, count_pairs=True)
     engine.exact_max_lag(ks, xs)
     for block in time_block_ranges(times, 3):
