@@ -69,6 +69,7 @@ SYMBOLS = {
     'aslsd_exact_sums': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, c_f64_p, ctypes.c_int,
                                         c_i64_p, c_i64_p, c_f64_p, c_i64_p]),
     'aslsd_point_sums': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, c_f64_p, ctypes.c_int, c_f64_p]),
+    'aslsd_exact_plan_rows': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int64, c_i64_p, c_i32_p, c_f64_p]),
     'aslsd_rng_choice': (ctypes.c_int, [ctypes.POINTER(Pcg64), ctypes.c_int64, ctypes.c_int64,
                                         ctypes.c_int, c_i64_p]),
     'aslsd_sample_single_ix': (ctypes.c_int, [ctypes.POINTER(Pcg64), ctypes.c_int64, c_i64_p, c_i64_p, c_i64_p,

@@ -932,6 +932,25 @@ extern "C" int aslsd_last_work_counts(aslsd_ctx* ctx, int64_t* counts, int n) {
   return ASLSD_OK;
 }
 
+// The rows of the last batch plan: what each one sums (include/aslsd_b200.h).  Host data only.
+extern "C" int aslsd_exact_plan_rows(aslsd_ctx* ctx, int64_t cap, int64_t* n_rows, int32_t* meta, double* params) {
+  if (!ctx || !n_rows || cap < 0 || (cap > 0 && (!meta || !params))) return ASLSD_ERR_ARG;
+  const BatchPlan* B = (const BatchPlan*)ctx->plan_cache;
+  if (!B) return aslsd_fail(ctx, ASLSD_ERR_ARG, "plan rows: no exact-sum call has been planned yet");
+  *n_rows = (int64_t)B->rows.size();
+  for (int64_t r = 0; r < std::min<int64_t>(cap, *n_rows); ++r) {
+    const ItemDev& it = B->rows[(size_t)r];
+    meta[5 * r + 0] = it.family;
+    meta[5 * r + 1] = it.tgt_dim;
+    meta[5 * r + 2] = it.src_dim;
+    meta[5 * r + 3] = it.same;
+    meta[5 * r + 4] = it.mask;
+    const double v[6] = {it.b1, it.d1, it.b2, it.d2, it.bo, it.dlo};
+    for (int q = 0; q < 6; ++q) params[6 * r + q] = v[q];
+  }
+  return ASLSD_OK;
+}
+
 extern "C" int aslsd_last_eval_counts(aslsd_ctx* ctx, int64_t* pair_evals, int64_t* single_evals) {
   int64_t c[8];
   int rc = aslsd_last_work_counts(ctx, c, 8);

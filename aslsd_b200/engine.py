@@ -372,6 +372,18 @@ class Engine:
                 capi.ptr_f64(rel) if with_alloc else None))
         return sums, np.asarray(out_offsets, dtype=np.int64), stat_mean, stat_std, rel
 
+    def plan_rows(self):
+        """(meta (n_rows, 5) int32: family, target type, source type, same-type flag, component mask;
+        params (n_rows, 6): beta_1, delta_1, beta_2, delta_2, beta_own, delta_own) of the rows of the
+        raw accumulator array of the last batch plan (aslsd_exact_plan_rows; host-side diagnostic)."""
+        n = ctypes.c_int64(0)
+        self._check(self._lib.aslsd_exact_plan_rows(self._ctx, 0, ctypes.byref(n), None, None))
+        meta = np.zeros((n.value, 5), dtype=np.int32)
+        params = np.zeros((n.value, 6), dtype=np.float64)
+        self._check(self._lib.aslsd_exact_plan_rows(self._ctx, n.value, ctypes.byref(n),
+                                                    meta.ctypes.data_as(capi.c_i32_p), capi.ptr_f64(params)))
+        return meta, params
+
     def update_allocation(self, strata_sizes, stat_std, default_alloc):
         sizes, std, dflt = (capi.as_f64(a) for a in (strata_sizes, stat_std, default_alloc))
         out = np.zeros(len(sizes), dtype=np.float64)

@@ -233,6 +233,19 @@ int aslsd_last_eval_counts(aslsd_ctx* ctx, int64_t* pair_evals, int64_t* single_
  *   [6] unique work items evaluated   [7] work items before de-duplication */
 int aslsd_last_work_counts(aslsd_ctx* ctx, int64_t* counts, int n);
 
+/* What every row of the raw accumulator array of the last batch plan sums (after a
+ * raw_device / exact_sums call): row r adds up, over its event pairs (pair families) or
+ * target events (single-index families), the components of one basis pair / one basis with the
+ * variables params[6 r ..] = (beta_1, delta_1, beta_2, delta_2, beta_own, delta_own);
+ * meta[5 r ..] = (family, target event type, source event type, same-type flag, component
+ * mask).  Family codes: 0 / 1 upsilon exp x exp / gauss x gauss, 2 / 3 phi exp / gauss,
+ * 4 / 5 psi exp / gauss, 6 / 7 upsilon at lag zero exp / gauss, 8-11 the mixed pairs.
+ * n_rows receives the number of rows; at most cap rows are written.  Host-side diagnostic:
+ * with it the planning (which parameters and event streams enter which row) and the assembly of
+ * the packed sums (aslsd_exact_assemble_batch) are checked on a GPU-less machine against the
+ * oracle, tests/test_plan_and_assembly_host.py. */
+int aslsd_exact_plan_rows(aslsd_ctx* ctx, int64_t cap, int64_t* n_rows, int32_t* meta, double* params);
+
 /* ---- sampled sums: replaces the bodies of MHPStratEstim.estimate_sum_* ------------
  * optimize/estimators/mhp_stratified_estimator.py:534-900, for every term of one
  * compute_objective call (:1333-1386) in a single launch.

@@ -1,0 +1,181 @@
+"""Driver of tests/test_plan_and_assembly_host.py (subprocess, sanitizer runtimes preloaded, library
+built against the do-nothing CUDA runtime).
+
+Planning and assembly are host code: which parameters and event streams enter which row of the
+raw accumulator array (csrc/plan.cu, exact.cu) and how the rows combine into the packed per-term
+sums (csrc/plan.h emit_term).  Here the rows of the plan are read back (aslsd_exact_plan_rows),
+their raw components are computed with numpy straight from the component definitions of
+csrc/basis_math.cuh - the part the device kernels do - and handed to aslsd_exact_assemble_batch;
+the packed sums must equal the oracle's (the literal restatement of the reference, pinned to its
+golden vectors).  That covers what depends on the number of event types without a GPU: models
+with one, two, three and five types."""
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, 'tests'))
+import numpy as np  # noqa: E402
+from scipy.special import ndtr  # noqa: E402
+
+from aslsd_b200 import capi  # noqa: E402
+
+capi.LIB_PATH = sys.argv[1]
+capi._lib = None
+import aslsd_b200  # noqa: E402
+from aslsd_b200.engine import unpack_terms  # noqa: E402
+from cases import CASES, case_x  # noqa: E402
+from oracle import exact as OE  # noqa: E402
+
+UPS_EXP, UPS_GAUSS, PHI_EXP, PHI_GAUSS, PSI_EXP, PSI_GAUSS, UPS0_EXP, UPS0_GAUSS = range(8)
+C_G, C_B1, C_D1, C_B2, C_D2, C_SW, C_SB, C_SD = range(8)
+N_COMP = 8
+
+
+def pairs(t_tgt, t_src, same):
+    """All (target, source) pairs with the source strictly earlier (by index inside one type)."""
+    if same:
+        m, n = np.tril_indices(len(t_tgt), k=-1)
+    else:
+        hi = np.searchsorted(t_src, t_tgt, side='left')
+        m = np.repeat(np.arange(len(t_tgt)), hi)
+        n = np.concatenate([np.arange(h) for h in hi]) if len(hi) else np.zeros(0, dtype=int)
+    return m, n
+
+
+def pdf(x, mean, std):
+    return np.exp(-0.5 * ((x - mean) / std) ** 2) / (std * np.sqrt(2. * np.pi))
+
+
+def ups_components(family, t, s, b1, d1, b2, d2, bo, dlo, mask):
+    """Raw components of one upsilon basis pair at (t = time to the end, s = lag): basis_math.cuh
+    eval_ups_exp / eval_ups_gauss (value component of the latter only)."""
+    out = np.zeros(N_COMP)
+    if family in (UPS_EXP, UPS0_EXP):
+        bsum = b1 + b2
+        pr = b1 * b2 / bsum
+        e, E = np.exp(-b2 * s), np.exp(-bsum * t)
+        out[C_G] = np.sum(e * (1. - E))
+        if mask & (1 << C_B1):
+            out[C_B1] = np.sum(e * ((b2 / bsum) ** 2 * (1. - E) + pr * t * E))
+        if mask & (1 << C_B2):
+            out[C_B2] = np.sum(e * ((b1 / bsum) ** 2 * (1. - E) + pr * ((t + s) * E - s)))
+        eo, E2 = np.exp(-bo * s), np.exp(-2. * bo * t)
+        if mask & (1 << C_SW):
+            out[C_SW] = np.sum(eo * (1. - E2))
+        if mask & (1 << C_SB):
+            out[C_SB] = np.sum(0.5 * eo * (1. - bo * s + E2 * (bo * (2. * t + s) - 1.)))
+        return out
+    sig = np.sqrt(b1 * b1 + b2 * b2)
+    dsv = (b2 * b2 * d1 + b1 * b1 * (d2 - s)) / (sig * sig)
+    b_s = b1 * b2 / sig
+    out[C_G] = np.sum(pdf(s, d2 - d1, sig) * (ndtr((t - dsv) / b_s) - ndtr(-dsv / b_s)))
+    if mask & (1 << C_SW):
+        # own-basis form behind d/d omega of a same-type term, the reference's limits without the
+        # s / 2 shift (basis_kernel_gaussian.py:507-508)
+        out[C_SW] = np.sum(2. * pdf(s, 0., np.sqrt(2.) * bo)
+                           * (ndtr(np.sqrt(2.) * (t - dlo) / bo) - ndtr(-np.sqrt(2.) * dlo / bo)))
+    assert not mask & ((1 << C_B1) | (1 << C_D1) | (1 << C_B2) | (1 << C_D2) | (1 << C_SB) | (1 << C_SD)), \
+        'beta / delta derivatives of Gaussian pairs are not restated here'
+    return out
+
+
+def row_components(meta, par, times, T_f, with_derivatives):
+    family, tgt, src, same, mask = (int(v) for v in meta)
+    b1, d1, b2, d2, bo, dlo = par
+    t_tgt, t_src = times[tgt], times[src]
+    out = np.zeros(N_COMP)
+    if family in (UPS_EXP, UPS_GAUSS):
+        m, n = pairs(t_tgt, t_src, same)
+        return ups_components(family, T_f - t_tgt[m], t_tgt[m] - t_src[n], b1, d1, b2, d2, bo, dlo, mask)
+    if family in (UPS0_EXP, UPS0_GAUSS):
+        return ups_components(family, T_f - t_tgt, 0., b1, d1, b2, d2, bo, dlo, mask)
+    if family in (PHI_EXP, PHI_GAUSS):
+        m, n = pairs(t_tgt, t_src, same)
+        s = t_tgt[m] - t_src[n]
+        if family == PHI_EXP:
+            e = np.exp(-b1 * s)
+            out[0] = np.sum(e)
+            out[1] = np.sum(e * (1. - b1 * s))
+        else:
+            out[0] = np.sum(pdf(s, d1, b1))
+        return out
+    if family in (PSI_EXP, PSI_GAUSS):
+        t = T_f - t_tgt
+        if family == PSI_EXP:
+            E = np.exp(-b1 * t)
+            out[0] = np.sum(1. - E)
+            out[1] = np.sum(t * E)
+        else:
+            out[0] = np.sum(ndtr((t - d1) / b1) - ndtr(-d1 / b1))
+        return out
+    raise AssertionError('family %d is not covered by this check' % family)
+
+
+def larger_model(name):
+    """Five event types (not among the golden cases): different parameters in every cell."""
+    from cases import exp_kernel, sbf_gauss_kernel, square
+    d = 5
+    model = square(d, exp_kernel if name == 'exp5d' else (lambda: sbf_gauss_kernel(2, beta=0.45, spacing=1.2)))
+    rng = np.random.default_rng(19)
+    xs = []
+    for k in range(d):
+        x = [rng.uniform(.3, .9)]
+        for i in range(d):
+            x += [rng.uniform(.02, .15), rng.uniform(.7, 2.5)] if name == 'exp5d' else \
+                [rng.uniform(.02, .1), rng.uniform(.02, .1)]
+        xs.append(np.array(x))
+    return model, xs
+
+
+def check(name, engine, with_derivatives):
+    model, xs_given = (CASES[name][0], None) if name in CASES else larger_model(name)
+    d = model['d']
+    rng = np.random.default_rng(7)
+    T_f = 25.
+    times = [np.sort(rng.uniform(0, T_f, size=40 + 11 * i)) for i in range(d)]
+    engine.set_events(times, T_f)
+    engine.set_model(model)
+    xs = case_x(name) if xs_given is None else xs_given
+    ks = list(range(d))
+    # plan the batch (the launches are no-ops under the stub runtime), read the rows back
+    scratch = np.zeros(engine.exact_raw_len_batch(d))
+    engine.exact_raw_device_batch(ks, xs, scratch.ctypes.data, True, with_derivatives)
+    meta, par = engine.plan_rows()
+    n_rows = len(meta)
+    assert n_rows * N_COMP == engine.exact_raw_used(), (n_rows, engine.exact_raw_used())
+    raw = np.zeros((n_rows, N_COMP))
+    for r in range(n_rows):
+        raw[r] = row_components(meta[r], par[r], times, T_f, with_derivatives)
+    packed = engine.exact_assemble_batch(ks, xs, raw.ravel(), True, with_derivatives)
+    worst = 0.
+    for k in ks:
+        sum_f, sum_diff_f = unpack_terms(engine.desc, k, packed[k])
+        o_f, o_df = OE.exact_sums_literal(model, k, xs[k], times, T_f)[:2]
+        for term in o_f:
+            assert abs(sum_f[term] - o_f[term]) <= 1e-11 * abs(o_f[term]), (name, k, term, sum_f[term], o_f[term])
+            worst = max(worst, abs(sum_f[term] - o_f[term]) / abs(o_f[term]))
+            if not with_derivatives:
+                continue
+            got, want = sum_diff_f[term], o_df[term]
+            for a, b in (zip(got[1:], want[1:]) if isinstance(want, list) else [(got, want)]):
+                np.testing.assert_allclose(a, b, rtol=1e-10, atol=1e-12 * np.abs(b).max(),
+                                           err_msg='%s k=%d %s' % (name, k, term))
+    print('%-8s d=%d rows=%3d derivatives=%s  worst value error %.1e' % (name, d, n_rows, with_derivatives, worst))
+
+
+def main():
+    engine = aslsd_b200.Engine(0)
+    for name in ('exp1d', 'exp2d', 'exp1d2b', 'exp3d', 'exp5d'):
+        check(name, engine, with_derivatives=True)
+    # sums of Gaussians with (beta, delta) fixed - the model family of configuration C5: every free
+    # parameter is an omega
+    for name in ('sbf1d3', 'sbf2d3', 'sbf1d10', 'sbf3d2', 'sbf5d2'):
+        check(name, engine, with_derivatives=True)
+    for name in ('gauss1d', 'gauss2d', 'gauss3d'):
+        check(name, engine, with_derivatives=False)
+    print('plan and assembly ok')
+
+
+if __name__ == '__main__':
+    main()
