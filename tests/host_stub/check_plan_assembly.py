@@ -49,7 +49,7 @@ def pdf(x, mean, std):
 
 def ups_components(family, t, s, b1, d1, b2, d2, bo, dlo, mask):
     """Raw components of one upsilon basis pair at (t = time to the end, s = lag): basis_math.cuh
-    eval_ups_exp / eval_ups_gauss (value component of the latter only)."""
+    eval_ups_exp / eval_ups_gauss."""
     out = np.zeros(N_COMP)
     if family in (UPS_EXP, UPS0_EXP):
         bsum = b1 + b2
@@ -66,17 +66,43 @@ def ups_components(family, t, s, b1, d1, b2, d2, bo, dlo, mask):
         if mask & (1 << C_SB):
             out[C_SB] = np.sum(0.5 * eo * (1. - bo * s + E2 * (bo * (2. * t + s) - 1.)))
         return out
-    sig = np.sqrt(b1 * b1 + b2 * b2)
-    dsv = (b2 * b2 * d1 + b1 * b1 * (d2 - s)) / (sig * sig)
+    sig2 = b1 * b1 + b2 * b2
+    sig = np.sqrt(sig2)
+    dsv = (b2 * b2 * d1 + b1 * b1 * (d2 - s)) / sig2
     b_s = b1 * b2 / sig
-    out[C_G] = np.sum(pdf(s, d2 - d1, sig) * (ndtr((t - dsv) / b_s) - ndtr(-dsv / b_s)))
-    if mask & (1 << C_SW):
-        # own-basis form behind d/d omega of a same-type term, the reference's limits without the
-        # s / 2 shift (basis_kernel_gaussian.py:507-508)
-        out[C_SW] = np.sum(2. * pdf(s, 0., np.sqrt(2.) * bo)
-                           * (ndtr(np.sqrt(2.) * (t - dlo) / bo) - ndtr(-np.sqrt(2.) * dlo / bo)))
-    assert not mask & ((1 << C_B1) | (1 << C_D1) | (1 << C_B2) | (1 << C_D2) | (1 << C_SB) | (1 << C_SD)), \
-        'beta / delta derivatives of Gaussian pairs are not restated here'
+    lo, hi = -dsv / b_s, (t - dsv) / b_s
+    P, J = pdf(s, d2 - d1, sig), ndtr(hi) - ndtr(lo)
+    p_lo, p_hi = pdf(lo, 0., 1.), pdf(hi, 0., 1.)
+    out[C_G] = np.sum(P * J)
+    quad = (s - d2 + d1) ** 2 / sig2 - 1.
+    # the beta / delta branches as the kernels evaluate them (the reference's closed forms,
+    # basis_kernel_gaussian.py:65-145, known-wrong branches included)
+    if mask & (1 << C_B1):
+        c = 2. * b1 * (d2 - d1 - s) / sig2
+        br = -(c - dsv / b1) * p_lo + (c + (t - dsv) / b1) * p_hi
+        out[C_B1] = np.sum(P * ((b1 / sig2) * quad * J - (b2 / (b1 * sig2)) * br))
+    if mask & (1 << C_B2):
+        c = 2. * b2 * (d1 - d2 + s) / sig2
+        br = -(c + dsv / b2) * p_lo + (c - (t - dsv) / b2) * p_hi
+        out[C_B2] = np.sum(P * ((b2 / sig2) * quad * J - (b1 / (b2 * sig2)) * br))
+    if mask & (1 << C_D1):
+        out[C_D1] = np.sum(P * (((d2 - s - d1) / sig2) * J - (b2 / (b1 * sig2)) * (p_hi - p_lo)))
+    if mask & (1 << C_D2):
+        out[C_D2] = np.sum(P * (((d1 + s - d2) / sig2) * J - (b1 / (b2 * sig2)) * (p_hi - p_lo)))
+    if mask & ((1 << C_SW) | (1 << C_SB) | (1 << C_SD)):
+        # own-basis forms behind the derivatives of a same-type term (:502-525); d / d omega with
+        # the reference's limits without the s / 2 shift (:507-508)
+        r2 = np.sqrt(2.)
+        P0 = pdf(s, 0., r2 * bo)
+        if mask & (1 << C_SW):
+            out[C_SW] = np.sum(2. * P0 * (ndtr(r2 * (t - dlo) / bo) - ndtr(-r2 * dlo / bo)))
+        a, e = -r2 * (dlo - 0.5 * s) / bo, r2 * (t - dlo + 0.5 * s) / bo
+        I_ae, pdf_a, pdf_e = ndtr(e) - ndtr(a), pdf(a, 0., 1.), pdf(e, 0., 1.)
+        if mask & (1 << C_SB):
+            br = -(r2 * (-dlo + 0.5 * s) / bo ** 2) * pdf_a + (r2 * (t - dlo + 0.5 * s) / bo ** 2) * pdf_e
+            out[C_SB] = np.sum(P0 * (((s * s - 2. * bo * bo) / (2. * bo ** 3)) * I_ae - br))
+        if mask & (1 << C_SD):
+            out[C_SD] = np.sum(-(r2 / bo) * P0 * (pdf_e - pdf_a))
     return out
 
 
@@ -98,7 +124,10 @@ def row_components(meta, par, times, T_f, with_derivatives):
             out[0] = np.sum(e)
             out[1] = np.sum(e * (1. - b1 * s))
         else:
-            out[0] = np.sum(pdf(s, d1, b1))
+            P, z = pdf(s, d1, b1), (s - d1) / b1
+            out[0] = np.sum(P)
+            out[1] = np.sum(P * (z * z - 1.))
+            out[2] = np.sum(P * (s - d1) / (b1 * b1))
         return out
     if family in (PSI_EXP, PSI_GAUSS):
         t = T_f - t_tgt
@@ -107,7 +136,10 @@ def row_components(meta, par, times, T_f, with_derivatives):
             out[0] = np.sum(1. - E)
             out[1] = np.sum(t * E)
         else:
-            out[0] = np.sum(ndtr((t - d1) / b1) - ndtr(-d1 / b1))
+            hi, lo = (t - d1) / b1, -d1 / b1
+            out[0] = np.sum(ndtr(hi) - ndtr(lo))
+            out[1] = np.sum((d1 - t) * pdf(hi, 0., 1.) - d1 * pdf(lo, 0., 1.))
+            out[2] = np.sum(pdf(hi, 0., 1.) - pdf(lo, 0., 1.))
         return out
     raise AssertionError('family %d is not covered by this check' % family)
 
@@ -172,8 +204,9 @@ def main():
     # parameter is an omega
     for name in ('sbf1d3', 'sbf2d3', 'sbf1d10', 'sbf3d2', 'sbf5d2'):
         check(name, engine, with_derivatives=True)
-    for name in ('gauss1d', 'gauss2d', 'gauss3d'):
-        check(name, engine, with_derivatives=False)
+    # free Gaussians and mixed fixed patterns: the beta / delta derivative components too
+    for name in ('gauss1d', 'gauss2d', 'gauss1d2b', 'gauss3d'):
+        check(name, engine, with_derivatives=True)
     print('plan and assembly ok')
 
 
