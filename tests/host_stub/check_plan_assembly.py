@@ -8,7 +8,7 @@ their raw components are computed with numpy straight from the component definit
 csrc/basis_math.cuh - the part the device kernels do - and handed to aslsd_exact_assemble_batch;
 the packed sums must equal the oracle's (the literal restatement of the reference, pinned to its
 golden vectors).  That covers what depends on the number of event types without a GPU: models
-with one, two, three and five types."""
+with one to five types."""
 import os
 import sys
 
@@ -27,7 +27,8 @@ from aslsd_b200.engine import unpack_terms  # noqa: E402
 from cases import CASES, case_x  # noqa: E402
 from oracle import exact as OE  # noqa: E402
 
-UPS_EXP, UPS_GAUSS, PHI_EXP, PHI_GAUSS, PSI_EXP, PSI_GAUSS, UPS0_EXP, UPS0_GAUSS = range(8)
+(UPS_EXP, UPS_GAUSS, PHI_EXP, PHI_GAUSS, PSI_EXP, PSI_GAUSS, UPS0_EXP, UPS0_GAUSS, UPS_EG, UPS_GE, UPS0_EG,
+ UPS0_GE) = range(12)
 C_G, C_B1, C_D1, C_B2, C_D2, C_SW, C_SB, C_SD = range(8)
 N_COMP = 8
 
@@ -66,6 +67,8 @@ def ups_components(family, t, s, b1, d1, b2, d2, bo, dlo, mask):
         if mask & (1 << C_SB):
             out[C_SB] = np.sum(0.5 * eo * (1. - bo * s + E2 * (bo * (2. * t + s) - 1.)))
         return out
+    if family in (UPS_EG, UPS0_EG, UPS_GE, UPS0_GE):
+        return mixed_components(family in (UPS_EG, UPS0_EG), t, s + 0. * t, b1, d1, b2, d2, mask)
     sig2 = b1 * b1 + b2 * b2
     sig = np.sqrt(sig2)
     dsv = (b2 * b2 * d1 + b1 * b1 * (d2 - s)) / sig2
@@ -106,15 +109,65 @@ def ups_components(family, t, s, b1, d1, b2, d2, bo, dlo, mask):
     return out
 
 
+def mixed_components(exp_first, t, s, b1, d1, b2, d2, mask):
+    """Exponential x Gaussian (exp_first) and Gaussian x exponential pairs: eval_ups_eg / eval_ups_ge.
+    Slot C_SW holds the value under the reference's overflow guard (np.where(arg > 10**2, 0., ...)),
+    which its derivatives apply sample by sample and its value does not."""
+    out = np.zeros(N_COMP)
+    std = lambda x: pdf(x, 0., 1.)
+    if exp_first:
+        be, bg, dg = b1, b2, d2
+        d_s = dg - s - be * bg * bg
+        arg = -be * (dg - s - 0.5 * be * bg * bg)
+        e = np.exp(arg)
+        lo, hi = -d_s / bg, (t - d_s) / bg
+        J = ndtr(hi) - ndtr(lo)
+        out[C_G] = np.sum(e * J)
+        keep = ~(arg > 100.)
+        p_lo, p_hi, be_e = std(lo), std(hi), be * e
+        if mask & (1 << C_SW):
+            out[C_SW] = np.sum((e * J)[keep])
+        if mask & (1 << C_B1):
+            out[C_B1] = np.sum((be_e * ((1. / be - dg + s + 0.5 * be * bg * bg) * J + bg * (p_hi - p_lo)))[keep])
+        if mask & (1 << C_B2):
+            pdf_term = -(be + (dg - s) / bg ** 2) * p_lo + (be + (dg - s - t) / bg ** 2) * p_hi
+            out[C_B2] = np.sum((be_e * (bg * be * be * J + pdf_term))[keep])
+        if mask & (1 << C_D2):
+            out[C_D2] = -np.sum((be_e * (be * J + (p_hi - p_lo) / bg))[keep])
+        return out
+    be, bg, dg = b2, b1, d1
+    d0 = dg - be * bg * bg
+    arg = -be * (dg + s - 0.5 * be * bg * bg)
+    e = np.exp(arg)
+    lo, hi = -d0 / bg, (t - d0) / bg
+    J = ndtr(hi) - ndtr(lo)
+    out[C_G] = np.sum(e * J)
+    if mask & (1 << C_SW):
+        out[C_SW] = np.sum((e * J)[~(arg > 100.)])
+    be_e = be * e
+    if mask & ((1 << C_B1) | (1 << C_D1)):
+        d1s = dg + s - be * bg * bg        # the reference shifts these limits by s (:176, :186)
+        lo1, hi1 = -d1s / bg, (t - d1s) / bg
+        J1, p_lo1, p_hi1 = ndtr(hi1) - ndtr(lo1), std(lo1), std(hi1)
+        if mask & (1 << C_B1):
+            pdf_term = -(be + dg / bg ** 2) * p_lo1 + (be - (t - dg) / bg ** 2) * p_hi1
+            out[C_B1] = np.sum(be_e * (bg * be * be * J1 + pdf_term))
+        if mask & (1 << C_D1):
+            out[C_D1] = np.sum(be_e * (-be * J1 - (p_hi1 - p_lo1) / bg))
+    if mask & (1 << C_B2):
+        out[C_B2] = np.sum(be_e * ((1. / be - dg - s + 0.5 * be * bg * bg) * J + bg * (std(hi) - std(lo))))
+    return out
+
+
 def row_components(meta, par, times, T_f, with_derivatives):
     family, tgt, src, same, mask = (int(v) for v in meta)
     b1, d1, b2, d2, bo, dlo = par
     t_tgt, t_src = times[tgt], times[src]
     out = np.zeros(N_COMP)
-    if family in (UPS_EXP, UPS_GAUSS):
+    if family in (UPS_EXP, UPS_GAUSS, UPS_EG, UPS_GE):
         m, n = pairs(t_tgt, t_src, same)
         return ups_components(family, T_f - t_tgt[m], t_tgt[m] - t_src[n], b1, d1, b2, d2, bo, dlo, mask)
-    if family in (UPS0_EXP, UPS0_GAUSS):
+    if family in (UPS0_EXP, UPS0_GAUSS, UPS0_EG, UPS0_GE):
         return ups_components(family, T_f - t_tgt, 0., b1, d1, b2, d2, bo, dlo, mask)
     if family in (PHI_EXP, PHI_GAUSS):
         m, n = pairs(t_tgt, t_src, same)
@@ -145,18 +198,20 @@ def row_components(meta, par, times, T_f, with_derivatives):
 
 
 def larger_model(name):
-    """Five event types (not among the golden cases): different parameters in every cell."""
+    """Models that are not among the golden cases: five event types (exponential, fixed-shape sums of
+    Gaussians) and three / four types with an exponential and a Gaussian basis in every kernel;
+    different parameters in every cell."""
     from cases import exp_kernel, sbf_gauss_kernel, square
-    d = 5
-    model = square(d, exp_kernel if name == 'exp5d' else (lambda: sbf_gauss_kernel(2, beta=0.45, spacing=1.2)))
+    d = int(name[3])        # 'exp5d', 'sbf5d2', 'mix3d': the digit after the family
+    make = {'exp': exp_kernel, 'sbf': lambda: sbf_gauss_kernel(2, beta=0.45, spacing=1.2),
+            'mix': lambda: [{'type': 'exp'}, {'type': 'gauss'}]}[name[:3]]
+    model = square(d, make)
     rng = np.random.default_rng(19)
-    xs = []
-    for k in range(d):
-        x = [rng.uniform(.3, .9)]
-        for i in range(d):
-            x += [rng.uniform(.02, .15), rng.uniform(.7, 2.5)] if name == 'exp5d' else \
-                [rng.uniform(.02, .1), rng.uniform(.02, .1)]
-        xs.append(np.array(x))
+    cell = {'exp': lambda: [rng.uniform(.02, .15), rng.uniform(.7, 2.5)],
+            'sbf': lambda: [rng.uniform(.02, .1), rng.uniform(.02, .1)],
+            'mix': lambda: [rng.uniform(.03, .12), rng.uniform(.8, 2.), rng.uniform(.03, .12), rng.uniform(.4, .8),
+                            rng.uniform(.5, 2.)]}[name[:3]]
+    xs = [np.array([rng.uniform(.3, .9)] + [v for _ in range(d) for v in cell()]) for _ in range(d)]
     return model, xs
 
 
@@ -206,6 +261,9 @@ def main():
         check(name, engine, with_derivatives=True)
     # free Gaussians and mixed fixed patterns: the beta / delta derivative components too
     for name in ('gauss1d', 'gauss2d', 'gauss1d2b', 'gauss3d'):
+        check(name, engine, with_derivatives=True)
+    # an exponential and a Gaussian basis in one kernel: the mixed pairs
+    for name in ('mix1d', 'mix2d', 'mix3d', 'mix4d'):
         check(name, engine, with_derivatives=True)
     print('plan and assembly ok')
 

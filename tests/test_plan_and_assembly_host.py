@@ -7,9 +7,9 @@ device kernels only traverse the event pairs of a row.  The driver
 (tests/host_stub/check_plan_assembly.py) plans a batch with the library built against the
 do-nothing CUDA runtime, reads the rows back (aslsd_exact_plan_rows), fills them with numpy from the
 component definitions, and lets the library assemble: values and derivatives must equal the
-literal oracle's for models with one, two, three and five event types (exponential kernels, free
-Gaussians, sums of Gaussians with fixed shapes - the family of configuration C5 - and mixed
-fixed / free patterns, every derivative included)."""
+literal oracle's for models with one to five event types (exponential kernels, free Gaussians,
+sums of Gaussians with fixed shapes - the family of configuration C5 -, mixed fixed / free patterns
+and kernels with an exponential and a Gaussian basis, every derivative included)."""
 import os
 import subprocess
 import sys
@@ -34,4 +34,4 @@ def test_rows_and_assembly_match_the_oracle():
     assert res.returncode == 0 and 'plan and assembly ok' in res.stdout, \
         (res.stdout[-3000:] + '\n' + res.stderr[-6000:])
     assert 'AddressSanitizer' not in res.stderr and 'runtime error:' not in res.stderr
-    assert res.stdout.count('derivatives=True') == 14 and res.stdout.count(' d=5 ') == 2
+    assert res.stdout.count('derivatives=True') == 18 and res.stdout.count(' d=5 ') == 2
