@@ -159,18 +159,35 @@ def mixed_components(exp_first, t, s, b1, d1, b2, d2, mask):
     return out
 
 
-def row_components(meta, par, times, T_f, with_derivatives):
+FAR = 1e7   # stands for t = infinity: every e^{-c t}, pdf(upper limit) and 1 - cdf(upper limit) is exactly 0
+
+
+def row_components(meta, par, times, T_f, with_derivatives, truncated=False):
+    """truncated: as the kernels traverse the row - only lags inside [s_lo, s_hi], and the limits
+    at infinity for targets whose time to T_f is at least t_int."""
     family, tgt, src, same, mask = (int(v) for v in meta)
-    b1, d1, b2, d2, bo, dlo = par
+    b1, d1, b2, d2, bo, dlo = par[:6]
+    s_lo, s_hi, t_int = par[6:9]
     t_tgt, t_src = times[tgt], times[src]
     out = np.zeros(N_COMP)
+
+    def to_end(t_m):
+        t = T_f - t_m
+        return np.where(t >= t_int, FAR, t) if truncated else t
+
+    def window(m, n):
+        if not truncated:
+            return m, n
+        s = t_tgt[m] - t_src[n]
+        keep = (s >= s_lo) & (s <= s_hi)
+        return m[keep], n[keep]
     if family in (UPS_EXP, UPS_GAUSS, UPS_EG, UPS_GE):
-        m, n = pairs(t_tgt, t_src, same)
-        return ups_components(family, T_f - t_tgt[m], t_tgt[m] - t_src[n], b1, d1, b2, d2, bo, dlo, mask)
+        m, n = window(*pairs(t_tgt, t_src, same))
+        return ups_components(family, to_end(t_tgt[m]), t_tgt[m] - t_src[n], b1, d1, b2, d2, bo, dlo, mask)
     if family in (UPS0_EXP, UPS0_GAUSS, UPS0_EG, UPS0_GE):
-        return ups_components(family, T_f - t_tgt, 0., b1, d1, b2, d2, bo, dlo, mask)
+        return ups_components(family, to_end(t_tgt), 0., b1, d1, b2, d2, bo, dlo, mask)
     if family in (PHI_EXP, PHI_GAUSS):
-        m, n = pairs(t_tgt, t_src, same)
+        m, n = window(*pairs(t_tgt, t_src, same))
         s = t_tgt[m] - t_src[n]
         if family == PHI_EXP:
             e = np.exp(-b1 * s)
@@ -183,7 +200,7 @@ def row_components(meta, par, times, T_f, with_derivatives):
             out[2] = np.sum(P * (s - d1) / (b1 * b1))
         return out
     if family in (PSI_EXP, PSI_GAUSS):
-        t = T_f - t_tgt
+        t = to_end(t_tgt)
         if family == PSI_EXP:
             E = np.exp(-b1 * t)
             out[0] = np.sum(1. - E)
@@ -251,8 +268,57 @@ def check(name, engine, with_derivatives):
     print('%-8s d=%d rows=%3d derivatives=%s  worst value error %.1e' % (name, d, n_rows, with_derivatives, worst))
 
 
+def check_truncation(engine):
+    """The truncation a plan prescribes (csrc/plan.cu: lag windows of 9 standard deviations / 42
+    decay lengths, limits at infinity beyond 10 standard deviations / 60 decay lengths of T_f)
+    does not change the packed sums: rows evaluated in full against rows evaluated the way the
+    kernels traverse them, both assembled by the library, for parameters drawn over a wide range."""
+    from cases import square
+    rng = np.random.default_rng(23)
+    T_f = 400.
+    worst = 0.
+    families = {'exp': lambda: [{'type': 'exp'}], 'gauss': lambda: [{'type': 'gauss'}],
+                'mix': lambda: [{'type': 'exp'}, {'type': 'gauss'}]}
+    for trial in range(24):
+        kind = ('exp', 'gauss', 'mix')[trial % 3]
+        d = 1 + trial % 2
+        model = square(d, families[kind])
+        times = [np.sort(rng.uniform(0, T_f, size=int(rng.integers(120, 220)))) for _ in range(d)]
+        cell = {'exp': lambda: [rng.uniform(.05, .3), rng.uniform(.15, 4.)],
+                'gauss': lambda: [rng.uniform(.05, .3), rng.uniform(.1, 2.5), rng.uniform(0., 6.)],
+                'mix': lambda: [rng.uniform(.05, .2), rng.uniform(.3, 3.), rng.uniform(.05, .2), rng.uniform(.2, 1.5),
+                                rng.uniform(.2, 4.)]}[kind]
+        xs = [np.array([rng.uniform(.3, .9)] + [v for _ in range(d) for v in cell()]) for _ in range(d)]
+        engine.set_events(times, T_f)
+        engine.set_model(model)
+        scratch = np.zeros(engine.exact_raw_len_batch(d))
+        engine.exact_raw_device_batch(list(range(d)), xs, scratch.ctypes.data, True, True)
+        meta, par = engine.plan_rows()
+        full, cut = np.zeros((len(meta), N_COMP)), np.zeros((len(meta), N_COMP))
+        for r in range(len(meta)):
+            with np.errstate(over='ignore', invalid='ignore'):
+                full[r] = row_components(meta[r], par[r], times, T_f, True)
+                cut[r] = row_components(meta[r], par[r], times, T_f, True, truncated=True)
+        if not np.all(np.isfinite(full)):
+            continue   # exp x gauss beyond the reference's own overflow (inf x 0): not a truncation matter
+        ks = list(range(d))
+        a = engine.exact_assemble_batch(ks, xs, full.ravel(), True, True)
+        b = engine.exact_assemble_batch(ks, xs, cut.ravel(), True, True)
+        for k in ks:
+            # per packed entry (term value or derivative): relative to itself, with a floor relative to
+            # the largest entry of the sub-problem - a term that lives entirely in a far Gaussian tail
+            # (its basis pair peaks at a negative lag) is cut relative to the peak, not to itself
+            floor = 1e-16 * np.abs(a[k]).max()
+            err = np.abs(b[k] - a[k]) / np.maximum(np.abs(a[k]), 1e-300)
+            bad = (err > 1e-12) & (np.abs(b[k] - a[k]) > floor)
+            assert not bad.any(), (kind, d, trial, k, np.flatnonzero(bad), a[k][bad], b[k][bad])
+            worst = max(worst, float(err[np.abs(a[k]) > 1e-6 * np.abs(a[k]).max()].max()))
+    print('truncation: 24 parameter draws, worst relative change of a packed sum %.1e' % worst)
+
+
 def main():
     engine = aslsd_b200.Engine(0)
+    check_truncation(engine)
     for name in ('exp1d', 'exp2d', 'exp1d2b', 'exp3d', 'exp5d'):
         check(name, engine, with_derivatives=True)
     # sums of Gaussians with (beta, delta) fixed - the model family of configuration C5: every free

@@ -9,7 +9,9 @@ do-nothing CUDA runtime, reads the rows back (aslsd_exact_plan_rows), fills them
 component definitions, and lets the library assemble: values and derivatives must equal the
 literal oracle's for models with one to five event types (exponential kernels, free Gaussians,
 sums of Gaussians with fixed shapes - the family of configuration C5 -, mixed fixed / free patterns
-and kernels with an exponential and a Gaussian basis, every derivative included)."""
+and kernels with an exponential and a Gaussian basis, every derivative included).  The same driver
+checks the truncation a plan prescribes (lag windows, limits at infinity near T_f) over random
+parameters: rows evaluated in full and the way the kernels traverse them give the same packed sums."""
 import os
 import subprocess
 import sys
@@ -34,4 +36,5 @@ def test_rows_and_assembly_match_the_oracle():
     assert res.returncode == 0 and 'plan and assembly ok' in res.stdout, \
         (res.stdout[-3000:] + '\n' + res.stderr[-6000:])
     assert 'AddressSanitizer' not in res.stderr and 'runtime error:' not in res.stderr
+    assert 'truncation: 24 parameter draws' in res.stdout
     assert res.stdout.count('derivatives=True') == 18 and res.stdout.count(' d=5 ') == 2
