@@ -945,8 +945,9 @@ extern "C" int aslsd_exact_plan_rows(aslsd_ctx* ctx, int64_t cap, int64_t* n_row
     meta[5 * r + 2] = it.src_dim;
     meta[5 * r + 3] = it.same;
     meta[5 * r + 4] = it.mask;
-    const double v[9] = {it.b1, it.d1, it.b2, it.d2, it.bo, it.dlo, it.s_lo, it.s_hi, it.t_int};
-    for (int q = 0; q < 9; ++q) params[9 * r + q] = v[q];
+    const double v[11] = {it.b1, it.d1, it.b2, it.d2, it.bo, it.dlo, it.s_lo, it.s_hi, it.t_int,
+                          (double)it.m_lo, (double)it.m_hi};
+    for (int q = 0; q < 11; ++q) params[11 * r + q] = v[q];
   }
   return ASLSD_OK;
 }

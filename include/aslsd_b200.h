@@ -236,9 +236,10 @@ int aslsd_last_work_counts(aslsd_ctx* ctx, int64_t* counts, int n);
 /* What every row of the raw accumulator array of the last batch plan sums (after a
  * raw_device / exact_sums call): row r adds up, over its event pairs (pair families) or
  * target events (single-index families), the components of one basis pair / one basis with the
- * variables params[9 r ..] = (beta_1, delta_1, beta_2, delta_2, beta_own, delta_own, and the
+ * variables params[11 r ..] = (beta_1, delta_1, beta_2, delta_2, beta_own, delta_own, the
  * truncation of the row: lags outside [s_lo, s_hi] are not visited, targets whose time to T_f is
- * at least t_int take the closed forms' limits at infinity);
+ * at least t_int take the closed forms' limits at infinity, and the block [m_lo, m_hi) of target
+ * events the call was asked for);
  * meta[5 r ..] = (family, target event type, source event type, same-type flag, component
  * mask).  Family codes: 0 / 1 upsilon exp x exp / gauss x gauss, 2 / 3 phi exp / gauss,
  * 4 / 5 psi exp / gauss, 6 / 7 upsilon at lag zero exp / gauss, 8-11 the mixed pairs.

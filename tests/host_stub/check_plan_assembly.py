@@ -168,24 +168,27 @@ def row_components(meta, par, times, T_f, with_derivatives, truncated=False):
     family, tgt, src, same, mask = (int(v) for v in meta)
     b1, d1, b2, d2, bo, dlo = par[:6]
     s_lo, s_hi, t_int = par[6:9]
+    m_lo, m_hi = int(par[9]), int(par[10])
     t_tgt, t_src = times[tgt], times[src]
     out = np.zeros(N_COMP)
+    block = np.zeros(len(t_tgt), dtype=bool)     # the targets the call was asked for
+    block[m_lo:m_hi] = True
 
     def to_end(t_m):
         t = T_f - t_m
         return np.where(t >= t_int, FAR, t) if truncated else t
 
     def window(m, n):
-        if not truncated:
-            return m, n
-        s = t_tgt[m] - t_src[n]
-        keep = (s >= s_lo) & (s <= s_hi)
+        keep = block[m]
+        if truncated:
+            s = t_tgt[m] - t_src[n]
+            keep &= (s >= s_lo) & (s <= s_hi)
         return m[keep], n[keep]
     if family in (UPS_EXP, UPS_GAUSS, UPS_EG, UPS_GE):
         m, n = window(*pairs(t_tgt, t_src, same))
         return ups_components(family, to_end(t_tgt[m]), t_tgt[m] - t_src[n], b1, d1, b2, d2, bo, dlo, mask)
     if family in (UPS0_EXP, UPS0_GAUSS, UPS0_EG, UPS0_GE):
-        return ups_components(family, to_end(t_tgt), 0., b1, d1, b2, d2, bo, dlo, mask)
+        return ups_components(family, to_end(t_tgt[block]), 0., b1, d1, b2, d2, bo, dlo, mask)
     if family in (PHI_EXP, PHI_GAUSS):
         m, n = window(*pairs(t_tgt, t_src, same))
         s = t_tgt[m] - t_src[n]
@@ -200,7 +203,7 @@ def row_components(meta, par, times, T_f, with_derivatives, truncated=False):
             out[2] = np.sum(P * (s - d1) / (b1 * b1))
         return out
     if family in (PSI_EXP, PSI_GAUSS):
-        t = to_end(t_tgt)
+        t = to_end(t_tgt[block])
         if family == PSI_EXP:
             E = np.exp(-b1 * t)
             out[0] = np.sum(1. - E)
@@ -316,8 +319,42 @@ def check_truncation(engine):
     print('truncation: 24 parameter draws, worst relative change of a packed sum %.1e' % worst)
 
 
+def check_shards(name, engine):
+    """Time-block shards (aslsd_b200/distributed.py): the plans of the blocks restrict every row to
+    the block's targets of the row's own target type (the type of the sub-problem for phi rows);
+    the packed sums of the blocks add up to those of the whole path."""
+    from aslsd_b200.distributed import time_block_ranges
+    model, xs = (CASES[name][0], case_x(name)) if name in CASES else larger_model(name)
+    d = model['d']
+    rng = np.random.default_rng(31)
+    T_f = 30.
+    times = [np.sort(rng.uniform(0, T_f, size=45 + 9 * i)) for i in range(d)]
+    engine.set_events(times, T_f)
+    engine.set_model(model)
+    ks = list(range(d))
+    scratch = np.zeros(engine.exact_raw_len_batch(d))
+
+    def packed(ranges):
+        engine.exact_raw_device_batch(ks, xs, scratch.ctypes.data, True, True, ranges=ranges)
+        meta, par = engine.plan_rows()
+        raw = np.array([row_components(meta[r], par[r], times, T_f, True) for r in range(len(meta))])
+        return engine.exact_assemble_batch(ks, xs, raw.ravel(), True, True)
+    whole = packed(None)
+    blocks = time_block_ranges(times, 3)
+    assert all(sum(b[i][1] - b[i][0] for b in blocks) == len(times[i]) for i in range(d))
+    acc = [np.zeros_like(w) for w in whole]
+    for block in blocks:
+        for a, part in zip(acc, packed(block)):
+            a += part
+    for k in ks:
+        np.testing.assert_allclose(acc[k], whole[k], rtol=1e-12, atol=1e-13 * np.abs(whole[k]).max())
+    print('%-8s d=%d: three time blocks add up to the whole path' % (name, d))
+
+
 def main():
     engine = aslsd_b200.Engine(0)
+    for name in ('exp2d', 'sbf3d2', 'mix3d', 'exp5d'):
+        check_shards(name, engine)
     check_truncation(engine)
     for name in ('exp1d', 'exp2d', 'exp1d2b', 'exp3d', 'exp5d'):
         check(name, engine, with_derivatives=True)

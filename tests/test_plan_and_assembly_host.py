@@ -11,7 +11,9 @@ literal oracle's for models with one to five event types (exponential kernels, f
 sums of Gaussians with fixed shapes - the family of configuration C5 -, mixed fixed / free patterns
 and kernels with an exponential and a Gaussian basis, every derivative included).  The same driver
 checks the truncation a plan prescribes (lag windows, limits at infinity near T_f) over random
-parameters: rows evaluated in full and the way the kernels traverse them give the same packed sums."""
+parameters: rows evaluated in full and the way the kernels traverse them give the same packed sums;
+and the plans of time-block shards (two to five event types): every row is restricted to the block's
+targets of its own target type, the packed sums of the blocks add up to those of the whole path."""
 import os
 import subprocess
 import sys
@@ -37,4 +39,5 @@ def test_rows_and_assembly_match_the_oracle():
         (res.stdout[-3000:] + '\n' + res.stderr[-6000:])
     assert 'AddressSanitizer' not in res.stderr and 'runtime error:' not in res.stderr
     assert 'truncation: 24 parameter draws' in res.stdout
+    assert res.stdout.count('three time blocks add up to the whole path') == 4
     assert res.stdout.count('derivatives=True') == 18 and res.stdout.count(' d=5 ') == 2
