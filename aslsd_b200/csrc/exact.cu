@@ -940,11 +940,19 @@ extern "C" int aslsd_exact_plan_rows(aslsd_ctx* ctx, int64_t cap, int64_t* n_row
   *n_rows = (int64_t)B->rows.size();
   for (int64_t r = 0; r < std::min<int64_t>(cap, *n_rows); ++r) {
     const ItemDev& it = B->rows[(size_t)r];
-    meta[5 * r + 0] = it.family;
-    meta[5 * r + 1] = it.tgt_dim;
-    meta[5 * r + 2] = it.src_dim;
-    meta[5 * r + 3] = it.same;
-    meta[5 * r + 4] = it.mask;
+    meta[7 * r + 0] = it.family;
+    meta[7 * r + 1] = it.tgt_dim;
+    meta[7 * r + 2] = it.src_dim;
+    meta[7 * r + 3] = it.same;
+    meta[7 * r + 4] = it.mask;
+    // weight vectors of the targets / sources (marked models): index into aslsd_set_weights, -1 = none
+    for (int side = 0; side < 2; ++side) {
+      const int64_t off = side == 0 ? it.wa_off : it.wb_off;
+      int32_t vec = -1;
+      for (size_t v = 0; off >= 0 && v < ctx->weight_off.size(); ++v)
+        if (ctx->weight_off[v] == off) vec = (int32_t)v;
+      meta[7 * r + 5 + side] = vec;
+    }
     const double v[11] = {it.b1, it.d1, it.b2, it.d2, it.bo, it.dlo, it.s_lo, it.s_hi, it.t_int,
                           (double)it.m_lo, (double)it.m_hi};
     for (int q = 0; q < 11; ++q) params[11 * r + q] = v[q];

@@ -373,13 +373,14 @@ class Engine:
         return sums, np.asarray(out_offsets, dtype=np.int64), stat_mean, stat_std, rel
 
     def plan_rows(self):
-        """(meta (n_rows, 5) int32: family, target type, source type, same-type flag, component mask;
+        """(meta (n_rows, 7) int32: family, target type, source type, same-type flag, component mask, weight
+        vectors of targets / sources;
         params (n_rows, 11): beta_1, delta_1, beta_2, delta_2, beta_own, delta_own, s_lo, s_hi, t_int, m_lo,
         m_hi) of the rows of the
         raw accumulator array of the last batch plan (aslsd_exact_plan_rows; host-side diagnostic)."""
         n = ctypes.c_int64(0)
         self._check(self._lib.aslsd_exact_plan_rows(self._ctx, 0, ctypes.byref(n), None, None))
-        meta = np.zeros((n.value, 5), dtype=np.int32)
+        meta = np.zeros((n.value, 7), dtype=np.int32)
         params = np.zeros((n.value, 11), dtype=np.float64)
         self._check(self._lib.aslsd_exact_plan_rows(self._ctx, n.value, ctypes.byref(n),
                                                     meta.ctypes.data_as(capi.c_i32_p), capi.ptr_f64(params)))

@@ -240,8 +240,9 @@ int aslsd_last_work_counts(aslsd_ctx* ctx, int64_t* counts, int n);
  * truncation of the row: lags outside [s_lo, s_hi] are not visited, targets whose time to T_f is
  * at least t_int take the closed forms' limits at infinity, and the block [m_lo, m_hi) of target
  * events the call was asked for);
- * meta[5 r ..] = (family, target event type, source event type, same-type flag, component
- * mask).  Family codes: 0 / 1 upsilon exp x exp / gauss x gauss, 2 / 3 phi exp / gauss,
+ * meta[7 r ..] = (family, target event type, source event type, same-type flag, component
+ * mask, weight vector of the targets, weight vector of the sources: indices into
+ * aslsd_set_weights, -1 = unweighted).  Family codes: 0 / 1 upsilon exp x exp / gauss x gauss, 2 / 3 phi exp / gauss,
  * 4 / 5 psi exp / gauss, 6 / 7 upsilon at lag zero exp / gauss, 8-11 the mixed pairs.
  * n_rows receives the number of rows; at most cap rows are written.  Host-side diagnostic:
  * with it the planning (which parameters and event streams enter which row) and the assembly of

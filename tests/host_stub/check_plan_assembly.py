@@ -162,10 +162,42 @@ def mixed_components(exp_first, t, s, b1, d1, b2, d2, mask):
 FAR = 1e7   # stands for t = infinity: every e^{-c t}, pdf(upper limit) and 1 - cdf(upper limit) is exactly 0
 
 
+def weighted_row(meta, par, times, T_f, weights):
+    """Rows of a marked model: every target event m and source event n carries a weight (the value
+    of an impact function at its mark, aslsd_set_weights); the row sums w_a[m] w_b[n] x component.
+    One pair at a time through the unweighted row evaluation (the paths of these cases are short)."""
+    family, tgt, src, same, mask, wa, wb = (int(v) for v in meta)
+    assert (wa < 0 or weights[wa][0] == tgt) and (wb < 0 or weights[wb][0] == src)
+    w_a = weights[wa][1] if wa >= 0 else np.ones(len(times[tgt]))
+    w_b = weights[wb][1] if wb >= 0 else np.ones(len(times[src]))
+    pair_family = family in (UPS_EXP, UPS_GAUSS, UPS_EG, UPS_GE, PHI_EXP, PHI_GAUSS)
+    out = np.zeros(N_COMP)
+    for m in range(len(times[tgt])):
+        # the row restricted to target m alone: its block is [m, m + 1)
+        one = np.array(par, dtype=float)
+        one[9], one[10] = m, m + 1
+        if not pair_family:
+            out += w_a[m] * row_components(meta[:5], one, times, T_f, True)
+            continue
+        # ... and, for pair rows, to one source at a time
+        n_hi = m if same else int(np.searchsorted(times[src], times[tgt][m], side='left'))
+        for n in range(n_hi):
+            sub = list(times)
+            if same:
+                # keep the target at index 1 behind its single source at index 0
+                sub[tgt] = np.array([times[src][n], times[tgt][m]])
+                one[9], one[10] = 1, 2
+            else:
+                sub[src] = times[src][n:n + 1]
+            out += w_a[m] * w_b[n] * row_components(meta[:5], one, sub, T_f, True)
+            one[9], one[10] = m, m + 1
+    return out
+
+
 def row_components(meta, par, times, T_f, with_derivatives, truncated=False):
     """truncated: as the kernels traverse the row - only lags inside [s_lo, s_hi], and the limits
     at infinity for targets whose time to T_f is at least t_int."""
-    family, tgt, src, same, mask = (int(v) for v in meta)
+    family, tgt, src, same, mask = (int(v) for v in meta[:5])
     b1, d1, b2, d2, bo, dlo = par[:6]
     s_lo, s_hi, t_int = par[6:9]
     m_lo, m_hi = int(par[9]), int(par[10])
@@ -351,8 +383,60 @@ def check_shards(name, engine):
     print('%-8s d=%d: three time blocks add up to the whole path' % (name, d))
 
 
+class InjectingEngine:
+    """The real engine (on the do-nothing runtime) whose weighted exact sums get their raw rows from
+    numpy: the fused entry point is called once to plan, the rows of the plan are evaluated here
+    with the weights that were set, and the call is repeated with the read-back of the raw array
+    substituted (aslsd_stub_next_d2h) - planning, role / mask handling and assembly are the
+    library's, as on the device."""
+
+    def __init__(self, stub_runtime):
+        import ctypes
+        self._real = aslsd_b200.Engine(0)
+        self._stub = ctypes.CDLL(stub_runtime)
+        self._stub.aslsd_stub_next_d2h.argtypes = [ctypes.c_void_p, ctypes.c_size_t]
+        self._stub.aslsd_stub_next_d2h.restype = None
+        self._weights = []
+        self._times = None
+
+    def __getattr__(self, name):
+        return getattr(self._real, name)
+
+    def bind(self, process_path, model):
+        self._times = [np.asarray(t, dtype=float) for t in process_path.list_times]
+        self._T_f = float(process_path.T_f)
+        return self._real.bind(process_path, model)
+
+    def set_weights(self, vectors):
+        self._weights = [(int(i), np.asarray(v, dtype=float)) for i, v in vectors]
+        return self._real.set_weights(vectors)
+
+    def exact_sums_weighted(self, k, x_k, roles, term_mask=None, compute_f_sum=True, compute_diff_f_sum=True,
+                            ranges=None):
+        args = (k, x_k, roles, term_mask, compute_f_sum, compute_diff_f_sum, ranges)
+        self._real.exact_sums_weighted(*args)            # plans; the kernels are no-ops
+        meta, par = self._real.plan_rows()
+        raw = np.zeros((max(len(meta), 1), N_COMP))
+        for r in range(len(meta)):
+            raw[r] = weighted_row(meta[r], par[r], self._times, self._T_f, self._weights)
+        self._stub.aslsd_stub_next_d2h(raw.ctypes.data, raw.nbytes)
+        return self._real.exact_sums_weighted(*args)     # same plan again, read-back substituted
+
+
+def check_marked(stub_runtime):
+    """Marked models end to end on the CPU: the B200 estimator (aslsd_b200/mtlh.py) over the library's
+    planning and assembly against the golden vectors of the reference's MTLHExactEstim, one to three
+    event types."""
+    import test_gpu_mtlh as TM
+    from cases import MTLH_CASES
+    for name in sorted(MTLH_CASES):
+        TM.test_mtlh_exact_matches_reference_golden(InjectingEngine(stub_runtime), name)
+        print('%-16s marked model: estimator state equals the golden vectors of the reference' % name)
+
+
 def main():
     engine = aslsd_b200.Engine(0)
+    check_marked(os.path.join(os.path.dirname(sys.argv[1]), 'libcudart_stub.so'))
     for name in ('exp2d', 'sbf3d2', 'mix3d', 'exp5d'):
         check_shards(name, engine)
     check_truncation(engine)

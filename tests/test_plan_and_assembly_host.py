@@ -13,7 +13,10 @@ and kernels with an exponential and a Gaussian basis, every derivative included)
 checks the truncation a plan prescribes (lag windows, limits at infinity near T_f) over random
 parameters: rows evaluated in full and the way the kernels traverse them give the same packed sums;
 and the plans of time-block shards (two to five event types): every row is restricted to the block's
-targets of its own target type, the packed sums of the blocks add up to those of the whole path."""
+targets of its own target type, the packed sums of the blocks add up to those of the whole path.
+Marked models run end to end: the B200 estimator over the library's planning, role / mask handling and
+assembly, the weighted rows evaluated with numpy and handed back through a substituted read-back,
+against the golden vectors of the reference's MTLHExactEstim (six cases, one to three event types)."""
 import os
 import subprocess
 import sys
@@ -39,5 +42,6 @@ def test_rows_and_assembly_match_the_oracle():
         (res.stdout[-3000:] + '\n' + res.stderr[-6000:])
     assert 'AddressSanitizer' not in res.stderr and 'runtime error:' not in res.stderr
     assert 'truncation: 24 parameter draws' in res.stdout
+    assert res.stdout.count('marked model: estimator state equals the golden vectors') == 6
     assert res.stdout.count('three time blocks add up to the whole path') == 4
     assert res.stdout.count('derivatives=True') == 18 and res.stdout.count(' d=5 ') == 2
