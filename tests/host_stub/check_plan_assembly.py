@@ -48,27 +48,28 @@ def pdf(x, mean, std):
     return np.exp(-0.5 * ((x - mean) / std) ** 2) / (std * np.sqrt(2. * np.pi))
 
 
-def ups_components(family, t, s, b1, d1, b2, d2, bo, dlo, mask):
+def ups_components(family, t, s, b1, d1, b2, d2, bo, dlo, mask, w=1.):
     """Raw components of one upsilon basis pair at (t = time to the end, s = lag): basis_math.cuh
     eval_ups_exp / eval_ups_gauss."""
     out = np.zeros(N_COMP)
+    S = lambda v: np.sum(w * v)          # w: weight of every pair (marked models), 1 otherwise
     if family in (UPS_EXP, UPS0_EXP):
         bsum = b1 + b2
         pr = b1 * b2 / bsum
         e, E = np.exp(-b2 * s), np.exp(-bsum * t)
-        out[C_G] = np.sum(e * (1. - E))
+        out[C_G] = S(e * (1. - E))
         if mask & (1 << C_B1):
-            out[C_B1] = np.sum(e * ((b2 / bsum) ** 2 * (1. - E) + pr * t * E))
+            out[C_B1] = S(e * ((b2 / bsum) ** 2 * (1. - E) + pr * t * E))
         if mask & (1 << C_B2):
-            out[C_B2] = np.sum(e * ((b1 / bsum) ** 2 * (1. - E) + pr * ((t + s) * E - s)))
+            out[C_B2] = S(e * ((b1 / bsum) ** 2 * (1. - E) + pr * ((t + s) * E - s)))
         eo, E2 = np.exp(-bo * s), np.exp(-2. * bo * t)
         if mask & (1 << C_SW):
-            out[C_SW] = np.sum(eo * (1. - E2))
+            out[C_SW] = S(eo * (1. - E2))
         if mask & (1 << C_SB):
-            out[C_SB] = np.sum(0.5 * eo * (1. - bo * s + E2 * (bo * (2. * t + s) - 1.)))
+            out[C_SB] = S(0.5 * eo * (1. - bo * s + E2 * (bo * (2. * t + s) - 1.)))
         return out
     if family in (UPS_EG, UPS0_EG, UPS_GE, UPS0_GE):
-        return mixed_components(family in (UPS_EG, UPS0_EG), t, s + 0. * t, b1, d1, b2, d2, mask)
+        return mixed_components(family in (UPS_EG, UPS0_EG), t, s + 0. * t, b1, d1, b2, d2, mask, w)
     sig2 = b1 * b1 + b2 * b2
     sig = np.sqrt(sig2)
     dsv = (b2 * b2 * d1 + b1 * b1 * (d2 - s)) / sig2
@@ -76,44 +77,45 @@ def ups_components(family, t, s, b1, d1, b2, d2, bo, dlo, mask):
     lo, hi = -dsv / b_s, (t - dsv) / b_s
     P, J = pdf(s, d2 - d1, sig), ndtr(hi) - ndtr(lo)
     p_lo, p_hi = pdf(lo, 0., 1.), pdf(hi, 0., 1.)
-    out[C_G] = np.sum(P * J)
+    out[C_G] = S(P * J)
     quad = (s - d2 + d1) ** 2 / sig2 - 1.
     # the beta / delta branches as the kernels evaluate them (the reference's closed forms,
     # basis_kernel_gaussian.py:65-145, known-wrong branches included)
     if mask & (1 << C_B1):
         c = 2. * b1 * (d2 - d1 - s) / sig2
         br = -(c - dsv / b1) * p_lo + (c + (t - dsv) / b1) * p_hi
-        out[C_B1] = np.sum(P * ((b1 / sig2) * quad * J - (b2 / (b1 * sig2)) * br))
+        out[C_B1] = S(P * ((b1 / sig2) * quad * J - (b2 / (b1 * sig2)) * br))
     if mask & (1 << C_B2):
         c = 2. * b2 * (d1 - d2 + s) / sig2
         br = -(c + dsv / b2) * p_lo + (c - (t - dsv) / b2) * p_hi
-        out[C_B2] = np.sum(P * ((b2 / sig2) * quad * J - (b1 / (b2 * sig2)) * br))
+        out[C_B2] = S(P * ((b2 / sig2) * quad * J - (b1 / (b2 * sig2)) * br))
     if mask & (1 << C_D1):
-        out[C_D1] = np.sum(P * (((d2 - s - d1) / sig2) * J - (b2 / (b1 * sig2)) * (p_hi - p_lo)))
+        out[C_D1] = S(P * (((d2 - s - d1) / sig2) * J - (b2 / (b1 * sig2)) * (p_hi - p_lo)))
     if mask & (1 << C_D2):
-        out[C_D2] = np.sum(P * (((d1 + s - d2) / sig2) * J - (b1 / (b2 * sig2)) * (p_hi - p_lo)))
+        out[C_D2] = S(P * (((d1 + s - d2) / sig2) * J - (b1 / (b2 * sig2)) * (p_hi - p_lo)))
     if mask & ((1 << C_SW) | (1 << C_SB) | (1 << C_SD)):
         # own-basis forms behind the derivatives of a same-type term (:502-525); d / d omega with
         # the reference's limits without the s / 2 shift (:507-508)
         r2 = np.sqrt(2.)
         P0 = pdf(s, 0., r2 * bo)
         if mask & (1 << C_SW):
-            out[C_SW] = np.sum(2. * P0 * (ndtr(r2 * (t - dlo) / bo) - ndtr(-r2 * dlo / bo)))
+            out[C_SW] = S(2. * P0 * (ndtr(r2 * (t - dlo) / bo) - ndtr(-r2 * dlo / bo)))
         a, e = -r2 * (dlo - 0.5 * s) / bo, r2 * (t - dlo + 0.5 * s) / bo
         I_ae, pdf_a, pdf_e = ndtr(e) - ndtr(a), pdf(a, 0., 1.), pdf(e, 0., 1.)
         if mask & (1 << C_SB):
             br = -(r2 * (-dlo + 0.5 * s) / bo ** 2) * pdf_a + (r2 * (t - dlo + 0.5 * s) / bo ** 2) * pdf_e
-            out[C_SB] = np.sum(P0 * (((s * s - 2. * bo * bo) / (2. * bo ** 3)) * I_ae - br))
+            out[C_SB] = S(P0 * (((s * s - 2. * bo * bo) / (2. * bo ** 3)) * I_ae - br))
         if mask & (1 << C_SD):
-            out[C_SD] = np.sum(-(r2 / bo) * P0 * (pdf_e - pdf_a))
+            out[C_SD] = S(-(r2 / bo) * P0 * (pdf_e - pdf_a))
     return out
 
 
-def mixed_components(exp_first, t, s, b1, d1, b2, d2, mask):
+def mixed_components(exp_first, t, s, b1, d1, b2, d2, mask, w=1.):
     """Exponential x Gaussian (exp_first) and Gaussian x exponential pairs: eval_ups_eg / eval_ups_ge.
     Slot C_SW holds the value under the reference's overflow guard (np.where(arg > 10**2, 0., ...)),
     which its derivatives apply sample by sample and its value does not."""
     out = np.zeros(N_COMP)
+    S = lambda v: np.sum(w * v)
     std = lambda x: pdf(x, 0., 1.)
     if exp_first:
         be, bg, dg = b1, b2, d2
@@ -122,18 +124,18 @@ def mixed_components(exp_first, t, s, b1, d1, b2, d2, mask):
         e = np.exp(arg)
         lo, hi = -d_s / bg, (t - d_s) / bg
         J = ndtr(hi) - ndtr(lo)
-        out[C_G] = np.sum(e * J)
+        out[C_G] = S(e * J)
         keep = ~(arg > 100.)
         p_lo, p_hi, be_e = std(lo), std(hi), be * e
         if mask & (1 << C_SW):
-            out[C_SW] = np.sum((e * J)[keep])
+            out[C_SW] = S(np.where(keep, e * J, 0.))
         if mask & (1 << C_B1):
-            out[C_B1] = np.sum((be_e * ((1. / be - dg + s + 0.5 * be * bg * bg) * J + bg * (p_hi - p_lo)))[keep])
+            out[C_B1] = S(np.where(keep, be_e * ((1. / be - dg + s + 0.5 * be * bg * bg) * J + bg * (p_hi - p_lo)), 0.))
         if mask & (1 << C_B2):
             pdf_term = -(be + (dg - s) / bg ** 2) * p_lo + (be + (dg - s - t) / bg ** 2) * p_hi
-            out[C_B2] = np.sum((be_e * (bg * be * be * J + pdf_term))[keep])
+            out[C_B2] = S(np.where(keep, be_e * (bg * be * be * J + pdf_term), 0.))
         if mask & (1 << C_D2):
-            out[C_D2] = -np.sum((be_e * (be * J + (p_hi - p_lo) / bg))[keep])
+            out[C_D2] = -S(np.where(keep, be_e * (be * J + (p_hi - p_lo) / bg), 0.))
         return out
     be, bg, dg = b2, b1, d1
     d0 = dg - be * bg * bg
@@ -141,9 +143,9 @@ def mixed_components(exp_first, t, s, b1, d1, b2, d2, mask):
     e = np.exp(arg)
     lo, hi = -d0 / bg, (t - d0) / bg
     J = ndtr(hi) - ndtr(lo)
-    out[C_G] = np.sum(e * J)
+    out[C_G] = S(e * J)
     if mask & (1 << C_SW):
-        out[C_SW] = np.sum((e * J)[~(arg > 100.)])
+        out[C_SW] = S(np.where(arg > 100., 0., e * J))
     be_e = be * e
     if mask & ((1 << C_B1) | (1 << C_D1)):
         d1s = dg + s - be * bg * bg        # the reference shifts these limits by s (:176, :186)
@@ -151,53 +153,37 @@ def mixed_components(exp_first, t, s, b1, d1, b2, d2, mask):
         J1, p_lo1, p_hi1 = ndtr(hi1) - ndtr(lo1), std(lo1), std(hi1)
         if mask & (1 << C_B1):
             pdf_term = -(be + dg / bg ** 2) * p_lo1 + (be - (t - dg) / bg ** 2) * p_hi1
-            out[C_B1] = np.sum(be_e * (bg * be * be * J1 + pdf_term))
+            out[C_B1] = S(be_e * (bg * be * be * J1 + pdf_term))
         if mask & (1 << C_D1):
-            out[C_D1] = np.sum(be_e * (-be * J1 - (p_hi1 - p_lo1) / bg))
+            out[C_D1] = S(be_e * (-be * J1 - (p_hi1 - p_lo1) / bg))
     if mask & (1 << C_B2):
-        out[C_B2] = np.sum(be_e * ((1. / be - dg - s + 0.5 * be * bg * bg) * J + bg * (std(hi) - std(lo))))
+        out[C_B2] = S(be_e * ((1. / be - dg - s + 0.5 * be * bg * bg) * J + bg * (std(hi) - std(lo))))
     return out
 
 
 FAR = 1e7   # stands for t = infinity: every e^{-c t}, pdf(upper limit) and 1 - cdf(upper limit) is exactly 0
 
 
-def weighted_row(meta, par, times, T_f, weights):
-    """Rows of a marked model: every target event m and source event n carries a weight (the value
-    of an impact function at its mark, aslsd_set_weights); the row sums w_a[m] w_b[n] x component.
-    One pair at a time through the unweighted row evaluation (the paths of these cases are short)."""
-    family, tgt, src, same, mask, wa, wb = (int(v) for v in meta)
-    assert (wa < 0 or weights[wa][0] == tgt) and (wb < 0 or weights[wb][0] == src)
-    w_a = weights[wa][1] if wa >= 0 else np.ones(len(times[tgt]))
-    w_b = weights[wb][1] if wb >= 0 else np.ones(len(times[src]))
-    pair_family = family in (UPS_EXP, UPS_GAUSS, UPS_EG, UPS_GE, PHI_EXP, PHI_GAUSS)
-    out = np.zeros(N_COMP)
-    for m in range(len(times[tgt])):
-        # the row restricted to target m alone: its block is [m, m + 1)
-        one = np.array(par, dtype=float)
-        one[9], one[10] = m, m + 1
-        if not pair_family:
-            out += w_a[m] * row_components(meta[:5], one, times, T_f, True)
-            continue
-        # ... and, for pair rows, to one source at a time
-        n_hi = m if same else int(np.searchsorted(times[src], times[tgt][m], side='left'))
-        for n in range(n_hi):
-            sub = list(times)
-            if same:
-                # keep the target at index 1 behind its single source at index 0
-                sub[tgt] = np.array([times[src][n], times[tgt][m]])
-                one[9], one[10] = 1, 2
-            else:
-                sub[src] = times[src][n:n + 1]
-            out += w_a[m] * w_b[n] * row_components(meta[:5], one, sub, T_f, True)
-            one[9], one[10] = m, m + 1
-    return out
-
-
-def row_components(meta, par, times, T_f, with_derivatives, truncated=False):
+def row_components(meta, par, times, T_f, with_derivatives, truncated=False, weights=None):
     """truncated: as the kernels traverse the row - only lags inside [s_lo, s_hi], and the limits
-    at infinity for targets whose time to T_f is at least t_int."""
+    at infinity for targets whose time to T_f is at least t_int.  weights (marked models): the
+    vectors of aslsd_set_weights; the row sums w_a[m] w_b[n] x component with the vectors named in
+    meta[5:7]."""
     family, tgt, src, same, mask = (int(v) for v in meta[:5])
+    w_a = w_b = None
+    if weights is not None:
+        wa, wb = int(meta[5]), int(meta[6])
+        assert (wa < 0 or weights[wa][0] == tgt) and (wb < 0 or weights[wb][0] == src)
+        w_a = weights[wa][1] if wa >= 0 else None
+        w_b = weights[wb][1] if wb >= 0 else None
+
+    def pair_w(m, n=None):
+        w = 1.
+        if w_a is not None:
+            w = w * w_a[m]
+        if w_b is not None and n is not None:
+            w = w * w_b[n]
+        return w
     b1, d1, b2, d2, bo, dlo = par[:6]
     s_lo, s_hi, t_int = par[6:9]
     m_lo, m_hi = int(par[9]), int(par[10])
@@ -218,33 +204,37 @@ def row_components(meta, par, times, T_f, with_derivatives, truncated=False):
         return m[keep], n[keep]
     if family in (UPS_EXP, UPS_GAUSS, UPS_EG, UPS_GE):
         m, n = window(*pairs(t_tgt, t_src, same))
-        return ups_components(family, to_end(t_tgt[m]), t_tgt[m] - t_src[n], b1, d1, b2, d2, bo, dlo, mask)
+        return ups_components(family, to_end(t_tgt[m]), t_tgt[m] - t_src[n], b1, d1, b2, d2, bo, dlo, mask,
+                              pair_w(m, n))
     if family in (UPS0_EXP, UPS0_GAUSS, UPS0_EG, UPS0_GE):
-        return ups_components(family, to_end(t_tgt[block]), 0., b1, d1, b2, d2, bo, dlo, mask)
+        return ups_components(family, to_end(t_tgt[block]), 0., b1, d1, b2, d2, bo, dlo, mask,
+                              pair_w(np.flatnonzero(block)))
     if family in (PHI_EXP, PHI_GAUSS):
         m, n = window(*pairs(t_tgt, t_src, same))
         s = t_tgt[m] - t_src[n]
+        w = pair_w(m, n)
         if family == PHI_EXP:
             e = np.exp(-b1 * s)
-            out[0] = np.sum(e)
-            out[1] = np.sum(e * (1. - b1 * s))
+            out[0] = np.sum(w * e)
+            out[1] = np.sum(w * e * (1. - b1 * s))
         else:
             P, z = pdf(s, d1, b1), (s - d1) / b1
-            out[0] = np.sum(P)
-            out[1] = np.sum(P * (z * z - 1.))
-            out[2] = np.sum(P * (s - d1) / (b1 * b1))
+            out[0] = np.sum(w * P)
+            out[1] = np.sum(w * P * (z * z - 1.))
+            out[2] = np.sum(w * P * (s - d1) / (b1 * b1))
         return out
     if family in (PSI_EXP, PSI_GAUSS):
         t = to_end(t_tgt[block])
+        w = pair_w(np.flatnonzero(block))
         if family == PSI_EXP:
             E = np.exp(-b1 * t)
-            out[0] = np.sum(1. - E)
-            out[1] = np.sum(t * E)
+            out[0] = np.sum(w * (1. - E))
+            out[1] = np.sum(w * t * E)
         else:
             hi, lo = (t - d1) / b1, -d1 / b1
-            out[0] = np.sum(ndtr(hi) - ndtr(lo))
-            out[1] = np.sum((d1 - t) * pdf(hi, 0., 1.) - d1 * pdf(lo, 0., 1.))
-            out[2] = np.sum(pdf(hi, 0., 1.) - pdf(lo, 0., 1.))
+            out[0] = np.sum(w * (ndtr(hi) - ndtr(lo)))
+            out[1] = np.sum(w * ((d1 - t) * pdf(hi, 0., 1.) - d1 * pdf(lo, 0., 1.)))
+            out[2] = np.sum(w * (pdf(hi, 0., 1.) - pdf(lo, 0., 1.)))
         return out
     raise AssertionError('family %d is not covered by this check' % family)
 
@@ -418,7 +408,7 @@ class InjectingEngine:
         meta, par = self._real.plan_rows()
         raw = np.zeros((max(len(meta), 1), N_COMP))
         for r in range(len(meta)):
-            raw[r] = weighted_row(meta[r], par[r], self._times, self._T_f, self._weights)
+            raw[r] = row_components(meta[r], par[r], self._times, self._T_f, True, weights=self._weights)
         self._stub.aslsd_stub_next_d2h(raw.ctypes.data, raw.nbytes)
         return self._real.exact_sums_weighted(*args)     # same plan again, read-back substituted
 
