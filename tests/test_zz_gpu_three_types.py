@@ -131,6 +131,26 @@ def test_estimators_on_three_types(engine, name):
             assert np.all(np.isfinite(dev.lse_k_grad_estimate(x, rng=rng_a, grad_alloc=False)))
 
 
+@pytest.mark.parametrize('name', ['exp3d', 'sbf3d2'])
+def test_intensity_and_residuals_on_three_types(engine, name):
+    """aslsd_point_sums with three event types against the oracle (mhp.py:669-690,
+    goodness_of_fit.py:134-236)."""
+    import aslsd_b200
+    from aslsd_b200 import residuals as R
+    from oracle import residuals as OR
+    model, mu, kp, _ = CASES[name]
+    rng = np.random.default_rng(12)
+    T_f = 600.
+    times = [np.sort(rng.uniform(0, T_f, size=n)) for n in (700, 520, 610)]
+    path = aslsd_b200.ProcessPath(times, T_f, engine=engine)
+    intensity = R.get_intensity_at_jumps(model, path, mu, kp, engine=engine)
+    want = OR.intensity_at_jumps(model, mu, kp, times)
+    for i in range(3):
+        np.testing.assert_allclose(intensity[i], want[i], rtol=RTOL, atol=1e-13)
+        got = R.get_residuals_k(model, path, i, mu, kp, engine=engine)
+        np.testing.assert_allclose(got, OR.residuals_k(model, i, mu, kp, times), rtol=1e-9, atol=1e-9)
+
+
 def test_marked_model_matches_reference_golden(engine):
     """mtlh_exp3d: golden vector of the reference's MTLHExactEstim with three event types."""
     import test_gpu_mtlh as TM
@@ -142,4 +162,5 @@ if __name__ == '__main__':
     from oracle_engine import OracleEngine
     for n in ['exp3d', 'sbf3d2']:
         test_estimators_on_three_types(OracleEngine(), n)
+        test_intensity_and_residuals_on_three_types(OracleEngine(), n)
     print('dry run ok')
