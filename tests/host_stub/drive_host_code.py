@@ -177,6 +177,11 @@ def main():
         else:
             raise AssertionError('invalid events were accepted')
     other.close()
+    # the error-path tests of the device suite are host-side argument checks: they run here as they are
+    import test_gpu_exact
+    import test_gpu_stratified
+    test_gpu_exact.test_errors(engine)
+    test_gpu_stratified.test_sampled_sums_reject_bad_indices(engine)
     engine.close()
     print('host code ok')
 
