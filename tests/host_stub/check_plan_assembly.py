@@ -258,11 +258,17 @@ def larger_model(name):
 
 
 def check(name, engine, with_derivatives):
-    model, xs_given = (CASES[name][0], None) if name in CASES else larger_model(name)
+    if name == 'C5':
+        # the benchmark's model itself (ten event types, ten fixed-shape Gaussians per kernel) at its
+        # own evaluation point, on a short uniform path
+        from aslsd_b200 import simulate
+        model, _, _, xs_given = simulate.config_c5(d=10, n_basis=10, T_f=5., seed=1234)
+    else:
+        model, xs_given = (CASES[name][0], None) if name in CASES else larger_model(name)
     d = model['d']
     rng = np.random.default_rng(7)
     T_f = 25.
-    times = [np.sort(rng.uniform(0, T_f, size=40 + 11 * i)) for i in range(d)]
+    times = [np.sort(rng.uniform(0, T_f, size=(40 + 11 * i) if d <= 5 else 14 + i)) for i in range(d)]
     engine.set_events(times, T_f)
     engine.set_model(model)
     xs = case_x(name) if xs_given is None else xs_given
@@ -280,7 +286,10 @@ def check(name, engine, with_derivatives):
     worst = 0.
     for k in ks:
         sum_f, sum_diff_f = unpack_terms(engine.desc, k, packed[k])
-        o_f, o_df = OE.exact_sums_literal(model, k, xs[k], times, T_f)[:2]
+        # (ten event types: the vectorised windowed form of the oracle, equal to the literal one to
+        # 1e-13 on every golden case, instead of its per-target Python loops)
+        oracle = OE.exact_sums_windowed if d > 5 else OE.exact_sums_literal
+        o_f, o_df = oracle(model, k, xs[k], times, T_f)[:2]
         for term in o_f:
             assert abs(sum_f[term] - o_f[term]) <= 1e-11 * abs(o_f[term]), (name, k, term, sum_f[term], o_f[term])
             worst = max(worst, abs(sum_f[term] - o_f[term]) / abs(o_f[term]))
@@ -290,7 +299,7 @@ def check(name, engine, with_derivatives):
             for a, b in (zip(got[1:], want[1:]) if isinstance(want, list) else [(got, want)]):
                 np.testing.assert_allclose(a, b, rtol=1e-10, atol=1e-12 * np.abs(b).max(),
                                            err_msg='%s k=%d %s' % (name, k, term))
-    print('%-8s d=%d rows=%3d derivatives=%s  worst value error %.1e' % (name, d, n_rows, with_derivatives, worst))
+    print('%-8s d=%d rows=%5d derivatives=%s  worst value error %.1e' % (name, d, n_rows, with_derivatives, worst))
 
 
 def check_truncation(engine):
@@ -434,7 +443,7 @@ def main():
         check(name, engine, with_derivatives=True)
     # sums of Gaussians with (beta, delta) fixed - the model family of configuration C5: every free
     # parameter is an omega
-    for name in ('sbf1d3', 'sbf2d3', 'sbf1d10', 'sbf3d2', 'sbf5d2'):
+    for name in ('sbf1d3', 'sbf2d3', 'sbf1d10', 'sbf3d2', 'sbf5d2', 'C5'):
         check(name, engine, with_derivatives=True)
     # free Gaussians and mixed fixed patterns: the beta / delta derivative components too
     for name in ('gauss1d', 'gauss2d', 'gauss1d2b', 'gauss3d'):

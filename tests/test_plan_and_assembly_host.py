@@ -7,7 +7,8 @@ device kernels only traverse the event pairs of a row.  The driver
 (tests/host_stub/check_plan_assembly.py) plans a batch with the library built against the
 do-nothing CUDA runtime, reads the rows back (aslsd_exact_plan_rows), fills them with numpy from the
 component definitions, and lets the library assemble: values and derivatives must equal the
-literal oracle's for models with one to five event types (exponential kernels, free Gaussians,
+literal oracle's for models with one to five event types and for the benchmark's own ten-type model
+(exponential kernels, free Gaussians,
 sums of Gaussians with fixed shapes - the family of configuration C5 -, mixed fixed / free patterns
 and kernels with an exponential and a Gaussian basis, every derivative included).  The same driver
 checks the truncation a plan prescribes (lag windows, limits at infinity near T_f) over random
@@ -44,4 +45,5 @@ def test_rows_and_assembly_match_the_oracle():
     assert 'truncation: 24 parameter draws' in res.stdout
     assert res.stdout.count('marked model: estimator state equals the golden vectors') == 6
     assert res.stdout.count('three time blocks add up to the whole path') == 4
-    assert res.stdout.count('derivatives=True') == 18 and res.stdout.count(' d=5 ') == 2
+    assert res.stdout.count('derivatives=True') == 19 and res.stdout.count(' d=5 ') == 2
+    assert 'C5       d=10 rows=11440' in res.stdout      # the benchmark's own model: the row count of bench.py
