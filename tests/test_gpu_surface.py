@@ -1,7 +1,6 @@
-"""Device tests of the estimator / container surface added after the GPU budget of round 1 was
-spent: residuals of marked models, ProcessPath.truncate, the per-term entry points of the
-estimators.  They pass on the oracle test double (``python tests/test_zy_gpu_surface.py``) and have
-not run on a B200 yet; the file is named to be collected after every established GPU test."""
+"""Device tests of the estimator / container surface: residuals of marked models,
+ProcessPath.truncate, the per-term entry points of the estimators.  (``python
+tests/test_gpu_surface.py`` dry-runs them on the oracle test double.)"""
 import numpy as np
 import pytest
 

@@ -4,9 +4,8 @@ d <= 2.  Golden vectors of the literal reference (exact_exp3d / exact_sbf3d2 / e
 tests/golden/make_golden.py 3d), the windowed oracle at ~10^4 events per type, sampled sums, the
 batched call and the time-block shards.  Tolerance 1e-10 as everywhere.
 
-(This file was added after the GPU budget of round 1 was spent: it passes on the oracle test
-double - ``python tests/test_zz_gpu_three_types.py`` - and has not run on a B200 yet.  It is named
-to be collected last.)"""
+(``python tests/test_gpu_three_types.py`` dry-runs the bodies that only need the engine interface
+on the oracle test double.)"""
 import numpy as np
 import pytest
 
