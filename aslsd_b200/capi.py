@@ -18,6 +18,7 @@ ASLSD_GRAD_ALLOC = 4
 OPT_LAG_QUADRATURE = 1
 OPT_WEIGHT_CACHE = 2
 OPT_ASYNC_EVENTS = 3
+OPT_DEVICE_ASSEMBLY = 4
 
 BASIS_EXPONENTIAL = 0
 BASIS_GAUSSIAN = 1
@@ -99,6 +100,14 @@ SYMBOLS = {
     'aslsd_exact_assemble_batch': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, c_i32_p,
                                                   ctypes.POINTER(c_f64_p), ctypes.c_int, c_f64_p,
                                                   ctypes.POINTER(c_f64_p)]),
+    'aslsd_exact_packed_len_batch': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, c_i32_p, c_i64_p]),
+    'aslsd_exact_packed_device_batch': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, c_i32_p,
+                                                       ctypes.POINTER(c_f64_p), ctypes.c_int, c_i64_p,
+                                                       c_i64_p, ctypes.c_void_p]),
+    'aslsd_exact_assemble_map_batch': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, c_i32_p,
+                                                      ctypes.POINTER(c_f64_p), ctypes.c_int, c_f64_p,
+                                                      ctypes.POINTER(c_f64_p)]),
+    'aslsd_synchronize': (ctypes.c_int, [ctypes.c_void_p]),
     'aslsd_sampled_n_out': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int,
                                            ctypes.c_int, ctypes.c_int, c_i32_p]),
     'aslsd_sampled_sums': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, c_f64_p, ctypes.c_int,

@@ -162,12 +162,27 @@ struct aslsd_ctx {
   bool use_quadrature = true;
   bool cache_weights = true;        // reuse the node weights while plan and events stay the same
   bool last_weights_reused = false;
+  // geometry of the streams whose node weights are in d_q_weights (they depend on the events and
+  // the bin grids only: plans of other sub-problems with the same streams reuse them)
+  std::vector<unsigned char> w_streams;    // QStreamDev records
+  int64_t w_events_epoch = -1;
   bool lq_tables_set = false;
   size_t q_smem_set = 0;
   // last batch plan (exact.cu): reused while the model, the events, the flags, the
   // target block and the non-omega parameters stay the same (plans hold no results)
   void* plan_cache = nullptr;
   void (*plan_cache_free)(void*) = nullptr;
+  // device assembly of the packed sums (exact.cu): CSR map of the cached plan, omega tables, result
+  void* d_asm = nullptr; size_t asm_cap = 0;
+  int64_t* d_asm_ptr = nullptr; size_t asm_ptr_cap = 0;
+  double* d_wtab = nullptr; size_t wtab_cap = 0;
+  double* h_wtab = nullptr; size_t h_wtab_cap = 0;     // page-locked, two halves used in turn
+  int wtab_flip = 0;
+  bool wtab_in_flight[2] = {false, false};
+  cudaEvent_t ev_wtab[2] = {nullptr, nullptr};
+  const void* asm_owner = nullptr;                     // the plan whose map is in d_asm
+  double* d_packed = nullptr; size_t packed_cap = 0;
+  bool device_assembly = true;                         // ASLSD_OPT_DEVICE_ASSEMBLY
   int64_t model_epoch = 0;    // bumped by set_model / set_option
   int64_t events_epoch = 0;   // bumped by set_events
   int64_t last_work[8] = {0};   // see aslsd_last_work_counts

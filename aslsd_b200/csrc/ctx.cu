@@ -54,6 +54,8 @@ extern "C" int aslsd_create(aslsd_ctx** out, int device) {
       cudaEventCreate(&ctx->ev_q0) != cudaSuccess || cudaEventCreate(&ctx->ev_q1) != cudaSuccess ||
       cudaEventCreateWithFlags(&ctx->ev_flag, cudaEventDisableTiming) != cudaSuccess ||
       cudaEventCreateWithFlags(&ctx->ev_tables, cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&ctx->ev_wtab[0], cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&ctx->ev_wtab[1], cudaEventDisableTiming) != cudaSuccess ||
       cudaMalloc((void**)&ctx->d_flag, sizeof(int)) != cudaSuccess ||
       cudaMallocHost((void**)&ctx->h_flag, sizeof(int)) != cudaSuccess ||
       cudaMemset(ctx->d_flag, 0, sizeof(int)) != cudaSuccess) {
@@ -88,6 +90,13 @@ extern "C" int aslsd_destroy(aslsd_ctx* ctx) {
   if (ctx->h_flag) cudaFreeHost(ctx->h_flag);
   if (ctx->h_tables) cudaFreeHost(ctx->h_tables);
   cudaEventDestroy(ctx->ev_tables);
+  cudaFree(ctx->d_asm);
+  cudaFree(ctx->d_asm_ptr);
+  cudaFree(ctx->d_wtab);
+  cudaFree(ctx->d_packed);
+  if (ctx->h_wtab) cudaFreeHost(ctx->h_wtab);
+  cudaEventDestroy(ctx->ev_wtab[0]);
+  cudaEventDestroy(ctx->ev_wtab[1]);
   cudaFree(ctx->d_flag);
   cudaEventDestroy(ctx->ev_flag);
   cudaEventDestroy(ctx->ev0);
@@ -112,6 +121,13 @@ extern "C" int aslsd_set_stream(aslsd_ctx* ctx, void* cuda_stream) {
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
   }
   ctx->stream = next;
+  return ASLSD_OK;
+}
+
+extern "C" int aslsd_synchronize(aslsd_ctx* ctx) {
+  if (!ctx) return ASLSD_ERR_ARG;
+  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
   return ASLSD_OK;
 }
 

@@ -62,6 +62,19 @@ struct BatchPlan {
   std::vector<ItemDev> scratch_q[ITEM_N_FAMILIES], scratch_f[ITEM_N_FAMILIES];
   int q_jmax = 0;
   size_t q_smem = 0;
+  // device assembly (raw rows -> packed sums): the linear map in CSR form, built once per row plan
+  std::vector<int64_t> out_off;                 // per sub-problem: offset in the concatenated packed sums
+  int64_t out_total = 0;
+  int w_stride = 0;                             // omega table entries per sub-problem
+  bool asm_built = false, asm_resident = false;
+  int64_t asm_entries = 0;
+  int uses = 0;                                 // calls served by this row plan
+};
+
+// One term of the assembly map: out += w[o] * ((w[a] * w[b] * g) * raw[raw_ix])
+struct AsmEntry {
+  int32_t raw_ix, a, b, o;
+  double g;
 };
 
 static ItemDev canonical(const ItemDev& it) {
@@ -418,6 +431,24 @@ static int get_batch(aslsd_ctx* ctx, int n_k, const int* ks, const double* const
   return ASLSD_OK;
 }
 
+// Do the node weights in d_q_weights (left by another plan) serve this plan?  They are a function
+// of the event streams, the target block and the bin grid of every stream: same events, same
+// streams in the same order with the same geometry, no per-event weights.
+static bool weights_match(const aslsd_ctx* ctx, const BatchPlan& B) {
+  if (ctx->w_events_epoch != ctx->events_epoch) return false;
+  if (ctx->w_streams.size() != B.qstreams.size() * sizeof(QStreamDev)) return false;
+  const QStreamDev* W = (const QStreamDev*)ctx->w_streams.data();
+  for (size_t x = 0; x < B.qstreams.size(); ++x) {
+    const QStreamDev& a = W[x];
+    const QStreamDev& b = B.qstreams[x];
+    if (a.tgt_dim != b.tgt_dim || a.src_dim != b.src_dim || a.same != b.same || a.J != b.J || a.m_lo != b.m_lo ||
+        a.m_hi != b.m_hi || a.w_first != b.w_first || a.s_max != b.s_max || a.h != b.h || a.wa_off >= 0 ||
+        a.wb_off >= 0 || b.wa_off >= 0 || b.wb_off >= 0)
+      return false;
+  }
+  return true;
+}
+
 template <int FAMILY>
 static void launch_pair(aslsd_ctx* ctx, const BatchPlan& B, const ItemDev* d_items) {
   if (B.fam_wu_count[FAMILY] == 0) return;
@@ -512,8 +543,10 @@ static int run_batch_impl(aslsd_ctx* ctx, BatchPlan& B, double* raw_device) {
     if ((rc = upload_quadrature_tables(ctx))) return rc;
     if ((rc = ensure_device_buffer(ctx, (void**)&ctx->d_q_partials, &ctx->q_partials_cap,
                                    (size_t)B.n_q_partials * sizeof(double)))) return rc;
+    const double* before = ctx->d_q_weights;
     if ((rc = ensure_device_buffer(ctx, (void**)&ctx->d_q_weights, &ctx->q_weights_cap,
                                    (size_t)B.n_q_weights * sizeof(double)))) return rc;
+    if (ctx->d_q_weights != before) { ctx->w_streams.clear(); B.weights_valid = false; }
   }
   if (!B.device_resident && (n_items || quad)) {
     // all plan tables go through one page-locked block of their own and two asynchronous
@@ -559,6 +592,7 @@ static int run_batch_impl(aslsd_ctx* ctx, BatchPlan& B, double* raw_device) {
   // on the evaluation point as long as the windows stay): with the weight cache on, a repeated
   // evaluation on the same plan - the iterations of a fit with fixed (beta, delta) - skips the
   // pass over the event pairs.
+  if (quad && ctx->cache_weights && !B.weights_valid && weights_match(ctx, B)) B.weights_valid = true;
   const bool reuse_weights = quad && ctx->cache_weights && B.weights_valid;
   ctx->last_weights_reused = reuse_weights;
   ctx->moment_timing_pending = false;
@@ -593,6 +627,9 @@ static int run_batch_impl(aslsd_ctx* ctx, BatchPlan& B, double* raw_device) {
     lag_weights_kernel<<<wgrid, LQ_WB * LQ_ND, 0, ctx->stream>>>(d_streams, ctx->d_q_partials, ctx->d_q_weights);
     ctx->last_launches++;
     B.weights_valid = true;
+    ctx->w_streams.assign((const unsigned char*)B.qstreams.data(),
+                          (const unsigned char*)(B.qstreams.data() + B.qstreams.size()));
+    ctx->w_events_epoch = ctx->events_epoch;
   }
   launch_pair<ITEM_UPS_GAUSS>(ctx, B, d_items);
   launch_pair<ITEM_UPS_EXP>(ctx, B, d_items);
@@ -699,6 +736,153 @@ static void assemble_all(const aslsd_ctx* ctx, const BatchPlan& B, int n_k, cons
   for (auto& th : pool) th.join();
 }
 
+
+// ---- assembly on the device -----------------------------------------------------------------
+// The map is linear in the raw rows with coefficients that are products of at most two omegas
+// (and mu_k) times a function of the non-omega variables: its structure is extracted once per row
+// plan (emit_term_w<SymW>), the omegas travel as a small table per call.  One warp per packed sum,
+// lanes striding over its entries, fixed order: deterministic.
+#define ASM_NT 256
+__global__ void __launch_bounds__(ASM_NT)
+assemble_kernel(const int64_t* __restrict__ ptr, const AsmEntry* __restrict__ entries,
+                const double* __restrict__ wtab, const double* __restrict__ raw, double* __restrict__ out,
+                int64_t n_out) {
+  const int lane = threadIdx.x & 31;
+  const int64_t o = ((int64_t)blockIdx.x * ASM_NT + threadIdx.x) >> 5;
+  if (o >= n_out) return;
+  double acc = 0.;
+  for (int64_t e = ptr[o] + lane; e < ptr[o + 1]; e += 32) {
+    const AsmEntry E = entries[e];
+    const double coef = (wtab[E.a] * wtab[E.b]) * E.g;
+    acc += wtab[E.o] * (coef * raw[E.raw_ix]);
+  }
+#pragma unroll
+  for (int s = 16; s > 0; s >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, s);
+  if (lane == 0) out[o] = acc;
+}
+
+// omega table of sub-problem q: [0] = 1, [1] = mu_k, then the omegas of K[k][i] read with its own
+// structure (P.V) and with the structure of KU (P.VU)
+static int asm_r_max(const aslsd_ctx* ctx) {
+  size_t r = 1;
+  for (auto& K : ctx->kernels) r = std::max(r, K.bases.size());
+  return (int)r;
+}
+static void fill_wtab(const aslsd_ctx* ctx, const BatchPlan& B, int q, const double* x_k, double* w) {
+  const int d = ctx->d, R = asm_r_max(ctx);
+  const SumPlan& P = B.plans[q];
+  w[0] = 1.;
+  w[1] = x_k[0];
+  for (int i = 0; i < d; ++i)
+    for (int r = 0; r < R; ++r) {
+      w[2 + i * R + r] = r < (int)P.V[i].size() ? P.V[i][r][0] : 0.;
+      w[2 + d * R + i * R + r] = r < (int)P.VU[i].size() ? P.VU[i][r][0] : 0.;
+    }
+}
+
+static int build_assembly_host(aslsd_ctx* ctx, BatchPlan& B, std::vector<int64_t>& count,
+                               std::vector<AsmEntry>& sorted) {
+  const int d = ctx->d, R = asm_r_max(ctx), n_k = (int)B.plans.size();
+  B.w_stride = 2 + 2 * d * R;
+  B.out_off.assign(n_k + 1, 0);
+  for (int q = 0; q < n_k; ++q) B.out_off[q + 1] = B.out_off[q] + B.plans[q].out_len;
+  B.out_total = B.out_off[n_k];
+  if ((int64_t)B.rows.size() * ASLSD_MAX_COMP >= 2147483647LL || (int64_t)n_k * B.w_stride >= 2147483647LL)
+    return aslsd_fail(ctx, ASLSD_ERR_ARG, "exact sums: assembly table too large");
+  count.assign((size_t)B.out_total + 1, 0);
+  struct Tmp { int64_t out; AsmEntry e; };
+  std::vector<Tmp> tmp;
+  for (int q = 0; q < n_k; ++q) {
+    const SumPlan& P = B.plans[q];
+    const int32_t base = q * B.w_stride;
+    const std::vector<int64_t>& item_row = B.item_row[q];
+    for (size_t t = 0; t < P.terms.size(); ++t) {
+      const int64_t o0 = B.out_off[q] + P.terms[t].out_off;
+      emit_term_w<SymW>(ctx, P, t, SymW(1, 1.),
+                        [&](int i, int r) { return SymW(2 + i * R + r, 1.); },
+                        [&](int i, int r) { return SymW(2 + d * R + i * R + r, 1.); },
+                        [&](int c, int item, int comp, SymW coef, SymW outer) {
+                          Tmp x;
+                          x.out = o0 + c;
+                          x.e.raw_ix = (int32_t)(item_row[item] * ASLSD_MAX_COMP + comp);
+                          x.e.a = base + coef.a;
+                          x.e.b = base + coef.b;
+                          x.e.o = base + outer.a;
+                          x.e.g = coef.g * outer.g;
+                          tmp.push_back(x);
+                          count[(size_t)x.out + 1]++;
+                        });
+    }
+  }
+  for (size_t o = 0; o < (size_t)B.out_total; ++o) count[o + 1] += count[o];
+  sorted.resize(tmp.size());
+  std::vector<int64_t> cur(count.begin(), count.end() - 1);
+  for (auto& x : tmp) sorted[(size_t)cur[(size_t)x.out]++] = x.e;   // stable: emission order within a sum
+  B.asm_entries = (int64_t)sorted.size();
+  return ASLSD_OK;
+}
+
+static int build_assembly(aslsd_ctx* ctx, BatchPlan& B) {
+  std::vector<int64_t> count;
+  std::vector<AsmEntry> sorted;
+  int rc;
+  if ((rc = build_assembly_host(ctx, B, count, sorted))) return rc;
+  if ((rc = ensure_device_buffer(ctx, &ctx->d_asm, &ctx->asm_cap,
+                                 std::max<size_t>(1, sorted.size()) * sizeof(AsmEntry)))) return rc;
+  if ((rc = ensure_device_buffer(ctx, (void**)&ctx->d_asm_ptr, &ctx->asm_ptr_cap, count.size() * sizeof(int64_t))))
+    return rc;
+  CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_asm, sorted.data(), sorted.size() * sizeof(AsmEntry), cudaMemcpyHostToDevice,
+                                ctx->stream));
+  CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_asm_ptr, count.data(), count.size() * sizeof(int64_t), cudaMemcpyHostToDevice,
+                                ctx->stream));
+  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));   // the sources are locals
+  B.asm_built = true;
+  B.asm_resident = true;
+  ctx->asm_owner = &B;
+  return ASLSD_OK;
+}
+
+// raw_device (rows of this plan) -> packed_device (out_total doubles), on the context's stream
+static int assemble_device(aslsd_ctx* ctx, BatchPlan& B, int n_k, const double* const* xs, const double* raw_device,
+                           double* packed_device) {
+  int rc;
+  if (!B.asm_built || ctx->asm_owner != &B)
+    if ((rc = build_assembly(ctx, B))) return rc;
+  const size_t n_w = (size_t)n_k * B.w_stride;
+  if ((rc = ensure_device_buffer(ctx, (void**)&ctx->d_wtab, &ctx->wtab_cap, n_w * sizeof(double)))) return rc;
+  // page-locked staging of the omega tables (two halves in turn: the previous call's transfer
+  // may still be in flight when the next one is planned)
+  if (n_w * 2 > ctx->h_wtab_cap) {
+    if (ctx->h_wtab) {
+      CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+      CUDA_TRY(ctx, cudaFreeHost(ctx->h_wtab));
+    }
+    ctx->h_wtab = nullptr;
+    ctx->h_wtab_cap = 0;
+    CUDA_TRY(ctx, cudaMallocHost((void**)&ctx->h_wtab, n_w * 2 * sizeof(double)));
+    ctx->h_wtab_cap = n_w * 2;
+    ctx->wtab_flip = 0;
+  }
+  double* hw = ctx->h_wtab + (ctx->wtab_flip ? n_w : 0);
+  if (ctx->wtab_in_flight[ctx->wtab_flip]) {
+    CUDA_TRY(ctx, cudaEventSynchronize(ctx->ev_wtab[ctx->wtab_flip]));
+    ctx->wtab_in_flight[ctx->wtab_flip] = false;
+  }
+  for (int q = 0; q < n_k; ++q) fill_wtab(ctx, B, q, xs[q], hw + (size_t)q * B.w_stride);
+  CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_wtab, hw, n_w * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  CUDA_TRY(ctx, cudaEventRecord(ctx->ev_wtab[ctx->wtab_flip], ctx->stream));
+  ctx->wtab_in_flight[ctx->wtab_flip] = true;
+  ctx->wtab_flip ^= 1;
+  const int64_t n_thr = B.out_total * 32;
+  if (B.out_total > 0) {
+    assemble_kernel<<<(unsigned)((n_thr + ASM_NT - 1) / ASM_NT), ASM_NT, 0, ctx->stream>>>(
+        ctx->d_asm_ptr, (const AsmEntry*)ctx->d_asm, ctx->d_wtab, raw_device, packed_device, B.out_total);
+    ctx->last_launches++;
+  }
+  CUDA_TRY(ctx, cudaGetLastError());
+  return ASLSD_OK;
+}
+
 static int64_t batch_out_len(const aslsd_ctx* ctx, int k) {
   const int d = ctx->d;
   int64_t out = 0;
@@ -744,6 +928,7 @@ extern "C" int aslsd_set_option(aslsd_ctx* ctx, int option, int value) {
   if (option == ASLSD_OPT_LAG_QUADRATURE) { ctx->use_quadrature = value != 0; ctx->model_epoch++; return ASLSD_OK; }
   if (option == ASLSD_OPT_WEIGHT_CACHE) { ctx->cache_weights = value != 0; ctx->model_epoch++; return ASLSD_OK; }
   if (option == ASLSD_OPT_ASYNC_EVENTS) { ctx->async_events = value != 0; return ASLSD_OK; }
+  if (option == ASLSD_OPT_DEVICE_ASSEMBLY) { ctx->device_assembly = value != 0; return ASLSD_OK; }
   return aslsd_fail(ctx, ASLSD_ERR_ARG, "set_option: unknown option");
 }
 
@@ -760,15 +945,71 @@ extern "C" int aslsd_exact_sums_batch(aslsd_ctx* ctx, int n_k, const int* ks, co
   CUDA_TRY(ctx, cudaSetDevice(ctx->device));
   if ((rc = ensure_device_buffer(ctx, (void**)&ctx->d_raw, &ctx->raw_cap, raw_bytes))) return rc;
   if ((rc = run_batch(ctx, B, ctx->d_raw))) return rc;
-  if ((rc = ensure_pinned_buffer(ctx, raw_bytes))) return rc;
-  CUDA_TRY(ctx, cudaMemcpyAsync(ctx->h_pinned, ctx->d_raw, raw_bytes, cudaMemcpyDeviceToHost, ctx->stream));
-  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
-  if ((rc = events_verdict(ctx, true))) return rc;
-  assemble_all(ctx, B, n_k, xs, (const double*)ctx->h_pinned, outs);
+  // Assembly: on the device once a row plan serves its second call (the iterations of a fit, the
+  // steps of a benchmark: the map is built once and only the packed sums are read back); a plan
+  // used once - and the weighted plans of marked models, which are - is assembled on the host
+  // from the raw rows, which costs one traversal of the map either way.
+  const bool on_device = ctx->device_assembly && !ctx->roles && (B.uses > 0 || B.asm_built);
+  B.uses++;
+  if (on_device) {
+    int64_t total = 0;
+    for (int q = 0; q < n_k; ++q) total += B.plans[q].out_len;
+    const size_t bytes = std::max<int64_t>(1, total) * sizeof(double);
+    if ((rc = ensure_device_buffer(ctx, (void**)&ctx->d_packed, &ctx->packed_cap, bytes))) return rc;
+    if ((rc = assemble_device(ctx, B, n_k, xs, ctx->d_raw, ctx->d_packed))) return rc;
+    CUDA_TRY(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
+    if ((rc = ensure_pinned_buffer(ctx, bytes))) return rc;
+    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->h_pinned, ctx->d_packed, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    if ((rc = events_verdict(ctx, true))) return rc;
+    for (int q = 0; q < n_k; ++q)
+      std::memcpy(outs[q], (const double*)ctx->h_pinned + B.out_off[q], (size_t)B.plans[q].out_len * sizeof(double));
+  } else {
+    if ((rc = ensure_pinned_buffer(ctx, raw_bytes))) return rc;
+    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->h_pinned, ctx->d_raw, raw_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    if ((rc = events_verdict(ctx, true))) return rc;
+    assemble_all(ctx, B, n_k, xs, (const double*)ctx->h_pinned, outs);
+  }
   if (n_pair_terms)
     for (int q = 0; q < n_k && !rc; ++q)
       if (n_pair_terms[q]) rc = count_pair_terms(ctx, B.plans[q], B.lo, B.hi, n_pair_terms[q]);
   return rc;
+}
+
+// Multi-GPU form with the assembly on the device: the packed sums of the batch (sub-problems
+// concatenated in call order, aslsd_exact_packed_len_batch doubles) are left in packed_device
+// on the context's stream.  Assembly is linear, so the caller all-reduces these few thousand
+// doubles instead of the raw rows, and only they are read back.
+extern "C" int aslsd_exact_packed_len_batch(aslsd_ctx* ctx, int n_k, const int* ks, int64_t* packed_len) {
+  if (!ctx || !ctx->has_model || n_k <= 0 || !ks || !packed_len) return ASLSD_ERR_ARG;
+  int64_t n = 0;
+  for (int q = 0; q < n_k; ++q) {
+    if (ks[q] < 0 || ks[q] >= ctx->d) return aslsd_fail(ctx, ASLSD_ERR_ARG, "exact sums: bad k");
+    n += batch_out_len(ctx, ks[q]);
+  }
+  *packed_len = n;
+  return ASLSD_OK;
+}
+
+extern "C" int aslsd_exact_packed_device_batch(aslsd_ctx* ctx, int n_k, const int* ks, const double* const* xs,
+                                               int flags, const int64_t* m_lo, const int64_t* m_hi,
+                                               double* packed_device) {
+  int rc = check_batch_args(ctx, n_k, ks, xs);
+  if (rc) return rc;
+  if (!packed_device) return aslsd_fail(ctx, ASLSD_ERR_ARG, "exact_packed_device: bad arguments");
+  if (ctx->roles) return aslsd_fail(ctx, ASLSD_ERR_ARG, "exact_packed_device: not for weighted plans");
+  BatchPlan* Bp = nullptr;
+  if ((rc = get_batch(ctx, n_k, ks, xs, flags, m_lo, m_hi, true, &Bp))) return rc;
+  BatchPlan& B = *Bp;
+  const size_t raw_bytes = std::max<size_t>(1, B.rows.size()) * ASLSD_MAX_COMP * sizeof(double);
+  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  if ((rc = ensure_device_buffer(ctx, (void**)&ctx->d_raw, &ctx->raw_cap, raw_bytes))) return rc;
+  if ((rc = run_batch(ctx, B, ctx->d_raw))) return rc;
+  B.uses++;
+  if ((rc = assemble_device(ctx, B, n_k, xs, ctx->d_raw, packed_device))) return rc;
+  CUDA_TRY(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
+  return ASLSD_OK;
 }
 
 extern "C" int aslsd_exact_sums(aslsd_ctx* ctx, int k, const double* x_k, int flags, const int64_t* m_lo,
@@ -885,6 +1126,37 @@ extern "C" int aslsd_exact_assemble_batch(aslsd_ctx* ctx, int n_k, const int* ks
   if ((rc = get_batch(ctx, n_k, ks, xs, flags, nullptr, nullptr, false, &Bp))) return rc;
   BatchPlan& B = *Bp;
   assemble_all(ctx, B, n_k, xs, raw_host, outs);
+  return ASLSD_OK;
+}
+
+// The map of the device assembly (CSR table + omega tables) evaluated on the host with the
+// kernel's arithmetic: a check of the table against aslsd_exact_assemble_batch that needs no device.
+extern "C" int aslsd_exact_assemble_map_batch(aslsd_ctx* ctx, int n_k, const int* ks, const double* const* xs,
+                                              int flags, const double* raw_host, double* const* outs) {
+  int rc = check_batch_args(ctx, n_k, ks, xs);
+  if (rc) return rc;
+  if (!raw_host || !outs) return aslsd_fail(ctx, ASLSD_ERR_ARG, "exact_assemble_map: bad arguments");
+  BatchPlan* Bp = nullptr;
+  if ((rc = get_batch(ctx, n_k, ks, xs, flags, nullptr, nullptr, false, &Bp))) return rc;
+  BatchPlan& B = *Bp;
+  std::vector<int64_t> ptr;
+  std::vector<AsmEntry> entries;
+  if ((rc = build_assembly_host(ctx, B, ptr, entries))) return rc;
+  std::vector<double> w((size_t)n_k * B.w_stride);
+  for (int q = 0; q < n_k; ++q) fill_wtab(ctx, B, q, xs[q], w.data() + (size_t)q * B.w_stride);
+  for (int q = 0; q < n_k; ++q)
+    for (int64_t c = 0; c < B.plans[q].out_len; ++c) {
+      const int64_t o = B.out_off[q] + c;
+      double lanes[32] = {0.};
+      for (int64_t e = ptr[o]; e < ptr[o + 1]; ++e) {
+        const AsmEntry& E = entries[(size_t)e];
+        const double coef = (w[E.a] * w[E.b]) * E.g;
+        lanes[(e - ptr[o]) & 31] += w[E.o] * (coef * raw_host[E.raw_ix]);
+      }
+      for (int s = 16; s > 0; s >>= 1)
+        for (int l = 0; l < s; ++l) lanes[l] += lanes[l + s];
+      outs[q][c] = lanes[0];
+    }
   return ASLSD_OK;
 }
 

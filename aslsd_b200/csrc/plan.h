@@ -10,6 +10,7 @@
 #pragma once
 
 #include <array>
+#include <cmath>
 
 #include "common.cuh"
 
@@ -47,6 +48,36 @@ void plan_shape_key(const aslsd_ctx* ctx, int k, const double* x_k, std::vector<
 // Index of a named term in SumPlan::terms (-1 if absent).
 int find_term(const aslsd_ctx* ctx, int kind, int i, int j);
 
+// Symbolic omega factor: coefficient = g x w[a] x w[b], with a, b indices into a per-sub-problem
+// table of the omega values (0 = the constant one) and g a function of the non-omega variables
+// only.  emit_term_w instantiated with it yields the structure of the linear map once per plan;
+// the device assembly (exact.cu) then evaluates the coefficients from the table of every call.
+struct SymW {
+  int32_t a = 0, b = 0;
+  double g = 1.;
+  SymW() {}
+  SymW(double v) : g(v) {}
+  SymW(int32_t ix, double v) : a(ix), g(v) {}
+};
+inline SymW operator*(const SymW& x, const SymW& y) {
+  SymW r;
+  r.g = x.g * y.g;
+  const int32_t idx[4] = {x.a, x.b, y.a, y.b};
+  int n = 0;
+  for (int q = 0; q < 4; ++q)
+    if (idx[q] != 0) {
+      if (n == 0) r.a = idx[q];
+      else if (n == 1) r.b = idx[q];
+      else r.g = std::nan("");   // more than two omega factors: no such coefficient exists
+      ++n;
+    }
+  return r;
+}
+inline SymW operator*(const SymW& x, double s) { SymW r = x; r.g = x.g * s; return r; }
+inline SymW operator*(double s, const SymW& x) { return x * s; }
+inline SymW operator/(const SymW& x, double s) { SymW r = x; r.g = x.g / s; return r; }
+inline SymW operator-(const SymW& x) { SymW r = x; r.g = -x.g; return r; }
+
 // Linear map raw components -> packed outputs of one term.  The sink is called
 // as sink(c, item, comp, coef, outer): output c of the term (0 = function value,
 // 1.. = derivatives) receives outer * (coef * raw[item][comp]); item < 0 never
@@ -54,16 +85,19 @@ int find_term(const aslsd_ctx* ctx, int kind, int i, int j);
 // (e.g. psi term: mu_k * (omega * (1 - e^{-beta t})), mhp_stratified_estimator.py
 // :1106-1108) so that per-sample values of near-constant strata come out
 // bit-identical and numpy's rounding residue in np.std is reproduced.
-template <class Sink>
-void emit_term(const aslsd_ctx* ctx, const SumPlan& P, size_t t, const double* x_k, Sink&& sink) {
+// W: type of the omega factors (double, or SymW for the structure alone); omV(i, r) / omVU(i, r):
+// omega of basis r of K[k][i] read with the structure of K[k][i] / of KU; the other variables
+// come from P.V / P.VU.
+template <class W, class OmV, class OmVU, class Sink>
+void emit_term_w(const aslsd_ctx* ctx, const SumPlan& P, size_t t, W mu_k, OmV&& omV, OmVU&& omVU, Sink&& sink) {
   const int d = ctx->d;
   const int k = P.k;
   const bool diff = (P.flags & ASLSD_DIFF) != 0;
-  const double mu_k = x_k[0];
   const KernelHost& KU = ctx->kernels[d * d - 1];
   const TermPlan& T = P.terms[t];
   const int voff = P.term_val_off[t], doff = P.term_der_off[t];
-  auto put = [&](int c, int off, int slot, int comp, double coef, double outer = 1.) {
+  const W one(1.);
+  auto put = [&](int c, int off, int slot, int comp, W coef, W outer) {
     const int idx = P.slot_item[off + slot];
     if (idx >= 0) sink(c, idx, comp, coef, outer);
   };
@@ -86,22 +120,23 @@ void emit_term(const aslsd_ctx* ctx, const SumPlan& P, size_t t, const double* x
     // psi_i / phi_i: one item per basis of K[k][i]
     const KernelHost& K = ctx->kernels[k * d + T.i];
     const std::vector<Vars>& V = P.V[T.i];
-    const double scale = (T.kind == 0) ? mu_k : 1.;
+    const W scale = (T.kind == 0) ? mu_k : one;
     int slot = 0;
     for (size_t r = 0; r < K.bases.size(); ++r) {
       const BasisHost& b = K.bases[r];
       const bool is_exp = b.type == ASLSD_BASIS_EXPONENTIAL;
-      const double w = V[r][0], be = V[r][1];
-      double cv, cw, cb, cd = 0.;   // coefficients of comp 0 (value), comp 0 (d omega), comp 1, comp 2
+      const W w = omV(T.i, (int)r);
+      const double be = V[r][1];
+      W cv, cw, cb, cd(0.);   // coefficients of comp 0 (value), comp 0 (d omega), comp 1, comp 2
       if (T.kind == 2) {
-        if (is_exp) { cv = w * be; cw = be; cb = w; }
-        else { cv = w; cw = 1.; cb = w / be; cd = w; }
+        if (is_exp) { cv = w * be; cw = W(be); cb = w; }
+        else { cv = w; cw = one; cb = w / be; cd = w; }
       } else {
-        if (is_exp) { cv = w; cw = 1.; cb = w; }
-        else { cv = w; cw = 1.; cb = w / (be * be); cd = -(w / be); }
+        if (is_exp) { cv = w; cw = one; cb = w; }
+        else { cv = w; cw = one; cb = w / (be * be); cd = -(w / be); }
       }
       put(0, voff, (int)r, 0, cv, scale);
-      if (T.kind == 0) put(1 + T.n1, voff, (int)r, 0, cv);   // d/d mu_k (ix_func 2)
+      if (T.kind == 0) put(1 + T.n1, voff, (int)r, 0, cv, one);   // d/d mu_k (ix_func 2)
       for (int v = 0; v < b.n_vars(); ++v) {
         if (!((b.free_mask >> v) & 1)) continue;
         if (diff) put(1 + slot, voff, (int)r, v, v == 0 ? cw : (v == 1 ? cb : cd), scale);
@@ -115,7 +150,7 @@ void emit_term(const aslsd_ctx* ctx, const SumPlan& P, size_t t, const double* x
     const std::vector<Vars>&V1 = P.VU[T.i], &V2 = P.VU[T.j];
     for (int p = 0; p < Rn; ++p)
       for (int q = 0; q < Rn; ++q)
-        put(0, voff, p * Rn + q, C_G, V1[p][0] * V2[q][0] * prat(p, q, V1[p], V2[q]));
+        put(0, voff, p * Rn + q, C_G, omVU(T.i, p) * omVU(T.j, q) * prat(p, q, V1[p], V2[q]), one);
     if (!diff) return;
     int slot = 0;
     for (int p = 0; p < Rn; ++p)
@@ -124,7 +159,7 @@ void emit_term(const aslsd_ctx* ctx, const SumPlan& P, size_t t, const double* x
         if (slot < T.n1)
           for (int q = 0; q < Rn; ++q)
             put(1 + slot, voff, p * Rn + q, v == 0 ? omega_comp(p, q, 1) : (v == 1 ? C_B1 : C_D1),
-                v == 0 ? V2[q][0] * prat(p, q, V1[p], V2[q]) : V1[p][0] * V2[q][0]);
+                v == 0 ? omVU(T.j, q) * prat(p, q, V1[p], V2[q]) : omVU(T.i, p) * omVU(T.j, q), one);
         ++slot;
       }
     slot = 0;
@@ -134,7 +169,7 @@ void emit_term(const aslsd_ctx* ctx, const SumPlan& P, size_t t, const double* x
         if (slot < T.n2)
           for (int p = 0; p < Rn; ++p)
             put(1 + T.n1 + slot, voff, p * Rn + q, v == 0 ? omega_comp(p, q, 2) : (v == 1 ? C_B2 : C_D2),
-                v == 0 ? V1[p][0] * prat(p, q, V1[p], V2[q]) : V1[p][0] * V2[q][0]);
+                v == 0 ? omVU(T.i, p) * prat(p, q, V1[p], V2[q]) : omVU(T.i, p) * omVU(T.j, q), one);
         ++slot;
       }
     return;
@@ -144,27 +179,34 @@ void emit_term(const aslsd_ctx* ctx, const SumPlan& P, size_t t, const double* x
   const std::vector<Vars>& VB = P.V[T.i];
   const KernelHost& KB = ctx->kernels[k * d + T.i];
   for (int p = 0; p < Rn; ++p)
-    for (int q = 0; q < Rn; ++q) put(0, voff, p * Rn + q, C_G, VA[p][0] * VA[q][0] * prat(p, q, VA[p], VA[q]));
+    for (int q = 0; q < Rn; ++q)
+      put(0, voff, p * Rn + q, C_G, omVU(T.i, p) * omVU(T.i, q) * prat(p, q, VA[p], VA[q]), one);
   if (!diff) return;
   int slot = 0;
   for (int b = 0; b < Rn; ++b)
     for (int v = 0; v < KB.bases[b].n_vars(); ++v) {
       if (!((KB.bases[b].free_mask >> v) & 1)) continue;
-      const double wb = VB[b][0];
+      const W wb = omV(T.i, b);
       // own-basis closed form, then the cross terms with every other basis in
       // both slots (kernel.py:282-299)
-      if (v == 0) put(1 + slot, doff, b * Rn + b, C_SW, is_exp(b) ? wb * VB[b][1] : wb);
-      else put(1 + slot, doff, b * Rn + b, v == 1 ? C_SB : C_SD, wb * wb);
+      if (v == 0) put(1 + slot, doff, b * Rn + b, C_SW, is_exp(b) ? wb * VB[b][1] : wb, one);
+      else put(1 + slot, doff, b * Rn + b, v == 1 ? C_SB : C_SD, wb * wb, one);
       for (int q = 0; q < Rn; ++q) {
         if (q == b) continue;
-        if (v == 0) put(1 + slot, doff, b * Rn + q, omega_comp(b, q, 1), VB[q][0] * prat(b, q, VB[b], VB[q]));
-        else put(1 + slot, doff, b * Rn + q, v == 1 ? C_B1 : C_D1, wb * VB[q][0]);
+        if (v == 0) put(1 + slot, doff, b * Rn + q, omega_comp(b, q, 1), omV(T.i, q) * prat(b, q, VB[b], VB[q]), one);
+        else put(1 + slot, doff, b * Rn + q, v == 1 ? C_B1 : C_D1, wb * omV(T.i, q), one);
       }
       for (int p = 0; p < Rn; ++p) {
         if (p == b) continue;
-        if (v == 0) put(1 + slot, doff, p * Rn + b, omega_comp(p, b, 2), VB[p][0] * prat(p, b, VB[p], VB[b]));
-        else put(1 + slot, doff, p * Rn + b, v == 1 ? C_B2 : C_D2, VB[p][0] * wb);
+        if (v == 0) put(1 + slot, doff, p * Rn + b, omega_comp(p, b, 2), omV(T.i, p) * prat(p, b, VB[p], VB[b]), one);
+        else put(1 + slot, doff, p * Rn + b, v == 1 ? C_B2 : C_D2, omV(T.i, p) * wb, one);
       }
       ++slot;
     }
+}
+
+template <class Sink>
+void emit_term(const aslsd_ctx* ctx, const SumPlan& P, size_t t, const double* x_k, Sink&& sink) {
+  emit_term_w<double>(ctx, P, t, x_k[0], [&](int i, int r) { return P.V[i][r][0]; },
+                      [&](int i, int r) { return P.VU[i][r][0]; }, sink);
 }

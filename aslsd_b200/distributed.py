@@ -92,17 +92,41 @@ class ShardedExactSums:
         self.ranges = time_block_ranges(list_times, world_size)[rank]
         self._raw = {}
         self.max_lag = None
+        self.last_d2h_bytes = 0
 
-    def set_events(self, list_times, T_f, ks, xs, slack=1.0):
+    def set_events(self, list_times, T_f, ks, xs, slack=1.25):
         """Upload this rank's time block of ``list_times`` plus the halo its first targets can
         reach (``slack`` x the largest lag of the sub-problems ``ks`` at ``xs``) and point the
-        target ranges at the block inside the uploaded slice."""
-        block = time_block_ranges(list_times, self.world_size)[self.rank]
+        target ranges at the block inside the uploaded slice.  Every later launch checks that
+        the reach of its parameters still fits the halo and uploads a wider slice if it does
+        not (``_check_reach``)."""
+        block = self._blocks(list_times)[self.rank]
         self.max_lag = slack * self.engine.exact_max_lag(ks, xs)
         local, ranges = block_slices(list_times, block, self.max_lag)
         self.engine.set_events(local, T_f)
         self.ranges = ranges
+        self._sliced = (list_times, T_f, slack)
         return ranges
+
+    def _blocks(self, list_times):
+        """Time blocks of ``list_times``, kept while the same arrays are handed in again."""
+        key = (tuple(id(t) for t in list_times), tuple(len(t) for t in list_times), self.world_size)
+        if getattr(self, '_blocks_key', None) != key:
+            self._blocks_val = time_block_ranges(list_times, self.world_size)
+            self._blocks_key = key
+            self._blocks_ref = list(list_times)     # keeps the ids unique
+        return self._blocks_val
+
+    def _check_reach(self, ks, xs):
+        """Halo mode only: a parameter update may have widened the kernels' reach (42 / beta,
+        delta + 9 sigma) beyond the halo uploaded with the block - the first targets of every
+        block but the first would then silently lose sources.  Re-slice and re-upload."""
+        if self.max_lag is None:
+            return
+        reach = self.engine.exact_max_lag(ks, xs)
+        if reach > self.max_lag:
+            list_times, T_f, slack = self._sliced
+            self.set_events(list_times, T_f, ks, xs, slack=max(slack, 1.25))
 
     def raw_buffer(self, k):
         if k not in self._raw:
@@ -117,6 +141,7 @@ class ShardedExactSums:
         if raw.is_cuda:
             # the library's kernels and the NCCL all-reduce share torch's current stream
             self.engine.set_stream(self.torch.cuda.current_stream().cuda_stream)
+        self._check_reach([k], [x_k])
         self.engine.exact_raw_device(k, x_k, raw.data_ptr(), compute_f_sum,
                                      compute_diff_f_sum, ranges=self.ranges)
         raw = raw[:self.engine.exact_raw_used()]     # the rows this model has (same on all ranks)
@@ -133,6 +158,7 @@ class ShardedExactSums:
         raw = self._raw[key]
         if raw.is_cuda:
             self.engine.set_stream(self.torch.cuda.current_stream().cuda_stream)
+        self._check_reach(ks, xs)
         self.engine.exact_raw_device_batch(ks, xs, raw.data_ptr(), compute_f_sum,
                                            compute_diff_f_sum, ranges=self.ranges)
         raw = raw[:self.engine.exact_raw_used()]     # the rows this model has (same on all ranks)
@@ -140,10 +166,29 @@ class ShardedExactSums:
             self.dist.all_reduce(raw, op=self.dist.ReduceOp.SUM)
         return raw
 
+    def launch_packed_batch(self, ks, xs, compute_f_sum=True, compute_diff_f_sum=True):
+        """Kernels, device-side assembly and the all-reduce of the packed sums (assembly is linear:
+        a few thousand doubles per sub-problem cross NVLink instead of the raw rows); returns the
+        device tensor of the concatenated packed sums (asynchronous)."""
+        key = ('packed', tuple(ks))
+        if key not in self._raw:
+            n = self.engine.exact_packed_len_batch(ks)
+            self._raw[key] = self.torch.zeros(n, dtype=self.torch.float64, device=self.device)
+        packed = self._raw[key]
+        if packed.is_cuda:
+            self.engine.set_stream(self.torch.cuda.current_stream().cuda_stream)
+        self._check_reach(ks, xs)
+        self.engine.exact_packed_device_batch(ks, xs, packed.data_ptr(), compute_f_sum,
+                                              compute_diff_f_sum, ranges=self.ranges)
+        if self.world_size > 1:
+            self.dist.all_reduce(packed, op=self.dist.ReduceOp.SUM)
+        return packed
+
     def packed_batch(self, ks, xs, compute_f_sum=True, compute_diff_f_sum=True):
-        raw = self.launch_batch(ks, xs, compute_f_sum, compute_diff_f_sum)
-        host = raw.cpu().numpy()
-        return self.engine.exact_assemble_batch(ks, xs, host, compute_f_sum, compute_diff_f_sum)
+        packed = self.launch_packed_batch(ks, xs, compute_f_sum, compute_diff_f_sum)
+        host = packed.cpu().numpy()      # synchronises the stream
+        self.last_d2h_bytes = host.nbytes
+        return self.engine.split_packed(ks, host)
 
     def packed(self, k, x_k, compute_f_sum=True, compute_diff_f_sum=True):
         raw = self.launch(k, x_k, compute_f_sum, compute_diff_f_sum)

@@ -98,6 +98,10 @@ class Engine:
             handle = int(cuda_stream) or 1
         self._check(self._lib.aslsd_set_stream(self._ctx, ctypes.c_void_p(handle)))
 
+    def synchronize(self):
+        """Wait for everything enqueued on the context's stream."""
+        self._check(self._lib.aslsd_synchronize(self._ctx))
+
     def last_timing(self):
         ms = ctypes.c_double()
         n = ctypes.c_int64()
@@ -465,6 +469,35 @@ class Engine:
         self._check(self._lib.aslsd_exact_raw_device_batch(
             self._ctx, len(ks), k_ptr, x_ptrs, flags, lo_p, hi_p, ctypes.c_void_p(raw_device_ptr)))
 
+    def exact_packed_len_batch(self, ks):
+        k_arr = np.ascontiguousarray(ks, dtype=np.int32)
+        n = ctypes.c_int64()
+        self._check(self._lib.aslsd_exact_packed_len_batch(self._ctx, len(ks), k_arr.ctypes.data_as(capi.c_i32_p),
+                                                           ctypes.byref(n)))
+        return n.value
+
+    def exact_packed_device_batch(self, ks, xs, packed_device_ptr, compute_f_sum=True,
+                                  compute_diff_f_sum=True, ranges=None):
+        """Kernels + device-side assembly: the packed sums of the sub-problems ``ks`` (concatenated)
+        are left at ``packed_device_ptr`` on the engine's stream (asynchronous)."""
+        xs, k_arr, k_ptr, x_ptrs = self._batch_args(ks, xs)
+        flags = (capi.ASLSD_F if compute_f_sum else 0) | (capi.ASLSD_DIFF if compute_diff_f_sum else 0)
+        lo, hi, lo_p, hi_p = self._ranges(ranges)
+        self._check(self._lib.aslsd_exact_packed_device_batch(
+            self._ctx, len(ks), k_ptr, x_ptrs, flags, lo_p, hi_p, ctypes.c_void_p(packed_device_ptr)))
+
+    def split_packed(self, ks, packed):
+        """Concatenated packed sums -> one array per sub-problem."""
+        out, pos = [], 0
+        for k in ks:
+            n = term_layout(self.desc, k)[1]
+            out.append(np.array(packed[pos:pos + n], dtype=np.float64))
+            pos += n
+        return out
+
+    def use_device_assembly(self, enabled=True):
+        self.set_option(capi.OPT_DEVICE_ASSEMBLY, 1 if enabled else 0)
+
     def exact_assemble_batch(self, ks, xs, raw_host, compute_f_sum=True, compute_diff_f_sum=True):
         xs, k_arr, k_ptr, x_ptrs = self._batch_args(ks, xs)
         raw = capi.as_f64(raw_host)
@@ -473,6 +506,17 @@ class Engine:
         flags = (capi.ASLSD_F if compute_f_sum else 0) | (capi.ASLSD_DIFF if compute_diff_f_sum else 0)
         self._check(self._lib.aslsd_exact_assemble_batch(self._ctx, len(ks), k_ptr, x_ptrs, flags,
                                                          capi.ptr_f64(raw), out_ptrs))
+        return outs
+
+    def exact_assemble_map_batch(self, ks, xs, raw_host, compute_f_sum=True, compute_diff_f_sum=True):
+        """Diagnostic: the device assembly's map applied on the host (aslsd_exact_assemble_map_batch)."""
+        xs, k_arr, k_ptr, x_ptrs = self._batch_args(ks, xs)
+        raw = capi.as_f64(raw_host)
+        outs = [np.zeros(term_layout(self.desc, k)[1], dtype=np.float64) for k in ks]
+        out_ptrs = (capi.c_f64_p * len(ks))(*[capi.ptr_f64(o) for o in outs])
+        flags = (capi.ASLSD_F if compute_f_sum else 0) | (capi.ASLSD_DIFF if compute_diff_f_sum else 0)
+        self._check(self._lib.aslsd_exact_assemble_map_batch(self._ctx, len(ks), k_ptr, x_ptrs, flags,
+                                                             capi.ptr_f64(raw), out_ptrs))
         return outs
 
     # split form (multi-GPU): raw accumulators stay on the device

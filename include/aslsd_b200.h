@@ -60,12 +60,15 @@ enum {
                                   and the lag windows only - are kept between calls while the events,
                                   the model, the target block and the non-omega parameters stay the
                                   same (the iterations of a fit); 0: recomputed on every call */
-  ASLSD_OPT_ASYNC_EVENTS = 3   /* page-locked inputs of aslsd_set_events are checked for order on the
+  ASLSD_OPT_ASYNC_EVENTS = 3,  /* page-locked inputs of aslsd_set_events are checked for order on the
                                   device, behind their transfer.  0 (default): aslsd_set_events waits
                                   for that verdict; 1: it returns as soon as the transfer is enqueued
                                   and a violation is reported (ASLSD_ERR_ARG, the context then has no
                                   events) by the next call that waits for the device - results of
                                   calls made in between are void */
+  ASLSD_OPT_DEVICE_ASSEMBLY = 4 /* 1 (default): from the second call on the same row plan, the packed
+                                  per-term sums are assembled from the raw rows by a device kernel and
+                                  only they are read back; 0: raw rows read back, assembly on the host */
 };
 
 /* ---- lifetime ------------------------------------------------------------------ */
@@ -221,6 +224,21 @@ int aslsd_exact_raw_device_batch(aslsd_ctx* ctx, int n_k, const int* ks, const d
                                  double* raw_device);
 int aslsd_exact_assemble_batch(aslsd_ctx* ctx, int n_k, const int* ks, const double* const* xs,
                                int flags, const double* raw_host, double* const* outs);
+/* The same with the assembly on the device: the packed sums of the batch (the sub-problems
+ * concatenated in call order, aslsd_exact_packed_len_batch doubles in all; layout of each as in
+ * aslsd_exact_sums) are left in packed_device (device memory of the caller, e.g. a torch tensor) on
+ * the context's stream.  recombine_* is linear (mhp_exact_estimator.py:442-530), so the shards of a
+ * time-block partition all-reduce these few thousand doubles instead of the raw rows. */
+int aslsd_exact_packed_len_batch(aslsd_ctx* ctx, int n_k, const int* ks, int64_t* packed_len);
+int aslsd_exact_packed_device_batch(aslsd_ctx* ctx, int n_k, const int* ks, const double* const* xs,
+                                    int flags, const int64_t* m_lo, const int64_t* m_hi,
+                                    double* packed_device);
+/* Diagnostic: the linear map of the device assembly evaluated on the host, in the kernel's order of
+ * operations - same arguments and results as aslsd_exact_assemble_batch (no device work). */
+int aslsd_exact_assemble_map_batch(aslsd_ctx* ctx, int n_k, const int* ks, const double* const* xs,
+                                   int flags, const double* raw_host, double* const* outs);
+/* Wait for everything enqueued on the context's stream. */
+int aslsd_synchronize(aslsd_ctx* ctx);
 
 /* Closed-form evaluations performed by the last exact-sum call (basis-pair
  * evaluations of the pair kernels / of the single-index kernels): the work

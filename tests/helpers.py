@@ -154,3 +154,24 @@ def _oracle_path(times, T_f):
         n_events=np.array([len(t) for t in times]), eta=np.array([len(t) for t in times]) / T_f,
         list_times2end=[T_f - t for t in times], kappa=kappa, varpi=varpi,
         lag_sizes=OT.lag_sizes(times, kappa, varpi))
+
+
+# ---- the windowed oracle on several host cores (sub-problems are independent) ----------------
+def _oracle_job(args):
+    model, k, x, times, T_f, ranges = args
+    from oracle import exact as OE
+    f, df, n_pairs = OE.exact_sums_windowed(model, k, x, times, T_f, ranges=ranges)
+    return {'k/%s' % label: val for label, val in iter_sum_entries(f, df)}, n_pairs
+
+
+def oracle_sums_parallel(model, ks, xs, times, T_f, ranges=None, n_proc=None):
+    """[(reference dict for assert_sums_close, n_pairs)] of ``OE.exact_sums_windowed`` for the
+    sub-problems ``ks``, one forked process each (the children only run numpy: they never touch
+    the parent's CUDA context)."""
+    import multiprocessing as mp
+    jobs = [(model, k, np.asarray(x), times, T_f, ranges) for k, x in zip(ks, xs)]
+    n_proc = n_proc or max(1, min(len(jobs), os.cpu_count() or 1))
+    if n_proc == 1:
+        return [_oracle_job(j) for j in jobs]
+    with mp.get_context('fork').Pool(n_proc) as pool:
+        return pool.map(_oracle_job, jobs)

@@ -209,6 +209,28 @@ class OracleEngine:
             buf[q * stride:q * stride + len(packed)] = packed
         self._raw_used = n
 
+    def exact_packed_len_batch(self, ks):
+        return sum(term_layout(self.desc, k)[1] for k in ks)
+
+    def exact_packed_device_batch(self, ks, xs, packed_ptr, compute_f_sum=True, compute_diff_f_sum=True,
+                                  ranges=None):
+        import ctypes
+        n = self.exact_packed_len_batch(ks)
+        buf = np.ctypeslib.as_array((ctypes.c_double * n).from_address(packed_ptr))
+        pos = 0
+        for k, x in zip(ks, xs):
+            packed = self.exact_sums_packed(k, x, compute_f_sum, compute_diff_f_sum, ranges=ranges)
+            buf[pos:pos + len(packed)] = packed
+            pos += len(packed)
+
+    def split_packed(self, ks, packed):
+        out, pos = [], 0
+        for k in ks:
+            n = term_layout(self.desc, k)[1]
+            out.append(np.array(packed[pos:pos + n], dtype=float))
+            pos += n
+        return out
+
     def exact_assemble_batch(self, ks, xs, raw_host, compute_f_sum=True, compute_diff_f_sum=True):
         stride = len(raw_host) // len(ks)
         return [np.array(raw_host[q * stride:q * stride + term_layout(self.desc, k)[1]], dtype=float)

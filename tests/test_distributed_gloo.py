@@ -47,8 +47,43 @@ def _worker(rank, world, port, times, T_f, name, out_dir):
     sliced = sharded.packed_batch([0, 1], case_x(name))
     np.save(os.path.join(out_dir, 'sliced%d.npy' % rank), np.concatenate(sliced))
     np.save(os.path.join(out_dir, 'held%d.npy' % rank), np.array([len(t) for t in engine.times]))
+    # a parameter update that widens the kernels' reach beyond the uploaded halo (exponential
+    # kernels with free decay rates): the launch re-slices instead of silently dropping sources
+    engine2 = OracleEngine()
+    engine2.bind(types.SimpleNamespace(list_times=times, T_f=T_f), CASES[WIDE_CASE][0])
+    sharded2 = ShardedExactSums(engine2, times, rank=rank, world_size=world, dist=dist,
+                                device=torch.device('cpu'))
+    sharded2.set_events(times, T_f, [0, 1], case_x(WIDE_CASE), slack=1.0)
+    lag_before = sharded2.max_lag
+    again = sharded2.packed_batch([0, 1], _wide_x(WIDE_CASE))
+    assert sharded2.max_lag > lag_before
+    np.save(os.path.join(out_dir, 'wide%d.npy' % rank), np.concatenate(again))
     dist.barrier()
     dist.destroy_process_group()
+
+
+WIDE_CASE = 'exp2d'
+
+
+def _wide_x(name):
+    """Evaluation point of ``name`` with every free kernel parameter but omega (first of each basis)
+    scaled so that the lag windows grow by ~60 %."""
+    from oracle import exact as OE
+    from oracle import functionals as F
+    model = CASES[name][0]
+    out = []
+    for k, x in enumerate(case_x(name)):
+        x = np.array(x, dtype=float)
+        for i, (a, b) in enumerate(OE.interval_map(model, k)):
+            pos = a
+            for basis in model['kernels'][k][i]:
+                free = [v for v in range(2 if basis['type'] == 'exp' else 3) if v not in basis.get('fixed', {})]
+                for v in free:
+                    if v == 1:      # beta: decay rate (exp) or width (gauss)
+                        x[pos] = x[pos] / 1.6 if basis['type'] == 'exp' else x[pos] * 1.6
+                    pos += 1
+        out.append(x)
+    return out
 
 
 def test_time_block_ranges_partition_the_events():
@@ -94,6 +129,11 @@ def test_two_rank_shards_allreduce_to_the_full_sums(tmp_path):
     np.testing.assert_allclose(batch, want_all, rtol=1e-12, atol=1e-13)
     sliced = np.load(os.path.join(tmp_path, 'sliced1.npy'))
     np.testing.assert_allclose(sliced, want_all, rtol=1e-12, atol=1e-13)
+    wide = np.load(os.path.join(tmp_path, 'wide1.npy'))
+    full2 = OracleEngine()
+    full2.bind(types.SimpleNamespace(list_times=times, T_f=T_f), CASES[WIDE_CASE][0])
+    want_wide = np.concatenate([full2.exact_sums_packed(k, _wide_x(WIDE_CASE)[k]) for k in range(2)])
+    np.testing.assert_allclose(wide, want_wide, rtol=1e-12, atol=1e-13)
     held = [np.load(os.path.join(tmp_path, 'held%d.npy' % r)) for r in range(2)]
     # rank 1 holds its half plus a halo, not the whole path
     assert np.all(held[1] < np.array([700, 500])) and np.all(held[0] < np.array([700, 500]))

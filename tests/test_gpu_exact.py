@@ -506,3 +506,84 @@ def test_named_configurations_at_full_size(engine, name):
         strat.initialize(0, 40, mirror, path)
         g = np.mean([strat.lse_k_grad_estimate(xs[0], rng=rng, grad_alloc=False) for _ in range(40)], axis=0)
         assert np.linalg.norm(g - g_exact) <= 0.25 * np.linalg.norm(g_exact)
+
+
+@pytest.fixture(scope='module')
+def c5_short():
+    """The benchmark's own model (10 event types, every kernel a sum of 10 Gaussians with fixed
+    shapes: 1 111 packed sums per sub-problem) on a path short enough for the oracle, with the
+    oracle's sums of every sub-problem (one host process each)."""
+    from aslsd_b200 import simulate
+    from helpers import oracle_sums_parallel
+    model, times, T_f, xs = simulate.config_c5(d=10, n_basis=10, T_f=700., seed=1234)
+    ref = oracle_sums_parallel(model, list(range(10)), xs, times, T_f)
+    return model, times, T_f, xs, ref
+
+
+def test_c5_model_matches_oracle_every_k(engine, c5_short):
+    """Device against the oracle on the 10-type benchmark model, every sub-problem, every term and
+    derivative at 1e-10 (mhp_exact_estimator.py:611-707): the single-k call, the batched call the
+    benchmark times (rows shared between the sub-problems) and time-block shards."""
+    from aslsd_b200.distributed import time_block_ranges
+    from aslsd_b200.engine import unpack_terms
+    model, times, T_f, xs, ref = c5_short
+    d = model['d']
+    engine.set_events(times, T_f)
+    engine.set_model(model)
+    ks = list(range(d))
+    batch = engine.exact_sums_batch(ks, xs)
+    work = engine.last_work_counts()
+    assert work['moment_pairs'] > 0 and work['rows'] == 11440    # the quadrature path, C5's row table
+    # the second call on the same row plan assembles on the device (linear map of the raw rows,
+    # exact.cu assemble_kernel) and reads back the packed sums only; the first one did it on the host
+    again = engine.exact_sums_batch(ks, xs)
+    for a, b in zip(batch, again):
+        np.testing.assert_allclose(b, a, rtol=1e-13, atol=1e-13 * np.abs(a).max())
+    import torch
+    dev = torch.zeros(engine.exact_packed_len_batch(ks), dtype=torch.float64, device='cuda:0')
+    engine.exact_packed_device_batch(ks, xs, dev.data_ptr())
+    engine.synchronize()
+    for a, b in zip(batch, engine.split_packed(ks, dev.cpu().numpy())):
+        np.testing.assert_allclose(b, a, rtol=1e-13, atol=1e-13 * np.abs(a).max())
+    try:
+        engine.use_device_assembly(False)
+        host = engine.exact_sums_batch(ks, xs)
+    finally:
+        engine.use_device_assembly(True)
+    for a, b in zip(batch, host):
+        np.testing.assert_array_equal(a, b)
+    blocks = time_block_ranges(times, 2)
+    for k in ks:
+        f, df = unpack_terms(engine.desc, k, again[k])
+        assert_sums_close(f, df, ref[k][0], 'k', rtol=RTOL)
+        f, df = unpack_terms(engine.desc, k, batch[k])
+        assert_sums_close(f, df, ref[k][0], 'k', rtol=RTOL)
+        f, df = engine.exact_sums(k, xs[k])
+        assert_sums_close(f, df, ref[k][0], 'k', rtol=RTOL)
+    for k in (0, 7):
+        acc = sum(engine.exact_sums_packed(k, xs[k], ranges=b) for b in blocks)
+        f, df = unpack_terms(engine.desc, k, acc)
+        assert_sums_close(f, df, ref[k][0], 'k', rtol=RTOL, atol=1e-13)
+    # the per-item kernels on the same model (no quadrature)
+    try:
+        engine.use_lag_quadrature(False)
+        f, df = engine.exact_sums(4, xs[4])
+    finally:
+        engine.use_lag_quadrature(True)
+    assert_sums_close(f, df, ref[4][0], 'k', rtol=RTOL)
+
+
+def test_c5_model_slice_matches_oracle(engine, c5_short):
+    """The parity gate of bench.py: targets of a time slice of sub-problem 0."""
+    from helpers import oracle_sums_parallel
+    from aslsd_b200.engine import unpack_terms
+    model, times, T_f, xs, _ = c5_short
+    engine.set_events(times, T_f)
+    engine.set_model(model)
+    ranges = [(int(np.searchsorted(t, 100.)), int(np.searchsorted(t, 450.))) for t in times]
+    (ref, n_pairs), = oracle_sums_parallel(model, [0], [xs[0]], times, T_f, ranges=ranges, n_proc=1)
+    packed, counts = engine.exact_sums_packed(0, xs[0], ranges=ranges, count_pairs=True)
+    f, df = unpack_terms(engine.desc, 0, packed)
+    assert_sums_close(f, df, ref, 'k', rtol=RTOL)
+    for name, n in n_pairs.items():
+        assert counts[name] == n, name
