@@ -71,10 +71,10 @@ struct BatchPlan {
   int uses = 0;                                 // calls served by this row plan
 };
 
-// One term of the assembly map: out += w[o] * ((w[a] * w[b] * g) * raw[raw_ix])
+// One term of the assembly map: out += w[o] * ((((w[a] * w[b]) * g) / gd) * raw[raw_ix])
 struct AsmEntry {
   int32_t raw_ix, a, b, o;
-  double g;
+  double g, gd;
 };
 
 static ItemDev canonical(const ItemDev& it) {
@@ -740,25 +740,31 @@ static void assemble_all(const aslsd_ctx* ctx, const BatchPlan& B, int n_k, cons
 // ---- assembly on the device -----------------------------------------------------------------
 // The map is linear in the raw rows with coefficients that are products of at most two omegas
 // (and mu_k) times a function of the non-omega variables: its structure is extracted once per row
-// plan (emit_term_w<SymW>), the omegas travel as a small table per call.  One warp per packed sum,
-// lanes striding over its entries, fixed order: deterministic.
-#define ASM_NT 256
+// plan (emit_term_w<SymW>), the omegas travel as a small table per call.  One thread per packed
+// sum walks its entries in emission order with the host's operations (no contraction into fused
+// multiply-adds): bit for bit the packed sums of the host assembly.
+#define ASM_NT 64
+__device__ __forceinline__ double asm_term(const AsmEntry& E, const double* __restrict__ wtab,
+                                           const double* __restrict__ raw) {
+  const double coef = __ddiv_rn(__dmul_rn(__dmul_rn(wtab[E.a], wtab[E.b]), E.g), E.gd);
+  return __dmul_rn(wtab[E.o], __dmul_rn(coef, raw[E.raw_ix]));
+}
 __global__ void __launch_bounds__(ASM_NT)
 assemble_kernel(const int64_t* __restrict__ ptr, const AsmEntry* __restrict__ entries,
                 const double* __restrict__ wtab, const double* __restrict__ raw, double* __restrict__ out,
                 int64_t n_out) {
-  const int lane = threadIdx.x & 31;
-  const int64_t o = ((int64_t)blockIdx.x * ASM_NT + threadIdx.x) >> 5;
+  const int64_t o = (int64_t)blockIdx.x * ASM_NT + threadIdx.x;
   if (o >= n_out) return;
   double acc = 0.;
-  for (int64_t e = ptr[o] + lane; e < ptr[o + 1]; e += 32) {
-    const AsmEntry E = entries[e];
-    const double coef = (wtab[E.a] * wtab[E.b]) * E.g;
-    acc += wtab[E.o] * (coef * raw[E.raw_ix]);
+  int64_t e = ptr[o];
+  const int64_t e1 = ptr[o + 1];
+  for (; e + 4 <= e1; e += 4) {   // the four terms are independent of the running sum
+    const double v0 = asm_term(entries[e], wtab, raw), v1 = asm_term(entries[e + 1], wtab, raw);
+    const double v2 = asm_term(entries[e + 2], wtab, raw), v3 = asm_term(entries[e + 3], wtab, raw);
+    acc = __dadd_rn(__dadd_rn(__dadd_rn(__dadd_rn(acc, v0), v1), v2), v3);
   }
-#pragma unroll
-  for (int s = 16; s > 0; s >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, s);
-  if (lane == 0) out[o] = acc;
+  for (; e < e1; ++e) acc = __dadd_rn(acc, asm_term(entries[e], wtab, raw));
+  out[o] = acc;
 }
 
 // omega table of sub-problem q: [0] = 1, [1] = mu_k, then the omegas of K[k][i] read with its own
@@ -809,6 +815,7 @@ static int build_assembly_host(aslsd_ctx* ctx, BatchPlan& B, std::vector<int64_t
                           x.e.b = base + coef.b;
                           x.e.o = base + outer.a;
                           x.e.g = coef.g * outer.g;
+                          x.e.gd = coef.gd * outer.gd;
                           tmp.push_back(x);
                           count[(size_t)x.out + 1]++;
                         });
@@ -873,9 +880,8 @@ static int assemble_device(aslsd_ctx* ctx, BatchPlan& B, int n_k, const double* 
   CUDA_TRY(ctx, cudaEventRecord(ctx->ev_wtab[ctx->wtab_flip], ctx->stream));
   ctx->wtab_in_flight[ctx->wtab_flip] = true;
   ctx->wtab_flip ^= 1;
-  const int64_t n_thr = B.out_total * 32;
   if (B.out_total > 0) {
-    assemble_kernel<<<(unsigned)((n_thr + ASM_NT - 1) / ASM_NT), ASM_NT, 0, ctx->stream>>>(
+    assemble_kernel<<<(unsigned)((B.out_total + ASM_NT - 1) / ASM_NT), ASM_NT, 0, ctx->stream>>>(
         ctx->d_asm_ptr, (const AsmEntry*)ctx->d_asm, ctx->d_wtab, raw_device, packed_device, B.out_total);
     ctx->last_launches++;
   }
@@ -1147,15 +1153,13 @@ extern "C" int aslsd_exact_assemble_map_batch(aslsd_ctx* ctx, int n_k, const int
   for (int q = 0; q < n_k; ++q)
     for (int64_t c = 0; c < B.plans[q].out_len; ++c) {
       const int64_t o = B.out_off[q] + c;
-      double lanes[32] = {0.};
+      double acc = 0.;
       for (int64_t e = ptr[o]; e < ptr[o + 1]; ++e) {
         const AsmEntry& E = entries[(size_t)e];
-        const double coef = (w[E.a] * w[E.b]) * E.g;
-        lanes[(e - ptr[o]) & 31] += w[E.o] * (coef * raw_host[E.raw_ix]);
+        const double coef = ((w[E.a] * w[E.b]) * E.g) / E.gd;
+        acc += w[E.o] * (coef * raw_host[E.raw_ix]);
       }
-      for (int s = 16; s > 0; s >>= 1)
-        for (int l = 0; l < s; ++l) lanes[l] += lanes[l + s];
-      outs[q][c] = lanes[0];
+      outs[q][c] = acc;
     }
   return ASLSD_OK;
 }

@@ -48,13 +48,13 @@ void plan_shape_key(const aslsd_ctx* ctx, int k, const double* x_k, std::vector<
 // Index of a named term in SumPlan::terms (-1 if absent).
 int find_term(const aslsd_ctx* ctx, int kind, int i, int j);
 
-// Symbolic omega factor: coefficient = g x w[a] x w[b], with a, b indices into a per-sub-problem
-// table of the omega values (0 = the constant one) and g a function of the non-omega variables
-// only.  emit_term_w instantiated with it yields the structure of the linear map once per plan;
+// Symbolic omega factor: coefficient = ((w[a] x w[b]) x g) / gd, with a, b indices into a
+// per-sub-problem table of the omega values (0 = the constant one) and g, gd functions of the
+// non-omega variables only (the divisor is kept apart so that w / beta rounds as in emit_term<double>).  emit_term_w instantiated with it yields the structure of the linear map once per plan;
 // the device assembly (exact.cu) then evaluates the coefficients from the table of every call.
 struct SymW {
   int32_t a = 0, b = 0;
-  double g = 1.;
+  double g = 1., gd = 1.;
   SymW() {}
   SymW(double v) : g(v) {}
   SymW(int32_t ix, double v) : a(ix), g(v) {}
@@ -62,6 +62,7 @@ struct SymW {
 inline SymW operator*(const SymW& x, const SymW& y) {
   SymW r;
   r.g = x.g * y.g;
+  r.gd = x.gd * y.gd;
   const int32_t idx[4] = {x.a, x.b, y.a, y.b};
   int n = 0;
   for (int q = 0; q < 4; ++q)
@@ -75,7 +76,7 @@ inline SymW operator*(const SymW& x, const SymW& y) {
 }
 inline SymW operator*(const SymW& x, double s) { SymW r = x; r.g = x.g * s; return r; }
 inline SymW operator*(double s, const SymW& x) { return x * s; }
-inline SymW operator/(const SymW& x, double s) { SymW r = x; r.g = x.g / s; return r; }
+inline SymW operator/(const SymW& x, double s) { SymW r = x; r.gd = x.gd * s; return r; }
 inline SymW operator-(const SymW& x) { SymW r = x; r.g = -x.g; return r; }
 
 // Linear map raw components -> packed outputs of one term.  The sink is called

@@ -284,10 +284,11 @@ def check(name, engine, with_derivatives):
         raw[r] = row_components(meta[r], par[r], times, T_f, with_derivatives)
     packed = engine.exact_assemble_batch(ks, xs, raw.ravel(), True, with_derivatives)
     # the linear map of the device assembly (CSR table of symbolic omega factors + omega tables,
-    # exact.cu build_assembly_host) applied on the host: same packed sums as the host assembly
+    # exact.cu build_assembly_host) applied on the host in the kernel's order of operations: bit for
+    # bit the packed sums of the host assembly
     mapped = engine.exact_assemble_map_batch(ks, xs, raw.ravel(), True, with_derivatives)
     for a, b in zip(packed, mapped):
-        np.testing.assert_allclose(b, a, rtol=1e-13, atol=1e-13 * np.abs(a).max(), err_msg=name + ' device map')
+        np.testing.assert_array_equal(b, a, err_msg=name + ' device map')
     worst = 0.
     for k in ks:
         sum_f, sum_diff_f = unpack_terms(engine.desc, k, packed[k])
