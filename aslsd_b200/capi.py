@@ -43,7 +43,7 @@ class Pcg64(ctypes.Structure):
 
 class SampleTerm(ctypes.Structure):
     _fields_ = [('kind', ctypes.c_int32), ('i', ctypes.c_int32), ('j', ctypes.c_int32),
-                ('n_strata', ctypes.c_int32)]
+                ('n_strata', ctypes.c_int32), ('sat_t', ctypes.c_double), ('v_sat', ctypes.c_double)]
 
 
 # every symbol declared in include/aslsd_b200.h: name -> (restype, argtypes)

@@ -172,15 +172,20 @@ struct aslsd_ctx {
   // target block and the non-omega parameters stay the same (plans hold no results)
   void* plan_cache = nullptr;
   void (*plan_cache_free)(void*) = nullptr;
-  // device assembly of the packed sums (exact.cu): CSR map of the cached plan, omega tables, result
-  void* d_asm = nullptr; size_t asm_cap = 0;
-  int64_t* d_asm_ptr = nullptr; size_t asm_ptr_cap = 0;
+  // index maps (index_maps.cu): pair table, lag counts and the three tables, kept between calls
+  void* d_im_pairs = nullptr; size_t im_pairs_cap = 0;
+  int64_t* d_im_H = nullptr; size_t im_H_cap = 0;
+  int64_t* d_im_kappa = nullptr; size_t im_kappa_cap = 0;
+  int64_t* d_im_varpi = nullptr; size_t im_varpi_cap = 0;
+  int64_t* d_im_lags = nullptr; size_t im_lags_cap = 0;
+  // device assembly of the packed sums (exact.cu; the CSR maps belong to the plans): omega tables, result
   double* d_wtab = nullptr; size_t wtab_cap = 0;
   double* h_wtab = nullptr; size_t h_wtab_cap = 0;     // page-locked, two halves used in turn
   int wtab_flip = 0;
   bool wtab_in_flight[2] = {false, false};
   cudaEvent_t ev_wtab[2] = {nullptr, nullptr};
-  const void* asm_owner = nullptr;                     // the plan whose map is in d_asm
+  const void* tables_owner = nullptr;                  // the plan whose item / stream tables are on the device
+  int64_t tables_owner_uid = 0, plan_uid = 0;
   double* d_packed = nullptr; size_t packed_cap = 0;
   bool device_assembly = true;                         // ASLSD_OPT_DEVICE_ASSEMBLY
   int64_t model_epoch = 0;    // bumped by set_model / set_option

@@ -90,8 +90,11 @@ extern "C" int aslsd_destroy(aslsd_ctx* ctx) {
   if (ctx->h_flag) cudaFreeHost(ctx->h_flag);
   if (ctx->h_tables) cudaFreeHost(ctx->h_tables);
   cudaEventDestroy(ctx->ev_tables);
-  cudaFree(ctx->d_asm);
-  cudaFree(ctx->d_asm_ptr);
+  cudaFree(ctx->d_im_pairs);
+  cudaFree(ctx->d_im_H);
+  cudaFree(ctx->d_im_kappa);
+  cudaFree(ctx->d_im_varpi);
+  cudaFree(ctx->d_im_lags);
   cudaFree(ctx->d_wtab);
   cudaFree(ctx->d_packed);
   if (ctx->h_wtab) cudaFreeHost(ctx->h_wtab);

@@ -57,19 +57,37 @@ struct BatchPlan {
   int qfam_first[ITEM_N_FAMILIES], qfam_count[ITEM_N_FAMILIES];
   std::vector<BoundaryGroupDev> bgroups;        // targets near T_f of the quadrature rows, by family
   int bfam_first[ITEM_N_FAMILIES], bfam_count[ITEM_N_FAMILIES];
-  int64_t n_wu_q = 0, n_wu_q_plain = 0, n_q_partials = 0, n_q_weights = 0, n_q_evals = 0;
+  int64_t n_wu_q = 0, n_q_partials = 0, n_q_weights = 0, n_q_evals = 0;
+  // streams are ordered by category - unweighted streams of the small CTA shape, unweighted streams
+  // of the big one, weighted streams - and each category is one launch over its work units
+  int64_t q_cat_wu[4] = {0, 0, 0, 0};           // first work unit of every category (prefix)
+  size_t q_cat_smem[3] = {0, 0, 0};
   // scratch of build_work, kept between calls (no reallocation when only the events change)
   std::vector<ItemDev> scratch_q[ITEM_N_FAMILIES], scratch_f[ITEM_N_FAMILIES];
   int q_jmax = 0;
-  size_t q_smem = 0;
   // device assembly (raw rows -> packed sums): the linear map in CSR form, built once per row plan
   std::vector<int64_t> out_off;                 // per sub-problem: offset in the concatenated packed sums
   int64_t out_total = 0;
   int w_stride = 0;                             // omega table entries per sub-problem
-  bool asm_built = false, asm_resident = false;
+  bool asm_built = false;
   int64_t asm_entries = 0;
+  void* d_asm = nullptr;                        // AsmEntry[asm_entries], owned by the plan
+  int64_t* d_asm_ptr = nullptr;                 // out_total + 1 row starts
   int uses = 0;                                 // calls served by this row plan
+  int64_t uid = 0;                              // distinguishes a plan from an earlier one at the same address
+  ~BatchPlan() {
+    if (d_asm) cudaFree(d_asm);
+    if (d_asm_ptr) cudaFree(d_asm_ptr);
+  }
 };
+
+// The last few batch plans, most recent first (one per sub-problem when a fit loop takes the
+// sub-problems in turn, plus the batched one).
+struct PlanCache {
+  std::vector<BatchPlan*> plans;
+  ~PlanCache() { for (auto* p : plans) delete p; }
+};
+#define PLAN_CACHE_MAX 24
 
 // One term of the assembly map: out += w[o] * ((((w[a] * w[b]) * g) / gd) * raw[raw_ix])
 struct AsmEntry {
@@ -137,8 +155,8 @@ static void build_stream(const aslsd_ctx* ctx, BatchPlan& B, const std::vector<i
     scale = std::min(scale, row_scale(it));
   }
   if (!(scale > 0.) || !(s_max > 0.) || !std::isfinite(s_max) || !std::isfinite(t_int)) return;
-  // the moment kernel counts the pairs of a tile (LQ_TM targets x their windows) in 32 bits: a
-  // reach that could hold ~2^31 / LQ_TM sources per target (16 x the mean density as margin for
+  // the moment kernel counts the pairs of a tile (at most 512 targets x their windows) in 32 bits: a
+  // reach that could hold ~2^31 / 512 sources per target (16 x the mean density as margin for
   // clustering) stays with the per-item kernels, which count in 64 bits
   {
     const int64_t n_src = ctx->n_events[first.src_dim];
@@ -146,10 +164,10 @@ static void build_stream(const aslsd_ctx* ctx, BatchPlan& B, const std::vector<i
     const double span = n_src > 1 ? ts[n_src - 1] - ts[0] : 0.;
     const double per_target = span > 0. ? std::min<double>((double)n_src, 16. * (double)n_src * s_max / span)
                                         : (double)n_src;
-    if (per_target * (double)LQ_TM >= 2.0e9) return;
+    if (per_target * (double)LqBig::TM >= 2.0e9) return;
   }
   const int64_t m_b = interior_end(ctx, first.tgt_dim, first.m_lo, first.m_hi, t_int);
-  if (m_b - first.m_lo < LQ_TM / 2) return;   // the per-item kernels take it all
+  if (m_b - first.m_lo < LqBig::TM / 2) return;   // the per-item kernels take it all
   // bins [j h, (j + 1) h) up to s_max plus a spare one (a lag can exceed s_max by a rounding
   // error); the count is rounded up to a multiple of 32 - the moment kernel hands bins to
   // groups of lanes in rounds of 64 - and the bins shrink accordingly
@@ -159,7 +177,9 @@ static void build_stream(const aslsd_ctx* ctx, BatchPlan& B, const std::vector<i
   nb = std::min<double>(LQ_JMAX, 32. * std::ceil(nb / 32.));
   const double h = s_max / (nb - 1.5);
   const bool weighted = first.wa_off >= 0 || first.wb_off >= 0;
-  const int ucap = lq_pick_ucap((int)nb, weighted);
+  // CTA shape: the small one where every pair of its lanes can own a bin for a whole work unit
+  const bool small = !weighted && nb <= (double)LqSmall::ONE_BIN_J;
+  const int ucap = small ? lq_pick_ucap<LqSmall>((int)nb, false) : lq_pick_ucap<LqBig>((int)nb, weighted);
   if (ucap == 0) return;
   QStreamDev S;
   std::memset(&S, 0, sizeof(S));
@@ -168,6 +188,7 @@ static void build_stream(const aslsd_ctx* ctx, BatchPlan& B, const std::vector<i
   S.same = first.same;
   S.J = (int32_t)nb;
   S.ucap = ucap;
+  S.shape = small ? LQ_SHAPE_SMALL : LQ_SHAPE_BIG;
   S.wa_off = first.wa_off;
   S.wb_off = first.wb_off;
   while ((1 << S.nbits) < S.J) ++S.nbits;
@@ -179,7 +200,11 @@ static void build_stream(const aslsd_ctx* ctx, BatchPlan& B, const std::vector<i
   const int sx = (int)B.qstreams.size();
   B.qstreams.push_back(S);
   B.q_jmax = std::max(B.q_jmax, (int)S.J);
-  B.q_smem = std::max(B.q_smem, lq_smem_bytes(S.J, S.ucap, weighted));
+  {
+    const int cat = weighted ? 2 : (small ? 0 : 1);
+    const size_t bytes = small ? lq_smem_bytes<LqSmall>(S.J, S.ucap, false) : lq_smem_bytes<LqBig>(S.J, S.ucap, weighted);
+    B.q_cat_smem[cat] = std::max(B.q_cat_smem[cat], bytes);
+  }
   for (int64_t r : group) {
     ItemDev it = B.rows[r];
     it.dst_row = r;
@@ -234,7 +259,7 @@ static int build_work(aslsd_ctx* ctx, const int64_t* m_lo, const int64_t* m_hi, 
   B.bgroups.clear();
   B.n_wu = B.n_wu_q = B.n_q_partials = B.n_q_weights = B.n_q_evals = 0;
   B.q_jmax = 0;
-  B.q_smem = 0;
+  for (int c = 0; c < 3; ++c) B.q_cat_smem[c] = 0;
   B.device_resident = false;
   B.weights_valid = false;
   const int d = ctx->d;
@@ -274,6 +299,22 @@ static int build_work(aslsd_ctx* ctx, const int64_t* m_lo, const int64_t* m_hi, 
       for (auto& key : order)
         if ((key[4] >= 0 || key[5] >= 0) == (pass == 1))
           build_stream(ctx, B, groups[key], fast, boundary_from, qfam);
+    // order the streams by category (stable) and renumber the rows' stream index
+    auto category = [](const QStreamDev& S) {
+      return (S.wa_off >= 0 || S.wb_off >= 0) ? 2 : (S.shape == LQ_SHAPE_SMALL ? 0 : 1);
+    };
+    std::vector<int> perm(B.qstreams.size()), new_ix(B.qstreams.size());
+    for (size_t x = 0; x < perm.size(); ++x) perm[x] = (int)x;
+    std::stable_sort(perm.begin(), perm.end(),
+                     [&](int a, int b) { return category(B.qstreams[a]) < category(B.qstreams[b]); });
+    std::vector<QStreamDev> sorted(B.qstreams.size());
+    for (size_t x = 0; x < perm.size(); ++x) {
+      sorted[x] = B.qstreams[perm[x]];
+      new_ix[perm[x]] = (int)x;
+    }
+    B.qstreams.swap(sorted);
+    for (int f = 0; f < ITEM_N_FAMILIES; ++f)
+      for (auto& it : qfam[f]) it.wu_first = new_ix[(size_t)it.wu_first];
   }
   for (int f = 0; f < ITEM_N_FAMILIES; ++f) {
     B.qfam_first[f] = (int)B.qrows.size();
@@ -348,15 +389,30 @@ static int build_work(aslsd_ctx* ctx, const int64_t* m_lo, const int64_t* m_hi, 
   }
   B.n_wu = wu;
   // ---- quadrature streams: work units of whole tiles, a few waves over the 148 SMs ----------
-  int64_t tot = 0;
-  for (auto& S : B.qstreams) tot += S.m_hi - S.m_lo;
-  int64_t tpw = (tot + 148 * 2 * 6 - 1) / (148 * 2 * 6);
-  tpw = std::max<int64_t>(LQ_TM, std::min<int64_t>(tpw, 64 * LQ_TM));
-  tpw = ((tpw + LQ_TM - 1) / LQ_TM) * LQ_TM;
+  // (per category: the streams of one launch share the size of their work units)
+  auto category = [](const QStreamDev& S) {
+    return (S.wa_off >= 0 || S.wb_off >= 0) ? 2 : (S.shape == LQ_SHAPE_SMALL ? 0 : 1);
+  };
+  int64_t tot[3] = {0, 0, 0}, tpw_cat[3];
+  for (auto& S : B.qstreams) tot[category(S)] += S.m_hi - S.m_lo;
+  for (int c = 0; c < 3; ++c) {
+    const int64_t tm = c == 0 ? LqSmall::TM : LqBig::TM;
+    // (small CTAs: ~32 work units per resident CTA measured best on the C5 step, 10.42 ms against
+    // 11.04 ms with 1.5 - 4 per CTA and 10.51 ms with 83: gpurun_out / profiles r2_g_units)
+    int64_t units = c == 0 ? 148 * LqSmall::CTAS * 32 : 148 * 2 * 6;
+    if (const char* e = std::getenv("ASLSD_LQ_UNITS")) units = std::max<int64_t>(1, std::atoll(e));   // tuning
+    int64_t tpw = (tot[c] + units - 1) / units;
+    tpw = std::max<int64_t>(tm, std::min<int64_t>(tpw, 64 * LqBig::TM));
+    tpw_cat[c] = ((tpw + tm - 1) / tm) * tm;
+  }
   int64_t qwu = 0, part = 0, wts = 0;
+  int cat_seen = 0;
+  B.q_cat_wu[0] = 0;
   for (auto& S : B.qstreams) {
-    S.tpw = tpw;
-    S.n_chunks = (int32_t)((S.m_hi - S.m_lo + tpw - 1) / tpw);
+    const int c = category(S);
+    while (cat_seen < c) B.q_cat_wu[++cat_seen] = qwu;
+    S.tpw = tpw_cat[c];
+    S.n_chunks = (int32_t)((S.m_hi - S.m_lo + S.tpw - 1) / S.tpw);
     S.wu_first = qwu;
     S.part_first = part;
     S.w_first = wts;
@@ -364,10 +420,8 @@ static int build_work(aslsd_ctx* ctx, const int64_t* m_lo, const int64_t* m_hi, 
     part += (int64_t)S.n_chunks * S.J * LQ_ND;
     wts += (int64_t)S.J * LQ_ND;
   }
+  while (cat_seen < 3) B.q_cat_wu[++cat_seen] = qwu;
   B.n_wu_q = qwu;
-  B.n_wu_q_plain = qwu;
-  for (auto& S : B.qstreams)
-    if (S.wa_off >= 0 || S.wb_off >= 0) { B.n_wu_q_plain = S.wu_first; break; }
   B.n_q_partials = part;
   B.n_q_weights = wts;
   if (B.n_wu >= (int64_t)2147483647 || qwu >= (int64_t)2147483647)
@@ -379,7 +433,7 @@ static int build_work(aslsd_ctx* ctx, const int64_t* m_lo, const int64_t* m_hi, 
 // non-omega parameters); its work part also of (events, target block, options).  Each part is
 // rebuilt only when its inputs change, and the omega-dependent variables are refreshed on
 // every call.  No result is cached - every call launches all of its kernels.
-static void free_batch(void* p) { delete (BatchPlan*)p; }
+static void free_batch(void* p) { delete (PlanCache*)p; }
 
 static int get_batch(aslsd_ctx* ctx, int n_k, const int* ks, const double* const* xs, int flags,
                      const int64_t* m_lo, const int64_t* m_hi, bool with_work, BatchPlan** out) {
@@ -403,18 +457,41 @@ static int get_batch(aslsd_ctx* ctx, int n_k, const int* ks, const double* const
     key_work.push_back(m_lo ? (double)m_lo[i] : -1.);
     key_work.push_back(m_hi ? (double)m_hi[i] : -1.);
   }
-  BatchPlan* C = (BatchPlan*)ctx->plan_cache;
+  if (!ctx->plan_cache) {
+    ctx->plan_cache = new PlanCache();
+    ctx->plan_cache_free = free_batch;
+  }
+  PlanCache& cache = *(PlanCache*)ctx->plan_cache;
+  // plans of an earlier model epoch can never match again (set_model, set_option, weighted calls)
+  for (size_t x = 0; x < cache.plans.size();)
+    if (cache.plans[x]->key_rows[0] != (double)ctx->model_epoch) {
+      delete cache.plans[x];
+      cache.plans.erase(cache.plans.begin() + x);
+    } else {
+      ++x;
+    }
+  BatchPlan* C = nullptr;
+  for (size_t x = 0; x < cache.plans.size(); ++x)
+    if (cache.plans[x]->key_rows == key_rows) {
+      C = cache.plans[x];
+      cache.plans.erase(cache.plans.begin() + x);
+      cache.plans.insert(cache.plans.begin(), C);
+      break;
+    }
   int rc;
-  if (C && C->key_rows == key_rows) {
+  if (C) {
     for (int q = 0; q < n_k; ++q)
       if ((rc = plan_vars(ctx, ks[q], xs[q], C->plans[q]))) return rc;
   } else {
     BatchPlan* B = new BatchPlan();
+    B->uid = ++ctx->plan_uid;
     if ((rc = build_rows(ctx, n_k, ks, xs, flags, *B))) { delete B; return rc; }
     B->key_rows.swap(key_rows);
-    if (ctx->plan_cache) free_batch(ctx->plan_cache);
-    ctx->plan_cache = C = B;
-    ctx->plan_cache_free = free_batch;
+    cache.plans.insert(cache.plans.begin(), C = B);
+    while (cache.plans.size() > PLAN_CACHE_MAX) {
+      delete cache.plans.back();
+      cache.plans.pop_back();
+    }
   }
   if (with_work && !(C->has_work && C->key_work == key_work)) {
     C->has_work = false;
@@ -546,8 +623,9 @@ static int run_batch_impl(aslsd_ctx* ctx, BatchPlan& B, double* raw_device) {
     const double* before = ctx->d_q_weights;
     if ((rc = ensure_device_buffer(ctx, (void**)&ctx->d_q_weights, &ctx->q_weights_cap,
                                    (size_t)B.n_q_weights * sizeof(double)))) return rc;
-    if (ctx->d_q_weights != before) { ctx->w_streams.clear(); B.weights_valid = false; }
+    if (ctx->d_q_weights != before) ctx->w_streams.clear();
   }
+  if (ctx->tables_owner != (const void*)&B || ctx->tables_owner_uid != B.uid) B.device_resident = false;
   if (!B.device_resident && (n_items || quad)) {
     // all plan tables go through one page-locked block of their own and two asynchronous
     // transfers: no wait for the stream here (an event upload may still be in flight on it)
@@ -581,6 +659,8 @@ static int run_batch_impl(aslsd_ctx* ctx, BatchPlan& B, double* raw_device) {
     ctx->tables_in_flight = true;
   }
   B.device_resident = true;
+  ctx->tables_owner = &B;
+  ctx->tables_owner_uid = B.uid;
   const ItemDev* d_items = (const ItemDev*)ctx->d_items;
   const QStreamDev* d_streams = (const QStreamDev*)((const char*)ctx->d_qtab + o_s);
   const ItemDev* d_qrows = (const ItemDev*)((const char*)ctx->d_qtab + o_r);
@@ -592,8 +672,8 @@ static int run_batch_impl(aslsd_ctx* ctx, BatchPlan& B, double* raw_device) {
   // on the evaluation point as long as the windows stay): with the weight cache on, a repeated
   // evaluation on the same plan - the iterations of a fit with fixed (beta, delta) - skips the
   // pass over the event pairs.
-  if (quad && ctx->cache_weights && !B.weights_valid && weights_match(ctx, B)) B.weights_valid = true;
-  const bool reuse_weights = quad && ctx->cache_weights && B.weights_valid;
+  // (the record of what d_q_weights holds decides: several plans share the buffer)
+  const bool reuse_weights = quad && ctx->cache_weights && weights_match(ctx, B);
   ctx->last_weights_reused = reuse_weights;
   ctx->moment_timing_pending = false;
   ctx->last_moment_ms = 0.;
@@ -601,35 +681,46 @@ static int run_batch_impl(aslsd_ctx* ctx, BatchPlan& B, double* raw_device) {
     if (ctx->q_smem_set == 0) {
       // the attribute belongs to the function, not to this context: every context asks for the
       // same ceiling, so contexts with different bin counts never lower each other's limit
-      CUDA_TRY(ctx, cudaFuncSetAttribute(lag_moment_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)LQ_SMEM_BUDGET));
-      CUDA_TRY(ctx, cudaFuncSetAttribute(lag_moment_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)LQ_SMEM_BUDGET));
-      ctx->q_smem_set = LQ_SMEM_BUDGET;
+      CUDA_TRY(ctx, cudaFuncSetAttribute(lag_moment_kernel<false, LqSmall>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)LqSmall::SMEM_BUDGET));
+      CUDA_TRY(ctx, cudaFuncSetAttribute(lag_moment_kernel<false, LqBig>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)LqBig::SMEM_BUDGET));
+      CUDA_TRY(ctx, cudaFuncSetAttribute(lag_moment_kernel<true, LqBig>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)LqBig::SMEM_BUDGET));
+      ctx->q_smem_set = LqBig::SMEM_BUDGET;
     }
     CUDA_TRY(ctx, cudaEventRecord(ctx->ev_q0, ctx->stream));
     unsigned long long* d_qcnt = ctx->d_counts + B.n_wu + n_items;
-    if (B.n_wu_q_plain > 0) {
-      lag_moment_kernel<false><<<(unsigned)B.n_wu_q_plain, LQ_NT, B.q_smem, ctx->stream>>>(
-          (const DimDev*)ctx->d_dims, d_streams, (int)B.qstreams.size(), ctx->d_q_partials, d_qcnt,
-          ctx->d_weights, 0);
+    const int n_streams = (int)B.qstreams.size();
+    if (B.q_cat_wu[1] > B.q_cat_wu[0]) {
+      lag_moment_kernel<false, LqSmall><<<(unsigned)(B.q_cat_wu[1] - B.q_cat_wu[0]), LqSmall::NT, B.q_cat_smem[0],
+                                           ctx->stream>>>((const DimDev*)ctx->d_dims, d_streams, n_streams,
+                                                          ctx->d_q_partials, d_qcnt, ctx->d_weights, B.q_cat_wu[0]);
       ctx->last_launches++;
     }
-    if (B.n_wu_q > B.n_wu_q_plain) {
-      lag_moment_kernel<true><<<(unsigned)(B.n_wu_q - B.n_wu_q_plain), LQ_NT, B.q_smem, ctx->stream>>>(
-          (const DimDev*)ctx->d_dims, d_streams, (int)B.qstreams.size(), ctx->d_q_partials, d_qcnt,
-          ctx->d_weights, B.n_wu_q_plain);
+    if (B.q_cat_wu[2] > B.q_cat_wu[1]) {
+      lag_moment_kernel<false, LqBig><<<(unsigned)(B.q_cat_wu[2] - B.q_cat_wu[1]), LqBig::NT, B.q_cat_smem[1],
+                                         ctx->stream>>>((const DimDev*)ctx->d_dims, d_streams, n_streams,
+                                                        ctx->d_q_partials, d_qcnt, ctx->d_weights, B.q_cat_wu[1]);
+      ctx->last_launches++;
+    }
+    if (B.q_cat_wu[3] > B.q_cat_wu[2]) {
+      lag_moment_kernel<true, LqBig><<<(unsigned)(B.q_cat_wu[3] - B.q_cat_wu[2]), LqBig::NT, B.q_cat_smem[2],
+                                        ctx->stream>>>((const DimDev*)ctx->d_dims, d_streams, n_streams,
+                                                       ctx->d_q_partials, d_qcnt, ctx->d_weights, B.q_cat_wu[2]);
       ctx->last_launches++;
     }
     CUDA_TRY(ctx, cudaEventRecord(ctx->ev_q1, ctx->stream));
     ctx->moment_timing_pending = true;
     const dim3 wgrid((unsigned)((B.q_jmax + LQ_WB - 1) / LQ_WB), (unsigned)B.qstreams.size());
+    ctx->w_streams.clear();   // being rewritten
     lag_weights_kernel<<<wgrid, LQ_WB * LQ_ND, 0, ctx->stream>>>(d_streams, ctx->d_q_partials, ctx->d_q_weights);
     ctx->last_launches++;
-    B.weights_valid = true;
-    ctx->w_streams.assign((const unsigned char*)B.qstreams.data(),
-                          (const unsigned char*)(B.qstreams.data() + B.qstreams.size()));
-    ctx->w_events_epoch = ctx->events_epoch;
+    if (ctx->cache_weights) {   // record what the buffer holds: later calls (of any plan) may reuse it
+      ctx->w_streams.assign((const unsigned char*)B.qstreams.data(),
+                            (const unsigned char*)(B.qstreams.data() + B.qstreams.size()));
+      ctx->w_events_epoch = ctx->events_epoch;
+    }
   }
   launch_pair<ITEM_UPS_GAUSS>(ctx, B, d_items);
   launch_pair<ITEM_UPS_EXP>(ctx, B, d_items);
@@ -834,18 +925,18 @@ static int build_assembly(aslsd_ctx* ctx, BatchPlan& B) {
   std::vector<AsmEntry> sorted;
   int rc;
   if ((rc = build_assembly_host(ctx, B, count, sorted))) return rc;
-  if ((rc = ensure_device_buffer(ctx, &ctx->d_asm, &ctx->asm_cap,
-                                 std::max<size_t>(1, sorted.size()) * sizeof(AsmEntry)))) return rc;
-  if ((rc = ensure_device_buffer(ctx, (void**)&ctx->d_asm_ptr, &ctx->asm_ptr_cap, count.size() * sizeof(int64_t))))
-    return rc;
-  CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_asm, sorted.data(), sorted.size() * sizeof(AsmEntry), cudaMemcpyHostToDevice,
+  if (B.d_asm) CUDA_TRY(ctx, cudaFree(B.d_asm));
+  if (B.d_asm_ptr) CUDA_TRY(ctx, cudaFree(B.d_asm_ptr));
+  B.d_asm = nullptr;
+  B.d_asm_ptr = nullptr;
+  CUDA_TRY(ctx, cudaMalloc(&B.d_asm, std::max<size_t>(1, sorted.size()) * sizeof(AsmEntry)));
+  CUDA_TRY(ctx, cudaMalloc((void**)&B.d_asm_ptr, count.size() * sizeof(int64_t)));
+  CUDA_TRY(ctx, cudaMemcpyAsync(B.d_asm, sorted.data(), sorted.size() * sizeof(AsmEntry), cudaMemcpyHostToDevice,
                                 ctx->stream));
-  CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_asm_ptr, count.data(), count.size() * sizeof(int64_t), cudaMemcpyHostToDevice,
+  CUDA_TRY(ctx, cudaMemcpyAsync(B.d_asm_ptr, count.data(), count.size() * sizeof(int64_t), cudaMemcpyHostToDevice,
                                 ctx->stream));
   CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));   // the sources are locals
   B.asm_built = true;
-  B.asm_resident = true;
-  ctx->asm_owner = &B;
   return ASLSD_OK;
 }
 
@@ -853,7 +944,7 @@ static int build_assembly(aslsd_ctx* ctx, BatchPlan& B) {
 static int assemble_device(aslsd_ctx* ctx, BatchPlan& B, int n_k, const double* const* xs, const double* raw_device,
                            double* packed_device) {
   int rc;
-  if (!B.asm_built || ctx->asm_owner != &B)
+  if (!B.asm_built)
     if ((rc = build_assembly(ctx, B))) return rc;
   const size_t n_w = (size_t)n_k * B.w_stride;
   if ((rc = ensure_device_buffer(ctx, (void**)&ctx->d_wtab, &ctx->wtab_cap, n_w * sizeof(double)))) return rc;
@@ -882,7 +973,7 @@ static int assemble_device(aslsd_ctx* ctx, BatchPlan& B, int n_k, const double* 
   ctx->wtab_flip ^= 1;
   if (B.out_total > 0) {
     assemble_kernel<<<(unsigned)((B.out_total + ASM_NT - 1) / ASM_NT), ASM_NT, 0, ctx->stream>>>(
-        ctx->d_asm_ptr, (const AsmEntry*)ctx->d_asm, ctx->d_wtab, raw_device, packed_device, B.out_total);
+        B.d_asm_ptr, (const AsmEntry*)B.d_asm, ctx->d_wtab, raw_device, packed_device, B.out_total);
     ctx->last_launches++;
   }
   CUDA_TRY(ctx, cudaGetLastError());
@@ -932,7 +1023,12 @@ extern "C" int aslsd_exact_out_len(const aslsd_ctx* ctx, int k, int64_t* out_len
 extern "C" int aslsd_set_option(aslsd_ctx* ctx, int option, int value) {
   if (!ctx) return ASLSD_ERR_ARG;
   if (option == ASLSD_OPT_LAG_QUADRATURE) { ctx->use_quadrature = value != 0; ctx->model_epoch++; return ASLSD_OK; }
-  if (option == ASLSD_OPT_WEIGHT_CACHE) { ctx->cache_weights = value != 0; ctx->model_epoch++; return ASLSD_OK; }
+  if (option == ASLSD_OPT_WEIGHT_CACHE) {
+    ctx->cache_weights = value != 0;
+    ctx->w_streams.clear();
+    ctx->model_epoch++;
+    return ASLSD_OK;
+  }
   if (option == ASLSD_OPT_ASYNC_EVENTS) { ctx->async_events = value != 0; return ASLSD_OK; }
   if (option == ASLSD_OPT_DEVICE_ASSEMBLY) { ctx->device_assembly = value != 0; return ASLSD_OK; }
   return aslsd_fail(ctx, ASLSD_ERR_ARG, "set_option: unknown option");
@@ -1211,8 +1307,10 @@ extern "C" int aslsd_last_work_counts(aslsd_ctx* ctx, int64_t* counts, int n) {
 // The rows of the last batch plan: what each one sums (include/aslsd_b200.h).  Host data only.
 extern "C" int aslsd_exact_plan_rows(aslsd_ctx* ctx, int64_t cap, int64_t* n_rows, int32_t* meta, double* params) {
   if (!ctx || !n_rows || cap < 0 || (cap > 0 && (!meta || !params))) return ASLSD_ERR_ARG;
-  const BatchPlan* B = (const BatchPlan*)ctx->plan_cache;
-  if (!B) return aslsd_fail(ctx, ASLSD_ERR_ARG, "plan rows: no exact-sum call has been planned yet");
+  const PlanCache* cache = (const PlanCache*)ctx->plan_cache;
+  if (!cache || cache->plans.empty())
+    return aslsd_fail(ctx, ASLSD_ERR_ARG, "plan rows: no exact-sum call has been planned yet");
+  const BatchPlan* B = cache->plans.front();
   *n_rows = (int64_t)B->rows.size();
   for (int64_t r = 0; r < std::min<int64_t>(cap, *n_rows); ++r) {
     const ItemDev& it = B->rows[(size_t)r];

@@ -22,7 +22,7 @@
 // the parameters at all.  The O(pairs) work drops from one exp + one erfc per (pair, basis pair) to ~2
 // fp64 instructions per (pair, Chebyshev degree); the closed forms are evaluated O(rows * J * LQ_ND) times.
 //
-// lag_moment_kernel, one CTA = (stream, block of targets), per tile of LQ_TM targets (one per thread):
+// lag_moment_kernel, one CTA = (stream, block of targets), per tile of NT targets (one per thread; NT, NW, GS: LqShape):
 //   a. the tile's source window sits in shared memory, fetched by one TMA bulk copy that was issued
 //      during the previous tile (the first source a tile can need is the window start of the previous
 //      tile's last target: no global search, two buffers); per-target source ranges by binary search
@@ -39,9 +39,9 @@
 //      lane), running count in a warp-private histogram -> (bin, rank in warp) key.  Scan of the
 //      histograms.  Pass 2: coordinates move to their sorted slots.  No atomics: the order inside a
 //      bin is fixed and the result is deterministic;
-//   c. every group of LQ_GS lanes takes a bin: three-term recurrence, LQ_ND - 1 register accumulators per lane,
+//   c. every group of GS lanes takes a bin: three-term recurrence, LQ_ND - 1 register accumulators per lane,
 //      transposed shuffle reduction, owner adds into the CTA's moment table.  With at most
-//      LQ_NW * 32 / LQ_GS = 64 bins every group owns one bin for the whole work unit: its sums stay
+//      NW * 32 / GS = 64 bins every group owns one bin for the whole work unit: its sums stay
 //      in registers across chunks and tiles and are reduced once, before the partial table is written;
 //   one partial table per work unit, reduced in fixed order by lag_weights_kernel.
 #pragma once
@@ -49,27 +49,38 @@
 #include "basis_math.cuh"
 #include "pair_kernels.cuh"
 
-#ifndef LQ_NT
-#define LQ_NT 512                 // threads per CTA (1024 measured slower: 17.3 vs 14.8 ms)
-#endif
-#ifndef LQ_CTAS
-#define LQ_CTAS 1                 // CTAs per SM the shared-memory budget is cut for
-#endif
-#define LQ_NW (LQ_NT / 32)
-#define LQ_GS (LQ_NT >= 1024 ? 16 : 8)   // lanes per bin in the moment pass (one round covers 64 bins)
-#define LQ_TM LQ_NT               // targets per tile: one per thread
 #define LQ_UCAP_MAX 8192          // pairs sorted at a time
-#define LQ_SMAX 2048              // staged source events per tile (two buffers)
 #define LQ_ND 12                  // Chebyshev terms = nodes per bin
 #define LQ_JMAX 1024              // bins per stream
-#define LQ_SMEM_BUDGET ((LQ_CTAS == 1 ? 220 : 110) * 1024)
 #define LQ_SCALE_FRACTION 0.5     // largest bin width in units of the smallest scale of the stream's rows
 #define LQ_MAGIC 6755399441055744.0   // 1.5 * 2^52: x + MAGIC holds rint(x) in its low word
 
+// Shape of the moment kernel's CTA: NT threads (one target of a tile each), CTAS of them resident per SM
+// (the shared-memory budget is cut for that).  Two instances are compiled:
+//   LqBig   512 x 1  serves any bin count up to LQ_JMAX (220 KB of shared memory);
+//   LqSmall 128 x 4  for unweighted streams of at most 64 bins (every pair of lanes owns one bin): the four
+//           CTAs of an SM are in different phases (sort: integer / shared-memory issue; recurrences:
+//           fp64 pipe; barriers), which overlap - measured 10.45 ms against 12.6 ms per C5 step
+//           (profiles/r2_variants.md; 256 x 2: 10.9 ms, 512 x 2 with 64 registers: 16.3 ms, 256 x 3: 12.3 ms).
+template <int NT_, int CTAS_>
+struct LqShape {
+  static constexpr int NT = NT_, CTAS = CTAS_;
+  static constexpr int NW = NT / 32;
+  // lanes per bin in the moment pass (one round of the CTA covers 64 bins)
+  static constexpr int GS = NT >= 1024 ? 16 : (NT >= 512 ? 8 : (NT >= 256 ? 4 : 2));
+  static constexpr int TM = NT;     // targets per tile: one per thread
+  static constexpr int SMAX = NT >= 512 ? 2048 : (NT >= 256 ? 1024 : 512);   // staged source events per tile (two buffers)
+  static constexpr int SMEM_BUDGET = (CTAS == 1 ? 220 : (CTAS == 2 ? 110 : (CTAS == 3 ? 73 : 54))) * 1024;
+  static constexpr int ONE_BIN_J = NW * (32 / GS);   // bins the groups of lanes can own for a whole work unit
+};
+typedef LqShape<512, 1> LqBig;
+typedef LqShape<128, 4> LqSmall;
+enum { LQ_SHAPE_BIG = 0, LQ_SHAPE_SMALL = 1 };
+
 struct QStreamDev {
   int32_t tgt_dim, src_dim, same, J;
-  int32_t n_chunks, ucap;  // work units; pairs sorted at a time (multiple of LQ_NT)
-  int32_t nbits, pad;      // bits of the bin index
+  int32_t n_chunks, ucap;  // work units; pairs sorted at a time (multiple of the shape's NT)
+  int32_t nbits, shape;    // bits of the bin index; LQ_SHAPE_* of the CTAs that take this stream
   int64_t m_lo, m_hi;      // interior target block
   int64_t tpw;             // targets per work unit
   int64_t wu_first;        // first work unit (prefix over streams)
@@ -86,21 +97,23 @@ __constant__ double LQ_CT[LQ_ND * LQ_ND];   // [i][d]
 
 // dynamic shared memory: [pair-order lags / coordinates | sorted coordinates | 2 source windows |
 //                         moment table | keys | bin starts | histograms]
+template <class C>
 __host__ __device__ inline size_t lq_smem_bytes(int J, int ucap, bool weighted) {
   size_t b = 0;
   b += (size_t)ucap * sizeof(double) * (weighted ? 4 : 2);   // + pair weights in both orders
-  b += (size_t)(LQ_SMAX + 2) * sizeof(double) * 2;
+  b += (size_t)(C::SMAX + 2) * sizeof(double) * 2;
   b += (size_t)J * LQ_ND * sizeof(double);
   b += (size_t)ucap * sizeof(uint32_t);
   b += (size_t)(J + 2) * sizeof(int32_t);
-  b += (size_t)LQ_NW * J * sizeof(uint16_t);
+  b += (size_t)C::NW * J * sizeof(uint16_t);
   return b + 64;
 }
 
-// largest chunk (multiple of LQ_NT) that fits the budget; 0 if none does
+// largest chunk (multiple of C::NT) that fits the budget; 0 if none does
+template <class C>
 inline int lq_pick_ucap(int J, bool weighted) {
-  for (int u = LQ_UCAP_MAX; u >= LQ_NT; u -= LQ_NT)
-    if (lq_smem_bytes(J, u, weighted) <= (size_t)LQ_SMEM_BUDGET) return u;
+  for (int u = (LQ_UCAP_MAX / C::NT) * C::NT; u >= C::NT; u -= C::NT)
+    if (lq_smem_bytes<C>(J, u, weighted) <= (size_t)C::SMEM_BUDGET) return u;
   return 0;
 }
 
@@ -187,7 +200,7 @@ __device__ __forceinline__ void lq_bin(double s, double inv_h, int& b, double& v
 // Pass 1 of the counting sort over the n_c pairs of a chunk (see the file header): s_val holds
 // the lags in pair order on entry, the bin positions on exit.  Two warp steps per iteration:
 // the ballots of the two are independent, the histogram updates are ordered.
-template <int NB>
+template <int NB, class C>
 __device__ __forceinline__ void lq_pass1(int n_c, double inv_h, uint16_t* my_hist, uint32_t* s_key,
                                          double* s_val) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -196,8 +209,8 @@ __device__ __forceinline__ void lq_pass1(int n_c, double inv_h, uint16_t* my_his
   const int n_full = n_c >> 5;   // steps whose 32 pairs all exist
   int st = warp;
   // full steps, two per iteration: no lane masks, no liveness tests
-  for (; st + LQ_NW < n_full; st += 2 * LQ_NW) {
-    const int qa = st * 32 + lane, qb = qa + LQ_NW * 32;
+  for (; st + C::NW < n_full; st += 2 * C::NW) {
+    const int qa = st * 32 + lane, qb = qa + C::NW * 32;
     const double sa = s_val[qa], sb = s_val[qb];
     int ba, bb;
     double va, vb;
@@ -221,7 +234,7 @@ __device__ __forceinline__ void lq_pass1(int n_c, double inv_h, uint16_t* my_his
   }
   // the remaining steps of this warp (at most two, the last one of the chunk possibly partial):
   // idle lanes redo pair 0 and are masked out of every peer set
-  for (; st < n_steps; st += LQ_NW) {
+  for (; st < n_steps; st += C::NW) {
     const int qa = st * 32 + lane;
     const bool live_a = qa < n_c;
     const int left_a = n_c - st * 32;
@@ -243,15 +256,15 @@ __device__ __forceinline__ void lq_pass1(int n_c, double inv_h, uint16_t* my_his
   }
 }
 
-// Chebyshev moments of the sorted positions s_u[e0 + qg], s_u[e0 + qg + LQ_GS], ... < e1, added to
+// Chebyshev moments of the sorted positions s_u[e0 + qg], s_u[e0 + qg + C::GS], ... < e1, added to
 // acc[1..] (acc[0], the count, is the caller's: exact for unweighted streams).  Two independent
 // recurrences per iteration (the chain is latency-bound).
-template <bool WEIGHTED>
+template <bool WEIGHTED, class C>
 __device__ __forceinline__ void lq_accumulate(const double* __restrict__ s_u, const double* __restrict__ s_wu,
                                               int32_t e0, int32_t e1, int qg, double* acc) {
   int32_t e = e0 + qg;
   if (WEIGHTED) {
-    for (; e < e1; e += LQ_GS) {
+    for (; e < e1; e += C::GS) {
       const double w = s_wu[e];
       const double uu = s_u[e] + s_u[e];
       const double two_u = uu + uu;
@@ -267,8 +280,8 @@ __device__ __forceinline__ void lq_accumulate(const double* __restrict__ s_u, co
       }
     }
   } else {
-  for (; e + LQ_GS < e1; e += 2 * LQ_GS) {
-    const double ua = s_u[e] + s_u[e], ub = s_u[e + LQ_GS] + s_u[e + LQ_GS];
+  for (; e + C::GS < e1; e += 2 * C::GS) {
+    const double ua = s_u[e] + s_u[e], ub = s_u[e + C::GS] + s_u[e + C::GS];
     const double two_a = ua + ua, two_b = ub + ub;
     double pa = 1., ca = ua, pb = 1., cb = ub;
     acc[1] += ca + cb;
@@ -297,44 +310,54 @@ __device__ __forceinline__ void lq_accumulate(const double* __restrict__ s_u, co
   }
 }
 
-// Transposed reduction of acc[LQ_ND] over the LQ_GS lanes of a group (12 -> 6 -> 3 values per
+// Transposed reduction of acc[LQ_ND] over the C::GS lanes of a group (12 -> 6 -> 3 values per
 // lane on the two widest exchanges, plain butterflies on the rest), then Mb[d] += the sums.
+template <class C>
 __device__ __forceinline__ void lq_reduce_store(double* acc, int qg, bool store, double* Mb) {
   {
-    const bool up = (qg & (LQ_GS / 2)) != 0;
+    const bool up = (qg & (C::GS / 2)) != 0;
 #pragma unroll
     for (int i = 0; i < 6; ++i) {
       const double send = up ? acc[i] : acc[i + 6];
       const double keep = up ? acc[i + 6] : acc[i];
-      acc[i] = keep + __shfl_xor_sync(0xffffffffu, send, LQ_GS / 2);
+      acc[i] = keep + __shfl_xor_sync(0xffffffffu, send, C::GS / 2);
     }
   }
+  if constexpr (C::GS >= 4) {
   {
-    const bool up = (qg & (LQ_GS / 4)) != 0;
+    const bool up = (qg & (C::GS / 4)) != 0;
 #pragma unroll
     for (int i = 0; i < 3; ++i) {
       const double send = up ? acc[i] : acc[i + 3];
       const double keep = up ? acc[i + 3] : acc[i];
-      acc[i] = keep + __shfl_xor_sync(0xffffffffu, send, LQ_GS / 4);
+      acc[i] = keep + __shfl_xor_sync(0xffffffffu, send, C::GS / 4);
     }
   }
 #pragma unroll
-  for (int o = LQ_GS / 8; o > 0; o >>= 1) {
+  for (int o = C::GS / 8; o > 0; o >>= 1) {
 #pragma unroll
     for (int i = 0; i < 3; ++i) acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], o);
   }
-  if (store && (qg & (LQ_GS / 4 - 1)) == 0) {
-    const int d0 = ((qg & (LQ_GS / 2)) ? 6 : 0) + ((qg & (LQ_GS / 4)) ? 3 : 0);
+  if (store && (qg & (C::GS / 4 - 1)) == 0) {
+    const int d0 = ((qg & (C::GS / 2)) ? 6 : 0) + ((qg & (C::GS / 4)) ? 3 : 0);
     Mb[d0] += acc[0];
     Mb[d0 + 1] += acc[1];
     Mb[d0 + 2] += acc[2];
+  }
+  } else {
+  // two lanes per bin: each ends up with six of the twelve sums
+  if (store) {
+    const int d0 = (qg & 1) ? 6 : 0;
+#pragma unroll
+    for (int i = 0; i < 6; ++i) Mb[d0 + i] += acc[i];
+  }
   }
 }
 
 // WEIGHTED: streams of marked models (per-event weights); launched separately from the
 // unweighted streams so that those keep their register budget
-template <bool WEIGHTED>
-__global__ void __launch_bounds__(LQ_NT, LQ_CTAS)
+template <bool WEIGHTED, class C>
+__global__ void __launch_bounds__(C::NT, C::CTAS)
 lag_moment_kernel(const DimDev* __restrict__ dims, const QStreamDev* __restrict__ streams, int n_streams,
                   double* __restrict__ partials, unsigned long long* __restrict__ counts,
                   const double* __restrict__ weights, int64_t wu_base) {
@@ -343,8 +366,8 @@ lag_moment_kernel(const DimDev* __restrict__ dims, const QStreamDev* __restrict_
   __shared__ int64_t s_a0[2];        // first source index of each window buffer
   __shared__ int64_t s_next_lo;      // window start of the tile's last target
   __shared__ double s_tlast;         // time of the tile's last target
-  __shared__ int32_t s_warp[LQ_NW];    // pair counts of a tile fit 32 bits (host guard, build_stream)
-  __shared__ int32_t s_scan[LQ_NW];
+  __shared__ int32_t s_warp[C::NW];    // pair counts of a tile fit 32 bits (host guard, build_stream)
+  __shared__ int32_t s_scan[C::NW];
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int64_t wu = (int64_t)blockIdx.x + wu_base;
@@ -364,14 +387,14 @@ lag_moment_kernel(const DimDev* __restrict__ dims, const QStreamDev* __restrict_
   double* s_u = s_val + ucap;
   double* s_wv = s_u + ucap;                        // pair weights, pair order (weighted streams)
   double* s_wu = s_wv + (weighted ? ucap : 0);      // pair weights, sorted by bin
-  double* s_src = s_wu + (weighted ? ucap : 0);     // two buffers of LQ_SMAX + 2
-  double* s_M = s_src + 2 * (LQ_SMAX + 2);
+  double* s_src = s_wu + (weighted ? ucap : 0);     // two buffers of C::SMAX + 2
+  double* s_M = s_src + 2 * (C::SMAX + 2);
   uint32_t* s_key = (uint32_t*)(s_M + (size_t)J * LQ_ND);
   int32_t* s_bin = (int32_t*)(s_key + ucap);
   uint16_t* s_hist = (uint16_t*)(s_bin + (J + 2));
   uint16_t* my_hist = s_hist + warp * J;
 
-  for (int x = tid; x < J * LQ_ND; x += LQ_NT) s_M[x] = 0.;
+  for (int x = tid; x < J * LQ_ND; x += C::NT) s_M[x] = 0.;
   if (tid == 0) {
     mbar_init(&s_bar[0], 1);
     mbar_init(&s_bar[1], 1);
@@ -380,7 +403,7 @@ lag_moment_kernel(const DimDev* __restrict__ dims, const QStreamDev* __restrict_
     int64_t a0 = 0;
     if (m_begin < m_end) a0 = dim_lower_bound(Ds, Dt.t[m_begin] - S.s_max) & ~(int64_t)1;
     s_a0[0] = a0;
-    const int64_t n_stage = min((int64_t)LQ_SMAX, n_src_padded - a0);
+    const int64_t n_stage = min((int64_t)C::SMAX, n_src_padded - a0);
     if (m_begin < m_end) {
       mbar_expect_tx(&s_bar[0], (uint32_t)(n_stage * sizeof(double)));
       tma_load_1d(s_src, Ds.t + a0, (uint32_t)(n_stage * sizeof(double)), &s_bar[0]);
@@ -391,28 +414,28 @@ lag_moment_kernel(const DimDev* __restrict__ dims, const QStreamDev* __restrict_
   unsigned long long n_pairs = 0;
   double t_mine = (m_begin + tid < m_end) ? Dt.t[m_begin + tid] : 0.;
 
-  // bins per pass of the moment stage = groups of LQ_GS lanes in the CTA
-  const int grp = lane / LQ_GS, qg = lane % LQ_GS;
-  const bool one_bin = J <= LQ_NW * (32 / LQ_GS);
-  const int my_bin = warp * (32 / LQ_GS) + grp;
+  // bins per pass of the moment stage = groups of C::GS lanes in the CTA
+  const int grp = lane / C::GS, qg = lane % C::GS;
+  const bool one_bin = J <= C::ONE_BIN_J;
+  const int my_bin = warp * (32 / C::GS) + grp;
   double racc[LQ_ND];
 #pragma unroll
   for (int d = 0; d < LQ_ND; ++d) racc[d] = 0.;
 
   int tile = 0;
-  for (int64_t m0 = m_begin; m0 < m_end; m0 += LQ_TM, ++tile) {
-    const int nt = (int)min((int64_t)LQ_TM, m_end - m0);
+  for (int64_t m0 = m_begin; m0 < m_end; m0 += C::TM, ++tile) {
+    const int nt = (int)min((int64_t)C::TM, m_end - m0);
     const int buf = tile & 1;
-    double* win = s_src + buf * (LQ_SMAX + 2);
+    double* win = s_src + buf * (C::SMAX + 2);
     // ---- a. per-target source ranges ---------------------------------------------------------
     const double t = t_mine;
     if (tid == nt - 1) s_tlast = t;
-    if (m0 + LQ_TM + tid < m_end) t_mine = Dt.t[m0 + LQ_TM + tid];   // next tile's target, in flight
+    if (m0 + C::TM + tid < m_end) t_mine = Dt.t[m0 + C::TM + tid];   // next tile's target, in flight
     mbar_wait(&s_bar[buf], (parity >> buf) & 1u);
     parity ^= 1u << buf;
     __syncthreads();
     const int64_t a0 = s_a0[buf];
-    const int n_win = (int)min((int64_t)LQ_SMAX, n_src_padded - a0);
+    const int n_win = (int)min((int64_t)C::SMAX, n_src_padded - a0);
     // the window serves the tile if it reaches the end of the stream or the last target (same type:
     // by index, ties in time included; other types: by time, the searches are lower bounds)
     const double t_last = s_tlast;
@@ -425,7 +448,8 @@ lag_moment_kernel(const DimDev* __restrict__ dims, const QStreamDev* __restrict_
     // one: one step less) whose entry reaches it
     int n_search = n_valid;
     if (staged) {
-      if (n_valid > 511 && win[510] >= t_last) n_search = 511;
+      if (C::TM <= 256 && n_valid > 255 && win[254] >= t_last) n_search = 255;
+      else if (n_valid > 511 && win[510] >= t_last) n_search = 511;
       else if (n_valid > 1023 && win[1022] >= t_last) n_search = 1023;
     }
     const int p2 = n_search > 0 ? (1 << (31 - __clz(n_search))) : 0;
@@ -437,6 +461,9 @@ lag_moment_kernel(const DimDev* __restrict__ dims, const QStreamDev* __restrict_
         if (n_search == 1023) {
           if (same) { r_hi = 0; r_lo = smem_lower_bound_full<10>(win, x_lo); }
           else smem_lower_bound_full2<10>(win, t, x_lo, r_hi, r_lo);
+        } else if (C::TM <= 256 && n_search == 255) {
+          if (same) { r_hi = 0; r_lo = smem_lower_bound_full<8>(win, x_lo); }
+          else smem_lower_bound_full2<8>(win, t, x_lo, r_hi, r_lo);
         } else if (n_search == 511) {
           if (same) { r_hi = 0; r_lo = smem_lower_bound_full<9>(win, x_lo); }
           else smem_lower_bound_full2<9>(win, t, x_lo, r_hi, r_lo);
@@ -463,19 +490,19 @@ lag_moment_kernel(const DimDev* __restrict__ dims, const QStreamDev* __restrict_
     __syncthreads();
     int32_t pre = incl - cnt, total = 0;
 #pragma unroll
-    for (int w = 0; w < LQ_NW; ++w) {
+    for (int w = 0; w < C::NW; ++w) {
       const int32_t v = s_warp[w];
       if (w < warp) pre += v;
       total += v;
     }
     // next tile's window into the other buffer (its readers finished before the previous tile's
     // closing barrier)
-    if (tid == 0 && m0 + LQ_TM < m_end) {
+    if (tid == 0 && m0 + C::TM < m_end) {
       const int64_t a1 = s_next_lo & ~(int64_t)1;
       s_a0[buf ^ 1] = a1;
-      const int64_t n_stage = min((int64_t)LQ_SMAX, n_src_padded - a1);
+      const int64_t n_stage = min((int64_t)C::SMAX, n_src_padded - a1);
       mbar_expect_tx(&s_bar[buf ^ 1], (uint32_t)(n_stage * sizeof(double)));
-      tma_load_1d(s_src + (buf ^ 1) * (LQ_SMAX + 2), Ds.t + a1, (uint32_t)(n_stage * sizeof(double)),
+      tma_load_1d(s_src + (buf ^ 1) * (C::SMAX + 2), Ds.t + a1, (uint32_t)(n_stage * sizeof(double)),
                   &s_bar[buf ^ 1]);
     }
     const double* my_win = win + (int)(lo_abs - a0);    // shared (staged tiles)
@@ -499,6 +526,13 @@ lag_moment_kernel(const DimDev* __restrict__ dims, const QStreamDev* __restrict_
         }
         if (staged) {
           int32_t r = ra;
+          for (; r + 3 < rb; r += 4) {
+            const double s0 = my_win[r], s1 = my_win[r + 1], s2 = my_win[r + 2], s3 = my_win[r + 3];
+            dst[r] = t - s0;
+            dst[r + 1] = t - s1;
+            dst[r + 2] = t - s2;
+            dst[r + 3] = t - s3;
+          }
           for (; r + 1 < rb; r += 2) {
             const double s0 = my_win[r], s1 = my_win[r + 1];
             dst[r] = t - s0;
@@ -509,18 +543,18 @@ lag_moment_kernel(const DimDev* __restrict__ dims, const QStreamDev* __restrict_
           for (int32_t r = ra; r < rb; ++r) dst[r] = t - __ldg(my_glb + r);
         }
       }
-      for (int x = tid; x < (LQ_NW * J + 1) / 2; x += LQ_NT) ((uint32_t*)s_hist)[x] = 0u;
+      for (int x = tid; x < (C::NW * J + 1) / 2; x += C::NT) ((uint32_t*)s_hist)[x] = 0u;
       __syncthreads();
       // pass 1: bin, position in the bin, rank among the equal bins seen so far by this warp
-      if (nbits <= 5) lq_pass1<5>(n_c, inv_h, my_hist, s_key, s_val);
-      else if (nbits == 6) lq_pass1<6>(n_c, inv_h, my_hist, s_key, s_val);
-      else if (nbits == 7) lq_pass1<7>(n_c, inv_h, my_hist, s_key, s_val);
-      else lq_pass1<10>(n_c, inv_h, my_hist, s_key, s_val);
+      if (nbits <= 5) lq_pass1<5, C>(n_c, inv_h, my_hist, s_key, s_val);
+      else if (nbits == 6) lq_pass1<6, C>(n_c, inv_h, my_hist, s_key, s_val);
+      else if (nbits == 7) lq_pass1<7, C>(n_c, inv_h, my_hist, s_key, s_val);
+      else lq_pass1<10, C>(n_c, inv_h, my_hist, s_key, s_val);
       __syncthreads();
       // bin totals -> bin starts; per-warp cursors = start + counts of the lower warps
       // (thread tid owns the jpt consecutive bins from tid * jpt)
       {
-        const int jpt = (J + LQ_NT - 1) / LQ_NT;
+        const int jpt = (J + C::NT - 1) / C::NT;
         const bool owns_bins = warp * 32 * jpt < J;   // warp-uniform: the other warps only meet the barrier
         int32_t tot = 0, inc = 0;
         if (owns_bins) {
@@ -528,7 +562,7 @@ lag_moment_kernel(const DimDev* __restrict__ dims, const QStreamDev* __restrict_
             const int b = tid * jpt + q;
             if (b < J) {
 #pragma unroll
-              for (int w = 0; w < LQ_NW; ++w) tot += s_hist[w * J + b];
+              for (int w = 0; w < C::NW; ++w) tot += s_hist[w * J + b];
             }
           }
           inc = tot;
@@ -548,7 +582,7 @@ lag_moment_kernel(const DimDev* __restrict__ dims, const QStreamDev* __restrict_
             if (b < J) {
               s_bin[b] = run;
 #pragma unroll
-              for (int w = 0; w < LQ_NW; ++w) {
+              for (int w = 0; w < C::NW; ++w) {
                 const int32_t v = s_hist[w * J + b];
                 s_hist[w * J + b] = (uint16_t)run;
                 run += v;
@@ -559,34 +593,56 @@ lag_moment_kernel(const DimDev* __restrict__ dims, const QStreamDev* __restrict_
         }
       }
       __syncthreads();
-      // pass 2: coordinates to their sorted slots (pair q was ranked by warp (q / 32) % LQ_NW = warp)
-      for (int32_t q = tid; q < n_c; q += LQ_NT) {
-        const uint32_t key = s_key[q];
-        const int b = (int)(key & 1023u);
-        const int pos = (int)my_hist[b] + (int)(key >> 10);
-        s_u[pos] = s_val[q];
-        if (weighted) s_wu[pos] = s_wv[q];
+      // pass 2: coordinates to their sorted slots (pair q was ranked by warp (q / 32) % C::NW = warp)
+      {
+        int32_t q = tid;
+        // four pairs per iteration: the dependent loads (key -> cursor of its bin) of the four overlap
+        for (; q + 3 * C::NT < n_c; q += 4 * C::NT) {
+          uint32_t key[4];
+          double val[4], wv[4];
+          int pos[4];
+#pragma unroll
+          for (int x = 0; x < 4; ++x) {
+            key[x] = s_key[q + x * C::NT];
+            val[x] = s_val[q + x * C::NT];
+            if (weighted) wv[x] = s_wv[q + x * C::NT];
+          }
+#pragma unroll
+          for (int x = 0; x < 4; ++x) pos[x] = (int)my_hist[key[x] & 1023u] + (int)(key[x] >> 10);
+#pragma unroll
+          for (int x = 0; x < 4; ++x) {
+            s_u[pos[x]] = val[x];
+            if (weighted) s_wu[pos[x]] = wv[x];
+          }
+        }
+        for (; q < n_c; q += C::NT) {
+          const uint32_t key = s_key[q];
+          const int b = (int)(key & 1023u);
+          const int pos = (int)my_hist[b] + (int)(key >> 10);
+          s_u[pos] = s_val[q];
+          if (weighted) s_wu[pos] = s_wv[q];
+        }
       }
       __syncthreads();
-      // ---- c. moments of every bin: LQ_GS lanes per bin -------------------------------------------
+      // ---- c. moments of every bin: C::GS lanes per bin -------------------------------------------
       if (one_bin) {
         // every group of lanes owns one bin for the whole work unit: the partial sums stay in
         // registers across chunks and tiles and are reduced once, at the end
         int32_t e0 = 0, e1 = 0;
         if (my_bin < J) { e0 = s_bin[my_bin]; e1 = s_bin[my_bin + 1]; }
-        lq_accumulate<WEIGHTED>(s_u, s_wu, e0, e1, qg, racc);
+        lq_accumulate<WEIGHTED, C>(s_u, s_wu, e0, e1, qg, racc);
         if (!WEIGHTED && qg == 0) racc[0] += (double)(e1 - e0);   // T_0 = 1: the bin count, exact
       } else {
-        for (int b0 = warp * (32 / LQ_GS); b0 < J; b0 += LQ_NW * (32 / LQ_GS)) {
+        for (int b0 = warp * (32 / C::GS); b0 < J; b0 += C::NW * (32 / C::GS)) {
           const int b = b0 + grp;
           int32_t e0 = 0, e1 = 0;
           if (b < J) { e0 = s_bin[b]; e1 = s_bin[b + 1]; }
           double acc[LQ_ND];
 #pragma unroll
           for (int d = 0; d < LQ_ND; ++d) acc[d] = 0.;
-          lq_accumulate<WEIGHTED>(s_u, s_wu, e0, e1, qg, acc);
+          lq_accumulate<WEIGHTED, C>(s_u, s_wu, e0, e1, qg, acc);
           if (!WEIGHTED && qg == 0) acc[0] = (double)(e1 - e0);
-          lq_reduce_store(acc, qg, b < J && e1 > e0, s_M + (size_t)min(b, J - 1) * LQ_ND);
+          lq_reduce_store<C>(acc, qg, b < J && e1 > e0, s_M + (size_t)min(b, J - 1) * LQ_ND);
         }
       }
       __syncthreads();
@@ -595,20 +651,20 @@ lag_moment_kernel(const DimDev* __restrict__ dims, const QStreamDev* __restrict_
     __syncthreads();
   }
   if (one_bin) {
-    lq_reduce_store(racc, qg, my_bin < J, s_M + (size_t)min(my_bin, J - 1) * LQ_ND);
+    lq_reduce_store<C>(racc, qg, my_bin < J, s_M + (size_t)min(my_bin, J - 1) * LQ_ND);
     __syncthreads();
   }
   // ---- one partial moment table per work unit ---------------------------------------------------
   double* out = partials + S.part_first + (int64_t)chunk * J * LQ_ND;
-  for (int x = tid; x < J * LQ_ND; x += LQ_NT) out[x] = s_M[x];
+  for (int x = tid; x < J * LQ_ND; x += C::NT) out[x] = s_M[x];
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) n_pairs += __shfl_xor_sync(0xffffffffu, n_pairs, o);
-  __shared__ unsigned long long s_cnt[LQ_NW];
+  __shared__ unsigned long long s_cnt[C::NW];
   if (lane == 0) s_cnt[warp] = n_pairs;
   __syncthreads();
   if (tid == 0) {
     unsigned long long c = 0;
-    for (int w = 0; w < LQ_NW; ++w) c += s_cnt[w];
+    for (int w = 0; w < C::NW; ++w) c += s_cnt[w];
     counts[wu] = c;
   }
 }

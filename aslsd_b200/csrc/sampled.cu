@@ -20,6 +20,7 @@
 #include "plan.h"
 
 #include <cstring>
+#include <limits>
 
 #define SAMP_NT 128
 #define SAMP_MAX_OUT 128   // 1 + n_param_1 + n_param_2 of a term
@@ -34,6 +35,7 @@ union ItemConst {
 struct SampleTermDev {
   int32_t kind, tgt_dim, src_dim, n_out;
   int32_t item_first, item_count;
+  double sat_t, v_sat;   // single-index terms: the reference's own value beyond saturation (aslsd_sample_term)
 };
 
 struct SampleEntry {
@@ -188,6 +190,9 @@ sampled_kernel(const DimDev* __restrict__ dims, const ItemDev* __restrict__ item
         val[E.c] = __dadd_rn(val[E.c], __dmul_rn(E.outer, __dmul_rn(E.coef, raw[E.comp])));
       }
     }
+    // beyond saturation the value is the caller's constant: the reference's own arithmetic
+    // (aslsd_sample_term; a NaN threshold compares false)
+    if (T.kind < 2 && t >= T.sat_t) val[0] = T.v_sat;
     if (wa_off >= 0 || wb_off >= 0) {
       // f = kernel functional x impact functional, impact product first
       // (mtlh_stratified_estimator.py:1530-1533, :686 np.prod over the two functions)
@@ -327,6 +332,8 @@ extern "C" int aslsd_sampled_sums(aslsd_ctx* ctx, int k, const double* x_k, int 
     D.n_out = 1 + T.n1 + T.n2;
     D.item_first = T.item_first;
     D.item_count = T.item_count;
+    D.sat_t = (T.kind < 2 && A.sat_t >= 0.) ? A.sat_t : std::numeric_limits<double>::infinity();
+    D.v_sat = A.v_sat;
     if (D.n_out > SAMP_MAX_OUT)
       return aslsd_fail(ctx, ASLSD_ERR_UNSUPPORTED, "sampled sums: more than 127 parameters in one term");
     if (T.kind >= 2) need_n = true;

@@ -180,9 +180,15 @@ class Engine:
                                                     capi.ptr_i64(vlen)))
 
         def alloc(lens, want):
+            # the d x d arrays of a table are views of one block, back to back in pair order:
+            # the library then reads the whole table back with a single transfer
             if not want:
                 return None, None
-            arrs = [np.empty(int(n), dtype=np.int64) for n in lens]
+            # (every array at an even element offset, the layout of the device tables)
+            padded = (np.asarray(lens, dtype=np.int64) + 1) & ~np.int64(1)
+            block = np.empty(int(np.sum(padded)), dtype=np.int64)
+            cuts = np.concatenate([[0], np.cumsum(padded)]).astype(np.int64)
+            arrs = [block[cuts[p]:cuts[p] + int(lens[p])] for p in range(d * d)]
             ptrs = (capi.c_i64_p * (d * d))(*[capi.ptr_i64(a) for a in arrs])
             return arrs, ptrs
         kap, kap_p = alloc(klen, want_kappa)
@@ -323,7 +329,7 @@ class Engine:
         """One launch for every stratum of every term of a compute_objective call
         (mhp_stratified_estimator.py:1333-1386).
 
-        terms: list of (kind, i, j, n_strata); the strata of all terms are
+        terms: list of (kind, i, j, n_strata[, sat_t, v_sat]); the strata of all terms are
         concatenated and stratum s owns samples [stratum_offsets[s],
         stratum_offsets[s+1]) of ix_m / ix_n.  Returns (sums, out_offsets,
         stat_mean, stat_std, rel_alloc): sums[out_offsets[s]:out_offsets[s+1]] are
@@ -334,8 +340,11 @@ class Engine:
         n_terms = len(terms)
         arr = (capi.SampleTerm * max(n_terms, 1))()
         n_strata, out_offsets = 0, [0]
-        for q, (kind, i, j, ns) in enumerate(terms):
+        for q, term in enumerate(terms):
+            kind, i, j, ns = term[:4]
             arr[q].kind, arr[q].i, arr[q].j, arr[q].n_strata = int(kind), int(i), int(j), int(ns)
+            # optional (sat_t, v_sat): the reference's constant value of saturated single-index samples
+            arr[q].sat_t, arr[q].v_sat = (float(term[4]), float(term[5])) if len(term) > 4 else (np.inf, 0.)
             n_out = self.sampled_n_out(k, kind, i, j)
             for _ in range(int(ns)):
                 out_offsets.append(out_offsets[-1] + n_out)

@@ -38,7 +38,7 @@ import pickle
 
 import numpy as np
 
-from aslsd_b200 import sampling
+from aslsd_b200 import sampling, saturation
 from aslsd_b200.engine import unpack_terms
 from aslsd_b200.stratifications import DoubleIxStratification, GeneralStratification
 
@@ -580,8 +580,12 @@ class MHPStratEstimB200(_B200Estimator):
     reference's result attributes.
     """
 
-    def __init__(self, *args, reference_adaptive_grad=True, **kwargs):
+    def __init__(self, *args, reference_adaptive_grad=True, saturated_values=True, **kwargs):
         super().__init__(*args, **kwargs)
+        # True: samples of psi_i / upsilonzero_i far from T_f carry the value of the model's own
+        # closures (bit for bit the reference's), so that the rounding-residue allocations of such
+        # strata - hence every later draw - are the reference's (aslsd_b200.saturation)
+        self.saturated_values = saturated_values
         # True: verbatim reference behaviour - without grad_alloc the derivative
         # means of the ADAPTIVE strata are never evaluated (the ``if n_func == 1``
         # block of mhp_stratified_estimator.py:607-627 is nested under
@@ -798,7 +802,11 @@ class MHPStratEstimB200(_B200Estimator):
                 plan['counts'].append(np.array([len(m)], dtype=np.int64))
             n_chunks = sum(n_strata for _, n_strata in plan['blocks'])
             if n_chunks:
-                dev_terms.append((kind, i, j, n_chunks))
+                sat = None
+                if kind in (KIND_PSI, KIND_UPSILONZERO) and self.saturated_values:
+                    # the reference's own value of the samples far from T_f (aslsd_b200.saturation)
+                    sat = saturation.term_saturation(self._model, self.desc, self.k, i, kind, x)
+                dev_terms.append((kind, i, j, n_chunks) + (sat if sat else ()))
             plans.append(plan)
         # ---- 2. one launch ----------------------------------------------------------------------
         if dev_terms:

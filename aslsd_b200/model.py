@@ -85,6 +85,10 @@ class MHP:
         self.matrix_n_param = self.desc.matrix_n_param
         self.ix_map = self.desc.ix_map
         self.interval_map = self.desc.interval_map
+        # value closures in the reference's layout (mhp.py:475-540): the stratified estimator takes
+        # the saturated value of its single-index terms from them (aslsd_b200.saturation)
+        from aslsd_b200.saturation import value_closures
+        self.psi, self.upsilon = value_closures(self.desc)
 
     def init_estimator(self, estimator, k):
         estimator.n_param_k = 1 + sum(self.matrix_n_param[k])

@@ -294,10 +294,19 @@ int aslsd_exact_plan_rows(aslsd_ctx* ctx, int64_t cap, int64_t* n_rows, int32_t*
  *   rel_alloc[s] = size_s * sqrt(size_s / (size_s - 1)) * std_s, normalised over
  * the group, or default_alloc[s] when every std of the group is zero.  Strata
  * outside any group get default_alloc[s]. */
+/* Saturated samples of the single-index terms (psi_i, upsilonzero_i): for a target further than
+ * sat_t from T_f every upper integration limit has reached +infinity in fp64, and the reference's
+ * per-sample value is one constant - computed by the caller with the reference's own closure
+ * (model.psi[k][i] / model.upsilon[i][i][k] at a large t) and handed in as v_sat, so that the
+ * samples of such strata carry the reference's value bit for bit (its "standard deviation" there
+ * is the rounding residue of numpy's summation, and the next integer allocations depend on it,
+ * :631-645).  sat_t = +infinity (or NaN) switches this off; v_sat only replaces the function value. */
 typedef struct {
   int32_t kind;
   int32_t i, j;
   int32_t n_strata;
+  double sat_t;
+  double v_sat;
 } aslsd_sample_term;
 
 int aslsd_sampled_n_out(const aslsd_ctx* ctx, int k, int term_kind, int i, int j, int32_t* n_out);

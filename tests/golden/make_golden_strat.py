@@ -46,6 +46,21 @@ STRAT_CASES = {
                     dict(n_exact_single=100, n_samples_adaptive_single=200,
                          nonadaptive_sample_size_single=300, n_samples_adaptive_double=600,
                          nonadaptive_sample_size_double=270)),
+    # >= 100 iterations under the fit default grad_alloc=False ("identical integer
+    # allocations over >= 100 iterations"): Gaussian kernels, where most single-index strata are
+    # saturated and their allocation statistic is a rounding residue (aslsd_b200/saturation.py)
+    'strat_gauss1d_long': ('gauss1d', 600., 120, False,
+                           dict(n_exact_single=100, n_samples_adaptive_single=200,
+                                nonadaptive_sample_size_single=300, n_samples_adaptive_double=600,
+                                nonadaptive_sample_size_double=270)),
+    'strat_sbf2d3_long': ('sbf2d3', 500., 100, False,
+                          dict(n_exact_single=100, n_samples_adaptive_single=200,
+                               nonadaptive_sample_size_single=300, n_samples_adaptive_double=600,
+                               nonadaptive_sample_size_double=270)),
+    'strat_exp2d_long': ('exp2d', 400., 100, False,
+                         dict(n_exact_single=100, n_samples_adaptive_single=200,
+                              nonadaptive_sample_size_single=300, n_samples_adaptive_double=600,
+                              nonadaptive_sample_size_double=270)),
 }
 SEED = 4321
 

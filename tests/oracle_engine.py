@@ -257,12 +257,17 @@ class OracleEngine:
         sums, out_off, means, stds = [], [0], [], []
         s_ix = 0
         groups = []
-        for kind, i, j, n_strata in terms:
+        for term in terms:
+            kind, i, j, n_strata = term[:4]
+            sat_t, v_sat = (term[4], term[5]) if len(term) > 4 else (np.inf, 0.)
             group = None
             for s in range(n_strata):
                 a, b = stratum_offsets[s_ix], stratum_offsets[s_ix + 1]
                 vals = OS.term_values(self.plain, k, x_k, self.times, self.T_f, kind, i, j,
                                       ix_m[a:b], None if ix_n is None else ix_n[a:b])
+                if kind < 2:    # saturated samples carry the caller's constant (aslsd_sample_term)
+                    far = (self.T_f - self.times[i][ix_m[a:b]]) >= sat_t
+                    vals[far, 0] = v_sat
                 if roles is not None:
                     w = weight(kind, i, j, ix_m[a:b], None if ix_n is None else ix_n[a:b])
                     vals = vals * (np.asarray(w, dtype=float) * np.ones(b - a))[:, None]

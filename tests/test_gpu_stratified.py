@@ -29,12 +29,15 @@ def test_replay_reference_trace_on_device(engine, name):
     assert worst <= RTOL
 
 
-@pytest.mark.parametrize('name', ['strat_exp1d', 'strat_exp2d'])
+@pytest.mark.parametrize('name', ['strat_exp1d', 'strat_exp2d', 'strat_sbf2d3', 'strat_exp2d_long',
+                                  'strat_gauss1d_long', 'strat_sbf2d3_long'])
 def test_replay_reference_trace_strict(engine, name):
-    """Exponential kernels: per-sample values of the near-constant single-index
-    strata are bit-identical to numpy's and the statistic kernels follow numpy's
-    summation order, so even the rounding-residue allocations - hence every integer
-    sample count and the whole RNG stream - are those of the reference."""
+    """Nothing but the evaluation point is forced: every integer sample count and the whole RNG
+    stream are those of the reference, over up to 120 iterations.  The samples of the
+    saturated single-index strata carry the value of the model's own closures
+    (aslsd_b200/saturation.py) and the statistic kernels follow numpy's summation order, so even
+    the rounding-residue allocations of those strata are the reference's; exponential, Gaussian
+    and sum-of-Gaussians kernels, grad_alloc=False (the fit default)."""
     replay_strat_golden(name, engine, mode='strict', free_running=(name == 'strat_exp1d'))
 
 

@@ -20,6 +20,13 @@ def test_replay_reference_trace(name):
     replay_strat_golden(name, OracleEngine(), mode='forced')
 
 
+@pytest.mark.parametrize('name', ['strat_gauss1d_long', 'strat_sbf2d3_long', 'strat_exp2d_long'])
+def test_replay_long_reference_trace(name):
+    """100 - 120 iterations under grad_alloc=False (the fit default): every integer allocation,
+    hence the whole RNG stream, is the reference's."""
+    replay_strat_golden(name, OracleEngine(), mode='strict')
+
+
 def test_stratification_defaults_match_survey_geometry():
     """Default geometry at N = 10^6 (measured on the reference)."""
     import aslsd_b200
