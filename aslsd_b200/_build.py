@@ -7,7 +7,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
 LIB_DIR = os.path.join(HERE, '_lib')
 LIB = os.path.join(LIB_DIR, 'libaslsd_b200.so')
-SOURCES = ['ctx.cu', 'index_maps.cu', 'plan.cu', 'exact.cu', 'sampled.cu', 'sampler.cu', 'point_sums.cu']
+SOURCES = ['ctx.cu', 'index_maps.cu', 'plan.cu', 'exact.cu', 'sampled.cu', 'sampler.cu', 'point_sums.cu',
+           'simulate.cu']
 HEADERS = ['common.cuh', 'basis_math.cuh', 'pair_kernels.cuh', 'pair_tiles.h', 'plan.h', 'lag_quadrature.cuh',
            os.path.join('..', '..', 'include', 'aslsd_b200.h')]
 FLAGS = ['-O3', '-std=c++17', '-lineinfo', '-gencode', 'arch=compute_100a,code=sm_100a',

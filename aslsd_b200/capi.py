@@ -107,6 +107,9 @@ SYMBOLS = {
     'aslsd_exact_assemble_map_batch': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, c_i32_p,
                                                       ctypes.POINTER(c_f64_p), ctypes.c_int, c_f64_p,
                                                       ctypes.POINTER(c_f64_p)]),
+    'aslsd_simulate': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, c_i32_p, ctypes.POINTER(Basis), c_f64_p,
+                                      ctypes.c_double, ctypes.c_uint64, c_i64_p]),
+    'aslsd_simulate_fetch': (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(c_f64_p)]),
     'aslsd_synchronize': (ctypes.c_int, [ctypes.c_void_p]),
     'aslsd_sampled_n_out': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int,
                                            ctypes.c_int, ctypes.c_int, c_i32_p]),

@@ -188,6 +188,9 @@ struct aslsd_ctx {
   int64_t tables_owner_uid = 0, plan_uid = 0;
   double* d_packed = nullptr; size_t packed_cap = 0;
   bool device_assembly = true;                         // ASLSD_OPT_DEVICE_ASSEMBLY
+  // device-side simulation (simulate.cu): the event pool of the last aslsd_simulate until it is fetched
+  void* sim_state = nullptr;
+  void (*sim_state_free)(void*) = nullptr;
   int64_t model_epoch = 0;    // bumped by set_model / set_option
   int64_t events_epoch = 0;   // bumped by set_events
   int64_t last_work[8] = {0};   // see aslsd_last_work_counts

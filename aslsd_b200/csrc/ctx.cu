@@ -79,6 +79,7 @@ extern "C" int aslsd_destroy(aslsd_ctx* ctx) {
   cudaFree(ctx->d_raw);
   cudaFree(ctx->d_counts);
   if (ctx->plan_cache && ctx->plan_cache_free) ctx->plan_cache_free(ctx->plan_cache);
+  if (ctx->sim_state && ctx->sim_state_free) ctx->sim_state_free(ctx->sim_state);
   cudaFree(ctx->d_sample);
   cudaFree(ctx->d_weights);
   cudaFree(ctx->d_qtab);
@@ -193,9 +194,19 @@ extern "C" int aslsd_set_events(aslsd_ctx* ctx, int d, const int64_t* n_events,
                                 const double* const* times, double T_f) {
   if (!ctx || d <= 0 || !n_events || !times) return aslsd_fail(ctx, ASLSD_ERR_ARG, "set_events: bad arguments");
   CUDA_TRY(ctx, cudaSetDevice(ctx->device));
-  for (int i = 0; i < d; ++i)
+  for (int i = 0; i < d; ++i) {
     if (n_events[i] < 0 || n_events[i] >= (int64_t)2147483000)
       return aslsd_fail(ctx, ASLSD_ERR_ARG, "set_events: event count out of range");
+    if (n_events[i] > 0 && !times[i])
+      return aslsd_fail(ctx, ASLSD_ERR_ARG, "set_events: NULL time array of a type that has events");
+  }
+  // a model of another dimension cannot describe these events: it is dropped (its kernel table
+  // is indexed by k * d + i everywhere), the next sum call asks for aslsd_set_model
+  if (ctx->has_model && (int)ctx->kernels.size() != d * d) {
+    ctx->has_model = false;
+    ctx->kernels.clear();
+    ctx->model_epoch++;
+  }
   // layout: every type starts on a 16 B boundary and is followed by >= 2 pad doubles
   // so that aligned bulk copies may over-read
   std::vector<int64_t> off(d + 1, 0), tab_off(d + 1, 0), tab_len(d, 1);

@@ -221,6 +221,39 @@ class Engine:
                     nbytes += 8 * int(n[i] + n[j])
         return ms, nbytes
 
+    # ---- simulation --------------------------------------------------------------------
+    def simulate(self, model, mu, kernel_param, T_f, seed=1234):
+        """Cluster simulation of the MHP ``model`` on the device (aslsd_simulate; the generation
+        loop of MHP.simulate, mhp.py:733-854): ``kernel_param[i][j]`` are the free parameters of
+        phi_ij as in the reference, ``mu`` the baselines.  Returns ``list_times``.  Same law as
+        the reference's simulator, not its random numbers."""
+        desc = describe_model(model)
+        d = desc.d
+        flat = []
+        n_basis = (ctypes.c_int32 * (d * d))()
+        for i in range(d):
+            for j in range(d):
+                params = iter(np.asarray(kernel_param[i][j], dtype=np.float64))
+                n_basis[i * d + j] = len(desc.bases[i][j])
+                for type_name, free_mask, fixed in desc.bases[i][j]:
+                    nv = 2 if type_name == 'ExponentialKernel' else 3
+                    flat.append((type_name, [float(next(params)) if (free_mask >> q) & 1 else float(fixed[q])
+                                             for q in range(nv)]))
+        arr = (capi.Basis * max(1, len(flat)))()
+        for ix, (type_name, v) in enumerate(flat):
+            arr[ix].type = capi.BASIS_EXPONENTIAL if type_name == 'ExponentialKernel' else capi.BASIS_GAUSSIAN
+            arr[ix].free_mask = 0
+            for q, val in enumerate(v):
+                arr[ix].fixed[q] = val
+        mu = capi.as_f64(mu)
+        counts = np.zeros(d, dtype=np.int64)
+        self._check(self._lib.aslsd_simulate(self._ctx, d, n_basis, arr, capi.ptr_f64(mu), float(T_f),
+                                             ctypes.c_uint64(int(seed) & (2 ** 64 - 1)), capi.ptr_i64(counts)))
+        times = [np.empty(int(n), dtype=np.float64) for n in counts]
+        ptrs = (capi.c_f64_p * d)(*[capi.ptr_f64(t) for t in times])
+        self._check(self._lib.aslsd_simulate_fetch(self._ctx, ptrs))
+        return times
+
     # ---- model -----------------------------------------------------------------------
     def set_model(self, model):
         desc = describe_model(model)

@@ -168,6 +168,11 @@ class ProcessPath:
 
     def get_book_keeping(self, only_missing=False):
         self.list_times2end = [self.T_f - L for L in self.list_times]
+        if self.d == 0:
+            # an empty path (``p = ProcessPath(); p.load(file)``, episodes.py:147): nothing to index,
+            # no device context needed
+            self.kappa, self.varpi, self.lag_sizes = [], [], []
+            return
         for t in self.list_times:
             if len(t) == 0:
                 raise IndexError('ProcessPath: an event type has no events')

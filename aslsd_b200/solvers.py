@@ -42,6 +42,10 @@ class ADAM:
         self.momentum_term_1 = 0.
         self.momentum_term_2 = 0.
         self.t = 0
+        if kwargs.get('clipping', False):
+            # the reference clips the gradient against a window of its past magnitudes
+            # (solver.py:78-95); a fit configured that way must use the reference's own solver
+            raise NotImplementedError('gradient clipping is not mirrored: pass the reference\'s ADAM')
         self.learning_rate = make_learning_rate(**kwargs)
 
     def iterate(self, t, x, grad):

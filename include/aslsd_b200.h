@@ -237,6 +237,18 @@ int aslsd_exact_packed_device_batch(aslsd_ctx* ctx, int n_k, const int* ks, cons
  * operations - same arguments and results as aslsd_exact_assemble_batch (no device work). */
 int aslsd_exact_assemble_map_batch(aslsd_ctx* ctx, int n_k, const int* ks, const double* const* xs,
                                    int flags, const double* raw_host, double* const* outs);
+/* ---- simulation ---------------------------------------------------------------------------
+ * Cluster (branching) simulation of a linear Hawkes process on the device: the generation loop of
+ * MHP.simulate (models/hawkes/linear/mhp.py:733-854).  Same law as the reference, not its random
+ * numbers (counter-based Philox streams keyed by `seed`).  bases: the d x d kernels phi_ij in
+ * row-major order (child type i, parent type j), n_basis[i * d + j] entries each, every basis with
+ * all its variables in `fixed` (omega, beta[, delta]; free_mask ignored); mu: d baseline rates.
+ * aslsd_simulate leaves the sorted event times on the device and returns the counts per type;
+ * aslsd_simulate_fetch copies them into the caller's arrays (n_events[i] doubles) and frees the pool. */
+int aslsd_simulate(aslsd_ctx* ctx, int d, const int32_t* n_basis, const aslsd_basis* bases,
+                   const double* mu, double T_f, uint64_t seed, int64_t* n_events);
+int aslsd_simulate_fetch(aslsd_ctx* ctx, double* const* times);
+
 /* Wait for everything enqueued on the context's stream. */
 int aslsd_synchronize(aslsd_ctx* ctx);
 

@@ -92,4 +92,23 @@ cudaError_t cudaEventSynchronize(cudaEvent_t) { return cudaSuccess; }
 cudaError_t cudaEventQuery(cudaEvent_t) { return cudaSuccess; }
 cudaError_t cudaEventElapsedTime(float* ms, cudaEvent_t, cudaEvent_t) { *ms = 0.f; return cudaSuccess; }
 
+// what the CUB dispatch layers (simulate.cu: scan, radix sort) ask the runtime before launching
+cudaError_t cudaGetDevice(int* dev) { *dev = 0; return cudaSuccess; }
+cudaError_t cudaPeekAtLastError(void) { return cudaSuccess; }
+cudaError_t cudaDeviceGetAttribute(int* v, cudaDeviceAttr a, int) {
+  *v = a == cudaDevAttrMultiProcessorCount ? 148 : a == cudaDevAttrComputeCapabilityMajor ? 10
+     : a == cudaDevAttrComputeCapabilityMinor ? 0 : 65536;
+  return cudaSuccess;
+}
+cudaError_t cudaFuncGetAttributes(cudaFuncAttributes* a, const void*) {
+  std::memset(a, 0, sizeof(*a));
+  a->maxThreadsPerBlock = 1024;
+  a->ptxVersion = a->binaryVersion = 100;
+  return cudaSuccess;
+}
+cudaError_t cudaOccupancyMaxActiveBlocksPerMultiprocessorWithFlags(int* n, const void*, int, size_t, unsigned) {
+  *n = 1;
+  return cudaSuccess;
+}
+
 }  // extern "C"

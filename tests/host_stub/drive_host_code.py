@@ -182,6 +182,14 @@ def main():
     import test_gpu_stratified
     test_gpu_exact.test_errors(engine)
     test_gpu_stratified.test_sampled_sums_reject_bad_indices(engine)
+    # simulation: spawn tables, pool sizing, the generation loop's bookkeeping and the error codes
+    # (the stub's kernels draw nothing, so no event is ever born)
+    import test_gpu_simulate
+    test_gpu_simulate.test_simulation_rejects_unstable_models(engine)
+    for name in ('exp2d', 'sbf2d3', 'mix2d'):
+        model, mu, kp, _ = CASES[name]
+        times = engine.simulate(model, mu, kp, 50., seed=5)
+        assert len(times) == model['d']
     engine.close()
     print('host code ok')
 
