@@ -189,6 +189,21 @@ static void build_stream(const aslsd_ctx* ctx, BatchPlan& B, const std::vector<i
   S.J = (int32_t)nb;
   S.ucap = ucap;
   S.shape = small ? LQ_SHAPE_SMALL : LQ_SHAPE_BIG;
+  {
+    // targets per tile: the pairs of a tile should fit one chunk (a second, nearly empty chunk pays the
+    // barriers, scans and short loops of a full one) - 90 % of a chunk at the stream's mean density.
+    // C5 (14 sources per target, 1 792 pairs per chunk, 128 targets overflowing every second tile):
+    // 10.56 ms at 128 targets, 10.45 at 115, 10.74 at 102, 11.97 at 77 - the fixed cost per tile
+    // (searches, scans, barriers) weighs more than the second chunk (gpurun_out / profiles r2_o_fill)
+    const int nt_shape = small ? LqSmall::NT : LqBig::NT;
+    const int64_t n_src = ctx->n_events[first.src_dim];
+    const double* ts = ctx->h_times[first.src_dim];
+    const double span = n_src > 1 ? ts[n_src - 1] - ts[0] : 0.;
+    const double per_target = span > 0. ? std::max(1e-3, (double)n_src * s_max / span) : (double)n_src;
+    double tmf = 0.9 * (double)ucap / per_target;
+    if (const char* e = std::getenv("ASLSD_LQ_FILL")) tmf = std::atof(e) * (double)ucap / per_target;   // tuning
+    S.tm = (int32_t)std::max(8., std::min((double)nt_shape, std::floor(tmf)));
+  }
   S.wa_off = first.wa_off;
   S.wb_off = first.wb_off;
   while ((1 << S.nbits) < S.J) ++S.nbits;

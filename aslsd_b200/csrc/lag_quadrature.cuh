@@ -70,17 +70,21 @@ struct LqShape {
   static constexpr int GS = NT >= 1024 ? 16 : (NT >= 512 ? 8 : (NT >= 256 ? 4 : 2));
   static constexpr int TM = NT;     // targets per tile: one per thread
   static constexpr int SMAX = NT >= 512 ? 2048 : (NT >= 256 ? 1024 : 512);   // staged source events per tile (two buffers)
-  static constexpr int SMEM_BUDGET = (CTAS == 1 ? 220 : (CTAS == 2 ? 110 : (CTAS == 3 ? 73 : 54))) * 1024;
+  static constexpr int SMEM_BUDGET = CTAS == 1 ? 220 * 1024 : (CTAS == 2 ? 110 * 1024 : (CTAS == 3 ? 73 * 1024 : (224 * 1024) / CTAS - 2048));
   static constexpr int ONE_BIN_J = NW * (32 / GS);   // bins the groups of lanes can own for a whole work unit
 };
 typedef LqShape<512, 1> LqBig;
-typedef LqShape<128, 4> LqSmall;
+#ifndef LQ_SMALL_CTAS
+#define LQ_SMALL_CTAS 4
+#endif
+typedef LqShape<128, LQ_SMALL_CTAS> LqSmall;
 enum { LQ_SHAPE_BIG = 0, LQ_SHAPE_SMALL = 1 };
 
 struct QStreamDev {
   int32_t tgt_dim, src_dim, same, J;
   int32_t n_chunks, ucap;  // work units; pairs sorted at a time (multiple of the shape's NT)
   int32_t nbits, shape;    // bits of the bin index; LQ_SHAPE_* of the CTAs that take this stream
+  int32_t tm, pad;         // targets per tile (<= the shape's NT): sized so that the pairs of a tile fit one chunk
   int64_t m_lo, m_hi;      // interior target block
   int64_t tpw;             // targets per work unit
   int64_t wu_first;        // first work unit (prefix over streams)
@@ -95,8 +99,18 @@ struct QStreamDev {
 __constant__ double LQ_X[LQ_ND];
 __constant__ double LQ_CT[LQ_ND * LQ_ND];   // [i][d]
 
-// dynamic shared memory: [pair-order lags / coordinates | sorted coordinates | 2 source windows |
-//                         moment table | keys | bin starts | histograms]
+// what pass 1 needs of a tile's target to form the lags of its pairs: the pairs of a tile are numbered
+// target-major, pair q of the chunk starting at pair c0 belongs to the target with pre <= c0 + q <
+// pre + cnt and pairs it with window entry base + c0 + q
+struct __align__(16) LqTarget {
+  double t;
+  int32_t base;   // (first source - window start) - pre
+  int32_t pad;
+};
+#define LQ_HEAD 0x80000000u   // s_key entries with this bit: 1 + the target that owns the pair (pass 1 input)
+
+// dynamic shared memory: [pair-order coordinates | sorted coordinates | 2 source windows |
+//                         moment table | target records | keys | bin starts | histograms | cursors]
 template <class C>
 __host__ __device__ inline size_t lq_smem_bytes(int J, int ucap, bool weighted) {
   size_t b = 0;
@@ -105,7 +119,8 @@ __host__ __device__ inline size_t lq_smem_bytes(int J, int ucap, bool weighted) 
   b += (size_t)J * LQ_ND * sizeof(double);
   b += (size_t)ucap * sizeof(uint32_t);
   b += (size_t)(J + 2) * sizeof(int32_t);
-  b += (size_t)C::NW * J * sizeof(uint16_t);
+  b += (size_t)C::NW * J * sizeof(uint16_t) * (J <= 64 ? 2 : 1);
+  b += (size_t)C::NT * (sizeof(LqTarget) + (weighted ? sizeof(double) : 0));
   return b + 64;
 }
 
@@ -197,21 +212,49 @@ __device__ __forceinline__ void lq_bin(double s, double inv_h, int& b, double& v
   v = xb - (tr - LQ_MAGIC);
 }
 
-// Pass 1 of the counting sort over the n_c pairs of a chunk (see the file header): s_val holds
-// the lags in pair order on entry, the bin positions on exit.  Two warp steps per iteration:
-// the ballots of the two are independent, the histogram updates are ordered.
-template <int NB, class C>
-__device__ __forceinline__ void lq_pass1(int n_c, double inv_h, uint16_t* my_hist, uint32_t* s_key,
-                                         double* s_val) {
+// Pass 1 of the counting sort over the n_c pairs of a chunk (see the file header).  On entry s_key
+// marks, for every target, the first of its pairs in the chunk and every 32nd slot after it
+// (LQ_HEAD | 1 + target): a lane finds the owner of its pair from a ballot of the marks of its warp
+// step (lane 0 always carries one), forms the lag from the target's record and the source window,
+// and leaves (bin, rank in warp) in s_key and the position inside the bin in s_val.  No pass over the
+// pairs by the targets' threads, whose pair counts differ (measured: 37 % of the instructions of the
+// kernel before).  Two warp steps per iteration: the ballots of the two are independent, the
+// histogram updates are ordered.
+template <bool STAGED, bool WEIGHTED>
+__device__ __forceinline__ double lq_pair_lag(uint32_t own, unsigned le_mask, int q, int c0,
+                                              const LqTarget* __restrict__ s_tgt, const double* __restrict__ s_tw,
+                                              const double* __restrict__ win, const double* __restrict__ src_glb,
+                                              const double* __restrict__ w_src, double& w) {
+  const unsigned heads = __ballot_sync(0xffffffffu, (int32_t)own < 0);
+  const int hl = 31 - __clz(heads & le_mask);
+  const int m = (int)(__shfl_sync(0xffffffffu, own, hl) & 0xffffu) - 1;
+  const LqTarget T = s_tgt[m];
+  const int idx = T.base + c0 + q;
+  if (WEIGHTED) {
+    w = s_tw[m];
+    if (w_src) w *= w_src[idx];
+  }
+  return T.t - (STAGED ? win[idx] : __ldg(src_glb + idx));
+}
+
+template <int NB, bool STAGED, bool WEIGHTED, class C>
+__device__ __forceinline__ void lq_pass1(int n_c, int c0, double inv_h, uint16_t* my_hist, uint32_t* s_key,
+                                         double* s_val, double* s_wv, const LqTarget* __restrict__ s_tgt,
+                                         const double* __restrict__ s_tw, const double* __restrict__ win,
+                                         const double* __restrict__ src_glb, const double* __restrict__ w_src) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const unsigned lt_mask = (1u << lane) - 1u;
+  const unsigned le_mask = lt_mask | (1u << lane);
   const int n_steps = (n_c + 31) >> 5;
   const int n_full = n_c >> 5;   // steps whose 32 pairs all exist
   int st = warp;
   // full steps, two per iteration: no lane masks, no liveness tests
   for (; st + C::NW < n_full; st += 2 * C::NW) {
     const int qa = st * 32 + lane, qb = qa + C::NW * 32;
-    const double sa = s_val[qa], sb = s_val[qb];
+    const uint32_t oa = s_key[qa], ob = s_key[qb];
+    double wa = 1., wb = 1.;
+    const double sa = lq_pair_lag<STAGED, WEIGHTED>(oa, le_mask, qa, c0, s_tgt, s_tw, win, src_glb, w_src, wa);
+    const double sb = lq_pair_lag<STAGED, WEIGHTED>(ob, le_mask, qb, c0, s_tgt, s_tw, win, src_glb, w_src, wb);
     int ba, bb;
     double va, vb;
     lq_bin(sa, inv_h, ba, va);
@@ -224,22 +267,27 @@ __device__ __forceinline__ void lq_pass1(int n_c, double inv_h, uint16_t* my_his
     if (ra == 0) my_hist[ba] = (uint16_t)(base_a + __popc(pa));
     s_key[qa] = (uint32_t)ba | ((uint32_t)(base_a + ra) << 10);
     s_val[qa] = va;
+    if (WEIGHTED) s_wv[qa] = wa;
     __syncwarp();
     const int base_b = my_hist[bb];
     __syncwarp();
     if (rb == 0) my_hist[bb] = (uint16_t)(base_b + __popc(pb));
     s_key[qb] = (uint32_t)bb | ((uint32_t)(base_b + rb) << 10);
     s_val[qb] = vb;
+    if (WEIGHTED) s_wv[qb] = wb;
     __syncwarp();
   }
   // the remaining steps of this warp (at most two, the last one of the chunk possibly partial):
-  // idle lanes redo pair 0 and are masked out of every peer set
+  // idle lanes redo the last pair and are masked out of every peer set
   for (; st < n_steps; st += C::NW) {
     const int qa = st * 32 + lane;
     const bool live_a = qa < n_c;
     const int left_a = n_c - st * 32;
     const unsigned mask_a = left_a >= 32 ? 0xffffffffu : ((1u << left_a) - 1u);
-    const double sa = s_val[live_a ? qa : 0];
+    const uint32_t oa = live_a ? s_key[qa] : 0u;
+    double wa = 1.;
+    const double sa = lq_pair_lag<STAGED, WEIGHTED>(oa, le_mask, live_a ? qa : n_c - 1, c0, s_tgt, s_tw, win, src_glb,
+                                                    w_src, wa);
     int ba;
     double va;
     lq_bin(sa, inv_h, ba, va);
@@ -251,6 +299,7 @@ __device__ __forceinline__ void lq_pass1(int n_c, double inv_h, uint16_t* my_his
       if (ra == 0) my_hist[ba] = (uint16_t)(base_a + __popc(pa));
       s_key[qa] = (uint32_t)ba | ((uint32_t)(base_a + ra) << 10);
       s_val[qa] = va;
+      if (WEIGHTED) s_wv[qa] = wa;
     }
     __syncwarp();
   }
@@ -364,9 +413,10 @@ lag_moment_kernel(const DimDev* __restrict__ dims, const QStreamDev* __restrict_
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ __align__(8) uint64_t s_bar[2];
   __shared__ int64_t s_a0[2];        // first source index of each window buffer
-  __shared__ int64_t s_next_lo;      // window start of the tile's last target
-  __shared__ double s_tlast;         // time of the tile's last target
-  __shared__ int32_t s_warp[C::NW];    // pair counts of a tile fit 32 bits (host guard, build_stream)
+  // barriers per tile: one after the pair counts of the warps, then per chunk one before pass 1, one
+  // after it and one after pass 2 - what a tile writes before its first barrier is double-buffered
+  __shared__ int64_t s_next_lo[2];   // window start of the tile's last target
+  __shared__ int32_t s_warp[2][C::NW];   // pair counts of a tile fit 32 bits (host guard, build_stream)
   __shared__ int32_t s_scan[C::NW];
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -389,12 +439,16 @@ lag_moment_kernel(const DimDev* __restrict__ dims, const QStreamDev* __restrict_
   double* s_wu = s_wv + (weighted ? ucap : 0);      // pair weights, sorted by bin
   double* s_src = s_wu + (weighted ? ucap : 0);     // two buffers of C::SMAX + 2
   double* s_M = s_src + 2 * (C::SMAX + 2);
-  uint32_t* s_key = (uint32_t*)(s_M + (size_t)J * LQ_ND);
+  LqTarget* s_tgt = (LqTarget*)(s_M + (size_t)J * LQ_ND);   // 16-byte aligned: every block before it is
+  double* s_tw = (double*)(s_tgt + C::NT);                  // target weights (weighted streams)
+  uint32_t* s_key = (uint32_t*)(s_tw + (weighted ? C::NT : 0));
   int32_t* s_bin = (int32_t*)(s_key + ucap);
   uint16_t* s_hist = (uint16_t*)(s_bin + (J + 2));
   uint16_t* my_hist = s_hist + warp * J;
+  uint16_t* s_cur = s_hist + C::NW * J;             // cursors of the warps' own scans (J <= 64)
 
   for (int x = tid; x < J * LQ_ND; x += C::NT) s_M[x] = 0.;
+  for (int x = tid; x < ucap; x += C::NT) s_key[x] = 0u;   // no marks (pass 1 leaves none behind)
   if (tid == 0) {
     mbar_init(&s_bar[0], 1);
     mbar_init(&s_bar[1], 1);
@@ -423,22 +477,23 @@ lag_moment_kernel(const DimDev* __restrict__ dims, const QStreamDev* __restrict_
   for (int d = 0; d < LQ_ND; ++d) racc[d] = 0.;
 
   int tile = 0;
-  for (int64_t m0 = m_begin; m0 < m_end; m0 += C::TM, ++tile) {
-    const int nt = (int)min((int64_t)C::TM, m_end - m0);
+  const int tm = S.tm;
+  for (int64_t m0 = m_begin; m0 < m_end; m0 += tm, ++tile) {
+    const int nt = (int)min((int64_t)tm, m_end - m0);
     const int buf = tile & 1;
     double* win = s_src + buf * (C::SMAX + 2);
     // ---- a. per-target source ranges ---------------------------------------------------------
     const double t = t_mine;
-    if (tid == nt - 1) s_tlast = t;
-    if (m0 + C::TM + tid < m_end) t_mine = Dt.t[m0 + C::TM + tid];   // next tile's target, in flight
+    const double t_last = __ldg(Dt.t + m0 + nt - 1);
+    if (m0 + tm + tid < m_end) t_mine = Dt.t[m0 + tm + tid];   // next tile's target, in flight
+    // the window and its first index (written before the copy was issued) are visible to whoever
+    // sees the copy complete
     mbar_wait(&s_bar[buf], (parity >> buf) & 1u);
     parity ^= 1u << buf;
-    __syncthreads();
     const int64_t a0 = s_a0[buf];
     const int n_win = (int)min((int64_t)C::SMAX, n_src_padded - a0);
     // the window serves the tile if it reaches the end of the stream or the last target (same type:
     // by index, ties in time included; other types: by time, the searches are lower bounds)
-    const double t_last = s_tlast;
     const bool staged = (a0 + n_win >= Ds.n) ||
                         (same ? (a0 + n_win >= m0 + nt - 1) : (win[n_win - 1] >= t_last));
     const int n_valid = (int)min((int64_t)n_win, Ds.n - a0);   // entries that are events, not padding
@@ -478,7 +533,7 @@ lag_moment_kernel(const DimDev* __restrict__ dims, const QStreamDev* __restrict_
         lo_abs = min(dim_lower_bound(Ds, t - S.s_max), hi);
       }
       cnt = (int32_t)(hi - lo_abs);
-      if (tid == nt - 1) s_next_lo = lo_abs;
+      if (tid == nt - 1) s_next_lo[buf] = lo_abs;
     }
     int32_t incl = cnt;
 #pragma unroll
@@ -486,74 +541,98 @@ lag_moment_kernel(const DimDev* __restrict__ dims, const QStreamDev* __restrict_
       const int32_t v = __shfl_up_sync(0xffffffffu, incl, o);
       if (lane >= o) incl += v;
     }
-    if (lane == 31) s_warp[warp] = incl;
+    if (lane == 31) s_warp[buf][warp] = incl;
+    fence_proxy_async();   // this thread's generic reads of the other window (previous tile) before its refill
     __syncthreads();
     int32_t pre = incl - cnt, total = 0;
 #pragma unroll
     for (int w = 0; w < C::NW; ++w) {
-      const int32_t v = s_warp[w];
+      const int32_t v = s_warp[buf][w];
       if (w < warp) pre += v;
       total += v;
     }
-    // next tile's window into the other buffer (its readers finished before the previous tile's
-    // closing barrier)
-    if (tid == 0 && m0 + C::TM < m_end) {
-      const int64_t a1 = s_next_lo & ~(int64_t)1;
+    // next tile's window into the other buffer (its readers, the previous tile's searches and pass 1,
+    // are behind that tile's barriers)
+    if (tid == 0 && m0 + tm < m_end) {
+      const int64_t a1 = s_next_lo[buf] & ~(int64_t)1;
       s_a0[buf ^ 1] = a1;
       const int64_t n_stage = min((int64_t)C::SMAX, n_src_padded - a1);
       mbar_expect_tx(&s_bar[buf ^ 1], (uint32_t)(n_stage * sizeof(double)));
       tma_load_1d(s_src + (buf ^ 1) * (C::SMAX + 2), Ds.t + a1, (uint32_t)(n_stage * sizeof(double)),
                   &s_bar[buf ^ 1]);
     }
-    const double* my_win = win + (int)(lo_abs - a0);    // shared (staged tiles)
-    const double* my_glb = Ds.t + lo_abs;               // global (fallback)
     n_pairs += (unsigned long long)cnt;
+    // the target's record for pass 1 (the previous tile's readers are behind the barrier after its pass 1)
+    {
+      LqTarget rec;
+      rec.t = t;
+      rec.base = (int32_t)(lo_abs - a0) - pre;
+      rec.pad = 0;
+      s_tgt[tid] = rec;
+      if (weighted) s_tw[tid] = (S.wa_off >= 0 && tid < nt) ? weights[S.wa_off + m0 + tid] : 1.;
+    }
+    const double* src_glb = Ds.t + a0;                                        // fallback tiles
+    const double* w_src = (weighted && S.wb_off >= 0) ? weights + S.wb_off + a0 : nullptr;
 
     // ---- b / c. chunks of at most ucap pairs ------------------------------------------------------
     for (int32_t c0 = 0; c0 < total; c0 += ucap) {
       const int32_t n_c = min(ucap, total - c0);
-      // lags of the chunk in pair order (target-major), written by the targets' threads;
+      // marks for pass 1: the first pair of every target in the chunk and every 32nd slot it covers;
       // histograms to zero
       {
-        const int32_t ra = min(max(c0 - pre, 0), cnt), rb = min(max(c0 + n_c - pre, 0), cnt);
-        double* dst = s_val + (pre - c0);
-        if (weighted) {
-          // weight(target) x weight(source) per pair (mtlh_exact_estimator.py:838, :896-897)
-          const double w_m = (S.wa_off >= 0 && tid < nt) ? weights[S.wa_off + m0 + tid] : 1.;
-          double* dw = s_wv + (pre - c0);
-          for (int32_t r = ra; r < rb; ++r)
-            dw[r] = S.wb_off >= 0 ? w_m * weights[S.wb_off + lo_abs + r] : w_m;
-        }
-        if (staged) {
-          int32_t r = ra;
-          for (; r + 3 < rb; r += 4) {
-            const double s0 = my_win[r], s1 = my_win[r + 1], s2 = my_win[r + 2], s3 = my_win[r + 3];
-            dst[r] = t - s0;
-            dst[r + 1] = t - s1;
-            dst[r + 2] = t - s2;
-            dst[r + 3] = t - s3;
-          }
-          for (; r + 1 < rb; r += 2) {
-            const double s0 = my_win[r], s1 = my_win[r + 1];
-            dst[r] = t - s0;
-            dst[r + 1] = t - s1;
-          }
-          if (r < rb) dst[r] = t - my_win[r];
-        } else {
-          for (int32_t r = ra; r < rb; ++r) dst[r] = t - __ldg(my_glb + r);
+        const int32_t qa = max(pre - c0, 0), qb = min(pre + cnt - c0, n_c);
+        if (qa < qb) {
+          const uint32_t mark = LQ_HEAD | (uint32_t)(tid + 1);
+          s_key[qa] = mark;
+          for (int32_t q = (qa & ~31) + 32; q < qb; q += 32) s_key[q] = mark;
         }
       }
       for (int x = tid; x < (C::NW * J + 1) / 2; x += C::NT) ((uint32_t*)s_hist)[x] = 0u;
       __syncthreads();
       // pass 1: bin, position in the bin, rank among the equal bins seen so far by this warp
-      if (nbits <= 5) lq_pass1<5, C>(n_c, inv_h, my_hist, s_key, s_val);
-      else if (nbits == 6) lq_pass1<6, C>(n_c, inv_h, my_hist, s_key, s_val);
-      else if (nbits == 7) lq_pass1<7, C>(n_c, inv_h, my_hist, s_key, s_val);
-      else lq_pass1<10, C>(n_c, inv_h, my_hist, s_key, s_val);
+#define LQ_PASS1(NB, STAGED) \
+  lq_pass1<NB, STAGED, WEIGHTED, C>(n_c, c0, inv_h, my_hist, s_key, s_val, s_wv, s_tgt, s_tw, win, src_glb, w_src)
+      if (!staged) LQ_PASS1(10, false);
+      else if (nbits <= 5) LQ_PASS1(5, true);
+      else if (nbits == 6) LQ_PASS1(6, true);
+      else if (nbits == 7) LQ_PASS1(7, true);
+      else LQ_PASS1(10, true);
+#undef LQ_PASS1
       __syncthreads();
       // bin totals -> bin starts; per-warp cursors = start + counts of the lower warps
-      // (thread tid owns the jpt consecutive bins from tid * jpt)
-      {
+      const uint16_t* my_cur = my_hist;
+      if (J <= 64) {
+        // few bins: every warp scans all of them for itself (lane: J / 32 adjacent bins) and keeps its
+        // own cursors - no barrier between the scan and pass 2, which only moves the warp's own pairs
+        const int bpl = J >> 5;   // J is a multiple of 32
+        int32_t tot0 = 0, tot1 = 0, below0 = 0, below1 = 0;
+#pragma unroll
+        for (int w = 0; w < C::NW; ++w) {
+          const uint32_t v = bpl == 2 ? ((const uint32_t*)(s_hist + w * J))[lane] : (uint32_t)s_hist[w * J + lane];
+          const int32_t c_lo = (int32_t)(v & 0xffffu), c_hi = (int32_t)(v >> 16);
+          if (w < warp) { below0 += c_lo; below1 += c_hi; }
+          tot0 += c_lo;
+          tot1 += c_hi;
+        }
+        int32_t inc = tot0 + tot1;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const int32_t v = __shfl_up_sync(0xffffffffu, inc, o);
+          if (lane >= o) inc += v;
+        }
+        const int32_t start0 = inc - tot0 - tot1, start1 = start0 + tot0;
+        uint16_t* cur = s_cur + warp * J;
+        if (bpl == 2) ((uint32_t*)cur)[lane] = (uint32_t)(start0 + below0) | ((uint32_t)(start1 + below1) << 16);
+        else cur[lane] = (uint16_t)(start0 + below0);
+        if (warp == 0) {
+          s_bin[lane * bpl] = start0;
+          if (bpl == 2) s_bin[lane * 2 + 1] = start1;
+          if (lane == 31) s_bin[J] = inc;
+        }
+        my_cur = cur;
+        __syncwarp();
+      } else {
+        // (thread tid owns the jpt consecutive bins from tid * jpt)
         const int jpt = (J + C::NT - 1) / C::NT;
         const bool owns_bins = warp * 32 * jpt < J;   // warp-uniform: the other warps only meet the barrier
         int32_t tot = 0, inc = 0;
@@ -591,8 +670,8 @@ lag_moment_kernel(const DimDev* __restrict__ dims, const QStreamDev* __restrict_
             }
           }
         }
+        __syncthreads();
       }
-      __syncthreads();
       // pass 2: coordinates to their sorted slots (pair q was ranked by warp (q / 32) % C::NW = warp)
       {
         int32_t q = tid;
@@ -608,7 +687,7 @@ lag_moment_kernel(const DimDev* __restrict__ dims, const QStreamDev* __restrict_
             if (weighted) wv[x] = s_wv[q + x * C::NT];
           }
 #pragma unroll
-          for (int x = 0; x < 4; ++x) pos[x] = (int)my_hist[key[x] & 1023u] + (int)(key[x] >> 10);
+          for (int x = 0; x < 4; ++x) pos[x] = (int)my_cur[key[x] & 1023u] + (int)(key[x] >> 10);
 #pragma unroll
           for (int x = 0; x < 4; ++x) {
             s_u[pos[x]] = val[x];
@@ -618,7 +697,7 @@ lag_moment_kernel(const DimDev* __restrict__ dims, const QStreamDev* __restrict_
         for (; q < n_c; q += C::NT) {
           const uint32_t key = s_key[q];
           const int b = (int)(key & 1023u);
-          const int pos = (int)my_hist[b] + (int)(key >> 10);
+          const int pos = (int)my_cur[b] + (int)(key >> 10);
           s_u[pos] = s_val[q];
           if (weighted) s_wu[pos] = s_wv[q];
         }
@@ -645,15 +724,13 @@ lag_moment_kernel(const DimDev* __restrict__ dims, const QStreamDev* __restrict_
           lq_reduce_store<C>(acc, qg, b < J && e1 > e0, s_M + (size_t)min(b, J - 1) * LQ_ND);
         }
       }
-      __syncthreads();
+      // no barrier here: what the moments read (sorted coordinates, bin starts) is next written behind
+      // the barrier after the next pass 1, what is written before it (marks, histograms, target
+      // records) was last read before the barrier after pass 2
     }
-    fence_proxy_async();   // generic reads of this window before a later tile's async write
-    __syncthreads();
   }
-  if (one_bin) {
-    lq_reduce_store<C>(racc, qg, my_bin < J, s_M + (size_t)min(my_bin, J - 1) * LQ_ND);
-    __syncthreads();
-  }
+  if (one_bin) lq_reduce_store<C>(racc, qg, my_bin < J, s_M + (size_t)min(my_bin, J - 1) * LQ_ND);
+  __syncthreads();
   // ---- one partial moment table per work unit ---------------------------------------------------
   double* out = partials + S.part_first + (int64_t)chunk * J * LQ_ND;
   for (int x = tid; x < J * LQ_ND; x += C::NT) out[x] = s_M[x];

@@ -1,4 +1,8 @@
-"""Work-unit count of the moment kernel (ASLSD_LQ_UNITS) against its time on the C5 step."""
+"""Tuning knobs of the moment kernel against its time on the C5 step:
+
+    python scripts/units_sweep.py [ENV_NAME] value ...     # default ASLSD_LQ_UNITS (work-unit count);
+                                                            # ASLSD_LQ_FILL: mean pairs of a tile / chunk capacity
+"""
 import json, os, subprocess, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 code = r'''
@@ -15,7 +19,11 @@ for rep in range(7):
 im = min(eng.index_maps_kernel_time()[0] for _ in range(4))
 print(json.dumps({'units': %r, 'moment_ms': float(np.mean(ms)), 'min': float(np.min(ms)), 'index_maps_ms': im}))
 '''
-for units in sys.argv[1:]:
-    env = dict(os.environ, ASLSD_LQ_UNITS=units)
+args = sys.argv[1:]
+name = 'ASLSD_LQ_UNITS'
+if args and args[0].startswith('ASLSD_'):
+    name, args = args[0], args[1:]
+for units in args:
+    env = dict(os.environ, **{name: units})
     r = subprocess.run([sys.executable, '-c', code % (ROOT, units)], env=env, capture_output=True, text=True)
     print(r.stdout.strip().split('\n')[-1] if r.returncode == 0 else r.stderr[-500:], flush=True)
