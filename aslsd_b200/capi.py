@@ -60,6 +60,7 @@ SYMBOLS = {
     'aslsd_measure_fp64_peak': (ctypes.c_int, [ctypes.c_void_p, c_f64_p]),
     'aslsd_set_events': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, c_i64_p,
                                         ctypes.POINTER(c_f64_p), ctypes.c_double]),
+    'aslsd_set_horizon': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_double]),
     'aslsd_index_map_sizes': (ctypes.c_int, [ctypes.c_void_p, c_i64_p, c_i64_p]),
     'aslsd_index_maps': (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(c_i64_p),
                                         ctypes.POINTER(c_i64_p), ctypes.POINTER(c_i64_p)]),

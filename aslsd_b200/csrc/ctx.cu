@@ -390,6 +390,16 @@ extern "C" int aslsd_set_events(aslsd_ctx* ctx, int d, const int64_t* n_events,
   return ASLSD_OK;
 }
 
+extern "C" int aslsd_set_horizon(aslsd_ctx* ctx, double T_f) {
+  if (!ctx || !(T_f > 0.) || !std::isfinite(T_f)) return aslsd_fail(ctx, ASLSD_ERR_ARG, "set_horizon: bad arguments");
+  if (ctx->d <= 0) return aslsd_fail(ctx, ASLSD_ERR_ARG, "set_horizon: no events set");
+  if (T_f != ctx->T_f) {
+    ctx->T_f = T_f;
+    ctx->events_epoch++;   // interior / boundary split of every plan, cached quadrature weights
+  }
+  return ASLSD_OK;
+}
+
 // Per-event weight vectors: the impact values I_ki(xi^i_n) of a marked model and their
 // parameter derivatives, evaluated by the reference's own impact objects on the host
 // (functionals/impact_functions/impact_function.py:116-131) once per evaluation point.

@@ -298,16 +298,23 @@ static int build_work(aslsd_ctx* ctx, const int64_t* m_lo, const int64_t* m_hi, 
     // (marked models: also by the pair of weight vectors - weighted moments)
     std::map<std::array<int64_t, 6>, std::vector<int64_t>> groups;
     std::vector<std::array<int64_t, 6>> order;
+    std::vector<int64_t>* last = nullptr;
+    std::array<int64_t, 6> last_key = {0, 0, 0, 0, 0, 0};
     for (size_t r = 0; r < n_rows; ++r) {
       const ItemDev& it = B.rows[r];
       if (!is_pair_family(it.family) || it.m_hi <= it.m_lo) continue;
       std::array<int64_t, 6> key = {it.tgt_dim, it.src_dim, it.m_lo, it.m_hi, it.wa_off, it.wb_off};
-      auto f = groups.find(key);
-      if (f == groups.end()) {
-        order.push_back(key);
-        f = groups.emplace(key, std::vector<int64_t>()).first;
+      // consecutive rows mostly share their streams: one map lookup per run of equal keys
+      if (last == nullptr || key != last_key) {
+        auto f = groups.find(key);
+        if (f == groups.end()) {
+          order.push_back(key);
+          f = groups.emplace(key, std::vector<int64_t>()).first;
+        }
+        last = &f->second;
+        last_key = key;
       }
-      f->second.push_back((int64_t)r);
+      last->push_back((int64_t)r);
     }
     // unweighted streams first: the two kinds are launched separately
     for (int pass = 0; pass < 2; ++pass)

@@ -69,7 +69,7 @@ struct LqShape {
   // lanes per bin in the moment pass (one round of the CTA covers 64 bins)
   static constexpr int GS = NT >= 1024 ? 16 : (NT >= 512 ? 8 : (NT >= 256 ? 4 : 2));
   static constexpr int TM = NT;     // targets per tile: one per thread
-  static constexpr int SMAX = NT >= 512 ? 2048 : (NT >= 256 ? 1024 : 512);   // staged source events per tile (two buffers)
+  static constexpr int SMAX = NT >= 512 ? 2048 : ((NT >= 256 && CTAS < 3) ? 1024 : 512);   // staged source events per tile (two buffers)
   static constexpr int SMEM_BUDGET = CTAS == 1 ? 220 * 1024 : (CTAS == 2 ? 110 * 1024 : (CTAS == 3 ? 73 * 1024 : (224 * 1024) / CTAS - 2048));
   static constexpr int ONE_BIN_J = NW * (32 / GS);   // bins the groups of lanes can own for a whole work unit
 };
@@ -77,7 +77,10 @@ typedef LqShape<512, 1> LqBig;
 #ifndef LQ_SMALL_CTAS
 #define LQ_SMALL_CTAS 4
 #endif
-typedef LqShape<128, LQ_SMALL_CTAS> LqSmall;
+#ifndef LQ_SMALL_NT
+#define LQ_SMALL_NT 128
+#endif
+typedef LqShape<LQ_SMALL_NT, LQ_SMALL_CTAS> LqSmall;
 enum { LQ_SHAPE_BIG = 0, LQ_SHAPE_SMALL = 1 };
 
 struct QStreamDev {
@@ -127,7 +130,7 @@ __host__ __device__ inline size_t lq_smem_bytes(int J, int ucap, bool weighted) 
 // largest chunk (multiple of C::NT) that fits the budget; 0 if none does
 template <class C>
 inline int lq_pick_ucap(int J, bool weighted) {
-  for (int u = (LQ_UCAP_MAX / C::NT) * C::NT; u >= C::NT; u -= C::NT)
+  for (int u = LQ_UCAP_MAX; u >= C::NT; u -= 32)
     if (lq_smem_bytes<C>(J, u, weighted) <= (size_t)C::SMEM_BUDGET) return u;
   return 0;
 }

@@ -101,7 +101,9 @@ class ShardedExactSums:
         the reach of its parameters still fits the halo and uploads a wider slice if it does
         not (``_check_reach``)."""
         block = self._blocks(list_times)[self.rank]
-        self.max_lag = slack * self.engine.exact_max_lag(ks, xs)
+        reach = self.engine.exact_max_lag(ks, xs)
+        self.max_lag = slack * reach
+        self._reach_checked = self._reach_key(ks, xs)      # these parameters fit: no second look at launch
         local, ranges = block_slices(list_times, block, self.max_lag)
         self.engine.set_events(local, T_f)
         self.ranges = ranges
@@ -123,10 +125,19 @@ class ShardedExactSums:
         block but the first would then silently lose sources.  Re-slice and re-upload."""
         if self.max_lag is None:
             return
+        key = self._reach_key(ks, xs)
+        if key == getattr(self, '_reach_checked', None):
+            return
         reach = self.engine.exact_max_lag(ks, xs)
+        if reach <= self.max_lag:
+            self._reach_checked = key
         if reach > self.max_lag:
             list_times, T_f, slack = self._sliced
             self.set_events(list_times, T_f, ks, xs, slack=max(slack, 1.25))
+
+    @staticmethod
+    def _reach_key(ks, xs):
+        return (tuple(int(k) for k in ks), tuple(np.asarray(x, dtype=np.float64).tobytes() for x in xs))
 
     def raw_buffer(self, k):
         if k not in self._raw:

@@ -170,6 +170,12 @@ class Engine:
         # page-locked arrays are read in place by the library (no staging copy): keep them alive
         self._events_arrays = times
 
+    def set_horizon(self, T_f):
+        """Move T_f of the events on the device (aslsd_set_horizon): later sums see T_f - t_m at the
+        new horizon; the caller restricts the targets to the events before it (``ranges``)."""
+        self._check(self._lib.aslsd_set_horizon(self._ctx, float(T_f)))
+        self.T_f = float(T_f)
+
     def index_maps(self, want_kappa=True, want_varpi=True, want_lag_sizes=True):
         """kappa, varpi, lag_sizes as d x d lists of int64 arrays
         (time_ordering.py:9-119)."""
@@ -530,12 +536,23 @@ class Engine:
 
     def split_packed(self, ks, packed):
         """Concatenated packed sums -> one array per sub-problem."""
+        lens = self._packed_lens(ks)
         out, pos = [], 0
-        for k in ks:
-            n = term_layout(self.desc, k)[1]
+        for n in lens:
             out.append(np.array(packed[pos:pos + n], dtype=np.float64))
             pos += n
         return out
+
+    def _packed_lens(self, ks):
+        """Lengths of the packed sums of the sub-problems ``ks`` (kept per model description)."""
+        cache = getattr(self, '_packed_len_cache', None)
+        if cache is None or cache[0] is not self.desc:
+            cache = (self.desc, {})
+            self._packed_len_cache = cache
+        for k in ks:
+            if k not in cache[1]:
+                cache[1][k] = term_layout(self.desc, k)[1]
+        return [cache[1][k] for k in ks]
 
     def use_device_assembly(self, enabled=True):
         self.set_option(capi.OPT_DEVICE_ASSEMBLY, 1 if enabled else 0)

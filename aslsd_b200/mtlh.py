@@ -18,8 +18,13 @@ Division of labour (BASELINE.json north_star: the functionals stay the reference
     upsilonzero_i x I_ki(xi^i_m)^2 (:755-805).  The derivative blocks with respect to the
     impact parameters (:847-853, :907-918, :963-971) are the same value sums with one weight
     vector replaced by the derivative of the impact;
-  * baselines: constant only (K = mu psi, M = mu^2: basis_baseline_constant.py:30-65); other
-    baselines raise NotImplementedError.
+  * baselines: ``ConstantBaseline`` (K = mu psi, M = mu^2: basis_baseline_constant.py:30-65) and, in
+    the exact estimator, ``PieceConstBaseline`` (constant on time intervals,
+    basis_baseline_piececonst.py): its K term is a combination of weighted psi sums up to the
+    interval ends, evaluated on the device with the horizon moved there (``aslsd_set_horizon``);
+    M, mu and their derivatives are the model's own closures (O(1) / O(N) numpy).  These two are
+    the baselines the reference's own MTLHExactEstim can evaluate (LinearBaseline is abstract,
+    CosineBaseline.make_K is empty: scripts/probe_reference_scope.py).
 ``MTLHStratEstimB200`` (below) is the stratified counterpart (MTLHStratEstim).
 
 ``MTLH`` below is the plain-data mirror of the reference model's parameter book-keeping
@@ -49,7 +54,9 @@ class MTLH:
                                for row in model['kernels']]
         self.impacts = [[dict(spec) for spec in row] for row in model['impacts']]
         self.desc = describe_model(self)
-        self.vector_n_param_mu = [1] * d
+        # baselines: {'type': 'constant'} (default) or {'type': 'piececonst', 'beta': breakpoints}
+        self.baselines = [_normalise_baseline(b) for b in model.get('baselines', [{'type': 'constant'}] * d)]
+        self.vector_n_param_mu = [1 if b['type'] == 'constant' else len(b['beta']) - 1 for b in self.baselines]
         self.matrix_n_param_ker = self.desc.matrix_n_param
         self.matrix_n_param_imp = [[_impact_n_param(self.impacts[k][i]) for i in range(d)]
                                    for k in range(d)]
@@ -59,7 +66,7 @@ class MTLH:
         self.ix_map_imp = [dict() for _ in range(d)]
         self.n_param_k = [0] * d
         for k in range(d):
-            pos = 1
+            pos = self.vector_n_param_mu[k]
             for i in range(d):
                 n = self.matrix_n_param_ker[k][i]
                 self.interval_map_ker[k][i] = [pos, pos + n]
@@ -73,11 +80,11 @@ class MTLH:
                     self.ix_map_imp[k][pos + r] = {'imp': i, 'par': r}
                 pos += n
             self.n_param_k[k] = pos
-        # constant baseline (basis_baseline_constant.py:30-49)
-        self.mu = [lambda t, x_mu: x_mu[0] * np.ones(len(t)) for _ in range(d)]
-        self.diff_mu = [lambda t, ix, x_mu: np.ones(len(t)) for _ in range(d)]
-        self.M = [lambda t, x_mu: x_mu[0] ** 2 for _ in range(d)]
-        self.diff_M = [lambda t, ix, x_mu: 2. * x_mu[0] for _ in range(d)]
+        closures = [_baseline_closures(b) for b in self.baselines]
+        self.mu = [c[0] for c in closures]
+        self.diff_mu = [c[1] for c in closures]
+        self.M = [c[2] for c in closures]
+        self.diff_M = [c[3] for c in closures]
         self.impact = [[self._make_impact(self.impacts[k][i]) for i in range(d)] for k in range(d)]
         self.diff_impact = [[self._make_diff_impact(self.impacts[k][i]) for i in range(d)]
                             for k in range(d)]
@@ -111,17 +118,87 @@ class MTLH:
             setattr(estimator, name, getattr(self, name))
 
 
-def _check_constant_baselines(model):
-    """Only ``ConstantBaseline`` is served by the device (K = mu psi)."""
+def _normalise_baseline(spec):
+    """Plain description of a baseline; the breakpoints as PieceConstBaseline.process_beta keeps them
+    (basis_baseline_piececonst.py:59-67: sorted, unique, non-negative, 0 first, +inf last)."""
+    if spec['type'] == 'constant':
+        return {'type': 'constant'}
+    if spec['type'] != 'piececonst':
+        raise NotImplementedError('baseline %r is outside the engine scope' % (spec['type'],))
+    q = np.array(sorted(set(float(v) for v in spec['beta'])))
+    q = q[q >= 0.]
+    if len(q) == 0 or q[0] != 0.:
+        q = np.insert(q, 0, 0.)
+    if q[-1] != np.inf:
+        q = np.append(q, np.inf)
+    return {'type': 'piececonst', 'beta': q}
+
+
+def _baseline_closures(spec):
+    """(mu, diff_mu, M, diff_M) of the mirror model: ConstantBaseline (basis_baseline_constant.py:30-49)
+    or PieceConstBaseline (basis_baseline_piececonst.py:108-170; M is the time average of mu^2)."""
+    if spec['type'] == 'constant':
+        return (lambda t, x_mu: x_mu[0] * np.ones(len(t)), lambda t, ix, x_mu: np.ones(len(t)),
+                lambda t, x_mu: x_mu[0] ** 2, lambda t, ix, x_mu: 2. * x_mu[0])
+    beta = spec['beta']
+    sizes = beta[1:] - beta[:-1]
+
+    def g(t):
+        return np.digitize(t, beta) - 1
+
+    def mu(t, x_mu):
+        return np.asarray(x_mu, dtype=float)[g(t)]
+
+    def diff_mu(t, ix, x_mu):
+        t = np.asarray(t, dtype=float)
+        return ((t >= beta[ix]) & (t <= beta[ix + 1])).astype(float)
+
+    def big_m(t, x_mu):
+        x_mu = np.asarray(x_mu, dtype=float)
+        if t == 0.:
+            return 0.
+        g_t = int(g(t))
+        res = x_mu[g_t] ** 2 * (t - beta[g_t])
+        if g_t > 0:
+            res += np.cumsum(x_mu ** 2 * sizes)[g_t - 1]
+        return res / t
+
+    def diff_m(t, ix, x_mu):
+        if t == 0.:
+            return 0.
+        g_t = int(g(t))
+        if g_t > ix:
+            return 2. * x_mu[ix] * (beta[ix + 1] - beta[ix]) / t
+        if g_t == ix:
+            return 2. * x_mu[ix] * (t - beta[ix]) / t
+        return 0.
+    return mu, diff_mu, big_m, diff_m
+
+
+def _baseline_spec(model, k, allow_piececonst):
+    """The baseline of sub-problem k as plain data: {'type': 'constant'} or {'type': 'piececonst',
+    'beta': breakpoints}.  Anything else - several basis baselines, fixed variables, baselines the
+    reference cannot evaluate either - is refused."""
     vec = getattr(model, '_baselines_vec', None)
     if vec is None:
-        return     # the mirror: constant by construction
-    for baseline in vec:
+        spec = getattr(model, 'baselines', None)
+        spec = spec[k] if spec is not None else {'type': 'constant'}     # the mirror
+    else:
+        baseline = vec[k]
         basis = getattr(baseline, '_basis_mus', None)
-        names = [type(b).__name__ for b in basis] if basis is not None else [type(baseline).__name__]
-        if names != ['ConstantBaseline']:
-            raise NotImplementedError('aslsd_b200 serves marked models with ConstantBaseline only '
-                                      '(got %s)' % names)
+        basis = list(basis) if basis is not None else [baseline]
+        names = [type(b).__name__ for b in basis]
+        if names == ['ConstantBaseline']:
+            spec = {'type': 'constant'}
+        elif names == ['PieceConstBaseline'] and not getattr(basis[0], 'n_fixed_vars', 0):
+            spec = {'type': 'piececonst', 'beta': np.asarray(basis[0].beta, dtype=float)}
+        else:
+            raise NotImplementedError('aslsd_b200 serves marked models with one ConstantBaseline or one '
+                                      'PieceConstBaseline without fixed variables (got %s)' % names)
+    if spec['type'] != 'constant' and not allow_piececonst:
+        raise NotImplementedError('the stratified marked estimator serves ConstantBaseline only '
+                                  '(use MTLHExactEstimB200 for %s)' % spec['type'])
+    return spec
 
 
 class MTLHExactEstimB200(_B200Estimator):
@@ -133,6 +210,12 @@ class MTLHExactEstimB200(_B200Estimator):
     _STATE_ATTRS = ('t', 'M_term', 'diff_M_term', 'sum_f', 'sum_diff_f')
     _TOTAL_LOG_ATTRS = ('M_term_log', 'sum_f_log')
     _STRATIFICATIONS_OPTIONAL = True
+    _ALLOW_PIECECONST = True
+
+    def initialize_model_data(self, model, data):
+        # (initialize and load both come through here)
+        self.baseline_spec = _baseline_spec(model, self.k, allow_piececonst=self._ALLOW_PIECECONST)
+        super().initialize_model_data(model, data)
 
     def _compute_terms(self, *args, **kwargs):
         raise NotImplementedError('marked models: the terms are evaluated together by compute_objective '
@@ -144,7 +227,6 @@ class MTLHExactEstimB200(_B200Estimator):
                    nonadaptive_sample_size_double=None, double_strfs=None):
         self.k = k
         self.n_iter = n_iter
-        _check_constant_baselines(model)
         self.initialize_model_data(model, data)
         if self.list_marks is None:
             raise ValueError('a marked model needs ProcessPath.list_marks')
@@ -264,8 +346,11 @@ class MTLHExactEstimB200(_B200Estimator):
                     ix_2wdw[i].append(len(vectors)); vectors.append((i, 2. * w[i] * dw[i][r]))
         engine = self._bound_engine()
         engine.set_weights(vectors)
-        n_dev = 1 + sum(self.matrix_n_param_ker[k])
-        x_dev = x[:n_dev]
+        # the device's parameter vector: [mu, kernel parameters]; a piecewise-constant baseline has
+        # several mu's - its K term is assembled below from sums taken with mu = 1
+        n_mu = self.vector_n_param_mu[k]
+        piececonst = self.baseline_spec['type'] == 'piececonst'
+        x_dev = np.concatenate([[1. if piececonst else x[0]], x[n_mu:n_mu + sum(self.matrix_n_param_ker[k])]])
         layout, _ = term_layout(engine.desc, k)
         term_ix = {entry[0]: t for t, entry in enumerate(layout)}
         # role rows: phi sources, upsilon targets, upsilon sources, psi (K) targets, upsilonzero targets
@@ -327,9 +412,99 @@ class MTLHExactEstimB200(_B200Estimator):
                     # same type in both slots: product rule (:963-971)
                     self.sum_diff_f['upsilon_%d_%d' % (p, p)][1][r] = \
                         va['upsilon_%d_%d' % (p, p)] + vb['upsilon_%d_%d' % (p, p)]
+        if piececonst:
+            self._piececonst_K(engine, x_dev, x_mu, w, dw, compute_diff_f_sum)
         self.log_estimates()
         if count_iter:
             self.t += 1
+
+    def _piececonst_K(self, engine, x_dev, x_mu, w, dw, compute_diff_f_sum):
+        """K_i sums of a baseline that is constant on the intervals [beta_j, beta_j+1)
+        (PieceConstBaseline.make_K / make_diff_K, basis_baseline_piececonst.py:172-300, evaluated at
+        t = T_f - t_n, s = t_n as compute_K_sum does, mtlh_exact_estimator.py:707-753).
+
+        With g_s the interval of the event, g_ts that of t + s (the last one, G) and psi the integrated
+        kernel, the reference's per-event value is
+            g_s = G:  mu_G psi(t)
+            g_s < G:  mu_gs psi(beta_gs+1 - s) + mu_G (psi(t) - psi(beta_G))            [sic: no - s]
+                      + sum_{g_s < j < G} mu_j (psi(beta_j+1 - s) - psi(beta_j - s))
+        so that, with Q_j = sum over the events before beta_j+1 of weight x psi(beta_j+1 - t_n) (j < G)
+        and Q_G the same over all events up to T_f,
+            K = sum_{j < G} mu_j (Q_j - Q_j-1) + mu_G (Q_G - psi(beta_G) x weight of the events before beta_G).
+        Every Q_j is the device's weighted psi sum with the horizon moved to beta_j+1 and the targets
+        restricted to the events before it; psi(beta_G) and its derivatives are the same sum over one
+        unweighted event.  Derivatives: kernel parameters through d psi, mu_j through the coefficients,
+        impact parameters through the weights."""
+        d, k, T_f = self.d, self.k, self.T_f
+        beta = np.asarray(self.baseline_spec['beta'], dtype=float)
+        layout, _ = term_layout(engine.desc, k)
+        term_ix = {entry[0]: t for t, entry in enumerate(layout)}
+        for i in range(d):
+            name = 'K_%d' % i
+            times = np.asarray(self.list_times[i], dtype=float)
+            n = len(times)
+            nk, ni = self.matrix_n_param_ker[k][i], len(dw[i])
+            val = 0.
+            d_ker, d_mu, d_imp = np.zeros(nk), np.zeros(len(x_mu)), np.zeros(ni)
+            if n == 0:
+                continue
+            mask = np.zeros(len(layout), dtype=np.uint8)
+            mask[term_ix['psi_%d' % i]] = 1
+            g_s = np.digitize(times, beta) - 1
+            g_ts = np.digitize((T_f - times) + times, beta) - 1      # as the reference forms t + s
+
+            def psi_sum(horizon, hi, vec, diff):
+                """(sum, kernel derivatives) of weight x psi(horizon - t_n) over the first hi events."""
+                if hi <= 0:
+                    return 0., np.zeros(nk)
+                engine.set_horizon(horizon)
+                roles = -np.ones((5, d), dtype=np.int32)
+                roles[3][i] = vec
+                ranges = [(0, 0)] * d
+                ranges[i] = (0, int(hi))
+                sf, sdf = unpack_terms(engine.desc, k, engine.exact_sums_weighted(
+                    k, x_dev, roles, term_mask=mask, compute_f_sum=True, compute_diff_f_sum=diff,
+                    ranges=ranges))
+                return sf['psi_%d' % i], (np.asarray(sdf['psi_%d' % i][1], dtype=float) if diff else np.zeros(nk))
+
+            try:
+                for G in np.unique(g_ts):
+                    G = int(G)
+                    ind = (g_ts == G).astype(float)
+                    vectors = [(i, w[i] * ind)] + [(i, dw[i][r] * ind) for r in range(ni)]
+                    engine.set_weights(vectors)
+                    before_G = g_s < G
+                    # psi(beta_G) and its derivatives: one unweighted event at distance beta_G of the horizon
+                    psi_G, dpsi_G = (0., np.zeros(nk))
+                    if G > 0 and np.any(before_G):
+                        psi_G, dpsi_G = psi_sum(times[0] + beta[G], 1, -1, compute_diff_f_sum)
+                    for v in range(1 + (ni if compute_diff_f_sum else 0)):
+                        diff = compute_diff_f_sum and v == 0
+                        weight = vectors[v][1]
+                        prev, dprev = 0., np.zeros(nk)
+                        for j in range(G + 1):
+                            if j < G:
+                                hi = int(np.searchsorted(times, beta[j + 1], side='left'))
+                                q, dq = psi_sum(beta[j + 1], hi, v, diff)
+                                c, dc = q - prev, dq - dprev
+                                prev, dprev = q, dq
+                            else:
+                                q, dq = psi_sum(T_f, n, v, diff)
+                                w_before = float(np.sum(weight[before_G]))
+                                c, dc = q - psi_G * w_before, dq - dpsi_G * w_before
+                            if v == 0:
+                                val += x_mu[j] * c
+                                d_ker += x_mu[j] * dc
+                                d_mu[j] += c
+                            else:
+                                d_imp[v - 1] += x_mu[j] * c
+            finally:
+                engine.set_horizon(T_f)
+            self.sum_f[name] = val
+            if compute_diff_f_sum:
+                self.sum_diff_f[name][0][1] = d_ker
+                self.sum_diff_f[name][0][2] = d_mu
+                self.sum_diff_f[name][1] = d_imp
 
     # ---- recombination (mtlh_exact_estimator.py:509-670) --------------------------------------
     def recombine_lse_k(self):
@@ -432,6 +607,7 @@ class MTLHStratEstimB200(MTLHExactEstimB200):
         'vecsum_diff_f_adaptive', 'sum_diff_f_adaptive', 'vecsum_diff_f_nonadaptive',
         'sum_diff_f_nonadaptive', 'sum_diff_f_exact')
     _STRATIFICATIONS_OPTIONAL = False
+    _ALLOW_PIECECONST = False
 
     # ---- stratifications (:76-169) -----------------------------------------------------------
     def initialize(self, k, n_iter, model, data, n_exact_single=None,
@@ -441,7 +617,6 @@ class MTLHStratEstimB200(MTLHExactEstimB200):
         from aslsd_b200.stratifications import DoubleIxStratification, GeneralStratification
         self.k = k
         self.n_iter = n_iter
-        _check_constant_baselines(model)
         self.initialize_model_data(model, data)
         if self.list_marks is None:
             raise ValueError('a marked model needs ProcessPath.list_marks')

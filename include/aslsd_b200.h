@@ -103,6 +103,13 @@ int aslsd_measure_fp64_peak(aslsd_ctx* ctx, double* tflops);
  * aslsd_set_events or aslsd_destroy. */
 int aslsd_set_events(aslsd_ctx* ctx, int d, const int64_t* n_events,
                      const double* const* times, double T_f);
+/* Move the end of the observation window of the events already on the device (ProcessPath.T_f,
+ * list_times2end = T_f - t: process_path.py:70-76) without a new upload.  Sums evaluated afterwards see
+ * psi(T_f - t_m), upsilon(T_f - t_m, .) at the new horizon; the caller restricts the targets to the
+ * events before it (m_lo / m_hi).  Used for baselines that are constant on time intervals
+ * (PieceConstBaseline.make_K, functionals/baselines/basis_baselines/basis_baseline_piececonst.py:172-254:
+ * the K term is a combination of psi sums up to the interval ends). */
+int aslsd_set_horizon(aslsd_ctx* ctx, double T_f);
 
 /* ---- index maps: replaces time_ordering.get_kappa_varpi / get_lag_sizes ----------
  * stats/events/time_ordering.py:9-84 and :87-119.  Two-pass: query lengths,

@@ -111,6 +111,32 @@ MTLH_CASES = {
 }
 
 
+# Baselines constant on time intervals (PieceConstBaseline, basis_baseline_piececonst.py): the one
+# non-constant baseline the reference's exact estimator can evaluate.  x_k = [one value per interval,
+# kernels, impacts].  Every sub-problem has the same breakpoints: the reference's K closures are all
+# bound to the baseline of the last one (late binding, mtlh.py:1028-1077) and index its intervals
+# with the caller's values.  In the two-type case the last breakpoint IS T_f, so that the interval of
+# t + s = (T_f - s) + s depends on the rounding of that sum, event by event (2 of 60 and 1 of 45 events
+# of this sample fall below T_f); in the one-type case the breakpoints lie inside the window and beyond it.
+def _with_baselines(model, baselines):
+    out = dict(model)
+    out['baselines'] = baselines
+    return out
+
+
+MTLH_CASES_PC = {
+    'mtlh_exp2d_pc': (_with_baselines(mtlh_model(2, exp_kernel, _linear),
+                                      [{'type': 'piececonst', 'beta': [0., 20., 35., 50.1]},
+                                       {'type': 'piececonst', 'beta': [0., 20., 35., 50.1]}]),
+                      [[.9, .6, .75, .8, .3, 1., .2, 1.5, .5, .7],
+                       [.5, .7, .6, .65, .25, 2., .1, 1.3, .4, .9]], [60, 45], 50.1),
+    'mtlh_gauss1d_pc': (_with_baselines(mtlh_model(1, gauss_kernel, _linear),
+                                        [{'type': 'piececonst', 'beta': [0., 10., 25., 40., 70.]}]),
+                        [[.9, .7, 1.1, .8, .6, .4, .5, 2., .8]], [70], 60.),
+}
+MTLH_CASES.update(MTLH_CASES_PC)
+
+
 # three event types, distinct parameters in every cell (see CASES_3D)
 MTLH_CASES_3D = {
     'mtlh_exp3d': (mtlh_model(3, exp_kernel, _linear),

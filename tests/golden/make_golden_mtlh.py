@@ -36,6 +36,7 @@ def build_reference_mtlh(model):
         from aslsd.functionals.kernels.basis_kernels.basis_kernel_gaussian import GaussianKernel
         from aslsd.functionals.baselines.baseline import BaselineModel
         from aslsd.functionals.baselines.basis_baselines.basis_baseline_constant import ConstantBaseline
+        from aslsd.functionals.baselines.basis_baselines.basis_baseline_piececonst import PieceConstBaseline
         from aslsd.functionals.impact_functions.impact_function import ImpactFunction
         from aslsd.functionals.impact_functions.basis_impacts.basis_impact_linear import LinearImpact
         from aslsd.functionals.impact_functions.basis_impacts.basis_impact_constant import ConstantImpact
@@ -54,12 +55,16 @@ def build_reference_mtlh(model):
             return ImpactFunction([LinearImpact(mark_dim=spec.get('mark_dim', 1))])
         return ImpactFunction([ConstantImpact()])
     km = [[KernelModel([basis(b) for b in model['kernels'][k][i]]) for i in range(d)] for k in range(d)]
-    bl = [BaselineModel([ConstantBaseline()]) for _ in range(d)]
+    specs = model.get('baselines', [{'type': 'constant'}] * d)
+    bl = [BaselineModel([ConstantBaseline() if b['type'] == 'constant'
+                         else PieceConstBaseline(beta=np.asarray(b['beta'], dtype=float))]) for b in specs]
     im = [[imp(model['impacts'][k][i]) for i in range(d)] for k in range(d)]
     gauss = any(b['type'] == 'gauss' for row in model['kernels'] for ker in row for b in ker)
-    # GaussianKernel.make_K is not implemented upstream (basis_kernel_gaussian.py:542-546):
-    # the baseline-side K = mu psi is the only route (mtlh.py:1055-1064)
-    return MTLH(km, _baselines_vec=bl, _impact_matrix=im, K_from_baseline=gauss)
+    # GaussianKernel.make_K is not implemented upstream (basis_kernel_gaussian.py:542-546), nor is
+    # any kernel-side K for a PieceConstBaseline (KeyError in the kernels' dict_K): the baseline-side
+    # K is the only route then (mtlh.py:1055-1064)
+    return MTLH(km, _baselines_vec=bl, _impact_matrix=im,
+                K_from_baseline=gauss or any(b['type'] != 'constant' for b in specs))
 
 
 def main():

@@ -147,7 +147,7 @@ def exercise_marked(name, engine):
         est = aslsd_b200.MTLHExactEstimB200(engine=engine)
         est.initialize(k, 2, mirror, path)
         est.compute_objective(x, compute_f_sum=True, compute_diff_f_sum=True)
-        if model['impacts'][0][0]['type'] == 'linear':
+        if model['impacts'][0][0]['type'] == 'linear' and 'baselines' not in model:
             strat = aslsd_b200.MTLHStratEstimB200(engine=engine)
             strat.initialize(k, 2, mirror, path, n_exact_single=10, n_samples_adaptive_single=20,
                              nonadaptive_sample_size_single=20, n_samples_adaptive_double=40,
@@ -164,7 +164,8 @@ def main():
         exercise_estimators(name, engine)
     engine.close()
     engine = aslsd_b200.Engine(0)
-    for name in ('mtlh_exp2d', 'mtlh_gauss1d', 'mtlh_exp1d_m2', 'mtlh_exp2d_const', 'mtlh_exp3d'):
+    for name in ('mtlh_exp2d', 'mtlh_gauss1d', 'mtlh_exp1d_m2', 'mtlh_exp2d_const', 'mtlh_exp3d', 'mtlh_exp2d_pc',
+                 'mtlh_gauss1d_pc'):
         exercise_marked(name, engine)
     # several contexts side by side; unsorted events and NaNs are rejected
     other = aslsd_b200.Engine(0)

@@ -31,6 +31,9 @@ class OracleEngine:
         self.times = [np.asarray(t, dtype=float) for t in list_times]
         self.T_f = float(T_f)
 
+    def set_horizon(self, T_f):
+        self.T_f = float(T_f)
+
     def index_maps(self, want_kappa=True, want_varpi=True, want_lag_sizes=True):
         from oracle import time_ordering as OT
         kappa, varpi = OT.kappa_varpi_closed_form(self.times, self.T_f)
@@ -129,10 +132,11 @@ class OracleEngine:
             t2e = T_f - times[i]
             if kind == 'psi':
                 w = wv(3, i, len(times[i]))
-                s_psi = np.sum(F.psi(K[k][i], t2e, x_ki) * w)
+                lo, hi = (0, len(times[i])) if ranges is None else (int(ranges[i][0]), int(ranges[i][1]))
+                s_psi = np.sum(F.psi(K[k][i], t2e[lo:hi], x_ki) * w[lo:hi])
                 out[off] = x_k[0] * s_psi
                 for p in range(n1):
-                    out[off + 1 + p] = x_k[0] * np.sum(F.diff_psi(K[k][i], t2e, p, x_ki) * w)
+                    out[off + 1 + p] = x_k[0] * np.sum(F.diff_psi(K[k][i], t2e[lo:hi], p, x_ki) * w[lo:hi])
                 out[off + 1 + n1] = s_psi
             elif kind == 'upsilonzero':
                 w = wv(4, i, len(times[i]))

@@ -24,7 +24,8 @@ def _reference_setup(name):
     return model, xs, mtlh, ProcessPath(times, T_f, list_marks=marks)
 
 
-@pytest.mark.parametrize('name', ['mtlh_exp2d', 'mtlh_gauss1d', 'mtlh_exp1d_m2', 'mtlh_exp3d'])
+@pytest.mark.parametrize('name', ['mtlh_exp2d', 'mtlh_gauss1d', 'mtlh_exp1d_m2', 'mtlh_exp3d', 'mtlh_exp2d_pc',
+                                  'mtlh_gauss1d_pc'])
 def test_estimator_state_matches_reference_estimator(name):
     import aslsd_b200
     from aslsd.optimize.estimators.mtlh_exact_estimator import MTLHExactEstim
@@ -90,7 +91,9 @@ def test_stratified_estimator_plugs_into_reference_mtlh_fit():
 
 
 def test_unsupported_baselines_raise():
-    """Baselines other than ConstantBaseline are outside the device's scope: loud refusal."""
+    """Baselines other than ConstantBaseline / PieceConstBaseline are outside the device's scope (the
+    reference's exact estimator cannot evaluate them either): loud refusal; the stratified estimator
+    refuses PieceConstBaseline as well."""
     import types
     import aslsd_b200
     model, xs, mtlh, path = _reference_setup('mtlh_exp1d_m2')
@@ -99,6 +102,9 @@ def test_unsupported_baselines_raise():
     est = aslsd_b200.MTLHExactEstimB200(engine=OracleEngine())
     with pytest.raises(NotImplementedError):
         est.initialize(0, 3, mtlh, path)
+    model, xs, mtlh, path = _reference_setup('mtlh_gauss1d_pc')
+    with pytest.raises(NotImplementedError):
+        aslsd_b200.MTLHStratEstimB200(engine=OracleEngine()).initialize(0, 3, mtlh, path)
 
 
 def test_marked_estimators_save_load(tmp_path):
