@@ -6,6 +6,7 @@ import numpy as np
 import aslsd_b200
 from aslsd_b200 import simulate
 
+DIRECT = os.environ.get('PLUGIN_TRACE_DIRECT', '1') == '1'   # a direct engine call before every estimator call
 model, times, T_f, xs = simulate.config_c5(T_f=float(sys.argv[1]) if len(sys.argv) > 1 else 1.1e6)
 engine = aslsd_b200.Engine(0)
 path = aslsd_b200.ProcessPath(times, T_f, book_keeping=False, engine=engine)
@@ -25,7 +26,8 @@ for cache in (False, True):
         for k in range(d):
             t0 = time.perf_counter()
             x = np.asarray(xs[k], dtype=np.float64)
-            packed = engine.exact_sums_packed(k, x, False, True)
+            if DIRECT:
+                packed = engine.exact_sums_packed(k, x, False, True)
             t1 = time.perf_counter()
             g = ests[k].lse_k_grad_estimate(xs[k])
             t2 = time.perf_counter()
