@@ -134,6 +134,7 @@ struct aslsd_ctx {
   double* d_partials = nullptr; size_t partials_cap = 0;
   double* d_raw = nullptr; size_t raw_cap = 0;
   unsigned long long* d_counts = nullptr; size_t counts_cap = 0;
+  unsigned long long* d_qcounts = nullptr; size_t qcounts_cap = 0;   // pair counts of the moment kernels' work units
   void* h_pinned = nullptr; size_t pinned_cap = 0;
   // page-locked staging of the plan tables (items, streams, rows, boundary groups); ev_tables marks
   // the end of their last transfer, so the block is rewritten only once the device has read it

@@ -78,6 +78,7 @@ extern "C" int aslsd_destroy(aslsd_ctx* ctx) {
   cudaFree(ctx->d_partials);
   cudaFree(ctx->d_raw);
   cudaFree(ctx->d_counts);
+  cudaFree(ctx->d_qcounts);
   if (ctx->plan_cache && ctx->plan_cache_free) ctx->plan_cache_free(ctx->plan_cache);
   if (ctx->sim_state && ctx->sim_state_free) ctx->sim_state_free(ctx->sim_state);
   cudaFree(ctx->d_sample);

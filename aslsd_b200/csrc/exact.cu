@@ -62,6 +62,10 @@ struct BatchPlan {
   // of the big one, weighted streams - and each category is one launch over its work units
   int64_t q_cat_wu[4] = {0, 0, 0, 0};           // first work unit of every category (prefix)
   size_t q_cat_smem[3] = {0, 0, 0};
+  // work part in two phases: the streams first (all the moment kernels need), the rows while those run
+  std::vector<std::vector<int64_t>> q_groups;   // rows of every (streams, target block, weights) group, launch order
+  std::vector<int> q_group_stream;              // its stream (index in qstreams), -1: per-item kernels only
+  bool rows_pending = false;                    // build_work_rows has not run for the current streams
   // scratch of build_work, kept between calls (no reallocation when only the events change)
   std::vector<ItemDev> scratch_q[ITEM_N_FAMILIES], scratch_f[ITEM_N_FAMILIES];
   int q_jmax = 0;
@@ -142,9 +146,8 @@ static double row_scale(const ItemDev& it) {
 
 // Turn the pair rows of one (target stream, source stream, target block) into a
 // quadrature stream, if the geometry allows it.
-static void build_stream(const aslsd_ctx* ctx, BatchPlan& B, const std::vector<int64_t>& group,
-                         std::vector<bool>& fast, std::vector<int64_t>& boundary_from,
-                         std::vector<ItemDev>* qfam) {
+// Returns its index in B.qstreams, or -1.
+static int build_stream(const aslsd_ctx* ctx, BatchPlan& B, const std::vector<int64_t>& group) {
   const ItemDev first = B.rows[group[0]];
   double t_int = 0., s_max = 0., scale = 1e300;
   for (int64_t r : group) {
@@ -154,7 +157,7 @@ static void build_stream(const aslsd_ctx* ctx, BatchPlan& B, const std::vector<i
     s_max = std::max(s_max, it.s_hi);
     scale = std::min(scale, row_scale(it));
   }
-  if (!(scale > 0.) || !(s_max > 0.) || !std::isfinite(s_max) || !std::isfinite(t_int)) return;
+  if (!(scale > 0.) || !(s_max > 0.) || !std::isfinite(s_max) || !std::isfinite(t_int)) return -1;
   // the moment kernel counts the pairs of a tile (at most 512 targets x their windows) in 32 bits: a
   // reach that could hold ~2^31 / 512 sources per target (16 x the mean density as margin for
   // clustering) stays with the per-item kernels, which count in 64 bits
@@ -164,23 +167,23 @@ static void build_stream(const aslsd_ctx* ctx, BatchPlan& B, const std::vector<i
     const double span = n_src > 1 ? ts[n_src - 1] - ts[0] : 0.;
     const double per_target = span > 0. ? std::min<double>((double)n_src, 16. * (double)n_src * s_max / span)
                                         : (double)n_src;
-    if (per_target * (double)LqBig::TM >= 2.0e9) return;
+    if (per_target * (double)LqBig::TM >= 2.0e9) return -1;
   }
   const int64_t m_b = interior_end(ctx, first.tgt_dim, first.m_lo, first.m_hi, t_int);
-  if (m_b - first.m_lo < LqBig::TM / 2) return;   // the per-item kernels take it all
+  if (m_b - first.m_lo < LqBig::TM / 2) return -1;   // the per-item kernels take it all
   // bins [j h, (j + 1) h) up to s_max plus a spare one (a lag can exceed s_max by a rounding
   // error); the count is rounded up to a multiple of 32 - the moment kernel hands bins to
   // groups of lanes in rounds of 64 - and the bins shrink accordingly
   const double h_max = LQ_SCALE_FRACTION * scale;
   double nb = std::floor(s_max / h_max) + 2.;
-  if (!(nb <= (double)LQ_JMAX)) return;
+  if (!(nb <= (double)LQ_JMAX)) return -1;
   nb = std::min<double>(LQ_JMAX, 32. * std::ceil(nb / 32.));
   const double h = s_max / (nb - 1.5);
   const bool weighted = first.wa_off >= 0 || first.wb_off >= 0;
   // CTA shape: the small one where every pair of its lanes can own a bin for a whole work unit
   const bool small = !weighted && nb <= (double)LqSmall::ONE_BIN_J;
   const int ucap = small ? lq_pick_ucap<LqSmall>((int)nb, false) : lq_pick_ucap<LqBig>((int)nb, weighted);
-  if (ucap == 0) return;
+  if (ucap == 0) return -1;
   QStreamDev S;
   std::memset(&S, 0, sizeof(S));
   S.tgt_dim = first.tgt_dim;
@@ -220,18 +223,7 @@ static void build_stream(const aslsd_ctx* ctx, BatchPlan& B, const std::vector<i
     const size_t bytes = small ? lq_smem_bytes<LqSmall>(S.J, S.ucap, false) : lq_smem_bytes<LqBig>(S.J, S.ucap, weighted);
     B.q_cat_smem[cat] = std::max(B.q_cat_smem[cat], bytes);
   }
-  for (int64_t r : group) {
-    ItemDev it = B.rows[r];
-    it.dst_row = r;
-    it.wu_first = sx;
-    it.m_hi = m_b;
-    qfam[it.family].push_back(it);
-    fast[r] = true;
-    boundary_from[r] = m_b;
-    const int64_t j_lo = std::max<int64_t>(0, (int64_t)std::floor(it.s_lo / h) - 1);
-    const int64_t j_hi = std::min<int64_t>(S.J - 1, (int64_t)std::floor(it.s_hi / h) + 1);
-    B.n_q_evals += std::max<int64_t>(0, j_hi - j_lo + 1) * LQ_ND;
-  }
+  return sx;
 }
 
 // Rows: the work items of every sub-problem and their de-duplication.  Pure function of
@@ -264,19 +256,25 @@ static int build_rows(aslsd_ctx* ctx, int n_k, const int* ks, const double* cons
   return ASLSD_OK;
 }
 
-// Work: target ranges, quadrature streams, per-item work units.  Depends on the events.
-static int build_work(aslsd_ctx* ctx, const int64_t* m_lo, const int64_t* m_hi, BatchPlan& B) {
+// Work: target ranges, quadrature streams, per-item work units.  Depends on the events.  Two phases:
+// build_work_streams leaves the stream records complete (all the moment kernels read), build_work_rows
+// the rows, boundary groups and per-item work units - run_batch runs it while the moment kernels are
+// on the device (the 0.5 - 0.8 ms it takes at C5 would otherwise sit between the upload and the first launch).
+static int build_work_streams(aslsd_ctx* ctx, const int64_t* m_lo, const int64_t* m_hi, BatchPlan& B) {
   if (!ctx->d_times || (int)ctx->n_events.size() != ctx->d)
     return aslsd_fail(ctx, ASLSD_ERR_ARG, "exact sums: no events set");
   B.items.clear();
   B.qstreams.clear();
   B.qrows.clear();
   B.bgroups.clear();
+  B.q_groups.clear();
+  B.q_group_stream.clear();
   B.n_wu = B.n_wu_q = B.n_q_partials = B.n_q_weights = B.n_q_evals = 0;
   B.q_jmax = 0;
   for (int c = 0; c < 3; ++c) B.q_cat_smem[c] = 0;
   B.device_resident = false;
   B.weights_valid = false;
+  B.rows_pending = true;
   const int d = ctx->d;
   B.lo.resize(d);
   B.hi.resize(d);
@@ -289,15 +287,12 @@ static int build_work(aslsd_ctx* ctx, const int64_t* m_lo, const int64_t* m_hi, 
     it.m_hi = B.hi[it.tgt_dim];
   }
   const size_t n_rows = B.rows.size();
-  std::vector<bool> fast(n_rows, false);
-  std::vector<int64_t> boundary_from(n_rows, 0);
-  std::vector<ItemDev>* qfam = B.scratch_q;
-  for (int f = 0; f < ITEM_N_FAMILIES; ++f) qfam[f].clear();
   if (ctx->use_quadrature) {
     // group the pair rows by (streams, target block), in row order
     // (marked models: also by the pair of weight vectors - weighted moments)
-    std::map<std::array<int64_t, 6>, std::vector<int64_t>> groups;
-    std::vector<std::array<int64_t, 6>> order;
+    std::map<std::array<int64_t, 6>, size_t> groups;
+    std::vector<std::vector<int64_t>> found;
+    std::vector<bool> weighted;
     std::vector<int64_t>* last = nullptr;
     std::array<int64_t, 6> last_key = {0, 0, 0, 0, 0, 0};
     for (size_t r = 0; r < n_rows; ++r) {
@@ -308,20 +303,23 @@ static int build_work(aslsd_ctx* ctx, const int64_t* m_lo, const int64_t* m_hi, 
       if (last == nullptr || key != last_key) {
         auto f = groups.find(key);
         if (f == groups.end()) {
-          order.push_back(key);
-          f = groups.emplace(key, std::vector<int64_t>()).first;
+          f = groups.emplace(key, found.size()).first;
+          found.emplace_back();
+          weighted.push_back(key[4] >= 0 || key[5] >= 0);
         }
-        last = &f->second;
+        last = &found[f->second];   // (found may have grown: taken after the emplace)
         last_key = key;
       }
       last->push_back((int64_t)r);
     }
     // unweighted streams first: the two kinds are launched separately
     for (int pass = 0; pass < 2; ++pass)
-      for (auto& key : order)
-        if ((key[4] >= 0 || key[5] >= 0) == (pass == 1))
-          build_stream(ctx, B, groups[key], fast, boundary_from, qfam);
-    // order the streams by category (stable) and renumber the rows' stream index
+      for (size_t g = 0; g < found.size(); ++g)
+        if (weighted[g] == (pass == 1)) {
+          B.q_group_stream.push_back(build_stream(ctx, B, found[g]));
+          B.q_groups.emplace_back(std::move(found[g]));
+        }
+    // order the streams by category (stable) and renumber the groups' stream index
     auto category = [](const QStreamDev& S) {
       return (S.wa_off >= 0 || S.wb_off >= 0) ? 2 : (S.shape == LQ_SHAPE_SMALL ? 0 : 1);
     };
@@ -335,8 +333,75 @@ static int build_work(aslsd_ctx* ctx, const int64_t* m_lo, const int64_t* m_hi, 
       new_ix[perm[x]] = (int)x;
     }
     B.qstreams.swap(sorted);
-    for (int f = 0; f < ITEM_N_FAMILIES; ++f)
-      for (auto& it : qfam[f]) it.wu_first = new_ix[(size_t)it.wu_first];
+    for (auto& sx : B.q_group_stream)
+      if (sx >= 0) sx = new_ix[(size_t)sx];
+  }
+  // ---- quadrature streams: work units of whole tiles, a few waves over the 148 SMs ----------
+  // (per category: the streams of one launch share the size of their work units)
+  auto category = [](const QStreamDev& S) {
+    return (S.wa_off >= 0 || S.wb_off >= 0) ? 2 : (S.shape == LQ_SHAPE_SMALL ? 0 : 1);
+  };
+  int64_t tot[3] = {0, 0, 0}, tpw_cat[3];
+  for (auto& S : B.qstreams) tot[category(S)] += S.m_hi - S.m_lo;
+  for (int c = 0; c < 3; ++c) {
+    const int64_t tm = c == 0 ? LqSmall::TM : LqBig::TM;
+    // (small CTAs: ~32 work units per resident CTA measured best on the C5 step, 10.42 ms against
+    // 11.04 ms with 1.5 - 4 per CTA and 10.51 ms with 83: gpurun_out / profiles r2_g_units)
+    int64_t units = c == 0 ? 148 * LqSmall::CTAS * 32 : 148 * 2 * 6;
+    // ... but at least ~12 tiles per work unit: a unit pays for its first window search, the zeroing and
+    // the write-out of its moment table (one eighth of C5, one time-block shard of eight: 1.372 ms with
+    // 9 472 units, 1.422 ms with 18 944, 1.598 ms with 1 184)
+    if (c == 0) units = std::min<int64_t>(units, std::max<int64_t>(148 * LqSmall::CTAS, tot[c] / (12 * tm)));
+    if (const char* e = std::getenv("ASLSD_LQ_UNITS")) units = std::max<int64_t>(1, std::atoll(e));   // tuning
+    int64_t tpw = (tot[c] + units - 1) / units;
+    tpw = std::max<int64_t>(tm, std::min<int64_t>(tpw, 64 * LqBig::TM));
+    tpw_cat[c] = ((tpw + tm - 1) / tm) * tm;
+  }
+  int64_t qwu = 0, part = 0, wts = 0;
+  int cat_seen = 0;
+  B.q_cat_wu[0] = 0;
+  for (auto& S : B.qstreams) {
+    const int c = category(S);
+    while (cat_seen < c) B.q_cat_wu[++cat_seen] = qwu;
+    S.tpw = tpw_cat[c];
+    S.n_chunks = (int32_t)((S.m_hi - S.m_lo + S.tpw - 1) / S.tpw);
+    S.wu_first = qwu;
+    S.part_first = part;
+    S.w_first = wts;
+    qwu += S.n_chunks;
+    part += (int64_t)S.n_chunks * S.J * LQ_ND;
+    wts += (int64_t)S.J * LQ_ND;
+  }
+  while (cat_seen < 3) B.q_cat_wu[++cat_seen] = qwu;
+  B.n_wu_q = qwu;
+  B.n_q_partials = part;
+  B.n_q_weights = wts;
+  if (qwu >= (int64_t)2147483647) return aslsd_fail(ctx, ASLSD_ERR_ARG, "exact sums: too many work units");
+  return ASLSD_OK;
+}
+
+static int build_work_rows(aslsd_ctx* ctx, BatchPlan& B) {
+  if (!B.rows_pending) return ASLSD_OK;
+  const size_t n_rows = B.rows.size();
+  std::vector<bool> fast(n_rows, false);
+  std::vector<ItemDev>* qfam = B.scratch_q;
+  for (int f = 0; f < ITEM_N_FAMILIES; ++f) qfam[f].clear();
+  // rows of the streams: interior through the quadrature, targets near T_f through lag_boundary_kernel
+  for (size_t g = 0; g < B.q_groups.size(); ++g) {
+    const int sx = B.q_group_stream[g];
+    if (sx < 0) continue;
+    const QStreamDev& S = B.qstreams[(size_t)sx];
+    for (int64_t r : B.q_groups[g]) {
+      ItemDev it = B.rows[(size_t)r];
+      it.dst_row = r;
+      it.wu_first = sx;
+      it.m_hi = S.m_hi;
+      qfam[it.family].push_back(it);
+      fast[(size_t)r] = true;
+      const int64_t j_lo = std::max<int64_t>(0, (int64_t)std::floor(it.s_lo / S.h) - 1);
+      const int64_t j_hi = std::min<int64_t>(S.J - 1, (int64_t)std::floor(it.s_hi / S.h) + 1);
+      B.n_q_evals += std::max<int64_t>(0, j_hi - j_lo + 1) * LQ_ND;
+    }
   }
   for (int f = 0; f < ITEM_N_FAMILIES; ++f) {
     B.qfam_first[f] = (int)B.qrows.size();
@@ -410,45 +475,15 @@ static int build_work(aslsd_ctx* ctx, const int64_t* m_lo, const int64_t* m_hi, 
     base += B.fam_count[f];
   }
   B.n_wu = wu;
-  // ---- quadrature streams: work units of whole tiles, a few waves over the 148 SMs ----------
-  // (per category: the streams of one launch share the size of their work units)
-  auto category = [](const QStreamDev& S) {
-    return (S.wa_off >= 0 || S.wb_off >= 0) ? 2 : (S.shape == LQ_SHAPE_SMALL ? 0 : 1);
-  };
-  int64_t tot[3] = {0, 0, 0}, tpw_cat[3];
-  for (auto& S : B.qstreams) tot[category(S)] += S.m_hi - S.m_lo;
-  for (int c = 0; c < 3; ++c) {
-    const int64_t tm = c == 0 ? LqSmall::TM : LqBig::TM;
-    // (small CTAs: ~32 work units per resident CTA measured best on the C5 step, 10.42 ms against
-    // 11.04 ms with 1.5 - 4 per CTA and 10.51 ms with 83: gpurun_out / profiles r2_g_units)
-    int64_t units = c == 0 ? 148 * LqSmall::CTAS * 32 : 148 * 2 * 6;
-    if (const char* e = std::getenv("ASLSD_LQ_UNITS")) units = std::max<int64_t>(1, std::atoll(e));   // tuning
-    int64_t tpw = (tot[c] + units - 1) / units;
-    tpw = std::max<int64_t>(tm, std::min<int64_t>(tpw, 64 * LqBig::TM));
-    tpw_cat[c] = ((tpw + tm - 1) / tm) * tm;
-  }
-  int64_t qwu = 0, part = 0, wts = 0;
-  int cat_seen = 0;
-  B.q_cat_wu[0] = 0;
-  for (auto& S : B.qstreams) {
-    const int c = category(S);
-    while (cat_seen < c) B.q_cat_wu[++cat_seen] = qwu;
-    S.tpw = tpw_cat[c];
-    S.n_chunks = (int32_t)((S.m_hi - S.m_lo + S.tpw - 1) / S.tpw);
-    S.wu_first = qwu;
-    S.part_first = part;
-    S.w_first = wts;
-    qwu += S.n_chunks;
-    part += (int64_t)S.n_chunks * S.J * LQ_ND;
-    wts += (int64_t)S.J * LQ_ND;
-  }
-  while (cat_seen < 3) B.q_cat_wu[++cat_seen] = qwu;
-  B.n_wu_q = qwu;
-  B.n_q_partials = part;
-  B.n_q_weights = wts;
-  if (B.n_wu >= (int64_t)2147483647 || qwu >= (int64_t)2147483647)
-    return aslsd_fail(ctx, ASLSD_ERR_ARG, "exact sums: too many work units");
+  B.rows_pending = false;
+  if (B.n_wu >= (int64_t)2147483647) return aslsd_fail(ctx, ASLSD_ERR_ARG, "exact sums: too many work units");
   return ASLSD_OK;
+}
+
+static int build_work(aslsd_ctx* ctx, const int64_t* m_lo, const int64_t* m_hi, BatchPlan& B, bool defer_rows) {
+  int rc;
+  if ((rc = build_work_streams(ctx, m_lo, m_hi, B))) return rc;
+  return defer_rows ? ASLSD_OK : build_work_rows(ctx, B);
 }
 
 // The last batch plan is kept.  Its rows are a pure function of (model, flags, sub-problems,
@@ -518,7 +553,7 @@ static int get_batch(aslsd_ctx* ctx, int n_k, const int* ks, const double* const
   if (with_work && !(C->has_work && C->key_work == key_work)) {
     C->has_work = false;
     const auto t0 = std::chrono::steady_clock::now();
-    if ((rc = build_work(ctx, m_lo, m_hi, *C))) return rc;
+    if ((rc = build_work(ctx, m_lo, m_hi, *C, true))) return rc;   // the rows: in run_batch, behind the first launches
     if (std::getenv("ASLSD_TRACE"))
       std::fprintf(stderr, "[aslsd] build_work %.3f ms (%zu rows, %zu streams)\n",
                    1e3 * std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count(),
@@ -610,11 +645,118 @@ static int run_batch(aslsd_ctx* ctx, BatchPlan& B, double* raw_device) {
                  1e3 * std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count());
   return rc;
 }
+// The moment kernels of every category and the weights kernel, on the context's stream.
+static int launch_moments(aslsd_ctx* ctx, BatchPlan& B, const QStreamDev* d_streams) {
+  if (ctx->q_smem_set == 0) {
+    // the attribute belongs to the function, not to this context: every context asks for the
+    // same ceiling, so contexts with different bin counts never lower each other's limit
+    CUDA_TRY(ctx, cudaFuncSetAttribute(lag_moment_kernel<false, LqSmall>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)LqSmall::SMEM_BUDGET));
+    CUDA_TRY(ctx, cudaFuncSetAttribute(lag_moment_kernel<false, LqBig>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)LqBig::SMEM_BUDGET));
+    CUDA_TRY(ctx, cudaFuncSetAttribute(lag_moment_kernel<true, LqBig>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)LqBig::SMEM_BUDGET));
+    ctx->q_smem_set = LqBig::SMEM_BUDGET;
+  }
+  CUDA_TRY(ctx, cudaEventRecord(ctx->ev_q0, ctx->stream));
+  unsigned long long* d_qcnt = ctx->d_qcounts;
+  const int n_streams = (int)B.qstreams.size();
+  if (B.q_cat_wu[1] > B.q_cat_wu[0]) {
+    lag_moment_kernel<false, LqSmall><<<(unsigned)(B.q_cat_wu[1] - B.q_cat_wu[0]), LqSmall::NT, B.q_cat_smem[0],
+                                         ctx->stream>>>((const DimDev*)ctx->d_dims, d_streams, n_streams,
+                                                        ctx->d_q_partials, d_qcnt, ctx->d_weights, B.q_cat_wu[0]);
+    ctx->last_launches++;
+  }
+  if (B.q_cat_wu[2] > B.q_cat_wu[1]) {
+    lag_moment_kernel<false, LqBig><<<(unsigned)(B.q_cat_wu[2] - B.q_cat_wu[1]), LqBig::NT, B.q_cat_smem[1],
+                                       ctx->stream>>>((const DimDev*)ctx->d_dims, d_streams, n_streams,
+                                                      ctx->d_q_partials, d_qcnt, ctx->d_weights, B.q_cat_wu[1]);
+    ctx->last_launches++;
+  }
+  if (B.q_cat_wu[3] > B.q_cat_wu[2]) {
+    lag_moment_kernel<true, LqBig><<<(unsigned)(B.q_cat_wu[3] - B.q_cat_wu[2]), LqBig::NT, B.q_cat_smem[2],
+                                      ctx->stream>>>((const DimDev*)ctx->d_dims, d_streams, n_streams,
+                                                     ctx->d_q_partials, d_qcnt, ctx->d_weights, B.q_cat_wu[2]);
+    ctx->last_launches++;
+  }
+  CUDA_TRY(ctx, cudaEventRecord(ctx->ev_q1, ctx->stream));
+  ctx->moment_timing_pending = true;
+  const dim3 wgrid((unsigned)((B.q_jmax + LQ_WB - 1) / LQ_WB), (unsigned)B.qstreams.size());
+  ctx->w_streams.clear();   // being rewritten
+  lag_weights_kernel<<<wgrid, LQ_WB * LQ_ND, 0, ctx->stream>>>(d_streams, ctx->d_q_partials, ctx->d_q_weights);
+  ctx->last_launches++;
+  if (ctx->cache_weights) {   // record what the buffer holds: later calls (of any plan) may reuse it
+    ctx->w_streams.assign((const unsigned char*)B.qstreams.data(),
+                          (const unsigned char*)(B.qstreams.data() + B.qstreams.size()));
+    ctx->w_events_epoch = ctx->events_epoch;
+  }
+  return ASLSD_OK;
+}
+
 static int run_batch_impl(aslsd_ctx* ctx, BatchPlan& B, double* raw_device) {
   CUDA_TRY(ctx, cudaSetDevice(ctx->device));
-  const size_t n_items = B.items.size(), n_rows = B.rows.size();
+  const size_t n_rows = B.rows.size();
   int rc;
   ctx->last_launches = 0;
+  ctx->moment_timing_pending = false;
+  ctx->last_moment_ms = 0.;
+  const bool quad = !B.qstreams.empty();
+  if (ctx->tables_owner != (const void*)&B || ctx->tables_owner_uid != B.uid) B.device_resident = false;
+  // device table block [streams | rows | boundary groups], page-locked staging block
+  // [streams | rows | boundary groups | items]: the streams come first in both, their size is known
+  // before the rows are planned
+  const size_t o_s = 0;
+  const size_t o_r = o_s + ((B.qstreams.size() * sizeof(QStreamDev) + 15) & ~(size_t)15);
+  bool streams_uploaded = false, moments_done = false;
+  CUDA_TRY(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
+  if (quad) {
+    if ((rc = upload_quadrature_tables(ctx))) return rc;
+    if ((rc = ensure_device_buffer(ctx, (void**)&ctx->d_q_partials, &ctx->q_partials_cap,
+                                   (size_t)B.n_q_partials * sizeof(double)))) return rc;
+    const double* before = ctx->d_q_weights;
+    if ((rc = ensure_device_buffer(ctx, (void**)&ctx->d_q_weights, &ctx->q_weights_cap,
+                                   (size_t)B.n_q_weights * sizeof(double)))) return rc;
+    if (ctx->d_q_weights != before) ctx->w_streams.clear();
+    if ((rc = ensure_device_buffer(ctx, (void**)&ctx->d_qcounts, &ctx->qcounts_cap,
+                                   ((size_t)B.n_wu_q + 1) * sizeof(unsigned long long)))) return rc;
+  }
+  // The node weights depend on the event streams and on the bin grids only (not on omega, not
+  // on the evaluation point as long as the windows stay): with the weight cache on, a repeated
+  // evaluation on the same plan - the iterations of a fit with fixed (beta, delta) - skips the
+  // pass over the event pairs.
+  // (the record of what d_q_weights holds decides: several plans share the buffer)
+  const bool reuse_weights = quad && ctx->cache_weights && weights_match(ctx, B);
+  ctx->last_weights_reused = reuse_weights;
+  if (B.rows_pending && quad && !B.device_resident) {
+    // a fresh work part: streams to the device and the moment kernels on their way, then the rows are
+    // planned while they run.  The blocks are sized for the largest row part this plan can have.
+    const size_t n_groups_max = n_rows + (size_t)ITEM_N_FAMILIES * B.qstreams.size();
+    const size_t q_bytes_max = o_r + ((n_rows * sizeof(ItemDev) + 15) & ~(size_t)15) +
+                               n_groups_max * sizeof(BoundaryGroupDev);
+    const size_t need = q_bytes_max + ((n_rows * sizeof(ItemDev) + 15) & ~(size_t)15);
+    if (ctx->tables_in_flight) {
+      CUDA_TRY(ctx, cudaEventSynchronize(ctx->ev_tables));
+      ctx->tables_in_flight = false;
+    }
+    if (need > ctx->tables_cap) {
+      if (ctx->h_tables) CUDA_TRY(ctx, cudaFreeHost(ctx->h_tables));
+      ctx->h_tables = nullptr;
+      ctx->tables_cap = 0;
+      CUDA_TRY(ctx, cudaMallocHost(&ctx->h_tables, need + need / 4));
+      ctx->tables_cap = need + need / 4;
+    }
+    if ((rc = ensure_device_buffer(ctx, &ctx->d_qtab, &ctx->qtab_cap, q_bytes_max))) return rc;
+    char* hp = (char*)ctx->h_tables;
+    std::memcpy(hp + o_s, B.qstreams.data(), B.qstreams.size() * sizeof(QStreamDev));
+    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_qtab, hp, o_r, cudaMemcpyHostToDevice, ctx->stream));
+    streams_uploaded = true;
+    if (!reuse_weights) {
+      if ((rc = launch_moments(ctx, B, (const QStreamDev*)((const char*)ctx->d_qtab + o_s)))) return rc;
+      moments_done = true;
+    }
+  }
+  if ((rc = build_work_rows(ctx, B))) return rc;
+  const size_t n_items = B.items.size();
   ctx->last_n_wu = B.n_wu;
   ctx->last_n_items = (int)n_items;
   ctx->last_n_wu_q = B.n_wu_q;
@@ -628,54 +770,47 @@ static int run_batch_impl(aslsd_ctx* ctx, BatchPlan& B, double* raw_device) {
     return rc;
   if ((rc = ensure_device_buffer(ctx, (void**)&ctx->d_partials, &ctx->partials_cap,
                                  std::max<size_t>(1, (size_t)B.n_wu) * ASLSD_MAX_COMP * sizeof(double)))) return rc;
+  // counters: [per-item work units | items | boundary groups]; the moment kernels have their own block
   if ((rc = ensure_device_buffer(ctx, (void**)&ctx->d_counts, &ctx->counts_cap,
-                                 ((size_t)B.n_wu + n_items + (size_t)B.n_wu_q + B.bgroups.size() + 1) *
-                                     sizeof(unsigned long long))))
+                                 ((size_t)B.n_wu + n_items + B.bgroups.size() + 1) * sizeof(unsigned long long))))
     return rc;
-  // quadrature tables: one block [streams | rows | boundary groups]
-  const bool quad = !B.qstreams.empty();
-  const size_t o_s = 0;
-  const size_t o_r = o_s + ((B.qstreams.size() * sizeof(QStreamDev) + 15) & ~(size_t)15);
   const size_t o_g = o_r + ((B.qrows.size() * sizeof(ItemDev) + 15) & ~(size_t)15);
   const size_t q_bytes = o_g + B.bgroups.size() * sizeof(BoundaryGroupDev);
-  if (quad) {
-    if ((rc = upload_quadrature_tables(ctx))) return rc;
-    if ((rc = ensure_device_buffer(ctx, (void**)&ctx->d_q_partials, &ctx->q_partials_cap,
-                                   (size_t)B.n_q_partials * sizeof(double)))) return rc;
-    const double* before = ctx->d_q_weights;
-    if ((rc = ensure_device_buffer(ctx, (void**)&ctx->d_q_weights, &ctx->q_weights_cap,
-                                   (size_t)B.n_q_weights * sizeof(double)))) return rc;
-    if (ctx->d_q_weights != before) ctx->w_streams.clear();
-  }
-  if (ctx->tables_owner != (const void*)&B || ctx->tables_owner_uid != B.uid) B.device_resident = false;
   if (!B.device_resident && (n_items || quad)) {
-    // all plan tables go through one page-locked block of their own and two asynchronous
-    // transfers: no wait for the stream here (an event upload may still be in flight on it)
+    // all plan tables go through one page-locked block of their own and asynchronous transfers:
+    // no wait for the stream here (an event upload may still be in flight on it)
     const size_t i_bytes = (n_items * sizeof(ItemDev) + 15) & ~(size_t)15;
     const size_t need = i_bytes + (quad ? q_bytes : 0);
-    if (ctx->tables_in_flight) {
-      CUDA_TRY(ctx, cudaEventSynchronize(ctx->ev_tables));
-      ctx->tables_in_flight = false;
-    }
-    if (need > ctx->tables_cap) {
-      if (ctx->h_tables) CUDA_TRY(ctx, cudaFreeHost(ctx->h_tables));
-      ctx->h_tables = nullptr;
-      ctx->tables_cap = 0;
-      CUDA_TRY(ctx, cudaMallocHost(&ctx->h_tables, need + need / 4));
-      ctx->tables_cap = need + need / 4;
+    if (!streams_uploaded) {
+      if (ctx->tables_in_flight) {
+        CUDA_TRY(ctx, cudaEventSynchronize(ctx->ev_tables));
+        ctx->tables_in_flight = false;
+      }
+      if (need > ctx->tables_cap) {
+        if (ctx->h_tables) CUDA_TRY(ctx, cudaFreeHost(ctx->h_tables));
+        ctx->h_tables = nullptr;
+        ctx->tables_cap = 0;
+        CUDA_TRY(ctx, cudaMallocHost(&ctx->h_tables, need + need / 4));
+        ctx->tables_cap = need + need / 4;
+      }
     }
     char* hp = (char*)ctx->h_tables;
-    if (n_items) {
-      std::memcpy(hp, B.items.data(), n_items * sizeof(ItemDev));
-      CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_items, hp, n_items * sizeof(ItemDev), cudaMemcpyHostToDevice, ctx->stream));
-    }
+    char* hi = hp + (quad ? q_bytes : 0);   // items behind the quadrature tables
     if (quad) {
-      if ((rc = ensure_device_buffer(ctx, &ctx->d_qtab, &ctx->qtab_cap, q_bytes))) return rc;
-      char* hq = hp + i_bytes;
-      std::memcpy(hq + o_s, B.qstreams.data(), B.qstreams.size() * sizeof(QStreamDev));
-      std::memcpy(hq + o_r, B.qrows.data(), B.qrows.size() * sizeof(ItemDev));
-      std::memcpy(hq + o_g, B.bgroups.data(), B.bgroups.size() * sizeof(BoundaryGroupDev));
-      CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_qtab, hq, q_bytes, cudaMemcpyHostToDevice, ctx->stream));
+      if (!streams_uploaded) {
+        if ((rc = ensure_device_buffer(ctx, &ctx->d_qtab, &ctx->qtab_cap, q_bytes))) return rc;
+        std::memcpy(hp + o_s, B.qstreams.data(), B.qstreams.size() * sizeof(QStreamDev));
+      }
+      std::memcpy(hp + o_r, B.qrows.data(), B.qrows.size() * sizeof(ItemDev));
+      std::memcpy(hp + o_g, B.bgroups.data(), B.bgroups.size() * sizeof(BoundaryGroupDev));
+      const size_t from = streams_uploaded ? o_r : 0;
+      if (q_bytes > from)
+        CUDA_TRY(ctx, cudaMemcpyAsync((char*)ctx->d_qtab + from, hp + from, q_bytes - from, cudaMemcpyHostToDevice,
+                                      ctx->stream));
+    }
+    if (n_items) {
+      std::memcpy(hi, B.items.data(), n_items * sizeof(ItemDev));
+      CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_items, hi, n_items * sizeof(ItemDev), cudaMemcpyHostToDevice, ctx->stream));
     }
     CUDA_TRY(ctx, cudaEventRecord(ctx->ev_tables, ctx->stream));
     ctx->tables_in_flight = true;
@@ -687,63 +822,10 @@ static int run_batch_impl(aslsd_ctx* ctx, BatchPlan& B, double* raw_device) {
   const QStreamDev* d_streams = (const QStreamDev*)((const char*)ctx->d_qtab + o_s);
   const ItemDev* d_qrows = (const ItemDev*)((const char*)ctx->d_qtab + o_r);
   const BoundaryGroupDev* d_groups = (const BoundaryGroupDev*)((const char*)ctx->d_qtab + o_g);
-  CUDA_TRY(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
   CUDA_TRY(ctx, cudaMemsetAsync(raw_device, 0, std::max<size_t>(1, n_rows) * ASLSD_MAX_COMP * sizeof(double),
                                 ctx->stream));
-  // The node weights depend on the event streams and on the bin grids only (not on omega, not
-  // on the evaluation point as long as the windows stay): with the weight cache on, a repeated
-  // evaluation on the same plan - the iterations of a fit with fixed (beta, delta) - skips the
-  // pass over the event pairs.
-  // (the record of what d_q_weights holds decides: several plans share the buffer)
-  const bool reuse_weights = quad && ctx->cache_weights && weights_match(ctx, B);
-  ctx->last_weights_reused = reuse_weights;
-  ctx->moment_timing_pending = false;
-  ctx->last_moment_ms = 0.;
-  if (quad && !reuse_weights) {
-    if (ctx->q_smem_set == 0) {
-      // the attribute belongs to the function, not to this context: every context asks for the
-      // same ceiling, so contexts with different bin counts never lower each other's limit
-      CUDA_TRY(ctx, cudaFuncSetAttribute(lag_moment_kernel<false, LqSmall>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)LqSmall::SMEM_BUDGET));
-      CUDA_TRY(ctx, cudaFuncSetAttribute(lag_moment_kernel<false, LqBig>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)LqBig::SMEM_BUDGET));
-      CUDA_TRY(ctx, cudaFuncSetAttribute(lag_moment_kernel<true, LqBig>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)LqBig::SMEM_BUDGET));
-      ctx->q_smem_set = LqBig::SMEM_BUDGET;
-    }
-    CUDA_TRY(ctx, cudaEventRecord(ctx->ev_q0, ctx->stream));
-    unsigned long long* d_qcnt = ctx->d_counts + B.n_wu + n_items;
-    const int n_streams = (int)B.qstreams.size();
-    if (B.q_cat_wu[1] > B.q_cat_wu[0]) {
-      lag_moment_kernel<false, LqSmall><<<(unsigned)(B.q_cat_wu[1] - B.q_cat_wu[0]), LqSmall::NT, B.q_cat_smem[0],
-                                           ctx->stream>>>((const DimDev*)ctx->d_dims, d_streams, n_streams,
-                                                          ctx->d_q_partials, d_qcnt, ctx->d_weights, B.q_cat_wu[0]);
-      ctx->last_launches++;
-    }
-    if (B.q_cat_wu[2] > B.q_cat_wu[1]) {
-      lag_moment_kernel<false, LqBig><<<(unsigned)(B.q_cat_wu[2] - B.q_cat_wu[1]), LqBig::NT, B.q_cat_smem[1],
-                                         ctx->stream>>>((const DimDev*)ctx->d_dims, d_streams, n_streams,
-                                                        ctx->d_q_partials, d_qcnt, ctx->d_weights, B.q_cat_wu[1]);
-      ctx->last_launches++;
-    }
-    if (B.q_cat_wu[3] > B.q_cat_wu[2]) {
-      lag_moment_kernel<true, LqBig><<<(unsigned)(B.q_cat_wu[3] - B.q_cat_wu[2]), LqBig::NT, B.q_cat_smem[2],
-                                        ctx->stream>>>((const DimDev*)ctx->d_dims, d_streams, n_streams,
-                                                       ctx->d_q_partials, d_qcnt, ctx->d_weights, B.q_cat_wu[2]);
-      ctx->last_launches++;
-    }
-    CUDA_TRY(ctx, cudaEventRecord(ctx->ev_q1, ctx->stream));
-    ctx->moment_timing_pending = true;
-    const dim3 wgrid((unsigned)((B.q_jmax + LQ_WB - 1) / LQ_WB), (unsigned)B.qstreams.size());
-    ctx->w_streams.clear();   // being rewritten
-    lag_weights_kernel<<<wgrid, LQ_WB * LQ_ND, 0, ctx->stream>>>(d_streams, ctx->d_q_partials, ctx->d_q_weights);
-    ctx->last_launches++;
-    if (ctx->cache_weights) {   // record what the buffer holds: later calls (of any plan) may reuse it
-      ctx->w_streams.assign((const unsigned char*)B.qstreams.data(),
-                            (const unsigned char*)(B.qstreams.data() + B.qstreams.size()));
-      ctx->w_events_epoch = ctx->events_epoch;
-    }
-  }
+  if (quad && !reuse_weights && !moments_done)
+    if ((rc = launch_moments(ctx, B, d_streams))) return rc;
   launch_pair<ITEM_UPS_GAUSS>(ctx, B, d_items);
   launch_pair<ITEM_UPS_EXP>(ctx, B, d_items);
   launch_pair<ITEM_UPS_EG>(ctx, B, d_items);
@@ -770,7 +852,7 @@ static int run_batch_impl(aslsd_ctx* ctx, BatchPlan& B, double* raw_device) {
     launch_quad<ITEM_UPS_GE>(ctx, B, d_streams, d_qrows, raw_device);
     launch_quad<ITEM_PHI_GAUSS>(ctx, B, d_streams, d_qrows, raw_device);
     launch_quad<ITEM_PHI_EXP>(ctx, B, d_streams, d_qrows, raw_device);
-    unsigned long long* d_bcnt = ctx->d_counts + B.n_wu + n_items + B.n_wu_q;
+    unsigned long long* d_bcnt = ctx->d_counts + B.n_wu + n_items;
     launch_boundary<ITEM_UPS_GAUSS>(ctx, B, d_streams, d_groups, d_qrows, raw_device, d_bcnt);
     launch_boundary<ITEM_UPS_EXP>(ctx, B, d_streams, d_groups, d_qrows, raw_device, d_bcnt);
     launch_boundary<ITEM_UPS_EG>(ctx, B, d_streams, d_groups, d_qrows, raw_device, d_bcnt);
@@ -1300,27 +1382,29 @@ extern "C" int aslsd_exact_assemble(aslsd_ctx* ctx, int k, const double* x_k, in
 extern "C" int aslsd_last_work_counts(aslsd_ctx* ctx, int64_t* counts, int n) {
   if (!ctx || !counts || n < 8) return ASLSD_ERR_ARG;
   CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  // d_counts: [per-item work units | items | boundary groups]; d_qcounts: the moment kernels' work units
   const size_t n_old = (size_t)ctx->last_n_wu + (size_t)ctx->last_n_items;
-  const size_t n_all = n_old + (size_t)ctx->last_n_wu_q + (size_t)ctx->last_n_bgroups;
-  std::vector<unsigned long long> h(std::max<size_t>(1, n_all));
-  if (n_all) {
+  const size_t n_all = n_old + (size_t)ctx->last_n_bgroups;
+  const size_t n_q = ctx->last_weights_reused ? 0 : (size_t)ctx->last_n_wu_q;
+  std::vector<unsigned long long> h(std::max<size_t>(1, n_all)), hq(std::max<size_t>(1, n_q));
+  if (n_all)
     CUDA_TRY(ctx, cudaMemcpyAsync(h.data(), ctx->d_counts, sizeof(unsigned long long) * n_all,
                                   cudaMemcpyDeviceToHost, ctx->stream));
-    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
-  }
+  if (n_q)
+    CUDA_TRY(ctx, cudaMemcpyAsync(hq.data(), ctx->d_qcounts, sizeof(unsigned long long) * n_q,
+                                  cudaMemcpyDeviceToHost, ctx->stream));
+  if (n_all || n_q) CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
   int64_t pe = 0, se = 0;
   for (int f = 0; f < ITEM_N_FAMILIES; ++f) {
     const bool pair = is_pair_family(f);
     for (int x = 0; x < ctx->last_fam_count[f]; ++x)
       (pair ? pe : se) += (int64_t)h[(size_t)ctx->last_n_wu + ctx->last_fam_first[f] + x];
   }
-  for (int64_t g = 0; g < ctx->last_n_bgroups; ++g)
-    pe += (int64_t)h[n_old + (size_t)ctx->last_n_wu_q + (size_t)g];
+  for (int64_t g = 0; g < ctx->last_n_bgroups; ++g) pe += (int64_t)h[n_old + (size_t)g];
   counts[0] = pe;
   counts[1] = se;
   int64_t pairs = 0;
-  if (!ctx->last_weights_reused)
-    for (int64_t w = 0; w < ctx->last_n_wu_q; ++w) pairs += (int64_t)h[n_old + (size_t)w];
+  for (size_t w = 0; w < n_q; ++w) pairs += (int64_t)hq[w];
   counts[2] = pairs;
   for (int c = 3; c < 8; ++c) counts[c] = ctx->last_work[c];
   return ASLSD_OK;

@@ -416,6 +416,10 @@ class InjectingEngine:
         self._weights = [(int(i), np.asarray(v, dtype=float)) for i, v in vectors]
         return self._real.set_weights(vectors)
 
+    def set_horizon(self, T_f):
+        self._T_f = float(T_f)
+        return self._real.set_horizon(T_f)
+
     def exact_sums_weighted(self, k, x_k, roles, term_mask=None, compute_f_sum=True, compute_diff_f_sum=True,
                             ranges=None):
         args = (k, x_k, roles, term_mask, compute_f_sum, compute_diff_f_sum, ranges)
