@@ -41,11 +41,12 @@ def test_replay_reference_trace_strict(engine, name):
     replay_strat_golden(name, engine, mode='strict', free_running=(name == 'strat_exp1d'))
 
 
-def _random_batch(rng, times, k, d, n_strata, n_per):
+def _random_batch(rng, times, k, d, n_strata, n_per, kinds=None):
     """Random (m, n) samples for every term kind, far lags included."""
     terms, offsets, ms, ns = [], [0], [], []
-    for kind, i, j in [(0, 0, 0), (1, d - 1, d - 1), (2, 0, 0), (2, d - 1, d - 1), (3, 0, 0),
-                       (3, 0, d - 1), (3, d - 1, 0)]:
+    if kinds is None:
+        kinds = [(0, 0, 0), (1, d - 1, d - 1), (2, 0, 0), (2, d - 1, d - 1), (3, 0, 0), (3, 0, d - 1), (3, d - 1, 0)]
+    for kind, i, j in kinds:
         tgt, src = (k, i) if kind == 2 else (i, j)
         terms.append((kind, i, j, n_strata))
         for s in range(n_strata):
@@ -82,39 +83,58 @@ def test_sampled_sums_match_oracle(engine, name, grad_alloc):
     engine.set_events(times, T_f)
     engine.set_model(model)
     for k in range(d):
-        x = case_x(name)[k]
-        terms, offsets, ix_m, ix_n = _random_batch(rng, times, k, d, n_strata=4, n_per=300)
-        n_strata = len(offsets) - 1
-        sizes = np.where(np.arange(n_strata) % 4 < 2, rng.integers(2, 10 ** 6, size=n_strata), 0).astype(float)
-        dflt = rng.uniform(size=n_strata)
-        sums, out_off, mean, std, rel = engine.sampled_sums(
-            k, x, terms, offsets, ix_m, ix_n, strata_sizes=sizes, default_alloc=dflt,
-            compute_diff_f_sum=True, grad_alloc=grad_alloc)
-        s_ix = 0
-        for kind, i, j, ns in terms:
-            for s in range(ns):
-                a, b = offsets[s_ix], offsets[s_ix + 1]
-                vals = OS.term_values(model, k, x, times, T_f, kind, i, j, ix_m[a:b], ix_n[a:b])
-                tot, o_mean, o_std = OS.stratum_statistics(vals, grad_alloc)
-                got = sums[out_off[s_ix]:out_off[s_ix + 1]]
-                scale = np.abs(vals).sum(axis=0)
-                # absolute floor ("abs floor 1e-300"; here 1e-290): a Gaussian stratum
-                # whose samples all lie in the far tail sums to a denormal (< 2.2e-308), where
-                # exp of the device and of numpy differ in the few bits that are left
-                err = np.abs(got - tot)
-                ok = err <= RTOL * np.abs(tot) + 1e-13 * scale
-                # ... and the floor is only ever what decides in that range
-                assert np.all(scale[~ok] < ABS_FLOOR), (kind, i, j, s, err, scale)
-                assert np.all(err <= RTOL * np.abs(tot) + 1e-13 * scale + ABS_FLOOR), (kind, i, j, s)
-                assert abs(mean[s_ix] - o_mean) <= RTOL * abs(o_mean) + ABS_FLOOR
-                assert abs(std[s_ix] - o_std) <= 1e-9 * abs(o_std) + 1e-14 * abs(o_mean) + ABS_FLOOR
-                s_ix += 1
-        # allocation groups: strata 0-1 of every term
-        for q in range(len(terms)):
-            a = 4 * q
-            want = OS.update_allocation(sizes[a:a + 2], std[a:a + 2], dflt[a:a + 2])
-            np.testing.assert_allclose(rel[a:a + 2], want, rtol=1e-12)
-            np.testing.assert_array_equal(rel[a + 2:a + 4], dflt[a + 2:a + 4])
+        _check_sampled_against_oracle(engine, model, times, T_f, k, case_x(name)[k], rng, grad_alloc)
+
+
+def _check_sampled_against_oracle(engine, model, times, T_f, k, x, rng, grad_alloc, kinds=None):
+    d = model['d']
+    terms, offsets, ix_m, ix_n = _random_batch(rng, times, k, d, n_strata=4, n_per=300, kinds=kinds)
+    n_strata = len(offsets) - 1
+    sizes = np.where(np.arange(n_strata) % 4 < 2, rng.integers(2, 10 ** 6, size=n_strata), 0).astype(float)
+    dflt = rng.uniform(size=n_strata)
+    sums, out_off, mean, std, rel = engine.sampled_sums(
+        k, x, terms, offsets, ix_m, ix_n, strata_sizes=sizes, default_alloc=dflt,
+        compute_diff_f_sum=True, grad_alloc=grad_alloc)
+    s_ix = 0
+    for kind, i, j, ns in terms:
+        for s in range(ns):
+            a, b = offsets[s_ix], offsets[s_ix + 1]
+            vals = OS.term_values(model, k, x, times, T_f, kind, i, j, ix_m[a:b], ix_n[a:b])
+            tot, o_mean, o_std = OS.stratum_statistics(vals, grad_alloc)
+            got = sums[out_off[s_ix]:out_off[s_ix + 1]]
+            scale = np.abs(vals).sum(axis=0)
+            # absolute floor ("abs floor 1e-300"; here 1e-290): a Gaussian stratum
+            # whose samples all lie in the far tail sums to a denormal (< 2.2e-308), where
+            # exp of the device and of numpy differ in the few bits that are left
+            err = np.abs(got - tot)
+            ok = err <= RTOL * np.abs(tot) + 1e-13 * scale
+            # ... and the floor is only ever what decides in that range
+            assert np.all(scale[~ok] < ABS_FLOOR), (kind, i, j, s, err, scale)
+            assert np.all(err <= RTOL * np.abs(tot) + 1e-13 * scale + ABS_FLOOR), (kind, i, j, s)
+            assert abs(mean[s_ix] - o_mean) <= RTOL * abs(o_mean) + ABS_FLOOR
+            assert abs(std[s_ix] - o_std) <= 1e-9 * abs(o_std) + 1e-14 * abs(o_mean) + ABS_FLOOR
+            s_ix += 1
+    # allocation groups: strata 0-1 of every term
+    for q in range(len(terms)):
+        a = 4 * q
+        want = OS.update_allocation(sizes[a:a + 2], std[a:a + 2], dflt[a:a + 2])
+        np.testing.assert_allclose(rel[a:a + 2], want, rtol=1e-12)
+        np.testing.assert_array_equal(rel[a + 2:a + 4], dflt[a + 2:a + 4])
+
+
+@pytest.mark.parametrize('grad_alloc', [False, True])
+def test_sampled_sums_of_the_benchmark_model_match_oracle(engine, grad_alloc):
+    """The benchmark's own model (ten event types, sums of ten Gaussians, configuration C5) on a
+    short path: per-stratum sums, statistics and allocations of terms whose event types differ from
+    the sub-problem's and from each other (the rule at d = 10), against the oracle."""
+    from aslsd_b200 import simulate
+    model, times, T_f, xs = simulate.config_c5(d=10, n_basis=10, T_f=700., seed=1234)
+    engine.set_events(times, T_f)
+    engine.set_model(model)
+    rng = np.random.default_rng(17)
+    for k, kinds in ((0, [(0, 3, 3), (1, 7, 7), (2, 5, 5), (2, 0, 0), (3, 4, 4), (3, 2, 8), (3, 8, 2), (3, 0, 6)]),
+                     (6, [(0, 6, 6), (1, 1, 1), (2, 9, 9), (3, 6, 6), (3, 9, 3), (3, 3, 6)])):
+        _check_sampled_against_oracle(engine, model, times, T_f, k, xs[k], rng, grad_alloc, kinds=kinds)
 
 
 def test_update_allocation_entry_point(engine):
