@@ -97,10 +97,33 @@ struct TermPlan {
   int item_first, item_count;   // items computing this term's cross components
 };
 
+struct aslsd_ctx;
+// The context's compute stream.  Event uploads from page-locked arrays run on a copy stream of their
+// own (ctx.cu: aslsd_set_events); whoever takes the compute stream as a cudaStream_t - every kernel
+// launch, copy and event record written `ctx->stream` - first orders it behind those uploads
+// (aslsd_join_uploads).  Only the launch sequence that knows what it may start before the last event
+// type has arrived (exact.cu: the moment kernels of the streams whose types are there) asks for raw().
+struct CtxStream {
+  cudaStream_t s = nullptr;
+  aslsd_ctx* owner = nullptr;
+  inline operator cudaStream_t() const;
+  cudaStream_t raw() const { return s; }
+};
+
 struct aslsd_ctx {
   int device = 0;
   cudaStream_t own_stream = nullptr;
-  cudaStream_t stream = nullptr;
+  CtxStream stream;
+  // uploads in flight on the copy stream: ev_type[i] = type i (and every type before it) is on the
+  // device, checked for order, its bucket table built
+  cudaStream_t copy_stream = nullptr;
+  std::vector<cudaEvent_t> ev_type;
+  int n_upload_types = 0;
+  bool uploads_pending = false;
+  size_t upload_bytes = 0;              // of the uploads in flight
+  // second lane of the moment kernels launched behind those uploads (exact.cu: launch_moments)
+  cudaStream_t aux_stream = nullptr;
+  cudaEvent_t ev_aux0 = nullptr, ev_aux1 = nullptr;
   std::string err;
 
   // events
@@ -207,6 +230,17 @@ struct aslsd_ctx {
   int last_n_items = 0;
   int last_fam_first[ITEM_N_FAMILIES] = {0}, last_fam_count[ITEM_N_FAMILIES] = {0};
 };
+
+inline void aslsd_join_uploads(aslsd_ctx* ctx) {
+  if (!ctx->uploads_pending) return;
+  ctx->uploads_pending = false;
+  if (ctx->n_upload_types > 0) cudaStreamWaitEvent(ctx->stream.s, ctx->ev_type[(size_t)ctx->n_upload_types - 1], 0);
+}
+inline CtxStream::operator cudaStream_t() const {
+  if (owner) aslsd_join_uploads(owner);
+  return s;
+}
+
 
 struct DimDev {
   const double* t;     // event times of this type

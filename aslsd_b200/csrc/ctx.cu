@@ -50,6 +50,10 @@ extern "C" int aslsd_create(aslsd_ctx** out, int device) {
   ctx->device = device;
   if (cudaSetDevice(device) != cudaSuccess ||
       cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaStreamCreateWithFlags(&ctx->aux_stream, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaEventCreateWithFlags(&ctx->ev_aux0, cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&ctx->ev_aux1, cudaEventDisableTiming) != cudaSuccess ||
       cudaEventCreate(&ctx->ev0) != cudaSuccess || cudaEventCreate(&ctx->ev1) != cudaSuccess ||
       cudaEventCreate(&ctx->ev_q0) != cudaSuccess || cudaEventCreate(&ctx->ev_q1) != cudaSuccess ||
       cudaEventCreateWithFlags(&ctx->ev_flag, cudaEventDisableTiming) != cudaSuccess ||
@@ -62,7 +66,8 @@ extern "C" int aslsd_create(aslsd_ctx** out, int device) {
     delete ctx;
     return ASLSD_ERR_CUDA;
   }
-  ctx->stream = ctx->own_stream;
+  ctx->stream.s = ctx->own_stream;
+  ctx->stream.owner = ctx;
   *out = ctx;
   return ASLSD_OK;
 }
@@ -71,6 +76,12 @@ extern "C" int aslsd_destroy(aslsd_ctx* ctx) {
   if (!ctx) return ASLSD_OK;
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
+  if (ctx->copy_stream) cudaStreamSynchronize(ctx->copy_stream);
+  for (auto ev : ctx->ev_type) cudaEventDestroy(ev);
+  if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+  if (ctx->aux_stream) { cudaStreamSynchronize(ctx->aux_stream); cudaStreamDestroy(ctx->aux_stream); }
+  if (ctx->ev_aux0) cudaEventDestroy(ctx->ev_aux0);
+  if (ctx->ev_aux1) cudaEventDestroy(ctx->ev_aux1);
   cudaFree(ctx->d_times);
   cudaFree(ctx->d_tab);
   cudaFree(ctx->d_dims);
@@ -120,12 +131,12 @@ extern "C" const char* aslsd_last_error(const aslsd_ctx* ctx) {
 extern "C" int aslsd_set_stream(aslsd_ctx* ctx, void* cuda_stream) {
   if (!ctx) return ASLSD_ERR_ARG;
   cudaStream_t next = cuda_stream ? (cudaStream_t)cuda_stream : ctx->own_stream;
-  if (next != ctx->stream) {
+  if (next != ctx->stream.raw()) {
     // uploads and kernels already enqueued are ordered on the old stream only
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
   }
-  ctx->stream = next;
+  ctx->stream.s = next;
   return ASLSD_OK;
 }
 
@@ -259,7 +270,46 @@ extern "C" int aslsd_set_events(aslsd_ctx* ctx, int d, const int64_t* n_events,
   ctx->h_times.assign(d, nullptr);
   bool any_in_place = false;
   for (int i = 0; i < d; ++i) any_in_place |= in_place[i] != 0;
-  CUDA_TRY(ctx, cudaMemsetAsync(ctx->d_flag, 0, sizeof(int), ctx->stream));
+  // Every array page-locked: the uploads, the order checks and the bucket tables go to the copy stream,
+  // one event per type, and the compute stream is ordered behind them only when it is next used
+  // (CtxStream) - or, for the moment kernels of an exact-sum call, type by type as the data arrives
+  // (exact.cu).  Otherwise everything stays on the compute stream as before.
+  const bool on_copy_stream = n_staged == 0 && any_in_place;
+  cudaStream_t up = on_copy_stream ? ctx->copy_stream : ctx->stream.raw();
+  ctx->uploads_pending = false;
+  if (on_copy_stream) {
+    while ((int)ctx->ev_type.size() < d) {
+      cudaEvent_t ev;
+      CUDA_TRY(ctx, cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+      ctx->ev_type.push_back(ev);
+    }
+  }
+  // descriptors of the types (bucket-table geometry from the first and last time of each)
+  ctx->tab_t0.assign(d, 0.);
+  ctx->tab_w.assign(d, 1.);
+  ctx->h_dims.assign(sizeof(DimDev) * (size_t)d, 0);
+  DimDev* dims0 = reinterpret_cast<DimDev*>(ctx->h_dims.data());
+  for (int i = 0; i < d; ++i) {
+    if (n_events[i] > 0) {
+      const double t0 = times[i][0], t1 = times[i][n_events[i] - 1];
+      double w = (t1 - t0) / (double)tab_len[i];
+      w = w * (1. + 1e-9) + 1e-300;
+      if (!(w > 0.)) w = 1.;
+      ctx->tab_t0[i] = t0;
+      ctx->tab_w[i] = w;
+    }
+    dims0[i].t = ctx->d_times + off[i];
+    dims0[i].tab = ctx->d_tab + tab_off[i];
+    dims0[i].n = n_events[i];
+    dims0[i].n_buckets = tab_len[i];
+    dims0[i].t0 = ctx->tab_t0[i];
+    dims0[i].w = ctx->tab_w[i];
+    dims0[i].inv_w = 1. / ctx->tab_w[i];
+    dims0[i].bad = ctx->d_flag;
+  }
+  CUDA_TRY(ctx, cudaMemsetAsync(ctx->d_flag, 0, sizeof(int), up));
+  if (on_copy_stream)
+    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_dims, dims0, sizeof(DimDev) * d, cudaMemcpyHostToDevice, up));
   // Host pass (copy into the pinned block + order check) split into segments over a few
   // threads; the thread that completes a type issues its host -> device copy, so the
   // transfer of one type overlaps the host pass over the others.
@@ -280,11 +330,20 @@ extern "C" int aslsd_set_events(aslsd_ctx* ctx, int d, const int64_t* n_events,
       // the transfer starts now and runs while the threads below check the order
       const int64_t len = off[i + 1] - off[i];
       CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_times + off[i], times[i], sizeof(double) * (size_t)n,
-                                    cudaMemcpyHostToDevice, ctx->stream));
+                                    cudaMemcpyHostToDevice, up));
       CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_times + off[i] + n, ctx->h_pad, sizeof(double) * (size_t)(len - n),
-                                    cudaMemcpyHostToDevice, ctx->stream));
-      check_sorted_kernel<<<(unsigned)std::min<int64_t>(1184, (n + 255) / 256), 256, 0, ctx->stream>>>(
+                                    cudaMemcpyHostToDevice, up));
+      check_sorted_kernel<<<(unsigned)std::min<int64_t>(1184, (n + 255) / 256), 256, 0, up>>>(
           ctx->d_times + off[i], n, ctx->d_flag);
+      if (on_copy_stream) {
+        // the type is complete once its bucket table is built: one event per type, in upload order
+        // (the copy stream is in order: the event of type i covers the types before it and the
+        // descriptors above)
+        const int64_t nb = tab_len[i];
+        build_bucket_table_kernel<<<(int)((nb + 1 + 255) / 256), 256, 0, up>>>(
+            dims0[i].t, dims0[i].n, ctx->d_tab + tab_off[i], nb, dims0[i].t0, dims0[i].w);
+        CUDA_TRY(ctx, cudaEventRecord(ctx->ev_type[(size_t)i], up));
+      }
     }
   }
   std::atomic<size_t> next(0);
@@ -316,7 +375,7 @@ extern "C" int aslsd_set_events(aslsd_ctx* ctx, int d, const int64_t* n_events,
         const int64_t len = off[sg.dim + 1] - off[sg.dim];
         for (int64_t m = n_events[sg.dim]; m < len; ++m) dst[m] = 1.7e308;
         if (cudaMemcpyAsync(ctx->d_times + off[sg.dim], dst, sizeof(double) * (size_t)len,
-                            cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess)
+                            cudaMemcpyHostToDevice, up) != cudaSuccess)
           cuda_err.store(1);
       }
     }
@@ -344,44 +403,29 @@ extern "C" int aslsd_set_events(aslsd_ctx* ctx, int d, const int64_t* n_events,
   ctx->off = off;
   ctx->tab_off = tab_off;
   ctx->tab_len = tab_len;
-  ctx->tab_t0.assign(d, 0.);
-  ctx->tab_w.assign(d, 1.);
   ctx->times_len = off[d];
-  ctx->h_dims.assign(sizeof(DimDev) * (size_t)d, 0);
   DimDev* dims = reinterpret_cast<DimDev*>(ctx->h_dims.data());
-  for (int i = 0; i < d; ++i) {
-    if (n_events[i] > 0) {
-      const double t0 = times[i][0], t1 = times[i][n_events[i] - 1];
-      double w = (t1 - t0) / (double)tab_len[i];
-      w = w * (1. + 1e-9) + 1e-300;
-      if (!(w > 0.)) w = 1.;
-      ctx->tab_t0[i] = t0;
-      ctx->tab_w[i] = w;
+  if (!on_copy_stream) {
+    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_dims, dims, sizeof(DimDev) * d, cudaMemcpyHostToDevice, up));
+    for (int i = 0; i < d; ++i) {
+      const int64_t nb = tab_len[i];
+      const int threads = 256;
+      const int blocks = (int)((nb + 1 + threads - 1) / threads);
+      build_bucket_table_kernel<<<blocks, threads, 0, up>>>(
+          dims[i].t, dims[i].n, ctx->d_tab + tab_off[i], nb, dims[i].t0, dims[i].w);
     }
-    dims[i].t = ctx->d_times + off[i];
-    dims[i].tab = ctx->d_tab + tab_off[i];
-    dims[i].n = n_events[i];
-    dims[i].n_buckets = tab_len[i];
-    dims[i].t0 = ctx->tab_t0[i];
-    dims[i].w = ctx->tab_w[i];
-    dims[i].inv_w = 1. / ctx->tab_w[i];
-    dims[i].bad = ctx->d_flag;
-  }
-  CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_dims, dims, sizeof(DimDev) * d, cudaMemcpyHostToDevice,
-                                ctx->stream));
-  for (int i = 0; i < d; ++i) {
-    const int64_t nb = tab_len[i];
-    const int threads = 256;
-    const int blocks = (int)((nb + 1 + threads - 1) / threads);
-    build_bucket_table_kernel<<<blocks, threads, 0, ctx->stream>>>(
-        dims[i].t, dims[i].n, ctx->d_tab + tab_off[i], nb, dims[i].t0, dims[i].w);
   }
   CUDA_TRY(ctx, cudaGetLastError());
+  if (on_copy_stream) {
+    ctx->n_upload_types = d;
+    ctx->uploads_pending = true;
+    ctx->upload_bytes = sizeof(double) * n_tot;
+  }
   // no synchronisation here: the copies and the table kernels are ordered before whatever the
-  // caller enqueues next on this stream, and they overlap its host-side planning
+  // caller enqueues next on the compute stream, and they overlap its host-side planning
   if (any_in_place) {
-    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->h_flag, ctx->d_flag, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-    CUDA_TRY(ctx, cudaEventRecord(ctx->ev_flag, ctx->stream));
+    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->h_flag, ctx->d_flag, sizeof(int), cudaMemcpyDeviceToHost, up));
+    CUDA_TRY(ctx, cudaEventRecord(ctx->ev_flag, up));
     ctx->verdict_pending = true;
     // ASLSD_OPT_ASYNC_EVENTS off: wait for the device's verdict, so that an order violation is
     // reported by this call like for pageable inputs; on: the next call that waits for the

@@ -66,6 +66,10 @@ struct BatchPlan {
   std::vector<std::vector<int64_t>> q_groups;   // rows of every (streams, target block, weights) group, launch order
   std::vector<int> q_group_stream;              // its stream (index in qstreams), -1: per-item kernels only
   bool rows_pending = false;                    // build_work_rows has not run for the current streams
+  // streams of the small CTA shape are ordered by the later of their two event types: the work units of
+  // [q_arrival_wu[a], q_arrival_wu[a + 1]) need the types 0..a only, and can start while the other
+  // types are still being uploaded
+  std::vector<int64_t> q_arrival_wu;
   // scratch of build_work, kept between calls (no reallocation when only the events change)
   std::vector<ItemDev> scratch_q[ITEM_N_FAMILIES], scratch_f[ITEM_N_FAMILIES];
   int q_jmax = 0;
@@ -325,8 +329,11 @@ static int build_work_streams(aslsd_ctx* ctx, const int64_t* m_lo, const int64_t
     };
     std::vector<int> perm(B.qstreams.size()), new_ix(B.qstreams.size());
     for (size_t x = 0; x < perm.size(); ++x) perm[x] = (int)x;
-    std::stable_sort(perm.begin(), perm.end(),
-                     [&](int a, int b) { return category(B.qstreams[a]) < category(B.qstreams[b]); });
+    auto arrival = [](const QStreamDev& S) { return std::max(S.tgt_dim, S.src_dim); };
+    std::stable_sort(perm.begin(), perm.end(), [&](int a, int b) {
+      const int ca = category(B.qstreams[a]), cb = category(B.qstreams[b]);
+      return ca != cb ? ca < cb : arrival(B.qstreams[a]) < arrival(B.qstreams[b]);
+    });
     std::vector<QStreamDev> sorted(B.qstreams.size());
     for (size_t x = 0; x < perm.size(); ++x) {
       sorted[x] = B.qstreams[perm[x]];
@@ -373,6 +380,10 @@ static int build_work_streams(aslsd_ctx* ctx, const int64_t* m_lo, const int64_t
     wts += (int64_t)S.J * LQ_ND;
   }
   while (cat_seen < 3) B.q_cat_wu[++cat_seen] = qwu;
+  B.q_arrival_wu.assign((size_t)d + 1, B.q_cat_wu[1]);
+  for (auto it = B.qstreams.rbegin(); it != B.qstreams.rend(); ++it)
+    if (category(*it) == 0)
+      for (int a = 0; a <= std::max(it->tgt_dim, it->src_dim); ++a) B.q_arrival_wu[(size_t)a] = it->wu_first;
   B.n_wu_q = qwu;
   B.n_q_partials = part;
   B.n_q_weights = wts;
@@ -646,7 +657,11 @@ static int run_batch(aslsd_ctx* ctx, BatchPlan& B, double* raw_device) {
   return rc;
 }
 // The moment kernels of every category and the weights kernel, on the context's stream.
-static int launch_moments(aslsd_ctx* ctx, BatchPlan& B, const QStreamDev* d_streams) {
+// `st`: the compute stream.  With event uploads still in flight on the copy stream (`staged`, st then is
+// the raw stream, not yet ordered behind them) the small-shape launch is cut by the later event type of
+// its streams: each piece waits for that type's upload only and runs while the following ones arrive;
+// the stream is ordered behind all uploads before anything else is launched.
+static int launch_moments(aslsd_ctx* ctx, BatchPlan& B, const QStreamDev* d_streams, cudaStream_t st, bool staged) {
   if (ctx->q_smem_set == 0) {
     // the attribute belongs to the function, not to this context: every context asks for the
     // same ceiling, so contexts with different bin counts never lower each other's limit
@@ -658,32 +673,57 @@ static int launch_moments(aslsd_ctx* ctx, BatchPlan& B, const QStreamDev* d_stre
                                        (int)LqBig::SMEM_BUDGET));
     ctx->q_smem_set = LqBig::SMEM_BUDGET;
   }
-  CUDA_TRY(ctx, cudaEventRecord(ctx->ev_q0, ctx->stream));
+  CUDA_TRY(ctx, cudaEventRecord(ctx->ev_q0, st));
   unsigned long long* d_qcnt = ctx->d_qcounts;
   const int n_streams = (int)B.qstreams.size();
   if (B.q_cat_wu[1] > B.q_cat_wu[0]) {
-    lag_moment_kernel<false, LqSmall><<<(unsigned)(B.q_cat_wu[1] - B.q_cat_wu[0]), LqSmall::NT, B.q_cat_smem[0],
-                                         ctx->stream>>>((const DimDev*)ctx->d_dims, d_streams, n_streams,
-                                                        ctx->d_q_partials, d_qcnt, ctx->d_weights, B.q_cat_wu[0]);
-    ctx->last_launches++;
+    if (!staged) {
+      lag_moment_kernel<false, LqSmall><<<(unsigned)(B.q_cat_wu[1] - B.q_cat_wu[0]), LqSmall::NT, B.q_cat_smem[0], st>>>(
+          (const DimDev*)ctx->d_dims, d_streams, n_streams, ctx->d_q_partials, d_qcnt, ctx->d_weights, B.q_cat_wu[0]);
+      ctx->last_launches++;
+    } else {
+      // pieces of at least 1/16 of the launch, alternating between the compute stream and a second
+      // lane: the last wave of a piece (a work unit runs ~0.3 ms at C5) is filled by the next piece
+      const int64_t total = B.q_cat_wu[1] - B.q_cat_wu[0];
+      cudaStream_t lanes[2] = {st, ctx->aux_stream};
+      CUDA_TRY(ctx, cudaEventRecord(ctx->ev_aux0, st));                 // the stream table is on its way on st
+      CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->aux_stream, ctx->ev_aux0, 0));
+      int piece = 0;
+      int64_t w0 = B.q_cat_wu[0];
+      for (int a = 0; a < ctx->n_upload_types; ++a) {
+        const int64_t w1 = B.q_arrival_wu[(size_t)a + 1];
+        const bool last = a + 1 == ctx->n_upload_types;
+        if (w1 <= w0 || (!last && w1 - w0 < total / 16)) continue;    // too small: joins the next type's piece
+        cudaStream_t lane = lanes[piece++ & 1];
+        CUDA_TRY(ctx, cudaStreamWaitEvent(lane, ctx->ev_type[(size_t)a], 0));
+        lag_moment_kernel<false, LqSmall><<<(unsigned)(w1 - w0), LqSmall::NT, B.q_cat_smem[0], lane>>>(
+            (const DimDev*)ctx->d_dims, d_streams, n_streams, ctx->d_q_partials, d_qcnt, ctx->d_weights, w0);
+        ctx->last_launches++;
+        w0 = w1;
+      }
+      CUDA_TRY(ctx, cudaEventRecord(ctx->ev_aux1, ctx->aux_stream));
+      CUDA_TRY(ctx, cudaStreamWaitEvent(st, ctx->ev_aux1, 0));
+    }
+  }
+  if (staged) {
+    aslsd_join_uploads(ctx);   // everything below may read any event type
+    st = ctx->stream;
   }
   if (B.q_cat_wu[2] > B.q_cat_wu[1]) {
-    lag_moment_kernel<false, LqBig><<<(unsigned)(B.q_cat_wu[2] - B.q_cat_wu[1]), LqBig::NT, B.q_cat_smem[1],
-                                       ctx->stream>>>((const DimDev*)ctx->d_dims, d_streams, n_streams,
-                                                      ctx->d_q_partials, d_qcnt, ctx->d_weights, B.q_cat_wu[1]);
+    lag_moment_kernel<false, LqBig><<<(unsigned)(B.q_cat_wu[2] - B.q_cat_wu[1]), LqBig::NT, B.q_cat_smem[1], st>>>(
+        (const DimDev*)ctx->d_dims, d_streams, n_streams, ctx->d_q_partials, d_qcnt, ctx->d_weights, B.q_cat_wu[1]);
     ctx->last_launches++;
   }
   if (B.q_cat_wu[3] > B.q_cat_wu[2]) {
-    lag_moment_kernel<true, LqBig><<<(unsigned)(B.q_cat_wu[3] - B.q_cat_wu[2]), LqBig::NT, B.q_cat_smem[2],
-                                      ctx->stream>>>((const DimDev*)ctx->d_dims, d_streams, n_streams,
-                                                     ctx->d_q_partials, d_qcnt, ctx->d_weights, B.q_cat_wu[2]);
+    lag_moment_kernel<true, LqBig><<<(unsigned)(B.q_cat_wu[3] - B.q_cat_wu[2]), LqBig::NT, B.q_cat_smem[2], st>>>(
+        (const DimDev*)ctx->d_dims, d_streams, n_streams, ctx->d_q_partials, d_qcnt, ctx->d_weights, B.q_cat_wu[2]);
     ctx->last_launches++;
   }
-  CUDA_TRY(ctx, cudaEventRecord(ctx->ev_q1, ctx->stream));
+  CUDA_TRY(ctx, cudaEventRecord(ctx->ev_q1, st));
   ctx->moment_timing_pending = true;
   const dim3 wgrid((unsigned)((B.q_jmax + LQ_WB - 1) / LQ_WB), (unsigned)B.qstreams.size());
   ctx->w_streams.clear();   // being rewritten
-  lag_weights_kernel<<<wgrid, LQ_WB * LQ_ND, 0, ctx->stream>>>(d_streams, ctx->d_q_partials, ctx->d_q_weights);
+  lag_weights_kernel<<<wgrid, LQ_WB * LQ_ND, 0, st>>>(d_streams, ctx->d_q_partials, ctx->d_q_weights);
   ctx->last_launches++;
   if (ctx->cache_weights) {   // record what the buffer holds: later calls (of any plan) may reuse it
     ctx->w_streams.assign((const unsigned char*)B.qstreams.data(),
@@ -708,7 +748,8 @@ static int run_batch_impl(aslsd_ctx* ctx, BatchPlan& B, double* raw_device) {
   const size_t o_s = 0;
   const size_t o_r = o_s + ((B.qstreams.size() * sizeof(QStreamDev) + 15) & ~(size_t)15);
   bool streams_uploaded = false, moments_done = false;
-  CUDA_TRY(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
+  // (raw: recording the start of the call must not order the stream behind uploads in flight)
+  CUDA_TRY(ctx, cudaEventRecord(ctx->ev0, ctx->stream.raw()));
   if (quad) {
     if ((rc = upload_quadrature_tables(ctx))) return rc;
     if ((rc = ensure_device_buffer(ctx, (void**)&ctx->d_q_partials, &ctx->q_partials_cap,
@@ -748,10 +789,14 @@ static int run_batch_impl(aslsd_ctx* ctx, BatchPlan& B, double* raw_device) {
     if ((rc = ensure_device_buffer(ctx, &ctx->d_qtab, &ctx->qtab_cap, q_bytes_max))) return rc;
     char* hp = (char*)ctx->h_tables;
     std::memcpy(hp + o_s, B.qstreams.data(), B.qstreams.size() * sizeof(QStreamDev));
-    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_qtab, hp, o_r, cudaMemcpyHostToDevice, ctx->stream));
+    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_qtab, hp, o_r, cudaMemcpyHostToDevice, ctx->stream.raw()));
     streams_uploaded = true;
     if (!reuse_weights) {
-      if ((rc = launch_moments(ctx, B, (const QStreamDev*)((const char*)ctx->d_qtab + o_s)))) return rc;
+      // (worth it when the transfer is long against the planning that already overlaps it: >= 24 MB)
+      const bool staged = ctx->uploads_pending && ctx->n_upload_types == ctx->d && ctx->upload_bytes >= ((size_t)24 << 20);
+      if ((rc = launch_moments(ctx, B, (const QStreamDev*)((const char*)ctx->d_qtab + o_s),
+                               staged ? ctx->stream.raw() : (cudaStream_t)ctx->stream, staged)))
+        return rc;
       moments_done = true;
     }
   }
@@ -825,7 +870,7 @@ static int run_batch_impl(aslsd_ctx* ctx, BatchPlan& B, double* raw_device) {
   CUDA_TRY(ctx, cudaMemsetAsync(raw_device, 0, std::max<size_t>(1, n_rows) * ASLSD_MAX_COMP * sizeof(double),
                                 ctx->stream));
   if (quad && !reuse_weights && !moments_done)
-    if ((rc = launch_moments(ctx, B, d_streams))) return rc;
+    if ((rc = launch_moments(ctx, B, d_streams, ctx->stream, false))) return rc;
   launch_pair<ITEM_UPS_GAUSS>(ctx, B, d_items);
   launch_pair<ITEM_UPS_EXP>(ctx, B, d_items);
   launch_pair<ITEM_UPS_EG>(ctx, B, d_items);

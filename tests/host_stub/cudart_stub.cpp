@@ -84,6 +84,7 @@ cudaError_t cudaFuncSetAttribute(const void*, cudaFuncAttribute, int) { return c
 cudaError_t cudaStreamCreateWithFlags(cudaStream_t* s, unsigned) { *s = (cudaStream_t)std::malloc(1); return cudaSuccess; }
 cudaError_t cudaStreamDestroy(cudaStream_t s) { std::free(s); return cudaSuccess; }
 cudaError_t cudaStreamSynchronize(cudaStream_t) { return cudaSuccess; }
+cudaError_t cudaStreamWaitEvent(cudaStream_t, cudaEvent_t, unsigned) { return cudaSuccess; }
 cudaError_t cudaEventCreate(cudaEvent_t* e) { *e = (cudaEvent_t)std::malloc(1); return cudaSuccess; }
 cudaError_t cudaEventCreateWithFlags(cudaEvent_t* e, unsigned) { *e = (cudaEvent_t)std::malloc(1); return cudaSuccess; }
 cudaError_t cudaEventDestroy(cudaEvent_t e) { std::free(e); return cudaSuccess; }
