@@ -118,3 +118,41 @@ def test_views_into_page_locked_arrays_are_uploaded_in_place(engine):
     got = engine.exact_assemble_batch([0, 1], xs, total)
     for a, b in zip(got, want):
         np.testing.assert_allclose(a, b, rtol=1e-12, atol=1e-12)
+
+
+def test_staged_moment_launches_give_identical_sums(engine):
+    """Page-locked uploads of at least 24 MB go to the copy stream and the moment kernels of the next
+    exact-sum call start in pieces, type by type as the data arrives, on two lanes (exact.cu:
+    launch_moments).  The pieces cut the same work units out of the same launch: bit-identical sums,
+    first call and repeated calls, against the pageable upload of the same events; other entry
+    points used right after such an upload (index maps) are ordered behind it."""
+    from aslsd_b200 import simulate
+    d = 4
+    model = simulate.sbf_gauss_model(d, 3)
+    rng = np.random.default_rng(21)
+    T_f = 9.0e5
+    times = [np.sort(rng.uniform(0, T_f, size=n)) for n in (900_001, 850_000, 910_000, 880_003)]   # 28 MB
+    xs = [np.concatenate([[0.5], rng.uniform(0.02, 0.1, size=3 * d)]) for _ in range(d)]
+    ks = list(range(d))
+    engine.set_model(model)
+    engine.use_weight_cache(False)
+    engine.set_events(times, T_f)
+    want = engine.exact_sums_batch(ks, xs)
+    kap, var, lag = engine.index_maps(want_lag_sizes=False)
+    pinned = _pinned(times)
+    for async_events in (True, False):
+        engine.use_async_events(async_events)
+        for rep in range(3):
+            engine.set_events(pinned, T_f)
+            got = engine.exact_sums_batch(ks, xs)
+            for a, b in zip(got, want):
+                np.testing.assert_array_equal(a, b)
+        again = engine.exact_sums_batch(ks, xs)          # events resident: one launch
+        for a, b in zip(again, want):
+            np.testing.assert_array_equal(a, b)
+        engine.set_events(pinned, T_f)
+        kap2, var2, _ = engine.index_maps(want_lag_sizes=False)   # straight after the upload
+        for i in range(d):
+            for j in range(d):
+                np.testing.assert_array_equal(kap2[i][j], kap[i][j])
+                np.testing.assert_array_equal(var2[i][j], var[i][j])
