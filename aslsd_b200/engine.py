@@ -21,6 +21,14 @@ def term_layout(desc, k):
     (log_name, offset, n1, n2, n_func) in the order the reference evaluates the
     terms (mhp_exact_estimator.py:722-756); n_func as in make_param_indexing
     (:141-170)."""
+    cache = getattr(desc, '_term_layouts', None)      # (an estimator call asks twice; d = 10: 120 terms)
+    if cache is None:
+        try:
+            cache = desc._term_layouts = {}
+        except AttributeError:
+            cache = {}
+    if k in cache:
+        return cache[k]
     d = desc.d
     npar = desc.matrix_n_param[k]
     out, pos = [], 0
@@ -36,6 +44,7 @@ def term_layout(desc, k):
             if i != j:
                 out.append(('upsilon_%d_%d' % (i, j), pos, npar[i], npar[j], 2))
                 pos += 1 + npar[i] + npar[j]
+    cache[k] = (out, pos)
     return out, pos
 
 
