@@ -301,8 +301,7 @@ def plugin_e2e(engine, model, times, T_f, xs, n_rep):
         for rep in range(n_rep + 2):
             engine.synchronize()
             t0 = time.perf_counter()
-            engine.set_events(path.list_times, T_f)           # what a new fit's first bind does
-            engine._events_key = None
+            engine._events_key = None                         # a new fit's first bind: one upload of the events
             engine.bind(path, mirror)
             t1 = time.perf_counter()
             calls = []

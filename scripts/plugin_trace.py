@@ -20,7 +20,6 @@ for k in range(d):
 for cache in (False, True):
     engine.use_weight_cache(cache)
     for rep in range(3):
-        engine.set_events(path.list_times, T_f)
         engine._events_key = None
         engine.bind(path, mirror)
         for k in range(d):
