@@ -124,6 +124,7 @@ struct aslsd_ctx {
   // second lane of the moment kernels launched behind those uploads (exact.cu: launch_moments)
   cudaStream_t aux_stream = nullptr;
   cudaEvent_t ev_aux0 = nullptr, ev_aux1 = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;   // second lane of an exact-sum call (exact.cu: run_batch_impl)
   std::string err;
 
   // events

@@ -54,6 +54,8 @@ extern "C" int aslsd_create(aslsd_ctx** out, int device) {
       cudaStreamCreateWithFlags(&ctx->aux_stream, cudaStreamNonBlocking) != cudaSuccess ||
       cudaEventCreateWithFlags(&ctx->ev_aux0, cudaEventDisableTiming) != cudaSuccess ||
       cudaEventCreateWithFlags(&ctx->ev_aux1, cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming) != cudaSuccess ||
       cudaEventCreate(&ctx->ev0) != cudaSuccess || cudaEventCreate(&ctx->ev1) != cudaSuccess ||
       cudaEventCreate(&ctx->ev_q0) != cudaSuccess || cudaEventCreate(&ctx->ev_q1) != cudaSuccess ||
       cudaEventCreateWithFlags(&ctx->ev_flag, cudaEventDisableTiming) != cudaSuccess ||
@@ -82,6 +84,8 @@ extern "C" int aslsd_destroy(aslsd_ctx* ctx) {
   if (ctx->aux_stream) { cudaStreamSynchronize(ctx->aux_stream); cudaStreamDestroy(ctx->aux_stream); }
   if (ctx->ev_aux0) cudaEventDestroy(ctx->ev_aux0);
   if (ctx->ev_aux1) cudaEventDestroy(ctx->ev_aux1);
+  if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
+  if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
   cudaFree(ctx->d_times);
   cudaFree(ctx->d_tab);
   cudaFree(ctx->d_dims);

@@ -595,17 +595,17 @@ static bool weights_match(const aslsd_ctx* ctx, const BatchPlan& B) {
 }
 
 template <int FAMILY>
-static void launch_pair(aslsd_ctx* ctx, const BatchPlan& B, const ItemDev* d_items) {
+static void launch_pair(aslsd_ctx* ctx, const BatchPlan& B, const ItemDev* d_items, cudaStream_t st) {
   if (B.fam_wu_count[FAMILY] == 0) return;
-  pair_kernel<FAMILY><<<(unsigned)B.fam_wu_count[FAMILY], PAIR_NT, 0, ctx->stream>>>(
+  pair_kernel<FAMILY><<<(unsigned)B.fam_wu_count[FAMILY], PAIR_NT, 0, st>>>(
       (const DimDev*)ctx->d_dims, d_items + B.fam_first[FAMILY], B.fam_count[FAMILY], ctx->T_f,
       ctx->d_partials, ctx->d_counts, B.fam_wu_first[FAMILY], ctx->d_weights);
   ctx->last_launches++;
 }
 template <int FAMILY>
-static void launch_single(aslsd_ctx* ctx, const BatchPlan& B, const ItemDev* d_items) {
+static void launch_single(aslsd_ctx* ctx, const BatchPlan& B, const ItemDev* d_items, cudaStream_t st) {
   if (B.fam_wu_count[FAMILY] == 0) return;
-  single_kernel<FAMILY><<<(unsigned)B.fam_wu_count[FAMILY], PAIR_NT, 0, ctx->stream>>>(
+  single_kernel<FAMILY><<<(unsigned)B.fam_wu_count[FAMILY], PAIR_NT, 0, st>>>(
       (const DimDev*)ctx->d_dims, d_items + B.fam_first[FAMILY], B.fam_count[FAMILY], ctx->T_f,
       ctx->d_partials, ctx->d_counts, B.fam_wu_first[FAMILY], ctx->d_weights);
   ctx->last_launches++;
@@ -628,9 +628,9 @@ static int upload_quadrature_tables(aslsd_ctx* ctx) {
 
 template <int FAMILY>
 static void launch_quad(aslsd_ctx* ctx, const BatchPlan& B, const QStreamDev* d_streams, const ItemDev* d_qrows,
-                        double* raw_device) {
+                        double* raw_device, cudaStream_t st) {
   if (B.qfam_count[FAMILY] == 0) return;
-  lag_quad_kernel<FAMILY><<<(unsigned)B.qfam_count[FAMILY], LQ_QT, 0, ctx->stream>>>(
+  lag_quad_kernel<FAMILY><<<(unsigned)B.qfam_count[FAMILY], LQ_QT, 0, st>>>(
       d_streams, d_qrows + B.qfam_first[FAMILY], ctx->d_q_weights, raw_device);
   ctx->last_launches++;
 }
@@ -638,9 +638,9 @@ static void launch_quad(aslsd_ctx* ctx, const BatchPlan& B, const QStreamDev* d_
 template <int FAMILY>
 static void launch_boundary(aslsd_ctx* ctx, const BatchPlan& B, const QStreamDev* d_streams,
                             const BoundaryGroupDev* d_groups, const ItemDev* d_qrows, double* raw_device,
-                            unsigned long long* d_cnt) {
+                            unsigned long long* d_cnt, cudaStream_t st) {
   if (B.bfam_count[FAMILY] == 0) return;
-  lag_boundary_kernel<FAMILY><<<(unsigned)B.bfam_count[FAMILY], LB_NT, 0, ctx->stream>>>(
+  lag_boundary_kernel<FAMILY><<<(unsigned)B.bfam_count[FAMILY], LB_NT, 0, st>>>(
       (const DimDev*)ctx->d_dims, d_streams, d_groups + B.bfam_first[FAMILY], d_qrows, ctx->T_f, raw_device,
       d_cnt + B.bfam_first[FAMILY], ctx->d_weights);
   ctx->last_launches++;
@@ -750,6 +750,7 @@ static int run_batch_impl(aslsd_ctx* ctx, BatchPlan& B, double* raw_device) {
   bool streams_uploaded = false, moments_done = false;
   // (raw: recording the start of the call must not order the stream behind uploads in flight)
   CUDA_TRY(ctx, cudaEventRecord(ctx->ev0, ctx->stream.raw()));
+  CUDA_TRY(ctx, cudaEventRecord(ctx->ev_fork, ctx->stream.raw()));
   if (quad) {
     if ((rc = upload_quadrature_tables(ctx))) return rc;
     if ((rc = ensure_device_buffer(ctx, (void**)&ctx->d_q_partials, &ctx->q_partials_cap,
@@ -821,6 +822,17 @@ static int run_batch_impl(aslsd_ctx* ctx, BatchPlan& B, double* raw_device) {
     return rc;
   const size_t o_g = o_r + ((B.qrows.size() * sizeof(ItemDev) + 15) & ~(size_t)15);
   const size_t q_bytes = o_g + B.bgroups.size() * sizeof(BoundaryGroupDev);
+  // Two lanes.  The moment kernels and the node weights need the event pairs and nothing else; the per-item
+  // kernels and the targets near T_f need the rows and nothing of the moments: when the moments run, those
+  // take the second lane (`side`) - they fill the last, partly empty wave of the moment kernels instead of
+  // following it - and the quadrature rows, which need both, wait for it.  Every row is written in a fixed
+  // order whatever the lanes do: zero, per-item partials (finalize), targets near T_f, quadrature.
+  const bool fork = quad && !reuse_weights;
+  cudaStream_t main_st = ctx->stream;
+  cudaStream_t side = fork ? ctx->aux_stream : main_st;
+  // (ev_fork: what the side lane starts behind - recorded at the top of this call when the moment kernels
+  // are already out, so that it waits for the previous call's readers of the tables and of the raw rows
+  // but not for them; otherwise recorded below, behind the upload of the tables)
   if (!B.device_resident && (n_items || quad)) {
     // all plan tables go through one page-locked block of their own and asynchronous transfers:
     // no wait for the stream here (an event upload may still be in flight on it)
@@ -839,6 +851,10 @@ static int run_batch_impl(aslsd_ctx* ctx, BatchPlan& B, double* raw_device) {
         ctx->tables_cap = need + need / 4;
       }
     }
+    // with the moment kernels already on the compute stream the rest of the tables travels on the side
+    // lane, which reads them
+    cudaStream_t up = moments_done ? side : main_st;
+    if (moments_done) CUDA_TRY(ctx, cudaStreamWaitEvent(side, ctx->ev_fork, 0));
     char* hp = (char*)ctx->h_tables;
     char* hi = hp + (quad ? q_bytes : 0);   // items behind the quadrature tables
     if (quad) {
@@ -850,14 +866,13 @@ static int run_batch_impl(aslsd_ctx* ctx, BatchPlan& B, double* raw_device) {
       std::memcpy(hp + o_g, B.bgroups.data(), B.bgroups.size() * sizeof(BoundaryGroupDev));
       const size_t from = streams_uploaded ? o_r : 0;
       if (q_bytes > from)
-        CUDA_TRY(ctx, cudaMemcpyAsync((char*)ctx->d_qtab + from, hp + from, q_bytes - from, cudaMemcpyHostToDevice,
-                                      ctx->stream));
+        CUDA_TRY(ctx, cudaMemcpyAsync((char*)ctx->d_qtab + from, hp + from, q_bytes - from, cudaMemcpyHostToDevice, up));
     }
     if (n_items) {
       std::memcpy(hi, B.items.data(), n_items * sizeof(ItemDev));
-      CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_items, hi, n_items * sizeof(ItemDev), cudaMemcpyHostToDevice, ctx->stream));
+      CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_items, hi, n_items * sizeof(ItemDev), cudaMemcpyHostToDevice, up));
     }
-    CUDA_TRY(ctx, cudaEventRecord(ctx->ev_tables, ctx->stream));
+    CUDA_TRY(ctx, cudaEventRecord(ctx->ev_tables, up));
     ctx->tables_in_flight = true;
   }
   B.device_resident = true;
@@ -867,43 +882,49 @@ static int run_batch_impl(aslsd_ctx* ctx, BatchPlan& B, double* raw_device) {
   const QStreamDev* d_streams = (const QStreamDev*)((const char*)ctx->d_qtab + o_s);
   const ItemDev* d_qrows = (const ItemDev*)((const char*)ctx->d_qtab + o_r);
   const BoundaryGroupDev* d_groups = (const BoundaryGroupDev*)((const char*)ctx->d_qtab + o_g);
-  CUDA_TRY(ctx, cudaMemsetAsync(raw_device, 0, std::max<size_t>(1, n_rows) * ASLSD_MAX_COMP * sizeof(double),
-                                ctx->stream));
-  if (quad && !reuse_weights && !moments_done)
-    if ((rc = launch_moments(ctx, B, d_streams, ctx->stream, false))) return rc;
-  launch_pair<ITEM_UPS_GAUSS>(ctx, B, d_items);
-  launch_pair<ITEM_UPS_EXP>(ctx, B, d_items);
-  launch_pair<ITEM_UPS_EG>(ctx, B, d_items);
-  launch_pair<ITEM_UPS_GE>(ctx, B, d_items);
-  launch_pair<ITEM_PHI_GAUSS>(ctx, B, d_items);
-  launch_pair<ITEM_PHI_EXP>(ctx, B, d_items);
-  launch_single<ITEM_UPS0_GAUSS>(ctx, B, d_items);
-  launch_single<ITEM_UPS0_EXP>(ctx, B, d_items);
-  launch_single<ITEM_UPS0_EG>(ctx, B, d_items);
-  launch_single<ITEM_UPS0_GE>(ctx, B, d_items);
-  launch_single<ITEM_PSI_GAUSS>(ctx, B, d_items);
-  launch_single<ITEM_PSI_EXP>(ctx, B, d_items);
+  if (fork && !moments_done) {
+    // tables uploaded on the compute stream: the side lane starts behind them, the moment kernels follow
+    CUDA_TRY(ctx, cudaEventRecord(ctx->ev_fork, main_st));
+    if ((rc = launch_moments(ctx, B, d_streams, main_st, false))) return rc;
+  }
+  if (fork) CUDA_TRY(ctx, cudaStreamWaitEvent(side, ctx->ev_fork, 0));
+  CUDA_TRY(ctx, cudaMemsetAsync(raw_device, 0, std::max<size_t>(1, n_rows) * ASLSD_MAX_COMP * sizeof(double), side));
+  launch_pair<ITEM_UPS_GAUSS>(ctx, B, d_items, side);
+  launch_pair<ITEM_UPS_EXP>(ctx, B, d_items, side);
+  launch_pair<ITEM_UPS_EG>(ctx, B, d_items, side);
+  launch_pair<ITEM_UPS_GE>(ctx, B, d_items, side);
+  launch_pair<ITEM_PHI_GAUSS>(ctx, B, d_items, side);
+  launch_pair<ITEM_PHI_EXP>(ctx, B, d_items, side);
+  launch_single<ITEM_UPS0_GAUSS>(ctx, B, d_items, side);
+  launch_single<ITEM_UPS0_EXP>(ctx, B, d_items, side);
+  launch_single<ITEM_UPS0_EG>(ctx, B, d_items, side);
+  launch_single<ITEM_UPS0_GE>(ctx, B, d_items, side);
+  launch_single<ITEM_PSI_GAUSS>(ctx, B, d_items, side);
+  launch_single<ITEM_PSI_EXP>(ctx, B, d_items, side);
   if (n_items) {
     const int n_fin = (int)n_items * (ASLSD_MAX_COMP + 1);
-    finalize_kernel<<<(n_fin + 127) / 128, 128, 0, ctx->stream>>>(d_items, (int)n_items, ctx->d_partials,
-                                                                  ctx->d_counts, raw_device,
-                                                                  ctx->d_counts + B.n_wu);
+    finalize_kernel<<<(n_fin + 127) / 128, 128, 0, side>>>(d_items, (int)n_items, ctx->d_partials, ctx->d_counts,
+                                                          raw_device, ctx->d_counts + B.n_wu);
     ctx->last_launches++;
   }
   if (quad) {
-    launch_quad<ITEM_UPS_GAUSS>(ctx, B, d_streams, d_qrows, raw_device);
-    launch_quad<ITEM_UPS_EXP>(ctx, B, d_streams, d_qrows, raw_device);
-    launch_quad<ITEM_UPS_EG>(ctx, B, d_streams, d_qrows, raw_device);
-    launch_quad<ITEM_UPS_GE>(ctx, B, d_streams, d_qrows, raw_device);
-    launch_quad<ITEM_PHI_GAUSS>(ctx, B, d_streams, d_qrows, raw_device);
-    launch_quad<ITEM_PHI_EXP>(ctx, B, d_streams, d_qrows, raw_device);
     unsigned long long* d_bcnt = ctx->d_counts + B.n_wu + n_items;
-    launch_boundary<ITEM_UPS_GAUSS>(ctx, B, d_streams, d_groups, d_qrows, raw_device, d_bcnt);
-    launch_boundary<ITEM_UPS_EXP>(ctx, B, d_streams, d_groups, d_qrows, raw_device, d_bcnt);
-    launch_boundary<ITEM_UPS_EG>(ctx, B, d_streams, d_groups, d_qrows, raw_device, d_bcnt);
-    launch_boundary<ITEM_UPS_GE>(ctx, B, d_streams, d_groups, d_qrows, raw_device, d_bcnt);
-    launch_boundary<ITEM_PHI_GAUSS>(ctx, B, d_streams, d_groups, d_qrows, raw_device, d_bcnt);
-    launch_boundary<ITEM_PHI_EXP>(ctx, B, d_streams, d_groups, d_qrows, raw_device, d_bcnt);
+    launch_boundary<ITEM_UPS_GAUSS>(ctx, B, d_streams, d_groups, d_qrows, raw_device, d_bcnt, side);
+    launch_boundary<ITEM_UPS_EXP>(ctx, B, d_streams, d_groups, d_qrows, raw_device, d_bcnt, side);
+    launch_boundary<ITEM_UPS_EG>(ctx, B, d_streams, d_groups, d_qrows, raw_device, d_bcnt, side);
+    launch_boundary<ITEM_UPS_GE>(ctx, B, d_streams, d_groups, d_qrows, raw_device, d_bcnt, side);
+    launch_boundary<ITEM_PHI_GAUSS>(ctx, B, d_streams, d_groups, d_qrows, raw_device, d_bcnt, side);
+    launch_boundary<ITEM_PHI_EXP>(ctx, B, d_streams, d_groups, d_qrows, raw_device, d_bcnt, side);
+    if (fork) {
+      CUDA_TRY(ctx, cudaEventRecord(ctx->ev_join, side));
+      CUDA_TRY(ctx, cudaStreamWaitEvent(main_st, ctx->ev_join, 0));
+    }
+    launch_quad<ITEM_UPS_GAUSS>(ctx, B, d_streams, d_qrows, raw_device, main_st);
+    launch_quad<ITEM_UPS_EXP>(ctx, B, d_streams, d_qrows, raw_device, main_st);
+    launch_quad<ITEM_UPS_EG>(ctx, B, d_streams, d_qrows, raw_device, main_st);
+    launch_quad<ITEM_UPS_GE>(ctx, B, d_streams, d_qrows, raw_device, main_st);
+    launch_quad<ITEM_PHI_GAUSS>(ctx, B, d_streams, d_qrows, raw_device, main_st);
+    launch_quad<ITEM_PHI_EXP>(ctx, B, d_streams, d_qrows, raw_device, main_st);
   }
   ctx->last_n_bgroups = (int64_t)B.bgroups.size();
   CUDA_TRY(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
