@@ -69,9 +69,13 @@ struct LqShape {
   // lanes per bin in the moment pass (one round of the CTA covers 64 bins)
   static constexpr int GS = NT >= 1024 ? 16 : (NT >= 512 ? 8 : (NT >= 256 ? 4 : 2));
   static constexpr int TM = NT;     // targets per tile: one per thread
-  static constexpr int SMAX = NT >= 512 ? 2048 : ((NT >= 256 && CTAS < 3) ? 1024 : 512);   // staged source events per tile (two buffers)
-  static constexpr int SMEM_BUDGET = CTAS == 1 ? 220 * 1024 : (CTAS == 2 ? 110 * 1024 : (CTAS == 3 ? 73 * 1024 : (224 * 1024) / CTAS - 2048));
+  static constexpr int SMAX = NT >= 512 ? 2048 : ((NT >= 256 && CTAS < 3) ? 1024 : (CTAS >= 5 ? 256 : 512));   // staged source events per tile (two buffers)
+  // (227 KB per SM, 1 KB of each resident CTA reserved by the system)
+  static constexpr int SMEM_BUDGET = CTAS == 1 ? 220 * 1024 : (CTAS == 2 ? 110 * 1024 : (CTAS == 3 ? 73 * 1024 : ((227 - CTAS) * 1024) / CTAS));
   static constexpr int ONE_BIN_J = NW * (32 / GS);   // bins the groups of lanes can own for a whole work unit
+  // the small shape only takes streams whose bins are all owned (ONE_BIN_J): the moment table is touched
+  // once, after the last tile, and shares its shared memory with the pair buffers
+  static constexpr bool ALIAS_M = CTAS >= 4;
 };
 typedef LqShape<512, 1> LqBig;
 #ifndef LQ_SMALL_CTAS
@@ -119,7 +123,7 @@ __host__ __device__ inline size_t lq_smem_bytes(int J, int ucap, bool weighted) 
   size_t b = 0;
   b += (size_t)ucap * sizeof(double) * (weighted ? 4 : 2);   // + pair weights in both orders
   b += (size_t)(C::SMAX + 2) * sizeof(double) * 2;
-  b += (size_t)J * LQ_ND * sizeof(double);
+  if (!C::ALIAS_M) b += (size_t)J * LQ_ND * sizeof(double);
   b += (size_t)ucap * sizeof(uint32_t);
   b += (size_t)(J + 2) * sizeof(int32_t);
   b += (size_t)C::NW * J * sizeof(uint16_t) * (J <= 64 ? 2 : 1);
@@ -441,8 +445,8 @@ lag_moment_kernel(const DimDev* __restrict__ dims, const QStreamDev* __restrict_
   double* s_wv = s_u + ucap;                        // pair weights, pair order (weighted streams)
   double* s_wu = s_wv + (weighted ? ucap : 0);      // pair weights, sorted by bin
   double* s_src = s_wu + (weighted ? ucap : 0);     // two buffers of C::SMAX + 2
-  double* s_M = s_src + 2 * (C::SMAX + 2);
-  LqTarget* s_tgt = (LqTarget*)(s_M + (size_t)J * LQ_ND);   // 16-byte aligned: every block before it is
+  double* s_M = C::ALIAS_M ? s_val : s_src + 2 * (C::SMAX + 2);
+  LqTarget* s_tgt = (LqTarget*)(s_src + 2 * (C::SMAX + 2) + (C::ALIAS_M ? 0 : (size_t)J * LQ_ND));   // 16-byte aligned: every block before it is
   double* s_tw = (double*)(s_tgt + C::NT);                  // target weights (weighted streams)
   uint32_t* s_key = (uint32_t*)(s_tw + (weighted ? C::NT : 0));
   int32_t* s_bin = (int32_t*)(s_key + ucap);
@@ -450,7 +454,8 @@ lag_moment_kernel(const DimDev* __restrict__ dims, const QStreamDev* __restrict_
   uint16_t* my_hist = s_hist + warp * J;
   uint16_t* s_cur = s_hist + C::NW * J;             // cursors of the warps' own scans (J <= 64)
 
-  for (int x = tid; x < J * LQ_ND; x += C::NT) s_M[x] = 0.;
+  if (!C::ALIAS_M)
+    for (int x = tid; x < J * LQ_ND; x += C::NT) s_M[x] = 0.;
   for (int x = tid; x < ucap; x += C::NT) s_key[x] = 0u;   // no marks (pass 1 leaves none behind)
   if (tid == 0) {
     mbar_init(&s_bar[0], 1);
@@ -731,6 +736,12 @@ lag_moment_kernel(const DimDev* __restrict__ dims, const QStreamDev* __restrict_
       // the barrier after the next pass 1, what is written before it (marks, histograms, target
       // records) was last read before the barrier after pass 2
     }
+  }
+  if (C::ALIAS_M) {
+    // the pair buffers are free now: the moment table takes their place
+    __syncthreads();
+    for (int x = tid; x < J * LQ_ND; x += C::NT) s_M[x] = 0.;
+    __syncthreads();
   }
   if (one_bin) lq_reduce_store<C>(racc, qg, my_bin < J, s_M + (size_t)min(my_bin, J - 1) * LQ_ND);
   __syncthreads();

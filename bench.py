@@ -318,6 +318,16 @@ def plugin_e2e(engine, model, times, T_f, xs, n_rep):
         pc = np.mean(np.array(per_call), axis=0)
         out[label] = {'ms_per_epoch': 1e3 * float(np.mean(total)), 'upload_ms': 1e3 * float(np.mean(upload)),
                       'first_call_ms': 1e3 * float(pc[0]), 'later_calls_ms_mean': 1e3 * float(np.mean(pc[1:]))}
+        # the following epochs of the same fit: the events stay (the reference's fit loop keeps one path),
+        # the evaluation points move
+        steady = []
+        for rep in range(3):
+            engine.synchronize()
+            t0 = time.perf_counter()
+            for k in range(d):
+                g = ests[k].lse_k_grad_estimate(xs[k] * (1. + 1e-3 * (rep + 1)))
+            steady.append(time.perf_counter() - t0)
+        out[label]['next_epochs_ms'] = 1e3 * float(np.mean(steady[1:]))
     engine.use_weight_cache(False)
     return out
 
@@ -670,7 +680,8 @@ def run_b200(args):
                      'gradient back on the host.  Each call needs the moments of all d^2 event-stream pairs: with the '
                      'weight cache off they are recomputed d times per epoch (no sharing between calls - the batched '
                      'call of the headline exists for that), with the cache on (library default) the first call '
-                     'computes them and the others reuse them')
+                     'computes them and the others reuse them.  next_epochs_ms: the following epochs of the same fit - same events, '
+                     'moved evaluation points (omega only: beta and delta are fixed in this model)')
         if simulation:
             line['simulation'] = simulation
         if aslsd:
