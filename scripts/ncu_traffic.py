@@ -39,7 +39,7 @@ out = {'kernel': vals[ix['Kernel Name']][:60], 'dram_bytes_read': num('dram__byt
        'duration_ms_under_ncu': float(vals[ix['gpu__time_duration.sum']].replace(',', '')) *
        {'ns': 1e-6, 'us': 1e-3, 'ms': 1., 's': 1e3}.get(units[ix['gpu__time_duration.sum']], 1.),
        'grid_size': vals[ix['launch__grid_size']], 'capture': label,
-       'how': 'ncu --set full --clock-control none, one launch of the C5 step (bench.py's step, or scripts/profile_one.py 1.1e6: same stream, model, evaluation point and batched call)'}
+       'how': "ncu --set full --clock-control none, one launch of the C5 step (bench.py's step, or scripts/profile_one.py 1.1e6: same stream, model, evaluation point and batched call)"}
 with open(os.path.join(ROOT, 'profiles', 'lag_moment_kernel_dram.json'), 'w') as f:
     json.dump(out, f, indent=1)
 print(json.dumps(out))
