@@ -148,6 +148,15 @@ static double row_scale(const ItemDev& it) {
   }
 }
 
+// Unweighted streams of at most 64 bins: one warp per work unit (default) or the 128-thread CTAs
+static bool lq_warp_shape_enabled() {
+  static const bool on = [] {
+    const char* e = std::getenv("ASLSD_LQ_WARP");
+    return e == nullptr ? (LQW_DEFAULT != 0) : std::atoi(e) != 0;
+  }();
+  return on;
+}
+
 // Turn the pair rows of one (target stream, source stream, target block) into a
 // quadrature stream, if the geometry allows it.
 // Returns its index in B.qstreams, or -1.
@@ -186,7 +195,10 @@ static int build_stream(const aslsd_ctx* ctx, BatchPlan& B, const std::vector<in
   const bool weighted = first.wa_off >= 0 || first.wb_off >= 0;
   // CTA shape: the small one where every pair of its lanes can own a bin for a whole work unit
   const bool small = !weighted && nb <= (double)LqSmall::ONE_BIN_J;
-  const int ucap = small ? lq_pick_ucap<LqSmall>((int)nb, false) : lq_pick_ucap<LqBig>((int)nb, weighted);
+  // ... or, by default, one warp per work unit (lag_moment_warp_kernel; ASLSD_LQ_WARP=0: the small CTA shape)
+  const bool warp_shape = small && lq_warp_shape_enabled();
+  const int ucap = warp_shape ? LQW_PC
+                              : (small ? lq_pick_ucap<LqSmall>((int)nb, false) : lq_pick_ucap<LqBig>((int)nb, weighted));
   if (ucap == 0) return -1;
   QStreamDev S;
   std::memset(&S, 0, sizeof(S));
@@ -195,8 +207,9 @@ static int build_stream(const aslsd_ctx* ctx, BatchPlan& B, const std::vector<in
   S.same = first.same;
   S.J = (int32_t)nb;
   S.ucap = ucap;
-  S.shape = small ? LQ_SHAPE_SMALL : LQ_SHAPE_BIG;
-  {
+  S.shape = warp_shape ? LQ_SHAPE_WARP : (small ? LQ_SHAPE_SMALL : LQ_SHAPE_BIG);
+  if (warp_shape) S.tm = LQW_TM;
+  else {
     // targets per tile: the pairs of a tile should fit one chunk (a second, nearly empty chunk pays the
     // barriers, scans and short loops of a full one) - 90 % of a chunk at the stream's mean density.
     // C5 (14 sources per target, 1 792 pairs per chunk, 128 targets overflowing every second tile):
@@ -224,7 +237,8 @@ static int build_stream(const aslsd_ctx* ctx, BatchPlan& B, const std::vector<in
   B.q_jmax = std::max(B.q_jmax, (int)S.J);
   {
     const int cat = weighted ? 2 : (small ? 0 : 1);
-    const size_t bytes = small ? lq_smem_bytes<LqSmall>(S.J, S.ucap, false) : lq_smem_bytes<LqBig>(S.J, S.ucap, weighted);
+    const size_t bytes = warp_shape ? 0 : (small ? lq_smem_bytes<LqSmall>(S.J, S.ucap, false)
+                                                 : lq_smem_bytes<LqBig>(S.J, S.ucap, weighted));
     B.q_cat_smem[cat] = std::max(B.q_cat_smem[cat], bytes);
   }
   return sx;
@@ -325,7 +339,7 @@ static int build_work_streams(aslsd_ctx* ctx, const int64_t* m_lo, const int64_t
         }
     // order the streams by category (stable) and renumber the groups' stream index
     auto category = [](const QStreamDev& S) {
-      return (S.wa_off >= 0 || S.wb_off >= 0) ? 2 : (S.shape == LQ_SHAPE_SMALL ? 0 : 1);
+      return (S.wa_off >= 0 || S.wb_off >= 0) ? 2 : (S.shape != LQ_SHAPE_BIG ? 0 : 1);
     };
     std::vector<int> perm(B.qstreams.size()), new_ix(B.qstreams.size());
     for (size_t x = 0; x < perm.size(); ++x) perm[x] = (int)x;
@@ -346,12 +360,13 @@ static int build_work_streams(aslsd_ctx* ctx, const int64_t* m_lo, const int64_t
   // ---- quadrature streams: work units of whole tiles, a few waves over the 148 SMs ----------
   // (per category: the streams of one launch share the size of their work units)
   auto category = [](const QStreamDev& S) {
-    return (S.wa_off >= 0 || S.wb_off >= 0) ? 2 : (S.shape == LQ_SHAPE_SMALL ? 0 : 1);
+    return (S.wa_off >= 0 || S.wb_off >= 0) ? 2 : (S.shape != LQ_SHAPE_BIG ? 0 : 1);
   };
   int64_t tot[3] = {0, 0, 0}, tpw_cat[3];
   for (auto& S : B.qstreams) tot[category(S)] += S.m_hi - S.m_lo;
   for (int c = 0; c < 3; ++c) {
-    const int64_t tm = c == 0 ? LqSmall::TM : LqBig::TM;
+    const bool warp_shape = c == 0 && lq_warp_shape_enabled();
+    const int64_t tm = warp_shape ? LQW_TM : (c == 0 ? LqSmall::TM : LqBig::TM);
     // (small CTAs: ~32 work units per resident CTA measured best on the C5 step, 10.42 ms against
     // 11.04 ms with 1.5 - 4 per CTA and 10.51 ms with 83: gpurun_out / profiles r2_g_units)
     int64_t units = c == 0 ? 148 * LqSmall::CTAS * 32 : 148 * 2 * 6;
@@ -359,6 +374,9 @@ static int build_work_streams(aslsd_ctx* ctx, const int64_t* m_lo, const int64_t
     // the write-out of its moment table (one eighth of C5, one time-block shard of eight: 1.372 ms with
     // 9 472 units, 1.422 ms with 18 944, 1.598 ms with 1 184)
     if (c == 0) units = std::min<int64_t>(units, std::max<int64_t>(148 * LqSmall::CTAS, tot[c] / (12 * tm)));
+    // one warp per unit: 2 368 resident warps, ~12 units each, at least ~48 tiles of 32 targets per unit
+    if (warp_shape)
+      units = std::min<int64_t>(148 * LQW_WARPS * 12, std::max<int64_t>(148 * LQW_WARPS, tot[c] / (48 * tm)));
     if (const char* e = std::getenv("ASLSD_LQ_UNITS")) units = std::max<int64_t>(1, std::atoll(e));   // tuning
     int64_t tpw = (tot[c] + units - 1) / units;
     tpw = std::max<int64_t>(tm, std::min<int64_t>(tpw, 64 * LqBig::TM));
@@ -671,16 +689,28 @@ static int launch_moments(aslsd_ctx* ctx, BatchPlan& B, const QStreamDev* d_stre
                                        (int)LqBig::SMEM_BUDGET));
     CUDA_TRY(ctx, cudaFuncSetAttribute(lag_moment_kernel<true, LqBig>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)LqBig::SMEM_BUDGET));
+    // (static shared memory, 16 one-warp CTAs per SM: the largest shared-memory carve-out)
+    CUDA_TRY(ctx, cudaFuncSetAttribute(lag_moment_warp_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                       (int)cudaSharedmemCarveoutMaxShared));
     ctx->q_smem_set = LqBig::SMEM_BUDGET;
   }
   CUDA_TRY(ctx, cudaEventRecord(ctx->ev_q0, st));
   unsigned long long* d_qcnt = ctx->d_qcounts;
   const int n_streams = (int)B.qstreams.size();
+  // category 0: unweighted streams of at most 64 bins, one warp or one 128-thread CTA per work unit
+  const bool warp_shape = !B.qstreams.empty() && B.qstreams[0].shape == LQ_SHAPE_WARP;
+  auto launch_small = [&](int64_t w0, int64_t w1, cudaStream_t on) {
+    if (warp_shape)
+      lag_moment_warp_kernel<<<(unsigned)(w1 - w0), 32, 0, on>>>((const DimDev*)ctx->d_dims, d_streams, n_streams,
+                                                                 ctx->d_q_partials, d_qcnt, w0);
+    else
+      lag_moment_kernel<false, LqSmall><<<(unsigned)(w1 - w0), LqSmall::NT, B.q_cat_smem[0], on>>>(
+          (const DimDev*)ctx->d_dims, d_streams, n_streams, ctx->d_q_partials, d_qcnt, ctx->d_weights, w0);
+    ctx->last_launches++;
+  };
   if (B.q_cat_wu[1] > B.q_cat_wu[0]) {
     if (!staged) {
-      lag_moment_kernel<false, LqSmall><<<(unsigned)(B.q_cat_wu[1] - B.q_cat_wu[0]), LqSmall::NT, B.q_cat_smem[0], st>>>(
-          (const DimDev*)ctx->d_dims, d_streams, n_streams, ctx->d_q_partials, d_qcnt, ctx->d_weights, B.q_cat_wu[0]);
-      ctx->last_launches++;
+      launch_small(B.q_cat_wu[0], B.q_cat_wu[1], st);
     } else {
       // pieces of at least 1/16 of the launch, alternating between the compute stream and a second
       // lane: the last wave of a piece (a work unit runs ~0.3 ms at C5) is filled by the next piece
@@ -696,9 +726,7 @@ static int launch_moments(aslsd_ctx* ctx, BatchPlan& B, const QStreamDev* d_stre
         if (w1 <= w0 || (!last && w1 - w0 < total / 16)) continue;    // too small: joins the next type's piece
         cudaStream_t lane = lanes[piece++ & 1];
         CUDA_TRY(ctx, cudaStreamWaitEvent(lane, ctx->ev_type[(size_t)a], 0));
-        lag_moment_kernel<false, LqSmall><<<(unsigned)(w1 - w0), LqSmall::NT, B.q_cat_smem[0], lane>>>(
-            (const DimDev*)ctx->d_dims, d_streams, n_streams, ctx->d_q_partials, d_qcnt, ctx->d_weights, w0);
-        ctx->last_launches++;
+        launch_small(w0, w1, lane);
         w0 = w1;
       }
       CUDA_TRY(ctx, cudaEventRecord(ctx->ev_aux1, ctx->aux_stream));

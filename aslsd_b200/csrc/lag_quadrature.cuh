@@ -85,7 +85,7 @@ typedef LqShape<512, 1> LqBig;
 #define LQ_SMALL_NT 128
 #endif
 typedef LqShape<LQ_SMALL_NT, LQ_SMALL_CTAS> LqSmall;
-enum { LQ_SHAPE_BIG = 0, LQ_SHAPE_SMALL = 1 };
+enum { LQ_SHAPE_BIG = 0, LQ_SHAPE_SMALL = 1, LQ_SHAPE_WARP = 2 };
 
 struct QStreamDev {
   int32_t tgt_dim, src_dim, same, J;
@@ -758,6 +758,377 @@ lag_moment_kernel(const DimDev* __restrict__ dims, const QStreamDev* __restrict_
     for (int w = 0; w < C::NW; ++w) c += s_cnt[w];
     counts[wu] = c;
   }
+}
+
+// ---- Warp-autonomous shape ---------------------------------------------------------------------------
+// One warp = one work unit, no CTA barrier anywhere: unweighted streams of 32 or 64 bins.  The kernel
+// above sorts the pairs of a chunk by bin through shared memory (two passes, four CTA barriers per
+// tile) so that groups of lanes can run the recurrences of one bin with register accumulators; a third
+// of its time is the fixed latency of its short phases.  Here lane L *owns* bins L and
+// L + 32 for the whole work unit (2 x 11 register accumulators) and the pairs are routed to their
+// owners through per-bin stacks in shared memory:
+//   a. tile = 32 targets, one per lane: source window by a TMA bulk copy issued one tile ahead (two
+//      buffers, one mbarrier each), per-target ranges by unrolled shared-memory searches, exclusive
+//      scan by shuffles, one 16-byte record per target, head marks (one byte per pair slot);
+//   b. step = 32 consecutive pairs (target-major), one per lane: owner of the pair from a ballot over
+//      the marks, lag from the record and the window, bin and position in the bin.  Six ballots over
+//      the bits of the bin give every owner lane the set of lanes that hold pairs of its two bins (five
+//      LOP3 on the warp-uniform ballots); a pair's lane fetches that set and the owner's stack heights
+//      with two shuffles - rank among its peers, slot - and pushes the position onto the bin's stack
+//      (s_stack[slot][bin]: the owners' reads are conflict-free);
+//   c. when a push would overflow a stack (LQW_CAP entries per bin) the owners pop the top I entries of
+//      both their stacks - two independent three-term recurrences per lane, lanes whose stack is
+//      shorter run with weight zero - with I chosen so that the fullest stack keeps LQW_RES free slots.
+//      Popping a fixed number from every stack instead of emptying them keeps 80 % of the lanes busy
+//      (emptying: 55 %; the sort above: 66 %); the summation order inside a bin is fixed, no atomics.
+//      A step that holds more than LQW_CAP pairs of one bin (ties, bursts) is fed to the owners pair
+//      by pair.
+// One partial moment table per work unit, written from the owners' registers.
+#ifndef LQW_CAP
+#define LQW_CAP 16      // stack entries per bin
+#endif
+#ifndef LQW_RES
+#define LQW_RES 6       // free slots of the fullest stack after a partial drain
+#endif
+#define LQW_SW 128      // staged source events per tile (two buffers)
+#define LQW_PC 1024     // pair slots with head marks (pairs of a tile are taken LQW_PC at a time)
+#ifndef LQW_WARPS
+#define LQW_WARPS 16    // resident warps (CTAs of one warp) per SM
+#endif
+#ifndef LQW_DEFAULT
+#define LQW_DEFAULT 1   // 0: the 128-thread CTAs unless ASLSD_LQ_WARP=1
+#endif
+#define LQW_TM 32       // targets per tile
+
+// pop the top n_it entries of the two stacks of this lane (fewer if a stack is shorter)
+__device__ __forceinline__ void lqw_drain(const double* __restrict__ s_stack, int lane, int n_it, int& cnt0, int& cnt1,
+                                          double* acc0, double* acc1, double& tot0, double& tot1) {
+  const double* col0 = s_stack + lane;
+  const double* col1 = s_stack + 32 + lane;
+  for (int i = 0; i < n_it; ++i) {
+    const int e0 = cnt0 - 1 - i, e1 = cnt1 - 1 - i;
+    const double w0 = e0 >= 0 ? 1. : 0., w1 = e1 >= 0 ? 1. : 0.;
+    const double v0 = col0[max(e0, 0) * 64], v1 = col1[max(e1, 0) * 64];
+    const double ua = v0 + v0, ub = v1 + v1;
+    const double two_a = ua + ua, two_b = ub + ub;
+    double pa = 1., ca = ua, pb = 1., cb = ub;
+    acc0[1] = fma(w0, ca, acc0[1]);
+    acc1[1] = fma(w1, cb, acc1[1]);
+#pragma unroll
+    for (int d = 2; d < LQ_ND; ++d) {
+      const double na = fma(two_a, ca, -pa), nb = fma(two_b, cb, -pb);
+      pa = ca; ca = na;
+      pb = cb; cb = nb;
+      acc0[d] = fma(w0, na, acc0[d]);
+      acc1[d] = fma(w1, nb, acc1[d]);
+    }
+  }
+  const int p0 = min(cnt0, n_it), p1 = min(cnt1, n_it);
+  tot0 += (double)p0;
+  tot1 += (double)p1;
+  cnt0 -= p0;
+  cnt1 -= p1;
+}
+
+// one pair straight into the accumulators of its owner (steps that no stack can take)
+__device__ __forceinline__ void lqw_direct(int lane, int b, double v, unsigned live, double* acc0, double* acc1,
+                                           double& tot0, double& tot1) {
+  for (int k = 0; k < 32; ++k) {
+    const int bk = __shfl_sync(0xffffffffu, b, k);
+    const double vk = __shfl_sync(0xffffffffu, v, k);
+    if (!((live >> k) & 1u)) continue;
+    const bool mine = (bk & 31) == lane;
+    const double w0 = (mine && bk < 32) ? 1. : 0., w1 = (mine && bk >= 32) ? 1. : 0.;
+    const double uu = vk + vk, two_u = uu + uu;
+    double tp = 1., tc = uu;
+    tot0 += w0;
+    tot1 += w1;
+    acc0[1] = fma(w0, tc, acc0[1]);
+    acc1[1] = fma(w1, tc, acc1[1]);
+#pragma unroll
+    for (int d = 2; d < LQ_ND; ++d) {
+      const double tn = fma(two_u, tc, -tp);
+      tp = tc;
+      tc = tn;
+      acc0[d] = fma(w0, tn, acc0[d]);
+      acc1[d] = fma(w1, tn, acc1[d]);
+    }
+  }
+}
+
+// ballot of bit K of b (one LOP3 with a predicate result + one VOTE)
+template <int K>
+__device__ __forceinline__ unsigned lqw_bit_ballot(int b) {
+  unsigned v;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      ".reg .b32 t;\n"
+      "and.b32 t, %1, %2;\n"
+      "setp.ne.u32 p, t, 0;\n"
+      "vote.sync.ballot.b32 %0, p, 0xffffffff;\n"
+      "}\n"
+      : "=r"(v)
+      : "r"(b), "n"(1 << K));
+  return v;
+}
+
+// Route the pairs of one step (bin b, position v; bit k of live: lane k holds a pair) to the stacks.
+// cpk: heights of this lane's two stacks, bin lane in the low half-word, bin lane + 32 in the high one.
+template <bool FULL>
+__device__ __forceinline__ void lqw_route(double* __restrict__ s_stack, int lane, unsigned lt_mask, int b, double v,
+                                          unsigned live, const unsigned* xm, unsigned& cpk,
+                                          double* acc0, double* acc1, double& tot0, double& tot1) {
+  const unsigned B0 = lqw_bit_ballot<0>(b), B1 = lqw_bit_ballot<1>(b), B2 = lqw_bit_ballot<2>(b),
+                 B3 = lqw_bit_ballot<3>(b), B4 = lqw_bit_ballot<4>(b), B5 = lqw_bit_ballot<5>(b);
+  // lanes whose pair falls into bin `lane` or `lane + 32` (xm[i] = all ones where bit i of lane is 0)
+  unsigned common = (B0 ^ xm[0]) & (B1 ^ xm[1]) & (B2 ^ xm[2]) & (B3 ^ xm[3]) & (B4 ^ xm[4]);
+  if (!FULL) common &= live;
+  const unsigned npk = (unsigned)__popc(common & ~B5) | ((unsigned)__popc(common & B5) << 16);
+  // a half-word of cpk + npk above LQW_CAP: bit 15 of that half-word of the biased sum
+  const unsigned bias = (0x8000u - LQW_CAP - 1u) * 0x10001u;
+  if (__any_sync(0xffffffffu, ((cpk + npk + bias) & 0x80008000u) != 0u)) {
+    int cnt0 = (int)(cpk & 0xffffu), cnt1 = (int)(cpk >> 16);
+    const int n0 = (int)(npk & 0xffffu), n1 = (int)(npk >> 16);
+    int need = max(cnt0 + n0, cnt1 + n1) - LQW_CAP;
+    int top = max(cnt0, cnt1);
+    need = __reduce_max_sync(0xffffffffu, need);
+    top = __reduce_max_sync(0xffffffffu, top);
+    const int n_it = min(top, max(top - (LQW_CAP - LQW_RES), need));
+    lqw_drain(s_stack, lane, n_it, cnt0, cnt1, acc0, acc1, tot0, tot1);
+    cpk = (unsigned)cnt0 | ((unsigned)cnt1 << 16);
+    if (__any_sync(0xffffffffu, max(cnt0 + n0, cnt1 + n1) > LQW_CAP)) {
+      // more pairs of one bin in this step than a stack holds
+      lqw_direct(lane, b, v, live, acc0, acc1, tot0, tot1);
+      return;
+    }
+  }
+  // (shuffles take the source lane modulo 32: the owner of bin b is lane b & 31)
+  const unsigned pc = __shfl_sync(0xffffffffu, common, b);
+  const unsigned ck = __shfl_sync(0xffffffffu, cpk, b);
+  const int hi = b >> 5;
+  const unsigned peers = pc & (B5 ^ (unsigned)(hi - 1)) & lt_mask;
+  const int slot = (int)((ck >> (hi << 4)) & 0xffffu) + __popc(peers);
+  if (FULL || ((live >> lane) & 1u)) s_stack[slot * 64 + b] = v;
+  cpk += npk;
+}
+
+// The steps of LQW_PC pair slots: pairs c0 .. c0 + n_c of the tile.
+template <bool STAGED>
+__device__ __forceinline__ void lqw_steps(double* __restrict__ s_stack, uint8_t* __restrict__ s_mark,
+                                          const LqTarget* __restrict__ s_tgt, const double* __restrict__ win,
+                                          const double* __restrict__ src_glb, int lane, unsigned lt_mask,
+                                          unsigned le_mask, int c0, int n_c, double inv_h, const unsigned* xm,
+                                          unsigned& cpk, double* acc0, double* acc1, double& tot0, double& tot1) {
+  const int n_full = n_c >> 5;
+  int q = lane;
+  for (int st = 0; st < n_full; ++st, q += 32) {
+    const uint32_t mk = s_mark[q];
+    const unsigned heads = __ballot_sync(0xffffffffu, mk != 0u);
+    const int hl = 31 - __clz(heads & le_mask);
+    const int m = (int)__shfl_sync(0xffffffffu, mk, hl) - 1;
+    s_mark[q] = 0;
+    const double2 rec = *(const double2*)(s_tgt + m);
+    const int idx = __double2loint(rec.y) + c0 + q;
+    const double s = rec.x - (STAGED ? win[idx] : __ldg(src_glb + idx));
+    int b;
+    double v;
+    lq_bin(s, inv_h, b, v);
+    lqw_route<true>(s_stack, lane, lt_mask, b, v, 0xffffffffu, xm, cpk, acc0, acc1, tot0, tot1);
+  }
+  const int left = n_c - n_full * 32;
+  if (left > 0) {
+    const unsigned live = (1u << left) - 1u;
+    const bool is_live = lane < left;
+    const uint32_t mk = is_live ? (uint32_t)s_mark[q] : 0u;
+    const unsigned heads = __ballot_sync(0xffffffffu, mk != 0u);
+    const int hl = 31 - __clz(heads & le_mask);
+    const int m = (int)__shfl_sync(0xffffffffu, mk, hl) - 1;
+    if (is_live) s_mark[q] = 0;
+    const double2 rec = *(const double2*)(s_tgt + (is_live ? m : 0));
+    const int idx = is_live ? __double2loint(rec.y) + c0 + q : 0;
+    const double s = rec.x - (STAGED ? win[idx] : __ldg(src_glb + idx));
+    int b;
+    double v;
+    lq_bin(s, inv_h, b, v);
+    if (!is_live) b = 0;
+    lqw_route<false>(s_stack, lane, lt_mask, b, v, live, xm, cpk, acc0, acc1, tot0, tot1);
+  }
+}
+
+__global__ void __launch_bounds__(32, LQW_WARPS)
+lag_moment_warp_kernel(const DimDev* __restrict__ dims, const QStreamDev* __restrict__ streams, int n_streams,
+                       double* __restrict__ partials, unsigned long long* __restrict__ counts, int64_t wu_base) {
+  __shared__ __align__(16) double s_stack[LQW_CAP * 64];
+  __shared__ __align__(16) double s_src[2 * (LQW_SW + 2)];
+  __shared__ __align__(16) LqTarget s_tgt[LQW_TM];
+  __shared__ __align__(8) uint64_t s_bar[2];
+  __shared__ __align__(16) uint8_t s_mark[LQW_PC];
+
+  const int lane = threadIdx.x;
+  const unsigned lt_mask = (1u << lane) - 1u;
+  const unsigned le_mask = lt_mask | (1u << lane);
+  const int64_t wu = (int64_t)blockIdx.x + wu_base;
+  const QStreamDev S = streams[find_stream(streams, n_streams, wu)];
+  const int chunk = (int)(wu - S.wu_first);
+  const DimDev Dt = dims[S.tgt_dim], Ds = dims[S.src_dim];
+  if (*Dt.bad) return;   // unsorted upload (aslsd_set_events): the verdict reaches the host later
+  const int64_t m_begin = S.m_lo + (int64_t)chunk * S.tpw;
+  const int64_t m_end = min(S.m_hi, m_begin + S.tpw);
+  const bool same = S.same != 0;
+  const double inv_h = S.inv_h;
+  const int64_t n_src_padded = ((Ds.n + 1) & ~(int64_t)1) + 2;   // set_events pads every type (ctx.cu)
+
+  unsigned xm[5];
+#pragma unroll
+  for (int i = 0; i < 5; ++i) xm[i] = ((lane >> i) & 1) ? 0u : 0xffffffffu;
+
+  // stacks to zero (entries above a stack's height are read with weight zero: they must be finite),
+  // no marks (every step clears the ones it read)
+  for (int x = lane; x < LQW_CAP * 64; x += 32) s_stack[x] = 0.;
+  for (int x = lane; x < LQW_PC / 4; x += 32) ((uint32_t*)s_mark)[x] = 0u;
+  int64_t a0 = 0;
+  if (lane == 0) {
+    mbar_init(&s_bar[0], 1);
+    mbar_init(&s_bar[1], 1);
+    fence_proxy_async();
+    // window of the first tile: starts at the first source its first target can reach
+    if (m_begin < m_end) {
+      a0 = dim_lower_bound(Ds, Dt.t[m_begin] - S.s_max) & ~(int64_t)1;
+      const int64_t n_stage = min((int64_t)LQW_SW, n_src_padded - a0);
+      mbar_expect_tx(&s_bar[0], (uint32_t)(n_stage * sizeof(double)));
+      tma_load_1d(s_src, Ds.t + a0, (uint32_t)(n_stage * sizeof(double)), &s_bar[0]);
+    }
+  }
+  a0 = __shfl_sync(0xffffffffu, a0, 0);
+  __syncwarp();
+  uint32_t parity = 0u;   // bit b: phase of window buffer b
+  unsigned long long n_pairs = 0;
+  double t_mine = (m_begin + lane < m_end) ? Dt.t[m_begin + lane] : 0.;
+
+  double acc0[LQ_ND], acc1[LQ_ND];   // [0] unused: the counts are kept as tot0 / tot1 (exact)
+#pragma unroll
+  for (int d = 0; d < LQ_ND; ++d) acc0[d] = acc1[d] = 0.;
+  double tot0 = 0., tot1 = 0.;
+  unsigned cpk = 0u;   // heights of the stacks of bins lane (low half-word) and lane + 32 (high half-word)
+
+  int tile = 0;
+  for (int64_t m0 = m_begin; m0 < m_end; m0 += LQW_TM, ++tile) {
+    const int nt = (int)min((int64_t)LQW_TM, m_end - m0);
+    const int buf = tile & 1;
+    const double* win = s_src + buf * (LQW_SW + 2);
+    // ---- a. per-target source ranges ---------------------------------------------------------
+    const double t = t_mine;
+    const double t_last = __shfl_sync(0xffffffffu, t, nt - 1);
+    if (m0 + LQW_TM + lane < m_end) t_mine = Dt.t[m0 + LQW_TM + lane];   // next tile's target, in flight
+    mbar_wait(&s_bar[buf], (parity >> buf) & 1u);
+    parity ^= 1u << buf;
+    const int n_win = (int)min((int64_t)LQW_SW, n_src_padded - a0);
+    // the window serves the tile if it reaches the end of the stream or the last target (same type:
+    // by index, ties in time included; other types: by time, the searches are lower bounds)
+    const bool staged = (a0 + n_win >= Ds.n) ||
+                        (same ? (a0 + n_win >= m0 + nt - 1) : (win[n_win - 1] >= t_last));
+    const int n_valid = (int)min((int64_t)n_win, Ds.n - a0);   // entries that are events, not padding
+    int n_search = n_valid;
+    if (staged) {
+      if (n_valid > 63 && win[62] >= t_last) n_search = 63;
+      else if (n_valid > 127 && win[126] >= t_last) n_search = 127;
+    }
+    const int p2 = n_search > 0 ? (1 << (31 - __clz(n_search))) : 0;
+    int64_t lo_abs = 0;
+    int32_t cnt = 0;
+    if (lane < nt) {
+      int64_t hi;
+      if (staged) {
+        const double x_lo = t - S.s_max;
+        int r_hi, r_lo;
+        if (n_search == 63) {
+          if (same) { r_hi = 0; r_lo = smem_lower_bound_full<6>(win, x_lo); }
+          else smem_lower_bound_full2<6>(win, t, x_lo, r_hi, r_lo);
+        } else if (n_search == 127) {
+          if (same) { r_hi = 0; r_lo = smem_lower_bound_full<7>(win, x_lo); }
+          else smem_lower_bound_full2<7>(win, t, x_lo, r_hi, r_lo);
+        } else {
+          r_hi = same ? 0 : smem_lower_bound(win, n_search, p2, t);
+          r_lo = smem_lower_bound(win, n_search, p2, x_lo);
+        }
+        hi = same ? (m0 + lane) : a0 + r_hi;
+        lo_abs = min(a0 + (int64_t)r_lo, hi);
+      } else {
+        hi = same ? (m0 + lane) : dim_lower_bound(Ds, t);
+        lo_abs = min(dim_lower_bound(Ds, t - S.s_max), hi);
+      }
+      cnt = (int32_t)(hi - lo_abs);
+    }
+    int32_t incl = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int32_t v = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += v;
+    }
+    const int32_t pre = incl - cnt;
+    const int32_t total = __shfl_sync(0xffffffffu, incl, 31);
+    // next tile's window into the other buffer: it starts at the window start of this tile's last
+    // target (the readers of that buffer, the previous tile's searches and steps, are done)
+    const int64_t a1 = __shfl_sync(0xffffffffu, lo_abs, nt - 1) & ~(int64_t)1;
+    fence_proxy_async();
+    __syncwarp();
+    if (lane == 0 && m0 + LQW_TM < m_end) {
+      const int64_t n_stage = min((int64_t)LQW_SW, n_src_padded - a1);
+      mbar_expect_tx(&s_bar[buf ^ 1], (uint32_t)(n_stage * sizeof(double)));
+      tma_load_1d(s_src + (buf ^ 1) * (LQW_SW + 2), Ds.t + a1, (uint32_t)(n_stage * sizeof(double)), &s_bar[buf ^ 1]);
+    }
+    n_pairs += (unsigned long long)cnt;
+    {
+      LqTarget rec;
+      rec.t = t;
+      rec.base = (int32_t)(lo_abs - a0) - pre;
+      rec.pad = 0;
+      s_tgt[lane] = rec;
+    }
+    const double* src_glb = Ds.t + a0;   // fallback tiles
+
+    // ---- b. steps of 32 pairs, LQW_PC pair slots at a time --------------------------------------
+    for (int32_t c0 = 0; c0 < total; c0 += LQW_PC) {
+      const int32_t n_c = min((int32_t)LQW_PC, total - c0);
+      {
+        const int32_t qa = max(pre - c0, 0), qb = min(pre + cnt - c0, n_c);
+        if (qa < qb) {
+          const uint8_t mark = (uint8_t)(lane + 1);
+          s_mark[qa] = mark;
+          for (int32_t q = (qa & ~31) + 32; q < qb; q += 32) s_mark[q] = mark;
+        }
+      }
+      __syncwarp();
+      if (staged)
+        lqw_steps<true>(s_stack, s_mark, s_tgt, win, src_glb, lane, lt_mask, le_mask, c0, n_c, inv_h, xm, cpk, acc0, acc1,
+                        tot0, tot1);
+      else
+        lqw_steps<false>(s_stack, s_mark, s_tgt, win, src_glb, lane, lt_mask, le_mask, c0, n_c, inv_h, xm, cpk, acc0,
+                         acc1, tot0, tot1);
+      __syncwarp();
+    }
+    a0 = a1;
+  }
+  // what is left on the stacks
+  {
+    int cnt0 = (int)(cpk & 0xffffu), cnt1 = (int)(cpk >> 16);
+    const int top = __reduce_max_sync(0xffffffffu, max(cnt0, cnt1));
+    lqw_drain(s_stack, lane, top, cnt0, cnt1, acc0, acc1, tot0, tot1);
+  }
+  // ---- one partial moment table per work unit ---------------------------------------------------
+  double* out = partials + S.part_first + (int64_t)chunk * S.J * LQ_ND;
+  out[lane * LQ_ND] = tot0;
+#pragma unroll
+  for (int d = 1; d < LQ_ND; ++d) out[lane * LQ_ND + d] = acc0[d];
+  if (S.J > 32) {
+    out[(lane + 32) * LQ_ND] = tot1;
+#pragma unroll
+    for (int d = 1; d < LQ_ND; ++d) out[(lane + 32) * LQ_ND + d] = acc1[d];
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) n_pairs += __shfl_xor_sync(0xffffffffu, n_pairs, o);
+  if (lane == 0) counts[wu] = n_pairs;
 }
 
 // Moments of a stream (partials summed in work-unit order) -> node weights.
