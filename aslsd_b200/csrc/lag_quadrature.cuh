@@ -764,31 +764,35 @@ lag_moment_kernel(const DimDev* __restrict__ dims, const QStreamDev* __restrict_
 // One warp = one work unit, no CTA barrier anywhere: unweighted streams of 32 or 64 bins.  The kernel
 // above sorts the pairs of a chunk by bin through shared memory (two passes, four CTA barriers per
 // tile) so that groups of lanes can run the recurrences of one bin with register accumulators; a third
-// of its time is the fixed latency of its short phases.  Here lane L *owns* bins L and
-// L + 32 for the whole work unit (2 x 11 register accumulators) and the pairs are routed to their
-// owners through per-bin stacks in shared memory:
+// of its time is the fixed latency of its short phases.  Here lane L *owns* bin L of the
+// current pass for the whole work unit (11 register accumulators) and the pairs are routed to their
+// owners through per-bin stacks in shared memory.  A stream of 64 bins is taken in two passes over
+// the work unit's targets - lags in the first 32 bins, then in the last 32 - so that a pass
+// enumerates only its own pairs (the search bounds of the two overlap by a thousandth of a bin and a
+// pair is kept by the pass that its computed bin names: an exact partition).
 //   a. tile = 32 targets, one per lane: source window by a TMA bulk copy issued one tile ahead (two
 //      buffers, one mbarrier each), per-target ranges by unrolled shared-memory searches, exclusive
 //      scan by shuffles, one 16-byte record per target, head marks (one byte per pair slot);
-//   b. step = 32 consecutive pairs (target-major), one per lane: owner of the pair from a ballot over
-//      the marks, lag from the record and the window, bin and position in the bin.  Six ballots over
-//      the bits of the bin give every owner lane the set of lanes that hold pairs of its two bins (five
-//      LOP3 on the warp-uniform ballots); a pair's lane fetches that set and the owner's stack heights
-//      with two shuffles - rank among its peers, slot - and pushes the position onto the bin's stack
-//      (s_stack[slot][bin]: the owners' reads are conflict-free);
-//   c. when a push would overflow a stack (LQW_CAP entries per bin) the owners pop the top I entries of
-//      both their stacks - two independent three-term recurrences per lane, lanes whose stack is
-//      shorter run with weight zero - with I chosen so that the fullest stack keeps LQW_RES free slots.
-//      Popping a fixed number from every stack instead of emptying them keeps 80 % of the lanes busy
-//      (emptying: 55 %; the sort above: 66 %); the summation order inside a bin is fixed, no atomics.
-//      A step that holds more than LQW_CAP pairs of one bin (ties, bursts) is fed to the owners pair
-//      by pair.
+//   b. step = 32 consecutive pairs (target-major), one per lane, two steps interleaved: owner of the
+//      pair from a ballot over the marks, lag from the record and the window, bin and position in
+//      the bin.  Five ballots over the bits of the bin (and one over "this pass") give every owner
+//      lane the set of lanes that hold pairs of its bin (five LOP3 on the warp-uniform ballots); a
+//      pair's lane fetches that set and the owner's stack height with two shuffles - rank among its
+//      peers, slot - and pushes the position onto the bin's stack (s_stack[slot][bin]: the owners'
+//      reads are conflict-free);
+//   c. when a push would overflow a stack (LQW_CAP entries per bin) every owner pops the top I
+//      entries of its stack - two independent three-term recurrences per lane, lanes whose stack is
+//      shorter run with weight zero - with I chosen so that the fullest stack keeps LQW_RES free
+//      slots.  Popping a fixed number from every stack instead of emptying them keeps ~88 % of the
+//      lanes busy (emptying: 55 %; the sort above: 66 %); the summation order inside a bin is fixed,
+//      no atomics.  A step that holds more pairs of one bin than a stack takes (ties, bursts) is fed
+//      to the owners pair by pair.
 // One partial moment table per work unit, written from the owners' registers.
 #ifndef LQW_CAP
-#define LQW_CAP 16      // stack entries per bin
+#define LQW_CAP 32      // stack entries per bin
 #endif
 #ifndef LQW_RES
-#define LQW_RES 6       // free slots of the fullest stack after a partial drain
+#define LQW_RES 12      // free slots of the fullest stack after a partial drain
 #endif
 #define LQW_SW 128      // staged source events per tile (two buffers)
 #define LQW_PC 1024     // pair slots with head marks (pairs of a tile are taken LQW_PC at a time)
@@ -800,58 +804,70 @@ lag_moment_kernel(const DimDev* __restrict__ dims, const QStreamDev* __restrict_
 #endif
 #define LQW_TM 32       // targets per tile
 
-// pop the top n_it entries of the two stacks of this lane (fewer if a stack is shorter)
-__device__ __forceinline__ void lqw_drain(const double* __restrict__ s_stack, int lane, int n_it, int& cnt0, int& cnt1,
-                                          double* acc0, double* acc1, double& tot0, double& tot1) {
-  const double* col0 = s_stack + lane;
-  const double* col1 = s_stack + 32 + lane;
-  for (int i = 0; i < n_it; ++i) {
-    const int e0 = cnt0 - 1 - i, e1 = cnt1 - 1 - i;
-    const double w0 = e0 >= 0 ? 1. : 0., w1 = e1 >= 0 ? 1. : 0.;
-    const double v0 = col0[max(e0, 0) * 64], v1 = col1[max(e1, 0) * 64];
-    const double ua = v0 + v0, ub = v1 + v1;
+// shared-memory accesses of the step loop by 32-bit address (the addresses stay in registers; the
+// compiler otherwise re-derives every array base from the CTA's shared window in each iteration)
+__device__ __forceinline__ uint32_t lqw_lds_u8(uint32_t a) {
+  uint32_t v;
+  asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
+  return v;
+}
+__device__ __forceinline__ void lqw_sts_u8(uint32_t a, uint32_t v) {
+  asm volatile("st.shared.u8 [%0], %1;" ::"r"(a), "r"(v) : "memory");
+}
+__device__ __forceinline__ double lqw_lds_f64(uint32_t a) {
+  double v;
+  asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(a) : "memory");
+  return v;
+}
+__device__ __forceinline__ void lqw_sts_f64(uint32_t a, double v) {
+  asm volatile("st.shared.f64 [%0], %1;" ::"r"(a), "d"(v) : "memory");
+}
+__device__ __forceinline__ void lqw_lds_v2(uint32_t a, double& x, double& y) {
+  asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(x), "=d"(y) : "r"(a) : "memory");
+}
+
+// pop the top n_pop entries of this lane's stack (fewer if it is shorter): two recurrences at a time
+__device__ __forceinline__ void lqw_drain(uint32_t col_a, int n_pop, int& cnt, double* acc, double& tot) {
+  const int pop = min(cnt, n_pop);
+  for (int i = 0; i < n_pop; i += 2) {
+    const int ea = cnt - 1 - i, eb = cnt - 2 - i;
+    const double wa = i < pop ? 1. : 0., wb = i + 1 < pop ? 1. : 0.;
+    const double va = lqw_lds_f64(col_a + (uint32_t)max(ea, 0) * 256u), vb = lqw_lds_f64(col_a + (uint32_t)max(eb, 0) * 256u);
+    const double ua = va + va, ub = vb + vb;
     const double two_a = ua + ua, two_b = ub + ub;
     double pa = 1., ca = ua, pb = 1., cb = ub;
-    acc0[1] = fma(w0, ca, acc0[1]);
-    acc1[1] = fma(w1, cb, acc1[1]);
+    acc[1] = fma(wa, ca, acc[1]);
+    acc[1] = fma(wb, cb, acc[1]);
 #pragma unroll
     for (int d = 2; d < LQ_ND; ++d) {
       const double na = fma(two_a, ca, -pa), nb = fma(two_b, cb, -pb);
       pa = ca; ca = na;
       pb = cb; cb = nb;
-      acc0[d] = fma(w0, na, acc0[d]);
-      acc1[d] = fma(w1, nb, acc1[d]);
+      acc[d] = fma(wa, na, acc[d]);
+      acc[d] = fma(wb, nb, acc[d]);
     }
   }
-  const int p0 = min(cnt0, n_it), p1 = min(cnt1, n_it);
-  tot0 += (double)p0;
-  tot1 += (double)p1;
-  cnt0 -= p0;
-  cnt1 -= p1;
+  tot += (double)pop;
+  cnt -= pop;
 }
 
-// one pair straight into the accumulators of its owner (steps that no stack can take)
-__device__ __forceinline__ void lqw_direct(int lane, int b, double v, unsigned live, double* acc0, double* acc1,
-                                           double& tot0, double& tot1) {
+// the pairs of a step straight into the accumulators of their owners (steps that no stack can take)
+__device__ __forceinline__ void lqw_direct(int lane, int b, double v, unsigned live, double* acc, double& tot) {
   for (int k = 0; k < 32; ++k) {
     const int bk = __shfl_sync(0xffffffffu, b, k);
     const double vk = __shfl_sync(0xffffffffu, v, k);
     if (!((live >> k) & 1u)) continue;
-    const bool mine = (bk & 31) == lane;
-    const double w0 = (mine && bk < 32) ? 1. : 0., w1 = (mine && bk >= 32) ? 1. : 0.;
+    const double w = (bk & 31) == lane ? 1. : 0.;
     const double uu = vk + vk, two_u = uu + uu;
     double tp = 1., tc = uu;
-    tot0 += w0;
-    tot1 += w1;
-    acc0[1] = fma(w0, tc, acc0[1]);
-    acc1[1] = fma(w1, tc, acc1[1]);
+    tot += w;
+    acc[1] = fma(w, tc, acc[1]);
 #pragma unroll
     for (int d = 2; d < LQ_ND; ++d) {
       const double tn = fma(two_u, tc, -tp);
       tp = tc;
       tc = tn;
-      acc0[d] = fma(w0, tn, acc0[d]);
-      acc1[d] = fma(w1, tn, acc1[d]);
+      acc[d] = fma(w, tn, acc[d]);
     }
   }
 }
@@ -873,101 +889,130 @@ __device__ __forceinline__ unsigned lqw_bit_ballot(int b) {
   return v;
 }
 
-// Route the pairs of one step (bin b, position v; bit k of live: lane k holds a pair) to the stacks.
-// cpk: heights of this lane's two stacks, bin lane in the low half-word, bin lane + 32 in the high one.
-template <bool FULL>
-__device__ __forceinline__ void lqw_route(double* __restrict__ s_stack, int lane, unsigned lt_mask, int b, double v,
-                                          unsigned live, const unsigned* xm, unsigned& cpk,
-                                          double* acc0, double* acc1, double& tot0, double& tot1) {
+// what the step loop keeps in registers
+struct LqwLoop {
+  uint32_t mark_a;    // s_mark
+  uint32_t tgt_a;     // s_tgt - 16 (marks hold 1 + the target)
+  uint32_t win_a;     // the tile's source window
+  uint32_t push_a;    // s_stack - 8 * 32 * pass: a live pair's bin b lies in [32 pass, 32 pass + 32)
+  uint32_t col_a;     // s_stack + 8 * lane: this lane's stack
+  const double* src_glb;   // fallback tiles: the sources from the window start on
+  double inv_h;
+  unsigned lt_mask, le_mask;
+  unsigned xm[5];     // all ones where bit i of the lane index is 0
+  int pass, lane;
+};
+
+// One pair per lane: lag -> (bin, position), whether this pass owns the bin, and for the owner lanes
+// the set of lanes whose pair falls into their bin.  q: pair slot of this lane in the chunk; cq: its
+// pair index in the tile.
+template <bool FULL, bool STAGED>
+__device__ __forceinline__ void lqw_form(const LqwLoop& L, int q, int cq, bool in_range, int& b, double& v,
+                                         bool& live, unsigned& lv, unsigned& common) {
+  uint32_t mk = 0u;
+  if (FULL || in_range) mk = lqw_lds_u8(L.mark_a + (uint32_t)q);
+  const unsigned heads = __ballot_sync(0xffffffffu, mk != 0u);
+  const int hl = 31 - __clz(heads & L.le_mask);
+  const int m1 = (int)__shfl_sync(0xffffffffu, mk, hl);   // 1 + owner (lane 0 of a step always carries a mark)
+  if (FULL || in_range) lqw_sts_u8(L.mark_a + (uint32_t)q, 0u);
+  double t_m, rest;
+  lqw_lds_v2(L.tgt_a + ((uint32_t)m1 << 4), t_m, rest);
+  int idx = __double2loint(rest) + cq;
+  if (!FULL && !in_range) idx = 0;
+  const double s = t_m - (STAGED ? lqw_lds_f64(L.win_a + ((uint32_t)idx << 3)) : __ldg(L.src_glb + idx));
+  lq_bin(s, L.inv_h, b, v);
+  live = ((b >> 5) == L.pass) && (FULL || in_range);
+  lv = __ballot_sync(0xffffffffu, live);
   const unsigned B0 = lqw_bit_ballot<0>(b), B1 = lqw_bit_ballot<1>(b), B2 = lqw_bit_ballot<2>(b),
-                 B3 = lqw_bit_ballot<3>(b), B4 = lqw_bit_ballot<4>(b), B5 = lqw_bit_ballot<5>(b);
-  // lanes whose pair falls into bin `lane` or `lane + 32` (xm[i] = all ones where bit i of lane is 0)
-  unsigned common = (B0 ^ xm[0]) & (B1 ^ xm[1]) & (B2 ^ xm[2]) & (B3 ^ xm[3]) & (B4 ^ xm[4]);
-  if (!FULL) common &= live;
-  const unsigned npk = (unsigned)__popc(common & ~B5) | ((unsigned)__popc(common & B5) << 16);
-  // a half-word of cpk + npk above LQW_CAP: bit 15 of that half-word of the biased sum
-  const unsigned bias = (0x8000u - LQW_CAP - 1u) * 0x10001u;
-  if (__any_sync(0xffffffffu, ((cpk + npk + bias) & 0x80008000u) != 0u)) {
-    int cnt0 = (int)(cpk & 0xffffu), cnt1 = (int)(cpk >> 16);
-    const int n0 = (int)(npk & 0xffffu), n1 = (int)(npk >> 16);
-    int need = max(cnt0 + n0, cnt1 + n1) - LQW_CAP;
-    int top = max(cnt0, cnt1);
-    need = __reduce_max_sync(0xffffffffu, need);
-    top = __reduce_max_sync(0xffffffffu, top);
-    const int n_it = min(top, max(top - (LQW_CAP - LQW_RES), need));
-    lqw_drain(s_stack, lane, n_it, cnt0, cnt1, acc0, acc1, tot0, tot1);
-    cpk = (unsigned)cnt0 | ((unsigned)cnt1 << 16);
-    if (__any_sync(0xffffffffu, max(cnt0 + n0, cnt1 + n1) > LQW_CAP)) {
-      // more pairs of one bin in this step than a stack holds
-      lqw_direct(lane, b, v, live, acc0, acc1, tot0, tot1);
-      return;
-    }
-  }
-  // (shuffles take the source lane modulo 32: the owner of bin b is lane b & 31)
-  const unsigned pc = __shfl_sync(0xffffffffu, common, b);
-  const unsigned ck = __shfl_sync(0xffffffffu, cpk, b);
-  const int hi = b >> 5;
-  const unsigned peers = pc & (B5 ^ (unsigned)(hi - 1)) & lt_mask;
-  const int slot = (int)((ck >> (hi << 4)) & 0xffffu) + __popc(peers);
-  if (FULL || ((live >> lane) & 1u)) s_stack[slot * 64 + b] = v;
-  cpk += npk;
+                 B3 = lqw_bit_ballot<3>(b), B4 = lqw_bit_ballot<4>(b);
+  common = lv & (B0 ^ L.xm[0]) & (B1 ^ L.xm[1]) & (B2 ^ L.xm[2]) & (B3 ^ L.xm[3]) & (B4 ^ L.xm[4]);
 }
 
-// The steps of LQW_PC pair slots: pairs c0 .. c0 + n_c of the tile.
+// push a formed pair: rank among the lanes of the same bin, slot above the owner's height `cnt_at`
+__device__ __forceinline__ void lqw_push(const LqwLoop& L, int b, double v, bool live, unsigned common, int cnt_at) {
+  // (shuffles take the source lane modulo 32: the owner of bin b is lane b & 31)
+  const unsigned pc = __shfl_sync(0xffffffffu, common, b);
+  const int ck = __shfl_sync(0xffffffffu, cnt_at, b);
+  const int slot = ck + __popc(pc & L.lt_mask);
+  if (live) lqw_sts_f64(L.push_a + ((uint32_t)(slot * 32 + b) << 3), v);
+}
+
+// make room for n more entries on every stack (n: this lane's bin), or report that no drain can
+template <class ACC>
+__device__ __forceinline__ bool lqw_make_room(const LqwLoop& L, int n, int& cnt, ACC* acc, double& tot) {
+  int need = cnt + n - LQW_CAP;
+  need = __reduce_max_sync(0xffffffffu, need);
+  const int top = __reduce_max_sync(0xffffffffu, cnt);
+  const int n_pop = min(top, max(top - (LQW_CAP - LQW_RES), need));
+  __syncwarp();   // the pushes of the other lanes onto this lane's stack
+  lqw_drain(L.col_a, n_pop, cnt, acc, tot);
+  return !__any_sync(0xffffffffu, cnt + n > LQW_CAP);
+}
+
+// The steps over pair slots 0 .. n_c of a chunk (pairs c0 .. c0 + n_c of the tile).
 template <bool STAGED>
-__device__ __forceinline__ void lqw_steps(double* __restrict__ s_stack, uint8_t* __restrict__ s_mark,
-                                          const LqTarget* __restrict__ s_tgt, const double* __restrict__ win,
-                                          const double* __restrict__ src_glb, int lane, unsigned lt_mask,
-                                          unsigned le_mask, int c0, int n_c, double inv_h, const unsigned* xm,
-                                          unsigned& cpk, double* acc0, double* acc1, double& tot0, double& tot1) {
+__device__ __forceinline__ void lqw_steps(const LqwLoop& L, int c0, int n_c, int& cnt, double* acc, double& tot) {
   const int n_full = n_c >> 5;
-  int q = lane;
-  for (int st = 0; st < n_full; ++st, q += 32) {
-    const uint32_t mk = s_mark[q];
-    const unsigned heads = __ballot_sync(0xffffffffu, mk != 0u);
-    const int hl = 31 - __clz(heads & le_mask);
-    const int m = (int)__shfl_sync(0xffffffffu, mk, hl) - 1;
-    s_mark[q] = 0;
-    const double2 rec = *(const double2*)(s_tgt + m);
-    const int idx = __double2loint(rec.y) + c0 + q;
-    const double s = rec.x - (STAGED ? win[idx] : __ldg(src_glb + idx));
-    int b;
-    double v;
-    lq_bin(s, inv_h, b, v);
-    lqw_route<true>(s_stack, lane, lt_mask, b, v, 0xffffffffu, xm, cpk, acc0, acc1, tot0, tot1);
+  int st = 0;
+  int q = L.lane;
+  for (; st + 1 < n_full; st += 2, q += 64) {
+    int ba, bb;
+    double va, vb;
+    bool la, lb;
+    unsigned lva, lvb, ca, cb;
+    lqw_form<true, STAGED>(L, q, c0 + q, true, ba, va, la, lva, ca);
+    lqw_form<true, STAGED>(L, q + 32, c0 + q + 32, true, bb, vb, lb, lvb, cb);
+    const int na = __popc(ca), nb = __popc(cb);
+    if (__any_sync(0xffffffffu, cnt + na + nb > LQW_CAP)) {
+      if (!lqw_make_room(L, na + nb, cnt, acc, tot)) {
+        // one step at a time, then pair by pair
+        if (__any_sync(0xffffffffu, cnt + na > LQW_CAP) && !lqw_make_room(L, na, cnt, acc, tot))
+          lqw_direct(L.lane, ba, va, lva, acc, tot);
+        else {
+          lqw_push(L, ba, va, la, ca, cnt);
+          cnt += na;
+        }
+        if (__any_sync(0xffffffffu, cnt + nb > LQW_CAP) && !lqw_make_room(L, nb, cnt, acc, tot))
+          lqw_direct(L.lane, bb, vb, lvb, acc, tot);
+        else {
+          lqw_push(L, bb, vb, lb, cb, cnt);
+          cnt += nb;
+        }
+        continue;
+      }
+    }
+    lqw_push(L, ba, va, la, ca, cnt);
+    lqw_push(L, bb, vb, lb, cb, cnt + na);
+    cnt += na + nb;
   }
-  const int left = n_c - n_full * 32;
-  if (left > 0) {
-    const unsigned live = (1u << left) - 1u;
-    const bool is_live = lane < left;
-    const uint32_t mk = is_live ? (uint32_t)s_mark[q] : 0u;
-    const unsigned heads = __ballot_sync(0xffffffffu, mk != 0u);
-    const int hl = 31 - __clz(heads & le_mask);
-    const int m = (int)__shfl_sync(0xffffffffu, mk, hl) - 1;
-    if (is_live) s_mark[q] = 0;
-    const double2 rec = *(const double2*)(s_tgt + (is_live ? m : 0));
-    const int idx = is_live ? __double2loint(rec.y) + c0 + q : 0;
-    const double s = rec.x - (STAGED ? win[idx] : __ldg(src_glb + idx));
-    int b;
-    double v;
-    lq_bin(s, inv_h, b, v);
-    if (!is_live) b = 0;
-    lqw_route<false>(s_stack, lane, lt_mask, b, v, live, xm, cpk, acc0, acc1, tot0, tot1);
+  for (; st * 32 < n_c; ++st, q += 32) {
+    const int left = n_c - st * 32;
+    int ba;
+    double va;
+    bool la;
+    unsigned lva, ca;
+    if (left >= 32) lqw_form<true, STAGED>(L, q, c0 + q, true, ba, va, la, lva, ca);
+    else lqw_form<false, STAGED>(L, q, c0 + q, L.lane < left, ba, va, la, lva, ca);
+    const int na = __popc(ca);
+    if (__any_sync(0xffffffffu, cnt + na > LQW_CAP) && !lqw_make_room(L, na, cnt, acc, tot)) {
+      lqw_direct(L.lane, ba, va, lva, acc, tot);
+      continue;
+    }
+    lqw_push(L, ba, va, la, ca, cnt);
+    cnt += na;
   }
 }
 
 __global__ void __launch_bounds__(32, LQW_WARPS)
 lag_moment_warp_kernel(const DimDev* __restrict__ dims, const QStreamDev* __restrict__ streams, int n_streams,
                        double* __restrict__ partials, unsigned long long* __restrict__ counts, int64_t wu_base) {
-  __shared__ __align__(16) double s_stack[LQW_CAP * 64];
+  __shared__ __align__(16) double s_stack[LQW_CAP * 32];
   __shared__ __align__(16) double s_src[2 * (LQW_SW + 2)];
   __shared__ __align__(16) LqTarget s_tgt[LQW_TM];
   __shared__ __align__(8) uint64_t s_bar[2];
   __shared__ __align__(16) uint8_t s_mark[LQW_PC];
 
   const int lane = threadIdx.x;
-  const unsigned lt_mask = (1u << lane) - 1u;
-  const unsigned le_mask = lt_mask | (1u << lane);
   const int64_t wu = (int64_t)blockIdx.x + wu_base;
   const QStreamDev S = streams[find_stream(streams, n_streams, wu)];
   const int chunk = (int)(wu - S.wu_first);
@@ -975,156 +1020,165 @@ lag_moment_warp_kernel(const DimDev* __restrict__ dims, const QStreamDev* __rest
   if (*Dt.bad) return;   // unsorted upload (aslsd_set_events): the verdict reaches the host later
   const int64_t m_begin = S.m_lo + (int64_t)chunk * S.tpw;
   const int64_t m_end = min(S.m_hi, m_begin + S.tpw);
-  const bool same = S.same != 0;
-  const double inv_h = S.inv_h;
   const int64_t n_src_padded = ((Ds.n + 1) & ~(int64_t)1) + 2;   // set_events pads every type (ctx.cu)
+  const int n_pass = S.J >> 5;
 
-  unsigned xm[5];
+  LqwLoop L;
+  L.lane = lane;
+  L.lt_mask = (1u << lane) - 1u;
+  L.le_mask = L.lt_mask | (1u << lane);
 #pragma unroll
-  for (int i = 0; i < 5; ++i) xm[i] = ((lane >> i) & 1) ? 0u : 0xffffffffu;
+  for (int i = 0; i < 5; ++i) L.xm[i] = ((lane >> i) & 1) ? 0u : 0xffffffffu;
+  L.inv_h = S.inv_h;
+  L.mark_a = smem_u32(s_mark);
+  L.tgt_a = smem_u32(s_tgt) - 16u;
+  L.col_a = smem_u32(s_stack) + 8u * (uint32_t)lane;
 
   // stacks to zero (entries above a stack's height are read with weight zero: they must be finite),
   // no marks (every step clears the ones it read)
-  for (int x = lane; x < LQW_CAP * 64; x += 32) s_stack[x] = 0.;
+  for (int x = lane; x < LQW_CAP * 32; x += 32) s_stack[x] = 0.;
   for (int x = lane; x < LQW_PC / 4; x += 32) ((uint32_t*)s_mark)[x] = 0u;
-  int64_t a0 = 0;
   if (lane == 0) {
     mbar_init(&s_bar[0], 1);
     mbar_init(&s_bar[1], 1);
     fence_proxy_async();
-    // window of the first tile: starts at the first source its first target can reach
-    if (m_begin < m_end) {
-      a0 = dim_lower_bound(Ds, Dt.t[m_begin] - S.s_max) & ~(int64_t)1;
-      const int64_t n_stage = min((int64_t)LQW_SW, n_src_padded - a0);
-      mbar_expect_tx(&s_bar[0], (uint32_t)(n_stage * sizeof(double)));
-      tma_load_1d(s_src, Ds.t + a0, (uint32_t)(n_stage * sizeof(double)), &s_bar[0]);
-    }
   }
-  a0 = __shfl_sync(0xffffffffu, a0, 0);
   __syncwarp();
   uint32_t parity = 0u;   // bit b: phase of window buffer b
   unsigned long long n_pairs = 0;
-  double t_mine = (m_begin + lane < m_end) ? Dt.t[m_begin + lane] : 0.;
-
-  double acc0[LQ_ND], acc1[LQ_ND];   // [0] unused: the counts are kept as tot0 / tot1 (exact)
-#pragma unroll
-  for (int d = 0; d < LQ_ND; ++d) acc0[d] = acc1[d] = 0.;
-  double tot0 = 0., tot1 = 0.;
-  unsigned cpk = 0u;   // heights of the stacks of bins lane (low half-word) and lane + 32 (high half-word)
-
-  int tile = 0;
-  for (int64_t m0 = m_begin; m0 < m_end; m0 += LQW_TM, ++tile) {
-    const int nt = (int)min((int64_t)LQW_TM, m_end - m0);
-    const int buf = tile & 1;
-    const double* win = s_src + buf * (LQW_SW + 2);
-    // ---- a. per-target source ranges ---------------------------------------------------------
-    const double t = t_mine;
-    const double t_last = __shfl_sync(0xffffffffu, t, nt - 1);
-    if (m0 + LQW_TM + lane < m_end) t_mine = Dt.t[m0 + LQW_TM + lane];   // next tile's target, in flight
-    mbar_wait(&s_bar[buf], (parity >> buf) & 1u);
-    parity ^= 1u << buf;
-    const int n_win = (int)min((int64_t)LQW_SW, n_src_padded - a0);
-    // the window serves the tile if it reaches the end of the stream or the last target (same type:
-    // by index, ties in time included; other types: by time, the searches are lower bounds)
-    const bool staged = (a0 + n_win >= Ds.n) ||
-                        (same ? (a0 + n_win >= m0 + nt - 1) : (win[n_win - 1] >= t_last));
-    const int n_valid = (int)min((int64_t)n_win, Ds.n - a0);   // entries that are events, not padding
-    int n_search = n_valid;
-    if (staged) {
-      if (n_valid > 63 && win[62] >= t_last) n_search = 63;
-      else if (n_valid > 127 && win[126] >= t_last) n_search = 127;
-    }
-    const int p2 = n_search > 0 ? (1 << (31 - __clz(n_search))) : 0;
-    int64_t lo_abs = 0;
-    int32_t cnt = 0;
-    if (lane < nt) {
-      int64_t hi;
-      if (staged) {
-        const double x_lo = t - S.s_max;
-        int r_hi, r_lo;
-        if (n_search == 63) {
-          if (same) { r_hi = 0; r_lo = smem_lower_bound_full<6>(win, x_lo); }
-          else smem_lower_bound_full2<6>(win, t, x_lo, r_hi, r_lo);
-        } else if (n_search == 127) {
-          if (same) { r_hi = 0; r_lo = smem_lower_bound_full<7>(win, x_lo); }
-          else smem_lower_bound_full2<7>(win, t, x_lo, r_hi, r_lo);
-        } else {
-          r_hi = same ? 0 : smem_lower_bound(win, n_search, p2, t);
-          r_lo = smem_lower_bound(win, n_search, p2, x_lo);
-        }
-        hi = same ? (m0 + lane) : a0 + r_hi;
-        lo_abs = min(a0 + (int64_t)r_lo, hi);
-      } else {
-        hi = same ? (m0 + lane) : dim_lower_bound(Ds, t);
-        lo_abs = min(dim_lower_bound(Ds, t - S.s_max), hi);
-      }
-      cnt = (int32_t)(hi - lo_abs);
-    }
-    int32_t incl = cnt;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const int32_t v = __shfl_up_sync(0xffffffffu, incl, o);
-      if (lane >= o) incl += v;
-    }
-    const int32_t pre = incl - cnt;
-    const int32_t total = __shfl_sync(0xffffffffu, incl, 31);
-    // next tile's window into the other buffer: it starts at the window start of this tile's last
-    // target (the readers of that buffer, the previous tile's searches and steps, are done)
-    const int64_t a1 = __shfl_sync(0xffffffffu, lo_abs, nt - 1) & ~(int64_t)1;
-    fence_proxy_async();
-    __syncwarp();
-    if (lane == 0 && m0 + LQW_TM < m_end) {
-      const int64_t n_stage = min((int64_t)LQW_SW, n_src_padded - a1);
-      mbar_expect_tx(&s_bar[buf ^ 1], (uint32_t)(n_stage * sizeof(double)));
-      tma_load_1d(s_src + (buf ^ 1) * (LQW_SW + 2), Ds.t + a1, (uint32_t)(n_stage * sizeof(double)), &s_bar[buf ^ 1]);
-    }
-    n_pairs += (unsigned long long)cnt;
-    {
-      LqTarget rec;
-      rec.t = t;
-      rec.base = (int32_t)(lo_abs - a0) - pre;
-      rec.pad = 0;
-      s_tgt[lane] = rec;
-    }
-    const double* src_glb = Ds.t + a0;   // fallback tiles
-
-    // ---- b. steps of 32 pairs, LQW_PC pair slots at a time --------------------------------------
-    for (int32_t c0 = 0; c0 < total; c0 += LQW_PC) {
-      const int32_t n_c = min((int32_t)LQW_PC, total - c0);
-      {
-        const int32_t qa = max(pre - c0, 0), qb = min(pre + cnt - c0, n_c);
-        if (qa < qb) {
-          const uint8_t mark = (uint8_t)(lane + 1);
-          s_mark[qa] = mark;
-          for (int32_t q = (qa & ~31) + 32; q < qb; q += 32) s_mark[q] = mark;
-        }
-      }
-      __syncwarp();
-      if (staged)
-        lqw_steps<true>(s_stack, s_mark, s_tgt, win, src_glb, lane, lt_mask, le_mask, c0, n_c, inv_h, xm, cpk, acc0, acc1,
-                        tot0, tot1);
-      else
-        lqw_steps<false>(s_stack, s_mark, s_tgt, win, src_glb, lane, lt_mask, le_mask, c0, n_c, inv_h, xm, cpk, acc0,
-                         acc1, tot0, tot1);
-      __syncwarp();
-    }
-    a0 = a1;
-  }
-  // what is left on the stacks
-  {
-    int cnt0 = (int)(cpk & 0xffffu), cnt1 = (int)(cpk >> 16);
-    const int top = __reduce_max_sync(0xffffffffu, max(cnt0, cnt1));
-    lqw_drain(s_stack, lane, top, cnt0, cnt1, acc0, acc1, tot0, tot1);
-  }
-  // ---- one partial moment table per work unit ---------------------------------------------------
   double* out = partials + S.part_first + (int64_t)chunk * S.J * LQ_ND;
-  out[lane * LQ_ND] = tot0;
+  int tile = 0;
+
+  for (int pass = 0; pass < n_pass; ++pass) {
+    // lags of this pass: bins [32 pass, 32 pass + 32).  Sources of a target at t: t - s_hi <= t_n < t - s_lo
+    // (first pass: t_n < t, by index for a stream paired with itself; last pass: down to t - s_max)
+    const bool by_index = S.same != 0 && pass == 0;
+    const double s_lo = pass == 0 ? 0. : (32. * pass - 1e-3) * S.h;
+    const double s_hi = pass == n_pass - 1 ? S.s_max : (32. * (pass + 1) + 1e-3) * S.h;
+    L.pass = pass;
+    L.push_a = smem_u32(s_stack) - 256u * (uint32_t)pass;
+    double acc[LQ_ND];   // [0] unused: the count is kept as tot (exact)
 #pragma unroll
-  for (int d = 1; d < LQ_ND; ++d) out[lane * LQ_ND + d] = acc0[d];
-  if (S.J > 32) {
-    out[(lane + 32) * LQ_ND] = tot1;
+    for (int d = 0; d < LQ_ND; ++d) acc[d] = 0.;
+    double tot = 0.;
+    int cnt = 0;   // height of this lane's stack
+
+    int64_t a0 = 0;
+    if (lane == 0 && m_begin < m_end) {
+      // window of the first tile: starts at the first source its first target can reach
+      a0 = dim_lower_bound(Ds, Dt.t[m_begin] - s_hi) & ~(int64_t)1;
+      const int64_t n_stage = min((int64_t)LQW_SW, n_src_padded - a0);
+      mbar_expect_tx(&s_bar[tile & 1], (uint32_t)(n_stage * sizeof(double)));
+      tma_load_1d(s_src + (tile & 1) * (LQW_SW + 2), Ds.t + a0, (uint32_t)(n_stage * sizeof(double)), &s_bar[tile & 1]);
+    }
+    a0 = __shfl_sync(0xffffffffu, a0, 0);
+    double t_mine = (m_begin + lane < m_end) ? Dt.t[m_begin + lane] : 0.;
+
+    for (int64_t m0 = m_begin; m0 < m_end; m0 += LQW_TM, ++tile) {
+      const int nt = (int)min((int64_t)LQW_TM, m_end - m0);
+      const int buf = tile & 1;
+      const double* win = s_src + buf * (LQW_SW + 2);
+      // ---- a. per-target source ranges ---------------------------------------------------------
+      const double t = t_mine;
+      const double x_last = __shfl_sync(0xffffffffu, t, nt - 1) - s_lo;   // no threshold of the tile lies above
+      if (m0 + LQW_TM + lane < m_end) t_mine = Dt.t[m0 + LQW_TM + lane];   // next tile's target, in flight
+      mbar_wait(&s_bar[buf], (parity >> buf) & 1u);
+      parity ^= 1u << buf;
+      const int n_win = (int)min((int64_t)LQW_SW, n_src_padded - a0);
+      // the window serves the tile if it reaches the end of the stream or the last target's sources
+      // (by index: ties in time included; by time: the searches are lower bounds)
+      const bool staged = (a0 + n_win >= Ds.n) ||
+                          (by_index ? (a0 + n_win >= m0 + nt - 1) : (win[n_win - 1] >= x_last));
+      const int n_valid = (int)min((int64_t)n_win, Ds.n - a0);   // entries that are events, not padding
+      int n_search = n_valid;
+      if (staged) {
+        if (n_valid > 63 && win[62] >= x_last) n_search = 63;
+        else if (n_valid > 127 && win[126] >= x_last) n_search = 127;
+      }
+      const int p2 = n_search > 0 ? (1 << (31 - __clz(n_search))) : 0;
+      int64_t lo_abs = 0;
+      int32_t npair = 0;
+      if (lane < nt) {
+        const double x_hi = t - s_lo, x_lo = t - s_hi;
+        int64_t hi;
+        if (staged) {
+          int r_hi, r_lo;
+          if (n_search == 63) {
+            if (by_index) { r_hi = 0; r_lo = smem_lower_bound_full<6>(win, x_lo); }
+            else smem_lower_bound_full2<6>(win, x_hi, x_lo, r_hi, r_lo);
+          } else if (n_search == 127) {
+            if (by_index) { r_hi = 0; r_lo = smem_lower_bound_full<7>(win, x_lo); }
+            else smem_lower_bound_full2<7>(win, x_hi, x_lo, r_hi, r_lo);
+          } else {
+            r_hi = by_index ? 0 : smem_lower_bound(win, n_search, p2, x_hi);
+            r_lo = smem_lower_bound(win, n_search, p2, x_lo);
+          }
+          hi = by_index ? (m0 + lane) : a0 + r_hi;
+          lo_abs = min(a0 + (int64_t)r_lo, hi);
+        } else {
+          hi = by_index ? (m0 + lane) : dim_lower_bound(Ds, x_hi);
+          lo_abs = min(dim_lower_bound(Ds, x_lo), hi);
+        }
+        npair = (int32_t)(hi - lo_abs);
+      }
+      int32_t incl = npair;
 #pragma unroll
-    for (int d = 1; d < LQ_ND; ++d) out[(lane + 32) * LQ_ND + d] = acc1[d];
+      for (int o = 1; o < 32; o <<= 1) {
+        const int32_t v = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += v;
+      }
+      const int32_t pre = incl - npair;
+      const int32_t total = __shfl_sync(0xffffffffu, incl, 31);
+      // next tile's window into the other buffer: it starts at the window start of this tile's last
+      // target (the readers of that buffer, the previous tile's searches and steps, are done)
+      const int64_t a1 = __shfl_sync(0xffffffffu, lo_abs, nt - 1) & ~(int64_t)1;
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0 && m0 + LQW_TM < m_end) {
+        const int64_t n_stage = min((int64_t)LQW_SW, n_src_padded - a1);
+        mbar_expect_tx(&s_bar[buf ^ 1], (uint32_t)(n_stage * sizeof(double)));
+        tma_load_1d(s_src + (buf ^ 1) * (LQW_SW + 2), Ds.t + a1, (uint32_t)(n_stage * sizeof(double)), &s_bar[buf ^ 1]);
+      }
+      {
+        LqTarget rec;
+        rec.t = t;
+        rec.base = (int32_t)(lo_abs - a0) - pre;
+        rec.pad = 0;
+        s_tgt[lane] = rec;
+      }
+      L.win_a = smem_u32(win);
+      L.src_glb = Ds.t + a0;   // fallback tiles
+
+      // ---- b. steps of 32 pairs, LQW_PC pair slots at a time --------------------------------------
+      for (int32_t c0 = 0; c0 < total; c0 += LQW_PC) {
+        const int32_t n_c = min((int32_t)LQW_PC, total - c0);
+        {
+          const int32_t qa = max(pre - c0, 0), qb = min(pre + npair - c0, n_c);
+          if (qa < qb) {
+            const uint8_t mark = (uint8_t)(lane + 1);
+            s_mark[qa] = mark;
+            for (int32_t q = (qa & ~31) + 32; q < qb; q += 32) s_mark[q] = mark;
+          }
+        }
+        __syncwarp();
+        if (staged) lqw_steps<true>(L, c0, n_c, cnt, acc, tot);
+        else lqw_steps<false>(L, c0, n_c, cnt, acc, tot);
+        __syncwarp();
+      }
+      a0 = a1;
+    }
+    // what is left on the stacks
+    {
+      const int top = __reduce_max_sync(0xffffffffu, cnt);
+      __syncwarp();
+      lqw_drain(L.col_a, top, cnt, acc, tot);
+    }
+    // ---- this pass's 32 bins of the work unit's partial moment table ---------------------------
+    double* o = out + (size_t)(32 * pass + lane) * LQ_ND;
+    o[0] = tot;
+#pragma unroll
+    for (int d = 1; d < LQ_ND; ++d) o[d] = acc[d];
+    n_pairs += (unsigned long long)tot;
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) n_pairs += __shfl_xor_sync(0xffffffffu, n_pairs, o);
