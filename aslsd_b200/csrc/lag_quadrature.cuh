@@ -183,6 +183,22 @@ __device__ __forceinline__ void smem_lower_bound_full2(const double* win, double
   }
 }
 
+// N such searches at once
+template <int K, int N>
+__device__ __forceinline__ void smem_lower_bound_fullN(const double* win, const double* x, int* p) {
+#pragma unroll
+  for (int c = 0; c < N; ++c) p[c] = 0;
+#pragma unroll
+  for (int step = 1 << (K - 1); step > 0; step >>= 1) {
+    double v[N];
+#pragma unroll
+    for (int c = 0; c < N; ++c) v[c] = win[p[c] + step - 1];
+#pragma unroll
+    for (int c = 0; c < N; ++c)
+      if (v[c] < x[c]) p[c] += step;
+  }
+}
+
 // lanes of the warp whose b equals this lane's, from ballots over NB bits
 // (per bit: test, vote, select, and-not-xor)
 template <int K>
@@ -770,7 +786,7 @@ lag_moment_kernel(const DimDev* __restrict__ dims, const QStreamDev* __restrict_
 // the work unit's targets - lags in the first 32 bins, then in the last 32 - so that a pass
 // enumerates only its own pairs (the search bounds of the two overlap by a thousandth of a bin and a
 // pair is kept by the pass that its computed bin names: an exact partition).
-//   a. tile = 32 targets, one per lane: source window by a TMA bulk copy issued one tile ahead (two
+//   a. tile = 64 targets, two per lane: source window by a TMA bulk copy issued one tile ahead (two
 //      buffers, one mbarrier each), per-target ranges by unrolled shared-memory searches, exclusive
 //      scan by shuffles, one 16-byte record per target, head marks (one byte per pair slot);
 //   b. step = 32 consecutive pairs (target-major), one per lane, two steps interleaved: owner of the
@@ -789,20 +805,23 @@ lag_moment_kernel(const DimDev* __restrict__ dims, const QStreamDev* __restrict_
 //      to the owners pair by pair.
 // One partial moment table per work unit, written from the owners' registers.
 #ifndef LQW_CAP
-#define LQW_CAP 32      // stack entries per bin
+#define LQW_CAP 24      // stack entries per bin
 #endif
 #ifndef LQW_RES
-#define LQW_RES 12      // free slots of the fullest stack after a partial drain
+#define LQW_RES 10      // free slots of the fullest stack after a partial drain
 #endif
-#define LQW_SW 128      // staged source events per tile (two buffers)
 #define LQW_PC 1024     // pair slots with head marks (pairs of a tile are taken LQW_PC at a time)
 #ifndef LQW_WARPS
-#define LQW_WARPS 16    // resident warps (CTAs of one warp) per SM
+#define LQW_WARPS 20    // resident warps (CTAs of one warp) per SM
 #endif
 #ifndef LQW_DEFAULT
 #define LQW_DEFAULT 1   // 0: the 128-thread CTAs unless ASLSD_LQ_WARP=1
 #endif
-#define LQW_TM 32       // targets per tile
+#ifndef LQW_NTL
+#define LQW_NTL 2       // targets per lane and tile
+#endif
+#define LQW_TM (32 * LQW_NTL)   // targets per tile
+#define LQW_SW (LQW_NTL >= 4 ? 256 : 128)   // staged source events per tile (two buffers)
 
 // shared-memory accesses of the step loop by 32-bit address (the addresses stay in registers; the
 // compiler otherwise re-derives every array base from the CTA's shared window in each iteration)
@@ -949,19 +968,20 @@ __device__ __forceinline__ bool lqw_make_room(const LqwLoop& L, int n, int& cnt,
   return !__any_sync(0xffffffffu, cnt + n > LQW_CAP);
 }
 
-// The steps over pair slots 0 .. n_c of a chunk (pairs c0 .. c0 + n_c of the tile).
+// The steps over pair slots 0 .. n_c of a chunk (pairs c0 .. c0 + n_c of the tile), two at a time.
 template <bool STAGED>
 __device__ __forceinline__ void lqw_steps(const LqwLoop& L, int c0, int n_c, int& cnt, double* acc, double& tot) {
-  const int n_full = n_c >> 5;
+  const int n_steps = (n_c + 31) >> 5;
   int st = 0;
   int q = L.lane;
-  for (; st + 1 < n_full; st += 2, q += 64) {
+  for (; st + 1 < n_steps; st += 2, q += 64) {
     int ba, bb;
     double va, vb;
     bool la, lb;
     unsigned lva, lvb, ca, cb;
     lqw_form<true, STAGED>(L, q, c0 + q, true, ba, va, la, lva, ca);
-    lqw_form<true, STAGED>(L, q + 32, c0 + q + 32, true, bb, vb, lb, lvb, cb);
+    if ((st + 2) * 32 <= n_c) lqw_form<true, STAGED>(L, q + 32, c0 + q + 32, true, bb, vb, lb, lvb, cb);
+    else lqw_form<false, STAGED>(L, q + 32, c0 + q + 32, q + 32 < n_c, bb, vb, lb, lvb, cb);   // the chunk's last step
     const int na = __popc(ca), nb = __popc(cb);
     if (__any_sync(0xffffffffu, cnt + na + nb > LQW_CAP)) {
       if (!lqw_make_room(L, na + nb, cnt, acc, tot)) {
@@ -985,21 +1005,20 @@ __device__ __forceinline__ void lqw_steps(const LqwLoop& L, int c0, int n_c, int
     lqw_push(L, bb, vb, lb, cb, cnt + na);
     cnt += na + nb;
   }
-  for (; st * 32 < n_c; ++st, q += 32) {
-    const int left = n_c - st * 32;
+  if (st < n_steps) {
     int ba;
     double va;
     bool la;
     unsigned lva, ca;
-    if (left >= 32) lqw_form<true, STAGED>(L, q, c0 + q, true, ba, va, la, lva, ca);
-    else lqw_form<false, STAGED>(L, q, c0 + q, L.lane < left, ba, va, la, lva, ca);
+    if ((st + 1) * 32 <= n_c) lqw_form<true, STAGED>(L, q, c0 + q, true, ba, va, la, lva, ca);
+    else lqw_form<false, STAGED>(L, q, c0 + q, q < n_c, ba, va, la, lva, ca);
     const int na = __popc(ca);
     if (__any_sync(0xffffffffu, cnt + na > LQW_CAP) && !lqw_make_room(L, na, cnt, acc, tot)) {
       lqw_direct(L.lane, ba, va, lva, acc, tot);
-      continue;
+    } else {
+      lqw_push(L, ba, va, la, ca, cnt);
+      cnt += na;
     }
-    lqw_push(L, ba, va, la, ca, cnt);
-    cnt += na;
   }
 }
 
@@ -1072,16 +1091,32 @@ lag_moment_warp_kernel(const DimDev* __restrict__ dims, const QStreamDev* __rest
       tma_load_1d(s_src + (tile & 1) * (LQW_SW + 2), Ds.t + a0, (uint32_t)(n_stage * sizeof(double)), &s_bar[tile & 1]);
     }
     a0 = __shfl_sync(0xffffffffu, a0, 0);
-    double t_mine = (m_begin + lane < m_end) ? Dt.t[m_begin + lane] : 0.;
+    // this lane's targets of a tile: LQW_NTL consecutive ones
+    double t_mine[LQW_NTL];
+#pragma unroll
+    for (int k = 0; k < LQW_NTL; ++k)
+      t_mine[k] = (m_begin + LQW_NTL * lane + k < m_end) ? Dt.t[m_begin + LQW_NTL * lane + k] : 0.;
 
     for (int64_t m0 = m_begin; m0 < m_end; m0 += LQW_TM, ++tile) {
       const int nt = (int)min((int64_t)LQW_TM, m_end - m0);
       const int buf = tile & 1;
       const double* win = s_src + buf * (LQW_SW + 2);
       // ---- a. per-target source ranges ---------------------------------------------------------
-      const double t = t_mine;
-      const double x_last = __shfl_sync(0xffffffffu, t, nt - 1) - s_lo;   // no threshold of the tile lies above
-      if (m0 + LQW_TM + lane < m_end) t_mine = Dt.t[m0 + LQW_TM + lane];   // next tile's target, in flight
+      double t[LQW_NTL];
+#pragma unroll
+      for (int k = 0; k < LQW_NTL; ++k) t[k] = t_mine[k];
+      // the tile's last target: lane (nt - 1) / LQW_NTL, its target (nt - 1) % LQW_NTL
+      const int l_last = (nt - 1) / LQW_NTL, k_last = (nt - 1) % LQW_NTL;
+      double t_last = __shfl_sync(0xffffffffu, t[0], l_last);
+#pragma unroll
+      for (int k = 1; k < LQW_NTL; ++k) {
+        const double tk = __shfl_sync(0xffffffffu, t[k], l_last);
+        if (k_last == k) t_last = tk;
+      }
+      const double x_last = t_last - s_lo;   // no threshold of the tile lies above
+#pragma unroll
+      for (int k = 0; k < LQW_NTL; ++k)   // next tile's targets, in flight
+        if (m0 + LQW_TM + LQW_NTL * lane + k < m_end) t_mine[k] = Dt.t[m0 + LQW_TM + LQW_NTL * lane + k];
       mbar_wait(&s_bar[buf], (parity >> buf) & 1u);
       parity ^= 1u << buf;
       const int n_win = (int)min((int64_t)LQW_SW, n_src_padded - a0);
@@ -1094,44 +1129,76 @@ lag_moment_warp_kernel(const DimDev* __restrict__ dims, const QStreamDev* __rest
       if (staged) {
         if (n_valid > 63 && win[62] >= x_last) n_search = 63;
         else if (n_valid > 127 && win[126] >= x_last) n_search = 127;
+        else if (LQW_SW > 128 && n_valid > 255 && win[254] >= x_last) n_search = 255;
       }
       const int p2 = n_search > 0 ? (1 << (31 - __clz(n_search))) : 0;
-      int64_t lo_abs = 0;
-      int32_t npair = 0;
-      if (lane < nt) {
-        const double x_hi = t - s_lo, x_lo = t - s_hi;
-        int64_t hi;
-        if (staged) {
-          int r_hi, r_lo;
-          if (n_search == 63) {
-            if (by_index) { r_hi = 0; r_lo = smem_lower_bound_full<6>(win, x_lo); }
-            else smem_lower_bound_full2<6>(win, x_hi, x_lo, r_hi, r_lo);
-          } else if (n_search == 127) {
-            if (by_index) { r_hi = 0; r_lo = smem_lower_bound_full<7>(win, x_lo); }
-            else smem_lower_bound_full2<7>(win, x_hi, x_lo, r_hi, r_lo);
-          } else {
-            r_hi = by_index ? 0 : smem_lower_bound(win, n_search, p2, x_hi);
-            r_lo = smem_lower_bound(win, n_search, p2, x_lo);
-          }
-          hi = by_index ? (m0 + lane) : a0 + r_hi;
-          lo_abs = min(a0 + (int64_t)r_lo, hi);
-        } else {
-          hi = by_index ? (m0 + lane) : dim_lower_bound(Ds, x_hi);
-          lo_abs = min(dim_lower_bound(Ds, x_lo), hi);
+      int64_t lo_abs[LQW_NTL];
+      int32_t npair[LQW_NTL];
+      {
+        // thresholds: [0, NTL) lower ends, [NTL, 2 NTL) upper ends (not needed by index)
+        double x[2 * LQW_NTL];
+        int r[2 * LQW_NTL];
+#pragma unroll
+        for (int k = 0; k < LQW_NTL; ++k) {
+          x[k] = t[k] - s_hi;
+          x[LQW_NTL + k] = t[k] - s_lo;
+          r[k] = r[LQW_NTL + k] = 0;
         }
-        npair = (int32_t)(hi - lo_abs);
+        if (staged) {
+          if (n_search == 63) {
+            if (by_index) smem_lower_bound_fullN<6, LQW_NTL>(win, x, r);
+            else smem_lower_bound_fullN<6, 2 * LQW_NTL>(win, x, r);
+          } else if (n_search == 127) {
+            if (by_index) smem_lower_bound_fullN<7, LQW_NTL>(win, x, r);
+            else smem_lower_bound_fullN<7, 2 * LQW_NTL>(win, x, r);
+          } else if (LQW_SW > 128 && n_search == 255) {
+            if (by_index) smem_lower_bound_fullN<8, LQW_NTL>(win, x, r);
+            else smem_lower_bound_fullN<8, 2 * LQW_NTL>(win, x, r);
+          } else {
+#pragma unroll
+            for (int k = 0; k < LQW_NTL; ++k) {
+              r[k] = smem_lower_bound(win, n_search, p2, x[k]);
+              if (!by_index) r[LQW_NTL + k] = smem_lower_bound(win, n_search, p2, x[LQW_NTL + k]);
+            }
+          }
+        }
+#pragma unroll
+        for (int k = 0; k < LQW_NTL; ++k) {
+          const int j = LQW_NTL * lane + k;   // target of the tile
+          int64_t hi, lo;
+          if (staged) {
+            hi = by_index ? (m0 + j) : a0 + r[LQW_NTL + k];
+            lo = a0 + (int64_t)r[k];
+          } else if (j < nt) {
+            hi = by_index ? (m0 + j) : dim_lower_bound(Ds, x[LQW_NTL + k]);
+            lo = dim_lower_bound(Ds, x[k]);
+          } else {
+            hi = lo = a0;
+          }
+          lo = min(lo, hi);
+          lo_abs[k] = lo;
+          npair[k] = j < nt ? (int32_t)(hi - lo) : 0;
+        }
       }
-      int32_t incl = npair;
+      int32_t mine = 0;
+#pragma unroll
+      for (int k = 0; k < LQW_NTL; ++k) mine += npair[k];
+      int32_t incl = mine;
 #pragma unroll
       for (int o = 1; o < 32; o <<= 1) {
         const int32_t v = __shfl_up_sync(0xffffffffu, incl, o);
         if (lane >= o) incl += v;
       }
-      const int32_t pre = incl - npair;
       const int32_t total = __shfl_sync(0xffffffffu, incl, 31);
       // next tile's window into the other buffer: it starts at the window start of this tile's last
       // target (the readers of that buffer, the previous tile's searches and steps, are done)
-      const int64_t a1 = __shfl_sync(0xffffffffu, lo_abs, nt - 1) & ~(int64_t)1;
+      int64_t a1 = __shfl_sync(0xffffffffu, lo_abs[0], l_last);
+#pragma unroll
+      for (int k = 1; k < LQW_NTL; ++k) {
+        const int64_t ak = __shfl_sync(0xffffffffu, lo_abs[k], l_last);
+        if (k_last == k) a1 = ak;
+      }
+      a1 &= ~(int64_t)1;
       fence_proxy_async();
       __syncwarp();
       if (lane == 0 && m0 + LQW_TM < m_end) {
@@ -1139,12 +1206,19 @@ lag_moment_warp_kernel(const DimDev* __restrict__ dims, const QStreamDev* __rest
         mbar_expect_tx(&s_bar[buf ^ 1], (uint32_t)(n_stage * sizeof(double)));
         tma_load_1d(s_src + (buf ^ 1) * (LQW_SW + 2), Ds.t + a1, (uint32_t)(n_stage * sizeof(double)), &s_bar[buf ^ 1]);
       }
+      int32_t pre[LQW_NTL];
       {
-        LqTarget rec;
-        rec.t = t;
-        rec.base = (int32_t)(lo_abs - a0) - pre;
-        rec.pad = 0;
-        s_tgt[lane] = rec;
+        int32_t run = incl - mine;
+#pragma unroll
+        for (int k = 0; k < LQW_NTL; ++k) {
+          pre[k] = run;
+          run += npair[k];
+          LqTarget rec;
+          rec.t = t[k];
+          rec.base = (int32_t)(lo_abs[k] - a0) - pre[k];
+          rec.pad = 0;
+          s_tgt[LQW_NTL * lane + k] = rec;
+        }
       }
       L.win_a = smem_u32(win);
       L.src_glb = Ds.t + a0;   // fallback tiles
@@ -1152,10 +1226,11 @@ lag_moment_warp_kernel(const DimDev* __restrict__ dims, const QStreamDev* __rest
       // ---- b. steps of 32 pairs, LQW_PC pair slots at a time --------------------------------------
       for (int32_t c0 = 0; c0 < total; c0 += LQW_PC) {
         const int32_t n_c = min((int32_t)LQW_PC, total - c0);
-        {
-          const int32_t qa = max(pre - c0, 0), qb = min(pre + npair - c0, n_c);
+#pragma unroll
+        for (int k = 0; k < LQW_NTL; ++k) {
+          const int32_t qa = max(pre[k] - c0, 0), qb = min(pre[k] + npair[k] - c0, n_c);
           if (qa < qb) {
-            const uint8_t mark = (uint8_t)(lane + 1);
+            const uint8_t mark = (uint8_t)(LQW_NTL * lane + k + 1);
             s_mark[qa] = mark;
             for (int32_t q = (qa & ~31) + 32; q < qb; q += 32) s_mark[q] = mark;
           }
