@@ -286,6 +286,45 @@ def test_lag_quadrature_unbalanced_rates_and_many_bins(engine):
         engine.use_lag_quadrature(True)
 
 
+@pytest.mark.parametrize('sigma,delta', [(1.0, 0.0), (0.4, 4.0)])
+def test_warp_shape_dense_sources_bursts_and_ties(engine, sigma, delta):
+    """Gaussian kernels (streams of at most 64 bins: the one-warp-per-work-unit moment kernel,
+    one and two passes) on a sparse stream against a dense one with bursts of exact ties: source
+    windows that do not fit the staged buffer (global-memory tiles), tiles of tens of thousands of
+    pairs (several mark chunks), steps with more pairs of one bin than a stack holds (pair-by-pair
+    path), partial drains - against the per-item kernels."""
+    rng = np.random.default_rng(909)
+    from aslsd_b200.engine import unpack_terms
+    T_f = 300.
+    sparse = np.sort(rng.uniform(0, T_f, size=700))
+    dense = rng.uniform(0, T_f, size=30000)
+    bursts = np.repeat(rng.uniform(5., T_f - 5., size=12), 40)          # 12 bursts of 40 simultaneous events
+    dense = np.sort(np.concatenate([dense, bursts, sparse[:30]]))      # and ties across the two types
+    times = [sparse, dense]
+    basis = [{'type': 'gauss'}]
+    model = {'d': 2, 'kernels': [[basis for _ in range(2)] for _ in range(2)]}
+    engine.set_events(times, T_f)
+    engine.set_model(model)
+    try:
+        for k in range(2):
+            x = np.array([0.6, 0.2, sigma, delta, 0.1, 1.3 * sigma, 0.5 * delta])
+            engine.use_lag_quadrature(True)
+            a = engine.exact_sums_packed(k, x)
+            wa = engine.last_work_counts()
+            a2 = engine.exact_sums_packed(k, x)
+            engine.use_lag_quadrature(False)
+            b = engine.exact_sums_packed(k, x)
+            assert wa['moment_pairs'] > 10 ** 6 and wa['streams'] >= 2
+            assert wa['bins'] <= 64 * wa['streams']      # every stream in the warp shape
+            assert np.array_equal(a, a2)        # fixed summation order: bit-identical repeats
+            fa, dfa = unpack_terms(engine.desc, k, a)
+            fb, dfb = unpack_terms(engine.desc, k, b)
+            ref = {'k/%s' % label: val for label, val in iter_sum_entries(fb, dfb)}
+            assert_sums_close(fa, dfa, ref, 'k', rtol=1e-11, atol=1e-10)
+    finally:
+        engine.use_lag_quadrature(True)
+
+
 def test_long_memory_kernel_pairs_with_every_earlier_event(engine):
     """An exponential kernel whose reach exceeds the observation window: every target pairs
     with every earlier event (2 x 10^8 pairs per stream, thousands of sort chunks per tile, the
