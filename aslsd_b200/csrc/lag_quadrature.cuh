@@ -962,7 +962,8 @@ __device__ __forceinline__ bool lqw_make_room(const LqwLoop& L, int n, int& cnt,
   int need = cnt + n - LQW_CAP;
   need = __reduce_max_sync(0xffffffffu, need);
   const int top = __reduce_max_sync(0xffffffffu, cnt);
-  const int n_pop = min(top, max(top - (LQW_CAP - LQW_RES), need));
+  // (an even number: the drain pops two entries per iteration)
+  const int n_pop = min(top, (max(top - (LQW_CAP - LQW_RES), need) + 1) & ~1);
   __syncwarp();   // the pushes of the other lanes onto this lane's stack
   lqw_drain(L.col_a, n_pop, cnt, acc, tot);
   return !__any_sync(0xffffffffu, cnt + n > LQW_CAP);

@@ -142,7 +142,7 @@ def load_measured_peaks():
 
 
 def load_traffic():
-    """dram__bytes_read.sum + dram__bytes_write.sum of one lag_moment_kernel launch on this
+    """dram__bytes_read.sum + dram__bytes_write.sum of one lag_moment_warp_kernel launch on this
     workload, from the committed ``ncu --set full`` capture (profiles/); None when there is none."""
     try:
         with open(TRAFFIC_FILE) as f:
@@ -575,7 +575,7 @@ def run_b200(args):
         peaks, peak_kind = load_measured_peaks()
         ms_per_step = total_ms / args.steps
         value = pair_terms / (ms_per_step * 1e-3)
-        # roofline of the dominant kernel (lag_moment_kernel) on this rank: its algorithmic
+        # roofline of the dominant kernel (lag_moment_warp_kernel) on this rank: its algorithmic
         # flops (event pairs it binned x FLOPS_MOMENT_PAIR) over its own CUDA-event time
         flops = executed_flops(work)
         m_flops = work.get('moment_pairs', 0) * FLOPS_MOMENT_PAIR
@@ -633,17 +633,17 @@ def run_b200(args):
                          'frac': (achieved / fp64_peak) if achieved else None,
                          'traffic': traffic,
                          'traffic_source': traffic_src,
-                         'traffic_note': 'dram__bytes_read.sum + dram__bytes_write.sum of one lag_moment_kernel '
+                         'traffic_note': 'dram__bytes_read.sum + dram__bytes_write.sum of one lag_moment_warp_kernel '
                                          'launch, read from %s (written by scripts/ncu_traffic.py from the committed '
                                          'ncu --set full capture of this workload); algorithmic bytes %.0f MB (each '
                                          'event time read once per stream it belongs to) - the 80 MB of events stay '
                                          'in L2' % (os.path.relpath(TRAFFIC_FILE, ROOT), n_src_tgt / 1e6),
-                         'kernel': 'lag_moment_kernel',
+                         'kernel': 'lag_moment_warp_kernel',
                          'kernel_ms': m_ms_sum, 'kernel_share_of_step': (m_ms_sum / k_ms_sum) if k_ms_sum else None,
                          'algorithmic_flops_per_launch': m_flops,
-                         'note': 'the kernel is bound by instruction issue (counting sort of the lags by bin: '
-                                 'integer / shared-memory work), not by the fp64 pipe or HBM (ncu summaries under '
-                                 'profiles/). frac is its fp64 rate over the measured DFMA peak',
+                         'note': 'the kernel is bound by instruction issue (routing every event pair to the lane that '
+                                 'owns its bin: ballots, shuffles, shared-memory stacks), not by the fp64 pipe or HBM '
+                                 '(ncu summaries under profiles/). frac is its fp64 rate over the measured DFMA peak',
                          'all_kernels_tflops': flops / (k_ms_sum * 1e-3) * 1e-12 if k_ms_sum > 0 else None,
                          'reference_equivalent_tflops': pair_terms * FLOPS_REF_DIRECT / (ms_per_step * 1e-3) * 1e-12,
                          'reference_equivalent_shared_tflops': pair_terms * FLOPS_REF_SHARED / (ms_per_step * 1e-3) * 1e-12,

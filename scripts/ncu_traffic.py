@@ -20,13 +20,13 @@ ix = {h: i for i, h in enumerate(hdr)}
 scale = {'byte': 1., 'Kbyte': 1e3, 'Mbyte': 1e6, 'Gbyte': 1e9}
 best = None
 for vals in rows[2:]:
-    if 'lag_moment_kernel' not in vals[ix['Kernel Name']]:
+    if 'lag_moment_' not in vals[ix['Kernel Name']]:
         continue
     dur = float(vals[ix['gpu__time_duration.sum']].replace(',', ''))
     if best is None or dur > best[0]:
         best = (dur, vals)
 if best is None:
-    sys.exit('no lag_moment_kernel launch in ' + rep)
+    sys.exit('no lag_moment_* launch in ' + rep)
 vals = best[1]
 
 

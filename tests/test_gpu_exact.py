@@ -305,6 +305,7 @@ def test_warp_shape_dense_sources_bursts_and_ties(engine, sigma, delta):
     model = {'d': 2, 'kernels': [[basis for _ in range(2)] for _ in range(2)]}
     engine.set_events(times, T_f)
     engine.set_model(model)
+    engine.use_weight_cache(False)      # the two sub-problems share (beta, delta): every call bins its pairs
     try:
         for k in range(2):
             x = np.array([0.6, 0.2, sigma, delta, 0.1, 1.3 * sigma, 0.5 * delta])
@@ -323,6 +324,7 @@ def test_warp_shape_dense_sources_bursts_and_ties(engine, sigma, delta):
             assert_sums_close(fa, dfa, ref, 'k', rtol=1e-11, atol=1e-10)
     finally:
         engine.use_lag_quadrature(True)
+        engine.use_weight_cache(True)
 
 
 def test_long_memory_kernel_pairs_with_every_earlier_event(engine):
