@@ -805,14 +805,16 @@ lag_moment_kernel(const DimDev* __restrict__ dims, const QStreamDev* __restrict_
 //      to the owners pair by pair.
 // One partial moment table per work unit, written from the owners' registers.
 #ifndef LQW_CAP
-#define LQW_CAP 24      // stack entries per bin
+#define LQW_CAP 20      // stack entries per bin
 #endif
 #ifndef LQW_RES
-#define LQW_RES 10      // free slots of the fullest stack after a partial drain
+#define LQW_RES 8       // free slots of the fullest stack after a partial drain
 #endif
+#ifndef LQW_PC
 #define LQW_PC 1024     // pair slots with head marks (pairs of a tile are taken LQW_PC at a time)
+#endif
 #ifndef LQW_WARPS
-#define LQW_WARPS 20    // resident warps (CTAs of one warp) per SM
+#define LQW_WARPS 22    // resident warps (CTAs of one warp) per SM
 #endif
 #ifndef LQW_DEFAULT
 #define LQW_DEFAULT 1   // 0: the 128-thread CTAs unless ASLSD_LQ_WARP=1
@@ -821,7 +823,9 @@ lag_moment_kernel(const DimDev* __restrict__ dims, const QStreamDev* __restrict_
 #define LQW_NTL 2       // targets per lane and tile
 #endif
 #define LQW_TM (32 * LQW_NTL)   // targets per tile
+#ifndef LQW_SW
 #define LQW_SW (LQW_NTL >= 4 ? 256 : 128)   // staged source events per tile (two buffers)
+#endif
 
 // shared-memory accesses of the step loop by 32-bit address (the addresses stay in registers; the
 // compiler otherwise re-derives every array base from the CTA's shared window in each iteration)
