@@ -805,16 +805,16 @@ lag_moment_kernel(const DimDev* __restrict__ dims, const QStreamDev* __restrict_
 //      to the owners pair by pair.
 // One partial moment table per work unit, written from the owners' registers.
 #ifndef LQW_CAP
-#define LQW_CAP 20      // stack entries per bin
+#define LQW_CAP 24      // stack entries per bin
 #endif
 #ifndef LQW_RES
-#define LQW_RES 8       // free slots of the fullest stack after a partial drain
+#define LQW_RES 10      // free slots of the fullest stack after a partial drain
 #endif
 #ifndef LQW_PC
 #define LQW_PC 1024     // pair slots with head marks (pairs of a tile are taken LQW_PC at a time)
 #endif
 #ifndef LQW_WARPS
-#define LQW_WARPS 22    // resident warps (CTAs of one warp) per SM
+#define LQW_WARPS 20    // resident warps (CTAs of one warp) per SM
 #endif
 #ifndef LQW_DEFAULT
 #define LQW_DEFAULT 1   // 0: the 128-thread CTAs unless ASLSD_LQ_WARP=1
@@ -826,6 +826,10 @@ lag_moment_kernel(const DimDev* __restrict__ dims, const QStreamDev* __restrict_
 #ifndef LQW_SW
 #define LQW_SW (LQW_NTL >= 4 ? 256 : 128)   // staged source events per tile (two buffers)
 #endif
+
+// a value the compiler may not re-derive inside the loops (it otherwise rebuilds lane masks and
+// shared-memory addresses from the lane index and the CTA's shared window in every step)
+__device__ __forceinline__ void lqw_keep(unsigned& x) { asm volatile("" : "+r"(x)); }
 
 // shared-memory accesses of the step loop by 32-bit address (the addresses stay in registers; the
 // compiler otherwise re-derives every array base from the CTA's shared window in each iteration)
@@ -973,49 +977,64 @@ __device__ __forceinline__ bool lqw_make_room(const LqwLoop& L, int n, int& cnt,
   return !__any_sync(0xffffffffu, cnt + n > LQW_CAP);
 }
 
+// Two formed steps onto the stacks (the second one above the first).
+__device__ __forceinline__ void lqw_push_two(const LqwLoop& L, int ba, double va, bool la, unsigned lva, unsigned ca,
+                                             int bb, double vb, bool lb, unsigned lvb, unsigned cb, int& cnt,
+                                             double* acc, double& tot) {
+  const int na = __popc(ca), nb = __popc(cb);
+  if (__any_sync(0xffffffffu, cnt + na + nb > LQW_CAP)) {
+    if (!lqw_make_room(L, na + nb, cnt, acc, tot)) {
+      // one step at a time, then pair by pair
+      if (__any_sync(0xffffffffu, cnt + na > LQW_CAP) && !lqw_make_room(L, na, cnt, acc, tot))
+        lqw_direct(L.lane, ba, va, lva, acc, tot);
+      else {
+        lqw_push(L, ba, va, la, ca, cnt);
+        cnt += na;
+      }
+      if (__any_sync(0xffffffffu, cnt + nb > LQW_CAP) && !lqw_make_room(L, nb, cnt, acc, tot))
+        lqw_direct(L.lane, bb, vb, lvb, acc, tot);
+      else {
+        lqw_push(L, bb, vb, lb, cb, cnt);
+        cnt += nb;
+      }
+      return;
+    }
+  }
+  lqw_push(L, ba, va, la, ca, cnt);
+  lqw_push(L, bb, vb, lb, cb, cnt + na);
+  cnt += na + nb;
+}
+
 // The steps over pair slots 0 .. n_c of a chunk (pairs c0 .. c0 + n_c of the tile), two at a time.
 template <bool STAGED>
 __device__ __forceinline__ void lqw_steps(const LqwLoop& L, int c0, int n_c, int& cnt, double* acc, double& tot) {
-  const int n_steps = (n_c + 31) >> 5;
-  int st = 0;
   int q = L.lane;
-  for (; st + 1 < n_steps; st += 2, q += 64) {
+  int left = n_c;
+  // full steps, two interleaved
+  for (; left >= 64; left -= 64, q += 64) {
     int ba, bb;
     double va, vb;
     bool la, lb;
     unsigned lva, lvb, ca, cb;
     lqw_form<true, STAGED>(L, q, c0 + q, true, ba, va, la, lva, ca);
-    if ((st + 2) * 32 <= n_c) lqw_form<true, STAGED>(L, q + 32, c0 + q + 32, true, bb, vb, lb, lvb, cb);
-    else lqw_form<false, STAGED>(L, q + 32, c0 + q + 32, q + 32 < n_c, bb, vb, lb, lvb, cb);   // the chunk's last step
-    const int na = __popc(ca), nb = __popc(cb);
-    if (__any_sync(0xffffffffu, cnt + na + nb > LQW_CAP)) {
-      if (!lqw_make_room(L, na + nb, cnt, acc, tot)) {
-        // one step at a time, then pair by pair
-        if (__any_sync(0xffffffffu, cnt + na > LQW_CAP) && !lqw_make_room(L, na, cnt, acc, tot))
-          lqw_direct(L.lane, ba, va, lva, acc, tot);
-        else {
-          lqw_push(L, ba, va, la, ca, cnt);
-          cnt += na;
-        }
-        if (__any_sync(0xffffffffu, cnt + nb > LQW_CAP) && !lqw_make_room(L, nb, cnt, acc, tot))
-          lqw_direct(L.lane, bb, vb, lvb, acc, tot);
-        else {
-          lqw_push(L, bb, vb, lb, cb, cnt);
-          cnt += nb;
-        }
-        continue;
-      }
-    }
-    lqw_push(L, ba, va, la, ca, cnt);
-    lqw_push(L, bb, vb, lb, cb, cnt + na);
-    cnt += na + nb;
+    lqw_form<true, STAGED>(L, q + 32, c0 + q + 32, true, bb, vb, lb, lvb, cb);
+    lqw_push_two(L, ba, va, la, lva, ca, bb, vb, lb, lvb, cb, cnt, acc, tot);
   }
-  if (st < n_steps) {
+  if (left > 32) {
+    // a full step and the chunk's last, partial one
+    int ba, bb;
+    double va, vb;
+    bool la, lb;
+    unsigned lva, lvb, ca, cb;
+    lqw_form<true, STAGED>(L, q, c0 + q, true, ba, va, la, lva, ca);
+    lqw_form<false, STAGED>(L, q + 32, c0 + q + 32, q + 32 < n_c, bb, vb, lb, lvb, cb);
+    lqw_push_two(L, ba, va, la, lva, ca, bb, vb, lb, lvb, cb, cnt, acc, tot);
+  } else if (left > 0) {
     int ba;
     double va;
     bool la;
     unsigned lva, ca;
-    if ((st + 1) * 32 <= n_c) lqw_form<true, STAGED>(L, q, c0 + q, true, ba, va, la, lva, ca);
+    if (left == 32) lqw_form<true, STAGED>(L, q, c0 + q, true, ba, va, la, lva, ca);
     else lqw_form<false, STAGED>(L, q, c0 + q, q < n_c, ba, va, la, lva, ca);
     const int na = __popc(ca);
     if (__any_sync(0xffffffffu, cnt + na > LQW_CAP) && !lqw_make_room(L, na, cnt, acc, tot)) {
@@ -1057,6 +1076,13 @@ lag_moment_warp_kernel(const DimDev* __restrict__ dims, const QStreamDev* __rest
   L.mark_a = smem_u32(s_mark);
   L.tgt_a = smem_u32(s_tgt) - 16u;
   L.col_a = smem_u32(s_stack) + 8u * (uint32_t)lane;
+  lqw_keep(L.lt_mask);
+  lqw_keep(L.le_mask);
+#pragma unroll
+  for (int i = 0; i < 5; ++i) lqw_keep(L.xm[i]);
+  lqw_keep(L.mark_a);
+  lqw_keep(L.tgt_a);
+  lqw_keep(L.col_a);
 
   // stacks to zero (entries above a stack's height are read with weight zero: they must be finite),
   // no marks (every step clears the ones it read)
@@ -1081,6 +1107,7 @@ lag_moment_warp_kernel(const DimDev* __restrict__ dims, const QStreamDev* __rest
     const double s_hi = pass == n_pass - 1 ? S.s_max : (32. * (pass + 1) + 1e-3) * S.h;
     L.pass = pass;
     L.push_a = smem_u32(s_stack) - 256u * (uint32_t)pass;
+    lqw_keep(L.push_a);
     double acc[LQ_ND];   // [0] unused: the count is kept as tot (exact)
 #pragma unroll
     for (int d = 0; d < LQ_ND; ++d) acc[d] = 0.;
@@ -1226,6 +1253,7 @@ lag_moment_warp_kernel(const DimDev* __restrict__ dims, const QStreamDev* __rest
         }
       }
       L.win_a = smem_u32(win);
+      lqw_keep(L.win_a);
       L.src_glb = Ds.t + a0;   // fallback tiles
 
       // ---- b. steps of 32 pairs, LQW_PC pair slots at a time --------------------------------------
@@ -1237,7 +1265,13 @@ lag_moment_warp_kernel(const DimDev* __restrict__ dims, const QStreamDev* __rest
           if (qa < qb) {
             const uint8_t mark = (uint8_t)(LQW_NTL * lane + k + 1);
             s_mark[qa] = mark;
-            for (int32_t q = (qa & ~31) + 32; q < qb; q += 32) s_mark[q] = mark;
+            // ... and every 32nd slot after it (one at most unless a target has more than 32 pairs)
+            const int32_t q1 = (qa & ~31) + 32;
+            if (q1 < qb) {
+              s_mark[q1] = mark;
+              if (q1 + 32 < qb)
+                for (int32_t q = q1 + 32; q < qb; q += 32) s_mark[q] = mark;
+            }
           }
         }
         __syncwarp();
