@@ -878,8 +878,13 @@ __device__ __forceinline__ void lqw_drain(uint32_t col_a, int n_pop, int& cnt, d
   cnt -= pop;
 }
 
-// the pairs of a step straight into the accumulators of their owners (steps that no stack can take)
-__device__ __forceinline__ void lqw_direct(int lane, int b, double v, unsigned live, double* acc, double& tot) {
+// the pairs of a step straight into the accumulators of their owners (steps that no stack can take).
+// Rare: a real function (the step loop stays small), the accumulators travel through local memory.
+__device__ __noinline__ void lqw_direct_call(int lane, int b, double v, unsigned live, double* buf) {
+  double acc[LQ_ND];
+#pragma unroll
+  for (int d = 1; d < LQ_ND; ++d) acc[d] = buf[d];
+  double tot = buf[0];
   for (int k = 0; k < 32; ++k) {
     const int bk = __shfl_sync(0xffffffffu, b, k);
     const double vk = __shfl_sync(0xffffffffu, v, k);
@@ -897,6 +902,19 @@ __device__ __forceinline__ void lqw_direct(int lane, int b, double v, unsigned l
       acc[d] = fma(w, tn, acc[d]);
     }
   }
+#pragma unroll
+  for (int d = 1; d < LQ_ND; ++d) buf[d] = acc[d];
+  buf[0] = tot;
+}
+__device__ __forceinline__ void lqw_direct(int lane, int b, double v, unsigned live, double* acc, double& tot) {
+  double buf[LQ_ND];
+  buf[0] = tot;
+#pragma unroll
+  for (int d = 1; d < LQ_ND; ++d) buf[d] = acc[d];
+  lqw_direct_call(lane, b, v, live, buf);
+  tot = buf[0];
+#pragma unroll
+  for (int d = 1; d < LQ_ND; ++d) acc[d] = buf[d];
 }
 
 // ballot of bit K of b (one LOP3 with a predicate result + one VOTE)
@@ -1020,30 +1038,46 @@ __device__ __forceinline__ void lqw_steps(const LqwLoop& L, int c0, int n_c, int
     lqw_form<true, STAGED>(L, q + 32, c0 + q + 32, true, bb, vb, lb, lvb, cb);
     lqw_push_two(L, ba, va, la, lva, ca, bb, vb, lb, lvb, cb, cnt, acc, tot);
   }
-  if (left > 32) {
-    // a full step and the chunk's last, partial one
-    int ba, bb;
-    double va, vb;
-    bool la, lb;
-    unsigned lva, lvb, ca, cb;
-    lqw_form<true, STAGED>(L, q, c0 + q, true, ba, va, la, lva, ca);
-    lqw_form<false, STAGED>(L, q + 32, c0 + q + 32, q + 32 < n_c, bb, vb, lb, lvb, cb);
+  if (left > 0) {
+    // the chunk's last one or two steps (one copy of the code for every remainder)
+    int ba, bb = 0;
+    double va, vb = 0.;
+    bool la, lb = false;
+    unsigned lva, lvb = 0u, ca, cb = 0u;
+    lqw_form<false, STAGED>(L, q, c0 + q, q < n_c, ba, va, la, lva, ca);
+    if (left > 32) lqw_form<false, STAGED>(L, q + 32, c0 + q + 32, q + 32 < n_c, bb, vb, lb, lvb, cb);
     lqw_push_two(L, ba, va, la, lva, ca, bb, vb, lb, lvb, cb, cnt, acc, tot);
-  } else if (left > 0) {
-    int ba;
-    double va;
-    bool la;
-    unsigned lva, ca;
-    if (left == 32) lqw_form<true, STAGED>(L, q, c0 + q, true, ba, va, la, lva, ca);
-    else lqw_form<false, STAGED>(L, q, c0 + q, q < n_c, ba, va, la, lva, ca);
-    const int na = __popc(ca);
-    if (__any_sync(0xffffffffu, cnt + na > LQW_CAP) && !lqw_make_room(L, na, cnt, acc, tot)) {
-      lqw_direct(L.lane, ba, va, lva, acc, tot);
-    } else {
-      lqw_push(L, ba, va, la, ca, cnt);
-      cnt += na;
-    }
   }
+}
+
+// Tiles whose source window does not fit the staged buffer read their sources from global memory.
+// Rare (a source stream far denser than the target stream): a real function, so that the kernel holds
+// one copy of the step loop's code; loop state and accumulators travel through local memory.
+__device__ __noinline__ void lqw_steps_global_call(const LqwLoop* Lp, int c0, int n_c, int* cnt_p, double* buf) {
+  const LqwLoop L = *Lp;
+  double acc[LQ_ND];
+#pragma unroll
+  for (int d = 1; d < LQ_ND; ++d) acc[d] = buf[d];
+  double tot = buf[0];
+  int cnt = *cnt_p;
+  lqw_steps<false>(L, c0, n_c, cnt, acc, tot);
+#pragma unroll
+  for (int d = 1; d < LQ_ND; ++d) buf[d] = acc[d];
+  buf[0] = tot;
+  *cnt_p = cnt;
+}
+__device__ __forceinline__ void lqw_steps_global(const LqwLoop& L, int c0, int n_c, int& cnt, double* acc, double& tot) {
+  LqwLoop Lc = L;
+  double buf[LQ_ND];
+  int c = cnt;
+  buf[0] = tot;
+#pragma unroll
+  for (int d = 1; d < LQ_ND; ++d) buf[d] = acc[d];
+  lqw_steps_global_call(&Lc, c0, n_c, &c, buf);
+  cnt = c;
+  tot = buf[0];
+#pragma unroll
+  for (int d = 1; d < LQ_ND; ++d) acc[d] = buf[d];
 }
 
 __global__ void __launch_bounds__(32, LQW_WARPS)
@@ -1276,7 +1310,7 @@ lag_moment_warp_kernel(const DimDev* __restrict__ dims, const QStreamDev* __rest
         }
         __syncwarp();
         if (staged) lqw_steps<true>(L, c0, n_c, cnt, acc, tot);
-        else lqw_steps<false>(L, c0, n_c, cnt, acc, tot);
+        else lqw_steps_global(L, c0, n_c, cnt, acc, tot);
         __syncwarp();
       }
       a0 = a1;
