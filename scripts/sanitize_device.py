@@ -7,8 +7,8 @@ so the script carries its own check for races: every call is repeated and must r
 the kernels have no atomics and a fixed summation order, so any difference is a race.)
 
 Every kernel family of the library runs once on inputs small enough for the sanitizer's
-slow-down: the lag-moment kernel in both CTA shapes (a 10-type model with 64 bins per stream and a
-2-type exponential model with more bins), the per-pair kernels (targets near T_f), the sampled
+slow-down: the lag-moment kernels (a 10-type model with 64 bins per stream: the warp-shaped kernel;
+exponential / mixed models with more bins: the sorting kernel in its 512-thread shape), the per-pair kernels (targets near T_f), the sampled
 sums, the point sums, the index maps and the simulator.  The sums are compared with the oracle, so
 a race that changes a result fails the run as well."""
 import os
@@ -28,7 +28,7 @@ def main():
     import oracle_engine
     from cases import CASES, case_x
     eng = aslsd_b200.Engine(0)
-    # ---- C5's model on a short stream: moment kernel (128 x 4 shape), quadrature rows, boundary targets
+    # ---- C5's model on a short stream: moment kernel (warp-shaped: streams of 64 bins), quadrature rows, boundary targets
     model, times, T_f, xs = simulate.config_c5(T_f=1500.)
     eng.set_events(times, T_f)
     eng.set_model(model)
