@@ -168,10 +168,35 @@ def mtlh_inputs(name):
     return times, marks, T_f
 
 
+def _bench_weights(n, coeff):
+    """get_random_mixture_weights of the reference (utilities/useful_statistics.py:23-32), seed 1234:
+    the mixture weights of bench.py's model (aslsd_b200/simulate.py)."""
+    rng = np.random.default_rng(1234)
+    w = rng.uniform(size=n)
+    w /= np.sum(w)
+    w *= coeff
+    w[-1] = coeff - np.sum(w[:-1])
+    return w
+
+
+# The benchmark's own model (config C5: ten event types, every kernel a sum of ten Gaussians with beta
+# and delta fixed, every adjacency row summing to 0.5).  Kept out of CASES: the device tests that run
+# over CASES are sized for one to three event types; this one is replayed on the CPU
+# (tests/test_stratified_golden.py) and has its own device test (tests/test_gpu_exact.py, c5_short).
+BENCH_CASES = {
+    'c5model': (square(10, lambda: sbf_gauss_kernel(10)), [.5] * 10,
+                [[list(_bench_weights(10, 0.05)) for _ in range(10)] for _ in range(10)], 250.),
+}
+
+
+def lookup_case(name):
+    return CASES[name] if name in CASES else BENCH_CASES[name]
+
+
 def case_x(name):
     """Evaluation points: truth * (1 + 0.1 U(-1, 1)), default_rng(12)
     (SURVEY section 8d)."""
-    model, mu, kp, T_f = CASES[name]
+    model, mu, kp, T_f = lookup_case(name)
     rng = np.random.default_rng(12)
     xs = []
     for k in range(model['d']):

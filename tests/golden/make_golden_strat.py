@@ -20,7 +20,7 @@ for _p in (HERE, os.path.dirname(HERE), os.path.dirname(os.path.dirname(HERE))):
     if _p not in sys.path:
         sys.path.insert(0, _p)
 
-from cases import CASES, case_x  # noqa: E402
+from cases import CASES, case_x, lookup_case  # noqa: E402,F401
 
 STRAT_CASES = {
     # name: (model case, T_f, n_iter, grad_alloc, stratification keywords)
@@ -57,6 +57,12 @@ STRAT_CASES = {
                           dict(n_exact_single=100, n_samples_adaptive_single=200,
                                nonadaptive_sample_size_single=300, n_samples_adaptive_double=600,
                                nonadaptive_sample_size_double=270)),
+    # the benchmark's own model (ten event types, SBF-Gaussian(10)): every term family at d = 10, where most
+    # cross terms upsilon_i_j have k != i, j; replayed on the CPU only (tests/test_stratified_golden.py)
+    'strat_c5model': ('c5model', 250., 3, False,
+                      dict(n_exact_single=40, n_samples_adaptive_single=80,
+                           nonadaptive_sample_size_single=120, n_samples_adaptive_double=200,
+                           nonadaptive_sample_size_double=90)),
     'strat_exp2d_long': ('exp2d', 400., 100, False,
                          dict(n_exact_single=100, n_samples_adaptive_single=200,
                               nonadaptive_sample_size_single=300, n_samples_adaptive_double=600,
@@ -89,7 +95,7 @@ def make_strat(ref, only=None):
     for name, (case, T_f, n_iter, grad_alloc, kw) in STRAT_CASES.items():
         if only and name not in only:
             continue
-        model, mu, kp, _ = CASES[case]
+        model, mu, kp, _ = lookup_case(case)
         d = model['d']
         import ref_shim
         mhp = ref_shim.build_reference_model(ref, model)

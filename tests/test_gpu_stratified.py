@@ -41,6 +41,16 @@ def test_replay_reference_trace_strict(engine, name):
     replay_strat_golden(name, engine, mode='strict', free_running=(name == 'strat_exp1d'))
 
 
+def test_replay_reference_trace_of_the_benchmark_model(engine):
+    """The benchmark's own model (config C5: ten event types, SBF-Gaussian(10)): the reference's
+    trace of three ADAM iterations of every sub-problem (tests/golden/strat_c5model.npz, 121 terms
+    per call), nothing forced but the evaluation points - per-term sums, gradients, every adaptive
+    allocation and the final generator state are the reference's (profiles/r2_zj_replay_c5model_device.log:
+    8e-16, one second; the CPU suite replays the same trace over the oracle double)."""
+    worst = replay_strat_golden('strat_c5model', engine, mode='strict')
+    assert worst <= RTOL
+
+
 def _random_batch(rng, times, k, d, n_strata, n_per, kinds=None):
     """Random (m, n) samples for every term kind, far lags included."""
     terms, offsets, ms, ns = [], [0], [], []

@@ -27,6 +27,19 @@ def test_replay_long_reference_trace(name):
     replay_strat_golden(name, OracleEngine(), mode='strict')
 
 
+def test_replay_reference_trace_of_the_benchmark_model():
+    """The benchmark's own model (config C5: ten event types, SBF-Gaussian(10)) under the reference's
+    stratified estimator (tests/golden/make_golden_strat.py, 'strat_c5model': three ADAM iterations of
+    every sub-problem on a 2 255-event path).  The oracle double takes ~25 s per estimator call at
+    d = 10, so the default run replays the first call of sub-problem 0 - 121 terms, whose sums can
+    only match if every sample of every term was drawn in the reference's order - and the whole trace
+    (30 calls, final generator state included) with ASLSD_FULL_REPLAY=1: profiles/r2_strat_c5model_replay.log."""
+    import os
+    full = os.environ.get('ASLSD_FULL_REPLAY') == '1'
+    worst = replay_strat_golden('strat_c5model', OracleEngine(), mode='strict', first_calls=None if full else 1)
+    print('strat_c5model %s replay: worst relative difference of a per-term sum %.2e' % ('full' if full else 'first-call', worst))
+
+
 def test_stratification_defaults_match_survey_geometry():
     """Default geometry at N = 10^6 (measured on the reference)."""
     import aslsd_b200
