@@ -32,6 +32,22 @@ def test_exact_sums_match_reference_golden(engine, name):
         assert worst <= RTOL
 
 
+def test_benchmark_model_matches_reference_golden(engine):
+    """The benchmark's own model (config C5: ten event types, SBF-Gaussian(10)) against the LIVE
+    REFERENCE's sums of sub-problems 0, 4 and 9 on a short path (tests/golden/make_golden_c5model.py;
+    every target of that path lies near T_f, so the per-item kernels evaluate it - the lag quadrature
+    of the same model is checked against the oracle in test_c5_model_matches_oracle_every_k)."""
+    from aslsd_b200 import simulate
+    g = load_golden('exact_c5model')
+    times, T_f = golden_times(g)
+    engine.set_events(times, T_f)
+    engine.set_model(simulate.sbf_gauss_model(10, 10))
+    for k in (int(v) for v in g['ks']):
+        sum_f, sum_diff_f = engine.exact_sums(k, g['k%d/x' % k])
+        worst = assert_sums_close(sum_f, sum_diff_f, g, 'k%d' % k, rtol=RTOL)
+        assert worst <= RTOL
+
+
 @pytest.mark.parametrize('name', ['exp2d', 'sbf2d3', 'gauss2d'])
 def test_function_only_flag(engine, name):
     model = CASES[name][0]
